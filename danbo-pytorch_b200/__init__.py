@@ -1,0 +1,13 @@
+"""danbo-pytorch_b200 — B200-native (sm_100a) implementation of DANBO's per-sample body-field hot path.
+
+The directory name carries a hyphen, so import it through the alias module at the repo root:
+
+    import danbo_b200                       # == importlib.import_module("danbo-pytorch_b200")
+
+Host side: PyTorch for device memory, streams and torch.distributed.  Compute: hand-written CUDA kernels in
+csrc/, reached only through the C ABI declared in include/danbo_b200.h (ctypes, raw pointers + sizes).
+There is no CPU fallback: calling any kernel entry without the built library raises.
+"""
+from . import skeleton, synthetic, params  # noqa: F401
+
+__all__ = ["skeleton", "synthetic", "params"]

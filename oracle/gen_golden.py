@@ -1,0 +1,313 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (authoring container only).
+
+    python oracle/gen_golden.py            # needs /root/reference; writes tests/golden/
+
+Every fixture holds the synthetic inputs, the seed of the deterministic weights
+(danbo_b200.synthetic.synth_state_dict, numpy RandomState -> reproducible anywhere) and the reference's own
+tensors at each stage boundary of SURVEY §8(a), captured by wrapping the reference's functions in place.
+The reference is never copied; the GPU box only sees these vectors.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import danbo_b200  # noqa: E402
+from danbo_b200 import synthetic as syn, params  # noqa: E402
+import ref_harness as rh  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+STAGE_RAYS = 16          # rays for which the big per-(sample,bone) tensors are kept
+
+
+class Tap:
+    """Wraps callables on the reference objects and records what flows through them."""
+
+    def __init__(self):
+        self.rec = {}
+        self._undo = []
+
+    def add(self, key, val):
+        self.rec.setdefault(key, []).append(val.detach().clone() if torch.is_tensor(val) else val)
+
+    def wrap(self, obj, name, fn):
+        import types
+        orig = getattr(obj, name)
+        if isinstance(orig, torch.nn.Module):            # child module: observe through a forward hook
+            h = orig.register_forward_hook(lambda m, a, out: fn(lambda *x, **y: out))
+            self._undo.append(("hook", h, None, None))
+            return
+        is_module_global = isinstance(obj, types.ModuleType)
+        setattr(obj, name, lambda *a, **k: fn(orig, *a, **k))
+        self._undo.append(("global" if is_module_global else "inst", obj, name, orig))
+
+    def undo(self):
+        for kind, obj, name, orig in reversed(self._undo):
+            if kind == "hook":
+                obj.remove()
+            elif kind == "global":
+                setattr(obj, name, orig)
+            else:
+                obj.__dict__.pop(name, None)             # un-shadow the bound method
+        self._undo = []
+
+
+def tap_reference(caster, tap, rc):
+    net = caster.network
+
+    def cyl(orig, *a, **k):
+        n, f = orig(*a, **k)
+        tap.add("near_cyl", n), tap.add("far_cyl", f)
+        return n, f
+    tap.wrap(rc, "get_near_far_in_cylinder", cyl)
+
+    def nf(orig, *a, **k):
+        n, f = orig(*a, **k)
+        tap.add("near", n), tap.add("far", f)
+        return n, f
+    tap.wrap(caster, "get_near_far", nf)
+
+    def boxes(orig, *a, **k):
+        pv, vv, seg = orig(*a, **k)
+        tap.add("p_valid", pv), tap.add("v_valid", vv)
+        return pv, vv, seg
+    tap.wrap(rc, "get_ray_box_intersections", boxes)
+
+    def spts(orig, *a, **k):
+        pts, z = orig(*a, **k)
+        tap.add("z", z)
+        return pts, z
+    tap.wrap(caster, "sample_pts", spts)
+
+    def spts_is(orig, *a, **k):
+        pts, z_all, zs, order = orig(*a, **k)
+        tap.add("z_all", z_all), tap.add("z_samples", zs), tap.add("sorted_idxs", order)
+        return pts, z_all, zs, order
+    tap.wrap(caster, "sample_pts_is", spts_is)
+
+    def emb(orig, *a, **k):
+        enc = orig(*a, **k)
+        tap.add("pts_t", enc["pts_t"][:STAGE_RAYS])
+        return enc
+    tap.wrap(net.pts_embedder, "encode_pts", emb)
+
+    def gfwd(orig, *a, **k):
+        v = orig(*a, **k)
+        tap.add("vol", v)
+        return v
+    tap.wrap(net, "forward_graph", gfwd)
+
+    def gpe(orig, *a, **k):
+        w = orig(*a, **k)
+        tap.add("graph_w", w[0])
+        return w
+    tap.wrap(net, "graph_pe_fn", gpe)
+
+    def samp(orig, *a, **k):
+        h, inv = orig(*a, **k)
+        tap.add("h", h[:STAGE_RAYS]), tap.add("invalid", inv)
+        return h, inv
+    tap.wrap(net, "extract_graph_feat", samp)
+
+    def enc_pts(orig, *a, **k):
+        d, enc = orig(*a, **k)
+        S = enc["confd"].shape[1]
+        tap.add("density_inputs", d[:STAGE_RAYS * S]), tap.add("confd", enc["confd"]), tap.add("agg_p", enc["agg_p"])
+        return d, enc
+    tap.wrap(net, "encode_pts", enc_pts)
+
+    def enc_views(orig, *a, **k):
+        v, enc = orig(*a, **k)
+        S = a[0]["pts"].shape[1] if a else k["inputs"]["pts"].shape[1]
+        tap.add("view_inputs", v[::S])
+        return v, enc
+    tap.wrap(net, "encode_views", enc_views)
+
+    def r2o(orig, raw, z, rays_d, *a, **k):
+        out = orig(raw, z, rays_d, *a, **k)
+        tap.add("raw", raw), tap.add("weights", out["weights"]), tap.add("alpha", out["alpha"])
+        return out
+    tap.wrap(net, "raw2outputs", r2o)
+
+    def spdf(orig, *a, **k):
+        return orig(*a, **k)
+    tap.wrap(rc, "sample_pdf", spdf)
+
+
+class RandTape:
+    """Records torch.rand / torch.randn draws in call order (SURVEY §7 hard part 4)."""
+
+    def __enter__(self):
+        self.tape = []
+        self._rand, self._randn = torch.rand, torch.randn
+
+        def rand(*a, **k):
+            t = self._rand(*a, **k)
+            self.tape.append(("rand", t.clone()))
+            return t
+
+        def randn(*a, **k):
+            t = self._randn(*a, **k)
+            self.tape.append(("randn", t.clone()))
+            return t
+        torch.rand, torch.randn = rand, randn
+        return self
+
+    def __exit__(self, *exc):
+        torch.rand, torch.randn = self._rand, self._randn
+
+
+def npify(d):
+    out = {}
+    for k, v in d.items():
+        if torch.is_tensor(v):
+            v = v.detach().cpu().numpy()
+        out[k] = v
+    return out
+
+
+def subsample_rays(batch, n, seed=0):
+    tot = batch["ray_batch"].shape[0]
+    pick = torch.as_tensor(np.sort(np.random.RandomState(seed).choice(tot, n, replace=False)))
+    out = {}
+    for k, v in batch.items():
+        out[k] = v[pick].contiguous() if torch.is_tensor(v) and v.shape[0] == tot else v
+    return out
+
+
+def run_render_case(name, config, extra, pose_seed, H, n_rays, weight_seed=0, full_image=False):
+    rc, _ = rh._imports()
+    args = rh.parse_args(config, extra)
+    rest = syn.rest_pose()
+    caster, kw = rh.build(args, rest)
+    caster.eval()
+    sd = syn.synth_state_dict(params.danbo_param_shapes(), weight_seed)
+    rh.load_weights(caster, sd)
+    pose = syn.make_pose(pose_seed)
+    b = subsample_rays(syn.render_batch(pose, H, H, full_image=full_image), n_rays, seed=pose_seed)
+    tap = Tap()
+    tap_reference(caster, tap, rc)
+    kwargs = {k: v for k, v in kw.items() if k not in ("ray_caster", "N_samples", "use_viewdirs")}
+    with torch.no_grad():
+        ret = caster(b["ray_batch"], N_samples=args.N_samples, kp_batch=b["kp_batch"], skts=b["skts"],
+                     cyls=b["cyls"], bones=b["bones"], cams=b["cams"], N_uniques=1, **kwargs)
+    tap.undo()
+    fx = {"config": config, "extra": " ".join(extra), "pose_seed": pose_seed, "weight_seed": weight_seed, "H": H,
+          "N_samples": args.N_samples, "N_importance": args.N_importance,
+          "use_volume_near_far": int(bool(args.use_volume_near_far)),
+          "ray_batch": b["ray_batch"], "cams": b["cams"], "pose_bones": pose["bones"], "pose_kps": pose["kps"],
+          "pose_skts": pose["skts"], "pose_cyl": pose["cyl"]}
+    for k, v in ret.items():
+        fx["out." + k] = v
+    for k, lst in tap.rec.items():
+        for i, v in enumerate(lst):
+            fx[f"st.{k}.{i}"] = v
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **npify(fx))
+    print(name, "->", path, f"{os.path.getsize(path) / 1e6:.2f} MB", {k: len(v) for k, v in tap.rec.items()})
+
+
+def run_train_case(name, config, extra, n_poses, rays_per_pose, weight_seed=0, batch_seed=0):
+    rc, _ = rh._imports()
+    import core.trainer as trainer_mod
+    args = rh.parse_args(config, extra)
+    rest = syn.rest_pose()
+    caster, kw = rh.build(args, rest)
+    caster.train()
+    sd = syn.synth_state_dict(params.danbo_param_shapes(), weight_seed)
+    rh.load_weights(caster, sd)
+    b = syn.training_batch(n_poses, rays_per_pose, seed=batch_seed)
+    tap = Tap()
+    tap_reference(caster, tap, rc)
+    torch.manual_seed(1234)
+    with RandTape() as tape:
+        ret = caster(b["ray_batch"], N_samples=args.N_samples, kp_batch=b["kp_batch"], skts=b["skts"],
+                     cyls=b["cyls"], bones=b["bones"], cams=b["cams"], N_uniques=n_poses,
+                     perturb=args.perturb, N_importance=args.N_importance, raw_noise_std=args.raw_noise_std,
+                     ray_noise_std=0., ext_scale=args.ext_scale, lindisp=False, nerf_type=args.nerf_type,
+                     preproc_kwargs={"density_scale": args.density_scale, "density_fn": torch.nn.functional.relu})
+    tap.undo()
+    # the trainer's own loss code (core/trainer.py:348-553) on a minimal shim of its state
+    class _Wrap:                                   # stands in for nn.DataParallel(...).module
+        def __init__(self, m): self.module = m
+    tr = trainer_mod.Trainer.__new__(trainer_mod.Trainer)
+    tr.args = args
+    tr.render_kwargs_train = {"ray_caster": _Wrap(caster)}
+    batch = {"target_s": b["target_s"], "bgs": b["bgs"]}
+    loss_dict, stats = tr.compute_loss(batch, ret, kp_opts=None, popt_detach=True, global_step=0)
+    loss_dict["total_loss"].backward()
+    fx = {"config": config, "extra": " ".join(extra), "weight_seed": weight_seed, "batch_seed": batch_seed,
+          "n_poses": n_poses, "rays_per_pose": rays_per_pose,
+          "N_samples": args.N_samples, "N_importance": args.N_importance,
+          "use_volume_near_far": int(bool(args.use_volume_near_far)),
+          "raw_noise_std": args.raw_noise_std,
+          "loss.total": loss_dict["total_loss"].detach()}
+    for k, v in loss_dict.items():
+        fx["loss." + k] = v.detach()
+    kinds = [k for k, _ in tape.tape]
+    assert kinds == ["rand", "randn", "rand", "randn"], kinds
+    for nm, (_, t) in zip(("t_rand", "noise0", "u", "noise1"), tape.tape):
+        fx["rand." + nm] = t
+    for k, v in ret.items():
+        fx["out." + k] = v.detach()
+    for k, lst in tap.rec.items():
+        if k in ("h", "pts_t", "density_inputs", "agg_p"):
+            continue
+        for i, v in enumerate(lst):
+            fx[f"st.{k}.{i}"] = v
+    rng = np.random.RandomState(7)
+    for n, p in caster.network.named_parameters():
+        g = p.grad
+        if g is None:
+            continue
+        flat = g.detach().reshape(-1)
+        idx = torch.as_tensor(rng.choice(flat.numel(), min(512, flat.numel()), replace=False))
+        fx["grad_idx." + n] = idx
+        fx["grad_val." + n] = flat[idx]
+        fx["grad_norm." + n] = flat.norm()
+        fx["grad_sum." + n] = flat.double().sum()
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **npify(fx))
+    print(name, "->", path, f"{os.path.getsize(path) / 1e6:.2f} MB")
+
+
+def run_grid_case(name, config, pose_seed, res, radius=0.9, weight_seed=0):
+    rc, _ = rh._imports()
+    args = rh.parse_args(config)
+    rest = syn.rest_pose()
+    caster, kw = rh.build(args, rest)
+    caster.eval()
+    rh.load_weights(caster, syn.synth_state_dict(params.danbo_param_shapes(), weight_seed))
+    pose = syn.make_pose(pose_seed)
+    t = lambda a: torch.as_tensor(a)[None]
+    with torch.no_grad():
+        sigma = caster(kps=t(pose["kps"]), skts=t(pose["skts"]), bones=t(pose["bones"]), radius=radius, res=res,
+                       fwd_type="mesh")
+    fx = {"config": config, "pose_seed": pose_seed, "weight_seed": weight_seed, "res": res, "radius": radius,
+          "pose_bones": pose["bones"], "pose_kps": pose["kps"], "pose_skts": pose["skts"], "sigma": sigma}
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **npify(fx))
+    print(name, "->", path, f"{os.path.getsize(path) / 1e6:.2f} MB")
+
+
+def main():
+    assert rh.available(), "needs /root/reference (authoring container)"
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    run_render_case("render_fast", "h36m_zju/danbo_fast.txt", [], pose_seed=3, H=64, n_rays=256)
+    run_render_case("render_base", "h36m_zju/danbo_base.txt", [], pose_seed=5, H=64, n_rays=96)
+    run_render_case("render_fast_miss", "h36m_zju/danbo_fast.txt", [], pose_seed=7, H=48, n_rays=192, full_image=True)
+    run_train_case("train_fast", "h36m_zju/danbo_fast.txt", [], n_poses=4, rays_per_pose=48)
+    run_train_case("train_cfg3", "h36m_zju/danbo_base.txt", ["--N_samples", "64", "--N_importance", "16"],
+                   n_poses=2, rays_per_pose=32)
+    run_grid_case("grid_base", "h36m_zju/danbo_base.txt", pose_seed=3, res=11)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,84 @@
+"""Runs the UNMODIFIED reference from /root/reference (authoring container only).  TEST INFRASTRUCTURE.
+
+Used by oracle/gen_golden.py to pin the oracle and by tests/test_oracle_vs_reference.py (skipped when
+/root/reference is absent, i.e. on the GPU box).  Needs only import stubs for packages that are not installed
+(SURVEY §8c): pytorch3d's three rotation conversions (published formula), empty plotly/matplotlib, an argparse
+shim for configargparse, and empty h5py/imageio/deepdish/smplx/pytorch_msssim.  Two compatibility shims:
+F6 (np.float32 widths into a tensor under numpy 2) and F5 (A-NeRF ctor kwargs).
+"""
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+REF = os.environ.get("DANBO_REFERENCE", "/root/reference")
+STUBS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_stubs")
+
+
+def available():
+    return os.path.isdir(os.path.join(REF, "core"))
+
+
+def _imports():
+    for p in (STUBS, REF):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import core.raycasters as rc                      # noqa
+    import run_nerf                                   # noqa
+    return rc, run_nerf
+
+
+def parse_args(config="h36m_zju/danbo_fast.txt", extra=()):
+    rc, run_nerf = _imports()
+    tmp = tempfile.mkdtemp(prefix="danbo_ref_")
+    argv = ["--config", os.path.join(REF, "configs", config), "--no_reload", "--basedir", tmp,
+            "--expname", "probe"] + list(extra)
+    args = run_nerf.config_parser().parse_args(argv)
+    os.makedirs(os.path.join(tmp, "probe"), exist_ok=True)
+    return args
+
+
+def build(args, rest_pose, n_views=8, near=1.0, far=5.0, seed=0):
+    """create_raycaster under the shims -> the bare (non-DataParallel) reference ray caster."""
+    rc, _ = _imports()
+    from core.utils.skeleton_utils import SMPLSkeleton
+
+    orig_profile = rc.get_skel_profile_from_rest_pose
+
+    def profile_f64(*a, **k):                          # F6
+        prof = orig_profile(*a, **k)
+        return {k_: (v.astype(np.float64) if k_.endswith("_width") else v) for k_, v in prof.items()}
+
+    orig_create = rc.create_nerf
+
+    def create_nerf(args_, kwargs, data_attrs):        # F5
+        if args_.nerf_type == "nerf":
+            kwargs = {k_: v for k_, v in kwargs.items() if k_ not in ("mask_vol_prob", "agg_type")}
+        return orig_create(args_, kwargs, data_attrs)
+
+    rc.get_skel_profile_from_rest_pose = profile_f64
+    rc.create_nerf = create_nerf
+    try:
+        torch.manual_seed(seed)
+        data_attrs = {"skel_type": SMPLSkeleton, "near": near, "far": far, "n_views": n_views,
+                      "rest_pose": rest_pose}
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):
+            _, kw_test, _, _, _, _ = rc.create_raycaster(args, data_attrs)
+    finally:
+        rc.get_skel_profile_from_rest_pose = orig_profile
+        rc.create_nerf = orig_create
+    return kw_test["ray_caster"], kw_test
+
+
+def load_weights(caster, sd):
+    """Overwrite the reference network's parameters with `sd` (reference names); returns the full dict."""
+    net = caster.network
+    own = net.state_dict()
+    for k, v in sd.items():
+        assert k in own and tuple(own[k].shape) == tuple(v.shape), (k, v.shape)
+        own[k] = v.clone()
+    net.load_state_dict(own)
+    return {k: v.clone() for k, v in net.state_dict().items()}
