@@ -8,6 +8,10 @@ Host side: PyTorch for device memory, streams and torch.distributed.  Compute: h
 csrc/, reached only through the C ABI declared in include/danbo_b200.h (ctypes, raw pointers + sizes).
 There is no CPU fallback: calling any kernel entry without the built library raises.
 """
-from . import skeleton, synthetic, params  # noqa: F401
+from . import skeleton, synthetic, params, config  # noqa: F401
+from . import _lib, build, kernels, networks, raycaster  # noqa: F401
+from .raycaster import RayCaster, GraphCaster, create_raycaster  # noqa: F401
+from .config import make_args  # noqa: F401
 
-__all__ = ["skeleton", "synthetic", "params"]
+__all__ = ["skeleton", "synthetic", "params", "config", "kernels", "networks", "raycaster", "RayCaster",
+           "GraphCaster", "create_raycaster", "make_args", "build"]

@@ -1,0 +1,61 @@
+"""Flag handling for the path: defaults of the reference's argparse (run_nerf.py:186-572) for the subset that
+selects the DANBO hot path, and a reader for its `key = value` config files (configs/**.txt)."""
+import argparse
+
+DEFAULTS = dict(
+    expname="danbo", basedir="./logs", no_reload=False, ft_path=None, finetune=False, finetune_light=False,
+    nerf_type="danbo", gnn_backbone="FGNNcat", agg_backbone="vox_MIXGNN", agg_type="sigmoid", agg_W=32, agg_D=3,
+    node_W=128, gcn_D=4, gcn_fc_D=1, voxel_res=16, voxel_feat=5, multires_voxel=6, multires_graph=5,
+    multires_views=4, multires=1, netdepth=8, netwidth=256, netwidth_view=None, mask_root=True, mask_vol_prob=True,
+    opt_vol_scale=True, vol_cal_scale=True, attenuate_feat=True, attenuate_invalid=False, align_bones="align",
+    use_volume_near_far=False, single_net=True, opt_framecode=True, framecode_size=128, n_framecodes=None,
+    density_type="relu", density_scale=1.0, raw_noise_std=1.0, ray_noise_std=0.0, perturb=1.0, N_samples=64,
+    N_importance=0, N_rand=3072, N_sample_images=16, chunk=4096, netchunk=65536, lrate=5e-4, lrate_decay=500000,
+    lrate_decay_rate=0.1, decay_unit=1, weight_decay=None, loss_fn="L1", coarse_weight=1.0, rgb_loss_coef=1.0,
+    soft_softmax_loss_coef=0.001, vol_scale_penalty=0.001, use_background=True, use_viewdirs=True, lindisp=False,
+    ext_scale=0.001, kp_dist_type="reldist", view_type="identity", ray_tr_type="world", pts_tr_type="local",
+    bone_type="Nope", graph_input_type="rot6d", use_cutoff=False, opt_posecode=False, gnn_concat=False, no_adj=False,
+    adj_self_one=False, align_corners=False, opt_pose=False,
+)
+
+PRESETS = {
+    # configs/h36m_zju/danbo_base.txt and danbo_fast.txt, reduced to the flags of this path
+    "danbo_base": dict(N_samples=96, N_importance=48, use_volume_near_far=False),
+    "danbo_fast": dict(N_samples=32, N_importance=16, use_volume_near_far=True),
+    "danbo_cfg3": dict(N_samples=64, N_importance=16, use_volume_near_far=False),   # BASELINE config #3
+}
+
+
+def _coerce(v):
+    if v in ("True", "False"):
+        return v == "True"
+    if v == "None":
+        return None
+    for cast in (int, float):
+        try:
+            return cast(v)
+        except ValueError:
+            pass
+    if v.startswith("[") and v.endswith("]"):
+        return [x.strip() for x in v[1:-1].split(",")]
+    return v
+
+
+def read_config_file(path):
+    out = {}
+    for line in open(path):
+        line = line.split("#")[0].strip()
+        if "=" in line:
+            k, v = [s.strip() for s in line.split("=", 1)]
+            out[k] = _coerce(v)
+    return out
+
+
+def make_args(preset=None, config_file=None, **overrides):
+    d = dict(DEFAULTS)
+    if config_file is not None:
+        d.update(read_config_file(config_file))
+    if preset is not None:
+        d.update(PRESETS[preset])
+    d.update(overrides)
+    return argparse.Namespace(**d)

@@ -1,0 +1,273 @@
+// C1 alpha compositing, R1 importance resampling + sorted merge order, R2 merge of coarse and fine samples.
+// Reference: core/networks/nerf.py:281-347 (raw2outputs), core/utils/ray_utils.py:159-203,257-291
+// (sample_pdf / isample_from_lineseg), core/raycasters.py:484-514,745-761 (_merge_encodings / merge_samples).
+//
+// One warp per ray; every lane owns a contiguous run of samples, products and prefix sums are done as
+// lane-local sequential work plus one warp scan.  cumprod / cumsum accumulate in fp64 like ATen's CPU kernels
+// (acc_type<float>) and round each output to fp32.  HBM bound: 16 B raw + 4 B z in, 8 B (weight, alpha) out
+// per sample, 20 B per ray.
+#include "common.cuh"
+#include <math.h>
+
+namespace danbo {
+
+constexpr int kMaxS = 160;          // longest ray: 96 + 48 = 144 samples
+constexpr int kEPL = 5;             // elements per lane at kMaxS
+constexpr int kWarpsPerBlock = 4;
+
+struct RaySmem {
+    float z[kMaxS];
+    float w[kMaxS];
+    float cdf[kMaxS];
+    float cat[kMaxS];
+    float zs[kMaxS];
+    int order[kMaxS];
+};
+
+__device__ __forceinline__ double warp_excl_prod(double v, int lane) {
+    double inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const double u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc *= u; }
+    const double ex = __shfl_up_sync(0xffffffffu, inc, 1);
+    return lane == 0 ? 1.0 : ex;
+}
+__device__ __forceinline__ double warp_excl_sum(double v, int lane) {
+    double inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const double u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+    const double ex = __shfl_up_sync(0xffffffffu, inc, 1);
+    return lane == 0 ? 0.0 : ex;
+}
+
+// Composites one ray whose S samples are described by fetch(i) -> raw (rgb, sigma).  sm.z must hold z[0..S).
+// Writes weights / alpha rows and the per-ray maps; leaves the weights in sm.w.
+template <class Fetch>
+__device__ __forceinline__ void composite_ray(RaySmem& sm, int S, int lane, float norm_d, float inv_B,
+                                              const float* __restrict__ noise_row, Fetch fetch,
+                                              float* __restrict__ w_row, float* __restrict__ alpha_row,
+                                              float* __restrict__ rgb_out, float* __restrict__ disp_out,
+                                              float* __restrict__ acc_out) {
+    const int epl = (S + 31) / 32;
+    float al[kEPL], cr[kEPL], cg[kEPL], cb[kEPL];
+    double lp = 1.0;
+#pragma unroll
+    for (int e = 0; e < kEPL; ++e) {
+        const int i = lane * epl + e;
+        al[e] = 0.f; cr[e] = cg[e] = cb[e] = 0.f;
+        if (e < epl && i < S) {
+            const float4 raw = fetch(i);
+            float d = (i + 1 < S) ? __fsub_rn(sm.z[i + 1], sm.z[i]) : 1e10f;
+            d = __fmul_rn(d, norm_d);
+            cr[e] = (1.f / (1.f + expf(-raw.x))) * 1.002f - 0.001f;
+            cg[e] = (1.f / (1.f + expf(-raw.y))) * 1.002f - 0.001f;
+            cb[e] = (1.f / (1.f + expf(-raw.z))) * 1.002f - 0.001f;
+            float sg = __fmul_rn(raw.w, inv_B);
+            if (noise_row) sg = __fadd_rn(sg, noise_row[i]);
+            sg = fmaxf(sg, 0.f);
+            al[e] = __fsub_rn(1.f, expf(-__fmul_rn(sg, d)));
+            lp *= (double)__fadd_rn(__fsub_rn(1.f, al[e]), 1e-10f);
+        }
+    }
+    double T = warp_excl_prod(lp, lane);
+    float sr = 0.f, sg_ = 0.f, sb = 0.f, sd = 0.f, sw = 0.f;
+#pragma unroll
+    for (int e = 0; e < kEPL; ++e) {
+        const int i = lane * epl + e;
+        if (e < epl && i < S) {
+            const float w = __fmul_rn(al[e], (float)T);
+            T *= (double)__fadd_rn(__fsub_rn(1.f, al[e]), 1e-10f);
+            sm.w[i] = w;
+            if (w_row) w_row[i] = w;
+            if (alpha_row) alpha_row[i] = al[e];
+            sr = fmaf(w, cr[e], sr); sg_ = fmaf(w, cg[e], sg_); sb = fmaf(w, cb[e], sb);
+            sd = fmaf(w, sm.z[i], sd); sw += w;
+        }
+    }
+    sr = warp_sum(sr); sg_ = warp_sum(sg_); sb = warp_sum(sb); sd = warp_sum(sd); sw = warp_sum(sw);
+    if (lane == 0) {
+        rgb_out[0] = sr; rgb_out[1] = sg_; rgb_out[2] = sb;
+        float disp = 1.f / fmaxf(1e-10f, sd / (sw + 1e-10f));
+        if (fabsf(sw) <= 1e-8f) disp = 0.f;                         // torch.isclose(sum w, 0) -> disparity 0
+        *disp_out = disp;
+        *acc_out = fminf(sw, 1.f);
+    }
+    __syncwarp();
+}
+
+// Coarse pass: composite + inverse-CDF importance sampling + merge order.
+__global__ void __launch_bounds__(32 * kWarpsPerBlock)
+composite_resample_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, int S, int S_f,
+                          const float* __restrict__ raw /* (n_rays*S + n_rays, 4); tail = per-ray empty sample */,
+                          const uint32_t* __restrict__ mask, const float* __restrict__ z,
+                          const float* __restrict__ noise, float inv_B, const float* __restrict__ u_vals /* (S_f) or null */,
+                          const float* __restrict__ u_rand /* (n_rays,S_f) or null */,
+                          float* __restrict__ weights, float* __restrict__ alpha, float* __restrict__ rgb0,
+                          float* __restrict__ disp0, float* __restrict__ acc0, float* __restrict__ z_samples,
+                          float* __restrict__ z_all, int* __restrict__ order_out, int* __restrict__ inds_out) {
+    __shared__ RaySmem smem[kWarpsPerBlock];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int n = blockIdx.x * kWarpsPerBlock + wib;
+    if (n >= n_rays) return;
+    RaySmem& sm = smem[wib];
+    const float* r = rays + (size_t)n * ray_stride;
+    const float norm_d = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(r[3], r[3]), __fmul_rn(r[4], r[4])), __fmul_rn(r[5], r[5])));
+    for (int i = lane; i < S; i += 32) sm.z[i] = z[(size_t)n * S + i];
+    __syncwarp();
+    const float4* raw4 = reinterpret_cast<const float4*>(raw);
+    const float4 empty = raw4[(size_t)n_rays * S + n];
+    auto fetch = [&](int i) { return mask[(size_t)n * S + i] ? raw4[(size_t)n * S + i] : empty; };
+    composite_ray(sm, S, lane, norm_d, inv_B, noise ? noise + (size_t)n * S : nullptr, fetch,
+                  weights + (size_t)n * S, alpha + (size_t)n * S, rgb0 + (size_t)n * 3, disp0 + n, acc0 + n);
+    if (S_f <= 0) return;
+    // ---- R1: pdf over the S-2 interior bins, cdf with a leading zero (ray_utils.py:161-164,272-279)
+    const int nb = S - 2;
+    const int epl = (nb + 31) / 32;
+    float dw[kEPL];
+    double lsum = 0.0;
+#pragma unroll
+    for (int e = 0; e < kEPL; ++e) {
+        const int k = lane * epl + e;
+        dw[e] = 0.f;
+        if (e < epl && k < nb) {
+            const float a = fmaxf(sm.w[k], sm.w[k + 1]), b = fmaxf(sm.w[k + 1], sm.w[k + 2]);
+            dw[e] = __fadd_rn(__fadd_rn(__fmul_rn(0.5f, __fadd_rn(a, b)), 0.01f), 1e-5f);
+            lsum += (double)dw[e];
+        }
+    }
+    double tot = lsum;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    const float total = (float)tot;
+    double lpdf = 0.0;
+#pragma unroll
+    for (int e = 0; e < kEPL; ++e) {
+        const int k = lane * epl + e;
+        if (e < epl && k < nb) { dw[e] = __fdiv_rn(dw[e], total); lpdf += (double)dw[e]; }
+    }
+    double run = warp_excl_sum(lpdf, lane);
+    if (lane == 0) sm.cdf[0] = 0.f;
+#pragma unroll
+    for (int e = 0; e < kEPL; ++e) {
+        const int k = lane * epl + e;
+        if (e < epl && k < nb) { run += (double)dw[e]; sm.cdf[k + 1] = (float)run; }
+    }
+    __syncwarp();
+    const int n_cdf = S - 1;
+    for (int j = lane; j < S_f; j += 32) {
+        const float u = u_rand ? u_rand[(size_t)n * S_f + j] : u_vals[j];
+        int ind = 0;                                                // searchsorted(cdf, u, right=True)
+        for (int k = 0; k < n_cdf; ++k) ind += (sm.cdf[k] <= u) ? 1 : 0;
+        const int below = ind - 1 > 0 ? ind - 1 : 0;
+        const int above = ind < n_cdf - 1 ? ind : n_cdf - 1;
+        const float cb = sm.cdf[below], ca = sm.cdf[above];
+        const float bb = __fmul_rn(.5f, __fadd_rn(sm.z[below + 1], sm.z[below]));
+        const float ba = __fmul_rn(.5f, __fadd_rn(sm.z[above + 1], sm.z[above]));
+        float den = __fsub_rn(ca, cb);
+        if (den < 1e-5f) den = 1.f;
+        const float t = __fdiv_rn(__fsub_rn(u, cb), den);
+        const float zsv = __fadd_rn(bb, __fmul_rn(t, __fsub_rn(ba, bb)));
+        sm.zs[j] = zsv;
+        z_samples[(size_t)n * S_f + j] = zsv;
+        if (inds_out) inds_out[(size_t)n * S_f + j] = ind;
+    }
+    __syncwarp();
+    // ---- sorted merge of [z ; z_samples] (stable: ties keep concatenation order)
+    const int St = S + S_f;
+    for (int i = lane; i < St; i += 32) sm.cat[i] = i < S ? sm.z[i] : sm.zs[i - S];
+    __syncwarp();
+    for (int i = lane; i < St; i += 32) {
+        const float v = sm.cat[i];
+        int rank = 0;
+        for (int k = 0; k < St; ++k) { const float c = sm.cat[k]; rank += (c < v || (c == v && k < i)) ? 1 : 0; }
+        sm.order[rank] = i;
+    }
+    __syncwarp();
+    for (int i = lane; i < St; i += 32) {
+        const int src = sm.order[i];
+        order_out[(size_t)n * St + i] = src;
+        z_all[(size_t)n * St + i] = sm.cat[src];
+    }
+}
+
+// Fine pass: gather coarse / fine raw by merge order, composite the S_t samples.
+__global__ void __launch_bounds__(32 * kWarpsPerBlock)
+merge_composite_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, int S_c, int S_f,
+                       const float* __restrict__ raw0 /* (n_rays*S_c + n_rays, 4) */, const uint32_t* __restrict__ mask0,
+                       const float* __restrict__ raw1 /* (n_rays*S_f, 4) */, const uint32_t* __restrict__ mask1,
+                       const float* __restrict__ z_all, const int* __restrict__ order, const float* __restrict__ noise,
+                       float inv_B, float* __restrict__ weights, float* __restrict__ alpha, float* __restrict__ rgb,
+                       float* __restrict__ disp, float* __restrict__ acc, float* __restrict__ raw_merged /* (n,St,4) or null */,
+                       const float* __restrict__ confd0, const float* __restrict__ confd1,
+                       float* __restrict__ confd_merged /* (n,St,24) or null */, float* __restrict__ invalid_merged /* or null */) {
+    __shared__ RaySmem smem[kWarpsPerBlock];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int n = blockIdx.x * kWarpsPerBlock + wib;
+    if (n >= n_rays) return;
+    RaySmem& sm = smem[wib];
+    const int St = S_c + S_f;
+    const float* r = rays + (size_t)n * ray_stride;
+    const float norm_d = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(r[3], r[3]), __fmul_rn(r[4], r[4])), __fmul_rn(r[5], r[5])));
+    for (int i = lane; i < St; i += 32) { sm.z[i] = z_all[(size_t)n * St + i]; sm.order[i] = order[(size_t)n * St + i]; }
+    __syncwarp();
+    const float4* r0 = reinterpret_cast<const float4*>(raw0);
+    const float4* r1 = reinterpret_cast<const float4*>(raw1);
+    const float4 empty = r0[(size_t)n_rays * S_c + n];
+    auto fetch = [&](int i) {
+        const int src = sm.order[i];
+        float4 v;
+        if (src < S_c) v = mask0[(size_t)n * S_c + src] ? r0[(size_t)n * S_c + src] : empty;
+        else           v = mask1[(size_t)n * S_f + src - S_c] ? r1[(size_t)n * S_f + src - S_c] : empty;
+        if (raw_merged) reinterpret_cast<float4*>(raw_merged)[(size_t)n * St + i] = v;
+        return v;
+    };
+    composite_ray(sm, St, lane, norm_d, inv_B, noise ? noise + (size_t)n * St : nullptr, fetch,
+                  weights + (size_t)n * St, alpha + (size_t)n * St, rgb + (size_t)n * 3, disp + n, acc + n);
+    if (confd_merged || invalid_merged) {                          // training outputs (raycasters.py:710-716)
+        for (int e = lane; e < St * DANBO_J; e += 32) {
+            const int i = e / DANBO_J, j = e - i * DANBO_J;
+            const int src = sm.order[i];
+            const bool coarse = src < S_c;
+            const size_t sidx = coarse ? (size_t)n * S_c + src : (size_t)n * S_f + src - S_c;
+            const uint32_t m = coarse ? mask0[sidx] : mask1[sidx];
+            const bool vis = (m >> j) & 1u;
+            if (invalid_merged) invalid_merged[(size_t)n * St * DANBO_J + e] = vis ? 0.f : 1.f;
+            if (confd_merged) confd_merged[(size_t)n * St * DANBO_J + e] = vis ? (coarse ? confd0 : confd1)[sidx * DANBO_J + j] : 0.f;
+        }
+    }
+}
+
+}  // namespace danbo
+
+using namespace danbo;
+
+extern "C" int danbo_composite_resample(const float* rays, int ray_stride, int n_rays, int S, int S_f, const float* raw,
+                                        const unsigned int* mask, const float* z, const float* noise, float inv_B,
+                                        const float* u_vals, const float* u_rand, float* weights, float* alpha,
+                                        float* rgb0, float* disp0, float* acc0, float* z_samples, float* z_all,
+                                        int* order, int* inds, void* stream) {
+    if (n_rays <= 0) return 0;
+    if (S < 3 || S > kMaxS || S + S_f > kMaxS) return -1;
+    if (S_f > 0 && !u_vals && !u_rand) return -2;
+    const int G = (n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    composite_resample_kernel<<<G, 32 * kWarpsPerBlock, 0, (cudaStream_t)stream>>>(
+        rays, ray_stride, n_rays, S, S_f, raw, mask, z, noise, inv_B, u_vals, u_rand, weights, alpha, rgb0, disp0, acc0,
+        z_samples, z_all, order, inds);
+    DANBO_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int danbo_merge_composite(const float* rays, int ray_stride, int n_rays, int S_c, int S_f, const float* raw0,
+                                     const unsigned int* mask0, const float* raw1, const unsigned int* mask1,
+                                     const float* z_all, const int* order, const float* noise, float inv_B,
+                                     float* weights, float* alpha, float* rgb, float* disp, float* acc,
+                                     float* raw_merged, const float* confd0, const float* confd1, float* confd_merged,
+                                     float* invalid_merged, void* stream) {
+    if (n_rays <= 0) return 0;
+    if (S_c + S_f > kMaxS) return -1;
+    const int G = (n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    merge_composite_kernel<<<G, 32 * kWarpsPerBlock, 0, (cudaStream_t)stream>>>(
+        rays, ray_stride, n_rays, S_c, S_f, raw0, mask0, raw1, mask1, z_all, order, noise, inv_B, weights, alpha, rgb,
+        disp, acc, raw_merged, confd0, confd1, confd_merged, invalid_merged);
+    DANBO_CHECK_LAUNCH();
+    return 0;
+}

@@ -1,0 +1,486 @@
+// Near/far (NF1, NF2), coarse sampling (SM1), world->bone transform + visibility mask (T1, T2, G1 mask),
+// per-bone feature gather + aggregation net + blend + positional encoding (G1, G2, A1-A3), per-ray view bias (V1).
+// Reference rows: SURVEY.md §8(a).  All kernels are HBM / latency bound integer-and-fp32 work; they share one
+// layout rule: one thread (or one warp) per ray sample, pose tables read through L1 as warp-uniform float4 loads.
+#include "common.cuh"
+#include <math.h>
+
+namespace danbo {
+
+struct FieldConsts {
+    const float* align;       // (24,4,4) bone-align transforms A_j                     raycasters.py:548-591
+    const float* axis_scale;  // (24,3)  per-bone half extents (|.| applied here)       gnn_backbone.py:802
+    const float* agg_w0;      // (24,15,32) prob_linears.layers.0.lin.weight
+    const float* agg_adjw;    // (24,24) prob_linears.layers.0.adj_w
+    const float* agg_adj;     // (24,24) prob_linears.layers.0.adj (tree + self, 0/1)
+    const float* agg_b0;      // (32)
+    const float* agg_w1;      // (24,32,32)
+    const float* agg_b1;      // (24,32)
+    const float* agg_w2;      // (24,32)
+    const float* agg_b2;      // (24)
+};
+
+// tree neighbours (self, parent, children) of every SMPL joint as bit masks (gnn_backbone.py:18-34)
+__constant__ uint32_t kNbrMask[DANBO_J] = {
+    0x0000000Fu, 0x00000013u, 0x00000025u, 0x00000049u, 0x00000092u, 0x00000124u, 0x00000248u, 0x00000490u,
+    0x00000920u, 0x00007240u, 0x00000480u, 0x00000900u, 0x00009200u, 0x00012200u, 0x00024200u, 0x00009000u,
+    0x00052000u, 0x000A4000u, 0x00150000u, 0x002A0000u, 0x00540000u, 0x00A80000u, 0x00500000u, 0x00A00000u};
+
+// ---------------------------------------------------------------------------------------------------------
+// x_j = (A_j (R_j p + t_j) + a_j) / |s_j| for one joint, in the reference's two-step order with a true divide.
+// encoders.py:288-303 (transform_batch_pts), :442-444 (bone align), gnn_backbone.py:802 (scale)
+__device__ __forceinline__ void bone_coords(const float* __restrict__ skt, const float* __restrict__ A,
+                                            const float* __restrict__ scale, float px, float py, float pz,
+                                            float& x0, float& x1, float& x2) {
+    const float4 r0 = __ldg(reinterpret_cast<const float4*>(skt));
+    const float4 r1 = __ldg(reinterpret_cast<const float4*>(skt) + 1);
+    const float4 r2 = __ldg(reinterpret_cast<const float4*>(skt) + 2);
+    const float l0 = fmaf(r0.z, pz, fmaf(r0.y, py, fmaf(r0.x, px, r0.w)));
+    const float l1 = fmaf(r1.z, pz, fmaf(r1.y, py, fmaf(r1.x, px, r1.w)));
+    const float l2 = fmaf(r2.z, pz, fmaf(r2.y, py, fmaf(r2.x, px, r2.w)));
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(A));
+    const float4 a1 = __ldg(reinterpret_cast<const float4*>(A) + 1);
+    const float4 a2 = __ldg(reinterpret_cast<const float4*>(A) + 2);
+    const float t0 = __fadd_rn(fmaf(a0.z, l2, fmaf(a0.y, l1, __fmul_rn(a0.x, l0))), a0.w);
+    const float t1 = __fadd_rn(fmaf(a1.z, l2, fmaf(a1.y, l1, __fmul_rn(a1.x, l0))), a1.w);
+    const float t2 = __fadd_rn(fmaf(a2.z, l2, fmaf(a2.y, l1, __fmul_rn(a2.x, l0))), a2.w);
+    x0 = __fdiv_rn(t0, fabsf(__ldg(scale + 0)));
+    x1 = __fdiv_rn(t1, fabsf(__ldg(scale + 1)));
+    x2 = __fdiv_rn(t2, fabsf(__ldg(scale + 2)));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// NF1: ray / bounding-cylinder near & far in the x-z plane, fp32, op order of ray_utils.py:294-328.
+// Writes NaN for rays that miss; accumulates per-segment sums for the reference's chunk-wide nanmean (F8).
+__global__ void nearfar_cyl_kernel(const float* __restrict__ rays, int ray_stride, int n_rays,
+                                   const float* __restrict__ pose_cyl, int cyl_stride, int rays_per_pose, int n_poses,
+                                   int seg_len, float* __restrict__ near_out, float* __restrict__ far_out,
+                                   double* __restrict__ seg_acc /* [n_seg][4] sum_near,cnt_near,sum_far,cnt_far */) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_rays) return;
+    const float* r = rays + (size_t)n * ray_stride;
+    const float ox = r[0], oz = r[2], dx = r[3], dz = r[5], near = r[6], far = r[7];
+    int pose = n / rays_per_pose; if (pose >= n_poses) pose = n_poses - 1;
+    const float* c = pose_cyl + (size_t)pose * cyl_stride;
+    const float cx = c[0], cz = c[1], rad = c[2];
+    const float nx = __fadd_rn(ox, __fmul_rn(dx, near)), nz = __fadd_rn(oz, __fmul_rn(dz, near));
+    const float fx = __fadd_rn(ox, __fmul_rn(dx, far)), fz = __fadd_rn(oz, __fmul_rn(dz, far));
+    const float ncx = __fsub_rn(cx, nx), ncz = __fsub_rn(cz, nz);
+    const float nfx = __fsub_rn(fx, nx), nfz = __fsub_rn(fz, nz);
+    const float nf_norm = __fsqrt_rn(__fadd_rn(__fmul_rn(nfx, nfx), __fmul_rn(nfz, nfz)));
+    const float scale = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dz, dz)));
+    const float cross = __fsub_rn(__fmul_rn(ncx, nfz), __fmul_rn(ncz, nfx));
+    const float dist = __fdiv_rn(fabsf(cross), nf_norm);
+    const float Q = __fsqrt_rn(__fsub_rn(__fmul_rn(rad, rad), __fmul_rn(dist, dist)));      // NaN when the ray misses
+    const float K = __fdiv_rn(__fadd_rn(__fmul_rn(ncx, nfx), __fmul_rn(ncz, nfz)), nf_norm);
+    const float m = (Q < K) ? 1.f : 0.f;
+    const float nn = __fadd_rn(near, __fdiv_rn(__fmul_rn(m, __fsub_rn(K, Q)), scale));
+    const float ff = __fadd_rn(near, __fdiv_rn(__fadd_rn(K, Q), scale));
+    // rows with NaN Q are refilled later; flag them by writing NaN to BOTH outputs' sign of Q via far (already NaN)
+    near_out[n] = (Q != Q) ? __int_as_float(0x7fc00000) : nn;
+    far_out[n] = (Q != Q) ? __int_as_float(0x7fc00000) : ff;
+    const int seg = seg_len > 0 ? n / seg_len : 0;
+    double* acc = seg_acc + 4 * (size_t)seg;
+    // nanmean over the segment: every non-NaN entry counts (ray_utils.py:334,340)
+    if (nn == nn) { atomicAdd(acc + 0, (double)nn); atomicAdd(acc + 1, 1.0); }
+    if (ff == ff) { atomicAdd(acc + 2, (double)ff); atomicAdd(acc + 3, 1.0); }
+}
+
+// NF1 fill + NF2: per-bone oriented-box near/far in fp64 with the exactly-two-hits rule (F7).
+// raycasters.py:648-707, ray_utils.py:383-417.  One thread per ray.
+__global__ void nearfar_finish_kernel(const float* __restrict__ rays, int ray_stride, int n_rays,
+                                      const float* __restrict__ pose_skts, int rays_per_pose, int n_poses,
+                                      FieldConsts fc, int seg_len, const double* __restrict__ seg_acc, int use_box,
+                                      float bound, float hi, float* __restrict__ near_io, float* __restrict__ far_io,
+                                      uint8_t* __restrict__ p_valid /* (N,24) 6-bit masks or null */,
+                                      uint8_t* __restrict__ v_valid /* (N,24) or null */) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_rays) return;
+    const float* r = rays + (size_t)n * ray_stride;
+    float near = near_io[n], far = far_io[n];
+    if (far != far) {                                   // Q was NaN: take the segment nanmean, else the input bound
+        const double* acc = seg_acc + 4 * (size_t)(seg_len > 0 ? n / seg_len : 0);
+        near = acc[1] > 0.0 ? (float)(acc[0] / acc[1]) : r[6];
+        far = acc[3] > 0.0 ? (float)(acc[2] / acc[3]) : r[7];
+    }
+    if (use_box) {
+        int pose = n / rays_per_pose; if (pose >= n_poses) pose = n_poses - 1;
+        const float ox = r[0], oy = r[1], oz = r[2], dx = r[3], dy = r[4], dz = r[5];
+        // hi = fp32(bound_range + eps) computed by the host in double, the way torch compares a float tensor
+        // with the Python scalar `bound_range + eps` (ray_utils.py:404-409)
+        float vnear = 100000.f, vfar = -100000.f;
+        bool any = false;
+        for (int j = 0; j < DANBO_J; ++j) {
+            const float* S = pose_skts + ((size_t)pose * DANBO_J + j) * 16;
+            const float* A = fc.align + j * 16;
+            // rays_ot = R o + t ; rays_dt = R d            (batched 3x3 matvec, fp32)
+            float o[3], d[3], ot[3], dt[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                o[i] = __fadd_rn(fmaf(S[4 * i + 2], oz, fmaf(S[4 * i + 1], oy, __fmul_rn(S[4 * i], ox))), S[4 * i + 3]);
+                d[i] = fmaf(S[4 * i + 2], dz, fmaf(S[4 * i + 1], dy, __fmul_rn(S[4 * i], dx)));
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                ot[i] = __fadd_rn(fmaf(A[4 * i + 2], o[2], fmaf(A[4 * i + 1], o[1], __fmul_rn(A[4 * i], o[0]))), A[4 * i + 3]);
+                dt[i] = fmaf(A[4 * i + 2], d[2], fmaf(A[4 * i + 1], d[1], __fmul_rn(A[4 * i], d[0])));
+            }
+            float s[3], os[3], ds[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                s[i] = fabsf(fc.axis_scale[j * 3 + i]);
+                os[i] = __fdiv_rn(ot[i], s[i]);
+                ds[i] = __fdiv_rn(dt[i], s[i]);
+            }
+            int n_in = 0;
+            uint32_t bits = 0;
+            float seg[2][3];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {               // planes: -b on x,y,z then +b on x,y,z
+                const int a = k % 3;
+                const double b = (k < 3) ? -(double)bound : (double)bound;
+                const double t = (b - (double)os[a]) / (double)ds[a];
+                float p[3];
+                bool in = true;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    p[i] = (float)(t * (double)ds[i] + (double)os[i]);
+                    in = in && (p[i] <= hi) && (p[i] >= -hi);
+                }
+                if (in) {
+                    if (n_in < 2) { seg[n_in][0] = p[0]; seg[n_in][1] = p[1]; seg[n_in][2] = p[2]; }
+                    ++n_in;
+                    bits |= 1u << k;
+                }
+            }
+            const bool valid = (n_in == 2);
+            if (p_valid) p_valid[(size_t)n * DANBO_J + j] = (uint8_t)bits;
+            if (v_valid) v_valid[(size_t)n * DANBO_J + j] = valid ? 1 : 0;
+            if (valid) {
+                const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dt[0], dt[0]), __fmul_rn(dt[1], dt[1])), __fmul_rn(dt[2], dt[2])));
+                float st[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const float q0 = __fsub_rn(__fmul_rn(seg[e][0], s[0]), ot[0]);
+                    const float q1 = __fsub_rn(__fmul_rn(seg[e][1], s[1]), ot[1]);
+                    const float q2 = __fsub_rn(__fmul_rn(seg[e][2], s[2]), ot[2]);
+                    st[e] = __fdiv_rn(__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(q0, q0), __fmul_rn(q1, q1)), __fmul_rn(q2, q2))), nrm);
+                }
+                vnear = fminf(vnear, fminf(st[0], st[1]));
+                vfar = fmaxf(vfar, fmaxf(st[0], st[1]));
+                any = true;
+            }
+        }
+        if (any) { near = vnear; far = vfar; }
+    }
+    near_io[n] = near;
+    far_io[n] = far;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// SM1 + T1/T2 + visibility mask + compaction.  One thread per (ray, sample).
+//   coarse mode (z_in == null): z = near(1-t)+far*t (+ stratified jitter), written to z_out
+//   fine mode   (z_in != null): z given (importance samples)
+// Emits the 24-bit visibility mask of every sample and appends samples with a non-empty mask to the active
+// list; with append_empty, one extra entry per ray (id = n_rays*S + ray) stands for "a sample no bone sees".
+__global__ void sample_mask_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, int S,
+                                   const float* __restrict__ near, const float* __restrict__ far,
+                                   const float* __restrict__ t_vals, const float* __restrict__ t_rand,
+                                   const float* __restrict__ z_in, float* __restrict__ z_out,
+                                   const float* __restrict__ pose_skts, int rays_per_pose, int n_poses,
+                                   FieldConsts fc, uint32_t* __restrict__ mask_out, int* __restrict__ active_ids,
+                                   int* __restrict__ active_count, int capacity, int append_empty) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = n_rays * S;
+    uint32_t mask = 0;
+    int n = 0, s = 0;
+    if (idx < total) {
+        n = idx / S; s = idx - n * S;
+        const float* r = rays + (size_t)n * ray_stride;
+        float z;
+        if (z_in) {
+            z = z_in[idx];
+        } else {
+            const float nr = near[n], fr = far[n];
+            auto zv = [&](int i) { const float t = t_vals[i]; return __fadd_rn(__fmul_rn(nr, __fsub_rn(1.f, t)), __fmul_rn(fr, t)); };
+            z = zv(s);
+            if (t_rand) {                                // ray_utils.py:233-248
+                const float lower = (s == 0) ? z : __fmul_rn(.5f, __fadd_rn(z, zv(s - 1)));
+                const float upper = (s == S - 1) ? z : __fmul_rn(.5f, __fadd_rn(zv(s + 1), z));
+                z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), t_rand[idx]));
+            }
+            z_out[idx] = z;
+        }
+        const float px = __fadd_rn(r[0], __fmul_rn(r[3], z));
+        const float py = __fadd_rn(r[1], __fmul_rn(r[4], z));
+        const float pz = __fadd_rn(r[2], __fmul_rn(r[5], z));
+        int pose = n / rays_per_pose; if (pose >= n_poses) pose = n_poses - 1;
+        const float* skt = pose_skts + (size_t)pose * DANBO_J * 16;
+#pragma unroll 4
+        for (int j = 0; j < DANBO_J; ++j) {
+            float x0, x1, x2;
+            bone_coords(skt + j * 16, fc.align + j * 16, fc.axis_scale + j * 3, px, py, pz, x0, x1, x2);
+            const bool invalid = (fabsf(x0) > 1.f) || (fabsf(x1) > 1.f) || (fabsf(x2) > 1.f);
+            mask |= (invalid ? 0u : 1u) << j;
+        }
+        mask_out[idx] = mask;
+    }
+    // ---- compaction: active samples, plus one "empty" entry per ray
+    const bool act = (idx < total) && (mask != 0);
+    // append_empty: 1 = one empty entry per ray, 2 = a single one (for the last ray; density queries)
+    const bool emp = (idx < total) && (s == 0) && (append_empty == 1 || (append_empty == 2 && n == n_rays - 1));
+    const int want = (act ? 1 : 0) + (emp ? 1 : 0);
+    __shared__ int warp_tot[32];
+    __shared__ int block_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = want;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = blockDim.x >> 5;
+        int v = lane < nw ? warp_tot[lane] : 0, inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+        if (lane < nw) warp_tot[lane] = inc - v;        // exclusive offset of each warp
+        const int tot = __shfl_sync(0xffffffffu, inc, 31);
+        if (lane == 0) block_base = tot > 0 ? atomicAdd(active_count, tot) : 0;
+    }
+    __syncthreads();
+    if (want) {
+        int pos = block_base + warp_tot[warp] + incl - want;
+        if (act) { if (pos < capacity) active_ids[pos] = idx; ++pos; }
+        if (emp && pos < capacity) active_ids[pos] = total + n;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// G1/G2 + A1-A3 + PE.  One warp per active entry; lanes = hidden units of the aggregation net.
+//   * features of bone k: lane l < 15 -> channel f = l/3 on axis a = l%3, linear interpolation over 16 bins with
+//     zero padding (closed form of misc.py:331-351), times the window exp(-2 sum x^6)   (gnn_backbone.py:802-826)
+//   * logit of a visible bone j needs layer 0 of j's tree neighbours only (the 24x24 mix has 70 non-zeros);
+//     bones the sample is outside of get blend weight exactly 0, so only visible bones are evaluated (danbo.py:406-415)
+//   * writes the encoded row X (bf16, 195 -> K 256) into its 128-row swizzled tile, ready to be an MMA A operand.
+__global__ void __launch_bounds__(256)
+field_agg_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, int S, const float* __restrict__ z,
+                 const uint32_t* __restrict__ mask, const int* __restrict__ active_ids,
+                 const int* __restrict__ active_count, int capacity,
+                 const float* __restrict__ pose_skts, const float* __restrict__ pose_vol, int rays_per_pose,
+                 int n_poses, FieldConsts fc, uint8_t* __restrict__ xtiles, int* __restrict__ row_ray,
+                 float* __restrict__ confd /* (n_rays*S,24) or null */, float* __restrict__ hbar_out /* (rows,16) or null */) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const int gwarp = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const int n_warps = gridDim.x * warps_per_block;
+    int count = *active_count; if (count > capacity) count = capacity;
+    const int total = n_rays * S;
+    for (int e = gwarp; e < count; e += n_warps) {
+        const int id = active_ids[e];
+        float hbar = 0.f;                               // lane l < 15 holds blended feature l
+        int n;
+        if (id >= total) {
+            n = id - total;                             // the ray's "no bone sees me" entry: h = 0
+        } else {
+            n = id / S;
+            const float* r = rays + (size_t)n * ray_stride;
+            const float zz = z[id];
+            const float px = __fadd_rn(r[0], __fmul_rn(r[3], zz));
+            const float py = __fadd_rn(r[1], __fmul_rn(r[4], zz));
+            const float pz = __fadd_rn(r[2], __fmul_rn(r[5], zz));
+            int pose = n / rays_per_pose; if (pose >= n_poses) pose = n_poses - 1;
+            const float* skt = pose_skts + (size_t)pose * DANBO_J * 16;
+            const float* vol = pose_vol + (size_t)pose * DANBO_J * DANBO_VOL;
+            uint32_t m = mask[id];
+            while (m) {
+                const int j = __ffs(m) - 1; m &= m - 1;
+                float mix = 0.f, hj = 0.f;
+                uint32_t nb = kNbrMask[j];
+                while (nb) {
+                    const int k = __ffs(nb) - 1; nb &= nb - 1;
+                    float x0, x1, x2;
+                    bone_coords(skt + k * 16, fc.align + k * 16, fc.axis_scale + k * 3, px, py, pz, x0, x1, x2);
+                    const float x0_2 = x0 * x0, x1_2 = x1 * x1, x2_2 = x2 * x2;
+                    const float win = expf(-2.f * (x0_2 * x0_2 * x0_2 + x1_2 * x1_2 * x1_2 + x2_2 * x2_2 * x2_2));
+                    float hk = 0.f;
+                    if (lane < DANBO_FEAT) {
+                        const int f = lane / 3, a = lane - 3 * f;
+                        const float xa = a == 0 ? x0 : (a == 1 ? x1 : x2);
+                        const float iy = ((xa + 1.f) * (float)DANBO_RES - 1.f) * 0.5f;
+                        const float fl = floorf(iy);
+                        const float w1 = iy - fl, w0 = 1.f - w1;
+                        const int i0 = (int)fl, i1 = i0 + 1;
+                        const float* line = vol + k * DANBO_VOL + f * (DANBO_RES * 3) + a;
+                        const float v0 = (i0 >= 0 && i0 < DANBO_RES) ? __ldg(line + i0 * 3) : 0.f;
+                        const float v1 = (i1 >= 0 && i1 < DANBO_RES) ? __ldg(line + i1 * 3) : 0.f;
+                        hk = (v0 * w0 + v1 * w1) * win;
+                    }
+                    if (k == j) hj = hk;
+                    const float* w0p = fc.agg_w0 + (size_t)k * DANBO_FEAT * DANBO_AGG_W + lane;
+                    float l0 = 0.f;
+#pragma unroll
+                    for (int i = 0; i < DANBO_FEAT; ++i) l0 = fmaf(__shfl_sync(0xffffffffu, hk, i), __ldg(w0p + i * DANBO_AGG_W), l0);
+                    const float adj = __ldg(fc.agg_adjw + j * DANBO_J + k) * __ldg(fc.agg_adj + j * DANBO_J + k);
+                    mix = fmaf(adj, l0, mix);
+                }
+                const float o1 = fmaxf(mix + __ldg(fc.agg_b0 + lane), 0.f);
+                const float* w1p = fc.agg_w1 + (size_t)j * DANBO_AGG_W * DANBO_AGG_W + lane;
+                float l1 = 0.f;
+#pragma unroll
+                for (int i = 0; i < DANBO_AGG_W; ++i) l1 = fmaf(__shfl_sync(0xffffffffu, o1, i), __ldg(w1p + i * DANBO_AGG_W), l1);
+                const float o2 = fmaxf(l1 + __ldg(fc.agg_b1 + j * DANBO_AGG_W + lane), 0.f);
+                const float a = warp_sum(o2 * __ldg(fc.agg_w2 + j * DANBO_AGG_W + lane)) + __ldg(fc.agg_b2 + j);
+                const float p = (1.f / (1.f + expf(-a))) * 1.002f - 0.001f;      // danbo.py:410, valid bone
+                hbar = fmaf(p, hj, hbar);
+                if (confd && lane == 0) confd[(size_t)id * DANBO_J + j] = a;
+            }
+        }
+        if (hbar_out && lane < 16) hbar_out[(size_t)e * 16 + lane] = lane < DANBO_FEAT ? hbar : 0.f;
+        if (lane == 0) row_ray[e] = n;
+        // ---- positional encoding (cutoff_embedder.py:62-73): [h, sin(2^0 h), cos(2^0 h), ..., cos(2^5 h)] -> bf16
+        const int tile = e >> 7, rr = e & 127;
+        uint8_t* xt = xtiles + (size_t)tile * DANBO_X_TILE_BYTES;
+        uint32_t pk[4];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int col = lane * 8 + c;
+            int src = 0, fn = 0; float freq = 1.f;
+            if (col < DANBO_FEAT) { src = col; fn = 0; }
+            else if (col < DANBO_X_COLS) {
+                const int q = col - DANBO_FEAT;
+                const int f = q / 30, rem = q - f * 30;
+                fn = 1 + rem / DANBO_FEAT; src = rem % DANBO_FEAT; freq = (float)(1 << f);
+            } else { fn = 3; }
+            const float hv = __shfl_sync(0xffffffffu, hbar, src);
+            float val;
+            if (fn == 0) val = hv;
+            else if (fn == 1) val = sinf(hv * freq);
+            else if (fn == 2) val = cosf(hv * freq);
+            else val = 0.f;
+            const uint16_t b = __bfloat16_as_ushort(__float2bfloat16_rn(val));
+            if (c & 1) pk[c >> 1] |= (uint32_t)b << 16; else pk[c >> 1] = b;
+        }
+        if (lane < 26) {                                // 26 x 8 = 208 columns (13 k-steps of 16)
+            *reinterpret_cast<uint4*>(xt + sw128_offset((uint32_t)rr, (uint32_t)lane * 8)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// V1 folded into the view layer: b_ray[n] = W_v[:, 256:411] . [PE(rays_d) (27) ; frame code (128)] + b_v.
+// nerf.py:252-279, embedding.py:86-108.  8 rays per block of 128 threads; thread = output unit.
+__global__ void __launch_bounds__(128)
+ray_bias_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, const int* __restrict__ cam_idx,
+                const float* __restrict__ codes, int n_codes,
+                const float* __restrict__ wv_ray /* (155,128) transposed view/code slice of W_v, then b_v (128) */,
+                float* __restrict__ out /* (n_rays,128) */) {
+    constexpr int RB = 8, VIN = 155;
+    __shared__ float v[RB][VIN + 1];
+    const int base = blockIdx.x * RB;
+    for (int i = threadIdx.x; i < RB * VIN; i += blockDim.x) {
+        const int rb = i / VIN, c = i - rb * VIN;
+        const int n = base + rb;
+        float val = 0.f;
+        if (n < n_rays) {
+            if (c < 27) {
+                const float* r = rays + (size_t)n * ray_stride + 3;
+                if (c < 3) val = r[c];
+                else { const int q = c - 3, f = q / 6, rem = q - 6 * f; const float x = r[rem % 3] * (float)(1 << f); val = rem < 3 ? sinf(x) : cosf(x); }
+            } else {
+                int ci = cam_idx ? cam_idx[n] : 0;
+                ci = ci < 0 ? n_codes : (ci > n_codes - 1 ? n_codes - 1 : ci);      // row n_codes holds the mean code
+                val = codes[(size_t)ci * 128 + (c - 27)];
+            }
+        }
+        v[rb][c] = val;
+    }
+    __syncthreads();
+    const int o = threadIdx.x;
+    float acc[RB];
+#pragma unroll
+    for (int rb = 0; rb < RB; ++rb) acc[rb] = 0.f;
+    for (int c = 0; c < VIN; ++c) {
+        const float wc = __ldg(wv_ray + c * 128 + o);
+#pragma unroll
+        for (int rb = 0; rb < RB; ++rb) acc[rb] = fmaf(wc, v[rb][c], acc[rb]);
+    }
+    const float b = wv_ray[VIN * 128 + o];
+#pragma unroll
+    for (int rb = 0; rb < RB; ++rb) if (base + rb < n_rays) out[(size_t)(base + rb) * 128 + o] = acc[rb] + b;
+}
+
+}  // namespace danbo
+
+using namespace danbo;
+
+extern "C" int danbo_nearfar(const float* rays, int ray_stride, int n_rays, const float* pose_cyl, int cyl_stride,
+                             const float* pose_skts, int rays_per_pose, int n_poses, const float* align,
+                             const float* axis_scale, int seg_len, int use_box, float bound, float bound_hi, float* near_out,
+                             float* far_out, double* seg_acc, int n_seg, unsigned char* p_valid,
+                             unsigned char* v_valid, void* stream) {
+    if (n_rays <= 0) return 0;
+    if (rays_per_pose <= 0 || n_poses <= 0 || ray_stride < 8) return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(seg_acc, 0, sizeof(double) * 4 * (size_t)n_seg, st);
+    if (e != cudaSuccess) return (int)e;
+    const int B = 128, G = (n_rays + B - 1) / B;
+    nearfar_cyl_kernel<<<G, B, 0, st>>>(rays, ray_stride, n_rays, pose_cyl, cyl_stride, rays_per_pose, n_poses, seg_len,
+                                        near_out, far_out, seg_acc);
+    DANBO_CHECK_LAUNCH();
+    FieldConsts fc{}; fc.align = align; fc.axis_scale = axis_scale;
+    nearfar_finish_kernel<<<G, B, 0, st>>>(rays, ray_stride, n_rays, pose_skts, rays_per_pose, n_poses, fc, seg_len,
+                                           seg_acc, use_box, bound, bound_hi, near_out, far_out, p_valid, v_valid);
+    DANBO_CHECK_LAUNCH();
+    return 0;
+}
+
+static FieldConsts make_consts(const float* const* p) {
+    FieldConsts fc;
+    fc.align = p[0]; fc.axis_scale = p[1]; fc.agg_w0 = p[2]; fc.agg_adjw = p[3]; fc.agg_adj = p[4];
+    fc.agg_b0 = p[5]; fc.agg_w1 = p[6]; fc.agg_b1 = p[7]; fc.agg_w2 = p[8]; fc.agg_b2 = p[9];
+    return fc;
+}
+
+extern "C" int danbo_sample_mask(const float* rays, int ray_stride, int n_rays, int S, const float* near,
+                                 const float* far, const float* t_vals, const float* t_rand, const float* z_in,
+                                 float* z_out, const float* pose_skts, int rays_per_pose, int n_poses,
+                                 const float* const* consts, unsigned int* mask_out, int* active_ids,
+                                 int* active_count, int capacity, int append_empty, void* stream) {
+    if (n_rays <= 0 || S <= 0) return 0;
+    if (!z_in && (!near || !far || !t_vals || !z_out)) return -1;
+    const long long total = (long long)n_rays * S;
+    if (total + n_rays >= (1LL << 31)) return -2;
+    const int B = 256, G = (int)((total + B - 1) / B);
+    sample_mask_kernel<<<G, B, 0, (cudaStream_t)stream>>>(rays, ray_stride, n_rays, S, near, far, t_vals, t_rand, z_in,
+                                                          z_out, pose_skts, rays_per_pose, n_poses, make_consts(consts),
+                                                          mask_out, active_ids, active_count, capacity, append_empty);
+    DANBO_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int danbo_field_agg(const float* rays, int ray_stride, int n_rays, int S, const float* z,
+                               const unsigned int* mask, const int* active_ids, const int* active_count,
+                               int capacity, const float* pose_skts, const float* pose_vol, int rays_per_pose,
+                               int n_poses, const float* const* consts, void* xtiles, int* row_ray, float* confd,
+                               float* hbar_out, int num_sms, void* stream) {
+    if (capacity <= 0) return 0;
+    int blocks = num_sms * 8;
+    const int need = (capacity + 7) / 8;
+    if (blocks > need) blocks = need;
+    if (blocks < 1) blocks = 1;
+    field_agg_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(rays, ray_stride, n_rays, S, z, mask, active_ids,
+                                                               active_count, capacity, pose_skts, pose_vol,
+                                                               rays_per_pose, n_poses, make_consts(consts),
+                                                               (uint8_t*)xtiles, row_ray, confd, hbar_out);
+    DANBO_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int danbo_ray_bias(const float* rays, int ray_stride, int n_rays, const int* cam_idx, const float* codes,
+                              int n_codes, const float* wv_ray, float* out, void* stream) {
+    if (n_rays <= 0) return 0;
+    ray_bias_kernel<<<(n_rays + 7) / 8, 128, 0, (cudaStream_t)stream>>>(rays, ray_stride, n_rays, cam_idx, codes, n_codes,
+                                                                       wv_ray, out);
+    DANBO_CHECK_LAUNCH();
+    return 0;
+}

@@ -1,0 +1,442 @@
+// M1: density/colour MLP of the DANBO field as ONE persistent tcgen05 kernel (sm_100a).
+//
+// Reference being replaced: core/networks/nerf.py:164-209 (inference_batchify / forward_density /
+// forward_view, ten addmm launches + relu/cat per 65 536-point chunk, every activation round-tripping HBM).
+//
+// Design:
+//   * one CTA per SM, 6 warps: warp 0 = bulk-copy (TMA) producer, warp 1 = MMA issuer (one elected thread),
+//     warps 2-5 = epilogue (one TMEM lane quarter each, thread <-> sample row).
+//   * tile = 128 samples.  Accumulators live in TMEM as two N=128 halves (columns 0-255, fp32).  The activation
+//     of every layer is written back to TMEM as packed bf16 (two ping-pong buffers, columns 256-511) and is the
+//     A operand of the next layer's tcgen05.mma straight from TMEM -- activations never touch shared or global
+//     memory.  Only the encoded input X (195 -> K 208, needed by layers 0 and 5) sits in shared memory.
+//   * weights (bf16, 1.3 MB, L2 resident) stream through a 9-deep ring of 16 KB stages
+//     ([128 out-rows x 64 k], canonical 128B-swizzled K-major) with cp.async.bulk + mbarrier complete_tx; the
+//     pack kernel below writes them to global memory already in that shared-memory image, so no tensor map is
+//     needed.
+//   * the epilogue of output half 0 overlaps the MMAs of half 1; the next layer starts on the K range that half 0
+//     produced while half 1 is still in its epilogue.
+//   * heads: sigma = w_alpha . relu(h7) in the layer-7 epilogue (fp32 FFMA), rgb = W_rgb . relu(view layer) in the
+//     last epilogue; the per-ray part of the view layer (view PE + frame code, 155 inputs) arrives as a per-ray
+//     128-vector computed once per ray (ray_bias kernel).
+#include "common.cuh"
+
+namespace danbo {
+namespace mlp {
+
+constexpr int kStages = 9;
+constexpr int kStageBytes = 128 * 64 * 2;          // 16 KB
+constexpr int kXBytes = DANBO_X_TILE_BYTES;        // 64 KB
+constexpr int kNumHeadFloats = 9 * 256 + 256 + 3 * 128 + 4;   // biases L0..L8, w_alpha, W_rgb, b_alpha, b_rgb[3]
+constexpr int kThreads = 192;
+
+// TMEM column map
+constexpr uint32_t kAccCol = 0;        // + 128*h
+constexpr uint32_t kActCol = 256;      // + 128*buf
+
+// stages consumed per tile (full / density-only)
+__host__ __device__ constexpr int stages_per_tile(bool full) { return full ? 84 : 72; }
+
+struct __align__(1024) Smem {
+    uint8_t x[kXBytes];
+    uint8_t w[kStages][kStageBytes];
+    float heads[kNumHeadFloats + 4];
+    uint64_t w_full[kStages];
+    uint64_t w_empty[kStages];
+    uint64_t x_full, x_empty;
+    uint64_t acc_full[2];
+    uint64_t act_ready[2];
+    uint32_t tmem_base;
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+    uint32_t addr = smem_u32(b);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(addr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T
+__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]^T
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand descriptor: start>>4 | LBO=1 | SBO=1024>>4 | version=1 (sm100) | SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=128
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&p);
+}
+
+// Layer plan (L = 0..9): 0 = pts_linears.0 (A = X), 1-4, 5 = skip layer (A = [X ; act]), 6, 7, 8 = feature_linear,
+// 9 = views_linears.0 (feature part; N = 128).
+__device__ __forceinline__ int n_halves(int L) { return L == 9 ? 1 : 2; }
+__device__ __forceinline__ bool uses_x(int L) { return L == 0 || L == 5; }
+__device__ __forceinline__ bool uses_act(int L) { return L != 0; }
+
+template <bool kFull>
+__global__ void __launch_bounds__(kThreads, 1)
+mlp_kernel(const uint8_t* __restrict__ xtiles,       // [tiles][64 KB] swizzled bf16 X tiles
+           const uint8_t* __restrict__ wstream,      // [84|72][16 KB] packed weight stages
+           const float* __restrict__ heads,          // kNumHeadFloats
+           const float* __restrict__ ray_bias,       // [n_rays][128] (full mode)
+           const int* __restrict__ row_sample,       // [rows] destination sample id of every row
+           const int* __restrict__ row_ray,          // [rows] ray of every row (full mode)
+           const int* __restrict__ n_rows_ptr,       // device scalar: number of valid rows
+           float* __restrict__ out,                  // full: raw [*,4]; density: sigma [*]
+           int out_capacity) {
+    extern __shared__ uint8_t smem_raw[];
+    Smem& S = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_rows = *n_rows_ptr;
+    const int n_tiles = (n_rows + DANBO_TILE_M - 1) / DANBO_TILE_M;
+    constexpr int kLayers = kFull ? 10 : 8;
+
+    for (int i = threadIdx.x; i < kNumHeadFloats; i += kThreads) S.heads[i] = heads[i];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&S.w_full[s], 1); mbar_init(&S.w_empty[s], 1); }
+        mbar_init(&S.x_full, 1); mbar_init(&S.x_empty, 1);
+        mbar_init(&S.acc_full[0], 1); mbar_init(&S.acc_full[1], 1);
+        mbar_init(&S.act_ready[0], 4); mbar_init(&S.act_ready[1], 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = S.tmem_base;
+
+    if (warp == 0) {
+        // ===== producer: X tile + weight stages =====
+        if (lane == 0) {
+            uint32_t ws = 0, wphase = 0, xphase = 0;
+            for (int t = blockIdx.x, it = 0; t < n_tiles; t += gridDim.x, ++it) {
+                if (it > 0) { mbar_wait(&S.x_empty, xphase); xphase ^= 1; }
+                mbar_expect_tx(&S.x_full, kXBytes);
+                const uint8_t* xs = xtiles + (size_t)t * kXBytes;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) bulk_g2s(S.x + c * 16384, xs + c * 16384, 16384, &S.x_full);
+                for (int s = 0; s < stages_per_tile(kFull); ++s) {
+                    mbar_wait(&S.w_empty[ws], wphase ^ 1);
+                    mbar_expect_tx(&S.w_full[ws], kStageBytes);
+                    bulk_g2s(S.w[ws], wstream + (size_t)s * kStageBytes, kStageBytes, &S.w_full[ws]);
+                    if (++ws == kStages) { ws = 0; wphase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            uint32_t ws = 0, wphase = 0, xphase = 0, r0 = 0, r1 = 0;
+            const uint32_t x_base = smem_u32(S.x);
+            for (int t = blockIdx.x, it = 0; t < n_tiles; t += gridDim.x, ++it) {
+                mbar_wait(&S.x_full, xphase); xphase ^= 1;
+                if (it > 0) {                                                   // accumulators drained by the last epilogues
+                    mbar_wait(&S.act_ready[0], r0 & 1); ++r0;
+                    if (!kFull) { mbar_wait(&S.act_ready[1], r1 & 1); ++r1; }    // density-only ends on a two-half layer
+                }
+                tc_fence_after();
+                for (int L = 0; L < kLayers; ++L) {
+                    if (L > 0) { mbar_wait(&S.act_ready[0], r0 & 1); ++r0; tc_fence_after(); }
+                    bool got_r1 = (L == 0);
+                    const uint32_t act_in = tmem + kActCol + 128u * ((L - 1) & 1);
+                    for (int h = 0; h < n_halves(L); ++h) {
+                        const uint32_t d = tmem + kAccCol + 128u * h;
+                        uint32_t accum = 0;
+                        const int n_xc = uses_x(L) ? 4 : 0;
+                        const int n_chunks = n_xc + (uses_act(L) ? 4 : 0);
+                        for (int c = 0; c < n_chunks; ++c) {
+                            const bool is_x = c < n_xc;
+                            const int kc = is_x ? c : c - n_xc;
+                            if (!is_x && kc == 2 && !got_r1) {
+                                mbar_wait(&S.act_ready[1], r1 & 1); ++r1; tc_fence_after(); got_r1 = true;
+                            }
+                            mbar_wait(&S.w_full[ws], wphase);
+                            tc_fence_after();
+                            const uint32_t b_base = smem_u32(S.w[ws]);
+                            const int nk = (is_x && kc == 3) ? 1 : 4;             // K = 208: last X chunk holds one k-step
+#pragma unroll 1
+                            for (int j = 0; j < nk; ++j) {
+                                const uint64_t bdesc = make_desc(b_base + j * 32);
+                                if (is_x) mma_ss(d, make_desc(x_base + kc * 16384 + j * 32), bdesc, kIdesc, accum);
+                                else      mma_ts(d, act_in + kc * 32 + j * 8, bdesc, kIdesc, accum);
+                                accum = 1;
+                            }
+                            tc_commit(&S.w_empty[ws]);
+                            if (++ws == kStages) { ws = 0; wphase ^= 1; }
+                            if (L == 5 && h == 1 && is_x && kc == 3) tc_commit(&S.x_empty);   // X no longer needed
+                        }
+                        tc_commit(&S.acc_full[h]);
+                    }
+                }
+            }
+        }
+    } else {
+        // ===== epilogue warps 2..5 =====
+        const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const float* bias = S.heads;                  // [9][256]
+        const float* w_alpha = S.heads + 9 * 256;     // [256]
+        const float* w_rgb = w_alpha + 256;           // [3][128]
+        const float* tail = w_rgb + 3 * 128;          // b_alpha, b_rgb[3]
+        uint32_t f0 = 0, f1 = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const int grow = t * DANBO_TILE_M + row;
+            const bool valid = grow < n_rows;
+            const int sample = valid ? row_sample[grow] : -1;
+            const int ray = (kFull && valid) ? row_ray[grow] : 0;
+            float alpha = tail[0];
+            float rgb[3] = {tail[1], tail[2], tail[3]};
+            for (int L = 0; L < kLayers; ++L) {
+                for (int h = 0; h < n_halves(L); ++h) {
+                    if (h == 0) { mbar_wait(&S.acc_full[0], f0 & 1); ++f0; }
+                    else        { mbar_wait(&S.acc_full[1], f1 & 1); ++f1; }
+                    tc_fence_after();
+                    const uint32_t acc = tmem + lane_addr + kAccCol + 128u * h;
+                    const uint32_t act_out = tmem + lane_addr + kActCol + 128u * (L & 1) + 64u * h;
+#pragma unroll 1
+                    for (int g = 0; g < 4; ++g) {
+                        uint32_t v[32];
+                        tmem_ld32(acc + 32 * g, v);
+                        tmem_wait_ld();
+                        const int col0 = h * 128 + g * 32;
+                        if (L < 9) {
+                            const float4* b4 = reinterpret_cast<const float4*>(bias + L * 256 + col0);
+                            uint32_t pk[16];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float4 b = b4[i];
+                                float a0 = __uint_as_float(v[4 * i + 0]) + b.x;
+                                float a1 = __uint_as_float(v[4 * i + 1]) + b.y;
+                                float a2 = __uint_as_float(v[4 * i + 2]) + b.z;
+                                float a3 = __uint_as_float(v[4 * i + 3]) + b.w;
+                                if (L < 8) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
+                                if (L == 7) {
+                                    const float4 wa = *reinterpret_cast<const float4*>(w_alpha + col0 + 4 * i);
+                                    alpha = fmaf(a0, wa.x, alpha); alpha = fmaf(a1, wa.y, alpha);
+                                    alpha = fmaf(a2, wa.z, alpha); alpha = fmaf(a3, wa.w, alpha);
+                                }
+                                pk[2 * i] = pack_bf16(a0, a1);
+                                pk[2 * i + 1] = pack_bf16(a2, a3);
+                            }
+                            if (kFull || L < 7) tmem_st16(act_out + 16 * g, pk);
+                        } else {
+                            const float4* b4 = reinterpret_cast<const float4*>(ray_bias + (size_t)ray * 128 + g * 32);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float4 b = __ldg(b4 + i);
+                                const float a[4] = {fmaxf(__uint_as_float(v[4 * i + 0]) + b.x, 0.f),
+                                                    fmaxf(__uint_as_float(v[4 * i + 1]) + b.y, 0.f),
+                                                    fmaxf(__uint_as_float(v[4 * i + 2]) + b.z, 0.f),
+                                                    fmaxf(__uint_as_float(v[4 * i + 3]) + b.w, 0.f)};
+#pragma unroll
+                                for (int k = 0; k < 3; ++k) {
+                                    const float4 w = *reinterpret_cast<const float4*>(w_rgb + k * 128 + g * 32 + 4 * i);
+                                    rgb[k] = fmaf(a[0], w.x, rgb[k]); rgb[k] = fmaf(a[1], w.y, rgb[k]);
+                                    rgb[k] = fmaf(a[2], w.z, rgb[k]); rgb[k] = fmaf(a[3], w.w, rgb[k]);
+                                }
+                            }
+                        }
+                    }
+                    tmem_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&S.act_ready[h]);
+                }
+            }
+            if (sample >= 0 && sample < out_capacity) {
+                if (kFull) *reinterpret_cast<float4*>(out + (size_t)sample * 4) = make_float4(rgb[0], rgb[1], rgb[2], alpha);
+                else out[sample] = alpha;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
+// -----------------------------------------------------------------------------------------------------------
+// Weight packing: fp32 nn.Linear weights (out,in) -> bf16 stage stream in consumption order + fp32 head vector.
+// One thread per bf16 element of the stream.
+struct PackArgs {
+    const float* w[8];        // pts_linears.0..7 weight
+    const float* b[8];        // pts_linears.0..7 bias
+    const float* w_alpha; const float* b_alpha;
+    const float* w_feat;  const float* b_feat;
+    const float* w_view;      // (128, 411): [feature 256 | view PE 27 | code 128]
+    const float* b_view;
+    const float* w_rgb;   const float* b_rgb;
+};
+constexpr int kRayBiasFloats = 155 * 128 + 128;      // W_v[:, 256:411]^T (155,128) then b_v (128)
+
+// stage s of the per-tile stream -> (layer, half, is_x, kc)
+__host__ __device__ inline void stage_to_layer(int s, int& L, int& h, int& is_x, int& kc) {
+    const int per_layer[10] = {8, 8, 8, 8, 8, 16, 8, 8, 8, 4};
+    L = 0;
+    while (s >= per_layer[L]) { s -= per_layer[L]; ++L; }
+    const int per_half = (L == 5) ? 8 : 4;
+    h = s / per_half;
+    int c = s % per_half;
+    is_x = (L == 0) || (L == 5 && c < 4);
+    kc = (L == 5 && c >= 4) ? c - 4 : c;
+}
+
+__global__ void pack_weights_kernel(PackArgs a, __nv_bfloat16* __restrict__ wstream, float* __restrict__ heads,
+                                    float* __restrict__ wv_ray) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kRayBiasFloats; i += gridDim.x * blockDim.x) {
+        if (i < 155 * 128) { const int c = i / 128, o = i % 128; wv_ray[i] = a.w_view[(size_t)o * 411 + 256 + c]; }
+        else wv_ray[i] = a.b_view[i - 155 * 128];
+    }
+    const int total = 84 * 128 * 64;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int s = i / (128 * 64), e = i % (128 * 64);
+        const int n = e / 64, k = e % 64;
+        int L, h, is_x, kc;
+        stage_to_layer(s, L, h, is_x, kc);
+        const int out_row = h * 128 + n;
+        const int kin = kc * 64 + k;
+        float val = 0.f;
+        if (L <= 7) {
+            const int in_dim = (L == 0) ? DANBO_X_COLS : (L == 5 ? DANBO_X_COLS + 256 : 256);
+            if (L == 0) { if (kin < DANBO_X_COLS) val = a.w[0][(size_t)out_row * in_dim + kin]; }
+            else if (L == 5) {
+                if (is_x) { if (kin < DANBO_X_COLS) val = a.w[5][(size_t)out_row * in_dim + kin]; }
+                else val = a.w[5][(size_t)out_row * in_dim + DANBO_X_COLS + kin];
+            } else val = a.w[L][(size_t)out_row * in_dim + kin];
+        } else if (L == 8) {
+            val = a.w_feat[(size_t)out_row * 256 + kin];
+        } else {
+            val = a.w_view[(size_t)out_row * 411 + kin];          // out_row < 128 because h == 0
+        }
+        const uint32_t off = sw128_offset((uint32_t)n, (uint32_t)k);     // chunk index is 0 for k < 64
+        wstream[(size_t)s * (128 * 64) + off / 2] = __float2bfloat16_rn(val);
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kNumHeadFloats; i += gridDim.x * blockDim.x) {
+        float v;
+        if (i < 8 * 256) v = a.b[i / 256][i % 256];
+        else if (i < 9 * 256) v = a.b_feat[i - 8 * 256];
+        else if (i < 10 * 256) v = a.w_alpha[i - 9 * 256];
+        else if (i < 10 * 256 + 384) v = a.w_rgb[i - 10 * 256];
+        else if (i == 10 * 256 + 384) v = a.b_alpha[0];
+        else v = a.b_rgb[i - (10 * 256 + 385)];
+        heads[i] = v;
+    }
+}
+
+}  // namespace mlp
+}  // namespace danbo
+
+using namespace danbo;
+
+extern "C" int danbo_mlp_workspace_bytes(long long* wstream_bytes, long long* heads_bytes, long long* raybias_bytes) {
+    *wstream_bytes = 84LL * mlp::kStageBytes;
+    *heads_bytes = (long long)mlp::kNumHeadFloats * 4;
+    *raybias_bytes = (long long)mlp::kRayBiasFloats * 4;
+    return 0;
+}
+
+extern "C" int danbo_pack_mlp_weights(const float* const* w_pts, const float* const* b_pts, const float* w_alpha,
+                                      const float* b_alpha, const float* w_feat, const float* b_feat,
+                                      const float* w_view, const float* b_view, const float* w_rgb,
+                                      const float* b_rgb, void* wstream, float* heads, float* wv_ray, void* stream) {
+    mlp::PackArgs a;
+    for (int i = 0; i < 8; ++i) { a.w[i] = w_pts[i]; a.b[i] = b_pts[i]; }
+    a.w_alpha = w_alpha; a.b_alpha = b_alpha; a.w_feat = w_feat; a.b_feat = b_feat;
+    a.w_view = w_view; a.b_view = b_view; a.w_rgb = w_rgb; a.b_rgb = b_rgb;
+    mlp::pack_weights_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(a, (__nv_bfloat16*)wstream, heads, wv_ray);
+    DANBO_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int danbo_mlp_forward(const void* xtiles, const void* wstream, const float* heads, const float* ray_bias,
+                                 const int* row_sample, const int* row_ray, const int* n_rows_dev, int max_rows,
+                                 float* out, int out_capacity, int density_only, int num_sms, void* stream) {
+    if (max_rows <= 0) return 0;
+    const int smem = (int)sizeof(mlp::Smem) + 1024;
+    int max_tiles = (max_rows + DANBO_TILE_M - 1) / DANBO_TILE_M;
+    int grid = num_sms < max_tiles ? num_sms : max_tiles;
+    if (grid < 1) grid = 1;
+    cudaError_t e;
+    if (density_only) {
+        e = cudaFuncSetAttribute(mlp::mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        mlp::mlp_kernel<false><<<grid, mlp::kThreads, smem, (cudaStream_t)stream>>>(
+            (const uint8_t*)xtiles, (const uint8_t*)wstream, heads, ray_bias, row_sample, row_ray, n_rows_dev, out, out_capacity);
+    } else {
+        e = cudaFuncSetAttribute(mlp::mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        mlp::mlp_kernel<true><<<grid, mlp::kThreads, smem, (cudaStream_t)stream>>>(
+            (const uint8_t*)xtiles, (const uint8_t*)wstream, heads, ray_bias, row_sample, row_ray, n_rows_dev, out, out_capacity);
+    }
+    DANBO_CHECK_LAUNCH();
+    return 0;
+}

@@ -1,0 +1,238 @@
+"""Thin torch-side wrappers of the C ABI (include/danbo_b200.h): allocate outputs, pass raw pointers + sizes.
+
+Every function requires CUDA tensors and enqueues on torch's current stream.  There is no CPU path."""
+import ctypes
+import functools
+
+import torch
+
+from . import _lib
+
+J = 24
+TILE_M = 128
+X_TILE_BYTES = 128 * 256 * 2
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("danbo_b200 kernels need CUDA tensors; there is no CPU fallback for this path")
+
+
+@functools.lru_cache(maxsize=8)
+def num_sms(device_index):
+    return torch.cuda.get_device_properties(device_index).multi_processor_count
+
+
+@functools.lru_cache(maxsize=64)
+def _linspace01(S, device_index):
+    # torch's CPU linspace is the oracle's definition of t; S floats, cached per device
+    return torch.linspace(0., 1., steps=S).to(torch.device("cuda", device_index))
+
+
+def f32c(t):
+    return t.detach().to(torch.float32).contiguous()
+
+
+class FieldConsts:
+    """Device pointers to the ten constant tensors the field kernels read (see danbo_b200.h)."""
+
+    def __init__(self, align, axis_scale, agg):
+        self.tensors = [f32c(align), f32c(axis_scale), f32c(agg["w0"]), f32c(agg["adj_w"]), f32c(agg["adj"]),
+                        f32c(agg["b0"]), f32c(agg["w1"]), f32c(agg["b1"]), f32c(agg["w2"]), f32c(agg["b2"])]
+        _need_cuda(*self.tensors)
+        self.array = (ctypes.c_void_p * 10)(*[t.data_ptr() for t in self.tensors])
+
+    @property
+    def align(self):
+        return self.tensors[0]
+
+    @property
+    def axis_scale(self):
+        return self.tensors[1]
+
+
+def nearfar(rays, pose_cyl, pose_skts, rays_per_pose, align, axis_scale, seg_len=0, use_box=False, bound=1.3,
+            return_masks=False):
+    """NF1 (+NF2).  rays (n,>=8) contiguous; pose_cyl (G,>=3); pose_skts (G,24,4,4).  -> near (n), far (n)."""
+    _need_cuda(rays, pose_cyl, pose_skts, align, axis_scale)
+    lib = _lib.load()
+    n = rays.shape[0]
+    near = torch.empty(n, device=rays.device, dtype=torch.float32)
+    far = torch.empty_like(near)
+    n_seg = 1 if seg_len <= 0 else (n + seg_len - 1) // seg_len
+    acc = torch.empty(4 * max(n_seg, 1), device=rays.device, dtype=torch.float64)
+    pv = vv = None
+    if return_masks:
+        pv = torch.zeros(n, J, device=rays.device, dtype=torch.uint8)
+        vv = torch.zeros(n, J, device=rays.device, dtype=torch.uint8)
+    import numpy as np
+    bound_hi = float(np.float32(bound + 1e-4))        # torch compares the fp32 hits with fp32(bound_range + eps)
+    _lib.check(lib.danbo_nearfar(_p(rays), rays.stride(0), n, _p(pose_cyl), pose_cyl.stride(0), _p(pose_skts),
+                                 int(rays_per_pose), pose_skts.shape[0], _p(align), _p(axis_scale), int(seg_len),
+                                 int(bool(use_box)), float(bound), bound_hi, _p(near), _p(far), _p(acc), n_seg,
+                                 _p(pv), _p(vv), _stream()), "danbo_nearfar")
+    if return_masks:
+        return near, far, pv, vv
+    return near, far
+
+
+class ActiveList:
+    """Compacted ids of the samples at least one bone sees (+ one empty entry per ray in the coarse pass)."""
+
+    def __init__(self, capacity, device):
+        self.capacity = int(capacity)
+        self.ids = torch.empty(self.capacity, device=device, dtype=torch.int32)
+        self.count = torch.zeros(1, device=device, dtype=torch.int32)
+
+
+def sample_mask(rays, S, pose_skts, rays_per_pose, consts, near=None, far=None, t_rand=None, z_in=None,
+                append_empty=False, capacity=None):
+    """-> z (n,S), mask (n,S) uint32-as-int32, ActiveList."""
+    _need_cuda(rays, pose_skts, near, far, t_rand, z_in)
+    lib = _lib.load()
+    n = rays.shape[0]
+    dev = rays.device
+    cap = n * S + (n if append_empty else 0) if capacity is None else int(capacity)
+    active = ActiveList(max(cap, 1), dev)
+    mask = torch.empty(n, S, device=dev, dtype=torch.int32)
+    if z_in is None:
+        z = torch.empty(n, S, device=dev, dtype=torch.float32)
+        t_vals = _linspace01(S, dev.index if dev.index is not None else torch.cuda.current_device())
+        z_out = z
+    else:
+        z = z_in.contiguous()
+        t_vals, z_out = None, None
+    _lib.check(lib.danbo_sample_mask(_p(rays), rays.stride(0), n, S, _p(near), _p(far), _p(t_vals), _p(t_rand),
+                                     _p(z if z_in is not None else None), _p(z_out), _p(pose_skts),
+                                     int(rays_per_pose), pose_skts.shape[0], consts.array, _p(mask), _p(active.ids),
+                                     _p(active.count), active.capacity, int(append_empty), _stream()),
+               "danbo_sample_mask")
+    return z, mask, active
+
+
+def field_agg(rays, S, z, mask, active, pose_skts, pose_vol, rays_per_pose, consts, want_confd=False,
+              want_hbar=False):
+    """-> xtiles (uint8 tiles), row_ray (cap) int32, confd (n*S,24) or None, hbar (cap,16) or None."""
+    _need_cuda(rays, z, mask, pose_skts, pose_vol)
+    lib = _lib.load()
+    n = rays.shape[0]
+    dev = rays.device
+    n_tiles = (active.capacity + TILE_M - 1) // TILE_M
+    xtiles = torch.empty(n_tiles * X_TILE_BYTES, device=dev, dtype=torch.uint8)
+    row_ray = torch.empty(active.capacity, device=dev, dtype=torch.int32)
+    confd = torch.zeros(n * S, J, device=dev, dtype=torch.float32) if want_confd else None
+    hbar = torch.empty(active.capacity, 16, device=dev, dtype=torch.float32) if want_hbar else None
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    _lib.check(lib.danbo_field_agg(_p(rays), rays.stride(0), n, S, _p(z), _p(mask), _p(active.ids), _p(active.count),
+                                   active.capacity, _p(pose_skts), _p(pose_vol), int(rays_per_pose),
+                                   pose_skts.shape[0], consts.array, _p(xtiles), _p(row_ray), _p(confd), _p(hbar),
+                                   num_sms(idx), _stream()), "danbo_field_agg")
+    return xtiles, row_ray, confd, hbar
+
+
+class PackedMLP:
+    """bf16 stage stream + fp32 heads + per-ray view slice, packed from the module's fp32 nn.Linear weights."""
+
+    def __init__(self, device):
+        lib = _lib.load()
+        a, b, c = ctypes.c_longlong(), ctypes.c_longlong(), ctypes.c_longlong()
+        lib.danbo_mlp_workspace_bytes(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+        self.wstream = torch.empty(a.value, device=device, dtype=torch.uint8)
+        self.heads = torch.empty(b.value // 4, device=device, dtype=torch.float32)
+        self.wv_ray = torch.empty(c.value // 4, device=device, dtype=torch.float32)
+        self.key = None
+
+    def pack(self, P):
+        """P: mapping with the reference's names (pts_linears.i.weight ...) -> fp32 CUDA tensors."""
+        lib = _lib.load()
+        ws = [f32c(P[f"pts_linears.{i}.weight"]) for i in range(8)]
+        bs = [f32c(P[f"pts_linears.{i}.bias"]) for i in range(8)]
+        others = [f32c(P[k]) for k in ("alpha_linear.weight", "alpha_linear.bias", "feature_linear.weight",
+                                       "feature_linear.bias", "views_linears.0.weight", "views_linears.0.bias",
+                                       "rgb_linear.weight", "rgb_linear.bias")]
+        _need_cuda(*ws, *bs, *others)
+        wa = (ctypes.c_void_p * 8)(*[t.data_ptr() for t in ws])
+        ba = (ctypes.c_void_p * 8)(*[t.data_ptr() for t in bs])
+        _lib.check(lib.danbo_pack_mlp_weights(wa, ba, *[_p(t) for t in others], _p(self.wstream), _p(self.heads),
+                                              _p(self.wv_ray), _stream()), "danbo_pack_mlp_weights")
+        self._keep = (ws, bs, others)          # keep sources alive until the stream has consumed them
+        return self
+
+
+def ray_bias(rays, cam_idx, codes_with_mean, packed):
+    """-> (n,128).  codes_with_mean (n_codes+1,128): last row = mean code (used when cam_idx < 0)."""
+    _need_cuda(rays, cam_idx, codes_with_mean)
+    lib = _lib.load()
+    n = rays.shape[0]
+    out = torch.empty(n, 128, device=rays.device, dtype=torch.float32)
+    _lib.check(lib.danbo_ray_bias(_p(rays), rays.stride(0), n, _p(cam_idx), _p(codes_with_mean),
+                                  codes_with_mean.shape[0] - 1, _p(packed.wv_ray), _p(out), _stream()), "danbo_ray_bias")
+    return out
+
+
+def mlp_forward(xtiles, packed, rbias, active, row_ray, out, density_only=False):
+    """Runs the fused MLP over the active rows; row r is written to out[active.ids[r]]."""
+    lib = _lib.load()
+    dev = xtiles.device
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    _lib.check(lib.danbo_mlp_forward(_p(xtiles), _p(packed.wstream), _p(packed.heads), _p(rbias), _p(active.ids),
+                                     _p(row_ray), _p(active.count), active.capacity, _p(out),
+                                     out.shape[0] if not density_only else out.numel(), int(bool(density_only)),
+                                     num_sms(idx), _stream()), "danbo_mlp_forward")
+    return out
+
+
+def composite_resample(rays, S, S_f, raw, mask, z, noise=None, inv_B=1.0, u_rand=None, want_inds=False):
+    """C1 + R1 on the coarse samples.  raw (n*S+n,4).  -> dict."""
+    _need_cuda(rays, raw, mask, z, noise, u_rand)
+    lib = _lib.load()
+    n = rays.shape[0]
+    dev = rays.device
+    f = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+    out = {"weights": f(n, S), "alpha": f(n, S), "rgb_map": f(n, 3), "disp_map": f(n), "acc_map": f(n)}
+    u_vals = None
+    if S_f > 0:
+        out["z_samples"], out["z_all"] = f(n, S_f), f(n, S + S_f)
+        out["order"] = torch.empty(n, S + S_f, device=dev, dtype=torch.int32)
+        if want_inds:
+            out["inds"] = torch.empty(n, S_f, device=dev, dtype=torch.int32)
+        if u_rand is None:
+            u_vals = _linspace01(S_f, dev.index if dev.index is not None else torch.cuda.current_device())
+    _lib.check(lib.danbo_composite_resample(_p(rays), rays.stride(0), n, S, S_f, _p(raw), _p(mask), _p(z), _p(noise),
+                                            float(inv_B), _p(u_vals), _p(u_rand), _p(out["weights"]), _p(out["alpha"]),
+                                            _p(out["rgb_map"]), _p(out["disp_map"]), _p(out["acc_map"]),
+                                            _p(out.get("z_samples")), _p(out.get("z_all")), _p(out.get("order")),
+                                            _p(out.get("inds")), _stream()), "danbo_composite_resample")
+    return out
+
+
+def merge_composite(rays, S_c, S_f, raw0, mask0, raw1, mask1, z_all, order, noise=None, inv_B=1.0, want_raw=False,
+                    confd0=None, confd1=None, want_invalid=False):
+    """R2 + C1 on the merged samples -> dict (rgb_map, disp_map, acc_map, alpha, weights [, raw, confd, part_invalid])."""
+    lib = _lib.load()
+    n = rays.shape[0]
+    dev = rays.device
+    St = S_c + S_f
+    f = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+    out = {"weights": f(n, St), "alpha": f(n, St), "rgb_map": f(n, 3), "disp_map": f(n), "acc_map": f(n)}
+    if want_raw:
+        out["raw"] = f(n, St, 4)
+    if confd0 is not None:
+        out["confd"] = f(n, St, J)
+    if want_invalid:
+        out["part_invalid"] = f(n, St, J)
+    _lib.check(lib.danbo_merge_composite(_p(rays), rays.stride(0), n, S_c, S_f, _p(raw0), _p(mask0), _p(raw1), _p(mask1),
+                                         _p(z_all), _p(order), _p(noise), float(inv_B), _p(out["weights"]),
+                                         _p(out["alpha"]), _p(out["rgb_map"]), _p(out["disp_map"]), _p(out["acc_map"]),
+                                         _p(out.get("raw")), _p(confd0), _p(confd1), _p(out.get("confd")),
+                                         _p(out.get("part_invalid")), _stream()), "danbo_merge_composite")
+    return out

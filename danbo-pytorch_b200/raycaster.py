@@ -1,0 +1,339 @@
+"""Drop-in mirror of the reference's ray caster for the DANBO hot path.
+
+Same class surface as core/raycasters.py:205-716 (RayCaster / GraphCaster): construction through
+`create_raycaster(args, data_attrs)`, `forward(*args, fwd_type=..., **kwargs)`, `render_rays(...)` with the
+reference's argument names, `render_mesh_density`, `render_pts_density`, the custom `state_dict` key scheme
+(`network_fn_state_dict`, `network_fine_state_dict`), `.network`, `.network_fine`, `.transforms`, `.rest_poses`,
+`update_embed_fns`, `get_networks`.  The work itself is a fixed sequence of CUDA kernels from libdanbo_b200.so.
+
+Unsupported flag combinations raise NotImplementedError (never a silent fallback).
+"""
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import kernels as K
+from . import skeleton as sk
+from .networks import DanboField
+
+MAX_RAYS_PER_LAUNCH = 131072          # multiple of every sane `chunk`; bounds the size of the X tile buffer
+
+
+class RayCaster(nn.Module):
+    """GraphCaster of the reference (raycasters.py:642-716) on B200 kernels."""
+
+    def __init__(self, network, network_fine=None, single_net=True, rest_poses=None, align_bones="align",
+                 skel_type=None, use_volume_near_far=False, **kwargs):
+        super().__init__()
+        if not single_net or (network_fine is not None and network_fine is not network):
+            raise NotImplementedError("single_net=False (separate fine network) is not implemented; every DANBO "
+                                      "config ships single_net=True")
+        if align_bones != "align":
+            raise NotImplementedError(f"align_bones={align_bones!r}: only 'align' is implemented")
+        self.network = network
+        self.network_fine = network
+        self.single_net = True
+        self.rest_poses = rest_poses
+        self.skel_type = skel_type if skel_type is not None else sk.SMPLSkeleton
+        self.align_bones = align_bones
+        self.use_volume_near_far = bool(use_volume_near_far)
+        A, child = sk.bone_align_transforms(rest_poses)          # S0
+        self.transforms = torch.from_numpy(A)[None]               # (1,24,4,4) like the reference attribute
+        self.child_idxs = child
+        self._packed = None
+        self._packed_key = None
+
+    # ------------------------------------------------------------------------------------------------ dispatch
+    def forward(self, *args, fwd_type="", **kwargs):
+        if fwd_type == "density":
+            return self.render_pts_density(*args, **kwargs)
+        if fwd_type == "mesh":
+            return self.render_mesh_density(*args, **kwargs)
+        if fwd_type == "density_color":
+            raise NotImplementedError("fwd_type='density_color' is broken in the reference (render_pts_density has no "
+                                      "`color` argument, raycasters.py:236-237)")
+        if not self.training:
+            with torch.no_grad():
+                return self.render_rays(*args, **kwargs)
+        return self.render_rays(*args, **kwargs)
+
+    def get_networks(self):
+        return self.network, self.network_fine
+
+    def update_embed_fns(self, global_step, args):
+        self.network.update_embed_fns(global_step, args)
+
+    # custom key scheme of raycasters.py:601-637
+    def state_dict(self, *args, **kwargs):
+        sd = self.network.state_dict()
+        return {"network_fn_state_dict": sd, "network_fine_state_dict": sd}
+
+    def load_state_dict(self, ckpt, strict=True):
+        sd = ckpt["network_fn_state_dict"] if "network_fn_state_dict" in ckpt else ckpt
+        own = self.network.state_dict()
+        try:
+            self.network.load_state_dict(sd, strict=strict)
+        except (KeyError, RuntimeError):
+            filt = {k: v for k, v in sd.items() if k in own and tuple(own[k].shape) == tuple(v.shape)}
+            self.network.load_state_dict(filt, strict=False)
+        self._packed_key = None
+
+    # ------------------------------------------------------------------------------------------------ helpers
+    def _device(self):
+        return self.network.alpha_linear.weight.device
+
+    def _consts(self):
+        net = self.network
+        dev = self._device()
+        return K.FieldConsts(self.transforms[0].to(dev), net.graph_net.axis_scale, net.agg_tensors())
+
+    def _packed_mlp(self):
+        net = self.network
+        names = [f"pts_linears.{i}.{w}" for i in range(8) for w in ("weight", "bias")] + [
+            "alpha_linear.weight", "alpha_linear.bias", "feature_linear.weight", "feature_linear.bias",
+            "views_linears.0.weight", "views_linears.0.bias", "rgb_linear.weight", "rgb_linear.bias"]
+        P = dict(net.named_parameters())
+        key = tuple((P[n].data_ptr(), P[n]._version) for n in names)
+        if self._packed is None or self._packed.wstream.device != self._device():
+            self._packed = K.PackedMLP(self._device())
+            self._packed_key = None
+        if key != self._packed_key:
+            self._packed.pack({n: P[n] for n in names})
+            self._packed_key = key
+        return self._packed
+
+    def _codes_with_mean(self):
+        w = self.network.framecodes.codes.weight.detach()
+        return torch.cat([w, w.mean(0, keepdim=True)], 0).contiguous()
+
+    @staticmethod
+    def _unique(t, skip):
+        return t[::skip].contiguous().float()
+
+    # ------------------------------------------------------------------------------------------------ render
+    def render_rays(self, ray_batch, N_samples, kp_batch, skts=None, cyls=None, bones=None, cams=None,
+                    subject_idxs=None, retraw=False, lindisp=False, perturb=0., N_importance=0, network_fine=None,
+                    raw_noise_std=0., ray_noise_std=0., verbose=False, ext_scale=0.001, pytest=False, N_uniques=1,
+                    render_confd=False, render_entropy=False, preproc_kwargs=None, netchunk=1024 * 64,
+                    nerf_type="danbo", use_viewdirs=True, nanmean_chunk=None, _rand=None, _stages=None):
+        """Same arguments and returned dict as raycasters.py:245-377,516-546,710-716.
+
+        Extra (optional) keywords: `nanmean_chunk` keeps the reference's per-chunk near/far fill (F8) when more than
+        one reference chunk is passed in a single call; `_rand`/`_stages` are test hooks (inject the four random
+        tensors / collect stage tensors)."""
+        if lindisp or ray_noise_std > 0 or render_confd or render_entropy or pytest:
+            raise NotImplementedError("lindisp / ray_noise_std / render_confd / render_entropy / pytest are not implemented")
+        if N_importance <= 0:
+            raise NotImplementedError("N_importance must be > 0 (the reference itself requires it, SURVEY F10)")
+        if skts is None or bones is None or cyls is None or cams is None:
+            raise ValueError("skts, bones, cyls and cams are required")
+        pk = preproc_kwargs or {}
+        if pk.get("density_fn", F.relu) is not F.relu:
+            raise NotImplementedError("density_type other than 'relu' is not implemented")
+        B = float(pk.get("density_scale", 1.0))
+        dev = self._device()
+        N = ray_batch.shape[0]
+        skip = max(N // max(int(N_uniques), 1), 1)
+        rays = ray_batch.to(dev, non_blocking=True).float().contiguous()
+        pose_skts = self._unique(skts, skip).to(dev, non_blocking=True)
+        pose_bones = self._unique(bones, skip).to(dev, non_blocking=True)
+        pose_cyls = self._unique(cyls, skip).to(dev, non_blocking=True)
+        cam_idx = cams.reshape(N, -1)[:, 0].to(dev, non_blocking=True).to(torch.int32).contiguous()
+
+        net = self.network
+        consts = self._consts()
+        packed = self._packed_mlp()
+        vol = net.bone_volumes(pose_bones).float().contiguous()            # GN1 + GN2 (PyTorch, <= 16 poses)
+        codes = self._codes_with_mean()
+        training = self.training
+        rand = _rand or {}
+        if training and perturb > 0 and "t_rand" not in rand:
+            # the reference's draw order (SURVEY §7 hard part 4): rand, randn, rand, randn
+            S_t = N_samples + N_importance
+            rand = {"t_rand": torch.rand(N, N_samples, device=dev),
+                    "noise0": torch.randn(N, N_samples, device=dev), "u": torch.rand(N, N_importance, device=dev),
+                    "noise1": torch.randn(N, S_t, device=dev)}
+        outs = []
+        for s0 in range(0, N, MAX_RAYS_PER_LAUNCH):
+            s1 = min(N, s0 + MAX_RAYS_PER_LAUNCH)
+            sub_rand = {k: v[s0:s1].to(dev).contiguous() for k, v in rand.items()}
+            outs.append(self._render_block(rays[s0:s1], s0, skip, pose_skts, pose_cyls, vol, cam_idx[s0:s1], codes,
+                                           consts, packed, N_samples, N_importance, B, raw_noise_std, perturb,
+                                           training, nanmean_chunk, sub_rand, _stages))
+        if len(outs) == 1:
+            return outs[0]
+        return {k: torch.cat([o[k] for o in outs], 0) for k in outs[0]}
+
+    def _render_block(self, rays, ray0, skip, pose_skts, pose_cyls, vol, cam_idx, codes, consts, packed, S_c, S_f, B,
+                      raw_noise_std, perturb, training, nanmean_chunk, rand, stages):
+        n = rays.shape[0]
+        # poses of this block: ray (ray0 + i) -> pose (ray0 + i) // skip.  Blocks start on pose boundaries whenever
+        # skip divides MAX_RAYS_PER_LAUNCH or there is a single pose; otherwise shift the tables.
+        p0 = ray0 // skip
+        if ray0 % skip != 0:
+            raise NotImplementedError("rays_per_pose must divide the internal launch size")
+        p_skts, p_cyls, p_vol = pose_skts[p0:], pose_cyls[p0:], vol[p0:]
+        seg = 0 if not nanmean_chunk else int(nanmean_chunk)
+        near, far = K.nearfar(rays, p_cyls, p_skts, skip, consts.align, consts.axis_scale, seg_len=seg,
+                              use_box=self.use_volume_near_far, bound=1.3)
+        rbias = K.ray_bias(rays, cam_idx, codes, packed)
+        inv_B = 1.0 / B
+        # ---- coarse pass
+        t_rand = rand.get("t_rand") if (training and perturb > 0) or "t_rand" in rand else None
+        z0, mask0, act0 = K.sample_mask(rays, S_c, p_skts, skip, consts, near=near, far=far, t_rand=t_rand,
+                                        append_empty=True)
+        xt0, rr0, confd0, _ = K.field_agg(rays, S_c, z0, mask0, act0, p_skts, p_vol, skip, consts, want_confd=training)
+        raw0 = torch.empty(n * S_c + n, 4, device=rays.device, dtype=torch.float32)
+        K.mlp_forward(xt0, packed, rbias, act0, rr0, raw0)
+        noise0 = (rand["noise0"] * (raw_noise_std * B)).contiguous() if ("noise0" in rand and raw_noise_std > 0) else None
+        c0 = K.composite_resample(rays, S_c, S_f, raw0, mask0, z0, noise=noise0, inv_B=inv_B, u_rand=rand.get("u"),
+                                  want_inds=stages is not None)
+        # ---- fine pass: only the S_f new samples go through the field (single_net)
+        z1, mask1, act1 = K.sample_mask(rays, S_f, p_skts, skip, consts, z_in=c0["z_samples"], append_empty=False)
+        xt1, rr1, confd1, _ = K.field_agg(rays, S_f, z1, mask1, act1, p_skts, p_vol, skip, consts, want_confd=training)
+        raw1 = torch.empty(n * S_f, 4, device=rays.device, dtype=torch.float32)
+        K.mlp_forward(xt1, packed, rbias, act1, rr1, raw1)
+        noise1 = (rand["noise1"] * (raw_noise_std * B)).contiguous() if ("noise1" in rand and raw_noise_std > 0) else None
+        c1 = K.merge_composite(rays, S_c, S_f, raw0, mask0, raw1, mask1, c0["z_all"], c0["order"], noise=noise1,
+                               inv_B=inv_B, want_raw=stages is not None, confd0=confd0, confd1=confd1,
+                               want_invalid=training)
+        ret = {"rgb_map": c1["rgb_map"], "disp_map": c1["disp_map"], "acc_map": c1["acc_map"], "alpha": c1["alpha"],
+               "T_i": c1["weights"], "rgb0": c0["rgb_map"], "disp0": c0["disp_map"], "acc0": c0["acc_map"],
+               "alpha0": c0["alpha"]}
+        if training:
+            ret["confd"] = c1["confd"]
+            ret["part_invalid"] = c1["part_invalid"]
+        if stages is not None:
+            stages.update({"near": near, "far": far, "vol": vol, "z_coarse": z0, "mask0": mask0, "raw0": raw0,
+                           "weights0": c0["weights"], "z_samples": c0["z_samples"], "z_all": c0["z_all"],
+                           "sorted_idxs": c0["order"], "inds": c0.get("inds"), "mask1": mask1, "raw1": raw1,
+                           "raw": c1.get("raw"), "n_active0": act0.count, "n_active1": act1.count,
+                           "ray_bias": rbias})
+        return ret
+
+    # ------------------------------------------------------------------------------------------------ density grid
+    @torch.no_grad()
+    def render_pts_density(self, pts, kps, skts, bones, netchunk=1024 * 64, network=None):
+        """Raw sigma at points (P,1,3) or (P,3) for ONE pose (raycasters.py:439-453, nerf.py:136-154)."""
+        assert kps.shape[0] == 1, f"Assuming only one poses are provided, got {kps.shape[0]} instead"
+        dev = self._device()
+        P = pts.shape[0]
+        p = pts.reshape(P, 3).to(dev).float()
+        rays = torch.zeros(P, 8, device=dev)                         # "rays" with o = point, d = 0, z = 0
+        rays[:, :3] = p
+        consts, packed = self._consts(), self._packed_mlp()
+        p_skts = skts.to(dev).float().contiguous()
+        vol = self.network.bone_volumes(bones.to(dev).float()).float().contiguous()
+        z = torch.zeros(P, 1, device=dev)
+        # append_empty=2: one extra entry (id 2P-1) carries sigma of a point that no bone sees (h = 0)
+        _, mask, act = K.sample_mask(rays, 1, p_skts, P, consts, z_in=z, append_empty=2, capacity=P + 1)
+        xt, rr, _, _ = K.field_agg(rays, 1, z, mask, act, p_skts, vol, P, consts)
+        sigma = torch.empty(2 * P, device=dev)
+        K.mlp_forward(xt, packed, None, act, rr, sigma, density_only=True)
+        out = torch.where(mask.reshape(-1) != 0, sigma[:P], sigma[2 * P - 1])
+        return out.reshape(P, 1, 1) if pts.dim() == 3 else out.reshape(P, 1)
+
+    @torch.no_grad()
+    def render_mesh_density(self, kps, skts, bones, subject_idxs=None, radius=1.0, res=64, render_kwargs=None,
+                            netchunk=1024 * 64, v=None):
+        """(res+1)^3 lattice of raw sigma around the root joint, x/y swapped (raycasters.py:421-437)."""
+        t = np.linspace(-radius, radius, res + 1)
+        grid = np.stack(np.meshgrid(t, t, t), axis=-1).astype(np.float32)
+        sh = grid.shape
+        pts = torch.tensor(grid.reshape(-1, 3)).to(self._device()) + kps[0, 0].to(self._device())
+        sigma = self.render_pts_density(pts.reshape(-1, 1, 3), kps, skts, bones, netchunk)[..., :1]
+        return sigma.reshape(*sh[:-1]).transpose(1, 0)
+
+
+GraphCaster = RayCaster
+
+
+# ------------------------------------------------------------------------------------------------------ factory
+_SUPPORTED = {"nerf_type": ("danbo", "graph"), "gnn_backbone": ("FGNNcat",), "agg_backbone": ("vox_MIXGNN",),
+              "agg_type": ("sigmoid",), "align_bones": ("align",), "density_type": ("relu",),
+              "kp_dist_type": ("reldist",), "view_type": ("identity",), "ray_tr_type": ("world",),
+              "pts_tr_type": ("local",), "bone_type": ("Nope",), "graph_input_type": ("rot6d",)}
+_REQUIRED = {"netdepth": 8, "netwidth": 256, "agg_W": 32, "agg_D": 3, "node_W": 128, "gcn_D": 4, "gcn_fc_D": 1,
+             "voxel_res": 16, "voxel_feat": 5, "multires_voxel": 6, "multires_graph": 5, "multires_views": 4,
+             "framecode_size": 128, "single_net": True, "opt_framecode": True, "use_viewdirs": True,
+             "mask_root": True, "attenuate_feat": True, "attenuate_invalid": False, "use_cutoff": False,
+             "lindisp": False, "opt_posecode": False, "gnn_concat": False, "no_adj": False, "adj_self_one": False,
+             "align_corners": False, "vol_cal_scale": True}
+
+
+def check_args(args):
+    """The flag subset that selects this path (SURVEY §8a 'config' row); anything else raises."""
+    for k, allowed in _SUPPORTED.items():
+        v = getattr(args, k, allowed[0])
+        if v not in allowed:
+            raise NotImplementedError(f"{k}={v!r} is not implemented by danbo_b200 (supported: {allowed})")
+    for k, want in _REQUIRED.items():
+        v = getattr(args, k, want)
+        if v != want:
+            raise NotImplementedError(f"{k}={v!r} is not implemented by danbo_b200 (kernels are built for {k}={want!r})")
+    if getattr(args, "netwidth_view", None) not in (None, 128):
+        raise NotImplementedError("netwidth_view must be None/128")
+
+
+def create_raycaster(args, data_attrs, device=None):
+    """Mirror of core/raycasters.py:17-143: returns (render_kwargs_train, render_kwargs_test, start, grad_vars,
+    optimizer, loaded_ckpt).  `render_kwargs_train['ray_caster']` exposes `.module` like nn.DataParallel does."""
+    check_args(args)
+    device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    skel_type = data_attrs.get("skel_type", sk.SMPLSkeleton)
+    rest_pose = np.asarray(data_attrs["rest_pose"], dtype=np.float32)
+    n_framecodes = data_attrs["n_views"] if getattr(args, "n_framecodes", None) is None else args.n_framecodes
+    profile = sk.skeleton_profile(rest_pose)
+    data_attrs["skel_profile"] = profile
+    net = DanboField(n_framecodes=n_framecodes, skel_profile=profile, opt_scale=bool(getattr(args, "opt_vol_scale", True)),
+                     agg_type=args.agg_type, mask_vol_prob=bool(getattr(args, "mask_vol_prob", True)))
+    caster = RayCaster(net, network_fine=net, single_net=True, rest_poses=rest_pose, align_bones=args.align_bones,
+                       skel_type=skel_type, use_volume_near_far=bool(getattr(args, "use_volume_near_far", False)))
+    caster.to(device)
+    grad_vars = [p for p in net.parameters() if p.requires_grad]
+    wd = getattr(args, "weight_decay", None)
+    if wd is None:
+        optimizer = torch.optim.Adam(params=grad_vars, lr=args.lrate, betas=(0.9, 0.999))
+    else:
+        optimizer = torch.optim.AdamW(params=grad_vars, lr=args.lrate, betas=(0.9, 0.999), weight_decay=wd)
+    start, loaded = 0, None
+    ft = getattr(args, "ft_path", None)
+    ckpts = []
+    if ft is not None and ft != "None":
+        ckpts = [ft]
+    else:
+        d = os.path.join(getattr(args, "basedir", "./logs"), getattr(args, "expname", ""))
+        if os.path.isdir(d):
+            ckpts = [os.path.join(d, f) for f in sorted(os.listdir(d)) if "tar" in f and "pose" not in f]
+    if ckpts and not getattr(args, "no_reload", False):
+        loaded = torch.load(ckpts[-1], map_location=device, weights_only=False)
+        caster.load_state_dict(loaded)
+        finetune = getattr(args, "finetune", False) or getattr(args, "finetune_light", False)
+        if not finetune:
+            start = loaded.get("global_step", 0)
+            if "optimizer_state_dict" in loaded:
+                optimizer.load_state_dict(loaded["optimizer_state_dict"])
+    kw_train = {"ray_caster": _ModuleHandle(caster), "perturb": args.perturb, "N_importance": args.N_importance,
+                "N_samples": args.N_samples, "use_viewdirs": args.use_viewdirs, "raw_noise_std": args.raw_noise_std,
+                "ray_noise_std": getattr(args, "ray_noise_std", 0.), "ext_scale": getattr(args, "ext_scale", 0.001),
+                "preproc_kwargs": {"density_scale": getattr(args, "density_scale", 1.0), "density_fn": F.relu},
+                "lindisp": False, "nerf_type": args.nerf_type}
+    kw_test = dict(kw_train)
+    kw_test.update({"ray_caster": caster, "perturb": False, "raw_noise_std": 0., "ray_noise_std": 0.})
+    optimizer.zero_grad()
+    return kw_train, kw_test, start, grad_vars, optimizer, loaded
+
+
+class _ModuleHandle(nn.Module):
+    """What the trainer expects where the reference wraps the caster in nn.DataParallel (raycasters.py:116):
+    callable, with `.module`.  One process drives one GPU here; multi-GPU is torch.distributed (parallel.py)."""
+
+    def __init__(self, module):
+        super().__init__()
+        self.module = module
+
+    def forward(self, *a, **k):
+        return self.module(*a, **k)

@@ -1,0 +1,106 @@
+/* danbo_b200.h -- C ABI of libdanbo_b200.so: the B200 (sm_100a) kernels of DANBO's per-sample body-field hot path.
+ *
+ * The reference (LemonATsu/DANBO-pytorch) has no FFI layer: its seam is the Python class RayCaster/GraphCaster
+ * (core/raycasters.py:205-716).  These entry points are what a binding for that path calls; each one names the
+ * reference code it replaces.  Conventions:
+ *   - every pointer is a DEVICE pointer (fp32 unless stated) owned by the caller; nothing is allocated here
+ *   - `stream` is a cudaStream_t passed as void*; entries only enqueue work and never synchronise
+ *   - return 0 on success, < 0 for invalid arguments, > 0 = cudaError_t of a failed launch
+ *   - re-entrant, no global mutable state
+ *   - rays: row-major (n_rays, ray_stride >= 8) = [o(3), d(3), near, far, ...]      (raycasters.py:302-306)
+ *   - poses: ray n uses pose min(n / rays_per_pose, n_poses-1); pose_skts is (n_poses,24,4,4) world->bone
+ *   - sample ids: id = ray*S + s; the extra id n_rays*S + ray is the ray's "sample that no bone sees"
+ */
+#ifndef DANBO_B200_H
+#define DANBO_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ABI version of this header (bumped on any signature change). */
+int danbo_version(void);
+
+/* NF1 + NF2.  get_near_far_in_cylinder (core/utils/ray_utils.py:294-346) followed, when use_box != 0, by
+ * GraphCaster.get_near_far / get_ray_box_intersections (core/raycasters.py:648-707, ray_utils.py:383-417):
+ * fp64 plane hits, a box counts only with exactly two hits inside +-(bound+1e-4) (bound_hi = fp32(bound+1e-4)).
+ * Rays that miss the cylinder take the nanmean of their segment of seg_len rays (the reference's chunk).
+ * seg_acc: workspace of 4*n_seg doubles.  p_valid/v_valid (n_rays,24) bytes are optional (may be NULL). */
+int danbo_nearfar(const float* rays, int ray_stride, int n_rays, const float* pose_cyl, int cyl_stride,
+                  const float* pose_skts, int rays_per_pose, int n_poses, const float* align, const float* axis_scale,
+                  int seg_len, int use_box, float bound, float bound_hi, float* near_out, float* far_out,
+                  double* seg_acc, int n_seg, unsigned char* p_valid, unsigned char* v_valid, void* stream);
+
+/* consts[10] = { align (24,4,4), axis_scale (24,3), prob_linears.layers.0.lin.weight (24,15,32),
+ *               .layers.0.adj_w (24,24), .layers.0.adj (24,24), .layers.0.bias (32), .layers.1.weight (24,32,32),
+ *               .layers.1.bias (24,32), .layers.2.weight (24,32), .layers.2.bias (24) }  (device pointers) */
+
+/* SM1 + T1/T2 + bone-visibility mask + compaction.
+ * sample_from_lineseg (ray_utils.py:206-253), transform_batch_pts (core/encoders.py:288-303), bone align
+ * (encoders.py:442-444), x/|axis_scale| and invalid = any(|x|>1) (core/networks/gnn_backbone.py:802-808).
+ * Coarse mode (z_in NULL): z = near(1-t)+far t with t_vals = linspace(0,1,S) (+ jitter t_rand (n,S) or NULL) -> z_out.
+ * Fine mode: z_in (n,S) given.  mask_out (n,S) gets bit j set when bone j sees the sample; ids of samples with a
+ * non-zero mask (and, with append_empty, one extra id per ray) are appended to active_ids at *active_count. */
+int danbo_sample_mask(const float* rays, int ray_stride, int n_rays, int S, const float* near, const float* far,
+                      const float* t_vals, const float* t_rand, const float* z_in, float* z_out,
+                      const float* pose_skts, int rays_per_pose, int n_poses, const float* const* consts,
+                      unsigned int* mask_out, int* active_ids, int* active_count, int capacity, int append_empty,
+                      void* stream);
+
+/* G1/G2 + A1-A3 + positional encoding for the active entries.
+ * FactorizeGNN.sample_from_volume / factorize_grid_sample (gnn_backbone.py:787-828, core/networks/misc.py:331-351),
+ * forward_blend -> MixGNN (core/networks/danbo.py:201-216, gnn_backbone.py:567-629), sigmoid blend weights
+ * (danbo.py:406-415), blend (danbo.py:299-300), Embedder (core/cutoff_embedder.py:62-73).
+ * pose_vol (n_poses,24,240) = graph-net output.  Writes bf16 rows into xtiles ((capacity+127)/128 tiles of 64 KB,
+ * swizzled MMA operand image), row_ray[row], and optionally confd (n_rays*S,24; visible bones only) and
+ * hbar (rows,16). */
+int danbo_field_agg(const float* rays, int ray_stride, int n_rays, int S, const float* z, const unsigned int* mask,
+                    const int* active_ids, const int* active_count, int capacity, const float* pose_skts,
+                    const float* pose_vol, int rays_per_pose, int n_poses, const float* const* consts, void* xtiles,
+                    int* row_ray, float* confd, float* hbar_out, int num_sms, void* stream);
+
+/* V1 folded into the view layer: out (n_rays,128) = W_v[:,256:411] . [PE(rays_d) ; frame code] + b_v
+ * (core/networks/nerf.py:252-279, core/networks/embedding.py:86-108).  codes is (n_codes+1,128) with the mean code in
+ * the last row (used for cam_idx < 0); wv_ray comes from danbo_pack_mlp_weights. */
+int danbo_ray_bias(const float* rays, int ray_stride, int n_rays, const int* cam_idx, const float* codes, int n_codes,
+                   const float* wv_ray, float* out, void* stream);
+
+/* Sizes of the packed-weight buffers below. */
+int danbo_mlp_workspace_bytes(long long* wstream_bytes, long long* heads_bytes, long long* raybias_bytes);
+
+/* fp32 nn.Linear weights -> bf16 tiled + swizzled stage stream, fp32 head vector and the transposed per-ray slice of
+ * views_linears.0.  Re-run after every optimizer step.  w_pts / b_pts are HOST arrays of 8 device pointers. */
+int danbo_pack_mlp_weights(const float* const* w_pts, const float* const* b_pts, const float* w_alpha,
+                           const float* b_alpha, const float* w_feat, const float* b_feat, const float* w_view,
+                           const float* b_view, const float* w_rgb, const float* b_rgb, void* wstream, float* heads,
+                           float* wv_ray, void* stream);
+
+/* M1: the 8x256 density MLP + feature/view/rgb heads (core/networks/nerf.py:164-209) as one persistent tcgen05
+ * kernel over 128-row tiles.  Row r of the tiles is written to out[row_sample[r]] (float4 rgb,sigma; or one float
+ * sigma when density_only, nerf.py:136-154).  *n_rows_dev rows are valid (device scalar, e.g. the active counter). */
+int danbo_mlp_forward(const void* xtiles, const void* wstream, const float* heads, const float* ray_bias,
+                      const int* row_sample, const int* row_ray, const int* n_rows_dev, int max_rows, float* out,
+                      int out_capacity, int density_only, int num_sms, void* stream);
+
+/* C1 + R1: raw2outputs (nerf.py:281-347) on the coarse samples, then isample_from_lineseg / sample_pdf
+ * (ray_utils.py:159-203,257-291) and the sorted merge order.  raw is (n_rays*S + n_rays,4); samples whose mask is 0
+ * read the ray's empty entry.  noise (n,S) already scaled, or NULL.  u_vals = linspace(0,1,S_f) (eval) or u_rand
+ * (n,S_f) (train).  order (n,S+S_f) int32 = sorted_idxs. */
+int danbo_composite_resample(const float* rays, int ray_stride, int n_rays, int S, int S_f, const float* raw,
+                             const unsigned int* mask, const float* z, const float* noise, float inv_B,
+                             const float* u_vals, const float* u_rand, float* weights, float* alpha, float* rgb0,
+                             float* disp0, float* acc0, float* z_samples, float* z_all, int* order, int* inds,
+                             void* stream);
+
+/* R2 + C1: merge coarse and fine raw by `order` (core/raycasters.py:484-514,745-761) and composite the merged ray.
+ * Optional training outputs: merged raw, confd and part_invalid (raycasters.py:710-716). */
+int danbo_merge_composite(const float* rays, int ray_stride, int n_rays, int S_c, int S_f, const float* raw0,
+                          const unsigned int* mask0, const float* raw1, const unsigned int* mask1, const float* z_all,
+                          const int* order, const float* noise, float inv_B, float* weights, float* alpha, float* rgb,
+                          float* disp, float* acc, float* raw_merged, const float* confd0, const float* confd1,
+                          float* confd_merged, float* invalid_merged, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,41 @@
+"""CPU checks of the drop-in boundary: the C-ABI library builds, loads, and exports every symbol the header declares."""
+import ctypes
+import os
+import re
+
+import danbo_b200
+from danbo_b200 import _lib, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "danbo_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\bint\s+(danbo_\w+)\s*\(", text)))
+
+
+def test_header_and_library_agree():
+    build.build()
+    lib = ctypes.CDLL(_lib.path())
+    syms = header_symbols()
+    assert len(syms) >= 10
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/danbo_b200.h but not exported"
+    assert sorted(_lib.EXPORTS) == syms, "ctypes signatures must cover exactly the header's entry points"
+    assert lib.danbo_version() == 1
+
+
+def test_kernels_refuse_cpu_tensors():
+    import pytest
+    import torch
+    with pytest.raises(RuntimeError):
+        danbo_b200.kernels.nearfar(torch.zeros(4, 8), torch.zeros(1, 5), torch.zeros(1, 24, 4, 4), 4,
+                                   torch.zeros(24, 4, 4), torch.ones(24, 3))
+
+
+def test_unsupported_flags_raise():
+    import pytest
+    for kw in ({"agg_type": "softmax"}, {"gnn_backbone": "PNBGNN"}, {"netwidth": 128}, {"nerf_type": "nerf"}):
+        with pytest.raises(NotImplementedError):
+            danbo_b200.raycaster.check_args(danbo_b200.make_args("danbo_base", **kw))

@@ -1,0 +1,308 @@
+"""GPU parity tests (run on the B200 box with -m gpu): every CUDA stage, called through the C ABI, against the CPU
+oracle on the same seeded inputs and against the reference-generated fixtures in tests/golden/.
+
+Tolerances (stated per SURVEY §8d): integer / mask outputs bit-exact except samples within 16 ulp of a box face
+(counted and required to be explained by the margin); fp32 stages 1e-5 of the tensor scale; the bf16 tensor-core
+MLP: raw within 3e-2 of the raw scale against the fp32 oracle and 2e-3 against a bf16-emulating restatement;
+rendered maps: mean abs error <= 4e-3."""
+import numpy as np
+import pytest
+import torch
+
+import danbo_oracle as orc
+from util import (load_fixture, params_for, align_A, pose_tensors, mask_mismatch_report, decode_xtiles, make_caster,
+                  preset_of, mlp_bf16_reference)
+
+pytestmark = pytest.mark.gpu
+RENDER = ["render_fast", "render_base", "render_fast_miss"]
+DEV = "cuda"
+
+
+def K():
+    import danbo_b200
+    return danbo_b200.kernels
+
+
+def close(a, b, tol=1e-5, what=""):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    scale = max(float(b.abs().max()), 1e-6)
+    err = float((a - b).abs().max())
+    assert err <= tol * scale + 1e-7, f"{what}: err {err:.3e} scale {scale:.3e}"
+
+
+def bits_to_invalid(mask):
+    m = mask.to(torch.int64).cpu() & 0xFFFFFF
+    j = torch.arange(24)
+    return 1.0 - ((m[..., None] >> j) & 1).float()
+
+
+def test_library_loads_and_version():
+    import danbo_b200
+    lib = danbo_b200._lib.load()
+    assert lib.danbo_version() == 1
+
+
+@pytest.mark.parametrize("name", RENDER)
+def test_nearfar(name):
+    fx = load_fixture(name)
+    caster, args, P = make_caster(preset_of(fx))
+    skts, bones, cyl = pose_tensors(fx)
+    rb = fx["ray_batch"].to(DEV)
+    consts = caster._consts()
+    near, far, pv, vv = K().nearfar(rb, cyl.to(DEV), skts.to(DEV).contiguous(), rb.shape[0], consts.align,
+                                    consts.axis_scale, use_box=bool(fx["use_volume_near_far"]), return_masks=True)
+    close(near, fx["st.near.0"].reshape(-1), 2e-6, "near")
+    close(far, fx["st.far.0"].reshape(-1), 2e-6, "far")
+    if fx["use_volume_near_far"]:
+        want_p = fx["st.p_valid.0"].bool()
+        got_p = ((pv.cpu().to(torch.int64)[..., None] >> torch.arange(6)) & 1).bool()
+        assert torch.equal(got_p, want_p), f"p_valid mismatches: {int((got_p != want_p).sum())}"
+        assert torch.equal(vv.cpu().bool(), fx["st.v_valid.0"].bool())
+
+
+@pytest.mark.parametrize("name", RENDER)
+def test_sample_mask_and_compaction(name):
+    fx = load_fixture(name)
+    caster, args, P = make_caster(preset_of(fx))
+    skts, _, _ = pose_tensors(fx)
+    rb = fx["ray_batch"].to(DEV)
+    N, S = rb.shape[0], int(fx["N_samples"])
+    consts = caster._consts()
+    z, mask, act = K().sample_mask(rb, S, skts.to(DEV).contiguous(), N, consts, near=fx["st.near.0"].reshape(-1).to(DEV),
+                                   far=fx["st.far.0"].reshape(-1).to(DEV), append_empty=True)
+    assert torch.equal(z.cpu(), fx["st.z.0"]), "coarse z must be bit-identical to the reference"
+    got_inv = bits_to_invalid(mask)
+    want_inv = fx["st.invalid.0"]
+    # margin-aware comparison: recompute x with the oracle for the margin
+    A = align_A()
+    pts = orc.ray_points(fx["ray_batch"][:, 0:3], fx["ray_batch"][:, 3:6], fx["st.z.0"])
+    pts_t = orc.world_to_bone(pts, skts.expand(N, -1, -1, -1), A)
+    x = pts_t / params_for(fx)["graph_net.axis_scale"].abs()
+    n_bad, n_explained = mask_mismatch_report(x, got_inv, want_inv)
+    assert n_bad == n_explained, f"{n_bad} mask mismatches, only {n_explained} within 16 ulp of a box face"
+    assert n_bad <= 4
+    n_act = int((mask != 0).sum()) + N
+    assert int(act.count.item()) == n_act
+    ids = act.ids[:n_act].cpu().long()
+    assert len(torch.unique(ids)) == n_act
+    flat = (mask.reshape(-1) != 0).cpu()
+    assert bool(flat[ids[ids < N * S]].all()) and int((ids >= N * S).sum()) == N
+
+
+@pytest.mark.parametrize("name", RENDER)
+@pytest.mark.parametrize("which", [0, 1])
+def test_field_agg(name, which):
+    """G1/G2/A1-A3 + PE on the golden sample positions against the oracle (fp32 hbar/confd, bf16 encoded rows)."""
+    fx = load_fixture(name)
+    caster, args, P = make_caster(preset_of(fx))
+    Pc = params_for(fx)
+    skts, bones, _ = pose_tensors(fx)
+    rb = fx["ray_batch"]
+    N = rb.shape[0]
+    z = fx["st.z.0"] if which == 0 else fx["st.z_samples.0"]
+    S = z.shape[1]
+    consts = caster._consts()
+    vol = fx["st.vol.0"].to(DEV).contiguous()
+    zg, mask, act = K().sample_mask(rb.to(DEV), S, skts.to(DEV).contiguous(), N, consts, z_in=z.to(DEV), append_empty=False)
+    xt, row_ray, confd, hbar = K().field_agg(rb.to(DEV), S, zg, mask, act, skts.to(DEV).contiguous(), vol, N, consts,
+                                             want_confd=True, want_hbar=True)
+    n_act = int(act.count.item())
+    ids = act.ids[:n_act].cpu().long()
+    # oracle on the same points
+    A = align_A()
+    pts = orc.ray_points(rb[:, 0:3], rb[:, 3:6], z)
+    pts_t = orc.world_to_bone(pts, skts.expand(N, -1, -1, -1), A)
+    h, invalid, x = orc.bone_features(pts_t, fx["st.vol.0"], Pc["graph_net.axis_scale"], rays_per_pose=N)
+    hf = h.reshape(N * S, 24, 15)
+    a = orc.agg_net(hf, Pc)
+    p = orc.agg_prob(a, invalid.reshape(N * S, 24))
+    hb = (hf * p[..., None]).sum(-2)
+    got_inv = bits_to_invalid(mask).reshape(N * S, 24)
+    same = (got_inv == invalid.reshape(N * S, 24)).all(-1)          # skip the (rare) samples whose mask flipped
+    sel = same[ids]
+    close(hbar[:n_act, :15].cpu()[sel], hb[ids][sel], 2e-5, "hbar")
+    valid = 1 - invalid.reshape(N * S, 24)
+    close((confd.cpu() * valid)[ids][sel], (a * valid)[ids][sel], 1e-4, "confd (visible bones)")
+    assert torch.equal(row_ray[:n_act].cpu().long(), ids // S)
+    X = decode_xtiles(xt, n_act).cpu()
+    want = orc.pe_embed(hbar[:n_act, :15].cpu(), 6)
+    err = (X - want).abs().max()
+    assert float(err) <= 2 ** -8 * 1.01 * max(1.0, float(want.abs().max())), f"bf16 rows: {float(err)}"
+
+
+@pytest.mark.parametrize("name", ["render_fast", "render_base"])
+def test_mlp_tcgen05(name):
+    """M1: the fused tensor-core MLP on rows the field kernel produced, against (a) a bf16-emulating restatement
+    (tight) and (b) the fp32 oracle (bf16 tolerance)."""
+    fx = load_fixture(name)
+    caster, args, P = make_caster(preset_of(fx))
+    Pc = params_for(fx)
+    skts, bones, _ = pose_tensors(fx)
+    rb = fx["ray_batch"].to(DEV)
+    N, S = rb.shape[0], int(fx["N_samples"])
+    consts, packed = caster._consts(), caster._packed_mlp()
+    vol = fx["st.vol.0"].to(DEV).contiguous()
+    z, mask, act = K().sample_mask(rb, S, skts.to(DEV).contiguous(), N, consts, z_in=fx["st.z.0"].to(DEV), append_empty=1)
+    xt, row_ray, _, hbar = K().field_agg(rb, S, z, mask, act, skts.to(DEV).contiguous(), vol, N, consts, want_hbar=True)
+    cams = fx["cams"].reshape(-1).to(DEV).to(torch.int32)
+    rbias = K().ray_bias(rb, cams, caster._codes_with_mean(), packed)
+    # per-ray view bias against the oracle
+    view = orc.view_inputs(fx["ray_batch"][:, 3:6], fx["cams"], Pc, training=False)
+    want_bias = view @ Pc["views_linears.0.weight"][:, 256:].t() + Pc["views_linears.0.bias"]
+    close(rbias, want_bias, 1e-5, "ray bias")
+    raw = torch.full((N * S + N, 4), float("nan"), device=DEV)
+    K().mlp_forward(xt, packed, rbias, act, row_ray, raw)
+    torch.cuda.synchronize()
+    n_act = int(act.count.item())
+    ids = act.ids[:n_act].long()
+    got = raw[ids].cpu()
+    assert torch.isfinite(got).all(), "every active row must be written"
+    assert torch.isnan(raw).all(-1).sum() == N * S + N - n_act, "only active rows may be written"
+    X = decode_xtiles(xt, n_act).cpu()
+    vb = want_bias[row_ray[:n_act].cpu().long()]
+    emu = mlp_bf16_reference(X, vb, Pc)
+    scale = float(emu.abs().max())
+    err_emu = float((got - emu).abs().max())
+    assert err_emu <= 2e-3 * scale, f"vs bf16 emulation: {err_emu:.3e} (scale {scale:.3e})"
+    x32 = orc.pe_embed(hbar[:n_act, :15].cpu(), 6)
+    view_full = view[row_ray[:n_act].cpu().long()]
+    ref = orc.field_mlp(x32, view_full, Pc)
+    err = float((got - ref).abs().max())
+    assert err <= 3e-2 * float(ref.abs().max()), f"vs fp32 oracle: {err:.3e} (scale {float(ref.abs().max()):.3e})"
+
+
+@pytest.mark.parametrize("name", RENDER)
+def test_composite_resample(name):
+    fx = load_fixture(name)
+    rb = fx["ray_batch"].to(DEV)
+    N, S, S_f = rb.shape[0], int(fx["N_samples"]), int(fx["N_importance"])
+    raw = torch.cat([fx["st.raw.0"].reshape(N * S, 4), torch.zeros(N, 4)], 0).to(DEV).contiguous()
+    mask = torch.ones(N, S, dtype=torch.int32, device=DEV)
+    out = K().composite_resample(rb, S, S_f, raw, mask, fx["st.z.0"].to(DEV), want_inds=True)
+    close(out["weights"], fx["st.weights.0"], 2e-6, "weights0")
+    close(out["alpha"], fx["st.alpha.0"], 2e-6, "alpha0")
+    close(out["rgb_map"], fx["out.rgb0"], 2e-6, "rgb0")
+    close(out["disp_map"], fx["out.disp0"], 2e-6, "disp0")
+    close(out["acc_map"], fx["out.acc0"], 2e-6, "acc0")
+    # importance samples: computed from the GOLDEN weights for an index-exact check
+    rawg = raw.clone()
+    z_all, zs, order, inds = orc.importance_sample(fx["st.z.0"], out["weights"].cpu(), S_f)
+    same_inds = (out["inds"].cpu().long() == inds)
+    assert float(same_inds.float().mean()) >= 0.999, f"searchsorted indices differ on {int((~same_inds).sum())} samples"
+    close(out["z_samples"], zs, 2e-6, "z_samples")
+    ok_rows = same_inds.all(-1) & (out["z_samples"].cpu() == zs).all(-1)
+    assert torch.equal(out["order"].cpu().long()[ok_rows], order[ok_rows]), "merge order must be identical"
+    za = out["z_all"].cpu()
+    assert bool((za[:, 1:] >= za[:, :-1]).all()), "merged z must be sorted"
+
+
+@pytest.mark.parametrize("name", RENDER)
+def test_merge_composite(name):
+    fx = load_fixture(name)
+    rb = fx["ray_batch"].to(DEV)
+    N, S, S_f = rb.shape[0], int(fx["N_samples"]), int(fx["N_importance"])
+    St = S + S_f
+    order = fx["st.sorted_idxs.0"]
+    merged = fx["st.raw.1"]
+    cat = torch.empty(N, St, 4)
+    cat.scatter_(1, order[..., None].expand(-1, -1, 4), merged)          # cat[order[i]] = merged[i]
+    raw0 = torch.cat([cat[:, :S].reshape(N * S, 4), torch.zeros(N, 4)], 0).to(DEV).contiguous()
+    raw1 = cat[:, S:].reshape(N * S_f, 4).to(DEV).contiguous()
+    ones0 = torch.ones(N, S, dtype=torch.int32, device=DEV)
+    ones1 = torch.ones(N, S_f, dtype=torch.int32, device=DEV)
+    out = K().merge_composite(rb, S, S_f, raw0, ones0, raw1, ones1, fx["st.z_all.0"].to(DEV),
+                              order.to(torch.int32).to(DEV), want_raw=True)
+    assert torch.equal(out["raw"].cpu(), merged)
+    close(out["rgb_map"], fx["out.rgb_map"], 2e-6, "rgb_map")
+    close(out["disp_map"], fx["out.disp_map"], 2e-6, "disp_map")
+    close(out["acc_map"], fx["out.acc_map"], 2e-6, "acc_map")
+    close(out["weights"], fx["out.T_i"], 2e-6, "T_i")
+    close(out["alpha"], fx["out.alpha"], 2e-6, "alpha")
+
+
+def _report(tag, got, want):
+    err = (got.detach().float().cpu() - want).abs()
+    print(f"[parity] {tag}: mean {float(err.mean()):.3e} p99 {float(err.flatten().quantile(0.99)):.3e} max {float(err.max()):.3e}")
+    return err
+
+
+@pytest.mark.parametrize("name", RENDER)
+def test_render_rays_end_to_end(name):
+    """The drop-in call: ray_caster(ray_batch, N_samples=..., kp_batch=..., skts=..., ...) in eval mode."""
+    fx = load_fixture(name)
+    caster, args, P = make_caster(preset_of(fx))
+    skts, bones, cyl = pose_tensors(fx)
+    N = fx["ray_batch"].shape[0]
+    ex = lambda t: t.expand(N, *t.shape[1:])
+    stages = {}
+    out = caster(fx["ray_batch"], N_samples=args.N_samples, kp_batch=ex(fx["pose_kps"][None]), skts=ex(skts),
+                 cyls=ex(cyl), bones=ex(bones), cams=fx["cams"], N_uniques=1, perturb=False,
+                 N_importance=args.N_importance, raw_noise_std=0., _stages=stages)
+    torch.cuda.synchronize()
+    assert set(out) == {"rgb_map", "disp_map", "acc_map", "alpha", "T_i", "rgb0", "disp0", "acc0", "alpha0"}
+    # coarse pass: identical sample positions, so this isolates the bf16 MLP error
+    e = _report(name + " raw0", stages["raw0"][: N * args.N_samples].reshape(N, args.N_samples, 4), fx["st.raw.0"])
+    assert float(e.max()) <= 3e-2 * float(fx["st.raw.0"].abs().max())
+    for k, tol_mean in (("rgb0", 4e-3), ("acc0", 4e-3), ("rgb_map", 4e-3), ("acc_map", 4e-3)):
+        e = _report(f"{name} {k}", out[k], fx["out." + k])
+        assert float(e.mean()) <= tol_mean, (k, float(e.mean()))
+        assert float(e.max()) <= 8e-2, (k, float(e.max()))
+    assert out["alpha"].shape == fx["out.alpha"].shape and out["T_i"].shape == fx["out.T_i"].shape
+    assert torch.isfinite(out["rgb_map"]).all()
+
+
+def test_density_grid():
+    fx = load_fixture("grid_base")
+    caster, args, P = make_caster("danbo_base")
+    sig = caster(kps=fx["pose_kps"][None].to(DEV), skts=fx["pose_skts"][None].to(DEV), bones=fx["pose_bones"][None].to(DEV),
+                 radius=float(fx["radius"]), res=int(fx["res"]), fwd_type="mesh")
+    e = _report("sigma grid", sig, fx["sigma"])
+    assert float(e.max()) <= 3e-2 * float(fx["sigma"].abs().max())
+
+
+@pytest.mark.parametrize("name", ["train_fast", "train_cfg3"])
+def test_train_mode_forward(name):
+    """Train-mode forward with the reference's own random draws (perturbed samples, density noise, random u)."""
+    from danbo_b200 import synthetic as syn
+    fx = load_fixture(name)
+    caster, args, P = make_caster(preset_of(fx), train=True)
+    b = syn.training_batch(int(fx["n_poses"]), int(fx["rays_per_pose"]), seed=int(fx["batch_seed"]))
+    rand = {k: fx["rand." + k].to(DEV) for k in ("t_rand", "noise0", "u", "noise1")}
+    stages = {}
+    with torch.no_grad():
+        out = caster.render_rays(b["ray_batch"], N_samples=args.N_samples, kp_batch=b["kp_batch"], skts=b["skts"],
+                                 cyls=b["cyls"], bones=b["bones"], cams=b["cams"], N_uniques=int(fx["n_poses"]),
+                                 perturb=1.0, N_importance=args.N_importance, raw_noise_std=float(fx["raw_noise_std"]),
+                                 _rand=rand, _stages=stages)
+    torch.cuda.synchronize()
+    assert torch.equal(stages["z_coarse"].cpu(), fx["st.z.0"]), "perturbed coarse z must be bit-identical"
+    for k in ("rgb0", "acc0", "rgb_map", "acc_map"):
+        e = _report(f"{name} {k}", out[k], fx["out." + k])
+        assert float(e.mean()) <= 5e-3, (k, float(e.mean()))
+    inv_bad = float((out["part_invalid"].cpu() != fx["out.part_invalid"]).float().mean())
+    print(f"[parity] {name} part_invalid mismatch fraction {inv_bad:.2e}")
+    assert inv_bad <= 2e-2          # the fine samples move with the bf16 weights; identical samples are checked above
+    assert out["confd"].shape == fx["out.confd"].shape
+
+
+def test_full_size_properties():
+    """BASELINE config #2 at full size (512x512, danbo_fast): size-independent properties."""
+    from danbo_b200 import synthetic as syn
+    caster, args, P = make_caster("danbo_fast")
+    pose = syn.make_pose(3)
+    b = syn.render_batch(pose, 512, 512)
+    N = b["ray_batch"].shape[0]
+    kw = dict(N_samples=args.N_samples, kp_batch=b["kp_batch"], skts=b["skts"], cyls=b["cyls"], bones=b["bones"],
+              cams=b["cams"], N_uniques=1, perturb=False, N_importance=args.N_importance, raw_noise_std=0.)
+    out = caster(b["ray_batch"], nanmean_chunk=4096, **kw)
+    torch.cuda.synchronize()
+    assert out["rgb_map"].shape == (N, 3)
+    for k, v in out.items():
+        assert torch.isfinite(v).all(), k
+    assert float(out["acc_map"].min()) >= 0 and float(out["acc_map"].max()) <= 1.0
+    assert float(out["T_i"].sum(-1).max()) <= 1.0 + 1e-4
+    assert float(out["alpha"].min()) >= 0 and float(out["alpha"].max()) <= 1.0
+    # chunk invariance: rendering the reference's 4096-ray chunks one call at a time gives the same pixels
+    sl = slice(8192, 8192 + 4096)
+    sub = caster(b["ray_batch"][sl], **{k: (v[sl] if torch.is_tensor(v) and v.shape[0] == N else v) for k, v in kw.items()})
+    assert torch.equal(sub["rgb_map"], out["rgb_map"][sl]) and torch.equal(sub["acc_map"], out["acc_map"][sl])

@@ -44,3 +44,62 @@ def mask_mismatch_report(x, got_invalid, want_invalid, ulps=16):
     margin = (x.abs() - 1.0).abs().min(-1).values            # distance of the closest coordinate to a face
     near = margin <= ulps * 1.1920929e-07
     return n_bad, int((bad & near).sum())
+
+
+# ---------------------------------------------------------------------------------------------------- GPU helpers
+def sw128_offsets(n_cols=208):
+    """Byte offsets of (row r, col k) inside one 64 KB X tile, mirroring csrc/common.cuh::sw128_offset."""
+    r = np.arange(128)[:, None]
+    k = np.arange(n_cols)[None, :]
+    chunk, kk = k >> 6, k & 63
+    return chunk * (128 * 128) + (r >> 3) * 1024 + (r & 7) * 128 + (((kk >> 3) ^ (r & 7)) << 4) + ((kk & 7) << 1)
+
+
+def decode_xtiles(xtiles, n_rows, n_cols=195):
+    """uint8 tile buffer -> float32 (n_rows, n_cols) matrix of the bf16 rows the field kernel wrote."""
+    off = torch.from_numpy(sw128_offsets(208).astype(np.int64)).to(xtiles.device)        # (128,208)
+    n_tiles = (n_rows + 127) // 128
+    words = xtiles[: n_tiles * 65536].view(torch.int16).view(n_tiles, 32768)
+    idx = (off // 2).reshape(1, -1).expand(n_tiles, -1)
+    vals = torch.gather(words, 1, idx).reshape(n_tiles * 128, 208)
+    return vals.view(torch.bfloat16).float()[:n_rows, :n_cols]
+
+
+def make_caster(preset, weight_seed=0, device="cuda", train=False):
+    import danbo_b200 as db
+    args = db.make_args(preset, no_reload=True)
+    data_attrs = {"skel_type": sk.SMPLSkeleton, "near": syn.NEAR, "far": syn.FAR, "n_views": 8,
+                  "rest_pose": syn.rest_pose()}
+    kw_train, kw_test, *_ = db.create_raycaster(args, data_attrs, device=device)
+    caster = kw_test["ray_caster"]
+    P = syn.synthetic_params(weight_seed)
+    caster.network.load_state_dict(P)
+    caster.train(train)
+    return caster, args, {k: v.to(device) for k, v in P.items()}
+
+
+def preset_of(fx):
+    cfg = str(fx["config"])
+    if "fast" in cfg:
+        return "danbo_fast"
+    return "danbo_cfg3" if "N_samples 64" in str(fx.get("extra", "")) else "danbo_base"
+
+
+def mlp_bf16_reference(x, view_bias, P):
+    """The fused kernel's arithmetic restated in torch: bf16 operands, fp32 accumulation, activations rounded to
+    bf16 where the kernel writes them back to tensor memory; sigma and rgb heads in fp32."""
+    bf = lambda t: t.to(torch.bfloat16).float()
+    xb = bf(x)
+    h = xb
+    a = None
+    for i in range(8):
+        W = bf(P[f"pts_linears.{i}.weight"])
+        a = torch.relu(h @ W.t() + P[f"pts_linears.{i}.bias"])
+        h = bf(a)
+        if i == 4:
+            h = torch.cat([xb, h], -1)
+    sigma = a @ P["alpha_linear.weight"].t() + P["alpha_linear.bias"]
+    feat = bf(h @ bf(P["feature_linear.weight"]).t() + P["feature_linear.bias"])
+    g = torch.relu(feat @ bf(P["views_linears.0.weight"][:, :256]).t() + view_bias)
+    rgb = g @ P["rgb_linear.weight"].t() + P["rgb_linear.bias"]
+    return torch.cat([rgb, sigma], -1)
