@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""Benchmark of the DANBO hot path on B200 (contract: see the task statement / DESIGN.md §Measurement).
+
+    python bench.py --gpus 1 --steps 10 --warmup 3                 # this repo's CUDA path
+    python bench.py --impl reference --steps 2 --warmup 1           # the reference algorithm (oracle port) on host cores
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): DANBO `danbo_fast` (32 coarse + 16 fine samples, per-part volume near/far),
+512x512 render of one synthetic 24-joint pose, random-init weights; rays restricted to the image box of the pose's
+bounding cylinder exactly as the reference's render_path does.  One step = one image through the whole path
+(near/far -> sampling -> bone transform/mask -> gather + aggregation net -> fused MLP -> composite -> resample ->
+fine pass -> merged composite).  metric = rays/s.
+
+  value : steps timed with CUDA events, inputs already resident in HBM.
+  e2e   : the same call through the public `ray_caster(...)` API with pinned HOST inputs, H2D of the rays and D2H
+          of the pixels inside the timed region.
+At N > 1 every rank renders its own image (bullet-time view `rank`) and the pixels are all-gathered (weak scaling).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+MLP_FLOP_PER_SAMPLE = 1354752          # SURVEY §8(a) row M1 (FlopCounter-verified): 677 376 MAC / sample
+H = W = 512
+PRESET = "danbo_fast"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_scene(rank, device):
+    import danbo_b200 as db
+    from danbo_b200 import synthetic as syn, skeleton as sk
+    args = db.make_args(PRESET, no_reload=True)
+    data_attrs = {"skel_type": sk.SMPLSkeleton, "near": syn.NEAR, "far": syn.FAR, "n_views": 8,
+                  "rest_pose": syn.rest_pose()}
+    torch.manual_seed(0)
+    _, kw_test, *_ = db.create_raycaster(args, data_attrs, device=device)
+    caster = kw_test["ray_caster"]
+    caster.network.load_state_dict(syn.synthetic_params(0))      # random-init weights, same on every rank
+    caster.eval()
+    pose = syn.make_pose(3)
+    c2w = syn.bullet_time_cameras(syn.camera(), 8)[rank % 8]
+    batch = syn.render_batch(pose, H, W, c2w=c2w, cam_idx=0)
+    return caster, args, batch
+
+
+def caster_kwargs(args, batch, device=None):
+    mv = (lambda t: t.to(device)) if device is not None else (lambda t: t)
+    return dict(N_samples=args.N_samples, kp_batch=mv(batch["kp_batch"]), skts=mv(batch["skts"]), cyls=mv(batch["cyls"]),
+                bones=mv(batch["bones"]), cams=mv(batch["cams"]), N_uniques=1, perturb=False,
+                N_importance=args.N_importance, raw_noise_std=0., nanmean_chunk=args.chunk)
+
+
+def run_ours(opt):
+    import torch.distributed as dist
+    import danbo_b200 as db
+    from danbo_b200 import parallel, kernels
+    rank, world, local = parallel.init_distributed()
+    if world != opt.gpus:
+        opt.gpus = world
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    caster, args, batch = build_scene(rank, device)
+    n_rays = batch["ray_batch"].shape[0]
+    rays_dev = batch["ray_batch"].to(device)
+    kw_dev = caster_kwargs(args, batch, device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)       # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        ret = caster(rays_dev, **kw_dev)
+        pix = parallel.pack_pixels(ret)
+        if world > 1:
+            pix = parallel.allgather_rows(pix)
+        return pix
+
+    # pinned host inputs for the end-to-end path
+    rays_host = batch["ray_batch"].pin_memory()
+    pix_host = torch.empty(n_rays, 5).pin_memory()
+    kw_host = caster_kwargs(args, batch)
+
+    def step_e2e():
+        ret = caster(rays_host, **kw_host)                  # H2D of the (n,11) ray batch happens inside
+        pix = parallel.pack_pixels(ret)
+        if world > 1:
+            pix_all = parallel.allgather_rows(pix)
+        pix_host.copy_(pix, non_blocking=True)              # D2H of the 20 B / ray result
+        torch.cuda.current_stream().synchronize()
+        return pix_host
+
+    for _ in range(max(opt.warmup, 3)):
+        step_device()
+        flush.fill_(1)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    kernels.PROFILE = {"mlp": [], "launches": 0}
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(opt.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(opt.steps):
+        ev[i][0].record()
+        step_device()
+        ev[i][1].record()
+        flush.fill_(i)                                       # L2 flush between timed iterations (not timed)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    prof = kernels.PROFILE
+    kernels.PROFILE = None
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    mlp_ms = [a.elapsed_time(b) for a, b, _ in prof["mlp"]]
+    mlp_rows = [int(c.item()) for _, _, c in prof["mlp"]]
+    launches = prof["launches"]
+    # end-to-end (host buffers)
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(opt.steps)]
+    for i in range(opt.steps):
+        ev2[i][0].record()
+        step_e2e()
+        ev2[i][1].record()
+        flush.fill_(i)
+    barrier()
+    e2e_ms = sum(a.elapsed_time(b) for a, b in ev2)
+    clocks = sampler.stop()
+    t = torch.tensor([dev_ms, e2e_ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = measured_peaks()
+    total_rays = n_rays * world * opt.steps
+    value = total_rays / (dev_ms / 1e3)
+    flops = MLP_FLOP_PER_SAMPLE * float(sum(mlp_rows))
+    mlp_s = sum(mlp_ms) / 1e3
+    achieved = flops / mlp_s / 1e12 if mlp_s > 0 else 0.0
+    peak = peaks["bf16_tflops_sustained"]
+    samples_per_ray = args.N_samples + args.N_importance
+    line = {
+        "metric": "DANBO render rays/s (fwd+composite)", "value": value, "unit": "rays/s", "n_gpus": world,
+        "steps": opt.steps, "warmup": max(opt.warmup, 3), "ms_per_step": dev_ms / opt.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16 (tensor-core MLP, fp32 accumulate); fp32 elsewhere; fp64 box test",
+        "data": "synthetic",
+        "config": {"workload": f"danbo_fast {H}x{W} render, 1 synthetic 24-joint pose, {args.N_samples}+{args.N_importance} "
+                               f"samples/ray, box-restricted rays ({n_rays} rays/image), random-init weights",
+                   "rays_per_image": n_rays, "samples_per_ray": samples_per_ray,
+                   "parallelism": f"1 image per GPU x {world} + NCCL all-gather of pixels" if world > 1 else "single GPU",
+                   "l2": "256 MiB buffer written between timed steps (untimed)", "chunk": args.chunk,
+                   "wall_ms_per_step_incl_flush": t_wall * 1e3 / opt.steps},
+        "e2e": {"value": total_rays / (e2e_ms / 1e3), "unit": "rays/s", "h2d_bytes_per_step": int(rays_host.numel() * 4),
+                "d2h_bytes_per_step": int(pix_host.numel() * 4)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "danbo::mlp::mlp_kernel<true>", "achieved": achieved, "peak": peak,
+                     "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
+                     "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
+                     "launches_timed": len(mlp_ms), "rows_per_step": float(sum(mlp_rows)) / max(opt.steps, 1),
+                     "dense_samples_per_step": n_rays * samples_per_ray,
+                     "note": "achieved = 1 354 752 FLOP x rows the launch processed / CUDA-event time of the launch; rows = "
+                             "samples seen by at least one bone (+1 per ray); the rest reuse the ray's empty-sample output"},
+    }
+    if world == 1:
+        line["cpu_baseline"] = cpu_baseline(sample_rays=1024, repeats=1)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(sample_rays=1024, repeats=1, threads=None):
+    """The reference algorithm (oracle port, torch CPU ops like the reference itself) on the host cores, on a bounded
+    sample of the same workload."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import danbo_oracle as orc
+    import danbo_b200 as db
+    from danbo_b200 import synthetic as syn, skeleton as sk
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    args = db.make_args(PRESET)
+    pose = syn.make_pose(3)
+    b = syn.render_batch(pose, H, W)
+    n = min(sample_rays, b["ray_batch"].shape[0])
+    lo = (b["ray_batch"].shape[0] - n) // 2
+    rays = b["ray_batch"][lo:lo + n].contiguous()
+    P = syn.synthetic_params(0)
+    A = torch.from_numpy(sk.bone_align_transforms(syn.rest_pose())[0])
+    t = lambda a: torch.as_tensor(a)[None]
+    best = None
+    with torch.no_grad():
+        for _ in range(repeats + 1):                         # first pass = warm-up
+            t0 = time.perf_counter()
+            orc.render_rays(rays, t(pose["skts"]), t(pose["bones"]), t(pose["cyl"]), b["cams"][lo:lo + n], A, P,
+                            args.N_samples, args.N_importance, rays_per_pose=n, use_volume_near_far=True)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return {"value": n / best, "unit": "rays/s", "cores": int(torch.get_num_threads()), "kind": "port",
+            "sample": f"{n} consecutive rays from the middle of the same {H}x{W} danbo_fast image, fp32 torch CPU ops, "
+                      f"best of {repeats} after 1 warm-up ({best:.2f} s)"}
+
+
+def run_reference(opt):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = 2048
+    # each step = one bounded sample of the workload
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    res = []
+    base = None
+    for i in range(opt.warmup + opt.steps):
+        base = cpu_baseline(sample_rays=n, repeats=1)
+        if i >= opt.warmup:
+            res.append(base["value"])
+    v = float(np.mean(res))
+    import danbo_b200 as db
+    args = db.make_args(PRESET)
+    line = {"impl": "reference", "metric": "DANBO render rays/s (fwd+composite)", "value": v, "unit": "rays/s",
+            "n_gpus": opt.gpus, "steps": opt.steps, "warmup": opt.warmup, "ms_per_step": n / v * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"danbo_fast {H}x{W} render, 1 synthetic 24-joint pose, {args.N_samples}+{args.N_importance} "
+                                   f"samples/ray; each step = {n}-ray sample of the image on the host CPU"},
+            "cpu_baseline": dict(base, value=v),
+            "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    opt = ap.parse_args()
+    if opt.impl == "reference":
+        run_reference(opt)
+    else:
+        run_ours(opt)
+
+
+if __name__ == "__main__":
+    main()

@@ -12,6 +12,15 @@ J = 24
 TILE_M = 128
 X_TILE_BYTES = 128 * 256 * 2
 
+# bench.py sets this to {"mlp": [], "launches": 0} to count this library's kernel launches and to time the
+# dominant kernel with CUDA events on the launching stream; None in normal operation.
+PROFILE = None
+
+
+def _count(n):
+    if PROFILE is not None:
+        PROFILE["launches"] += n
+
 
 def _p(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
@@ -80,6 +89,7 @@ def nearfar(rays, pose_cyl, pose_skts, rays_per_pose, align, axis_scale, seg_len
                                  int(rays_per_pose), pose_skts.shape[0], _p(align), _p(axis_scale), int(seg_len),
                                  int(bool(use_box)), float(bound), bound_hi, _p(near), _p(far), _p(acc), n_seg,
                                  _p(pv), _p(vv), _stream()), "danbo_nearfar")
+    _count(2)
     if return_masks:
         return near, far, pv, vv
     return near, far
@@ -116,6 +126,7 @@ def sample_mask(rays, S, pose_skts, rays_per_pose, consts, near=None, far=None, 
                                      int(rays_per_pose), pose_skts.shape[0], consts.array, _p(mask), _p(active.ids),
                                      _p(active.count), active.capacity, int(append_empty), _stream()),
                "danbo_sample_mask")
+    _count(1)
     return z, mask, active
 
 
@@ -136,6 +147,7 @@ def field_agg(rays, S, z, mask, active, pose_skts, pose_vol, rays_per_pose, cons
                                    active.capacity, _p(pose_skts), _p(pose_vol), int(rays_per_pose),
                                    pose_skts.shape[0], consts.array, _p(xtiles), _p(row_ray), _p(confd), _p(hbar),
                                    num_sms(idx), _stream()), "danbo_field_agg")
+    _count(1)
     return xtiles, row_ray, confd, hbar
 
 
@@ -165,6 +177,7 @@ class PackedMLP:
         _lib.check(lib.danbo_pack_mlp_weights(wa, ba, *[_p(t) for t in others], _p(self.wstream), _p(self.heads),
                                               _p(self.wv_ray), _stream()), "danbo_pack_mlp_weights")
         self._keep = (ws, bs, others)          # keep sources alive until the stream has consumed them
+        _count(1)
         return self
 
 
@@ -176,6 +189,7 @@ def ray_bias(rays, cam_idx, codes_with_mean, packed):
     out = torch.empty(n, 128, device=rays.device, dtype=torch.float32)
     _lib.check(lib.danbo_ray_bias(_p(rays), rays.stride(0), n, _p(cam_idx), _p(codes_with_mean),
                                   codes_with_mean.shape[0] - 1, _p(packed.wv_ray), _p(out), _stream()), "danbo_ray_bias")
+    _count(1)
     return out
 
 
@@ -184,10 +198,17 @@ def mlp_forward(xtiles, packed, rbias, active, row_ray, out, density_only=False)
     lib = _lib.load()
     dev = xtiles.device
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     _lib.check(lib.danbo_mlp_forward(_p(xtiles), _p(packed.wstream), _p(packed.heads), _p(rbias), _p(active.ids),
                                      _p(row_ray), _p(active.count), active.capacity, _p(out),
                                      out.shape[0] if not density_only else out.numel(), int(bool(density_only)),
                                      num_sms(idx), _stream()), "danbo_mlp_forward")
+    if PROFILE is not None:
+        e1.record()
+        PROFILE["mlp"].append((e0, e1, active.count))
+    _count(1)
     return out
 
 
@@ -212,6 +233,7 @@ def composite_resample(rays, S, S_f, raw, mask, z, noise=None, inv_B=1.0, u_rand
                                             _p(out["rgb_map"]), _p(out["disp_map"]), _p(out["acc_map"]),
                                             _p(out.get("z_samples")), _p(out.get("z_all")), _p(out.get("order")),
                                             _p(out.get("inds")), _stream()), "danbo_composite_resample")
+    _count(1)
     return out
 
 
@@ -235,4 +257,5 @@ def merge_composite(rays, S_c, S_f, raw0, mask0, raw1, mask1, z_all, order, nois
                                          _p(out["alpha"]), _p(out["rgb_map"]), _p(out["disp_map"]), _p(out["acc_map"]),
                                          _p(out.get("raw")), _p(confd0), _p(confd1), _p(out.get("confd")),
                                          _p(out.get("part_invalid")), _stream()), "danbo_merge_composite")
+    _count(1)
     return out

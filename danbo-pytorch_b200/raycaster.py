@@ -157,8 +157,13 @@ class RayCaster(nn.Module):
                     "noise0": torch.randn(N, N_samples, device=dev), "u": torch.rand(N, N_importance, device=dev),
                     "noise1": torch.randn(N, S_t, device=dev)}
         outs = []
-        for s0 in range(0, N, MAX_RAYS_PER_LAUNCH):
-            s1 = min(N, s0 + MAX_RAYS_PER_LAUNCH)
+        # internal launches: any split works for a single pose; with several poses a block holds whole poses
+        G = pose_skts.shape[0]
+        block = MAX_RAYS_PER_LAUNCH if G == 1 else max((MAX_RAYS_PER_LAUNCH // skip) * skip, skip)
+        if nanmean_chunk:
+            block = max((block // int(nanmean_chunk)) * int(nanmean_chunk), int(nanmean_chunk)) if G == 1 else block
+        for s0 in range(0, N, block):
+            s1 = min(N, s0 + block)
             sub_rand = {k: v[s0:s1].to(dev).contiguous() for k, v in rand.items()}
             outs.append(self._render_block(rays[s0:s1], s0, skip, pose_skts, pose_cyls, vol, cam_idx[s0:s1], codes,
                                            consts, packed, N_samples, N_importance, B, raw_noise_std, perturb,
@@ -172,9 +177,11 @@ class RayCaster(nn.Module):
         n = rays.shape[0]
         # poses of this block: ray (ray0 + i) -> pose (ray0 + i) // skip.  Blocks start on pose boundaries whenever
         # skip divides MAX_RAYS_PER_LAUNCH or there is a single pose; otherwise shift the tables.
-        p0 = ray0 // skip
-        if ray0 % skip != 0:
-            raise NotImplementedError("rays_per_pose must divide the internal launch size")
+        if pose_skts.shape[0] == 1:
+            p0 = 0
+        else:
+            assert ray0 % skip == 0
+            p0 = ray0 // skip
         p_skts, p_cyls, p_vol = pose_skts[p0:], pose_cyls[p0:], vol[p0:]
         seg = 0 if not nanmean_chunk else int(nanmean_chunk)
         near, far = K.nearfar(rays, p_cyls, p_skts, skip, consts.align, consts.axis_scale, seg_len=seg,
