@@ -29,6 +29,22 @@ __constant__ uint32_t kNbrMask[DANBO_J] = {
 // ---------------------------------------------------------------------------------------------------------
 // x_j = (A_j (R_j p + t_j) + a_j) / |s_j| for one joint, in the reference's two-step order with a true divide.
 // encoders.py:288-303 (transform_batch_pts), :442-444 (bone align), gnn_backbone.py:802 (scale)
+__device__ __forceinline__ void bone_aligned(const float* __restrict__ skt, const float* __restrict__ A,
+                                             float px, float py, float pz, float& t0, float& t1, float& t2) {
+    const float4 r0 = __ldg(reinterpret_cast<const float4*>(skt));
+    const float4 r1 = __ldg(reinterpret_cast<const float4*>(skt) + 1);
+    const float4 r2 = __ldg(reinterpret_cast<const float4*>(skt) + 2);
+    const float l0 = fmaf(r0.z, pz, fmaf(r0.y, py, fmaf(r0.x, px, r0.w)));
+    const float l1 = fmaf(r1.z, pz, fmaf(r1.y, py, fmaf(r1.x, px, r1.w)));
+    const float l2 = fmaf(r2.z, pz, fmaf(r2.y, py, fmaf(r2.x, px, r2.w)));
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(A));
+    const float4 a1 = __ldg(reinterpret_cast<const float4*>(A) + 1);
+    const float4 a2 = __ldg(reinterpret_cast<const float4*>(A) + 2);
+    t0 = __fadd_rn(fmaf(a0.z, l2, fmaf(a0.y, l1, __fmul_rn(a0.x, l0))), a0.w);
+    t1 = __fadd_rn(fmaf(a1.z, l2, fmaf(a1.y, l1, __fmul_rn(a1.x, l0))), a1.w);
+    t2 = __fadd_rn(fmaf(a2.z, l2, fmaf(a2.y, l1, __fmul_rn(a2.x, l0))), a2.w);
+}
+
 __device__ __forceinline__ void bone_coords(const float* __restrict__ skt, const float* __restrict__ A,
                                             const float* __restrict__ scale, float px, float py, float pz,
                                             float& x0, float& x1, float& x2) {
@@ -218,9 +234,12 @@ __global__ void sample_mask_kernel(const float* __restrict__ rays, int ray_strid
         const float* skt = pose_skts + (size_t)pose * DANBO_J * 16;
 #pragma unroll 4
         for (int j = 0; j < DANBO_J; ++j) {
-            float x0, x1, x2;
-            bone_coords(skt + j * 16, fc.align + j * 16, fc.axis_scale + j * 3, px, py, pz, x0, x1, x2);
-            const bool invalid = (fabsf(x0) > 1.f) || (fabsf(x1) > 1.f) || (fabsf(x2) > 1.f);
+            // |fl(t/s)| > 1  <=>  |t| > |s| for correctly rounded division (t > s implies t/s > 1 + 2^-24, which
+            // rounds above 1), so the visibility mask needs no divide here; field_agg divides for the few bones it reads
+            float t0, t1, t2;
+            bone_aligned(skt + j * 16, fc.align + j * 16, px, py, pz, t0, t1, t2);
+            const float* sc = fc.axis_scale + j * 3;
+            const bool invalid = (fabsf(t0) > fabsf(__ldg(sc))) || (fabsf(t1) > fabsf(__ldg(sc + 1))) || (fabsf(t2) > fabsf(__ldg(sc + 2)));
             mask |= (invalid ? 0u : 1u) << j;
         }
         mask_out[idx] = mask;
@@ -269,12 +288,15 @@ field_agg_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, int
                  const float* __restrict__ pose_skts, const float* __restrict__ pose_vol, int rays_per_pose,
                  int n_poses, FieldConsts fc, uint8_t* __restrict__ xtiles, int* __restrict__ row_ray,
                  float* __restrict__ confd /* (n_rays*S,24) or null */, float* __restrict__ hbar_out /* (rows,16) or null */) {
+    __shared__ __align__(16) __nv_bfloat16 xrow[8][DANBO_X_KPAD];     // one encoded row per warp, staged for 16 B stores
     const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
     const int warps_per_block = blockDim.x >> 5;
-    const int gwarp = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const int gwarp = blockIdx.x * warps_per_block + wib;
     const int n_warps = gridDim.x * warps_per_block;
     int count = *active_count; if (count > capacity) count = capacity;
     const int total = n_rays * S;
+    if (lane < 13) xrow[wib][DANBO_X_COLS + lane] = __float2bfloat16_rn(0.f);   // K padding 195..207 stays zero
     for (int e = gwarp; e < count; e += n_warps) {
         const int id = active_ids[e];
         float hbar = 0.f;                               // lane l < 15 holds blended feature l
@@ -291,20 +313,25 @@ field_agg_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, int
             int pose = n / rays_per_pose; if (pose >= n_poses) pose = n_poses - 1;
             const float* skt = pose_skts + (size_t)pose * DANBO_J * 16;
             const float* vol = pose_vol + (size_t)pose * DANBO_J * DANBO_VOL;
+            // lane k < 24 owns bone k: local coordinates and window, computed once per sample
+            float bx0 = 0.f, bx1 = 0.f, bx2 = 0.f, bwin = 0.f;
+            if (lane < DANBO_J) {
+                bone_coords(skt + lane * 16, fc.align + lane * 16, fc.axis_scale + lane * 3, px, py, pz, bx0, bx1, bx2);
+                const float a2 = bx0 * bx0, b2 = bx1 * bx1, c2 = bx2 * bx2;
+                bwin = expf(-2.f * (a2 * a2 * a2 + b2 * b2 * b2 + c2 * c2 * c2));
+            }
             uint32_t m = mask[id];
+            const int f = lane / 3, a = lane - 3 * f;   // feature channel / axis of this lane (lanes < 15)
             while (m) {
                 const int j = __ffs(m) - 1; m &= m - 1;
                 float mix = 0.f, hj = 0.f;
                 uint32_t nb = kNbrMask[j];
                 while (nb) {
                     const int k = __ffs(nb) - 1; nb &= nb - 1;
-                    float x0, x1, x2;
-                    bone_coords(skt + k * 16, fc.align + k * 16, fc.axis_scale + k * 3, px, py, pz, x0, x1, x2);
-                    const float x0_2 = x0 * x0, x1_2 = x1 * x1, x2_2 = x2 * x2;
-                    const float win = expf(-2.f * (x0_2 * x0_2 * x0_2 + x1_2 * x1_2 * x1_2 + x2_2 * x2_2 * x2_2));
+                    const float x0 = __shfl_sync(0xffffffffu, bx0, k), x1 = __shfl_sync(0xffffffffu, bx1, k);
+                    const float x2 = __shfl_sync(0xffffffffu, bx2, k), win = __shfl_sync(0xffffffffu, bwin, k);
                     float hk = 0.f;
                     if (lane < DANBO_FEAT) {
-                        const int f = lane / 3, a = lane - 3 * f;
                         const float xa = a == 0 ? x0 : (a == 1 ? x1 : x2);
                         const float iy = ((xa + 1.f) * (float)DANBO_RES - 1.f) * 0.5f;
                         const float fl = floorf(iy);
@@ -329,40 +356,38 @@ field_agg_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, int
 #pragma unroll
                 for (int i = 0; i < DANBO_AGG_W; ++i) l1 = fmaf(__shfl_sync(0xffffffffu, o1, i), __ldg(w1p + i * DANBO_AGG_W), l1);
                 const float o2 = fmaxf(l1 + __ldg(fc.agg_b1 + j * DANBO_AGG_W + lane), 0.f);
-                const float a = warp_sum(o2 * __ldg(fc.agg_w2 + j * DANBO_AGG_W + lane)) + __ldg(fc.agg_b2 + j);
-                const float p = (1.f / (1.f + expf(-a))) * 1.002f - 0.001f;      // danbo.py:410, valid bone
+                const float al = warp_sum(o2 * __ldg(fc.agg_w2 + j * DANBO_AGG_W + lane)) + __ldg(fc.agg_b2 + j);
+                const float p = (1.f / (1.f + expf(-al))) * 1.002f - 0.001f;      // danbo.py:410, visible bone
                 hbar = fmaf(p, hj, hbar);
-                if (confd && lane == 0) confd[(size_t)id * DANBO_J + j] = a;
+                if (confd && lane == 0) confd[(size_t)id * DANBO_J + j] = al;
             }
         }
         if (hbar_out && lane < 16) hbar_out[(size_t)e * 16 + lane] = lane < DANBO_FEAT ? hbar : 0.f;
         if (lane == 0) row_ray[e] = n;
-        // ---- positional encoding (cutoff_embedder.py:62-73): [h, sin(2^0 h), cos(2^0 h), ..., cos(2^5 h)] -> bf16
+        // ---- positional encoding (cutoff_embedder.py:62-73): [h, sin(2^0 h), cos(2^0 h), ..., cos(2^5 h)] -> bf16.
+        // One sincos per feature; the five higher octaves come from the double-angle recurrence (error ~1e-6,
+        // three orders below bf16 resolution).  Column of (f, fn, i) = 15 + 30 f + 15 fn + i.
+        __nv_bfloat16* xr = xrow[wib];
+        if (lane < DANBO_FEAT) {
+            float sn, cs;
+            sincosf(hbar, &sn, &cs);
+            xr[lane] = __float2bfloat16_rn(hbar);
+#pragma unroll
+            for (int fq = 0; fq < 6; ++fq) {
+                xr[DANBO_FEAT + 30 * fq + lane] = __float2bfloat16_rn(sn);
+                xr[DANBO_FEAT + 30 * fq + DANBO_FEAT + lane] = __float2bfloat16_rn(cs);
+                const float s2 = 2.f * sn * cs, c2 = 1.f - 2.f * sn * sn;
+                sn = s2; cs = c2;
+            }
+        }
+        __syncwarp();
         const int tile = e >> 7, rr = e & 127;
         uint8_t* xt = xtiles + (size_t)tile * DANBO_X_TILE_BYTES;
-        uint32_t pk[4];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const int col = lane * 8 + c;
-            int src = 0, fn = 0; float freq = 1.f;
-            if (col < DANBO_FEAT) { src = col; fn = 0; }
-            else if (col < DANBO_X_COLS) {
-                const int q = col - DANBO_FEAT;
-                const int f = q / 30, rem = q - f * 30;
-                fn = 1 + rem / DANBO_FEAT; src = rem % DANBO_FEAT; freq = (float)(1 << f);
-            } else { fn = 3; }
-            const float hv = __shfl_sync(0xffffffffu, hbar, src);
-            float val;
-            if (fn == 0) val = hv;
-            else if (fn == 1) val = sinf(hv * freq);
-            else if (fn == 2) val = cosf(hv * freq);
-            else val = 0.f;
-            const uint16_t b = __bfloat16_as_ushort(__float2bfloat16_rn(val));
-            if (c & 1) pk[c >> 1] |= (uint32_t)b << 16; else pk[c >> 1] = b;
-        }
         if (lane < 26) {                                // 26 x 8 = 208 columns (13 k-steps of 16)
-            *reinterpret_cast<uint4*>(xt + sw128_offset((uint32_t)rr, (uint32_t)lane * 8)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(xt + sw128_offset((uint32_t)rr, (uint32_t)lane * 8)) =
+                *reinterpret_cast<const uint4*>(xr + lane * 8);
         }
+        __syncwarp();
     }
 }
 

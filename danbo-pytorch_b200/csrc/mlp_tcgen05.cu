@@ -4,8 +4,8 @@
 // forward_view, ten addmm launches + relu/cat per 65 536-point chunk, every activation round-tripping HBM).
 //
 // Design:
-//   * one CTA per SM, 6 warps: warp 0 = bulk-copy (TMA) producer, warp 1 = MMA issuer (one elected thread),
-//     warps 2-5 = epilogue (one TMEM lane quarter each, thread <-> sample row).
+//   * one CTA per SM, 10 warps: warp 0 = bulk-copy (TMA) producer, warp 1 = MMA issuer (one elected lane),
+//     warps 2-9 = epilogue (two warps per TMEM lane quarter, thread <-> sample row x 64-column slice).
 //   * tile = 128 samples.  Accumulators live in TMEM as two N=128 halves (columns 0-255, fp32).  The activation
 //     of every layer is written back to TMEM as packed bf16 (two ping-pong buffers, columns 256-511) and is the
 //     A operand of the next layer's tcgen05.mma straight from TMEM -- activations never touch shared or global
@@ -28,7 +28,7 @@ constexpr int kStages = 9;
 constexpr int kStageBytes = 128 * 64 * 2;          // 16 KB
 constexpr int kXBytes = DANBO_X_TILE_BYTES;        // 64 KB
 constexpr int kNumHeadFloats = 9 * 256 + 256 + 3 * 128 + 4;   // biases L0..L8, w_alpha, W_rgb, b_alpha, b_rgb[3]
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;            // producer warp, MMA warp, 8 epilogue warps
 
 // TMEM column map
 constexpr uint32_t kAccCol = 0;        // + 128*h
@@ -41,6 +41,7 @@ struct __align__(1024) Smem {
     uint8_t x[kXBytes];
     uint8_t w[kStages][kStageBytes];
     float heads[kNumHeadFloats + 4];
+    float4 part[DANBO_TILE_M];          // second column slice's partial (rgb, sigma) of every row
     uint64_t w_full[kStages];
     uint64_t w_empty[kStages];
     uint64_t x_full, x_empty;
@@ -125,6 +126,17 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=128
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// relu fused into the bf16x2 conversion (first PTX operand lands in the upper half)
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&p);
@@ -146,7 +158,8 @@ mlp_kernel(const uint8_t* __restrict__ xtiles,       // [tiles][64 KB] swizzled 
            const int* __restrict__ row_ray,          // [rows] ray of every row (full mode)
            const int* __restrict__ n_rows_ptr,       // device scalar: number of valid rows
            float* __restrict__ out,                  // full: raw [*,4]; density: sigma [*]
-           int out_capacity) {
+           int out_capacity,
+           long long* __restrict__ trace) {          // optional clock64 timeline of CTA 0 (profiling aid) or null
     extern __shared__ uint8_t smem_raw[];
     Smem& S = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -159,7 +172,7 @@ mlp_kernel(const uint8_t* __restrict__ xtiles,       // [tiles][64 KB] swizzled 
         for (int s = 0; s < kStages; ++s) { mbar_init(&S.w_full[s], 1); mbar_init(&S.w_empty[s], 1); }
         mbar_init(&S.x_full, 1); mbar_init(&S.x_empty, 1);
         mbar_init(&S.acc_full[0], 1); mbar_init(&S.acc_full[1], 1);
-        mbar_init(&S.act_ready[0], 4); mbar_init(&S.act_ready[1], 4);
+        mbar_init(&S.act_ready[0], 8); mbar_init(&S.act_ready[1], 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -170,75 +183,101 @@ mlp_kernel(const uint8_t* __restrict__ xtiles,       // [tiles][64 KB] swizzled 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = S.tmem_base;
+    const bool tr = (trace != nullptr) && blockIdx.x == 0;
+    // trace layout: [tile_iter < 4][role: 0 = mma, 1 = epilogue][(L*2+h)][begin, end]
+#define DANBO_TRACE(it, role, L, h, which) do { if (tr && (it) < 4) trace[(((it) * 2 + (role)) * 20 + (L) * 2 + (h)) * 2 + (which)] = clock64(); } while (0)
 
     if (warp == 0) {
-        // ===== producer: X tile + weight stages =====
-        if (lane == 0) {
-            uint32_t ws = 0, wphase = 0, xphase = 0;
-            for (int t = blockIdx.x, it = 0; t < n_tiles; t += gridDim.x, ++it) {
-                if (it > 0) { mbar_wait(&S.x_empty, xphase); xphase ^= 1; }
+        // ===== producer: X tile + weight stages (one elected lane issues, the warp stays converged) =====
+        const bool leader = elect_one();
+        uint32_t ws = 0, wphase = 0, xphase = 0;
+        for (int t = blockIdx.x, it = 0; t < n_tiles; t += gridDim.x, ++it) {
+            if (it > 0) { mbar_wait(&S.x_empty, xphase); xphase ^= 1; }
+            const uint8_t* xs = xtiles + (size_t)t * kXBytes;
+            if (leader) {
                 mbar_expect_tx(&S.x_full, kXBytes);
-                const uint8_t* xs = xtiles + (size_t)t * kXBytes;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) bulk_g2s(S.x + c * 16384, xs + c * 16384, 16384, &S.x_full);
-                for (int s = 0; s < stages_per_tile(kFull); ++s) {
-                    mbar_wait(&S.w_empty[ws], wphase ^ 1);
+            }
+            for (int s = 0; s < stages_per_tile(kFull); ++s) {
+                mbar_wait(&S.w_empty[ws], wphase ^ 1);
+                if (leader) {
                     mbar_expect_tx(&S.w_full[ws], kStageBytes);
                     bulk_g2s(S.w[ws], wstream + (size_t)s * kStageBytes, kStageBytes, &S.w_full[ws]);
-                    if (++ws == kStages) { ws = 0; wphase ^= 1; }
                 }
+                if (++ws == kStages) { ws = 0; wphase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            uint32_t ws = 0, wphase = 0, xphase = 0, r0 = 0, r1 = 0;
-            const uint32_t x_base = smem_u32(S.x);
-            for (int t = blockIdx.x, it = 0; t < n_tiles; t += gridDim.x, ++it) {
-                mbar_wait(&S.x_full, xphase); xphase ^= 1;
-                if (it > 0) {                                                   // accumulators drained by the last epilogues
-                    mbar_wait(&S.act_ready[0], r0 & 1); ++r0;
-                    if (!kFull) { mbar_wait(&S.act_ready[1], r1 & 1); ++r1; }    // density-only ends on a two-half layer
-                }
-                tc_fence_after();
-                for (int L = 0; L < kLayers; ++L) {
-                    if (L > 0) { mbar_wait(&S.act_ready[0], r0 & 1); ++r0; tc_fence_after(); }
-                    bool got_r1 = (L == 0);
-                    const uint32_t act_in = tmem + kActCol + 128u * ((L - 1) & 1);
-                    for (int h = 0; h < n_halves(L); ++h) {
-                        const uint32_t d = tmem + kAccCol + 128u * h;
-                        uint32_t accum = 0;
-                        const int n_xc = uses_x(L) ? 4 : 0;
-                        const int n_chunks = n_xc + (uses_act(L) ? 4 : 0);
-                        for (int c = 0; c < n_chunks; ++c) {
-                            const bool is_x = c < n_xc;
-                            const int kc = is_x ? c : c - n_xc;
-                            if (!is_x && kc == 2 && !got_r1) {
-                                mbar_wait(&S.act_ready[1], r1 & 1); ++r1; tc_fence_after(); got_r1 = true;
+        // ===== MMA issuer: the whole warp runs the (uniform) schedule, one elected lane issues tcgen05 =====
+        // Keeping the control flow warp-uniform lets descriptors and TMEM addresses live in uniform registers; a
+        // lane-0-only loop costs ~230 clk per MMA in R2UR waterfalls (measured), 3.6x the MMA itself.
+        const bool leader = elect_one();
+        uint32_t ws = 0, wphase = 0, xphase = 0, r0 = 0, r1 = 0;
+        const uint32_t x_base = smem_u32(S.x);
+        const uint64_t desc_hi = make_desc(0);
+        for (int t = blockIdx.x, it = 0; t < n_tiles; t += gridDim.x, ++it) {
+            mbar_wait(&S.x_full, xphase); xphase ^= 1;
+            if (it > 0) {                                                   // accumulators drained by the last epilogues
+                mbar_wait(&S.act_ready[0], r0 & 1); ++r0;
+                if (!kFull) { mbar_wait(&S.act_ready[1], r1 & 1); ++r1; }    // density-only ends on a two-half layer
+            }
+            tc_fence_after();
+            for (int L = 0; L < kLayers; ++L) {
+                if (L > 0) { mbar_wait(&S.act_ready[0], r0 & 1); ++r0; tc_fence_after(); }
+                bool got_r1 = (L == 0);
+                const uint32_t act_in = tmem + kActCol + 128u * ((L - 1) & 1);
+                for (int h = 0; h < n_halves(L); ++h) {
+                    const uint32_t d = tmem + kAccCol + 128u * h;
+                    const int n_xc = uses_x(L) ? 4 : 0;
+                    const int n_chunks = n_xc + (uses_act(L) ? 4 : 0);
+                    for (int c = 0; c < n_chunks; ++c) {
+                        const bool is_x = c < n_xc;
+                        const int kc = is_x ? c : c - n_xc;
+                        if (!is_x && kc == 2 && !got_r1) {
+                            mbar_wait(&S.act_ready[1], r1 & 1); ++r1; got_r1 = true;
+                        }
+                        mbar_wait(&S.w_full[ws], wphase);
+                        tc_fence_after();
+                        if (c == 0) { DANBO_TRACE(it, 0, L, h, 0); }
+                        const uint64_t bdesc = desc_hi | (uint64_t)((smem_u32(S.w[ws]) >> 4) & 0x3FFF);
+                        const uint32_t acc0 = c > 0 ? 1u : 0u;
+                        if (is_x) {
+                            const uint64_t adesc = desc_hi | (uint64_t)(((x_base + kc * 16384) >> 4) & 0x3FFF);
+                            if (leader) {
+                                mma_ss(d, adesc, bdesc, kIdesc, acc0);
+                                if (kc < 3) {                                   // K = 208: the last X chunk holds one k-step
+                                    mma_ss(d, adesc + 2, bdesc + 2, kIdesc, 1u);
+                                    mma_ss(d, adesc + 4, bdesc + 4, kIdesc, 1u);
+                                    mma_ss(d, adesc + 6, bdesc + 6, kIdesc, 1u);
+                                }
                             }
-                            mbar_wait(&S.w_full[ws], wphase);
-                            tc_fence_after();
-                            const uint32_t b_base = smem_u32(S.w[ws]);
-                            const int nk = (is_x && kc == 3) ? 1 : 4;             // K = 208: last X chunk holds one k-step
-#pragma unroll 1
-                            for (int j = 0; j < nk; ++j) {
-                                const uint64_t bdesc = make_desc(b_base + j * 32);
-                                if (is_x) mma_ss(d, make_desc(x_base + kc * 16384 + j * 32), bdesc, kIdesc, accum);
-                                else      mma_ts(d, act_in + kc * 32 + j * 8, bdesc, kIdesc, accum);
-                                accum = 1;
+                        } else {
+                            const uint32_t a_t = act_in + kc * 32;
+                            if (leader) {
+                                mma_ts(d, a_t, bdesc, kIdesc, acc0);
+                                mma_ts(d, a_t + 8, bdesc + 2, kIdesc, 1u);
+                                mma_ts(d, a_t + 16, bdesc + 4, kIdesc, 1u);
+                                mma_ts(d, a_t + 24, bdesc + 6, kIdesc, 1u);
                             }
+                        }
+                        if (leader) {
                             tc_commit(&S.w_empty[ws]);
-                            if (++ws == kStages) { ws = 0; wphase ^= 1; }
                             if (L == 5 && h == 1 && is_x && kc == 3) tc_commit(&S.x_empty);   // X no longer needed
                         }
-                        tc_commit(&S.acc_full[h]);
+                        __syncwarp();
+                        if (++ws == kStages) { ws = 0; wphase ^= 1; }
                     }
+                    if (leader) tc_commit(&S.acc_full[h]);
+                    __syncwarp();
+                    DANBO_TRACE(it, 0, L, h, 1);
                 }
             }
         }
     } else {
-        // ===== epilogue warps 2..5 =====
+        // ===== epilogue warps 2..9: two warps per TMEM lane quarter, each owns 64 of the 128 columns of a half =====
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        const int ch = (warp - 2) >> 2;               // which 64-column slice of every half
         const int row = q * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         const float* bias = S.heads;                  // [9][256]
@@ -246,58 +285,63 @@ mlp_kernel(const uint8_t* __restrict__ xtiles,       // [tiles][64 KB] swizzled 
         const float* w_rgb = w_alpha + 256;           // [3][128]
         const float* tail = w_rgb + 3 * 128;          // b_alpha, b_rgb[3]
         uint32_t f0 = 0, f1 = 0;
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (int t = blockIdx.x, it = 0; t < n_tiles; t += gridDim.x, ++it) {
             const int grow = t * DANBO_TILE_M + row;
             const bool valid = grow < n_rows;
             const int sample = valid ? row_sample[grow] : -1;
             const int ray = (kFull && valid) ? row_ray[grow] : 0;
-            float alpha = tail[0];
-            float rgb[3] = {tail[1], tail[2], tail[3]};
+            float alpha = ch == 0 ? tail[0] : 0.f;
+            float rgb[3] = {ch == 0 ? tail[1] : 0.f, ch == 0 ? tail[2] : 0.f, ch == 0 ? tail[3] : 0.f};
             for (int L = 0; L < kLayers; ++L) {
                 for (int h = 0; h < n_halves(L); ++h) {
                     if (h == 0) { mbar_wait(&S.acc_full[0], f0 & 1); ++f0; }
                     else        { mbar_wait(&S.acc_full[1], f1 & 1); ++f1; }
                     tc_fence_after();
-                    const uint32_t acc = tmem + lane_addr + kAccCol + 128u * h;
-                    const uint32_t act_out = tmem + lane_addr + kActCol + 128u * (L & 1) + 64u * h;
-#pragma unroll 1
-                    for (int g = 0; g < 4; ++g) {
-                        uint32_t v[32];
-                        tmem_ld32(acc + 32 * g, v);
-                        tmem_wait_ld();
-                        const int col0 = h * 128 + g * 32;
-                        if (L < 9) {
-                            const float4* b4 = reinterpret_cast<const float4*>(bias + L * 256 + col0);
+                    if (warp == 2 && lane == 0) DANBO_TRACE(it, 1, L, h, 0);
+                    const uint32_t acc = tmem + lane_addr + kAccCol + 128u * h + 64u * ch;
+                    const uint32_t act_out = tmem + lane_addr + kActCol + 128u * (L & 1) + 64u * h + 32u * ch;
+                    uint32_t v[2][32];
+                    tmem_ld32(acc, v[0]);
+                    tmem_ld32(acc + 32, v[1]);
+                    tmem_wait_ld();
+                    const int col0 = h * 128 + ch * 64;            // first output column of this thread's slice
+                    if (L < 9) {
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+                            const float4* b4 = reinterpret_cast<const float4*>(bias + L * 256 + col0 + 32 * g);
                             uint32_t pk[16];
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
                                 const float4 b = b4[i];
-                                float a0 = __uint_as_float(v[4 * i + 0]) + b.x;
-                                float a1 = __uint_as_float(v[4 * i + 1]) + b.y;
-                                float a2 = __uint_as_float(v[4 * i + 2]) + b.z;
-                                float a3 = __uint_as_float(v[4 * i + 3]) + b.w;
-                                if (L < 8) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
+                                float a0 = __uint_as_float(v[g][4 * i + 0]) + b.x;
+                                float a1 = __uint_as_float(v[g][4 * i + 1]) + b.y;
+                                float a2 = __uint_as_float(v[g][4 * i + 2]) + b.z;
+                                float a3 = __uint_as_float(v[g][4 * i + 3]) + b.w;
                                 if (L == 7) {
-                                    const float4 wa = *reinterpret_cast<const float4*>(w_alpha + col0 + 4 * i);
+                                    a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f);
+                                    const float4 wa = *reinterpret_cast<const float4*>(w_alpha + col0 + 32 * g + 4 * i);
                                     alpha = fmaf(a0, wa.x, alpha); alpha = fmaf(a1, wa.y, alpha);
                                     alpha = fmaf(a2, wa.z, alpha); alpha = fmaf(a3, wa.w, alpha);
                                 }
-                                pk[2 * i] = pack_bf16(a0, a1);
-                                pk[2 * i + 1] = pack_bf16(a2, a3);
+                                if (L < 8) { pk[2 * i] = pack_bf16_relu(a0, a1); pk[2 * i + 1] = pack_bf16_relu(a2, a3); }
+                                else       { pk[2 * i] = pack_bf16(a0, a1);      pk[2 * i + 1] = pack_bf16(a2, a3); }
                             }
                             if (kFull || L < 7) tmem_st16(act_out + 16 * g, pk);
-                        } else {
-                            const float4* b4 = reinterpret_cast<const float4*>(ray_bias + (size_t)ray * 128 + g * 32);
+                        }
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+                            const float4* b4 = reinterpret_cast<const float4*>(ray_bias + (size_t)ray * 128 + col0 + 32 * g);
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
                                 const float4 b = __ldg(b4 + i);
-                                const float a[4] = {fmaxf(__uint_as_float(v[4 * i + 0]) + b.x, 0.f),
-                                                    fmaxf(__uint_as_float(v[4 * i + 1]) + b.y, 0.f),
-                                                    fmaxf(__uint_as_float(v[4 * i + 2]) + b.z, 0.f),
-                                                    fmaxf(__uint_as_float(v[4 * i + 3]) + b.w, 0.f)};
+                                const float a[4] = {fmaxf(__uint_as_float(v[g][4 * i + 0]) + b.x, 0.f),
+                                                    fmaxf(__uint_as_float(v[g][4 * i + 1]) + b.y, 0.f),
+                                                    fmaxf(__uint_as_float(v[g][4 * i + 2]) + b.z, 0.f),
+                                                    fmaxf(__uint_as_float(v[g][4 * i + 3]) + b.w, 0.f)};
 #pragma unroll
                                 for (int k = 0; k < 3; ++k) {
-                                    const float4 w = *reinterpret_cast<const float4*>(w_rgb + k * 128 + g * 32 + 4 * i);
+                                    const float4 w = *reinterpret_cast<const float4*>(w_rgb + k * 128 + col0 + 32 * g + 4 * i);
                                     rgb[k] = fmaf(a[0], w.x, rgb[k]); rgb[k] = fmaf(a[1], w.y, rgb[k]);
                                     rgb[k] = fmaf(a[2], w.z, rgb[k]); rgb[k] = fmaf(a[3], w.w, rgb[k]);
                                 }
@@ -308,12 +352,18 @@ mlp_kernel(const uint8_t* __restrict__ xtiles,       // [tiles][64 KB] swizzled 
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&S.act_ready[h]);
+                    if (warp == 2 && lane == 0) DANBO_TRACE(it, 1, L, h, 1);
                 }
             }
-            if (sample >= 0 && sample < out_capacity) {
-                if (kFull) *reinterpret_cast<float4*>(out + (size_t)sample * 4) = make_float4(rgb[0], rgb[1], rgb[2], alpha);
-                else out[sample] = alpha;
+            // combine the two column slices of every row and write the row's output
+            if (ch == 1) S.part[row] = make_float4(rgb[0], rgb[1], rgb[2], alpha);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (ch == 0 && sample >= 0 && sample < out_capacity) {
+                const float4 o = S.part[row];
+                if (kFull) *reinterpret_cast<float4*>(out + (size_t)sample * 4) = make_float4(rgb[0] + o.x, rgb[1] + o.y, rgb[2] + o.z, alpha + o.w);
+                else out[sample] = alpha + o.w;
             }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
         }
     }
 
@@ -417,9 +467,9 @@ extern "C" int danbo_pack_mlp_weights(const float* const* w_pts, const float* co
     return 0;
 }
 
-extern "C" int danbo_mlp_forward(const void* xtiles, const void* wstream, const float* heads, const float* ray_bias,
-                                 const int* row_sample, const int* row_ray, const int* n_rows_dev, int max_rows,
-                                 float* out, int out_capacity, int density_only, int num_sms, void* stream) {
+static int mlp_launch(const void* xtiles, const void* wstream, const float* heads, const float* ray_bias,
+                      const int* row_sample, const int* row_ray, const int* n_rows_dev, int max_rows,
+                      float* out, int out_capacity, int density_only, int num_sms, long long* trace, void* stream) {
     if (max_rows <= 0) return 0;
     const int smem = (int)sizeof(mlp::Smem) + 1024;
     int max_tiles = (max_rows + DANBO_TILE_M - 1) / DANBO_TILE_M;
@@ -430,13 +480,29 @@ extern "C" int danbo_mlp_forward(const void* xtiles, const void* wstream, const 
         e = cudaFuncSetAttribute(mlp::mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
         mlp::mlp_kernel<false><<<grid, mlp::kThreads, smem, (cudaStream_t)stream>>>(
-            (const uint8_t*)xtiles, (const uint8_t*)wstream, heads, ray_bias, row_sample, row_ray, n_rows_dev, out, out_capacity);
+            (const uint8_t*)xtiles, (const uint8_t*)wstream, heads, ray_bias, row_sample, row_ray, n_rows_dev, out, out_capacity, trace);
     } else {
         e = cudaFuncSetAttribute(mlp::mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
         mlp::mlp_kernel<true><<<grid, mlp::kThreads, smem, (cudaStream_t)stream>>>(
-            (const uint8_t*)xtiles, (const uint8_t*)wstream, heads, ray_bias, row_sample, row_ray, n_rows_dev, out, out_capacity);
+            (const uint8_t*)xtiles, (const uint8_t*)wstream, heads, ray_bias, row_sample, row_ray, n_rows_dev, out, out_capacity, trace);
     }
     DANBO_CHECK_LAUNCH();
     return 0;
+}
+
+extern "C" int danbo_mlp_forward(const void* xtiles, const void* wstream, const float* heads, const float* ray_bias,
+                                 const int* row_sample, const int* row_ray, const int* n_rows_dev, int max_rows,
+                                 float* out, int out_capacity, int density_only, int num_sms, void* stream) {
+    return mlp_launch(xtiles, wstream, heads, ray_bias, row_sample, row_ray, n_rows_dev, max_rows, out, out_capacity,
+                      density_only, num_sms, nullptr, stream);
+}
+
+// Same launch, and CTA 0 writes a clock64 timeline of its first 4 tiles into trace[4*2*20*2] (profiling aid).
+extern "C" int danbo_mlp_forward_trace(const void* xtiles, const void* wstream, const float* heads, const float* ray_bias,
+                                       const int* row_sample, const int* row_ray, const int* n_rows_dev, int max_rows,
+                                       float* out, int out_capacity, int density_only, int num_sms, long long* trace,
+                                       void* stream) {
+    return mlp_launch(xtiles, wstream, heads, ray_bias, row_sample, row_ray, n_rows_dev, max_rows, out, out_capacity,
+                      density_only, num_sms, trace, stream);
 }

@@ -193,9 +193,20 @@ def ray_bias(rays, cam_idx, codes_with_mean, packed):
     return out
 
 
-def mlp_forward(xtiles, packed, rbias, active, row_ray, out, density_only=False):
-    """Runs the fused MLP over the active rows; row r is written to out[active.ids[r]]."""
+def mlp_forward(xtiles, packed, rbias, active, row_ray, out, density_only=False, trace=None):
+    """Runs the fused MLP over the active rows; row r is written to out[active.ids[r]].
+    trace: optional int64 CUDA tensor of 320 entries -> clock64 timeline of CTA 0 (profiling aid)."""
     lib = _lib.load()
+    if trace is not None:
+        dev = xtiles.device
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        _lib.check(lib.danbo_mlp_forward_trace(_p(xtiles), _p(packed.wstream), _p(packed.heads), _p(rbias),
+                                               _p(active.ids), _p(row_ray), _p(active.count), active.capacity, _p(out),
+                                               out.shape[0] if not density_only else out.numel(),
+                                               int(bool(density_only)), num_sms(idx), _p(trace), _stream()),
+                   "danbo_mlp_forward_trace")
+        _count(1)
+        return out
     dev = xtiles.device
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
     if PROFILE is not None:

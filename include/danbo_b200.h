@@ -82,6 +82,12 @@ int danbo_mlp_forward(const void* xtiles, const void* wstream, const float* head
                       const int* row_sample, const int* row_ray, const int* n_rows_dev, int max_rows, float* out,
                       int out_capacity, int density_only, int num_sms, void* stream);
 
+/* Profiling aid: the same launch as danbo_mlp_forward; CTA 0 also writes a clock64 timeline of its first 4 tiles to
+ * trace[4][2 roles: MMA issuer, epilogue][20 (layer, half)][begin, end] (320 long long). */
+int danbo_mlp_forward_trace(const void* xtiles, const void* wstream, const float* heads, const float* ray_bias,
+                            const int* row_sample, const int* row_ray, const int* n_rows_dev, int max_rows, float* out,
+                            int out_capacity, int density_only, int num_sms, long long* trace, void* stream);
+
 /* C1 + R1: raw2outputs (nerf.py:281-347) on the coarse samples, then isample_from_lineseg / sample_pdf
  * (ray_utils.py:159-203,257-291) and the sorted merge order.  raw is (n_rays*S + n_rays,4); samples whose mask is 0
  * read the ray's empty entry.  noise (n,S) already scaled, or NULL.  u_vals = linspace(0,1,S_f) (eval) or u_rand
