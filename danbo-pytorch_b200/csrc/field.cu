@@ -275,31 +275,185 @@ __global__ void sample_mask_kernel(const float* __restrict__ rays, int ray_strid
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// G1/G2 + A1-A3 + PE.  One warp per active entry; lanes = hidden units of the aggregation net.
-//   * features of bone k: lane l < 15 -> channel f = l/3 on axis a = l%3, linear interpolation over 16 bins with
-//     zero padding (closed form of misc.py:331-351), times the window exp(-2 sum x^6)   (gnn_backbone.py:802-826)
-//   * logit of a visible bone j needs layer 0 of j's tree neighbours only (the 24x24 mix has 70 non-zeros);
-//     bones the sample is outside of get blend weight exactly 0, so only visible bones are evaluated (danbo.py:406-415)
-//   * writes the encoded row X (bf16, 195 -> K 256) into its 128-row swizzled tile, ready to be an MMA A operand.
+// G1/G2 + A1-A3 + PE in three steps:
+//   pair_count / pair_scatter : bucket the (row, visible bone) pairs by bone, segments padded to 32 pairs
+//   pair_logits               : lane = one pair, warp = 32 pairs of the SAME bone, so every weight of the aggregation
+//                               net is a warp-uniform (broadcast) load and each instruction does 32 useful MACs
+//   field_rows                : lane = one row: blend weights, blended feature, positional encoding, bf16 X row
+// An earlier version with lanes = hidden units spent 1 200 warp instructions per row on shuffles and weight loads
+// (ncu: profiles/r1_ncu_field_summary.txt); this layout needs ~150.
+struct PairWork {            // int workspace: [0,24) count per bone, [24,48) scatter cursor, [64, 64+cap) pairs
+    int* base;
+    __device__ __forceinline__ int* count() const { return base; }
+    __device__ __forceinline__ int* cursor() const { return base + 24; }
+    __device__ __forceinline__ int* pairs() const { return base + 64; }
+};
+
+__device__ __forceinline__ int seg_start(const int* __restrict__ count, int j) {
+    int off = 0;
+    for (int i = 0; i < j; ++i) off += (count[i] + 31) & ~31;
+    return off;
+}
+
+template <bool kScatter>
 __global__ void __launch_bounds__(256)
-field_agg_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, int S, const float* __restrict__ z,
-                 const uint32_t* __restrict__ mask, const int* __restrict__ active_ids,
-                 const int* __restrict__ active_count, int capacity,
-                 const float* __restrict__ pose_skts, const float* __restrict__ pose_vol, int rays_per_pose,
-                 int n_poses, FieldConsts fc, uint8_t* __restrict__ xtiles, int* __restrict__ row_ray,
-                 float* __restrict__ confd /* (n_rays*S,24) or null */, float* __restrict__ hbar_out /* (rows,16) or null */) {
-    __shared__ __align__(16) __nv_bfloat16 xrow[8][DANBO_X_KPAD];     // one encoded row per warp, staged for 16 B stores
+pair_bucket_kernel(const uint32_t* __restrict__ mask, const int* __restrict__ active_ids,
+                   const int* __restrict__ active_count, int capacity, int total, PairWork pw, int pair_capacity) {
+    int count = *active_count; if (count > capacity) count = capacity;
     const int lane = threadIdx.x & 31;
-    const int wib = threadIdx.x >> 5;
-    const int warps_per_block = blockDim.x >> 5;
-    const int gwarp = blockIdx.x * warps_per_block + wib;
-    const int n_warps = gridDim.x * warps_per_block;
+    __shared__ int hist[DANBO_J];        // pairs of this block's current batch, per bone
+    __shared__ int base[DANBO_J];        // scatter: where this block's pairs of bone j start
+    for (int b0 = blockIdx.x * blockDim.x; b0 < count; b0 += gridDim.x * blockDim.x) {
+        if (threadIdx.x < DANBO_J) hist[threadIdx.x] = 0;
+        __syncthreads();
+        const int e = b0 + threadIdx.x;
+        uint32_t m = 0;
+        if (e < count) { const int id = active_ids[e]; if (id < total) m = mask[id]; }
+        uint32_t any = m;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) any |= __shfl_xor_sync(0xffffffffu, any, o);
+        // pass 1: per-warp counts -> block histogram; remember this warp's offset inside the block's range
+        int my_off = 0;                   // lane j < 24 keeps the warp's offset for bone j
+        for (uint32_t a = any; a;) {
+            const int j = __ffs(a) - 1; a &= a - 1;
+            const uint32_t b = __ballot_sync(0xffffffffu, (m >> j) & 1u);
+            int off = 0;
+            if (lane == 0) off = atomicAdd(&hist[j], __popc(b));
+            off = __shfl_sync(0xffffffffu, off, 0);
+            if (lane == j) my_off = off;
+        }
+        __syncthreads();
+        if (threadIdx.x < DANBO_J && hist[threadIdx.x]) {
+            if (!kScatter) atomicAdd(pw.count() + threadIdx.x, hist[threadIdx.x]);
+            else base[threadIdx.x] = seg_start(pw.count(), threadIdx.x) + atomicAdd(pw.cursor() + threadIdx.x, hist[threadIdx.x]);
+        }
+        if (kScatter) {
+            __syncthreads();
+            for (uint32_t a = any; a;) {
+                const int j = __ffs(a) - 1; a &= a - 1;
+                const uint32_t b = __ballot_sync(0xffffffffu, (m >> j) & 1u);
+                const int woff = __shfl_sync(0xffffffffu, my_off, j);
+                if ((m >> j) & 1u) {
+                    const int at = base[j] + woff + __popc(b & ((1u << lane) - 1));
+                    if (at < pair_capacity) pw.pairs()[at] = e;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// features of bone k at local coordinates x (closed form of misc.py:331-351 + window, gnn_backbone.py:802-826)
+__device__ __forceinline__ void bone_features(const float* __restrict__ vol_k, float x0, float x1, float x2, float (&h)[DANBO_FEAT]) {
+    const float a2 = x0 * x0, b2 = x1 * x1, c2 = x2 * x2;
+    const float win = expf(-2.f * (a2 * a2 * a2 + b2 * b2 * b2 + c2 * c2 * c2));
+    const float xs[3] = {x0, x1, x2};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float iy = ((xs[a] + 1.f) * (float)DANBO_RES - 1.f) * 0.5f;
+        const float fl = floorf(iy);
+        const float w1 = iy - fl, w0 = 1.f - w1;
+        const int i0 = (int)fl, i1 = i0 + 1;
+        const bool ok0 = i0 >= 0 && i0 < DANBO_RES, ok1 = i1 >= 0 && i1 < DANBO_RES;
+#pragma unroll
+        for (int f = 0; f < 5; ++f) {
+            const float* line = vol_k + f * (DANBO_RES * 3) + a;
+            const float v0 = ok0 ? __ldg(line + i0 * 3) : 0.f;
+            const float v1 = ok1 ? __ldg(line + i1 * 3) : 0.f;
+            h[f * 3 + a] = (v0 * w0 + v1 * w1) * win;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+pair_logits_kernel(const float* __restrict__ rays, int ray_stride, int S, const float* __restrict__ z,
+                   const int* __restrict__ active_ids, const float* __restrict__ pose_skts,
+                   const float* __restrict__ pose_vol, int rays_per_pose, int n_poses, FieldConsts fc, PairWork pw,
+                   int pair_capacity, float* __restrict__ logits /* (n_rays*S, 24), visible entries only */) {
+    const int lane = threadIdx.x & 31;
+    const int* cnt = pw.count();
+    int n_chunks = 0;
+    for (int j = 0; j < DANBO_J; ++j) n_chunks += (cnt[j] + 31) >> 5;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < n_chunks; c += warps) {
+        // bone of this chunk (warp-uniform)
+        int j = 0, first = 0;
+        for (;; ++j) { const int nc = (cnt[j] + 31) >> 5; if (c < first + nc) break; first += nc; }
+        const int in_seg = (c - first) * 32 + lane;
+        const int at = c * 32 + lane;
+        const bool live = in_seg < cnt[j] && at < pair_capacity;
+        float px = 0.f, py = 0.f, pz = 0.f;
+        int id = 0, pose = 0;
+        if (live) {
+            id = active_ids[pw.pairs()[at]];
+            const int n = id / S;
+            const float* r = rays + (size_t)n * ray_stride;
+            const float zz = z[id];
+            px = __fadd_rn(r[0], __fmul_rn(r[3], zz));
+            py = __fadd_rn(r[1], __fmul_rn(r[4], zz));
+            pz = __fadd_rn(r[2], __fmul_rn(r[5], zz));
+            pose = n / rays_per_pose; if (pose >= n_poses) pose = n_poses - 1;
+        }
+        const float* skt = pose_skts + (size_t)pose * DANBO_J * 16;
+        const float* vol = pose_vol + (size_t)pose * DANBO_J * DANBO_VOL;
+        float mix[DANBO_AGG_W];
+#pragma unroll
+        for (int o = 0; o < DANBO_AGG_W; ++o) mix[o] = 0.f;
+        uint32_t nb = kNbrMask[j];
+        while (nb) {                                    // layer 0 of the bone's tree neighbours, mixed by adjacency
+            const int k = __ffs(nb) - 1; nb &= nb - 1;
+            float x0, x1, x2, h[DANBO_FEAT];
+            bone_coords(skt + k * 16, fc.align + k * 16, fc.axis_scale + k * 3, px, py, pz, x0, x1, x2);
+            bone_features(vol + k * DANBO_VOL, x0, x1, x2, h);
+            const float adj = __ldg(fc.agg_adjw + j * DANBO_J + k) * __ldg(fc.agg_adj + j * DANBO_J + k);
+            const float4* w = reinterpret_cast<const float4*>(fc.agg_w0 + (size_t)k * DANBO_FEAT * DANBO_AGG_W);
+#pragma unroll
+            for (int i = 0; i < DANBO_FEAT; ++i) {
+                const float hi = h[i] * adj;
+#pragma unroll
+                for (int o4 = 0; o4 < DANBO_AGG_W / 4; ++o4) {
+                    const float4 wv = __ldg(w + i * (DANBO_AGG_W / 4) + o4);
+                    mix[4 * o4 + 0] = fmaf(hi, wv.x, mix[4 * o4 + 0]); mix[4 * o4 + 1] = fmaf(hi, wv.y, mix[4 * o4 + 1]);
+                    mix[4 * o4 + 2] = fmaf(hi, wv.z, mix[4 * o4 + 2]); mix[4 * o4 + 3] = fmaf(hi, wv.w, mix[4 * o4 + 3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < DANBO_AGG_W; ++o) mix[o] = fmaxf(mix[o] + __ldg(fc.agg_b0 + o), 0.f);
+        float l1[DANBO_AGG_W];
+#pragma unroll
+        for (int o = 0; o < DANBO_AGG_W; ++o) l1[o] = __ldg(fc.agg_b1 + j * DANBO_AGG_W + o);
+        const float4* w1 = reinterpret_cast<const float4*>(fc.agg_w1 + (size_t)j * DANBO_AGG_W * DANBO_AGG_W);
+#pragma unroll
+        for (int i = 0; i < DANBO_AGG_W; ++i) {
+#pragma unroll
+            for (int o4 = 0; o4 < DANBO_AGG_W / 4; ++o4) {
+                const float4 wv = __ldg(w1 + i * (DANBO_AGG_W / 4) + o4);
+                l1[4 * o4 + 0] = fmaf(mix[i], wv.x, l1[4 * o4 + 0]); l1[4 * o4 + 1] = fmaf(mix[i], wv.y, l1[4 * o4 + 1]);
+                l1[4 * o4 + 2] = fmaf(mix[i], wv.z, l1[4 * o4 + 2]); l1[4 * o4 + 3] = fmaf(mix[i], wv.w, l1[4 * o4 + 3]);
+            }
+        }
+        float a = __ldg(fc.agg_b2 + j);
+#pragma unroll
+        for (int o = 0; o < DANBO_AGG_W; ++o) a = fmaf(fmaxf(l1[o], 0.f), __ldg(fc.agg_w2 + j * DANBO_AGG_W + o), a);
+        if (live) logits[(size_t)id * DANBO_J + j] = a;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+field_rows_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, int S, const float* __restrict__ z,
+                  const uint32_t* __restrict__ mask, const int* __restrict__ active_ids,
+                  const int* __restrict__ active_count, int capacity, const float* __restrict__ pose_skts,
+                  const float* __restrict__ pose_vol, int rays_per_pose, int n_poses, FieldConsts fc,
+                  const float* __restrict__ logits, uint8_t* __restrict__ xtiles, int* __restrict__ row_ray,
+                  float* __restrict__ hbar_out /* (rows,16) or null */) {
     int count = *active_count; if (count > capacity) count = capacity;
     const int total = n_rays * S;
-    if (lane < 13) xrow[wib][DANBO_X_COLS + lane] = __float2bfloat16_rn(0.f);   // K padding 195..207 stays zero
-    for (int e = gwarp; e < count; e += n_warps) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
         const int id = active_ids[e];
-        float hbar = 0.f;                               // lane l < 15 holds blended feature l
+        float hbar[DANBO_FEAT];
+#pragma unroll
+        for (int i = 0; i < DANBO_FEAT; ++i) hbar[i] = 0.f;
         int n;
         if (id >= total) {
             n = id - total;                             // the ray's "no bone sees me" entry: h = 0
@@ -313,81 +467,52 @@ field_agg_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, int
             int pose = n / rays_per_pose; if (pose >= n_poses) pose = n_poses - 1;
             const float* skt = pose_skts + (size_t)pose * DANBO_J * 16;
             const float* vol = pose_vol + (size_t)pose * DANBO_J * DANBO_VOL;
-            // lane k < 24 owns bone k: local coordinates and window, computed once per sample
-            float bx0 = 0.f, bx1 = 0.f, bx2 = 0.f, bwin = 0.f;
-            if (lane < DANBO_J) {
-                bone_coords(skt + lane * 16, fc.align + lane * 16, fc.axis_scale + lane * 3, px, py, pz, bx0, bx1, bx2);
-                const float a2 = bx0 * bx0, b2 = bx1 * bx1, c2 = bx2 * bx2;
-                bwin = expf(-2.f * (a2 * a2 * a2 + b2 * b2 * b2 + c2 * c2 * c2));
-            }
             uint32_t m = mask[id];
-            const int f = lane / 3, a = lane - 3 * f;   // feature channel / axis of this lane (lanes < 15)
             while (m) {
                 const int j = __ffs(m) - 1; m &= m - 1;
-                float mix = 0.f, hj = 0.f;
-                uint32_t nb = kNbrMask[j];
-                while (nb) {
-                    const int k = __ffs(nb) - 1; nb &= nb - 1;
-                    const float x0 = __shfl_sync(0xffffffffu, bx0, k), x1 = __shfl_sync(0xffffffffu, bx1, k);
-                    const float x2 = __shfl_sync(0xffffffffu, bx2, k), win = __shfl_sync(0xffffffffu, bwin, k);
-                    float hk = 0.f;
-                    if (lane < DANBO_FEAT) {
-                        const float xa = a == 0 ? x0 : (a == 1 ? x1 : x2);
-                        const float iy = ((xa + 1.f) * (float)DANBO_RES - 1.f) * 0.5f;
-                        const float fl = floorf(iy);
-                        const float w1 = iy - fl, w0 = 1.f - w1;
-                        const int i0 = (int)fl, i1 = i0 + 1;
-                        const float* line = vol + k * DANBO_VOL + f * (DANBO_RES * 3) + a;
-                        const float v0 = (i0 >= 0 && i0 < DANBO_RES) ? __ldg(line + i0 * 3) : 0.f;
-                        const float v1 = (i1 >= 0 && i1 < DANBO_RES) ? __ldg(line + i1 * 3) : 0.f;
-                        hk = (v0 * w0 + v1 * w1) * win;
-                    }
-                    if (k == j) hj = hk;
-                    const float* w0p = fc.agg_w0 + (size_t)k * DANBO_FEAT * DANBO_AGG_W + lane;
-                    float l0 = 0.f;
+                float x0, x1, x2, h[DANBO_FEAT];
+                bone_coords(skt + j * 16, fc.align + j * 16, fc.axis_scale + j * 3, px, py, pz, x0, x1, x2);
+                bone_features(vol + j * DANBO_VOL, x0, x1, x2, h);
+                const float a = logits[(size_t)id * DANBO_J + j];
+                const float p = (1.f / (1.f + expf(-a))) * 1.002f - 0.001f;      // danbo.py:410, visible bone
 #pragma unroll
-                    for (int i = 0; i < DANBO_FEAT; ++i) l0 = fmaf(__shfl_sync(0xffffffffu, hk, i), __ldg(w0p + i * DANBO_AGG_W), l0);
-                    const float adj = __ldg(fc.agg_adjw + j * DANBO_J + k) * __ldg(fc.agg_adj + j * DANBO_J + k);
-                    mix = fmaf(adj, l0, mix);
-                }
-                const float o1 = fmaxf(mix + __ldg(fc.agg_b0 + lane), 0.f);
-                const float* w1p = fc.agg_w1 + (size_t)j * DANBO_AGG_W * DANBO_AGG_W + lane;
-                float l1 = 0.f;
-#pragma unroll
-                for (int i = 0; i < DANBO_AGG_W; ++i) l1 = fmaf(__shfl_sync(0xffffffffu, o1, i), __ldg(w1p + i * DANBO_AGG_W), l1);
-                const float o2 = fmaxf(l1 + __ldg(fc.agg_b1 + j * DANBO_AGG_W + lane), 0.f);
-                const float al = warp_sum(o2 * __ldg(fc.agg_w2 + j * DANBO_AGG_W + lane)) + __ldg(fc.agg_b2 + j);
-                const float p = (1.f / (1.f + expf(-al))) * 1.002f - 0.001f;      // danbo.py:410, visible bone
-                hbar = fmaf(p, hj, hbar);
-                if (confd && lane == 0) confd[(size_t)id * DANBO_J + j] = al;
+                for (int i = 0; i < DANBO_FEAT; ++i) hbar[i] = fmaf(p, h[i], hbar[i]);
             }
         }
-        if (hbar_out && lane < 16) hbar_out[(size_t)e * 16 + lane] = lane < DANBO_FEAT ? hbar : 0.f;
-        if (lane == 0) row_ray[e] = n;
+        row_ray[e] = n;
+        if (hbar_out) {
+            float4* ho = reinterpret_cast<float4*>(hbar_out + (size_t)e * 16);
+            ho[0] = make_float4(hbar[0], hbar[1], hbar[2], hbar[3]);   ho[1] = make_float4(hbar[4], hbar[5], hbar[6], hbar[7]);
+            ho[2] = make_float4(hbar[8], hbar[9], hbar[10], hbar[11]); ho[3] = make_float4(hbar[12], hbar[13], hbar[14], 0.f);
+        }
         // ---- positional encoding (cutoff_embedder.py:62-73): [h, sin(2^0 h), cos(2^0 h), ..., cos(2^5 h)] -> bf16.
-        // One sincos per feature; the five higher octaves come from the double-angle recurrence (error ~1e-6,
-        // three orders below bf16 resolution).  Column of (f, fn, i) = 15 + 30 f + 15 fn + i.
-        __nv_bfloat16* xr = xrow[wib];
-        if (lane < DANBO_FEAT) {
-            float sn, cs;
-            sincosf(hbar, &sn, &cs);
-            xr[lane] = __float2bfloat16_rn(hbar);
+        // One sincos per feature; higher octaves by the double-angle recurrence (error ~1e-6, far below bf16).
+        // Column of (octave f, fn, i) = 15 + 30 f + 15 fn + i; the row is emitted as 26 16-byte chunks.
+        float sn[DANBO_FEAT], cs[DANBO_FEAT];
 #pragma unroll
-            for (int fq = 0; fq < 6; ++fq) {
-                xr[DANBO_FEAT + 30 * fq + lane] = __float2bfloat16_rn(sn);
-                xr[DANBO_FEAT + 30 * fq + DANBO_FEAT + lane] = __float2bfloat16_rn(cs);
-                const float s2 = 2.f * sn * cs, c2 = 1.f - 2.f * sn * sn;
-                sn = s2; cs = c2;
-            }
-        }
-        __syncwarp();
+        for (int i = 0; i < DANBO_FEAT; ++i) sincosf(hbar[i], &sn[i], &cs[i]);
         const int tile = e >> 7, rr = e & 127;
         uint8_t* xt = xtiles + (size_t)tile * DANBO_X_TILE_BYTES;
-        if (lane < 26) {                                // 26 x 8 = 208 columns (13 k-steps of 16)
-            *reinterpret_cast<uint4*>(xt + sw128_offset((uint32_t)rr, (uint32_t)lane * 8)) =
-                *reinterpret_cast<const uint4*>(xr + lane * 8);
+        // 208 columns in order; emit 8 at a time.  Everything is unrolled so `col` is a compile-time constant.
+        uint32_t pk[4];
+#pragma unroll
+        for (int col = 0; col < 208; ++col) {
+            float v;
+            if (col < DANBO_FEAT) v = hbar[col];
+            else if (col < DANBO_X_COLS) {
+                const int q = col - DANBO_FEAT, rem = q % 30;
+                v = rem < DANBO_FEAT ? sn[rem] : cs[rem - DANBO_FEAT];
+            } else v = 0.f;
+            const uint32_t b = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+            if (col & 1) pk[(col & 7) >> 1] |= b << 16; else pk[(col & 7) >> 1] = b;
+            if ((col & 7) == 7)
+                *reinterpret_cast<uint4*>(xt + sw128_offset((uint32_t)rr, (uint32_t)(col - 7))) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            // after the last column of an octave (col == 14 + 30 (f+1)) advance every feature to the next octave
+            if (col >= 44 && (col - 44) % 30 == 0 && col < 194) {
+#pragma unroll
+                for (int i = 0; i < DANBO_FEAT; ++i) { const float s2 = 2.f * sn[i] * cs[i], c2 = 1.f - 2.f * sn[i] * sn[i]; sn[i] = s2; cs[i] = c2; }
+            }
         }
-        __syncwarp();
     }
 }
 
@@ -399,11 +524,11 @@ ray_bias_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, cons
                 const float* __restrict__ codes, int n_codes,
                 const float* __restrict__ wv_ray /* (155,128) transposed view/code slice of W_v, then b_v (128) */,
                 float* __restrict__ out /* (n_rays,128) */) {
-    constexpr int RB = 8, VIN = 155;
-    __shared__ float v[RB][VIN + 1];
+    constexpr int RB = 16, VIN = 155;
+    __shared__ __align__(16) float v[VIN][RB];          // inputs of 16 rays, ray-minor so one LDS.128 feeds 4 FMAs
     const int base = blockIdx.x * RB;
     for (int i = threadIdx.x; i < RB * VIN; i += blockDim.x) {
-        const int rb = i / VIN, c = i - rb * VIN;
+        const int rb = i % RB, c = i / RB;
         const int n = base + rb;
         float val = 0.f;
         if (n < n_rays) {
@@ -417,17 +542,23 @@ ray_bias_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, cons
                 val = codes[(size_t)ci * 128 + (c - 27)];
             }
         }
-        v[rb][c] = val;
+        v[c][rb] = val;
     }
     __syncthreads();
     const int o = threadIdx.x;
     float acc[RB];
 #pragma unroll
     for (int rb = 0; rb < RB; ++rb) acc[rb] = 0.f;
+#pragma unroll 5
     for (int c = 0; c < VIN; ++c) {
         const float wc = __ldg(wv_ray + c * 128 + o);
+        const float4* vr = reinterpret_cast<const float4*>(v[c]);
 #pragma unroll
-        for (int rb = 0; rb < RB; ++rb) acc[rb] = fmaf(wc, v[rb][c], acc[rb]);
+        for (int q = 0; q < RB / 4; ++q) {
+            const float4 x = vr[q];
+            acc[4 * q + 0] = fmaf(wc, x.x, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(wc, x.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(wc, x.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(wc, x.w, acc[4 * q + 3]);
+        }
     }
     const float b = wv_ray[VIN * 128 + o];
 #pragma unroll
@@ -486,17 +617,32 @@ extern "C" int danbo_sample_mask(const float* rays, int ray_stride, int n_rays, 
 extern "C" int danbo_field_agg(const float* rays, int ray_stride, int n_rays, int S, const float* z,
                                const unsigned int* mask, const int* active_ids, const int* active_count,
                                int capacity, const float* pose_skts, const float* pose_vol, int rays_per_pose,
-                               int n_poses, const float* const* consts, void* xtiles, int* row_ray, float* confd,
-                               float* hbar_out, int num_sms, void* stream) {
+                               int n_poses, const float* const* consts, void* xtiles, int* row_ray, float* logits,
+                               float* hbar_out, int* work, int pair_capacity, int num_sms, void* stream) {
     if (capacity <= 0) return 0;
-    int blocks = num_sms * 8;
-    const int need = (capacity + 7) / 8;
-    if (blocks > need) blocks = need;
-    if (blocks < 1) blocks = 1;
-    field_agg_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(rays, ray_stride, n_rays, S, z, mask, active_ids,
-                                                               active_count, capacity, pose_skts, pose_vol,
-                                                               rays_per_pose, n_poses, make_consts(consts),
-                                                               (uint8_t*)xtiles, row_ray, confd, hbar_out);
+    if (!logits || !work || pair_capacity < 32) return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(work, 0, 64 * sizeof(int), st);
+    if (e != cudaSuccess) return (int)e;
+    PairWork pw{work};
+    const FieldConsts fc = make_consts(consts);
+    const int total = n_rays * S;
+    int blocks = (capacity + 255) / 256;
+    if (blocks > num_sms * 8) blocks = num_sms * 8;
+    pair_bucket_kernel<false><<<blocks, 256, 0, st>>>(mask, active_ids, active_count, capacity, total, pw, pair_capacity);
+    DANBO_CHECK_LAUNCH();
+    pair_bucket_kernel<true><<<blocks, 256, 0, st>>>(mask, active_ids, active_count, capacity, total, pw, pair_capacity);
+    DANBO_CHECK_LAUNCH();
+    int pblocks = (pair_capacity / 32 + 3) / 4;
+    if (pblocks > num_sms * 8) pblocks = num_sms * 8;
+    pair_logits_kernel<<<pblocks, 128, 0, st>>>(rays, ray_stride, S, z, active_ids, pose_skts, pose_vol, rays_per_pose,
+                                                 n_poses, fc, pw, pair_capacity, logits);
+    DANBO_CHECK_LAUNCH();
+    int rblocks = (capacity + 127) / 128;
+    if (rblocks > num_sms * 16) rblocks = num_sms * 16;
+    field_rows_kernel<<<rblocks, 128, 0, st>>>(rays, ray_stride, n_rays, S, z, mask, active_ids, active_count, capacity,
+                                                pose_skts, pose_vol, rays_per_pose, n_poses, fc, logits,
+                                                (uint8_t*)xtiles, row_ray, hbar_out);
     DANBO_CHECK_LAUNCH();
     return 0;
 }
@@ -504,7 +650,7 @@ extern "C" int danbo_field_agg(const float* rays, int ray_stride, int n_rays, in
 extern "C" int danbo_ray_bias(const float* rays, int ray_stride, int n_rays, const int* cam_idx, const float* codes,
                               int n_codes, const float* wv_ray, float* out, void* stream) {
     if (n_rays <= 0) return 0;
-    ray_bias_kernel<<<(n_rays + 7) / 8, 128, 0, (cudaStream_t)stream>>>(rays, ray_stride, n_rays, cam_idx, codes, n_codes,
+    ray_bias_kernel<<<(n_rays + 15) / 16, 128, 0, (cudaStream_t)stream>>>(rays, ray_stride, n_rays, cam_idx, codes, n_codes,
                                                                        wv_ray, out);
     DANBO_CHECK_LAUNCH();
     return 0;

@@ -22,6 +22,24 @@ def _count(n):
         PROFILE["launches"] += n
 
 
+class _Timed:
+    """with _Timed("name"): ... -> CUDA-event pair appended to PROFILE["stages"] when stage timing is on."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        self.on = PROFILE is not None and "stages" in PROFILE
+        if self.on:
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.e1.record()
+            PROFILE["stages"].append((self.name, self.e0, self.e1))
+
+
 def _p(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
@@ -85,10 +103,11 @@ def nearfar(rays, pose_cyl, pose_skts, rays_per_pose, align, axis_scale, seg_len
         vv = torch.zeros(n, J, device=rays.device, dtype=torch.uint8)
     import numpy as np
     bound_hi = float(np.float32(bound + 1e-4))        # torch compares the fp32 hits with fp32(bound_range + eps)
-    _lib.check(lib.danbo_nearfar(_p(rays), rays.stride(0), n, _p(pose_cyl), pose_cyl.stride(0), _p(pose_skts),
-                                 int(rays_per_pose), pose_skts.shape[0], _p(align), _p(axis_scale), int(seg_len),
-                                 int(bool(use_box)), float(bound), bound_hi, _p(near), _p(far), _p(acc), n_seg,
-                                 _p(pv), _p(vv), _stream()), "danbo_nearfar")
+    with _Timed("nearfar"):
+        _lib.check(lib.danbo_nearfar(_p(rays), rays.stride(0), n, _p(pose_cyl), pose_cyl.stride(0), _p(pose_skts),
+                                     int(rays_per_pose), pose_skts.shape[0], _p(align), _p(axis_scale), int(seg_len),
+                                     int(bool(use_box)), float(bound), bound_hi, _p(near), _p(far), _p(acc), n_seg,
+                                     _p(pv), _p(vv), _stream()), "danbo_nearfar")
     _count(2)
     if return_masks:
         return near, far, pv, vv
@@ -121,18 +140,19 @@ def sample_mask(rays, S, pose_skts, rays_per_pose, consts, near=None, far=None, 
     else:
         z = z_in.contiguous()
         t_vals, z_out = None, None
-    _lib.check(lib.danbo_sample_mask(_p(rays), rays.stride(0), n, S, _p(near), _p(far), _p(t_vals), _p(t_rand),
-                                     _p(z if z_in is not None else None), _p(z_out), _p(pose_skts),
-                                     int(rays_per_pose), pose_skts.shape[0], consts.array, _p(mask), _p(active.ids),
-                                     _p(active.count), active.capacity, int(append_empty), _stream()),
-               "danbo_sample_mask")
+    with _Timed("sample_mask"):
+        _lib.check(lib.danbo_sample_mask(_p(rays), rays.stride(0), n, S, _p(near), _p(far), _p(t_vals), _p(t_rand),
+                                         _p(z if z_in is not None else None), _p(z_out), _p(pose_skts),
+                                         int(rays_per_pose), pose_skts.shape[0], consts.array, _p(mask), _p(active.ids),
+                                         _p(active.count), active.capacity, int(append_empty), _stream()),
+                   "danbo_sample_mask")
     _count(1)
     return z, mask, active
 
 
 def field_agg(rays, S, z, mask, active, pose_skts, pose_vol, rays_per_pose, consts, want_confd=False,
-              want_hbar=False):
-    """-> xtiles (uint8 tiles), row_ray (cap) int32, confd (n*S,24) or None, hbar (cap,16) or None."""
+              want_hbar=False, pairs_per_row=6):
+    """-> xtiles (uint8 tiles), row_ray (cap) int32, confd (n*S,24) [visible entries only], hbar (cap,16) or None."""
     _need_cuda(rays, z, mask, pose_skts, pose_vol)
     lib = _lib.load()
     n = rays.shape[0]
@@ -140,15 +160,18 @@ def field_agg(rays, S, z, mask, active, pose_skts, pose_vol, rays_per_pose, cons
     n_tiles = (active.capacity + TILE_M - 1) // TILE_M
     xtiles = torch.empty(n_tiles * X_TILE_BYTES, device=dev, dtype=torch.uint8)
     row_ray = torch.empty(active.capacity, device=dev, dtype=torch.int32)
-    confd = torch.zeros(n * S, J, device=dev, dtype=torch.float32) if want_confd else None
+    logits = torch.empty(n * S, J, device=dev, dtype=torch.float32)
     hbar = torch.empty(active.capacity, 16, device=dev, dtype=torch.float32) if want_hbar else None
+    pair_cap = int(pairs_per_row) * active.capacity + 24 * 32
+    work = torch.empty(64 + pair_cap, device=dev, dtype=torch.int32)
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
-    _lib.check(lib.danbo_field_agg(_p(rays), rays.stride(0), n, S, _p(z), _p(mask), _p(active.ids), _p(active.count),
-                                   active.capacity, _p(pose_skts), _p(pose_vol), int(rays_per_pose),
-                                   pose_skts.shape[0], consts.array, _p(xtiles), _p(row_ray), _p(confd), _p(hbar),
-                                   num_sms(idx), _stream()), "danbo_field_agg")
-    _count(1)
-    return xtiles, row_ray, confd, hbar
+    with _Timed("field_agg"):
+        _lib.check(lib.danbo_field_agg(_p(rays), rays.stride(0), n, S, _p(z), _p(mask), _p(active.ids), _p(active.count),
+                                       active.capacity, _p(pose_skts), _p(pose_vol), int(rays_per_pose),
+                                       pose_skts.shape[0], consts.array, _p(xtiles), _p(row_ray), _p(logits), _p(hbar),
+                                       _p(work), pair_cap, num_sms(idx), _stream()), "danbo_field_agg")
+    _count(4)
+    return xtiles, row_ray, logits, hbar
 
 
 class PackedMLP:
@@ -187,8 +210,9 @@ def ray_bias(rays, cam_idx, codes_with_mean, packed):
     lib = _lib.load()
     n = rays.shape[0]
     out = torch.empty(n, 128, device=rays.device, dtype=torch.float32)
-    _lib.check(lib.danbo_ray_bias(_p(rays), rays.stride(0), n, _p(cam_idx), _p(codes_with_mean),
-                                  codes_with_mean.shape[0] - 1, _p(packed.wv_ray), _p(out), _stream()), "danbo_ray_bias")
+    with _Timed("ray_bias"):
+        _lib.check(lib.danbo_ray_bias(_p(rays), rays.stride(0), n, _p(cam_idx), _p(codes_with_mean),
+                                      codes_with_mean.shape[0] - 1, _p(packed.wv_ray), _p(out), _stream()), "danbo_ray_bias")
     _count(1)
     return out
 
@@ -239,11 +263,12 @@ def composite_resample(rays, S, S_f, raw, mask, z, noise=None, inv_B=1.0, u_rand
             out["inds"] = torch.empty(n, S_f, device=dev, dtype=torch.int32)
         if u_rand is None:
             u_vals = _linspace01(S_f, dev.index if dev.index is not None else torch.cuda.current_device())
-    _lib.check(lib.danbo_composite_resample(_p(rays), rays.stride(0), n, S, S_f, _p(raw), _p(mask), _p(z), _p(noise),
-                                            float(inv_B), _p(u_vals), _p(u_rand), _p(out["weights"]), _p(out["alpha"]),
-                                            _p(out["rgb_map"]), _p(out["disp_map"]), _p(out["acc_map"]),
-                                            _p(out.get("z_samples")), _p(out.get("z_all")), _p(out.get("order")),
-                                            _p(out.get("inds")), _stream()), "danbo_composite_resample")
+    with _Timed("composite_resample"):
+        _lib.check(lib.danbo_composite_resample(_p(rays), rays.stride(0), n, S, S_f, _p(raw), _p(mask), _p(z), _p(noise),
+                                                float(inv_B), _p(u_vals), _p(u_rand), _p(out["weights"]), _p(out["alpha"]),
+                                                _p(out["rgb_map"]), _p(out["disp_map"]), _p(out["acc_map"]),
+                                                _p(out.get("z_samples")), _p(out.get("z_all")), _p(out.get("order")),
+                                                _p(out.get("inds")), _stream()), "danbo_composite_resample")
     _count(1)
     return out
 
@@ -263,10 +288,11 @@ def merge_composite(rays, S_c, S_f, raw0, mask0, raw1, mask1, z_all, order, nois
         out["confd"] = f(n, St, J)
     if want_invalid:
         out["part_invalid"] = f(n, St, J)
-    _lib.check(lib.danbo_merge_composite(_p(rays), rays.stride(0), n, S_c, S_f, _p(raw0), _p(mask0), _p(raw1), _p(mask1),
-                                         _p(z_all), _p(order), _p(noise), float(inv_B), _p(out["weights"]),
-                                         _p(out["alpha"]), _p(out["rgb_map"]), _p(out["disp_map"]), _p(out["acc_map"]),
-                                         _p(out.get("raw")), _p(confd0), _p(confd1), _p(out.get("confd")),
-                                         _p(out.get("part_invalid")), _stream()), "danbo_merge_composite")
+    with _Timed("merge_composite"):
+        _lib.check(lib.danbo_merge_composite(_p(rays), rays.stride(0), n, S_c, S_f, _p(raw0), _p(mask0), _p(raw1), _p(mask1),
+                                             _p(z_all), _p(order), _p(noise), float(inv_B), _p(out["weights"]),
+                                             _p(out["alpha"]), _p(out["rgb_map"]), _p(out["disp_map"]), _p(out["acc_map"]),
+                                             _p(out.get("raw")), _p(confd0), _p(confd1), _p(out.get("confd")),
+                                             _p(out.get("part_invalid")), _stream()), "danbo_merge_composite")
     _count(1)
     return out

@@ -78,8 +78,11 @@ class GraphNet(nn.Module):
             scale = sk.initial_axis_scale(skel_profile, base_scale)
         self.init_scale = scale.clone()
         self.axis_scale = nn.Parameter(scale, requires_grad=opt_scale)
-        self.mask = torch.ones(1, J, 1)
-        self.mask[:, 0] = 0.                                    # mask_root
+        mask = torch.ones(1, J, 1)
+        mask[:, 0] = 0.                                         # mask_root
+        # non-persistent buffer: follows .to(device) (a per-call host->device copy would synchronise the stream) but
+        # stays out of the state_dict, like the reference's plain attribute (gnn_backbone.py:669-670)
+        self.register_buffer("mask", mask, persistent=False)
 
     def get_axis_scale(self):
         return self.axis_scale
@@ -90,7 +93,7 @@ class GraphNet(nn.Module):
     def forward(self, w):
         """w (G,24,66) -> (G,24,240).  Layer 0's output is doubled, as in the reference (SURVEY F3:
         `if i == skip_gcn` with skip_gcn=False, gnn_backbone.py:695-699)."""
-        n = self.mask.to(w.device) * w
+        n = self.mask * w
         n = self.layers[0](n)
         n = F.relu(n + n)
         n = F.relu(self.layers[1](n))

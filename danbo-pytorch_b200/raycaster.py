@@ -45,6 +45,7 @@ class RayCaster(nn.Module):
         self.child_idxs = child
         self._packed = None
         self._packed_key = None
+        self._align_dev = None
 
     # ------------------------------------------------------------------------------------------------ dispatch
     def forward(self, *args, fwd_type="", **kwargs):
@@ -88,7 +89,9 @@ class RayCaster(nn.Module):
     def _consts(self):
         net = self.network
         dev = self._device()
-        return K.FieldConsts(self.transforms[0].to(dev), net.graph_net.axis_scale, net.agg_tensors())
+        if self._align_dev is None or self._align_dev.device != dev:
+            self._align_dev = self.transforms[0].to(dev).float().contiguous()      # once; a per-call H2D copy would sync
+        return K.FieldConsts(self._align_dev, net.graph_net.axis_scale, net.agg_tensors())
 
     def _packed_mlp(self):
         net = self.network
@@ -205,7 +208,8 @@ class RayCaster(nn.Module):
         K.mlp_forward(xt1, packed, rbias, act1, rr1, raw1)
         noise1 = (rand["noise1"] * (raw_noise_std * B)).contiguous() if ("noise1" in rand and raw_noise_std > 0) else None
         c1 = K.merge_composite(rays, S_c, S_f, raw0, mask0, raw1, mask1, c0["z_all"], c0["order"], noise=noise1,
-                               inv_B=inv_B, want_raw=stages is not None, confd0=confd0, confd1=confd1,
+                               inv_B=inv_B, want_raw=stages is not None, confd0=confd0 if training else None,
+                               confd1=confd1 if training else None,
                                want_invalid=training)
         ret = {"rgb_map": c1["rgb_map"], "disp_map": c1["disp_map"], "acc_map": c1["acc_map"], "alpha": c1["alpha"],
                "T_i": c1["weights"], "rgb0": c0["rgb_map"], "disp0": c0["disp_map"], "acc0": c0["acc_map"],

@@ -51,13 +51,16 @@ int danbo_sample_mask(const float* rays, int ray_stride, int n_rays, int S, cons
  * FactorizeGNN.sample_from_volume / factorize_grid_sample (gnn_backbone.py:787-828, core/networks/misc.py:331-351),
  * forward_blend -> MixGNN (core/networks/danbo.py:201-216, gnn_backbone.py:567-629), sigmoid blend weights
  * (danbo.py:406-415), blend (danbo.py:299-300), Embedder (core/cutoff_embedder.py:62-73).
- * pose_vol (n_poses,24,240) = graph-net output.  Writes bf16 rows into xtiles ((capacity+127)/128 tiles of 64 KB,
- * swizzled MMA operand image), row_ray[row], and optionally confd (n_rays*S,24; visible bones only) and
- * hbar (rows,16). */
+ * pose_vol (n_poses,24,240) = graph-net output.  Four launches: bucket the (row, visible bone) pairs by bone (count,
+ * scatter), evaluate the aggregation net per pair, then blend + encode per row.  Writes bf16 rows into xtiles
+ * ((capacity+127)/128 tiles of 64 KB, swizzled MMA operand image), row_ray[row], the blend logits ("confd") of every
+ * visible (sample, bone) into logits (n_rays*S,24) and optionally hbar (rows,16).
+ * work: int workspace of 64 + pair_capacity entries; pair_capacity >= number of visible pairs + 24*32. */
 int danbo_field_agg(const float* rays, int ray_stride, int n_rays, int S, const float* z, const unsigned int* mask,
                     const int* active_ids, const int* active_count, int capacity, const float* pose_skts,
                     const float* pose_vol, int rays_per_pose, int n_poses, const float* const* consts, void* xtiles,
-                    int* row_ray, float* confd, float* hbar_out, int num_sms, void* stream);
+                    int* row_ray, float* logits, float* hbar_out, int* work, int pair_capacity, int num_sms,
+                    void* stream);
 
 /* V1 folded into the view layer: out (n_rays,128) = W_v[:,256:411] . [PE(rays_d) ; frame code] + b_v
  * (core/networks/nerf.py:252-279, core/networks/embedding.py:86-108).  codes is (n_codes+1,128) with the mean code in
