@@ -1,0 +1,89 @@
+"""Autograd root of the training path: one torch.autograd.Function around a render block.
+
+Forward = the same kernel sequence as inference (train mode keeps the bf16 MLP activations, the encoded rows and the
+pair lists); backward = hand-written kernels for compositing, MLP, aggregation net, feature gather and ray bias
+(csrc/backward_*.cu, composite.cu).  Gradient sources are rgb_map, acc_map, rgb0, acc0 and confd, exactly the tensors the
+trainer's losses read (core/trainer.py:396-422,507-536); disp / alpha / T_i / part_invalid are non-differentiable, as in
+the reference where they are used only under comparisons.  The per-pose graph net stays in PyTorch: its output `vol` is
+an input of this Function and receives d vol.
+"""
+import torch
+
+from . import kernels as K
+
+MLP_NAMES = [f"pts_linears.{i}.{w}" for i in range(8) for w in ("weight", "bias")] + [
+    "alpha_linear.weight", "alpha_linear.bias", "feature_linear.weight", "feature_linear.bias",
+    "views_linears.0.weight", "views_linears.0.bias", "rgb_linear.weight", "rgb_linear.bias"]
+AGG_NAMES = ["prob_linears.layers.0.lin.weight", "prob_linears.layers.0.adj_w", "prob_linears.layers.0.bias",
+             "prob_linears.layers.1.weight", "prob_linears.layers.1.bias", "prob_linears.layers.2.weight",
+             "prob_linears.layers.2.bias"]
+OTHER_NAMES = ["framecodes.codes.weight", "graph_net.axis_scale"]
+PARAM_NAMES = MLP_NAMES + AGG_NAMES + OTHER_NAMES
+OUT_KEYS = ["rgb_map", "disp_map", "acc_map", "alpha", "T_i", "rgb0", "disp0", "acc0", "alpha0", "confd", "part_invalid"]
+DIFF_KEYS = ("rgb_map", "acc_map", "rgb0", "acc0", "confd")
+
+
+class _RenderBlock(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, caster, cfg, vol, *params):
+        keep = {}
+        with torch.no_grad():
+            ret = caster._render_block(cfg["rays"], 0, cfg["skip"], cfg["pose_skts"], cfg["pose_cyls"], vol, cfg["cam_idx"],
+                                       cfg["codes"], cfg["consts"], cfg["packed"], cfg["S_c"], cfg["S_f"], cfg["B"],
+                                       cfg["raw_noise_std"], cfg["perturb"], True, cfg["nanmean_chunk"], cfg["rand"],
+                                       cfg["stages"], keep=keep)
+        ctx.keep = keep
+        ctx.caster = caster
+        ctx.params = params
+        ctx.vol_shape = vol.shape
+        outs = tuple(ret[k] for k in OUT_KEYS)
+        ctx.mark_non_differentiable(*[ret[k] for k in OUT_KEYS if k not in DIFF_KEYS])
+        return outs
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        k = ctx.keep
+        g = dict(zip(OUT_KEYS, gouts))
+        rays, dev = k["rays"], k["rays"].device
+        n, S_c, S_f = rays.shape[0], k["S_c"], k["S_f"]
+        zeros = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
+        cg = lambda t, *s: zeros(*s) if t is None else t.contiguous().float()
+        g_rgb, g_acc = cg(g["rgb_map"], n, 3), cg(g["acc_map"], n)
+        g_rgb0, g_acc0 = cg(g["rgb0"], n, 3), cg(g["acc0"], n)
+        g_confd = None if g["confd"] is None else g["confd"].contiguous().float()
+        P = dict(zip(PARAM_NAMES, ctx.params))
+        G = {name: torch.zeros_like(p, dtype=torch.float32) for name, p in P.items()}
+        d_raw0, d_raw1 = zeros(n * S_c + n, 4), zeros(n * S_f, 4)
+        gl0 = gl1 = None
+        if g_confd is not None:
+            gl0 = torch.empty(n * S_c, K.J, device=dev, dtype=torch.float32)
+            gl1 = torch.empty(n * S_f, K.J, device=dev, dtype=torch.float32)
+        # compositing (fine/merged then coarse)
+        K.merge_composite_bwd(rays, S_c, S_f, k["raw0"], k["mask0"], k["raw1"], k["mask1"], k["z_all"], k["order"],
+                              k["noise1"], k["inv_B"], g_rgb, g_acc, g_confd, d_raw0, d_raw1, gl0, gl1)
+        K.composite_bwd(rays, S_c, k["raw0"], k["mask0"], k["z0"], k["noise0"], k["inv_B"], g_rgb0, g_acc0, d_raw0)
+        # MLP + field, per pass
+        d_ray_bias = zeros(n, 128)
+        d_vol = zeros(*ctx.vol_shape)
+        d_vol_blk = d_vol[k["p0"]:]
+        agg_grads = [G[nm] for nm in AGG_NAMES] + [d_vol_blk, G["graph_net.axis_scale"]]
+        for (d_raw, S, z, mask, act, fo, sv, gl) in ((d_raw0, S_c, k["z0"], k["mask0"], k["act0"], k["f0"], k["sv0"], gl0),
+                                                    (d_raw1, S_f, k["z1"], k["mask1"], k["act1"], k["f1"], k["sv1"], gl1)):
+            dX = K.mlp_backward(P, G, d_raw, act, fo, sv, d_ray_bias)
+            K.field_agg_bwd(rays, S, z, mask, act, k["p_skts"], k["p_vol"], k["skip"], k["consts"], fo, dX, gl, agg_grads)
+        K.ray_bias_bwd(rays, k["cam_idx"], k["codes"], P["views_linears.0.weight"], d_ray_bias,
+                       G["views_linears.0.weight"], G["views_linears.0.bias"], G["framecodes.codes.weight"])
+        ctx.keep = None
+        return (None, None, d_vol) + tuple(G[name] for name in PARAM_NAMES)
+
+
+def render_block_with_grad(caster, rays, skip, pose_skts, pose_cyls, vol, cam_idx, codes, consts, packed, S_c, S_f, B,
+                           raw_noise_std, perturb, nanmean_chunk, rand, stages):
+    named = dict(caster.network.named_parameters())
+    params = [named[n] for n in PARAM_NAMES]
+    cfg = dict(rays=rays, skip=skip, pose_skts=pose_skts, pose_cyls=pose_cyls, cam_idx=cam_idx, codes=codes, consts=consts,
+               packed=packed, S_c=S_c, S_f=S_f, B=B, raw_noise_std=raw_noise_std, perturb=perturb,
+               nanmean_chunk=nanmean_chunk, rand=rand, stages=stages)
+    outs = _RenderBlock.apply(caster, cfg, vol, *params)
+    return dict(zip(OUT_KEYS, outs))

@@ -271,3 +271,205 @@ extern "C" int danbo_merge_composite(const float* rays, int ray_stride, int n_ra
     DANBO_CHECK_LAUNCH();
     return 0;
 }
+
+// =========================================================================================================
+// Backward of C1 (+ R2): gradients of the rendered maps w.r.t. raw.  Autograd of nerf.py:297-347 as it is reached
+// from trainer.py:405-409: sources are rgb_map and acc_map (disp_map, alpha and weights carry no gradient), the
+// importance samples are detached (ray_utils.py:287), so each ray is independent:
+//   w_i = a_i T_i, T_i = prod_{k<i}(1 - a_k + 1e-10)
+//   dL/dw_i   = g_rgb . c_i + g_acc [sum w < 1]
+//   dL/da_i   = dw_i T_i - (sum_{k>i} dw_k w_k) / (1 - a_i + 1e-10)
+//   dL/dsig_i = da_i * dist_i * (1 - a_i) for sigma_i > 0,   dL/dc_i = w_i g_rgb,  c = 1.002 sigmoid(raw) - 0.001
+// One warp per ray, forward values recomputed from raw (nothing saved).  Gradients of samples no bone sees are
+// summed into the ray's empty entry.
+namespace danbo {
+
+template <class Fetch, class Emit>
+__device__ __forceinline__ void composite_ray_bwd(RaySmem& sm, int S, int lane, float norm_d, float inv_B,
+                                                  const float* __restrict__ noise_row, Fetch fetch, float gr, float gg,
+                                                  float gb, float gacc, Emit emit) {
+    const int epl = (S + 31) / 32;
+    float al[kEPL], sgm[kEPL], dist[kEPL], cr[kEPL], cg[kEPL], cb[kEPL];
+    double lp = 1.0;
+#pragma unroll
+    for (int e = 0; e < kEPL; ++e) {
+        const int i = lane * epl + e;
+        al[e] = 0.f; sgm[e] = 0.f; dist[e] = 0.f; cr[e] = cg[e] = cb[e] = 0.f;
+        if (e < epl && i < S) {
+            const float4 raw = fetch(i);
+            float d = (i + 1 < S) ? __fsub_rn(sm.z[i + 1], sm.z[i]) : 1e10f;
+            d = __fmul_rn(d, norm_d);
+            dist[e] = d;
+            cr[e] = 1.f / (1.f + expf(-raw.x)); cg[e] = 1.f / (1.f + expf(-raw.y)); cb[e] = 1.f / (1.f + expf(-raw.z));
+            float sg = __fmul_rn(raw.w, inv_B);
+            if (noise_row) sg = __fadd_rn(sg, noise_row[i]);
+            sgm[e] = sg;
+            al[e] = __fsub_rn(1.f, expf(-__fmul_rn(fmaxf(sg, 0.f), d)));
+            lp *= (double)__fadd_rn(__fsub_rn(1.f, al[e]), 1e-10f);
+        }
+    }
+    double T = warp_excl_prod(lp, lane);
+    float w[kEPL], Tf[kEPL], dw[kEPL];
+    float wsum = 0.f;
+#pragma unroll
+    for (int e = 0; e < kEPL; ++e) {
+        const int i = lane * epl + e;
+        w[e] = 0.f; Tf[e] = 0.f;
+        if (e < epl && i < S) {
+            Tf[e] = (float)T;
+            w[e] = al[e] * Tf[e];
+            T *= (double)__fadd_rn(__fsub_rn(1.f, al[e]), 1e-10f);
+            wsum += w[e];
+        }
+    }
+    wsum = warp_sum(wsum);
+    const float ga = (wsum < 1.f) ? gacc : 0.f;                 // acc = min(sum w, 1)
+    // suffix sums of dw_k w_k: lane-local reverse pass + warp suffix scan
+    float loc = 0.f;
+#pragma unroll
+    for (int e = 0; e < kEPL; ++e) {
+        const float c0 = cr[e] * 1.002f - 0.001f, c1 = cg[e] * 1.002f - 0.001f, c2 = cb[e] * 1.002f - 0.001f;
+        dw[e] = gr * c0 + gg * c1 + gb * c2 + ga;
+        loc += dw[e] * w[e];
+    }
+    float inc = loc;                                            // inclusive suffix over lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const float u = __shfl_down_sync(0xffffffffu, inc, o); if (lane + o < 32) inc += u; }
+    float suffix = inc - loc;                                   // sum over lanes > this lane
+#pragma unroll
+    for (int e = kEPL - 1; e >= 0; --e) {
+        const int i = lane * epl + e;
+        if (e < epl && i < S) {
+            const float om = __fadd_rn(__fsub_rn(1.f, al[e]), 1e-10f);
+            const float da = dw[e] * Tf[e] - suffix / om;
+            suffix += dw[e] * w[e];
+            float4 g;
+            g.x = w[e] * gr * 1.002f * cr[e] * (1.f - cr[e]);
+            g.y = w[e] * gg * 1.002f * cg[e] * (1.f - cg[e]);
+            g.z = w[e] * gb * 1.002f * cb[e] * (1.f - cb[e]);
+            g.w = sgm[e] > 0.f ? da * dist[e] * (1.f - al[e]) * inv_B : 0.f;
+            emit(i, g);
+        }
+    }
+}
+
+// d raw0 (+)= backward of the coarse composite; d raw0 is (n*S + n, 4), zero-initialised by the caller.
+__global__ void __launch_bounds__(32 * kWarpsPerBlock)
+composite_bwd_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, int S, const float* __restrict__ raw,
+                     const uint32_t* __restrict__ mask, const float* __restrict__ z, const float* __restrict__ noise,
+                     float inv_B, const float* __restrict__ g_rgb, const float* __restrict__ g_acc,
+                     float* __restrict__ d_raw) {
+    __shared__ RaySmem smem[kWarpsPerBlock];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int n = blockIdx.x * kWarpsPerBlock + wib;
+    if (n >= n_rays) return;
+    RaySmem& sm = smem[wib];
+    const float* r = rays + (size_t)n * ray_stride;
+    const float norm_d = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(r[3], r[3]), __fmul_rn(r[4], r[4])), __fmul_rn(r[5], r[5])));
+    for (int i = lane; i < S; i += 32) sm.z[i] = z[(size_t)n * S + i];
+    __syncwarp();
+    const float4* raw4 = reinterpret_cast<const float4*>(raw);
+    const float4 empty = raw4[(size_t)n_rays * S + n];
+    auto fetch = [&](int i) { return mask[(size_t)n * S + i] ? raw4[(size_t)n * S + i] : empty; };
+    float4 ge = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto emit = [&](int i, float4 g) {
+        if (mask[(size_t)n * S + i]) {
+            float4* d = reinterpret_cast<float4*>(d_raw) + (size_t)n * S + i;
+            float4 o = *d; o.x += g.x; o.y += g.y; o.z += g.z; o.w += g.w; *d = o;
+        } else { ge.x += g.x; ge.y += g.y; ge.z += g.z; ge.w += g.w; }
+    };
+    composite_ray_bwd(sm, S, lane, norm_d, inv_B, noise ? noise + (size_t)n * S : nullptr, fetch,
+                      g_rgb[n * 3], g_rgb[n * 3 + 1], g_rgb[n * 3 + 2], g_acc[n], emit);
+    ge.x = warp_sum(ge.x); ge.y = warp_sum(ge.y); ge.z = warp_sum(ge.z); ge.w = warp_sum(ge.w);
+    if (lane == 0) {
+        float4* d = reinterpret_cast<float4*>(d_raw) + (size_t)n_rays * S + n;
+        float4 o = *d; o.x += ge.x; o.y += ge.y; o.z += ge.z; o.w += ge.w; *d = o;
+    }
+}
+
+// backward of the merged composite: scatters to d raw0 (coarse + empty entries) and d raw1 (fine); also routes the
+// gradient of the merged blend logits (soft-softmax loss, trainer.py:507-536) back to the two sparse logit buffers.
+__global__ void __launch_bounds__(32 * kWarpsPerBlock)
+merge_composite_bwd_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, int S_c, int S_f,
+                           const float* __restrict__ raw0, const uint32_t* __restrict__ mask0,
+                           const float* __restrict__ raw1, const uint32_t* __restrict__ mask1,
+                           const float* __restrict__ z_all, const int* __restrict__ order,
+                           const float* __restrict__ noise, float inv_B, const float* __restrict__ g_rgb,
+                           const float* __restrict__ g_acc, const float* __restrict__ g_confd /* (n,St,24) or null */,
+                           float* __restrict__ d_raw0, float* __restrict__ d_raw1,
+                           float* __restrict__ d_logit0 /* (n*S_c,24) */, float* __restrict__ d_logit1 /* (n*S_f,24) */) {
+    __shared__ RaySmem smem[kWarpsPerBlock];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int n = blockIdx.x * kWarpsPerBlock + wib;
+    if (n >= n_rays) return;
+    RaySmem& sm = smem[wib];
+    const int St = S_c + S_f;
+    const float* r = rays + (size_t)n * ray_stride;
+    const float norm_d = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(r[3], r[3]), __fmul_rn(r[4], r[4])), __fmul_rn(r[5], r[5])));
+    for (int i = lane; i < St; i += 32) { sm.z[i] = z_all[(size_t)n * St + i]; sm.order[i] = order[(size_t)n * St + i]; }
+    __syncwarp();
+    const float4* r0 = reinterpret_cast<const float4*>(raw0);
+    const float4* r1 = reinterpret_cast<const float4*>(raw1);
+    const float4 empty = r0[(size_t)n_rays * S_c + n];
+    auto fetch = [&](int i) {
+        const int src = sm.order[i];
+        if (src < S_c) return mask0[(size_t)n * S_c + src] ? r0[(size_t)n * S_c + src] : empty;
+        return mask1[(size_t)n * S_f + src - S_c] ? r1[(size_t)n * S_f + src - S_c] : empty;
+    };
+    float4 ge = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto emit = [&](int i, float4 g) {
+        const int src = sm.order[i];
+        float4* d = nullptr;
+        if (src < S_c) { if (mask0[(size_t)n * S_c + src]) d = reinterpret_cast<float4*>(d_raw0) + (size_t)n * S_c + src; }
+        else if (mask1[(size_t)n * S_f + src - S_c]) d = reinterpret_cast<float4*>(d_raw1) + (size_t)n * S_f + src - S_c;
+        if (d) { float4 o = *d; o.x += g.x; o.y += g.y; o.z += g.z; o.w += g.w; *d = o; }
+        else { ge.x += g.x; ge.y += g.y; ge.z += g.z; ge.w += g.w; }
+    };
+    composite_ray_bwd(sm, St, lane, norm_d, inv_B, noise ? noise + (size_t)n * St : nullptr, fetch,
+                      g_rgb[n * 3], g_rgb[n * 3 + 1], g_rgb[n * 3 + 2], g_acc[n], emit);
+    ge.x = warp_sum(ge.x); ge.y = warp_sum(ge.y); ge.z = warp_sum(ge.z); ge.w = warp_sum(ge.w);
+    if (lane == 0) {
+        float4* d = reinterpret_cast<float4*>(d_raw0) + (size_t)n_rays * S_c + n;
+        float4 o = *d; o.x += ge.x; o.y += ge.y; o.z += ge.z; o.w += ge.w; *d = o;
+    }
+    if (g_confd) {
+        for (int e = lane; e < St * DANBO_J; e += 32) {
+            const int i = e / DANBO_J, j = e - i * DANBO_J;
+            const int src = sm.order[i];
+            const bool coarse = src < S_c;
+            const size_t sidx = coarse ? (size_t)n * S_c + src : (size_t)n * S_f + src - S_c;
+            const uint32_t m = coarse ? mask0[sidx] : mask1[sidx];
+            if ((m >> j) & 1u) (coarse ? d_logit0 : d_logit1)[sidx * DANBO_J + j] = g_confd[(size_t)n * St * DANBO_J + e];
+        }
+    }
+}
+
+}  // namespace danbo
+
+extern "C" int danbo_composite_bwd(const float* rays, int ray_stride, int n_rays, int S, const float* raw,
+                                   const unsigned int* mask, const float* z, const float* noise, float inv_B,
+                                   const float* g_rgb, const float* g_acc, float* d_raw, void* stream) {
+    if (n_rays <= 0) return 0;
+    if (S > danbo::kMaxS) return -1;
+    const int G = (n_rays + danbo::kWarpsPerBlock - 1) / danbo::kWarpsPerBlock;
+    danbo::composite_bwd_kernel<<<G, 32 * danbo::kWarpsPerBlock, 0, (cudaStream_t)stream>>>(
+        rays, ray_stride, n_rays, S, raw, mask, z, noise, inv_B, g_rgb, g_acc, d_raw);
+    DANBO_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int danbo_merge_composite_bwd(const float* rays, int ray_stride, int n_rays, int S_c, int S_f,
+                                         const float* raw0, const unsigned int* mask0, const float* raw1,
+                                         const unsigned int* mask1, const float* z_all, const int* order,
+                                         const float* noise, float inv_B, const float* g_rgb, const float* g_acc,
+                                         const float* g_confd, float* d_raw0, float* d_raw1, float* d_logit0,
+                                         float* d_logit1, void* stream) {
+    if (n_rays <= 0) return 0;
+    if (S_c + S_f > danbo::kMaxS) return -1;
+    const int G = (n_rays + danbo::kWarpsPerBlock - 1) / danbo::kWarpsPerBlock;
+    danbo::merge_composite_bwd_kernel<<<G, 32 * danbo::kWarpsPerBlock, 0, (cudaStream_t)stream>>>(
+        rays, ray_stride, n_rays, S_c, S_f, raw0, mask0, raw1, mask1, z_all, order, noise, inv_B, g_rgb, g_acc, g_confd,
+        d_raw0, d_raw1, d_logit0, d_logit1);
+    DANBO_CHECK_LAUNCH();
+    return 0;
+}

@@ -2,68 +2,9 @@
 // per-bone feature gather + aggregation net + blend + positional encoding (G1, G2, A1-A3), per-ray view bias (V1).
 // Reference rows: SURVEY.md §8(a).  All kernels are HBM / latency bound integer-and-fp32 work; they share one
 // layout rule: one thread (or one warp) per ray sample, pose tables read through L1 as warp-uniform float4 loads.
-#include "common.cuh"
-#include <math.h>
+#include "field_common.cuh"
 
 namespace danbo {
-
-struct FieldConsts {
-    const float* align;       // (24,4,4) bone-align transforms A_j                     raycasters.py:548-591
-    const float* axis_scale;  // (24,3)  per-bone half extents (|.| applied here)       gnn_backbone.py:802
-    const float* agg_w0;      // (24,15,32) prob_linears.layers.0.lin.weight
-    const float* agg_adjw;    // (24,24) prob_linears.layers.0.adj_w
-    const float* agg_adj;     // (24,24) prob_linears.layers.0.adj (tree + self, 0/1)
-    const float* agg_b0;      // (32)
-    const float* agg_w1;      // (24,32,32)
-    const float* agg_b1;      // (24,32)
-    const float* agg_w2;      // (24,32)
-    const float* agg_b2;      // (24)
-};
-
-// tree neighbours (self, parent, children) of every SMPL joint as bit masks (gnn_backbone.py:18-34)
-__constant__ uint32_t kNbrMask[DANBO_J] = {
-    0x0000000Fu, 0x00000013u, 0x00000025u, 0x00000049u, 0x00000092u, 0x00000124u, 0x00000248u, 0x00000490u,
-    0x00000920u, 0x00007240u, 0x00000480u, 0x00000900u, 0x00009200u, 0x00012200u, 0x00024200u, 0x00009000u,
-    0x00052000u, 0x000A4000u, 0x00150000u, 0x002A0000u, 0x00540000u, 0x00A80000u, 0x00500000u, 0x00A00000u};
-
-// ---------------------------------------------------------------------------------------------------------
-// x_j = (A_j (R_j p + t_j) + a_j) / |s_j| for one joint, in the reference's two-step order with a true divide.
-// encoders.py:288-303 (transform_batch_pts), :442-444 (bone align), gnn_backbone.py:802 (scale)
-__device__ __forceinline__ void bone_aligned(const float* __restrict__ skt, const float* __restrict__ A,
-                                             float px, float py, float pz, float& t0, float& t1, float& t2) {
-    const float4 r0 = __ldg(reinterpret_cast<const float4*>(skt));
-    const float4 r1 = __ldg(reinterpret_cast<const float4*>(skt) + 1);
-    const float4 r2 = __ldg(reinterpret_cast<const float4*>(skt) + 2);
-    const float l0 = fmaf(r0.z, pz, fmaf(r0.y, py, fmaf(r0.x, px, r0.w)));
-    const float l1 = fmaf(r1.z, pz, fmaf(r1.y, py, fmaf(r1.x, px, r1.w)));
-    const float l2 = fmaf(r2.z, pz, fmaf(r2.y, py, fmaf(r2.x, px, r2.w)));
-    const float4 a0 = __ldg(reinterpret_cast<const float4*>(A));
-    const float4 a1 = __ldg(reinterpret_cast<const float4*>(A) + 1);
-    const float4 a2 = __ldg(reinterpret_cast<const float4*>(A) + 2);
-    t0 = __fadd_rn(fmaf(a0.z, l2, fmaf(a0.y, l1, __fmul_rn(a0.x, l0))), a0.w);
-    t1 = __fadd_rn(fmaf(a1.z, l2, fmaf(a1.y, l1, __fmul_rn(a1.x, l0))), a1.w);
-    t2 = __fadd_rn(fmaf(a2.z, l2, fmaf(a2.y, l1, __fmul_rn(a2.x, l0))), a2.w);
-}
-
-__device__ __forceinline__ void bone_coords(const float* __restrict__ skt, const float* __restrict__ A,
-                                            const float* __restrict__ scale, float px, float py, float pz,
-                                            float& x0, float& x1, float& x2) {
-    const float4 r0 = __ldg(reinterpret_cast<const float4*>(skt));
-    const float4 r1 = __ldg(reinterpret_cast<const float4*>(skt) + 1);
-    const float4 r2 = __ldg(reinterpret_cast<const float4*>(skt) + 2);
-    const float l0 = fmaf(r0.z, pz, fmaf(r0.y, py, fmaf(r0.x, px, r0.w)));
-    const float l1 = fmaf(r1.z, pz, fmaf(r1.y, py, fmaf(r1.x, px, r1.w)));
-    const float l2 = fmaf(r2.z, pz, fmaf(r2.y, py, fmaf(r2.x, px, r2.w)));
-    const float4 a0 = __ldg(reinterpret_cast<const float4*>(A));
-    const float4 a1 = __ldg(reinterpret_cast<const float4*>(A) + 1);
-    const float4 a2 = __ldg(reinterpret_cast<const float4*>(A) + 2);
-    const float t0 = __fadd_rn(fmaf(a0.z, l2, fmaf(a0.y, l1, __fmul_rn(a0.x, l0))), a0.w);
-    const float t1 = __fadd_rn(fmaf(a1.z, l2, fmaf(a1.y, l1, __fmul_rn(a1.x, l0))), a1.w);
-    const float t2 = __fadd_rn(fmaf(a2.z, l2, fmaf(a2.y, l1, __fmul_rn(a2.x, l0))), a2.w);
-    x0 = __fdiv_rn(t0, fabsf(__ldg(scale + 0)));
-    x1 = __fdiv_rn(t1, fabsf(__ldg(scale + 1)));
-    x2 = __fdiv_rn(t2, fabsf(__ldg(scale + 2)));
-}
 
 // ---------------------------------------------------------------------------------------------------------
 // NF1: ray / bounding-cylinder near & far in the x-z plane, fp32, op order of ray_utils.py:294-328.
@@ -282,19 +223,6 @@ __global__ void sample_mask_kernel(const float* __restrict__ rays, int ray_strid
 //   field_rows                : lane = one row: blend weights, blended feature, positional encoding, bf16 X row
 // An earlier version with lanes = hidden units spent 1 200 warp instructions per row on shuffles and weight loads
 // (ncu: profiles/r1_ncu_field_summary.txt); this layout needs ~150.
-struct PairWork {            // int workspace: [0,24) count per bone, [24,48) scatter cursor, [64, 64+cap) pairs
-    int* base;
-    __device__ __forceinline__ int* count() const { return base; }
-    __device__ __forceinline__ int* cursor() const { return base + 24; }
-    __device__ __forceinline__ int* pairs() const { return base + 64; }
-};
-
-__device__ __forceinline__ int seg_start(const int* __restrict__ count, int j) {
-    int off = 0;
-    for (int i = 0; i < j; ++i) off += (count[i] + 31) & ~31;
-    return off;
-}
-
 template <bool kScatter>
 __global__ void __launch_bounds__(256)
 pair_bucket_kernel(const uint32_t* __restrict__ mask, const int* __restrict__ active_ids,
@@ -340,28 +268,6 @@ pair_bucket_kernel(const uint32_t* __restrict__ mask, const int* __restrict__ ac
             }
         }
         __syncthreads();
-    }
-}
-
-// features of bone k at local coordinates x (closed form of misc.py:331-351 + window, gnn_backbone.py:802-826)
-__device__ __forceinline__ void bone_features(const float* __restrict__ vol_k, float x0, float x1, float x2, float (&h)[DANBO_FEAT]) {
-    const float a2 = x0 * x0, b2 = x1 * x1, c2 = x2 * x2;
-    const float win = expf(-2.f * (a2 * a2 * a2 + b2 * b2 * b2 + c2 * c2 * c2));
-    const float xs[3] = {x0, x1, x2};
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        const float iy = ((xs[a] + 1.f) * (float)DANBO_RES - 1.f) * 0.5f;
-        const float fl = floorf(iy);
-        const float w1 = iy - fl, w0 = 1.f - w1;
-        const int i0 = (int)fl, i1 = i0 + 1;
-        const bool ok0 = i0 >= 0 && i0 < DANBO_RES, ok1 = i1 >= 0 && i1 < DANBO_RES;
-#pragma unroll
-        for (int f = 0; f < 5; ++f) {
-            const float* line = vol_k + f * (DANBO_RES * 3) + a;
-            const float v0 = ok0 ? __ldg(line + i0 * 3) : 0.f;
-            const float v1 = ok1 ? __ldg(line + i1 * 3) : 0.f;
-            h[f * 3 + a] = (v0 * w0 + v1 * w1) * win;
-        }
     }
 }
 
@@ -446,7 +352,8 @@ field_rows_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, in
                   const int* __restrict__ active_count, int capacity, const float* __restrict__ pose_skts,
                   const float* __restrict__ pose_vol, int rays_per_pose, int n_poses, FieldConsts fc,
                   const float* __restrict__ logits, uint8_t* __restrict__ xtiles, int* __restrict__ row_ray,
-                  float* __restrict__ hbar_out /* (rows,16) or null */) {
+                  float* __restrict__ hbar_out /* (rows,16) or null */,
+                  __nv_bfloat16* __restrict__ x_rows /* (rows,208) row-major copy for the backward pass, or null */) {
     int count = *active_count; if (count > capacity) count = capacity;
     const int total = n_rays * S;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
@@ -505,8 +412,10 @@ field_rows_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, in
             } else v = 0.f;
             const uint32_t b = __bfloat16_as_ushort(__float2bfloat16_rn(v));
             if (col & 1) pk[(col & 7) >> 1] |= b << 16; else pk[(col & 7) >> 1] = b;
-            if ((col & 7) == 7)
+            if ((col & 7) == 7) {
                 *reinterpret_cast<uint4*>(xt + sw128_offset((uint32_t)rr, (uint32_t)(col - 7))) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                if (x_rows) *reinterpret_cast<uint4*>(x_rows + (size_t)e * 208 + (col - 7)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
             // after the last column of an octave (col == 14 + 30 (f+1)) advance every feature to the next octave
             if (col >= 44 && (col - 44) % 30 == 0 && col < 194) {
 #pragma unroll
@@ -618,7 +527,7 @@ extern "C" int danbo_field_agg(const float* rays, int ray_stride, int n_rays, in
                                const unsigned int* mask, const int* active_ids, const int* active_count,
                                int capacity, const float* pose_skts, const float* pose_vol, int rays_per_pose,
                                int n_poses, const float* const* consts, void* xtiles, int* row_ray, float* logits,
-                               float* hbar_out, int* work, int pair_capacity, int num_sms, void* stream) {
+                               float* hbar_out, void* x_rows, int* work, int pair_capacity, int num_sms, void* stream) {
     if (capacity <= 0) return 0;
     if (!logits || !work || pair_capacity < 32) return -1;
     cudaStream_t st = (cudaStream_t)stream;
@@ -642,7 +551,7 @@ extern "C" int danbo_field_agg(const float* rays, int ray_stride, int n_rays, in
     if (rblocks > num_sms * 16) rblocks = num_sms * 16;
     field_rows_kernel<<<rblocks, 128, 0, st>>>(rays, ray_stride, n_rays, S, z, mask, active_ids, active_count, capacity,
                                                 pose_skts, pose_vol, rays_per_pose, n_poses, fc, logits,
-                                                (uint8_t*)xtiles, row_ray, hbar_out);
+                                                (uint8_t*)xtiles, row_ray, hbar_out, (__nv_bfloat16*)x_rows);
     DANBO_CHECK_LAUNCH();
     return 0;
 }

@@ -159,6 +159,9 @@ mlp_kernel(const uint8_t* __restrict__ xtiles,       // [tiles][64 KB] swizzled 
            const int* __restrict__ n_rows_ptr,       // device scalar: number of valid rows
            float* __restrict__ out,                  // full: raw [*,4]; density: sigma [*]
            int out_capacity,
+           __nv_bfloat16* __restrict__ act_save,     // train mode: [9][save_cap][256] activations of L0..L8, or null
+           __nv_bfloat16* __restrict__ g_save,       // train mode: [save_cap][128] relu(view layer), or null
+           int save_cap,
            long long* __restrict__ trace) {          // optional clock64 timeline of CTA 0 (profiling aid) or null
     extern __shared__ uint8_t smem_raw[];
     Smem& S = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
@@ -327,6 +330,11 @@ mlp_kernel(const uint8_t* __restrict__ xtiles,       // [tiles][64 KB] swizzled 
                                 else       { pk[2 * i] = pack_bf16(a0, a1);      pk[2 * i + 1] = pack_bf16(a2, a3); }
                             }
                             if (kFull || L < 7) tmem_st16(act_out + 16 * g, pk);
+                            if (act_save != nullptr && valid) {          // saved for the backward pass (bf16, row-major)
+                                uint4* dst = reinterpret_cast<uint4*>(act_save + ((size_t)L * save_cap + grow) * 256 + col0 + 32 * g);
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+                            }
                         }
                     } else {
 #pragma unroll
@@ -344,6 +352,10 @@ mlp_kernel(const uint8_t* __restrict__ xtiles,       // [tiles][64 KB] swizzled 
                                     const float4 w = *reinterpret_cast<const float4*>(w_rgb + k * 128 + col0 + 32 * g + 4 * i);
                                     rgb[k] = fmaf(a[0], w.x, rgb[k]); rgb[k] = fmaf(a[1], w.y, rgb[k]);
                                     rgb[k] = fmaf(a[2], w.z, rgb[k]); rgb[k] = fmaf(a[3], w.w, rgb[k]);
+                                }
+                                if (g_save != nullptr && valid) {
+                                    uint2* dst = reinterpret_cast<uint2*>(g_save + (size_t)grow * 128 + col0 + 32 * g + 4 * i);
+                                    *dst = make_uint2(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]));
                                 }
                             }
                         }
@@ -469,7 +481,8 @@ extern "C" int danbo_pack_mlp_weights(const float* const* w_pts, const float* co
 
 static int mlp_launch(const void* xtiles, const void* wstream, const float* heads, const float* ray_bias,
                       const int* row_sample, const int* row_ray, const int* n_rows_dev, int max_rows,
-                      float* out, int out_capacity, int density_only, int num_sms, long long* trace, void* stream) {
+                      float* out, int out_capacity, int density_only, int num_sms, void* act_save, void* g_save,
+                      int save_cap, long long* trace, void* stream) {
     if (max_rows <= 0) return 0;
     const int smem = (int)sizeof(mlp::Smem) + 1024;
     int max_tiles = (max_rows + DANBO_TILE_M - 1) / DANBO_TILE_M;
@@ -480,12 +493,14 @@ static int mlp_launch(const void* xtiles, const void* wstream, const float* head
         e = cudaFuncSetAttribute(mlp::mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
         mlp::mlp_kernel<false><<<grid, mlp::kThreads, smem, (cudaStream_t)stream>>>(
-            (const uint8_t*)xtiles, (const uint8_t*)wstream, heads, ray_bias, row_sample, row_ray, n_rows_dev, out, out_capacity, trace);
+            (const uint8_t*)xtiles, (const uint8_t*)wstream, heads, ray_bias, row_sample, row_ray, n_rows_dev, out, out_capacity,
+            (__nv_bfloat16*)act_save, (__nv_bfloat16*)g_save, save_cap, trace);
     } else {
         e = cudaFuncSetAttribute(mlp::mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
         mlp::mlp_kernel<true><<<grid, mlp::kThreads, smem, (cudaStream_t)stream>>>(
-            (const uint8_t*)xtiles, (const uint8_t*)wstream, heads, ray_bias, row_sample, row_ray, n_rows_dev, out, out_capacity, trace);
+            (const uint8_t*)xtiles, (const uint8_t*)wstream, heads, ray_bias, row_sample, row_ray, n_rows_dev, out, out_capacity,
+            (__nv_bfloat16*)act_save, (__nv_bfloat16*)g_save, save_cap, trace);
     }
     DANBO_CHECK_LAUNCH();
     return 0;
@@ -495,7 +510,19 @@ extern "C" int danbo_mlp_forward(const void* xtiles, const void* wstream, const 
                                  const int* row_sample, const int* row_ray, const int* n_rows_dev, int max_rows,
                                  float* out, int out_capacity, int density_only, int num_sms, void* stream) {
     return mlp_launch(xtiles, wstream, heads, ray_bias, row_sample, row_ray, n_rows_dev, max_rows, out, out_capacity,
-                      density_only, num_sms, nullptr, stream);
+                      density_only, num_sms, nullptr, nullptr, 0, nullptr, stream);
+}
+
+// Train-mode forward: the same launch, and every layer's bf16 activation is kept for the backward pass:
+// act_save [9][save_cap][256] = outputs of pts_linears.0..7 (after relu) and feature_linear; g_save [save_cap][128] =
+// relu(views_linears.0).  save_cap >= max_rows.
+extern "C" int danbo_mlp_forward_save(const void* xtiles, const void* wstream, const float* heads, const float* ray_bias,
+                                      const int* row_sample, const int* row_ray, const int* n_rows_dev, int max_rows,
+                                      float* out, int out_capacity, int num_sms, void* act_save, void* g_save,
+                                      int save_cap, void* stream) {
+    if (!act_save || !g_save || save_cap < max_rows) return -1;
+    return mlp_launch(xtiles, wstream, heads, ray_bias, row_sample, row_ray, n_rows_dev, max_rows, out, out_capacity, 0,
+                      num_sms, act_save, g_save, save_cap, nullptr, stream);
 }
 
 // Same launch, and CTA 0 writes a clock64 timeline of its first 4 tiles into trace[4*2*20*2] (profiling aid).
@@ -504,5 +531,5 @@ extern "C" int danbo_mlp_forward_trace(const void* xtiles, const void* wstream, 
                                        float* out, int out_capacity, int density_only, int num_sms, long long* trace,
                                        void* stream) {
     return mlp_launch(xtiles, wstream, heads, ray_bias, row_sample, row_ray, n_rows_dev, max_rows, out, out_capacity,
-                      density_only, num_sms, trace, stream);
+                      density_only, num_sms, nullptr, nullptr, 0, trace, stream);
 }

@@ -150,28 +150,37 @@ def sample_mask(rays, S, pose_skts, rays_per_pose, consts, near=None, far=None, 
     return z, mask, active
 
 
-def field_agg(rays, S, z, mask, active, pose_skts, pose_vol, rays_per_pose, consts, want_confd=False,
-              want_hbar=False, pairs_per_row=6):
-    """-> xtiles (uint8 tiles), row_ray (cap) int32, confd (n*S,24) [visible entries only], hbar (cap,16) or None."""
+class FieldOut:
+    """What danbo_field_agg produced for one pass (kept whole in train mode: the backward reuses the pair lists)."""
+    __slots__ = ("xtiles", "row_ray", "logits", "hbar", "x_rows", "work", "pair_cap")
+
+
+def field_agg(rays, S, z, mask, active, pose_skts, pose_vol, rays_per_pose, consts, want_hbar=False,
+              want_xrows=False, pairs_per_row=6):
+    """-> FieldOut: xtiles (uint8 tiles), row_ray (cap) int32, logits (n*S,24) [visible entries only],
+    hbar (cap,16) / x_rows (cap,208 bf16) when asked."""
     _need_cuda(rays, z, mask, pose_skts, pose_vol)
     lib = _lib.load()
     n = rays.shape[0]
     dev = rays.device
     n_tiles = (active.capacity + TILE_M - 1) // TILE_M
-    xtiles = torch.empty(n_tiles * X_TILE_BYTES, device=dev, dtype=torch.uint8)
-    row_ray = torch.empty(active.capacity, device=dev, dtype=torch.int32)
-    logits = torch.empty(n * S, J, device=dev, dtype=torch.float32)
-    hbar = torch.empty(active.capacity, 16, device=dev, dtype=torch.float32) if want_hbar else None
-    pair_cap = int(pairs_per_row) * active.capacity + 24 * 32
-    work = torch.empty(64 + pair_cap, device=dev, dtype=torch.int32)
+    o = FieldOut()
+    o.xtiles = torch.empty(n_tiles * X_TILE_BYTES, device=dev, dtype=torch.uint8)
+    o.row_ray = torch.empty(active.capacity, device=dev, dtype=torch.int32)
+    o.logits = torch.empty(n * S, J, device=dev, dtype=torch.float32)
+    o.hbar = torch.empty(active.capacity, 16, device=dev, dtype=torch.float32) if want_hbar else None
+    o.x_rows = torch.empty(active.capacity, 208, device=dev, dtype=torch.bfloat16) if want_xrows else None
+    o.pair_cap = int(pairs_per_row) * active.capacity + 24 * 32
+    o.work = torch.empty(64 + o.pair_cap, device=dev, dtype=torch.int32)
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
     with _Timed("field_agg"):
         _lib.check(lib.danbo_field_agg(_p(rays), rays.stride(0), n, S, _p(z), _p(mask), _p(active.ids), _p(active.count),
                                        active.capacity, _p(pose_skts), _p(pose_vol), int(rays_per_pose),
-                                       pose_skts.shape[0], consts.array, _p(xtiles), _p(row_ray), _p(logits), _p(hbar),
-                                       _p(work), pair_cap, num_sms(idx), _stream()), "danbo_field_agg")
+                                       pose_skts.shape[0], consts.array, _p(o.xtiles), _p(o.row_ray), _p(o.logits),
+                                       _p(o.hbar), _p(o.x_rows), _p(o.work), o.pair_cap, num_sms(idx), _stream()),
+                   "danbo_field_agg")
     _count(4)
-    return xtiles, row_ray, logits, hbar
+    return o
 
 
 class PackedMLP:
@@ -296,3 +305,152 @@ def merge_composite(rays, S_c, S_f, raw0, mask0, raw1, mask1, z_all, order, nois
                                              _p(out.get("part_invalid")), _stream()), "danbo_merge_composite")
     _count(1)
     return out
+
+
+# ------------------------------------------------------------------------------------------------------ backward
+class ActSave:
+    """bf16 activations of the fused MLP kept for the backward pass."""
+
+    def __init__(self, cap, device):
+        self.cap = int(cap)
+        self.act = torch.empty(9, self.cap, 256, device=device, dtype=torch.bfloat16)
+        self.g = torch.empty(self.cap, 128, device=device, dtype=torch.bfloat16)
+
+
+def mlp_forward_save(xtiles, packed, rbias, active, row_ray, out, save):
+    lib = _lib.load()
+    dev = xtiles.device
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    _lib.check(lib.danbo_mlp_forward_save(_p(xtiles), _p(packed.wstream), _p(packed.heads), _p(rbias), _p(active.ids),
+                                          _p(row_ray), _p(active.count), active.capacity, _p(out), out.shape[0],
+                                          num_sms(idx), _p(save.act), _p(save.g), save.cap, _stream()),
+               "danbo_mlp_forward_save")
+    _count(1)
+    return out
+
+
+def composite_bwd(rays, S, raw, mask, z, noise, inv_B, g_rgb, g_acc, d_raw):
+    lib = _lib.load()
+    _lib.check(lib.danbo_composite_bwd(_p(rays), rays.stride(0), rays.shape[0], S, _p(raw), _p(mask), _p(z), _p(noise),
+                                       float(inv_B), _p(g_rgb), _p(g_acc), _p(d_raw), _stream()), "danbo_composite_bwd")
+    _count(1)
+
+
+def merge_composite_bwd(rays, S_c, S_f, raw0, mask0, raw1, mask1, z_all, order, noise, inv_B, g_rgb, g_acc, g_confd,
+                        d_raw0, d_raw1, d_logit0, d_logit1):
+    lib = _lib.load()
+    _lib.check(lib.danbo_merge_composite_bwd(_p(rays), rays.stride(0), rays.shape[0], S_c, S_f, _p(raw0), _p(mask0),
+                                             _p(raw1), _p(mask1), _p(z_all), _p(order), _p(noise), float(inv_B),
+                                             _p(g_rgb), _p(g_acc), _p(g_confd), _p(d_raw0), _p(d_raw1), _p(d_logit0),
+                                             _p(d_logit1), _stream()), "danbo_merge_composite_bwd")
+    _count(1)
+
+
+def _dgrad(A, B, ldb, D, ldd, active, N, K, accumulate=False, mask=None):
+    lib = _lib.load()
+    _lib.check(lib.danbo_gemm_dgrad(_p(A), int(A.dtype == torch.bfloat16), A.stride(0), _p(B), int(ldb), _p(D), int(ldd),
+                                    _p(active.count), active.capacity, int(N), int(K), int(bool(accumulate)),
+                                    _p(mask), 0 if mask is None else mask.stride(0), _stream()), "danbo_gemm_dgrad")
+    _count(1)
+
+
+def _wgrad(A, B, dW, ldw, active, M, N):
+    lib = _lib.load()
+    _lib.check(lib.danbo_gemm_wgrad(_p(A), A.stride(0), _p(B), int(B.dtype == torch.bfloat16), B.stride(0), _p(dW),
+                                    int(ldw), _p(active.count), active.capacity, int(M), int(N), _stream()),
+               "danbo_gemm_wgrad")
+    _count(1)
+
+
+def _colsum(A, db, active, N):
+    lib = _lib.load()
+    _lib.check(lib.danbo_colsum(_p(A), A.stride(0), _p(db), _p(active.count), active.capacity, int(N), _stream()),
+               "danbo_colsum")
+    _count(1)
+
+
+def _off(t, elems):
+    """Device pointer `elems` elements into tensor t (for column slices of row-major weights)."""
+    return ctypes.c_void_p(t.data_ptr() + elems * t.element_size())
+
+
+class _Ptr:
+    """Minimal tensor-like view (pointer + row stride + dtype) so GEMM wrappers can address column slices."""
+
+    def __init__(self, t, col0=0):
+        self.t, self.col0, self.dtype = t, col0, t.dtype
+
+    def data_ptr(self):
+        return self.t.data_ptr() + self.col0 * self.t.element_size()
+
+    def stride(self, d):
+        return self.t.stride(d)
+
+
+def mlp_backward(P, G, d_raw, active, fo, save, d_ray_bias):
+    """Backward of the fused MLP over the rows of one pass.
+    P: fp32 parameter tensors by reference name; G: same-named fp32 gradient accumulators (added to).
+    fo: FieldOut of the pass (row_ray, x_rows); save: ActSave.  -> dX (cap,208) fp32."""
+    lib = _lib.load()
+    dev = d_raw.device
+    cap = active.capacity
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    f32 = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+    delta9, cur, nxt, d_feat, dX = f32(cap, 128), f32(cap, 256), f32(cap, 256), f32(cap, 256), f32(cap, 208)
+    a = save.act
+    _lib.check(lib.danbo_mlp_head_bwd(_p(d_raw), _p(active.ids), _p(fo.row_ray), _p(active.count), cap, _p(save.g),
+                                      _p(a[7]), _p(P["rgb_linear.weight"]), _p(P["alpha_linear.weight"]), _p(delta9),
+                                      _p(cur), _p(G["rgb_linear.weight"]), _p(G["rgb_linear.bias"]),
+                                      _p(G["alpha_linear.weight"]), _p(G["alpha_linear.bias"]), _p(d_ray_bias),
+                                      num_sms(idx), _stream()), "danbo_mlp_head_bwd")
+    _count(1)
+    Wv, Wf = P["views_linears.0.weight"], P["feature_linear.weight"]
+    # views_linears.0 (feature part): dW[:, :256] += delta9^T . feat ; d feat = delta9 . Wv[:, :256]
+    _wgrad(delta9, a[8], G["views_linears.0.weight"], 411, active, 128, 256)
+    _dgrad(delta9, Wv, 411, d_feat, 256, active, 256, 128)
+    # feature_linear (no activation): bias, weight, and d a7 += d feat . Wf, then the relu mask of layer 7
+    _colsum(d_feat, G["feature_linear.bias"], active, 256)
+    _wgrad(d_feat, a[7], G["feature_linear.weight"], 256, active, 256, 256)
+    _dgrad(d_feat, Wf, 256, cur, 256, active, 256, 256, accumulate=True, mask=a[7])
+    for L in range(7, 0, -1):
+        W = P[f"pts_linears.{L}.weight"]
+        _colsum(cur, G[f"pts_linears.{L}.bias"], active, 256)
+        if L == 5:
+            dW = G["pts_linears.5.weight"]
+            _wgrad(cur, fo.x_rows, dW, 451, active, 256, 195)
+            _wgrad(cur, a[4], _Ptr(dW.view(-1), 195), 451, active, 256, 256)
+            _dgrad(cur, W, 451, dX, 208, active, 195, 256)
+            _dgrad(cur, _Ptr(W.view(-1), 195), 451, nxt, 256, active, 256, 256, mask=a[4])
+        else:
+            _wgrad(cur, a[L - 1], G[f"pts_linears.{L}.weight"], 256, active, 256, 256)
+            _dgrad(cur, W, 256, nxt, 256, active, 256, 256, mask=a[L - 1])
+        cur, nxt = nxt, cur
+    _colsum(cur, G["pts_linears.0.bias"], active, 256)
+    _wgrad(cur, fo.x_rows, G["pts_linears.0.weight"], 195, active, 256, 195)
+    _dgrad(cur, P["pts_linears.0.weight"], 195, dX, 208, active, 195, 256, accumulate=True)
+    return dX
+
+
+def ray_bias_bwd(rays, cam_idx, codes_with_mean, w_view, d_ray_bias, d_w_view, d_b_view, d_codes):
+    lib = _lib.load()
+    _lib.check(lib.danbo_ray_bias_bwd(_p(rays), rays.stride(0), rays.shape[0], _p(cam_idx), _p(codes_with_mean),
+                                      codes_with_mean.shape[0] - 1, _p(w_view), _p(d_ray_bias), _p(d_w_view),
+                                      _p(d_b_view), _p(d_codes), _stream()), "danbo_ray_bias_bwd")
+    _count(1)
+
+
+def field_agg_bwd(rays, S, z, mask, active, pose_skts, pose_vol, rays_per_pose, consts, fo, dX, g_logit_ext, grads):
+    """grads: list of the 9 fp32 accumulators in the order of danbo_field_agg_bwd (see danbo_b200.h)."""
+    lib = _lib.load()
+    dev = rays.device
+    n = rays.shape[0]
+    d_hbar = torch.empty(active.capacity, 16, device=dev, dtype=torch.float32)
+    d_logit = torch.empty(n * S, J, device=dev, dtype=torch.float32)
+    ga = (ctypes.c_void_p * 9)(*[g.data_ptr() for g in grads])
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    _lib.check(lib.danbo_field_agg_bwd(_p(rays), rays.stride(0), n, S, _p(z), _p(mask), _p(active.ids), _p(active.count),
+                                       active.capacity, _p(pose_skts), _p(pose_vol), int(rays_per_pose),
+                                       pose_skts.shape[0], consts.array, _p(fo.logits), _p(fo.hbar), _p(dX),
+                                       _p(g_logit_ext), _p(d_hbar), _p(d_logit), _p(fo.work), fo.pair_cap, ga,
+                                       num_sms(idx), _stream()), "danbo_field_agg_bwd")
+    _count(2)

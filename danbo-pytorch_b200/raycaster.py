@@ -149,7 +149,7 @@ class RayCaster(nn.Module):
         net = self.network
         consts = self._consts()
         packed = self._packed_mlp()
-        vol = net.bone_volumes(pose_bones).float().contiguous()            # GN1 + GN2 (PyTorch, <= 16 poses)
+        vol = net.bone_volumes(pose_bones).float().contiguous()            # GN1 + GN2 (PyTorch, <= 16 poses; autograd)
         codes = self._codes_with_mean()
         training = self.training
         rand = _rand or {}
@@ -159,6 +159,13 @@ class RayCaster(nn.Module):
             rand = {"t_rand": torch.rand(N, N_samples, device=dev),
                     "noise0": torch.randn(N, N_samples, device=dev), "u": torch.rand(N, N_importance, device=dev),
                     "noise1": torch.randn(N, S_t, device=dev)}
+        if training and torch.is_grad_enabled():
+            from .autograd import render_block_with_grad
+            if N > MAX_RAYS_PER_LAUNCH:
+                raise NotImplementedError(f"training batches above {MAX_RAYS_PER_LAUNCH} rays are not implemented")
+            return render_block_with_grad(self, rays, skip, pose_skts, pose_cyls, vol, cam_idx, codes, consts, packed,
+                                          N_samples, N_importance, B, raw_noise_std, perturb, nanmean_chunk,
+                                          {k: v.to(dev).contiguous() for k, v in rand.items()}, _stages)
         outs = []
         # internal launches: any split works for a single pose; with several poses a block holds whole poses
         G = pose_skts.shape[0]
@@ -176,10 +183,11 @@ class RayCaster(nn.Module):
         return {k: torch.cat([o[k] for o in outs], 0) for k in outs[0]}
 
     def _render_block(self, rays, ray0, skip, pose_skts, pose_cyls, vol, cam_idx, codes, consts, packed, S_c, S_f, B,
-                      raw_noise_std, perturb, training, nanmean_chunk, rand, stages):
+                      raw_noise_std, perturb, training, nanmean_chunk, rand, stages, keep=None):
+        """One launch sequence over <= MAX_RAYS_PER_LAUNCH rays.  `keep` (dict) receives every intermediate the
+        backward pass needs (train mode with gradients)."""
         n = rays.shape[0]
-        # poses of this block: ray (ray0 + i) -> pose (ray0 + i) // skip.  Blocks start on pose boundaries whenever
-        # skip divides MAX_RAYS_PER_LAUNCH or there is a single pose; otherwise shift the tables.
+        # poses of this block: ray (ray0 + i) -> pose (ray0 + i) // skip
         if pose_skts.shape[0] == 1:
             p0 = 0
         else:
@@ -191,32 +199,46 @@ class RayCaster(nn.Module):
                               use_box=self.use_volume_near_far, bound=1.3)
         rbias = K.ray_bias(rays, cam_idx, codes, packed)
         inv_B = 1.0 / B
+        save = keep is not None
         # ---- coarse pass
         t_rand = rand.get("t_rand") if (training and perturb > 0) or "t_rand" in rand else None
         z0, mask0, act0 = K.sample_mask(rays, S_c, p_skts, skip, consts, near=near, far=far, t_rand=t_rand,
                                         append_empty=True)
-        xt0, rr0, confd0, _ = K.field_agg(rays, S_c, z0, mask0, act0, p_skts, p_vol, skip, consts, want_confd=training)
+        f0 = K.field_agg(rays, S_c, z0, mask0, act0, p_skts, p_vol, skip, consts, want_hbar=save, want_xrows=save)
         raw0 = torch.empty(n * S_c + n, 4, device=rays.device, dtype=torch.float32)
-        K.mlp_forward(xt0, packed, rbias, act0, rr0, raw0)
+        sv0 = sv1 = None
+        if save:
+            sv0 = K.ActSave(act0.capacity, rays.device)
+            K.mlp_forward_save(f0.xtiles, packed, rbias, act0, f0.row_ray, raw0, sv0)
+        else:
+            K.mlp_forward(f0.xtiles, packed, rbias, act0, f0.row_ray, raw0)
         noise0 = (rand["noise0"] * (raw_noise_std * B)).contiguous() if ("noise0" in rand and raw_noise_std > 0) else None
         c0 = K.composite_resample(rays, S_c, S_f, raw0, mask0, z0, noise=noise0, inv_B=inv_B, u_rand=rand.get("u"),
                                   want_inds=stages is not None)
         # ---- fine pass: only the S_f new samples go through the field (single_net)
         z1, mask1, act1 = K.sample_mask(rays, S_f, p_skts, skip, consts, z_in=c0["z_samples"], append_empty=False)
-        xt1, rr1, confd1, _ = K.field_agg(rays, S_f, z1, mask1, act1, p_skts, p_vol, skip, consts, want_confd=training)
+        f1 = K.field_agg(rays, S_f, z1, mask1, act1, p_skts, p_vol, skip, consts, want_hbar=save, want_xrows=save)
         raw1 = torch.empty(n * S_f, 4, device=rays.device, dtype=torch.float32)
-        K.mlp_forward(xt1, packed, rbias, act1, rr1, raw1)
+        if save:
+            sv1 = K.ActSave(act1.capacity, rays.device)
+            K.mlp_forward_save(f1.xtiles, packed, rbias, act1, f1.row_ray, raw1, sv1)
+        else:
+            K.mlp_forward(f1.xtiles, packed, rbias, act1, f1.row_ray, raw1)
         noise1 = (rand["noise1"] * (raw_noise_std * B)).contiguous() if ("noise1" in rand and raw_noise_std > 0) else None
         c1 = K.merge_composite(rays, S_c, S_f, raw0, mask0, raw1, mask1, c0["z_all"], c0["order"], noise=noise1,
-                               inv_B=inv_B, want_raw=stages is not None, confd0=confd0 if training else None,
-                               confd1=confd1 if training else None,
-                               want_invalid=training)
+                               inv_B=inv_B, want_raw=stages is not None, confd0=f0.logits if training else None,
+                               confd1=f1.logits if training else None, want_invalid=training)
         ret = {"rgb_map": c1["rgb_map"], "disp_map": c1["disp_map"], "acc_map": c1["acc_map"], "alpha": c1["alpha"],
                "T_i": c1["weights"], "rgb0": c0["rgb_map"], "disp0": c0["disp_map"], "acc0": c0["acc_map"],
                "alpha0": c0["alpha"]}
         if training:
             ret["confd"] = c1["confd"]
             ret["part_invalid"] = c1["part_invalid"]
+        if save:
+            keep.update(dict(rays=rays, cam_idx=cam_idx, codes=codes, p_skts=p_skts, p_vol=p_vol, p0=p0, skip=skip,
+                             consts=consts, S_c=S_c, S_f=S_f, inv_B=inv_B, z0=z0, mask0=mask0, act0=act0, f0=f0, raw0=raw0,
+                             sv0=sv0, noise0=noise0, z1=z1, mask1=mask1, act1=act1, f1=f1, raw1=raw1, sv1=sv1,
+                             noise1=noise1, z_all=c0["z_all"], order=c0["order"]))
         if stages is not None:
             stages.update({"near": near, "far": far, "vol": vol, "z_coarse": z0, "mask0": mask0, "raw0": raw0,
                            "weights0": c0["weights"], "z_samples": c0["z_samples"], "z_all": c0["z_all"],
@@ -241,9 +263,9 @@ class RayCaster(nn.Module):
         z = torch.zeros(P, 1, device=dev)
         # append_empty=2: one extra entry (id 2P-1) carries sigma of a point that no bone sees (h = 0)
         _, mask, act = K.sample_mask(rays, 1, p_skts, P, consts, z_in=z, append_empty=2, capacity=P + 1)
-        xt, rr, _, _ = K.field_agg(rays, 1, z, mask, act, p_skts, vol, P, consts)
+        fo = K.field_agg(rays, 1, z, mask, act, p_skts, vol, P, consts)
         sigma = torch.empty(2 * P, device=dev)
-        K.mlp_forward(xt, packed, None, act, rr, sigma, density_only=True)
+        K.mlp_forward(fo.xtiles, packed, None, act, fo.row_ray, sigma, density_only=True)
         out = torch.where(mask.reshape(-1) != 0, sigma[:P], sigma[2 * P - 1])
         return out.reshape(P, 1, 1) if pts.dim() == 3 else out.reshape(P, 1)
 

@@ -54,13 +54,14 @@ int danbo_sample_mask(const float* rays, int ray_stride, int n_rays, int S, cons
  * pose_vol (n_poses,24,240) = graph-net output.  Four launches: bucket the (row, visible bone) pairs by bone (count,
  * scatter), evaluate the aggregation net per pair, then blend + encode per row.  Writes bf16 rows into xtiles
  * ((capacity+127)/128 tiles of 64 KB, swizzled MMA operand image), row_ray[row], the blend logits ("confd") of every
- * visible (sample, bone) into logits (n_rays*S,24) and optionally hbar (rows,16).
+ * visible (sample, bone) into logits (n_rays*S,24) and optionally hbar (rows,16) and x_rows (rows,208 bf16, a
+ * row-major copy of the encoded rows for the backward pass).
  * work: int workspace of 64 + pair_capacity entries; pair_capacity >= number of visible pairs + 24*32. */
 int danbo_field_agg(const float* rays, int ray_stride, int n_rays, int S, const float* z, const unsigned int* mask,
                     const int* active_ids, const int* active_count, int capacity, const float* pose_skts,
                     const float* pose_vol, int rays_per_pose, int n_poses, const float* const* consts, void* xtiles,
-                    int* row_ray, float* logits, float* hbar_out, int* work, int pair_capacity, int num_sms,
-                    void* stream);
+                    int* row_ray, float* logits, float* hbar_out, void* x_rows, int* work, int pair_capacity,
+                    int num_sms, void* stream);
 
 /* V1 folded into the view layer: out (n_rays,128) = W_v[:,256:411] . [PE(rays_d) ; frame code] + b_v
  * (core/networks/nerf.py:252-279, core/networks/embedding.py:86-108).  codes is (n_codes+1,128) with the mean code in
@@ -108,6 +109,57 @@ int danbo_merge_composite(const float* rays, int ray_stride, int n_rays, int S_c
                           const int* order, const float* noise, float inv_B, float* weights, float* alpha, float* rgb,
                           float* disp, float* acc, float* raw_merged, const float* confd0, const float* confd1,
                           float* confd_merged, float* invalid_merged, void* stream);
+
+/* ---- backward (train mode; autograd of the same rows as reached from core/trainer.py:563-576) -------------------- */
+
+/* Train-mode M1 forward: danbo_mlp_forward plus the bf16 activations the backward needs: act_save [9][save_cap][256]
+ * (pts_linears.0..7 after relu, feature_linear), g_save [save_cap][128] (relu(views_linears.0)). */
+int danbo_mlp_forward_save(const void* xtiles, const void* wstream, const float* heads, const float* ray_bias,
+                           const int* row_sample, const int* row_ray, const int* n_rows_dev, int max_rows, float* out,
+                           int out_capacity, int num_sms, void* act_save, void* g_save, int save_cap, void* stream);
+
+/* Backward of C1 on the coarse samples (nerf.py:297-347): d raw (n*S + n, 4) += from d rgb0 (n,3), d acc0 (n). */
+int danbo_composite_bwd(const float* rays, int ray_stride, int n_rays, int S, const float* raw, const unsigned int* mask,
+                        const float* z, const float* noise, float inv_B, const float* g_rgb, const float* g_acc,
+                        float* d_raw, void* stream);
+
+/* Backward of R2 + C1 on the merged samples; also routes d confd (n,S_t,24) to the per-pass logit buffers. */
+int danbo_merge_composite_bwd(const float* rays, int ray_stride, int n_rays, int S_c, int S_f, const float* raw0,
+                              const unsigned int* mask0, const float* raw1, const unsigned int* mask1,
+                              const float* z_all, const int* order, const float* noise, float inv_B, const float* g_rgb,
+                              const float* g_acc, const float* g_confd, float* d_raw0, float* d_raw1, float* d_logit0,
+                              float* d_logit1, void* stream);
+
+/* M1 backward building blocks (fp32).  rows_dev = device scalar row count.
+ * head_bwd : d raw -> delta of views_linears.0 (rows,128), d a7 (rows,256) and the rgb/alpha head + ray-bias grads
+ * gemm_dgrad: D[rows x N] = A[rows x K] . B[K x N] (+ D) (* [mask > 0]);  gemm_wgrad: dW[M x N] += A^T . B;
+ * colsum: db[N] += sum_rows A. */
+int danbo_mlp_head_bwd(const float* d_raw, const int* row_sample, const int* row_ray, const int* rows_dev, int max_rows,
+                       const void* g_save, const void* a7_save, const float* w_rgb, const float* w_alpha, float* delta9,
+                       float* d_a7, float* d_w_rgb, float* d_b_rgb, float* d_w_alpha, float* d_b_alpha,
+                       float* d_ray_bias, int num_sms, void* stream);
+int danbo_gemm_dgrad(const void* A, int a_is_bf16, int lda, const float* B, int ldb, float* D, int ldd,
+                     const int* rows_dev, int max_rows, int N, int K, int accumulate, const void* mask, int ldmask,
+                     void* stream);
+int danbo_gemm_wgrad(const float* A, int lda, const void* B, int b_is_bf16, int ldb, float* dW, int ldw,
+                     const int* rows_dev, int max_rows, int M, int N, void* stream);
+int danbo_colsum(const float* A, int lda, float* db, const int* rows_dev, int max_rows, int N, void* stream);
+
+/* V1 backward: d ray_bias (n,128) -> grads of views_linears.0.weight[:,256:411] (written into the (128,411) layout),
+ * its bias and the frame codes (core/networks/nerf.py:252-279, embedding.py:86-108). */
+int danbo_ray_bias_bwd(const float* rays, int ray_stride, int n_rays, const int* cam_idx, const float* codes, int n_codes,
+                       const float* w_view, const float* d_ray_bias, float* d_w_view, float* d_b_view, float* d_codes,
+                       void* stream);
+
+/* G1/G2 + A1-A3 + PE backward (danbo.py:261-302, gnn_backbone.py:787-828, misc.py:331-351): d X (rows,208) and the
+ * extra logit gradient -> grads[9] = { w0, adj_w, b0, w1, b1, w2, b2 of prob_linears, d vol (n_poses,24,240),
+ * d axis_scale (24,3) } (fp32, accumulated).  work = the workspace the forward danbo_field_agg filled. */
+int danbo_field_agg_bwd(const float* rays, int ray_stride, int n_rays, int S, const float* z, const unsigned int* mask,
+                        const int* active_ids, const int* active_count, int capacity, const float* pose_skts,
+                        const float* pose_vol, int rays_per_pose, int n_poses, const float* const* consts,
+                        const float* logits, const float* hbar, const float* dX, const float* g_logit_ext, float* d_hbar,
+                        float* d_logit, const int* work, int pair_capacity, float* const* grads, int num_sms,
+                        void* stream);
 
 #ifdef __cplusplus
 }

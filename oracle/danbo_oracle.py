@@ -362,7 +362,7 @@ def field_eval(pts, rays_d, cams, skts, A, vol, P, rays_per_pose, training, agg_
 
 def render_rays(ray_batch, pose_skts, pose_bones, pose_cyls, cams, A, P, S_c, S_f, rays_per_pose,
                 use_volume_near_far=False, training=False, rand=None, raw_noise_std=0., agg_type="sigmoid",
-                return_stages=False):
+                return_stages=False, z_samples=None):
     """ray_batch (N,>=8); pose_* are per unique pose (G,...); ray n belongs to pose n // rays_per_pose.
     rand (training) = dict(t_rand (N,S_c), noise0 (N,S_c), u (N,S_f), noise1 (N,S_t)) drawn by the caller in
     the reference's order (SURVEY §7 hard part 4)."""
@@ -385,6 +385,11 @@ def render_rays(ray_batch, pose_skts, pose_bones, pose_cyls, cams, A, P, S_c, S_
     n0 = rand["noise0"] * raw_noise_std if "noise0" in rand else None
     out0 = composite(raw0, z, rays_d, n0)
     z_all, zs, order, inds = importance_sample(z, out0["weights"], S_f, rand.get("u"))
+    if z_samples is not None:
+        # test hook: evaluate the fine pass at externally supplied (detached) importance samples, so a comparison
+        # against an implementation whose coarse weights differ in the last bits is not dominated by resampling
+        zs = z_samples
+        z_all, order = torch.sort(torch.cat([z, zs], -1), -1)
     pts_f = ray_points(rays_o, rays_d, zs)
     raw1, confd1, inv1, st1 = field_eval(pts_f, rays_d, cams, skts, A, vol, P, rays_per_pose, training, agg_type)
     raw = merge_sorted(raw0, raw1, order)

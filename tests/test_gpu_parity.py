@@ -104,8 +104,9 @@ def test_field_agg(name, which):
     consts = caster._consts()
     vol = fx["st.vol.0"].to(DEV).contiguous()
     zg, mask, act = K().sample_mask(rb.to(DEV), S, skts.to(DEV).contiguous(), N, consts, z_in=z.to(DEV), append_empty=False)
-    xt, row_ray, confd, hbar = K().field_agg(rb.to(DEV), S, zg, mask, act, skts.to(DEV).contiguous(), vol, N, consts,
-                                             want_confd=True, want_hbar=True)
+    fo = K().field_agg(rb.to(DEV), S, zg, mask, act, skts.to(DEV).contiguous(), vol, N, consts, want_hbar=True,
+                       want_xrows=True)
+    xt, row_ray, confd, hbar = fo.xtiles, fo.row_ray, fo.logits, fo.hbar
     n_act = int(act.count.item())
     ids = act.ids[:n_act].cpu().long()
     # oracle on the same points
@@ -122,12 +123,14 @@ def test_field_agg(name, which):
     sel = same[ids]
     close(hbar[:n_act, :15].cpu()[sel], hb[ids][sel], 2e-5, "hbar")
     valid = 1 - invalid.reshape(N * S, 24)
-    close((confd.cpu() * valid)[ids][sel], (a * valid)[ids][sel], 1e-4, "confd (visible bones)")
+    confd_v = torch.where(valid.bool(), confd.cpu(), torch.zeros(()))        # only visible entries are defined
+    close(confd_v[ids][sel], (a * valid)[ids][sel], 1e-4, "confd (visible bones)")
     assert torch.equal(row_ray[:n_act].cpu().long(), ids // S)
     X = decode_xtiles(xt, n_act).cpu()
     want = orc.pe_embed(hbar[:n_act, :15].cpu(), 6)
     err = (X - want).abs().max()
     assert float(err) <= 2 ** -8 * 1.01 * max(1.0, float(want.abs().max())), f"bf16 rows: {float(err)}"
+    assert torch.equal(fo.x_rows[:n_act, :195].float().cpu(), X), "row-major copy of the encoded rows"
 
 
 @pytest.mark.parametrize("name", ["render_fast", "render_base"])
@@ -143,7 +146,8 @@ def test_mlp_tcgen05(name):
     consts, packed = caster._consts(), caster._packed_mlp()
     vol = fx["st.vol.0"].to(DEV).contiguous()
     z, mask, act = K().sample_mask(rb, S, skts.to(DEV).contiguous(), N, consts, z_in=fx["st.z.0"].to(DEV), append_empty=1)
-    xt, row_ray, _, hbar = K().field_agg(rb, S, z, mask, act, skts.to(DEV).contiguous(), vol, N, consts, want_hbar=True)
+    fo = K().field_agg(rb, S, z, mask, act, skts.to(DEV).contiguous(), vol, N, consts, want_hbar=True)
+    xt, row_ray, hbar = fo.xtiles, fo.row_ray, fo.hbar
     cams = fx["cams"].reshape(-1).to(DEV).to(torch.int32)
     rbias = K().ray_bias(rb, cams, caster._codes_with_mean(), packed)
     # per-ray view bias against the oracle

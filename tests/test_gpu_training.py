@@ -1,0 +1,280 @@
+"""Training path on the GPU (run with -m gpu): the hand-written backward kernels against autograd of the CPU oracle on
+the same batch, weights and random draws, and against the parameter gradients the reference itself produced
+(tests/golden/train_*.npz, sampled entries + norms).
+
+Every backward stage is checked on its own against torch autograd of the oracle (fp32 both sides): compositing
+<= 2e-4 of scale (measured 1e-7), field / aggregation net <= 2e-4 relative (measured 6e-6), MLP <= 2e-2 relative against
+autograd of a bf16-emulating restatement (measured 6e-3; the kernels use fp32 master weights in dgrad).
+
+End to end the forward MLP runs in bf16, and with raw_noise_std = 1 the density gate relu(sigma + noise) flips for the
+few per cent of samples whose sigma is within the bf16 error of -noise, so whole-step gradients are compared with
+cosine / relative-L2 bounds: train_fast (192 rays) cos >= 0.985, rel <= 0.2; train_cfg3 (64 rays, 80 samples, densities
+saturating: a handful of rays carry the density gradient) cos >= 0.85, rel <= 0.8."""
+import pytest
+import torch
+
+import danbo_oracle as orc
+from util import load_fixture, params_for, align_A, make_caster, preset_of
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def torch_loss(ret, target, bgs, axis_scale, init_scale):
+    """The trainer's losses restated on whatever device the tensors live on (trainer.py:396-422,507-553)."""
+    def l1(rgb, acc):
+        return torch.mean(torch.abs(rgb + (1. - acc)[..., None] * bgs - target))
+    loss = l1(ret["rgb_map"], ret["acc_map"]) + l1(ret["rgb0"], ret["acc0"])
+    labels = ((ret["T_i"] * ret["alpha"]) > 0).float()
+    valid = 1 - ret["part_invalid"]
+    p = torch.sigmoid(ret["confd"]) * 1.002 - 0.001
+    loss = loss + 0.001 * (labels - (p * valid).sum(-1)).pow(2.).mean()
+    scale = axis_scale.abs().clamp(min=init_scale * 0.05)
+    return loss + 0.001 * torch.prod(scale, dim=-1).sum()
+
+
+@pytest.mark.parametrize("name", ["train_fast", "train_cfg3"])
+def test_training_step_gradients(name):
+    from danbo_b200 import synthetic as syn, skeleton as sk
+    fx = load_fixture(name)
+    caster, args, _ = make_caster(preset_of(fx), train=True)
+    b = syn.training_batch(int(fx["n_poses"]), int(fx["rays_per_pose"]), seed=int(fx["batch_seed"]))
+    rpp = int(fx["rays_per_pose"])
+    rand = {k: fx["rand." + k] for k in ("t_rand", "noise0", "u", "noise1")}
+    init_scale = sk.initial_axis_scale(sk.skeleton_profile(syn.rest_pose()), 0.4)
+    # ---- CUDA path
+    stages = {}
+    out = caster.render_rays(b["ray_batch"], N_samples=args.N_samples, kp_batch=b["kp_batch"], skts=b["skts"],
+                             cyls=b["cyls"], bones=b["bones"], cams=b["cams"], N_uniques=int(fx["n_poses"]), perturb=1.0,
+                             N_importance=args.N_importance, raw_noise_std=float(fx["raw_noise_std"]),
+                             _rand={k: v.to(DEV) for k, v in rand.items()}, _stages=stages)
+    loss = torch_loss(out, b["target_s"].to(DEV), b["bgs"].to(DEV), caster.network.graph_net.axis_scale, init_scale.to(DEV))
+    loss.backward()
+    torch.cuda.synchronize()
+    got = {n: p.grad.detach().cpu() for n, p in caster.network.named_parameters() if p.grad is not None}
+    # ---- oracle autograd (fp32, CPU)
+    P = params_for(fx)
+    P = {k: v.clone().requires_grad_(v.dtype.is_floating_point and not k.endswith(".adj")) for k, v in P.items()}
+    ref = orc.render_rays(b["ray_batch"], b["skts"][::rpp], b["bones"][::rpp], b["cyls"][::rpp], b["cams"], align_A(), P,
+                          int(fx["N_samples"]), int(fx["N_importance"]), rays_per_pose=rpp,
+                          use_volume_near_far=bool(fx["use_volume_near_far"]), training=True, rand=rand,
+                          raw_noise_std=float(fx["raw_noise_std"]), z_samples=stages["z_samples"].cpu())
+    ref_loss = orc.training_loss(ref, b["target_s"], b["bgs"], P, init_scale)
+    ref_loss.backward()
+    print(f"[train] {name}: loss cuda {float(loss):.6f} oracle {float(ref_loss):.6f} reference {float(fx['loss.total']):.6f}")
+    assert abs(float(loss) - float(ref_loss)) <= 5e-3
+    big = max(float(v.grad.norm()) for v in P.values() if v.grad is not None)
+    bad = []
+    for k, v in P.items():
+        if v.grad is None:
+            continue
+        if k not in got:
+            bad.append((k, "no gradient"))
+            continue
+        a, r = got[k].reshape(-1).double(), v.grad.reshape(-1).double()
+        rn = float(r.norm())
+        cos = float(torch.dot(a, r) / (a.norm() * r.norm() + 1e-30))
+        rel = float((a - r).norm() / max(rn, 1e-3 * big))
+        ref_err = float("nan")
+        if ("grad_val." + k) in fx:            # the reference's own sampled gradient entries (its own fine samples)
+            idx = fx["grad_idx." + k].long()
+            want = fx["grad_val." + k].double()
+            ref_err = float((a[idx] - want).norm() / max(float(want.norm()), 1e-3 * big))
+        print(f"[train] {name} {k:40s} |g| {rn:.3e} cos {cos:.5f} rel {rel:.3e} | vs reference samples {ref_err:.3e}")
+        cos_min, rel_max = (0.985, 0.2) if name == "train_fast" else (0.85, 0.8)
+        if (rn > 1e-3 * big and cos < cos_min) or rel > rel_max:
+            bad.append((k, cos, rel))
+    assert not bad, bad
+
+
+def test_eval_unchanged_after_training_forward():
+    """Train-mode plumbing must not disturb the eval path (same weights -> same pixels)."""
+    fx = load_fixture("render_fast")
+    caster, args, _ = make_caster("danbo_fast")
+    from util import pose_tensors
+    skts, bones, cyl = pose_tensors(fx)
+    N = fx["ray_batch"].shape[0]
+    ex = lambda t: t.expand(N, *t.shape[1:])
+    kw = dict(N_samples=args.N_samples, kp_batch=ex(fx["pose_kps"][None]), skts=ex(skts), cyls=ex(cyl), bones=ex(bones),
+              cams=fx["cams"], N_uniques=1, perturb=False, N_importance=args.N_importance, raw_noise_std=0.)
+    a = caster(fx["ray_batch"], **kw)
+    caster.train()
+    with torch.no_grad():
+        caster.render_rays(fx["ray_batch"], **kw)
+    caster.eval()
+    b = caster(fx["ray_batch"], **kw)
+    assert torch.equal(a["rgb_map"], b["rgb_map"])
+
+
+# ------------------------------------------------------------------------------------------------ stage-level backward
+def _K():
+    import danbo_b200
+    return danbo_b200.kernels
+
+
+@pytest.mark.parametrize("S,S_f", [(32, 16), (64, 16), (96, 48)])
+def test_composite_backward(S, S_f):
+    """C1/R2 backward kernels against torch autograd of the oracle's compositing on the same raw values."""
+    torch.manual_seed(S)
+    N = 96
+    St = S + S_f
+    rays = torch.randn(N, 8); rays[:, 3:6] = torch.nn.functional.normalize(torch.randn(N, 3), dim=-1) * (0.8 + 0.4 * torch.rand(N, 1))
+    z0 = torch.sort(torch.rand(N, S) * 3 + 1, -1).values
+    z1 = torch.rand(N, S_f) * 3 + 1
+    raw0 = torch.randn(N, S, 4) * torch.tensor([1., 1., 1., 20.])
+    raw1 = torch.randn(N, S_f, 4) * torch.tensor([1., 1., 1., 20.])
+    empty = torch.randn(N, 4) * torch.tensor([1., 1., 1., 20.])
+    mask0 = (torch.rand(N, S) < 0.4).int()
+    mask1 = (torch.rand(N, S_f) < 0.4).int()
+    noise0, noise1 = torch.randn(N, S), torch.randn(N, St)
+    z_all, order = torch.sort(torch.cat([z0, z1], -1), -1)
+    g_rgb, g_acc, g_rgb0, g_acc0 = torch.randn(N, 3), torch.randn(N), torch.randn(N, 3), torch.randn(N)
+    # ---- oracle autograd
+    r0 = raw0.clone().requires_grad_(True); r1 = raw1.clone().requires_grad_(True); em = empty.clone().requires_grad_(True)
+    eff0 = torch.where(mask0[..., None].bool(), r0, em[:, None].expand(-1, S, -1))
+    eff1 = torch.where(mask1[..., None].bool(), r1, em[:, None].expand(-1, S_f, -1))
+    out0 = orc.composite(eff0, z0, rays[:, 3:6], noise0)
+    merged = orc.merge_sorted(eff0, eff1, order)
+    out = orc.composite(merged, z_all, rays[:, 3:6], noise1)
+    ((out["rgb_map"] * g_rgb).sum() + (out["acc_map"] * g_acc).sum() + (out0["rgb_map"] * g_rgb0).sum()
+     + (out0["acc_map"] * g_acc0).sum()).backward()
+    # ---- kernels
+    d = lambda t: t.to(DEV).contiguous()
+    raw0_buf = d(torch.cat([raw0.reshape(N * S, 4), empty], 0))
+    d_raw0 = torch.zeros(N * S + N, 4, device=DEV); d_raw1 = torch.zeros(N * S_f, 4, device=DEV)
+    K = _K()
+    K.merge_composite_bwd(d(rays), S, S_f, raw0_buf, d(mask0), d(raw1.reshape(N * S_f, 4)), d(mask1), d(z_all),
+                          d(order.int()), d(noise1), 1.0, d(g_rgb), d(g_acc), None, d_raw0, d_raw1, None, None)
+    K.composite_bwd(d(rays), S, raw0_buf, d(mask0), d(z0), d(noise0), 1.0, d(g_rgb0), d(g_acc0), d_raw0)
+    torch.cuda.synchronize()
+    got0 = d_raw0[: N * S].reshape(N, S, 4).cpu() * mask0[..., None]
+    got1 = d_raw1.reshape(N, S_f, 4).cpu() * mask1[..., None]
+    gote = d_raw0[N * S:].cpu()
+    for nm, a, b in (("d raw0", got0, r0.grad * mask0[..., None]), ("d raw1", got1, r1.grad * mask1[..., None]), ("d empty", gote, em.grad)):
+        err = float((a - b).abs().max()); sc = float(b.abs().max())
+        print(f"[train] composite bwd S={S}+{S_f} {nm}: err {err:.3e} scale {sc:.3e}")
+        assert err <= 2e-4 * sc + 1e-6, (nm, err, sc)
+
+
+def test_mlp_backward():
+    """M1 backward (fp32 kernels on the saved bf16 activations) against autograd of the bf16-emulating restatement."""
+    from util import mlp_bf16_reference
+    fx = load_fixture("render_fast")
+    caster, args, Pdev = make_caster("danbo_fast", train=True)
+    K = _K()
+    torch.manual_seed(1)
+    rows, n_rays = 700, 40
+    X = torch.randn(rows, 195) * 0.7
+    ray_of = torch.randint(0, n_rays, (rows,))
+    rbias = torch.randn(n_rays, 128) * 0.3
+    g_raw = torch.randn(rows, 4)
+    # pack X rows into tiles through the same layout helper the kernels use
+    from util import sw128_offsets
+    import numpy as np
+    n_tiles = (rows + 127) // 128
+    xt = torch.zeros(n_tiles * 65536, dtype=torch.uint8)
+    off = torch.from_numpy(sw128_offsets(208).astype(np.int64))
+    xb = torch.zeros(n_tiles * 128, 208, dtype=torch.bfloat16); xb[:rows, :195] = X.to(torch.bfloat16)
+    words = xt.view(torch.int16).view(n_tiles, 32768)
+    words.scatter_(1, (off // 2).reshape(1, -1).expand(n_tiles, -1), xb.view(torch.int16).reshape(n_tiles, -1))
+    act = K.ActiveList(rows, DEV); act.ids.copy_(torch.arange(rows, dtype=torch.int32)); act.count.fill_(rows)
+    packed = caster._packed_mlp()
+    save = K.ActSave(rows, DEV)
+    fo = K.FieldOut(); fo.row_ray = ray_of.int().to(DEV); fo.x_rows = xb[:rows].to(DEV).contiguous()
+    raw = torch.empty(rows, 4, device=DEV)
+    K.mlp_forward_save(xt.to(DEV), packed, rbias.to(DEV), act, fo.row_ray, raw, save)
+    names = [n for n in caster.network.state_dict() if n.split(".")[0] in ("pts_linears", "alpha_linear", "feature_linear", "views_linears", "rgb_linear")]
+    P = {n: Pdev[n].float().contiguous() for n in names}
+    G = {n: torch.zeros_like(v) for n, v in P.items()}
+    d_rb = torch.zeros(n_rays, 128, device=DEV)
+    dX = K.mlp_backward(P, G, g_raw.to(DEV), act, fo, save, d_rb)
+    torch.cuda.synchronize()
+    # reference: autograd through the bf16 emulation (straight-through on the roundings)
+    Pc = {n: v.cpu().clone().requires_grad_(True) for n, v in P.items()}
+    Xc = xb[:rows, :195].float().clone().requires_grad_(True)
+    rb = rbias.clone().requires_grad_(True)
+
+    def ste(t):                                    # bf16 rounding with identity gradient
+        return t + (t.to(torch.bfloat16).float() - t).detach()
+    h = Xc
+    a = None
+    for i in range(8):
+        a = torch.relu(h @ ste(Pc[f"pts_linears.{i}.weight"]).t() + Pc[f"pts_linears.{i}.bias"])
+        h = ste(a)
+        if i == 4:
+            h = torch.cat([Xc, h], -1)
+    sigma = a @ Pc["alpha_linear.weight"].t() + Pc["alpha_linear.bias"]
+    feat = ste(h @ ste(Pc["feature_linear.weight"]).t() + Pc["feature_linear.bias"])
+    g = torch.relu(feat @ ste(Pc["views_linears.0.weight"][:, :256]).t() + rb[ray_of])
+    rgb = g @ Pc["rgb_linear.weight"].t() + Pc["rgb_linear.bias"]
+    out = torch.cat([rgb, sigma], -1)
+    err_f = float((raw.cpu() - out.detach()).abs().max())
+    print(f"[train] mlp fwd(save) vs emulation: {err_f:.3e}")
+    (out * g_raw).sum().backward()
+    checks = [("dX", dX[:rows, :195].cpu(), Xc.grad), ("d ray_bias", d_rb.cpu(), rb.grad)]
+    for n in names:
+        want = Pc[n].grad
+        if n == "views_linears.0.weight":
+            checks.append((n + "[:, :256]", G[n].cpu()[:, :256], want[:, :256]))
+        elif n == "views_linears.0.bias":
+            continue                                # folded into the ray bias (checked through d ray_bias)
+        else:
+            checks.append((n, G[n].cpu(), want))
+    for nm, got, want in checks:
+        rel = float((got - want).norm() / (want.norm() + 1e-12))
+        print(f"[train] mlp bwd {nm:32s} rel {rel:.3e}")
+        assert rel <= 2e-2, (nm, rel)
+
+
+@pytest.mark.parametrize("name", ["render_fast", "render_base"])
+def test_field_backward(name):
+    """G1/G2 + A1-A3 + PE backward against torch autograd of the oracle on the same sample positions (fp32 both)."""
+    from util import pose_tensors
+    fx = load_fixture(name)
+    caster, args, Pdev = make_caster(preset_of(fx), train=True)
+    K = _K()
+    Pc = params_for(fx)
+    skts, bones, _ = pose_tensors(fx)
+    rb = fx["ray_batch"]
+    N, z = rb.shape[0], fx["st.z.0"]
+    S = z.shape[1]
+    consts = caster._consts()
+    vol = fx["st.vol.0"]
+    d = lambda t: t.to(DEV).contiguous()
+    zg, mask, act = K.sample_mask(d(rb), S, d(skts), N, consts, z_in=d(z), append_empty=1)
+    fo = K.field_agg(d(rb), S, zg, mask, act, d(skts), d(vol), N, consts, want_hbar=True, want_xrows=True)
+    n_act = int(act.count.item())
+    ids = act.ids[:n_act].cpu().long()
+    torch.manual_seed(5)
+    dX = torch.zeros(act.capacity, 208); dX[:n_act, :195] = torch.randn(n_act, 195)
+    g_ext = torch.randn(N * S, 24)
+    names = ["w0", "adj_w", "b0", "w1", "b1", "w2", "b2"]
+    keys = ["prob_linears.layers.0.lin.weight", "prob_linears.layers.0.adj_w", "prob_linears.layers.0.bias",
+            "prob_linears.layers.1.weight", "prob_linears.layers.1.bias", "prob_linears.layers.2.weight",
+            "prob_linears.layers.2.bias"]
+    grads = [torch.zeros_like(Pdev[k]) for k in keys] + [torch.zeros(1, 24, 240, device=DEV), torch.zeros(24, 3, device=DEV)]
+    K.field_agg_bwd(d(rb), S, zg, mask, act, d(skts), d(vol), N, consts, fo, d(dX), d(g_ext), grads)
+    torch.cuda.synchronize()
+    # ---- oracle autograd on the same rows
+    P = {k: v.clone().requires_grad_(k in keys or k == "graph_net.axis_scale") for k, v in Pc.items()}
+    vol_r = vol.clone().requires_grad_(True)
+    pts = orc.ray_points(rb[:, 0:3], rb[:, 3:6], z)
+    pts_t = orc.world_to_bone(pts, skts.expand(N, -1, -1, -1), align_A())
+    h, invalid, _ = orc.bone_features(pts_t, vol_r, P["graph_net.axis_scale"], rays_per_pose=N)
+    hf = h.reshape(N * S, 24, 15)
+    a = orc.agg_net(hf, P)
+    valid = 1 - invalid.reshape(N * S, 24)
+    p = orc.agg_prob(a, invalid.reshape(N * S, 24))
+    X = orc.pe_embed((hf * p[..., None]).sum(-2), 6)
+    real = ids < N * S
+    rows_real = torch.nonzero(real).reshape(-1)
+    loss = (X[ids[real]] * dX[rows_real, :195]).sum() + (a * valid * g_ext)[ids[real]].sum()
+    loss.backward()
+    got_inv = 1.0 - ((mask.cpu().long().reshape(-1, 1) >> torch.arange(24)) & 1).float()
+    assert torch.equal(got_inv, invalid.reshape(N * S, 24)), "fixture chosen so that no mask sits on a box face"
+    checks = [(k, g.cpu(), P[k].grad) for k, g in zip(keys, grads[:7])]
+    checks += [("d vol", grads[7].cpu(), vol_r.grad), ("d axis_scale", grads[8].cpu(), P["graph_net.axis_scale"].grad)]
+    for nm, got, want in checks:
+        rel = float((got.reshape(-1) - want.reshape(-1)).norm() / (want.norm() + 1e-12))
+        print(f"[train] field bwd {name} {nm:36s} |g| {float(want.norm()):.3e} rel {rel:.3e}")
+        assert rel <= 2e-4, (nm, rel)
