@@ -489,15 +489,22 @@ static int mlp_launch(const void* xtiles, const void* wstream, const float* head
     int grid = num_sms < max_tiles ? num_sms : max_tiles;
     if (grid < 1) grid = 1;
     cudaError_t e;
+    static bool attr_set[2] = {false, false};           // idempotent launch attribute, set on first use per variant
     if (density_only) {
-        e = cudaFuncSetAttribute(mlp::mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
+        if (!attr_set[0]) {
+            e = cudaFuncSetAttribute(mlp::mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return (int)e;
+            attr_set[0] = true;
+        }
         mlp::mlp_kernel<false><<<grid, mlp::kThreads, smem, (cudaStream_t)stream>>>(
             (const uint8_t*)xtiles, (const uint8_t*)wstream, heads, ray_bias, row_sample, row_ray, n_rows_dev, out, out_capacity,
             (__nv_bfloat16*)act_save, (__nv_bfloat16*)g_save, save_cap, trace);
     } else {
-        e = cudaFuncSetAttribute(mlp::mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
+        if (!attr_set[1]) {
+            e = cudaFuncSetAttribute(mlp::mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return (int)e;
+            attr_set[1] = true;
+        }
         mlp::mlp_kernel<true><<<grid, mlp::kThreads, smem, (cudaStream_t)stream>>>(
             (const uint8_t*)xtiles, (const uint8_t*)wstream, heads, ray_bias, row_sample, row_ray, n_rows_dev, out, out_capacity,
             (__nv_bfloat16*)act_save, (__nv_bfloat16*)g_save, save_cap, trace);

@@ -76,7 +76,8 @@ class GraphNet(nn.Module):
         scale = torch.ones(J, 3) * base_scale
         if skel_profile is not None:
             scale = sk.initial_axis_scale(skel_profile, base_scale)
-        self.init_scale = scale.clone()
+        # plain attribute in the reference (gnn_backbone.py:784); a non-persistent buffer here so it follows .to(device)
+        self.register_buffer("init_scale", scale.clone(), persistent=False)
         self.axis_scale = nn.Parameter(scale, requires_grad=opt_scale)
         mask = torch.ones(1, J, 1)
         mask[:, 0] = 0.                                         # mask_root

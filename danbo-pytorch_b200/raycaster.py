@@ -46,6 +46,7 @@ class RayCaster(nn.Module):
         self._packed = None
         self._packed_key = None
         self._align_dev = None
+        self._graphed = None
 
     # ------------------------------------------------------------------------------------------------ dispatch
     def forward(self, *args, fwd_type="", **kwargs):
@@ -63,6 +64,23 @@ class RayCaster(nn.Module):
 
     def get_networks(self):
         return self.network, self.network_fine
+
+    def render_graphed(self, ray_batch, N_samples, kp_batch=None, skts=None, cyls=None, bones=None, cams=None,
+                       N_uniques=1, N_importance=0, nanmean_chunk=None, preproc_kwargs=None, **ignored):
+        """Eval-mode render replayed from a CUDA graph (one graph per ray count).  Same inputs and returned dict as the
+        plain call; the returned tensors are static buffers that the next graphed call overwrites."""
+        from .graphs import GraphedFn
+        if self.training:
+            raise RuntimeError("render_graphed is for eval mode")
+        B = float((preproc_kwargs or {}).get("density_scale", 1.0))
+        rays, pose_skts, pose_bones, pose_cyls, cam_idx, skip = self._prepare(ray_batch, skts, cyls, bones, cams, N_uniques)
+        if self._graphed is None:
+            def run(rays, pose_skts, pose_bones, pose_cyls, cam_idx, **kw):
+                with torch.no_grad():
+                    return self._render_prepared(rays, pose_skts, pose_bones, pose_cyls, cam_idx, **kw)
+            self._graphed = GraphedFn(run, self._device())
+        return self._graphed(rays=rays, pose_skts=pose_skts, pose_bones=pose_bones, pose_cyls=pose_cyls, cam_idx=cam_idx,
+                             skip=skip, N_samples=N_samples, N_importance=N_importance, B=B, nanmean_chunk=nanmean_chunk)
 
     def update_embed_fns(self, global_step, args):
         self.network.update_embed_fns(global_step, args)
@@ -137,6 +155,13 @@ class RayCaster(nn.Module):
         if pk.get("density_fn", F.relu) is not F.relu:
             raise NotImplementedError("density_type other than 'relu' is not implemented")
         B = float(pk.get("density_scale", 1.0))
+        rays, pose_skts, pose_bones, pose_cyls, cam_idx, skip = self._prepare(ray_batch, skts, cyls, bones, cams, N_uniques)
+        return self._render_prepared(rays, pose_skts, pose_bones, pose_cyls, cam_idx, skip=skip, N_samples=N_samples,
+                                     N_importance=N_importance, B=B, raw_noise_std=raw_noise_std, perturb=perturb,
+                                     nanmean_chunk=nanmean_chunk, _rand=_rand, _stages=_stages)
+
+    def _prepare(self, ray_batch, skts, cyls, bones, cams, N_uniques):
+        """Host-side reduction of the reference's per-ray stride-0 expands to per-pose tables (encoders.py:465-471)."""
         dev = self._device()
         N = ray_batch.shape[0]
         skip = max(N // max(int(N_uniques), 1), 1)
@@ -145,7 +170,12 @@ class RayCaster(nn.Module):
         pose_bones = self._unique(bones, skip).to(dev, non_blocking=True)
         pose_cyls = self._unique(cyls, skip).to(dev, non_blocking=True)
         cam_idx = cams.reshape(N, -1)[:, 0].to(dev, non_blocking=True).to(torch.int32).contiguous()
+        return rays, pose_skts, pose_bones, pose_cyls, cam_idx, skip
 
+    def _render_prepared(self, rays, pose_skts, pose_bones, pose_cyls, cam_idx, skip=1, N_samples=64, N_importance=16,
+                         B=1.0, raw_noise_std=0., perturb=0., nanmean_chunk=None, _rand=None, _stages=None):
+        dev = self._device()
+        N = rays.shape[0]
         net = self.network
         consts = self._consts()
         packed = self._packed_mlp()

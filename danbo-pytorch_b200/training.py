@@ -1,0 +1,86 @@
+"""Training step around the hot path: the trainer's losses (they stay PyTorch elementwise ops, SURVEY §8a row L*),
+Adam, and the data-parallel gradient exchange.  Mirrors core/trainer.py:257-300 (train_batch), :348-422,507-553
+(losses), :563-576 (optimize) for the flags the shipped DANBO configs use."""
+import torch
+import torch.nn.functional as F
+
+from . import parallel
+
+
+def _img_loss(kind, x, y, beta=0.1):
+    if kind == "L1":
+        return torch.mean(torch.abs(x - y))
+    if kind == "MSE":
+        return torch.mean((x - y) ** 2)
+    if kind == "Huber":
+        return F.smooth_l1_loss(x, y, reduction="mean", beta=beta)
+    raise NotImplementedError(f"loss_fn {kind}")
+
+
+def compute_loss(args, preds, batch, network):
+    """total loss + dict of terms: rgb (fine + coarse), soft-softmax on confd, volume-scale penalty."""
+    bgs = batch.get("bgs", 1.0)
+    terms = {}
+
+    def rgb_term(rgb, acc):
+        if getattr(args, "use_background", True):
+            rgb = rgb + (1. - acc)[..., None] * bgs
+        return _img_loss(args.loss_fn, rgb, batch["target_s"], getattr(args, "loss_beta", 0.1)) * getattr(args, "rgb_loss_coef", 1.0)
+
+    terms["rgb_loss"] = rgb_term(preds["rgb_map"], preds["acc_map"])
+    if "rgb0" in preds:
+        terms["rgb_loss0"] = rgb_term(preds["rgb0"], preds["acc0"]) * getattr(args, "coarse_weight", 1.0)
+    if "confd" in preds and args.agg_type == "sigmoid":
+        labels = ((preds["T_i"] * preds["alpha"]) > 0).float()
+        valid = 1 - preds["part_invalid"]
+        p = network.sigmoid(preds["confd"], preds["part_invalid"], mask_invalid=False, clamp=False)
+        terms["soft_softmax_loss"] = args.soft_softmax_loss_coef * (labels - (p * valid).sum(-1)).pow(2.).mean()
+    if getattr(args, "opt_vol_scale", False):
+        gn = network.graph_net
+        scale = gn.axis_scale.abs().clamp(min=gn.init_scale.to(gn.axis_scale.device) * 0.05)
+        # product written out: torch.prod's backward inspects the input for zeros on the host (a sync, illegal in capture)
+        terms["vol_scale_loss"] = (scale[:, 0] * scale[:, 1] * scale[:, 2]).sum() * args.vol_scale_penalty
+    return sum(terms.values()), terms
+
+
+class TrainStep:
+    """forward -> losses -> backward -> (all-reduce of one flat fp32 gradient bucket) -> Adam."""
+
+    def __init__(self, caster, args, optimizer=None, world_size=1, graph=False):
+        self.caster, self.args, self.world = caster, args, world_size
+        params = [p for p in caster.network.parameters() if p.requires_grad]
+        self.bucket = parallel.GradBucket(params)
+        cuda = params[0].is_cuda
+        self.optimizer = optimizer or torch.optim.Adam(params, lr=args.lrate, betas=(0.9, 0.999), fused=cuda,
+                                                       capturable=bool(graph and cuda))
+        self._graphed = None
+        if graph:
+            from .graphs import GraphedFn
+
+            def run(**b):
+                loss, preds = self._step(b)
+                return {"loss": loss, "rgb_map": preds["rgb_map"], "acc_map": preds["acc_map"]}
+            self._graphed = GraphedFn(run, params[0].device, warmup=3)
+
+    def __call__(self, batch):
+        if self._graphed is not None:
+            out = self._graphed(**batch)
+            return out["loss"], out
+        return self._step(batch)
+
+    def _step(self, batch):
+        a = self.args
+        self.caster.train()
+        self.bucket.zero()
+        preds = self.caster(batch["ray_batch"], N_samples=a.N_samples, kp_batch=batch["kp_batch"], skts=batch["skts"],
+                            cyls=batch["cyls"], bones=batch["bones"], cams=batch["cams"], N_uniques=batch["N_uniques"],
+                            perturb=a.perturb, N_importance=a.N_importance, raw_noise_std=a.raw_noise_std)
+        loss, terms = compute_loss(a, preds, batch, self.caster.network)
+        if self.world > 1:
+            # every rank holds 1/world of the batch: mean-reduced data terms are averaged by the all-reduce; the
+            # parameter-only volume penalty is identical on every rank, so averaging leaves it unchanged
+            pass
+        loss.backward()
+        self.bucket.allreduce(average=True)
+        self.optimizer.step()
+        return loss.detach(), preds

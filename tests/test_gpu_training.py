@@ -278,3 +278,29 @@ def test_field_backward(name):
         rel = float((got.reshape(-1) - want.reshape(-1)).norm() / (want.norm() + 1e-12))
         print(f"[train] field bwd {name} {nm:36s} |g| {float(want.norm()):.3e} rel {rel:.3e}")
         assert rel <= 2e-4, (nm, rel)
+
+
+def test_cuda_graph_paths():
+    """Graph replay must reproduce the launch-by-launch results (render), and a graphed training step must train."""
+    from util import pose_tensors
+    from danbo_b200 import synthetic as syn, training
+    fx = load_fixture("render_fast")
+    caster, args, _ = make_caster("danbo_fast")
+    skts, bones, cyl = pose_tensors(fx)
+    N = fx["ray_batch"].shape[0]
+    ex = lambda t: t.expand(N, *t.shape[1:])
+    kw = dict(N_samples=args.N_samples, kp_batch=ex(fx["pose_kps"][None]), skts=ex(skts), cyls=ex(cyl), bones=ex(bones),
+              cams=fx["cams"], N_uniques=1, N_importance=args.N_importance)
+    a = caster(fx["ray_batch"], perturb=False, raw_noise_std=0., **kw)
+    for _ in range(2):
+        b = caster.render_graphed(fx["ray_batch"], **kw)
+    torch.cuda.synchronize()
+    for k in ("rgb_map", "acc_map", "disp_map", "rgb0"):
+        assert torch.equal(a[k], b[k]), k
+    caster2, args2, _ = make_caster("danbo_cfg3", train=True)
+    batch = syn.training_batch(4, 48, seed=2)
+    batch = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in batch.items()}
+    step = training.TrainStep(caster2, args2, graph=True)
+    losses = [float(step(batch)[0]) for _ in range(12)]
+    print("[train] graphed step losses", ["%.4f" % l for l in losses])
+    assert all(l == l for l in losses) and losses[-1] < losses[0]
