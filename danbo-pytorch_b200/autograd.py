@@ -68,9 +68,17 @@ class _RenderBlock(torch.autograd.Function):
         d_vol = zeros(*ctx.vol_shape)
         d_vol_blk = d_vol[k["p0"]:]
         agg_grads = [G[nm] for nm in AGG_NAMES] + [d_vol_blk, G["graph_net.axis_scale"]]
+        ws = None
+        if K.BACKWARD_IMPL == "tc":
+            ws = K.BwdWorkspace(max(k["act0"].capacity, k["act1"].capacity), dev)
+        first = True
         for (d_raw, S, z, mask, act, fo, sv, gl) in ((d_raw0, S_c, k["z0"], k["mask0"], k["act0"], k["f0"], k["sv0"], gl0),
                                                     (d_raw1, S_f, k["z1"], k["mask1"], k["act1"], k["f1"], k["sv1"], gl1)):
-            dX = K.mlp_backward(P, G, d_raw, act, fo, sv, d_ray_bias)
+            if ws is not None:
+                dX = K.mlp_backward_tc(P, G, d_raw, act, fo, sv, d_ray_bias, ws, repack=first)
+                first = False
+            else:
+                dX = K.mlp_backward(P, G, d_raw, act, fo, sv, d_ray_bias)
             K.field_agg_bwd(rays, S, z, mask, act, k["p_skts"], k["p_vol"], k["skip"], k["consts"], fo, dX, gl, agg_grads)
         K.ray_bias_bwd(rays, k["cam_idx"], k["codes"], P["views_linears.0.weight"], d_ray_bias,
                        G["views_linears.0.weight"], G["views_linears.0.bias"], G["framecodes.codes.weight"])

@@ -181,14 +181,14 @@ head_bwd_kernel(const float* __restrict__ d_raw, const int* __restrict__ row_sam
             const int c = lane + 32 * q;
             const float gv = __bfloat162float(g_save[(size_t)r * 128 + c]);
             const float d = gv > 0.f ? (g.x * w_rgb[c] + g.y * w_rgb[128 + c] + g.z * w_rgb[256 + c]) : 0.f;
-            delta9[(size_t)r * 128 + c] = d;
+            if (delta9) delta9[(size_t)r * 128 + c] = d;
             atomicAdd(d_ray_bias + (size_t)ray * 128 + c, d);
             atomicAdd(&s_wrgb[0][c], g.x * gv); atomicAdd(&s_wrgb[1][c], g.y * gv); atomicAdd(&s_wrgb[2][c], g.z * gv);
         }
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const int c = lane + 32 * q;
-            d_a7[(size_t)r * 256 + c] = g.w * w_alpha[c];
+            if (d_a7) d_a7[(size_t)r * 256 + c] = g.w * w_alpha[c];
             atomicAdd(&s_walpha[c], g.w * __bfloat162float(a7_save[(size_t)r * 256 + c]));
         }
         if (lane == 0) { atomicAdd(&s_brgb[0], g.x); atomicAdd(&s_brgb[1], g.y); atomicAdd(&s_brgb[2], g.z); atomicAdd(&s_balpha, g.w); }

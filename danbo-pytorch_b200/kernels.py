@@ -431,6 +431,55 @@ def mlp_backward(P, G, d_raw, active, fo, save, d_ray_bias):
     return dX
 
 
+BACKWARD_IMPL = "tc"          # "tc": tcgen05 dgrad/wgrad kernels; "simt": the fp32 SIMT GEMM chain (kept as a cross-check)
+
+
+class BwdWorkspace:
+    """Buffers of the tensor-core MLP backward for one row capacity (reused by the coarse and fine passes)."""
+
+    def __init__(self, cap, device):
+        lib = _lib.load()
+        sizes = [ctypes.c_longlong() for _ in range(5)]
+        ns = ctypes.c_int()
+        lib.danbo_mlp_bwd_workspace(int(cap), *[ctypes.byref(x) for x in sizes], ctypes.byref(ns))
+        u8 = lambda n: torch.empty(int(n), device=device, dtype=torch.uint8)
+        self.cap = int(cap)
+        self.wstream, self.delta, self.deltaT, self.actT, self.partial = [u8(x.value) for x in sizes]
+        self.packed_key = None
+
+
+def mlp_backward_tc(P, G, d_raw, active, fo, save, d_ray_bias, ws, repack=True):
+    """Tensor-core backward of the fused MLP over the rows of one pass -> dX (cap,208) fp32; parameter grads added to G."""
+    lib = _lib.load()
+    dev = d_raw.device
+    cap = active.capacity
+    assert ws.cap >= cap and save.cap == cap
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    # rgb / alpha heads, ray-bias gradient (small fp32 reductions)
+    _lib.check(lib.danbo_mlp_head_bwd(_p(d_raw), _p(active.ids), _p(fo.row_ray), _p(active.count), cap, _p(save.g),
+                                      _p(save.act[7]), _p(P["rgb_linear.weight"]), _p(P["alpha_linear.weight"]), None,
+                                      None, _p(G["rgb_linear.weight"]), _p(G["rgb_linear.bias"]),
+                                      _p(G["alpha_linear.weight"]), _p(G["alpha_linear.bias"]), _p(d_ray_bias),
+                                      num_sms(idx), _stream()), "danbo_mlp_head_bwd")
+    if repack:
+        wa = (ctypes.c_void_p * 8)(*[P[f"pts_linears.{i}.weight"].data_ptr() for i in range(8)])
+        _lib.check(lib.danbo_pack_mlp_dgrad(wa, _p(P["feature_linear.weight"]), _p(P["views_linears.0.weight"]),
+                                            _p(ws.wstream), _stream()), "danbo_pack_mlp_dgrad")
+        _count(1)
+    dX = torch.empty(cap, 208, device=dev, dtype=torch.float32)
+    _lib.check(lib.danbo_mlp_dgrad(_p(ws.wstream), _p(P["rgb_linear.weight"]), _p(P["alpha_linear.weight"]), _p(d_raw),
+                                   _p(active.ids), _p(active.count), cap, _p(save.act), _p(save.g), cap, _p(ws.delta),
+                                   _p(dX), num_sms(idx), _stream()), "danbo_mlp_dgrad")
+    dw_names = ["views_linears.0.weight", "feature_linear.weight"] + [f"pts_linears.{i}.weight" for i in range(7, -1, -1)]
+    db_names = ["feature_linear.bias"] + [f"pts_linears.{i}.bias" for i in range(7, -1, -1)]
+    dw = (ctypes.c_void_p * 10)(*[G[n].data_ptr() for n in dw_names])
+    db = (ctypes.c_void_p * 9)(*[G[n].data_ptr() for n in db_names])
+    _lib.check(lib.danbo_mlp_wgrad(_p(save.act), _p(fo.x_rows), _p(ws.delta), cap, _p(active.count), cap, _p(ws.deltaT),
+                                   _p(ws.actT), _p(ws.partial), dw, db, _stream()), "danbo_mlp_wgrad")
+    _count(9)
+    return dX
+
+
 def ray_bias_bwd(rays, cam_idx, codes_with_mean, w_view, d_ray_bias, d_w_view, d_b_view, d_codes):
     lib = _lib.load()
     _lib.check(lib.danbo_ray_bias_bwd(_p(rays), rays.stride(0), rays.shape[0], _p(cam_idx), _p(codes_with_mean),
