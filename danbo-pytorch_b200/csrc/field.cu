@@ -14,7 +14,7 @@ __global__ void nearfar_cyl_kernel(const float* __restrict__ rays, int ray_strid
                                    int seg_len, float* __restrict__ near_out, float* __restrict__ far_out,
                                    double* __restrict__ seg_acc /* [n_seg][4] sum_near,cnt_near,sum_far,cnt_far */) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= n_rays) return;
+    if (n >= n_rays) return;                             // (tail warps fall back to per-thread atomics below)
     const float* r = rays + (size_t)n * ray_stride;
     const float ox = r[0], oz = r[2], dx = r[3], dz = r[5], near = r[6], far = r[7];
     int pose = n / rays_per_pose; if (pose >= n_poses) pose = n_poses - 1;
@@ -38,9 +38,26 @@ __global__ void nearfar_cyl_kernel(const float* __restrict__ rays, int ray_strid
     far_out[n] = (Q != Q) ? __int_as_float(0x7fc00000) : ff;
     const int seg = seg_len > 0 ? n / seg_len : 0;
     double* acc = seg_acc + 4 * (size_t)seg;
-    // nanmean over the segment: every non-NaN entry counts (ray_utils.py:334,340)
-    if (nn == nn) { atomicAdd(acc + 0, (double)nn); atomicAdd(acc + 1, 1.0); }
-    if (ff == ff) { atomicAdd(acc + 2, (double)ff); atomicAdd(acc + 3, 1.0); }
+    // nanmean over the segment: every non-NaN entry counts (ray_utils.py:334,340).  One atomic per warp and quantity
+    // when the warp sits inside one segment (always, for the reference's 4096-ray chunks).
+    double v0 = (nn == nn) ? (double)nn : 0.0, c0 = (nn == nn) ? 1.0 : 0.0;
+    double v1 = (ff == ff) ? (double)ff : 0.0, c1 = (ff == ff) ? 1.0 : 0.0;
+    const unsigned active = __activemask();
+    const int seg0 = __shfl_sync(active, seg, __ffs(active) - 1);
+    if (__all_sync(active, seg == seg0) && active == 0xffffffffu) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            v0 += __shfl_xor_sync(0xffffffffu, v0, o); c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+            v1 += __shfl_xor_sync(0xffffffffu, v1, o); c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (c0 > 0.0) { atomicAdd(acc + 0, v0); atomicAdd(acc + 1, c0); }
+            if (c1 > 0.0) { atomicAdd(acc + 2, v1); atomicAdd(acc + 3, c1); }
+        }
+    } else {
+        if (c0 > 0.0) { atomicAdd(acc + 0, v0); atomicAdd(acc + 1, c0); }
+        if (c1 > 0.0) { atomicAdd(acc + 2, v1); atomicAdd(acc + 3, c1); }
+    }
 }
 
 // NF1 fill + NF2: per-bone oriented-box near/far in fp64 with the exactly-two-hits rule (F7).
@@ -140,7 +157,16 @@ __global__ void nearfar_finish_kernel(const float* __restrict__ rays, int ray_st
 //   fine mode   (z_in != null): z given (importance samples)
 // Emits the 24-bit visibility mask of every sample and appends samples with a non-empty mask to the active
 // list; with append_empty, one extra entry per ray (id = n_rays*S + ray) stands for "a sample no bone sees".
-__global__ void sample_mask_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, int S,
+// kTable: the block first builds, per ray it covers and per bone, the affine map z -> x = c + z e of the two-step
+// transform (x is affine in the sample depth), then every sample needs 3 FMAs per bone instead of ~45 instructions.
+// Rounding differs from the reference's op order by ~1e-5 at most, so a coordinate within 2e-4 of a box face is
+// re-evaluated in the exact order: the emitted mask is identical to the direct evaluation.
+constexpr int kMaskBlock = 256;
+constexpr int kMaxRaysPerBlock = 18;       // 256 / 16 + 2
+
+template <bool kTable>
+__global__ void __launch_bounds__(kMaskBlock)
+sample_mask_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, int S,
                                    const float* __restrict__ near, const float* __restrict__ far,
                                    const float* __restrict__ t_vals, const float* __restrict__ t_rand,
                                    const float* __restrict__ z_in, float* __restrict__ z_out,
@@ -151,6 +177,36 @@ __global__ void sample_mask_kernel(const float* __restrict__ rays, int ray_strid
     const int total = n_rays * S;
     uint32_t mask = 0;
     int n = 0, s = 0;
+    __shared__ float4 tab[kTable ? kMaxRaysPerBlock * DANBO_J * 2 : 1];     // (c.xyz, e.xyz) per (ray slot, bone)
+    const int ray_first = (blockIdx.x * kMaskBlock) / S;
+    if (kTable) {
+        const int ray_last = min(n_rays - 1, (blockIdx.x * kMaskBlock + kMaskBlock - 1) / S);
+        const int n_ent = (ray_last - ray_first + 1) * DANBO_J;
+        for (int e = threadIdx.x; e < n_ent; e += kMaskBlock) {
+            const int slot = e / DANBO_J, j = e - slot * DANBO_J;
+            const int rn = ray_first + slot;
+            const float* r = rays + (size_t)rn * ray_stride;
+            int pose = rn / rays_per_pose; if (pose >= n_poses) pose = n_poses - 1;
+            const float* sk = pose_skts + ((size_t)pose * DANBO_J + j) * 16;
+            const float* A = fc.align + j * 16;
+            float c[3], d[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                c[i] = sk[4 * i] * r[0] + sk[4 * i + 1] * r[1] + sk[4 * i + 2] * r[2] + sk[4 * i + 3];
+                d[i] = sk[4 * i] * r[3] + sk[4 * i + 1] * r[4] + sk[4 * i + 2] * r[5];
+            }
+            float cc[3], ee[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const float inv = 1.f / fabsf(__ldg(fc.axis_scale + j * 3 + i));
+                cc[i] = (A[4 * i] * c[0] + A[4 * i + 1] * c[1] + A[4 * i + 2] * c[2] + A[4 * i + 3]) * inv;
+                ee[i] = (A[4 * i] * d[0] + A[4 * i + 1] * d[1] + A[4 * i + 2] * d[2]) * inv;
+            }
+            tab[2 * e] = make_float4(cc[0], cc[1], cc[2], 0.f);
+            tab[2 * e + 1] = make_float4(ee[0], ee[1], ee[2], 0.f);
+        }
+        __syncthreads();
+    }
     if (idx < total) {
         n = idx / S; s = idx - n * S;
         const float* r = rays + (size_t)n * ray_stride;
@@ -173,14 +229,25 @@ __global__ void sample_mask_kernel(const float* __restrict__ rays, int ray_strid
         const float pz = __fadd_rn(r[2], __fmul_rn(r[5], z));
         int pose = n / rays_per_pose; if (pose >= n_poses) pose = n_poses - 1;
         const float* skt = pose_skts + (size_t)pose * DANBO_J * 16;
+        const float4* tr = tab + (kTable ? (n - ray_first) * DANBO_J * 2 : 0);
 #pragma unroll 4
         for (int j = 0; j < DANBO_J; ++j) {
-            // |fl(t/s)| > 1  <=>  |t| > |s| for correctly rounded division (t > s implies t/s > 1 + 2^-24, which
-            // rounds above 1), so the visibility mask needs no divide here; field_agg divides for the few bones it reads
-            float t0, t1, t2;
-            bone_aligned(skt + j * 16, fc.align + j * 16, px, py, pz, t0, t1, t2);
-            const float* sc = fc.axis_scale + j * 3;
-            const bool invalid = (fabsf(t0) > fabsf(__ldg(sc))) || (fabsf(t1) > fabsf(__ldg(sc + 1))) || (fabsf(t2) > fabsf(__ldg(sc + 2)));
+            bool decided = false, invalid = false;
+            if (kTable) {
+                const float4 c = tr[2 * j], e = tr[2 * j + 1];
+                const float a0 = fabsf(fmaf(z, e.x, c.x)), a1 = fabsf(fmaf(z, e.y, c.y)), a2 = fabsf(fmaf(z, e.z, c.z));
+                const float m = fminf(fminf(fabsf(a0 - 1.f), fabsf(a1 - 1.f)), fabsf(a2 - 1.f));
+                invalid = (a0 > 1.f) || (a1 > 1.f) || (a2 > 1.f);
+                decided = m > 2e-4f;
+            }
+            if (!decided) {
+                // |fl(t/s)| > 1  <=>  |t| > |s| for correctly rounded division (t > s implies t/s > 1 + 2^-24, which
+                // rounds above 1), so the visibility mask needs no divide; field_agg divides for the few bones it reads
+                float t0, t1, t2;
+                bone_aligned(skt + j * 16, fc.align + j * 16, px, py, pz, t0, t1, t2);
+                const float* sc = fc.axis_scale + j * 3;
+                invalid = (fabsf(t0) > fabsf(__ldg(sc))) || (fabsf(t1) > fabsf(__ldg(sc + 1))) || (fabsf(t2) > fabsf(__ldg(sc + 2)));
+            }
             mask |= (invalid ? 0u : 1u) << j;
         }
         mask_out[idx] = mask;
@@ -515,10 +582,17 @@ extern "C" int danbo_sample_mask(const float* rays, int ray_stride, int n_rays, 
     if (!z_in && (!near || !far || !t_vals || !z_out)) return -1;
     const long long total = (long long)n_rays * S;
     if (total + n_rays >= (1LL << 31)) return -2;
-    const int B = 256, G = (int)((total + B - 1) / B);
-    sample_mask_kernel<<<G, B, 0, (cudaStream_t)stream>>>(rays, ray_stride, n_rays, S, near, far, t_vals, t_rand, z_in,
-                                                          z_out, pose_skts, rays_per_pose, n_poses, make_consts(consts),
-                                                          mask_out, active_ids, active_count, capacity, append_empty);
+    const int B = kMaskBlock, G = (int)((total + B - 1) / B);
+    if (S >= 16)
+        sample_mask_kernel<true><<<G, B, 0, (cudaStream_t)stream>>>(rays, ray_stride, n_rays, S, near, far, t_vals, t_rand,
+                                                                    z_in, z_out, pose_skts, rays_per_pose, n_poses,
+                                                                    make_consts(consts), mask_out, active_ids,
+                                                                    active_count, capacity, append_empty);
+    else
+        sample_mask_kernel<false><<<G, B, 0, (cudaStream_t)stream>>>(rays, ray_stride, n_rays, S, near, far, t_vals, t_rand,
+                                                                     z_in, z_out, pose_skts, rays_per_pose, n_poses,
+                                                                     make_consts(consts), mask_out, active_ids,
+                                                                     active_count, capacity, append_empty);
     DANBO_CHECK_LAUNCH();
     return 0;
 }
