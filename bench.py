@@ -111,6 +111,12 @@ def caster_kwargs(args, batch, device=None):
                 N_importance=args.N_importance, raw_noise_std=0., nanmean_chunk=args.chunk)
 
 
+def _mark(msg):
+    if os.environ.get("DANBO_BENCH_VERBOSE"):
+        sys.stderr.write(f"[bench rank {os.environ.get('RANK', '0')} t={time.perf_counter():.1f}] {msg}\n")
+        sys.stderr.flush()
+
+
 def run_ours(opt):
     import torch.distributed as dist
     import danbo_b200 as db
@@ -120,7 +126,9 @@ def run_ours(opt):
         opt.gpus = world
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
+    _mark(f"init done world={world}")
     caster, args, batch = build_scene(rank, device)
+    _mark("scene built")
     n_rays = batch["ray_batch"].shape[0]
     rays_dev = batch["ray_batch"].to(device)
     kw_dev = caster_kwargs(args, batch, device)
@@ -155,7 +163,9 @@ def run_ours(opt):
     for _ in range(max(opt.warmup, 3)):
         step_device()
         flush.fill_(1)
+    _mark("warmup issued")
     barrier()
+    _mark("warmup done")
     sampler = ClockSampler(local)
     sampler.start()
     kernels.PROFILE = {"mlp": [], "launches": 0}
@@ -168,6 +178,7 @@ def run_ours(opt):
         ev[i][1].record()
         flush.fill_(i)                                       # L2 flush between timed iterations (not timed)
     barrier()
+    _mark("timed steps done")
     t_wall = time.perf_counter() - t_wall0
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     # the timed steps replay one CUDA graph; the same steps are run once more launch by launch with CUDA events around
@@ -192,6 +203,7 @@ def run_ours(opt):
         ev2[i][1].record()
         flush.fill_(i)
     barrier()
+    _mark("e2e done")
     e2e_ms = sum(a.elapsed_time(b) for a, b in ev2)
     clocks = sampler.stop()
     t = torch.tensor([dev_ms, e2e_ms], device=device, dtype=torch.float64)
@@ -201,7 +213,9 @@ def run_ours(opt):
     del caster, rays_dev, kw_dev, flush
     torch.cuda.empty_cache()
     try:
+        _mark("train start")
         train_info = run_train(rank, world, device, max(opt.steps, 5), opt.warmup)
+        _mark("train done")
     except Exception as exc:                                  # the headline render number must survive a training failure
         train_info = {"error": repr(exc)}
     if rank != 0:

@@ -56,19 +56,34 @@ class TrainStep:
         self._graphed = None
         if graph:
             from .graphs import GraphedFn
-
-            def run(**b):
-                loss, preds = self._step(b)
-                return {"loss": loss, "rgb_map": preds["rgb_map"], "acc_map": preds["acc_map"]}
+            if world_size > 1:
+                # the graph holds forward + backward; the gradient all-reduce and Adam stay ordinary stream work, so no
+                # NCCL call is ever captured
+                def run(**b):
+                    loss, preds = self._fwd_bwd(b)
+                    return {"loss": loss, "rgb_map": preds["rgb_map"], "acc_map": preds["acc_map"]}
+            else:
+                def run(**b):
+                    loss, preds = self._step(b)
+                    return {"loss": loss, "rgb_map": preds["rgb_map"], "acc_map": preds["acc_map"]}
             self._graphed = GraphedFn(run, params[0].device, warmup=3)
 
     def __call__(self, batch):
         if self._graphed is not None:
             out = self._graphed(**batch)
+            if self.world > 1:
+                self.bucket.allreduce(average=True)
+                self.optimizer.step()
             return out["loss"], out
         return self._step(batch)
 
     def _step(self, batch):
+        loss, preds = self._fwd_bwd(batch)
+        self.bucket.allreduce(average=True)
+        self.optimizer.step()
+        return loss, preds
+
+    def _fwd_bwd(self, batch):
         a = self.args
         self.caster.train()
         self.bucket.zero()
@@ -81,6 +96,4 @@ class TrainStep:
             # parameter-only volume penalty is identical on every rank, so averaging leaves it unchanged
             pass
         loss.backward()
-        self.bucket.allreduce(average=True)
-        self.optimizer.step()
         return loss.detach(), preds
