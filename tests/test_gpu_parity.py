@@ -331,3 +331,30 @@ def test_full_size_properties():
     sl = slice(8192, 8192 + 4096)
     sub = caster(b["ray_batch"][sl], **{k: (v[sl] if torch.is_tensor(v) and v.shape[0] == N else v) for k, v in kw.items()})
     assert torch.equal(sub["rgb_map"], out["rgb_map"][sl]) and torch.equal(sub["acc_map"], out["acc_map"][sl])
+
+
+def test_render_images_and_density_grid_callers():
+    """Callers of the path (render_path / render_mesh mirrors): device-side ray generation + box culling + image
+    assembly equals the host-side synthetic batch, and the slab-wise lattice equals the one-shot 'mesh' call."""
+    from danbo_b200 import synthetic as syn, render
+    caster, args, P = make_caster("danbo_fast")
+    pose = syn.make_pose(3)
+    H = W = 96
+    c2w = syn.camera()
+    imgs = render.render_images(caster, args, [c2w], [pose], H, W)
+    b = syn.render_batch(pose, H, W)
+    ret = caster(b["ray_batch"], N_samples=args.N_samples, kp_batch=b["kp_batch"], skts=b["skts"], cyls=b["cyls"],
+                 bones=b["bones"], cams=b["cams"], N_uniques=1, perturb=False, N_importance=args.N_importance,
+                 raw_noise_std=0., nanmean_chunk=args.chunk)
+    want = torch.ones(H * W, 3, device=DEV)
+    want[b["pixel_idx"].to(DEV)] = ret["rgb_map"] + (1. - ret["acc_map"])[:, None]
+    # ray directions generated on the device differ from the host ones in the last ulp (3-term sums in another order);
+    # a sample sitting on a bone-box face can then flip, so compare statistically
+    diff = (imgs[0].reshape(-1, 3) - want).abs()
+    assert float(diff.mean()) <= 2e-4 and float((diff > 1e-3).float().mean()) <= 1e-2, (float(diff.mean()), float(diff.max()))
+    g = render.render_images(caster, args, [c2w], [pose], H, W, graphed=True)
+    assert torch.equal(g, imgs)
+    t = lambda a: torch.as_tensor(a)[None].to(DEV)
+    full = caster(kps=t(pose["kps"]), skts=t(pose["skts"]), bones=t(pose["bones"]), radius=0.9, res=15, fwd_type="mesh")
+    slabs = render.density_grid(caster, t(pose["kps"]), t(pose["skts"]), t(pose["bones"]), radius=0.9, res=15, slab_points=1024)
+    assert torch.equal(full, slabs)
