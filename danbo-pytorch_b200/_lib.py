@@ -17,6 +17,7 @@ _SIGNATURES = {
     "danbo_field_agg": [c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p],
     "danbo_ray_bias": [c_p, c_i, c_i, c_p, c_p, c_i, c_p, c_p, c_p],
     "danbo_mlp_workspace_bytes": [c_p, c_p, c_p],
+    "danbo_mlp_set_cta_pair": [c_i],
     "danbo_pack_mlp_weights": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "danbo_mlp_forward": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_i, c_i, c_i, c_p],
     "danbo_mlp_forward_trace": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_i, c_i, c_i, c_p, c_p],
@@ -56,6 +57,8 @@ def load():
             fn = getattr(lib, name)
             fn.argtypes = argtypes
             fn.restype = ctypes.c_int
+        if os.environ.get("DANBO_MLP_CTA_PAIR", "") == "0":      # debugging aid: single-CTA MLP kernel variant
+            lib.danbo_mlp_set_cta_pair(0)
         _lib = lib
     return _lib
 

@@ -24,7 +24,17 @@
 namespace danbo {
 namespace mlp {
 
-constexpr int kStages = 9;
+constexpr int kStages = 9;                         // 16 KB units of shared memory reserved for the weight ring
+// Ring slots actually used.  Chosen so that the stages of one tile (84 full / 72 density-only) are an EVEN multiple of
+// the slot count: the slot and the mbarrier parity of every stage are then compile-time constants of the fully
+// unrolled MMA schedule (runtime slot arithmetic kept descriptors in vector registers: R2UR chains and a waterfall
+// loop around every commit, ~430 clk per 4-MMA stage instead of 256; measured).
+__host__ __device__ constexpr int ring_slots(bool full, bool pair) { return pair ? (full ? 7 : 9) : (full ? 7 : 9); }
+// Every ring slot is 16 KB and is filled by ONE bulk copy: issuing a cp.async.bulk costs the producer warp ~330 clk
+// whatever its size (measured, scripts/micro/bulk_rate.cu), so copies must be few and large.  Single CTA: a slot is
+// one stage ([128 x 64] of B).  CTA pair: a slot is this CTA's 64-row half of TWO consecutive stages (a "group"); the
+// pack kernel writes a second copy of the stream in that order behind the first.
+__host__ __device__ constexpr int stages_per_slot(bool pair) { return pair ? 2 : 1; }
 constexpr int kStageBytes = 128 * 64 * 2;          // 16 KB
 constexpr int kXBytes = DANBO_X_TILE_BYTES;        // 64 KB
 constexpr int kNumHeadFloats = 9 * 256 + 256 + 3 * 128 + 4;   // biases L0..L8, w_alpha, W_rgb, b_alpha, b_rgb[3]
@@ -42,8 +52,8 @@ struct __align__(1024) Smem {
     uint8_t w[kStages][kStageBytes];
     float heads[kNumHeadFloats + 4];
     float4 part[DANBO_TILE_M];          // second column slice's partial (rgb, sigma) of every row
-    uint64_t w_full[kStages];
-    uint64_t w_empty[kStages];
+    uint64_t w_full[2 * kStages];       // kStages slots of 16 KB, or (CTA pair) 2 * kStages slots of 8 KB
+    uint64_t w_empty[2 * kStages];
     uint64_t x_full, x_empty;
     uint64_t acc_full[2];
     uint64_t act_ready[2];
@@ -57,8 +67,131 @@ using namespace danbo::tc;
 __device__ __forceinline__ int n_halves(int L) { return L == 9 ? 1 : 2; }
 __device__ __forceinline__ bool uses_x(int L) { return L == 0 || L == 5; }
 __device__ __forceinline__ bool uses_act(int L) { return L != 0; }
+// position of chunk c of (layer L, half h) in the per-tile stage stream (see stage_to_layer below)
+__host__ __device__ constexpr int stage_index(int L, int h, int c) {
+    return (L <= 5 ? 8 * L : 8 * L + 8) + h * (L == 5 ? 8 : 4) + c;
+}
 
-template <bool kFull>
+// ---- epilogue bodies ---------------------------------------------------------------------------------------
+// One call = one thread's 64-column slice of one accumulator half.  The layer kind is a template parameter and all
+// operands that do not depend on the accumulator (bias, per-ray bias) are fetched BEFORE the wait on the MMA, so the
+// code between the TMEM load and the TMEM store is branch-free register arithmetic (a runtime `L ==` test inside
+// the unrolled loops cost 1 500 clk per half in exposed LDS latency and branches; measured).
+struct EpiCtx {
+    int q, ch, lane;
+    uint32_t tmem_lane, acc, act_out, phase;
+    uint64_t* acc_bar;
+    uint32_t done_addr;    // act_ready barrier: shared::cta address, or the leader CTA's shared::cluster address
+    bool remote;
+    long long* tslot;      // profiling aid (null when not tracing)
+    long long* dslot;
+};
+
+__device__ __forceinline__ void epi_finish(const EpiCtx& E) {
+    if (E.dslot) E.dslot[1] = clock64();
+    tmem_wait_st();
+    tc_fence_before();
+    __syncwarp();
+    if (E.lane == 0) {
+        if (E.remote) mbar_arrive_cluster(E.done_addr);
+        else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(E.done_addr) : "memory");
+    }
+    if (E.tslot) E.tslot[1] = clock64();
+}
+
+// kKind 0: relu hidden layer; 1: relu + sigma head (pts_linears.7); 2: linear (feature_linear)
+template <int kKind>
+__device__ __forceinline__ void epi_hidden(const EpiCtx& E, const float* __restrict__ bias, const float* __restrict__ w_alpha,
+                                           float& alpha, bool write_act, __nv_bfloat16* __restrict__ save_row) {
+    float4 b[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) b[i] = reinterpret_cast<const float4*>(bias)[i];
+    mbar_wait(E.acc_bar, E.phase);
+    tc_fence_after();
+    if (E.tslot) E.tslot[0] = clock64();
+    uint32_t v[2][32];
+    tmem_ld32(E.acc, v[0]);
+    tmem_ld32(E.acc + 32, v[1]);
+    tmem_wait_ld();
+    if (E.dslot) E.dslot[0] = clock64();
+    uint32_t pk[2][16];
+    float part[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 bb = b[g * 8 + i];
+            float a0 = __uint_as_float(v[g][4 * i + 0]) + bb.x;
+            float a1 = __uint_as_float(v[g][4 * i + 1]) + bb.y;
+            float a2 = __uint_as_float(v[g][4 * i + 2]) + bb.z;
+            float a3 = __uint_as_float(v[g][4 * i + 3]) + bb.w;
+            if (kKind == 1) {
+                const float4 wa = reinterpret_cast<const float4*>(w_alpha)[g * 8 + i];
+                part[0] = fmaf(fmaxf(a0, 0.f), wa.x, part[0]); part[1] = fmaf(fmaxf(a1, 0.f), wa.y, part[1]);
+                part[2] = fmaf(fmaxf(a2, 0.f), wa.z, part[2]); part[3] = fmaf(fmaxf(a3, 0.f), wa.w, part[3]);
+            }
+            if (kKind != 2) { pk[g][2 * i] = pack_bf16_relu(a0, a1); pk[g][2 * i + 1] = pack_bf16_relu(a2, a3); }
+            else            { pk[g][2 * i] = pack_bf16(a0, a1);      pk[g][2 * i + 1] = pack_bf16(a2, a3); }
+        }
+    }
+    if (kKind == 1) alpha += (part[0] + part[1]) + (part[2] + part[3]);
+    if (write_act) { tmem_st16(E.act_out, pk[0]); tmem_st16(E.act_out + 16, pk[1]); }
+    if (save_row != nullptr) {                           // saved for the backward pass (bf16, row-major)
+        uint4* dst = reinterpret_cast<uint4*>(save_row);
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[g * 4 + i] = make_uint4(pk[g][4 * i], pk[g][4 * i + 1], pk[g][4 * i + 2], pk[g][4 * i + 3]);
+    }
+    epi_finish(E);
+}
+
+// views_linears.0 (feature part from the MMA + per-ray part) -> relu -> rgb head
+__device__ __forceinline__ void epi_view(const EpiCtx& E, const float* __restrict__ ray_bias, int bias_off,
+                                         const float* __restrict__ w_rgb, float (&rgb)[3], __nv_bfloat16* __restrict__ gsave_row) {
+    float4 b[16];
+    const float4* rb4 = reinterpret_cast<const float4*>(ray_bias + bias_off);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) b[i] = __ldg(rb4 + i);
+    mbar_wait(E.acc_bar, E.phase);
+    tc_fence_after();
+    if (E.tslot) E.tslot[0] = clock64();
+    uint32_t v[2][32];
+    tmem_ld32(E.acc, v[0]);
+    tmem_ld32(E.acc + 32, v[1]);
+    tmem_wait_ld();
+    if (E.dslot) E.dslot[0] = clock64();
+    float part[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 bb = b[g * 8 + i];
+            const float a0 = fmaxf(__uint_as_float(v[g][4 * i + 0]) + bb.x, 0.f);
+            const float a1 = fmaxf(__uint_as_float(v[g][4 * i + 1]) + bb.y, 0.f);
+            const float a2 = fmaxf(__uint_as_float(v[g][4 * i + 2]) + bb.z, 0.f);
+            const float a3 = fmaxf(__uint_as_float(v[g][4 * i + 3]) + bb.w, 0.f);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float4 w = reinterpret_cast<const float4*>(w_rgb + k * 128)[g * 8 + i];
+                part[k][0] = fmaf(a0, w.x, part[k][0]); part[k][1] = fmaf(a1, w.y, part[k][1]);
+                part[k][0] = fmaf(a2, w.z, part[k][0]); part[k][1] = fmaf(a3, w.w, part[k][1]);
+            }
+            if (gsave_row != nullptr)
+                reinterpret_cast<uint2*>(gsave_row)[g * 8 + i] = make_uint2(pack_bf16(a0, a1), pack_bf16(a2, a3));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) rgb[k] += part[k][0] + part[k][1];
+    epi_finish(E);
+}
+
+// kPair: the two CTAs of a cluster (one TPC) run every MMA as cta_group::2 over a PAIR of row tiles: M = 256 (128 rows
+// from each CTA's X / TMEM) and each CTA stages only HALF of every weight stage (64 of the 128 B rows, 8 KB), which
+// halves the L2 -> SM weight traffic that bounds the single-CTA kernel.  CTA rank 0 issues all MMAs; its commits
+// arrive on the barriers of both CTAs (multicast); the peer CTA forwards "my half landed" / "my activations are in
+// TMEM" to the leader's barriers with cluster-scope arrives.
+template <bool kFull, bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_kernel(const uint8_t* __restrict__ xtiles,       // [tiles][64 KB] swizzled bf16 X tiles
            const uint8_t* __restrict__ wstream,      // [84|72][16 KB] packed weight stages
@@ -79,202 +212,227 @@ mlp_kernel(const uint8_t* __restrict__ xtiles,       // [tiles][64 KB] swizzled 
     const int n_rows = *n_rows_ptr;
     const int n_tiles = (n_rows + DANBO_TILE_M - 1) / DANBO_TILE_M;
     constexpr int kLayers = kFull ? 10 : 8;
+    constexpr int kSlots = ring_slots(kFull, kPair);                    // ring slots (16 KB each)
+    constexpr int kGroup = stages_per_slot(kPair);                      // stages per slot
+    constexpr int kGroupsPerTile = stages_per_tile(kFull) / kGroup;
+    static_assert(kGroupsPerTile % (2 * kSlots) == 0, "slot parity must repeat every tile");
+    static_assert(kSlots <= kStages, "ring exceeds its shared memory");
+    constexpr uint32_t kSlotBytes = kStageBytes;
+    constexpr uint32_t kHalfStage = kStageBytes / 2;                     // one CTA's 64 B-rows of a stage (pair mode)
+    const uint32_t rank = kPair ? cluster_ctarank() : 0u;                // CTA rank inside the pair
+    const bool lead_cta = rank == 0;
+    const int unit = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // persistent worker (CTA or CTA pair)
+    const int n_units = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int n_work = kPair ? (n_tiles + 1) / 2 : n_tiles;              // row tiles or pairs of row tiles
 
     for (int i = threadIdx.x; i < kNumHeadFloats; i += kThreads) S.heads[i] = heads[i];
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&S.w_full[s], 1); mbar_init(&S.w_empty[s], 1); }
-        mbar_init(&S.x_full, 1); mbar_init(&S.x_empty, 1);
+        const uint32_t n_prod = (kPair && lead_cta) ? 2u : 1u;            // own expect_tx + the peer's forwarded arrive
+        for (int s = 0; s < kSlots; ++s) { mbar_init(&S.w_full[s], n_prod); mbar_init(&S.w_empty[s], 1); }
+        mbar_init(&S.x_full, n_prod); mbar_init(&S.x_empty, 1);
         mbar_init(&S.acc_full[0], 1); mbar_init(&S.acc_full[1], 1);
-        mbar_init(&S.act_ready[0], 8); mbar_init(&S.act_ready[1], 8);
+        mbar_init(&S.act_ready[0], kPair ? 16 : 8); mbar_init(&S.act_ready[1], kPair ? 16 : 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (kPair) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (kPair) cluster_sync_all();                   // both CTAs' barriers initialised before any remote arrive / multicast commit
     tc_fence_after();
     const uint32_t tmem = S.tmem_base;
     const bool tr = (trace != nullptr) && blockIdx.x == 0;
     // trace layout: [tile_iter < 4][role: 0 = mma, 1 = epilogue][(L*2+h)][begin, end]
 #define DANBO_TRACE(it, role, L, h, which) do { if (tr && (it) < 4) trace[(((it) * 2 + (role)) * 20 + (L) * 2 + (h)) * 2 + (which)] = clock64(); } while (0)
+    // extra epilogue detail after the first 320 entries: [tile_iter < 4][(L*2+h)][tmem loads landed, stores issued]
 
     if (warp == 0) {
-        // ===== producer: X tile + weight stages (one elected lane issues, the warp stays converged) =====
+        // ===== producer: X tile + (this CTA's share of the) weight stages; one elected lane issues =====
         const bool leader = elect_one();
         uint32_t ws = 0, wphase = 0, xphase = 0;
-        for (int t = blockIdx.x, it = 0; t < n_tiles; t += gridDim.x, ++it) {
+        for (int w = unit, it = 0; w < n_work; w += n_units, ++it) {
+            int t = kPair ? 2 * w + (int)rank : w;
+            if (t >= n_tiles) t = n_tiles - 1;                           // odd tail of a pair: a dummy tile (rows all invalid)
             if (it > 0) { mbar_wait(&S.x_empty, xphase); xphase ^= 1; }
             const uint8_t* xs = xtiles + (size_t)t * kXBytes;
             if (leader) {
                 mbar_expect_tx(&S.x_full, kXBytes);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) bulk_g2s(S.x + c * 16384, xs + c * 16384, 16384, &S.x_full);
+                bulk_g2s(S.x, xs, kXBytes, &S.x_full);
             }
-            for (int s = 0; s < stages_per_tile(kFull); ++s) {
+            // pair mode reads the second copy of the stream: [group][rank][2 stages x 8 KB]
+            const uint8_t* wsrc = kPair ? wstream + (size_t)84 * kStageBytes + rank * kSlotBytes : wstream;
+            for (int g = 0; g < kGroupsPerTile; ++g) {
                 mbar_wait(&S.w_empty[ws], wphase ^ 1);
                 if (leader) {
-                    mbar_expect_tx(&S.w_full[ws], kStageBytes);
-                    bulk_g2s(S.w[ws], wstream + (size_t)s * kStageBytes, kStageBytes, &S.w_full[ws]);
+                    mbar_expect_tx(&S.w_full[ws], kSlotBytes);
+                    bulk_g2s(&S.w[0][0] + ws * kSlotBytes, wsrc + (size_t)g * (kPair ? 2 * kSlotBytes : kSlotBytes), kSlotBytes, &S.w_full[ws]);
                 }
-                if (++ws == kStages) { ws = 0; wphase ^= 1; }
+                if (++ws == kSlots) { ws = 0; wphase ^= 1; }
+            }
+        }
+    } else if (warp == 1 && kPair && !lead_cta) {
+        // ===== peer CTA: forward "my X tile / my half of the stage has landed" to the leader's barriers =====
+        uint32_t ws = 0, wphase = 0, xphase = 0;
+        const uint32_t x_full_lead = mapa_cluster(smem_u32(&S.x_full), 0);
+        const uint32_t w_full_lead = mapa_cluster(smem_u32(&S.w_full[0]), 0);
+        for (int w = unit; w < n_work; w += n_units) {
+            mbar_wait(&S.x_full, xphase); xphase ^= 1;
+            if (lane == 0) mbar_arrive_cluster(x_full_lead);
+            for (int g = 0; g < kGroupsPerTile; ++g) {
+                mbar_wait(&S.w_full[ws], wphase);
+                if (lane == 0) mbar_arrive_cluster(w_full_lead + 8u * ws);
+                __syncwarp();
+                if (++ws == kSlots) { ws = 0; wphase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer: the whole warp runs the (uniform) schedule, one elected lane issues tcgen05 =====
-        // Keeping the control flow warp-uniform lets descriptors and TMEM addresses live in uniform registers; a
-        // lane-0-only loop costs ~230 clk per MMA in R2UR waterfalls (measured), 3.6x the MMA itself.
+        // The schedule of one tile is fully unrolled: ring slot, barrier parity, descriptor offsets and TMEM columns
+        // of every stage are compile-time constants added to uniform bases.
         const bool leader = elect_one();
-        uint32_t ws = 0, wphase = 0, xphase = 0, r0 = 0, r1 = 0;
         const uint32_t x_base = smem_u32(S.x);
+        const uint32_t w_base = smem_u32(&S.w[0][0]);
         const uint64_t desc_hi = make_desc(0);
-        for (int t = blockIdx.x, it = 0; t < n_tiles; t += gridDim.x, ++it) {
-            mbar_wait(&S.x_full, xphase); xphase ^= 1;
+        const uint64_t x_desc0 = desc_hi | (uint64_t)((x_base >> 4) & 0x3FFF);
+        const uint64_t w_desc0 = desc_hi | (uint64_t)((w_base >> 4) & 0x3FFF);
+        constexpr uint32_t idesc = kPair ? kIdescPair : kIdesc;
+        // plain (acquire.cta) waits also on the barriers the peer CTA arrives on, as CUTLASS's ClusterBarrier does: what
+        // they order is TMEM / async-proxy state, and an acquire.cluster wait adds an L1 invalidate (CCTL.IVALL) per wait
+        auto wait_in = [](uint64_t* b, uint32_t ph) { mbar_wait(b, ph); };
+        auto commit = [](uint64_t* b) { if (kPair) tc_commit_pair(b); else tc_commit(b); };
+        // act_ready[1] completes 9 times per full tile (odd): its parity also depends on the tile iteration
+        constexpr int kReady1PerTile = kFull ? 9 : 8;
+        for (int w = unit, it = 0; w < n_work; w += n_units, ++it) {
+            wait_in(&S.x_full, it & 1);
+            const uint32_t r1_base = (uint32_t)(kReady1PerTile * it);
             if (it > 0) {                                                   // accumulators drained by the last epilogues
-                mbar_wait(&S.act_ready[0], r0 & 1); ++r0;
-                if (!kFull) { mbar_wait(&S.act_ready[1], r1 & 1); ++r1; }    // density-only ends on a two-half layer
+                wait_in(&S.act_ready[0], 1);                                //   completion #(kLayers-1) of the previous tile
+                if (!kFull) wait_in(&S.act_ready[1], (r1_base - 1) & 1);    // density-only ends on a two-half layer
             }
             tc_fence_after();
+#pragma unroll
             for (int L = 0; L < kLayers; ++L) {
-                if (L > 0) { mbar_wait(&S.act_ready[0], r0 & 1); ++r0; tc_fence_after(); }
-                bool got_r1 = (L == 0);
+                if (L > 0) { wait_in(&S.act_ready[0], (L - 1) & 1); tc_fence_after(); }
                 const uint32_t act_in = tmem + kActCol + 128u * ((L - 1) & 1);
-                for (int h = 0; h < n_halves(L); ++h) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (h >= n_halves(L)) continue;
                     const uint32_t d = tmem + kAccCol + 128u * h;
                     const int n_xc = uses_x(L) ? 4 : 0;
                     const int n_chunks = n_xc + (uses_act(L) ? 4 : 0);
-                    for (int c = 0; c < n_chunks; ++c) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        if (c >= n_chunks) continue;
                         const bool is_x = c < n_xc;
                         const int kc = is_x ? c : c - n_xc;
-                        if (!is_x && kc == 2 && !got_r1) {
-                            mbar_wait(&S.act_ready[1], r1 & 1); ++r1; got_r1 = true;
-                        }
-                        mbar_wait(&S.w_full[ws], wphase);
+                        const int s = stage_index(L, h, c);                 // position in the tile's stage stream
+                        const int g = s / kGroup;                           // ring slot use this stage belongs to
+                        const int slot = g % kSlots;
+                        const uint32_t par = (uint32_t)((g / kSlots) & 1);
+                        if (!is_x && kc == 2 && h == 0 && L > 0)            // K columns 128.. come from the other half's epilogue
+                            wait_in(&S.act_ready[1], (r1_base + (uint32_t)(L - 1)) & 1);
+                        if (s % kGroup == 0) wait_in(&S.w_full[slot], par);
                         tc_fence_after();
                         if (c == 0) { DANBO_TRACE(it, 0, L, h, 0); }
-                        const uint64_t bdesc = desc_hi | (uint64_t)((smem_u32(S.w[ws]) >> 4) & 0x3FFF);
+                        const uint64_t bdesc = w_desc0 + (uint64_t)((slot * kSlotBytes + (s % kGroup) * kHalfStage) >> 4);
                         const uint32_t acc0 = c > 0 ? 1u : 0u;
-                        if (is_x) {
-                            const uint64_t adesc = desc_hi | (uint64_t)(((x_base + kc * 16384) >> 4) & 0x3FFF);
-                            if (leader) {
-                                mma_ss(d, adesc, bdesc, kIdesc, acc0);
-                                if (kc < 3) {                                   // K = 208: the last X chunk holds one k-step
-                                    mma_ss(d, adesc + 2, bdesc + 2, kIdesc, 1u);
-                                    mma_ss(d, adesc + 4, bdesc + 4, kIdesc, 1u);
-                                    mma_ss(d, adesc + 6, bdesc + 6, kIdesc, 1u);
+                        if (leader) {
+                            if (is_x) {
+                                const uint64_t adesc = x_desc0 + (uint64_t)((kc * 16384) >> 4);
+                                if (kPair) {
+                                    mma_ss_pair(d, adesc, bdesc, idesc, acc0);
+                                    if (kc < 3) {                               // K = 208: the last X chunk holds one k-step
+                                        mma_ss_pair(d, adesc + 2, bdesc + 2, idesc, 1u);
+                                        mma_ss_pair(d, adesc + 4, bdesc + 4, idesc, 1u);
+                                        mma_ss_pair(d, adesc + 6, bdesc + 6, idesc, 1u);
+                                    }
+                                } else {
+                                    mma_ss(d, adesc, bdesc, idesc, acc0);
+                                    if (kc < 3) {
+                                        mma_ss(d, adesc + 2, bdesc + 2, idesc, 1u);
+                                        mma_ss(d, adesc + 4, bdesc + 4, idesc, 1u);
+                                        mma_ss(d, adesc + 6, bdesc + 6, idesc, 1u);
+                                    }
+                                }
+                            } else {
+                                const uint32_t a_t = act_in + kc * 32;
+                                if (kPair) {
+                                    mma_ts_pair(d, a_t, bdesc, idesc, acc0);
+                                    mma_ts_pair(d, a_t + 8, bdesc + 2, idesc, 1u);
+                                    mma_ts_pair(d, a_t + 16, bdesc + 4, idesc, 1u);
+                                    mma_ts_pair(d, a_t + 24, bdesc + 6, idesc, 1u);
+                                } else {
+                                    mma_ts(d, a_t, bdesc, idesc, acc0);
+                                    mma_ts(d, a_t + 8, bdesc + 2, idesc, 1u);
+                                    mma_ts(d, a_t + 16, bdesc + 4, idesc, 1u);
+                                    mma_ts(d, a_t + 24, bdesc + 6, idesc, 1u);
                                 }
                             }
-                        } else {
-                            const uint32_t a_t = act_in + kc * 32;
-                            if (leader) {
-                                mma_ts(d, a_t, bdesc, kIdesc, acc0);
-                                mma_ts(d, a_t + 8, bdesc + 2, kIdesc, 1u);
-                                mma_ts(d, a_t + 16, bdesc + 4, kIdesc, 1u);
-                                mma_ts(d, a_t + 24, bdesc + 6, kIdesc, 1u);
-                            }
-                        }
-                        if (leader) {
-                            tc_commit(&S.w_empty[ws]);
-                            if (L == 5 && h == 1 && is_x && kc == 3) tc_commit(&S.x_empty);   // X no longer needed
+                            if (s % kGroup == kGroup - 1) commit(&S.w_empty[slot]);
+                            if (L == 5 && h == 1 && is_x && kc == 3) commit(&S.x_empty);   // X no longer needed
+                            if (c == n_chunks - 1) commit(&S.acc_full[h]);
                         }
                         __syncwarp();
-                        if (++ws == kStages) { ws = 0; wphase ^= 1; }
                     }
-                    if (leader) tc_commit(&S.acc_full[h]);
-                    __syncwarp();
                     DANBO_TRACE(it, 0, L, h, 1);
                 }
             }
         }
     } else {
         // ===== epilogue warps 2..9: two warps per TMEM lane quarter, each owns 64 of the 128 columns of a half =====
-        const int q = warp & 3;                       // TMEM lane quarter this warp may access
-        const int ch = (warp - 2) >> 2;               // which 64-column slice of every half
+        EpiCtx E;
+        E.q = warp & 3;                               // TMEM lane quarter this warp may access
+        E.ch = (warp - 2) >> 2;                       // which 64-column slice of every half
+        const int q = E.q, ch = E.ch;
         const int row = q * 32 + lane;
-        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        E.tmem_lane = tmem + ((uint32_t)(q * 32) << 16);
+        E.lane = lane;
+        E.remote = kPair;
+        const uint32_t ready_addr[2] = {kPair ? mapa_cluster(smem_u32(&S.act_ready[0]), 0) : smem_u32(&S.act_ready[0]),
+                                        kPair ? mapa_cluster(smem_u32(&S.act_ready[1]), 0) : smem_u32(&S.act_ready[1])};
         const float* bias = S.heads;                  // [9][256]
         const float* w_alpha = S.heads + 9 * 256;     // [256]
         const float* w_rgb = w_alpha + 256;           // [3][128]
         const float* tail = w_rgb + 3 * 128;          // b_alpha, b_rgb[3]
         uint32_t f0 = 0, f1 = 0;
-        for (int t = blockIdx.x, it = 0; t < n_tiles; t += gridDim.x, ++it) {
+        for (int w = unit, it = 0; w < n_work; w += n_units, ++it) {
+            const int t = kPair ? 2 * w + (int)rank : w;
             const int grow = t * DANBO_TILE_M + row;
-            const bool valid = grow < n_rows;
+            const bool valid = grow < n_rows;                 // (a dummy tile of an odd tail has no valid row)
             const int sample = valid ? row_sample[grow] : -1;
             const int ray = (kFull && valid) ? row_ray[grow] : 0;
             float alpha = ch == 0 ? tail[0] : 0.f;
             float rgb[3] = {ch == 0 ? tail[1] : 0.f, ch == 0 ? tail[2] : 0.f, ch == 0 ? tail[3] : 0.f};
+            const bool save = act_save != nullptr && valid;
             for (int L = 0; L < kLayers; ++L) {
                 for (int h = 0; h < n_halves(L); ++h) {
-                    if (h == 0) { mbar_wait(&S.acc_full[0], f0 & 1); ++f0; }
-                    else        { mbar_wait(&S.acc_full[1], f1 & 1); ++f1; }
-                    tc_fence_after();
-                    if (warp == 2 && lane == 0) DANBO_TRACE(it, 1, L, h, 0);
-                    const uint32_t acc = tmem + lane_addr + kAccCol + 128u * h + 64u * ch;
-                    const uint32_t act_out = tmem + lane_addr + kActCol + 128u * (L & 1) + 64u * h + 32u * ch;
-                    uint32_t v[2][32];
-                    tmem_ld32(acc, v[0]);
-                    tmem_ld32(acc + 32, v[1]);
-                    tmem_wait_ld();
                     const int col0 = h * 128 + ch * 64;            // first output column of this thread's slice
-                    if (L < 9) {
-#pragma unroll
-                        for (int g = 0; g < 2; ++g) {
-                            const float4* b4 = reinterpret_cast<const float4*>(bias + L * 256 + col0 + 32 * g);
-                            uint32_t pk[16];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const float4 b = b4[i];
-                                float a0 = __uint_as_float(v[g][4 * i + 0]) + b.x;
-                                float a1 = __uint_as_float(v[g][4 * i + 1]) + b.y;
-                                float a2 = __uint_as_float(v[g][4 * i + 2]) + b.z;
-                                float a3 = __uint_as_float(v[g][4 * i + 3]) + b.w;
-                                if (L == 7) {
-                                    a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f);
-                                    const float4 wa = *reinterpret_cast<const float4*>(w_alpha + col0 + 32 * g + 4 * i);
-                                    alpha = fmaf(a0, wa.x, alpha); alpha = fmaf(a1, wa.y, alpha);
-                                    alpha = fmaf(a2, wa.z, alpha); alpha = fmaf(a3, wa.w, alpha);
-                                }
-                                if (L < 8) { pk[2 * i] = pack_bf16_relu(a0, a1); pk[2 * i + 1] = pack_bf16_relu(a2, a3); }
-                                else       { pk[2 * i] = pack_bf16(a0, a1);      pk[2 * i + 1] = pack_bf16(a2, a3); }
-                            }
-                            if (kFull || L < 7) tmem_st16(act_out + 16 * g, pk);
-                            if (act_save != nullptr && valid) {          // saved for the backward pass (bf16, row-major)
-                                uint4* dst = reinterpret_cast<uint4*>(act_save + ((size_t)L * save_cap + grow) * 256 + col0 + 32 * g);
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-                            }
-                        }
+                    long long* tslot = (tr && it < 4 && warp == 2 && lane == 0) ? trace + (((it * 2 + 1) * 20 + L * 2 + h) * 2) : nullptr;
+                    long long* dslot = tslot ? trace + 320 + ((it * 20 + L * 2 + h) * 2) : nullptr;
+                    E.acc = E.tmem_lane + kAccCol + 128u * h + 64u * ch;
+                    E.act_out = E.tmem_lane + kActCol + 128u * (L & 1) + 64u * h + 32u * ch;
+                    E.acc_bar = &S.acc_full[h];
+                    if (h == 0) { E.phase = f0 & 1; ++f0; } else { E.phase = f1 & 1; ++f1; }
+                    E.done_addr = ready_addr[h];
+                    E.tslot = tslot; E.dslot = dslot;
+                    __nv_bfloat16* srow = save ? act_save + ((size_t)L * save_cap + grow) * 256 + col0 : nullptr;
+                    if (L < 7) {
+                        epi_hidden<0>(E, bias + L * 256 + col0, nullptr, alpha, true, srow);
+                    } else if (L == 7) {
+                        epi_hidden<1>(E, bias + L * 256 + col0, w_alpha + col0, alpha, kFull, srow);
+                    } else if (L == 8) {
+                        epi_hidden<2>(E, bias + L * 256 + col0, nullptr, alpha, true, srow);
                     } else {
-#pragma unroll
-                        for (int g = 0; g < 2; ++g) {
-                            const float4* b4 = reinterpret_cast<const float4*>(ray_bias + (size_t)ray * 128 + col0 + 32 * g);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const float4 b = __ldg(b4 + i);
-                                const float a[4] = {fmaxf(__uint_as_float(v[g][4 * i + 0]) + b.x, 0.f),
-                                                    fmaxf(__uint_as_float(v[g][4 * i + 1]) + b.y, 0.f),
-                                                    fmaxf(__uint_as_float(v[g][4 * i + 2]) + b.z, 0.f),
-                                                    fmaxf(__uint_as_float(v[g][4 * i + 3]) + b.w, 0.f)};
-#pragma unroll
-                                for (int k = 0; k < 3; ++k) {
-                                    const float4 w = *reinterpret_cast<const float4*>(w_rgb + k * 128 + col0 + 32 * g + 4 * i);
-                                    rgb[k] = fmaf(a[0], w.x, rgb[k]); rgb[k] = fmaf(a[1], w.y, rgb[k]);
-                                    rgb[k] = fmaf(a[2], w.z, rgb[k]); rgb[k] = fmaf(a[3], w.w, rgb[k]);
-                                }
-                                if (g_save != nullptr && valid) {
-                                    uint2* dst = reinterpret_cast<uint2*>(g_save + (size_t)grow * 128 + col0 + 32 * g + 4 * i);
-                                    *dst = make_uint2(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]));
-                                }
-                            }
-                        }
+                        epi_view(E, ray_bias, ray * 128 + col0, w_rgb + col0, rgb,
+                                 (g_save != nullptr && valid) ? g_save + (size_t)grow * 128 + col0 : nullptr);
                     }
-                    tmem_wait_st();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&S.act_ready[h]);
-                    if (warp == 2 && lane == 0) DANBO_TRACE(it, 1, L, h, 1);
                 }
             }
             // combine the two column slices of every row and write the row's output
@@ -291,8 +449,10 @@ mlp_kernel(const uint8_t* __restrict__ xtiles,       // [tiles][64 KB] swizzled 
 
     tc_fence_before();
     __syncthreads();
+    if (kPair) cluster_sync_all();                   // the peer's TMEM / barriers stay alive until both CTAs are done
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+        if (kPair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+        else       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
     }
 }
 
@@ -350,7 +510,11 @@ __global__ void pack_weights_kernel(PackArgs a, __nv_bfloat16* __restrict__ wstr
             val = a.w_view[(size_t)out_row * 411 + kin];          // out_row < 128 because h == 0
         }
         const uint32_t off = sw128_offset((uint32_t)n, (uint32_t)k);     // chunk index is 0 for k < 64
-        wstream[(size_t)s * (128 * 64) + off / 2] = __float2bfloat16_rn(val);
+        const __nv_bfloat16 bv = __float2bfloat16_rn(val);
+        wstream[(size_t)s * (128 * 64) + off / 2] = bv;
+        // second copy for CTA pairs: [group of 2 stages][rank = n / 64][stage in group][64 rows x 64 k] (8 KB pieces)
+        const uint32_t half_off = off & 8191u;                           // rows 64..127 start at byte 8192 of a stage
+        wstream[(size_t)84 * (128 * 64) + (((size_t)(s >> 1) * 2 + (n >> 6)) * 2 + (s & 1)) * (64 * 64) + half_off / 2] = bv;
     }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kNumHeadFloats; i += gridDim.x * blockDim.x) {
         float v;
@@ -370,7 +534,7 @@ __global__ void pack_weights_kernel(PackArgs a, __nv_bfloat16* __restrict__ wstr
 using namespace danbo;
 
 extern "C" int danbo_mlp_workspace_bytes(long long* wstream_bytes, long long* heads_bytes, long long* raybias_bytes) {
-    *wstream_bytes = 84LL * mlp::kStageBytes;
+    *wstream_bytes = 2 * 84LL * mlp::kStageBytes;        // single-CTA order, then the CTA-pair order
     *heads_bytes = (long long)mlp::kNumHeadFloats * 4;
     *raybias_bytes = (long long)mlp::kRayBiasFloats * 4;
     return 0;
@@ -389,38 +553,63 @@ extern "C" int danbo_pack_mlp_weights(const float* const* w_pts, const float* co
     return 0;
 }
 
+static int g_cta_pair = 1;        // 1: cta_group::2 kernel over CTA pairs (default), 0: one CTA per row tile
+
+extern "C" int danbo_mlp_set_cta_pair(int enable) {
+    const int old = g_cta_pair;
+    g_cta_pair = enable ? 1 : 0;
+    return old;
+}
+
+template <bool kFull, bool kPair>
+static int mlp_launch_variant(int grid, int smem, cudaStream_t stream, const uint8_t* xtiles, const uint8_t* wstream,
+                              const float* heads, const float* ray_bias, const int* row_sample, const int* row_ray,
+                              const int* n_rows_dev, float* out, int out_capacity, __nv_bfloat16* act_save,
+                              __nv_bfloat16* g_save, int save_cap, long long* trace) {
+    static bool attr_set = false;             // idempotent launch attribute, set on first use per variant
+    auto kern = mlp::mlp_kernel<kFull, kPair>;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(mlp::kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kPair ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, xtiles, wstream, heads, ray_bias, row_sample, row_ray, n_rows_dev, out,
+                                       out_capacity, act_save, g_save, save_cap, trace);
+    if (e != cudaSuccess) return (int)e;
+    DANBO_CHECK_LAUNCH();
+    return 0;
+}
+
 static int mlp_launch(const void* xtiles, const void* wstream, const float* heads, const float* ray_bias,
                       const int* row_sample, const int* row_ray, const int* n_rows_dev, int max_rows,
                       float* out, int out_capacity, int density_only, int num_sms, void* act_save, void* g_save,
                       int save_cap, long long* trace, void* stream) {
     if (max_rows <= 0) return 0;
     const int smem = (int)sizeof(mlp::Smem) + 1024;
-    int max_tiles = (max_rows + DANBO_TILE_M - 1) / DANBO_TILE_M;
-    int grid = num_sms < max_tiles ? num_sms : max_tiles;
-    if (grid < 1) grid = 1;
-    cudaError_t e;
-    static bool attr_set[2] = {false, false};           // idempotent launch attribute, set on first use per variant
-    if (density_only) {
-        if (!attr_set[0]) {
-            e = cudaFuncSetAttribute(mlp::mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            if (e != cudaSuccess) return (int)e;
-            attr_set[0] = true;
-        }
-        mlp::mlp_kernel<false><<<grid, mlp::kThreads, smem, (cudaStream_t)stream>>>(
-            (const uint8_t*)xtiles, (const uint8_t*)wstream, heads, ray_bias, row_sample, row_ray, n_rows_dev, out, out_capacity,
-            (__nv_bfloat16*)act_save, (__nv_bfloat16*)g_save, save_cap, trace);
+    const int max_tiles = (max_rows + DANBO_TILE_M - 1) / DANBO_TILE_M;
+    const bool pair = g_cta_pair != 0 && num_sms >= 2;
+    int grid;
+    if (pair) {
+        const int max_pairs = (max_tiles + 1) / 2, sm_pairs = num_sms / 2;
+        grid = 2 * (sm_pairs < max_pairs ? sm_pairs : max_pairs);
     } else {
-        if (!attr_set[1]) {
-            e = cudaFuncSetAttribute(mlp::mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            if (e != cudaSuccess) return (int)e;
-            attr_set[1] = true;
-        }
-        mlp::mlp_kernel<true><<<grid, mlp::kThreads, smem, (cudaStream_t)stream>>>(
-            (const uint8_t*)xtiles, (const uint8_t*)wstream, heads, ray_bias, row_sample, row_ray, n_rows_dev, out, out_capacity,
-            (__nv_bfloat16*)act_save, (__nv_bfloat16*)g_save, save_cap, trace);
+        grid = num_sms < max_tiles ? num_sms : max_tiles;
     }
-    DANBO_CHECK_LAUNCH();
-    return 0;
+    if (grid < 1) grid = 1;
+#define DANBO_MLP_ARGS grid, smem, (cudaStream_t)stream, (const uint8_t*)xtiles, (const uint8_t*)wstream, heads, ray_bias, \
+                       row_sample, row_ray, n_rows_dev, out, out_capacity, (__nv_bfloat16*)act_save, (__nv_bfloat16*)g_save, save_cap, trace
+    if (density_only) return pair ? mlp_launch_variant<false, true>(DANBO_MLP_ARGS) : mlp_launch_variant<false, false>(DANBO_MLP_ARGS);
+    return pair ? mlp_launch_variant<true, true>(DANBO_MLP_ARGS) : mlp_launch_variant<true, false>(DANBO_MLP_ARGS);
+#undef DANBO_MLP_ARGS
 }
 
 extern "C" int danbo_mlp_forward(const void* xtiles, const void* wstream, const float* heads, const float* ray_bias,
@@ -442,7 +631,7 @@ extern "C" int danbo_mlp_forward_save(const void* xtiles, const void* wstream, c
                       num_sms, act_save, g_save, save_cap, nullptr, stream);
 }
 
-// Same launch, and CTA 0 writes a clock64 timeline of its first 4 tiles into trace[4*2*20*2] (profiling aid).
+// Same launch, and CTA 0 writes a clock64 timeline of its first 4 tiles into trace[480] (profiling aid).
 extern "C" int danbo_mlp_forward_trace(const void* xtiles, const void* wstream, const float* heads, const float* ray_bias,
                                        const int* row_sample, const int* row_ray, const int* n_rows_dev, int max_rows,
                                        float* out, int out_capacity, int density_only, int num_sms, long long* trace,

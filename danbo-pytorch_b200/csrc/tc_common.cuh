@@ -25,6 +25,55 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(addr), "r"(parity) : "memory");
 }
+// ---- CTA-pair (cta_group::2) helpers: cluster-scope barrier traffic between the two CTAs of a pair ---------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// shared::cluster address of `smem_addr` (a shared::cta address valid in every CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    // default (.release.cta) semantics, as CUTLASS's umma_arrive_2x1SM_sm0: an explicit .release.cluster costs ~1 000 clk
+    // per arrive (measured), and what is being published is TMEM / async-proxy state ordered by tcgen05 fences.
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait on a local barrier that CTAs of the whole cluster arrive on
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* b, uint32_t parity) {
+    uint32_t addr = smem_u32(b);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(addr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// commit of cta_group::2 MMAs: arrives on the barrier at this offset in both CTAs of the pair
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// cta_group::2 MMA (M = 256 over the pair: 128 rows and half of B's N rows from each CTA); leader CTA issues
+__device__ __forceinline__ void mma_ss_pair(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void mma_ts_pair(uint32_t d, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -80,6 +129,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 }
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=128
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+// same for a CTA pair: M = 256 (128 rows per CTA), N = 128 (64 rows of B per CTA)
+constexpr uint32_t kIdescPair = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
 
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;

@@ -226,9 +226,14 @@ def ray_bias(rays, cam_idx, codes_with_mean, packed):
     return out
 
 
+def set_mlp_cta_pair(enable):
+    """Kernel variant of the fused MLP forward: CTA pairs (cta_group::2, default) or one CTA per tile.  -> previous."""
+    return bool(_lib.load().danbo_mlp_set_cta_pair(int(bool(enable))))
+
+
 def mlp_forward(xtiles, packed, rbias, active, row_ray, out, density_only=False, trace=None):
     """Runs the fused MLP over the active rows; row r is written to out[active.ids[r]].
-    trace: optional int64 CUDA tensor of 320 entries -> clock64 timeline of CTA 0 (profiling aid)."""
+    trace: optional int64 CUDA tensor of 480 entries -> clock64 timeline of CTA 0 (profiling aid)."""
     lib = _lib.load()
     if trace is not None:
         dev = xtiles.device

@@ -72,8 +72,9 @@ int danbo_ray_bias(const float* rays, int ray_stride, int n_rays, const int* cam
 /* Sizes of the packed-weight buffers below. */
 int danbo_mlp_workspace_bytes(long long* wstream_bytes, long long* heads_bytes, long long* raybias_bytes);
 
-/* fp32 nn.Linear weights -> bf16 tiled + swizzled stage stream, fp32 head vector and the transposed per-ray slice of
- * views_linears.0.  Re-run after every optimizer step.  w_pts / b_pts are HOST arrays of 8 device pointers. */
+/* fp32 nn.Linear weights -> bf16 tiled + swizzled stage stream (written twice: 84 x 16 KB in single-CTA order, then the
+ * same tiles regrouped per CTA of a pair so that one bulk copy stages two half-stages), fp32 head vector and the
+ * transposed per-ray slice of views_linears.0.  Re-run after every optimizer step.  w_pts / b_pts are HOST arrays of 8 device pointers. */
 int danbo_pack_mlp_weights(const float* const* w_pts, const float* const* b_pts, const float* w_alpha,
                            const float* b_alpha, const float* w_feat, const float* b_feat, const float* w_view,
                            const float* b_view, const float* w_rgb, const float* b_rgb, void* wstream, float* heads,
@@ -87,10 +88,16 @@ int danbo_mlp_forward(const void* xtiles, const void* wstream, const float* head
                       int out_capacity, int density_only, int num_sms, void* stream);
 
 /* Profiling aid: the same launch as danbo_mlp_forward; CTA 0 also writes a clock64 timeline of its first 4 tiles to
- * trace[4][2 roles: MMA issuer, epilogue][20 (layer, half)][begin, end] (320 long long). */
+ * trace[4][2 roles: MMA issuer, epilogue][20 (layer, half)][begin, end] (320 long long) followed by
+ * [4][20][tmem loads landed, stores issued] of one epilogue warp (160 long long): 480 in total. */
 int danbo_mlp_forward_trace(const void* xtiles, const void* wstream, const float* heads, const float* ray_bias,
                             const int* row_sample, const int* row_ray, const int* n_rows_dev, int max_rows, float* out,
                             int out_capacity, int density_only, int num_sms, long long* trace, void* stream);
+
+/* Selects the kernel variant behind danbo_mlp_forward*: 1 (default) = CTA pairs (clusters of 2, tcgen05 cta_group::2,
+ * each CTA stages half of every weight stage), 0 = one CTA per 128-row tile.  Same results bit for bit (the MMA
+ * accumulation order does not change).  Returns the previous setting. */
+int danbo_mlp_set_cta_pair(int enable);
 
 /* C1 + R1: raw2outputs (nerf.py:281-347) on the coarse samples, then isample_from_lineseg / sample_pdf
  * (ray_utils.py:159-203,257-291) and the sorted merge order.  raw is (n_rays*S + n_rays,4); samples whose mask is 0
