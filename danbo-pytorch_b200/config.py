@@ -16,6 +16,10 @@ DEFAULTS = dict(
     ext_scale=0.001, kp_dist_type="reldist", view_type="identity", ray_tr_type="world", pts_tr_type="local",
     bone_type="Nope", graph_input_type="rot6d", use_cutoff=False, opt_posecode=False, gnn_concat=False, no_adj=False,
     adj_self_one=False, align_corners=False, opt_pose=False,
+    # A-NeRF (nerf_type=nerf) embedder flags, run_nerf.py:285-524
+    i_embed=0, multires_bones=0, cutoff_mm=500.0, cutoff_viewdir=False, cutoff_inputs=False, cutoff_shift=False,
+    cut_to_dist=False, cutoff_bones=False, normalize_cutoff=False, opt_cutoff=False, freq_schedule=False,
+    netwidth_fine=256,
 )
 
 PRESETS = {
@@ -23,6 +27,11 @@ PRESETS = {
     "danbo_base": dict(N_samples=96, N_importance=48, use_volume_near_far=False),
     "danbo_fast": dict(N_samples=32, N_importance=16, use_volume_near_far=True),
     "danbo_cfg3": dict(N_samples=64, N_importance=16, use_volume_near_far=False),   # BASELINE config #3
+    # configs/h36m_zju/anerf_base.txt (BASELINE config #4)
+    "anerf_base": dict(nerf_type="nerf", netwidth=448, netwidth_fine=448, multires=7, multires_views=4, bone_type="reldir",
+                       kp_dist_type="reldist", view_type="relray", ray_tr_type="local", use_cutoff=True,
+                       cutoff_viewdir=True, cutoff_inputs=True, cutoff_shift=True, cut_to_dist=True, N_samples=96,
+                       N_importance=48, use_volume_near_far=False),
 }
 
 

@@ -51,4 +51,28 @@ def danbo_param_shapes(n_framecodes=8, W=256, view_W=128, node_W=128, agg_W=32, 
     return s
 
 
+def anerf_param_shapes(n_framecodes=8, W=448, view_W=224, multires=7, multires_views=4, framecode_ch=128):
+    """A-NeRF field (nerf_type=nerf; configs/h36m_zju/anerf_base.txt; nerf.py:73-105): density input 24*(1+2*7) + 72
+    = 432, view input 72*(1+2*4) + 128 = 776.  The cutoff embedders' `cutoff_dist` / `tau` entries of the reference
+    state_dict (cutoff_embedder.py:128-133) are constants of the path (0.5, 20) and are not listed here."""
+    x_ch = J * (1 + 2 * multires) + J * 3
+    v_ch = J * 3 * (1 + 2 * multires_views)
+    s = OrderedDict()
+    s["pts_linears.0.weight"] = (W, x_ch)
+    s["pts_linears.0.bias"] = (W,)
+    for i in range(1, 8):
+        s[f"pts_linears.{i}.weight"] = (W, W + x_ch) if i == 5 else (W, W)
+        s[f"pts_linears.{i}.bias"] = (W,)
+    s["alpha_linear.weight"] = (1, W)
+    s["alpha_linear.bias"] = (1,)
+    s["views_linears.0.weight"] = (view_W, v_ch + framecode_ch + 2 * view_W)
+    s["views_linears.0.bias"] = (view_W,)
+    s["feature_linear.weight"] = (2 * view_W, W)
+    s["feature_linear.bias"] = (2 * view_W,)
+    s["rgb_linear.weight"] = (3, view_W)
+    s["rgb_linear.bias"] = (3,)
+    s["framecodes.codes.weight"] = (n_framecodes, framecode_ch)
+    return s
+
+
 BUFFER_NAMES = ("graph_net.layers.0.adj", "graph_net.layers.1.adj", "prob_linears.layers.0.adj")

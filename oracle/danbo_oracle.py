@@ -412,6 +412,113 @@ def render_rays(ray_batch, pose_skts, pose_bones, pose_cyls, cams, A, P, S_c, S_
 
 
 # ----------------------------------------------------------------------------------------------------------
+# AN1  A-NeRF field (nerf_type=nerf, configs/h36m_zju/anerf_base.txt): core/networks/nerf.py:222-279 encode_pts /
+# encode_views ; core/cutoff_embedder.py:151-214 CutoffEmbedder._embed ; core/encoders.py:639-651 RelDistEncoder,
+# :774-795 VecNormEncoder, :305-317 transform_batch_rays ; MLP nerf.py:164-209 with W=448, view_W=224.
+# ----------------------------------------------------------------------------------------------------------
+ANERF_CUTOFF = 500 * 0.001          # cutoff_mm * ext_scale (encoders.py:62, run_nerf.py:498)
+
+
+def anerf_cutoff_weight(dist, tau, cutoff=ANERF_CUTOFF):
+    """cutoff_embedder.py:177-184: w = 1 - sigmoid(tau * (dist - cutoff))."""
+    return 1. - torch.sigmoid(tau * (dist - cutoff))
+
+
+def anerf_dist_pe(v, tau, n_freq=7, cutoff=ANERF_CUTOFF):
+    """pe_fn of A-NeRF (cut_to_cutoff, shift_inputs, cutoff_inputs, include_input; dist_inputs False):
+    v (...,24) -> (...,15*24): rows [c - v, sin(2^0 s), cos(2^0 s), ..., cos(2^6 s)] each times w, s = (c-v)*2/c - 1;
+    flattened row-major (row, joint)."""
+    inp = cutoff - v
+    shifted = inp * (2. / cutoff) - 1.
+    freqs = 2. ** torch.linspace(0., n_freq - 1, steps=n_freq)
+    x = freqs.view(1, -1, 1) * shifted[..., None, :]                       # (..., F, 24)
+    w = anerf_cutoff_weight(v, tau, cutoff)[..., None, :]
+    emb = torch.stack([torch.sin(x), torch.cos(x)], dim=-2).flatten(start_dim=-3, end_dim=-2)   # (..., 2F, 24)
+    emb = torch.cat([inp[..., None, :], emb], dim=-2) * w
+    return emb.flatten(start_dim=-2)
+
+
+def anerf_dir_pe(d, v, tau, n_freq=4, cutoff=ANERF_CUTOFF):
+    """dirs_pe_fn (dist_inputs=True): d (...,72) per-joint unit vectors, v (...,24) -> (...,9*72); joint j's weight is
+    repeated over its three components."""
+    dist = v[..., None].expand(*v.shape, 3).flatten(start_dim=-2)           # (..., 72)
+    freqs = 2. ** torch.linspace(0., n_freq - 1, steps=n_freq)
+    x = freqs.view(1, -1, 1) * d[..., None, :]
+    w = anerf_cutoff_weight(dist, tau, cutoff)[..., None, :]
+    emb = torch.stack([torch.sin(x), torch.cos(x)], dim=-2).flatten(start_dim=-3, end_dim=-2)
+    emb = torch.cat([d[..., None, :], emb], dim=-2) * w
+    return emb.flatten(start_dim=-2)
+
+
+def anerf_inputs(pts, rays_d, cams, skts, A, P, training, tau=20.):
+    """pts (N,S,3) -> density_inputs (N*S,432), view_inputs (N*S,776), stage dict."""
+    N, S = pts.shape[:2]
+    pts_t = world_to_bone(pts, skts, A)                                     # (N,S,24,3) incl. bone alignment (T2)
+    v = torch.norm(pts_t, dim=-1, p=2)                                      # RelDistEncoder
+    r = F.normalize(pts_t, dim=-1, p=2).flatten(start_dim=2)                # VecNormEncoder on pts_t (bone_type reldir)
+    dens = torch.cat([anerf_dist_pe(v, tau), r], -1).reshape(N * S, -1)
+    rays_t = (skts[..., :3, :3] @ rays_d.reshape(N, 1, 3, 1)).reshape(N, 1, J, 3)     # transform_batch_rays (rotation only)
+    d = F.normalize(rays_t, dim=-1, p=2).flatten(start_dim=2).expand(N, S, -1)
+    d_pe = anerf_dir_pe(d, v, tau)
+    codes = P["framecodes.codes.weight"]
+    if (not training) and cams.max() < 0:
+        c = codes.mean(0, keepdim=True).expand(len(cams), -1)
+    else:
+        c = codes[cams.reshape(-1).long()]
+    view = torch.cat([d_pe, c[:, None].expand(N, S, -1)], -1).reshape(N * S, -1)
+    return dens, view, {"pts_t": pts_t, "v": v, "r": r, "d": d}
+
+
+def anerf_mlp(x, view, P):
+    """nerf.py:176-209 with the skip after layer 4 ([x ; h]); W read from the parameter shapes."""
+    h = x
+    for i in range(8):
+        h = F.relu(F.linear(h, P[f"pts_linears.{i}.weight"], P[f"pts_linears.{i}.bias"]))
+        if i == 4:
+            h = torch.cat([x, h], -1)
+    alpha = F.linear(h, P["alpha_linear.weight"], P["alpha_linear.bias"])
+    f = F.linear(h, P["feature_linear.weight"], P["feature_linear.bias"])
+    g = F.relu(F.linear(torch.cat([f, view], -1), P["views_linears.0.weight"], P["views_linears.0.bias"]))
+    rgb = F.linear(g, P["rgb_linear.weight"], P["rgb_linear.bias"])
+    return torch.cat([rgb, alpha], -1)
+
+
+def anerf_render_rays(ray_batch, pose_skts, pose_cyls, cams, A, P, S_c, S_f, rays_per_pose, training=False, rand=None,
+                      raw_noise_std=0., tau=20., return_stages=False, z_samples=None):
+    """RayCaster.render_rays (raycasters.py:245-377) for nerf_type=nerf: cylinder near/far only (:419-420), the field
+    evaluated on every sample, single_net fine pass on the S_f new samples (F9)."""
+    N = ray_batch.shape[0]
+    G = pose_skts.shape[0]
+    pose = torch.clamp(torch.arange(N) // rays_per_pose, max=G - 1)
+    skts, cyls = pose_skts[pose], pose_cyls[pose]
+    rays_o, rays_d = ray_batch[:, 0:3], ray_batch[:, 3:6]
+    near, far = cylinder_near_far(rays_o, rays_d, cyls, ray_batch[:, 6:7], ray_batch[:, 7:8])
+    rand = rand or {}
+    z = coarse_z(near, far, S_c, rand.get("t_rand"))
+    x0, v0, st0 = anerf_inputs(ray_points(rays_o, rays_d, z), rays_d, cams, skts, A, P, training, tau)
+    raw0 = anerf_mlp(x0, v0, P).reshape(N, S_c, 4)
+    n0 = rand["noise0"] * raw_noise_std if "noise0" in rand else None
+    out0 = composite(raw0, z, rays_d, n0)
+    z_all, zs, order, inds = importance_sample(z, out0["weights"], S_f, rand.get("u"))
+    if z_samples is not None:                                               # test hook, see render_rays
+        zs = z_samples
+        z_all, order = torch.sort(torch.cat([z, zs], -1), -1)
+    x1, v1, st1 = anerf_inputs(ray_points(rays_o, rays_d, zs), rays_d, cams, skts, A, P, training, tau)
+    raw1 = anerf_mlp(x1, v1, P).reshape(N, S_f, 4)
+    raw = merge_sorted(raw0, raw1, order)
+    n1 = rand["noise1"] * raw_noise_std if "noise1" in rand else None
+    out = composite(raw, z_all, rays_d, n1)
+    ret = {"rgb_map": out["rgb_map"], "disp_map": out["disp_map"], "acc_map": out["acc_map"],
+           "alpha": out["alpha"], "T_i": out["weights"],
+           "rgb0": out0["rgb_map"], "disp0": out0["disp_map"], "acc0": out0["acc_map"], "alpha0": out0["alpha"]}
+    if return_stages:
+        ret["_stages"] = {"near": near, "far": far, "z_coarse": z, "dens_in0": x0, "view_in0": v0, "raw0": raw0,
+                          "weights0": out0["weights"], "z_samples": zs, "z_all": z_all, "sorted_idxs": order,
+                          "raw1": raw1, "raw": raw, "v0": st0["v"]}
+    return ret
+
+
+# ----------------------------------------------------------------------------------------------------------
 # D1  core/raycasters.py:421-453 render_mesh_density ; core/networks/nerf.py:136-154
 # ----------------------------------------------------------------------------------------------------------
 def density_grid(kps, skts, bones, A, P, radius, res, agg_type="sigmoid"):

@@ -213,6 +213,78 @@ def run_render_case(name, config, extra, pose_seed, H, n_rays, weight_seed=0, fu
     print(name, "->", path, f"{os.path.getsize(path) / 1e6:.2f} MB", {k: len(v) for k, v in tap.rec.items()})
 
 
+def run_anerf_case(name, extra, pose_seed, H, n_rays, weight_seed=0):
+    """A-NeRF (BASELINE config #4): eval-mode render_rays of the reference's plain RayCaster + NeRF(W=448)."""
+    rc, _ = rh._imports()
+    config = "h36m_zju/anerf_base.txt"
+    args = rh.parse_args(config, extra)
+    rest = syn.rest_pose()
+    caster, kw = rh.build(args, rest)
+    caster.eval()
+    sd = syn.synth_state_dict(params.anerf_param_shapes(), weight_seed)
+    rh.load_weights(caster, sd)
+    pose = syn.make_pose(pose_seed)
+    b = subsample_rays(syn.render_batch(pose, H, H), n_rays, seed=pose_seed)
+    net = caster.network
+    tap = Tap()
+
+    def cyl(orig, *a, **k):
+        n, f = orig(*a, **k)
+        tap.add("near", n), tap.add("far", f)
+        return n, f
+    tap.wrap(rc, "get_near_far_in_cylinder", cyl)
+
+    def spts(orig, *a, **k):
+        pts, z = orig(*a, **k)
+        tap.add("z", z)
+        return pts, z
+    tap.wrap(caster, "sample_pts", spts)
+
+    def spts_is(orig, *a, **k):
+        pts, z_all, zs, order = orig(*a, **k)
+        tap.add("z_all", z_all), tap.add("z_samples", zs), tap.add("sorted_idxs", order)
+        return pts, z_all, zs, order
+    tap.wrap(caster, "sample_pts_is", spts_is)
+
+    def enc_pts(orig, *a, **k):
+        d, enc = orig(*a, **k)
+        S = enc["v"].shape[1]
+        tap.add("density_inputs", d[:STAGE_RAYS * S]), tap.add("v", enc["v"][:STAGE_RAYS])
+        return d, enc
+    tap.wrap(net, "encode_pts", enc_pts)
+
+    def enc_views(orig, *a, **k):
+        v, enc = orig(*a, **k)
+        S = k["refs"].shape[1]
+        tap.add("view_inputs", v[:STAGE_RAYS * S])
+        return v, enc
+    tap.wrap(net, "encode_views", enc_views)
+
+    def r2o(orig, raw, z, rays_d, *a, **k):
+        out = orig(raw, z, rays_d, *a, **k)
+        tap.add("raw", raw), tap.add("weights", out["weights"]), tap.add("alpha", out["alpha"])
+        return out
+    tap.wrap(net, "raw2outputs", r2o)
+
+    kwargs = {k: v for k, v in kw.items() if k not in ("ray_caster", "N_samples", "use_viewdirs")}
+    with torch.no_grad():
+        ret = caster(b["ray_batch"], N_samples=args.N_samples, kp_batch=b["kp_batch"], skts=b["skts"],
+                     cyls=b["cyls"], bones=b["bones"], cams=b["cams"], N_uniques=1, **kwargs)
+    tap.undo()
+    fx = {"config": config, "extra": " ".join(extra), "pose_seed": pose_seed, "weight_seed": weight_seed, "H": H,
+          "N_samples": args.N_samples, "N_importance": args.N_importance, "tau": float(net.pe_fn.get_tau()),
+          "ray_batch": b["ray_batch"], "cams": b["cams"], "pose_bones": pose["bones"], "pose_kps": pose["kps"],
+          "pose_skts": pose["skts"], "pose_cyl": pose["cyl"]}
+    for k, v in ret.items():
+        fx["out." + k] = v
+    for k, lst in tap.rec.items():
+        for i, v in enumerate(lst):
+            fx[f"st.{k}.{i}"] = v
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **npify(fx))
+    print(name, "->", path, f"{os.path.getsize(path) / 1e6:.2f} MB", {k: len(v) for k, v in tap.rec.items()})
+
+
 def run_train_case(name, config, extra, n_poses, rays_per_pose, weight_seed=0, batch_seed=0):
     rc, _ = rh._imports()
     import core.trainer as trainer_mod
@@ -300,6 +372,10 @@ def main():
     assert rh.available(), "needs /root/reference (authoring container)"
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    only = sys.argv[1] if len(sys.argv) > 1 else None       # `python oracle/gen_golden.py anerf` regenerates that case only
+    if only == "anerf":
+        run_anerf_case("render_anerf", ["--N_samples", "24", "--N_importance", "12"], pose_seed=4, H=64, n_rays=64)
+        return
     run_render_case("render_fast", "h36m_zju/danbo_fast.txt", [], pose_seed=3, H=64, n_rays=256)
     run_render_case("render_base", "h36m_zju/danbo_base.txt", [], pose_seed=5, H=64, n_rays=96)
     run_render_case("render_fast_miss", "h36m_zju/danbo_fast.txt", [], pose_seed=7, H=48, n_rays=192, full_image=True)
@@ -307,6 +383,7 @@ def main():
     run_train_case("train_cfg3", "h36m_zju/danbo_base.txt", ["--N_samples", "64", "--N_importance", "16"],
                    n_poses=2, rays_per_pose=32)
     run_grid_case("grid_base", "h36m_zju/danbo_base.txt", pose_seed=3, res=11)
+    run_anerf_case("render_anerf", ["--N_samples", "24", "--N_importance", "12"], pose_seed=4, H=64, n_rays=64)
 
 
 if __name__ == "__main__":
