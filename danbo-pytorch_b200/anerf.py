@@ -1,0 +1,196 @@
+"""A-NeRF (nerf_type = nerf, BASELINE config #4) behind the reference's plain `RayCaster`.
+
+`AnerfField` owns the parameters under the reference's names (core/networks/nerf.py:73-105 with W = 448, view_W = 224,
+plus the cutoff embedders' `cutoff_dist` / `tau` entries, cutoff_embedder.py:128-133) so reference checkpoints load.
+`AnerfCaster` mirrors raycasters.py:205-546 for this network type: cylinder near/far only (:419-420), every sample
+goes through the field, single_net fine pass on the S_f new samples (F9).  Rendering only: config #4 is a render
+benchmark, and the backward kernels of this path exist only for the DANBO field, so train mode raises.
+"""
+import torch
+import torch.nn as nn
+
+from . import kernels as K
+from .networks import Optcodes
+from .raycaster import RayCaster, MAX_RAYS_PER_LAUNCH
+
+J = 24
+CUTOFF = 500 * 0.001                     # cutoff_mm * ext_scale (encoders.py:62, run_nerf.py:498)
+
+
+class _CutoffPE(nn.Module):
+    """State of a CutoffEmbedder (cutoff_embedder.py:100-150): a frozen per-joint cutoff and the temperature buffer."""
+
+    def __init__(self, init_tau=20.):
+        super().__init__()
+        self.init_tau = init_tau
+        self.cutoff_dist = nn.Parameter(torch.ones(J) * CUTOFF, requires_grad=False)
+        self.register_buffer("tau", torch.tensor(init_tau))
+
+    def get_tau(self):
+        return self.tau.item()
+
+    def update_tau(self, global_step, step, rate):
+        self.tau = (self.init_tau * torch.ones_like(self.tau) * rate ** (global_step / float(step * 1000))).clamp(max=2000.)
+
+
+class AnerfField(nn.Module):
+    def __init__(self, n_framecodes=8, W=448, D=8, view_W=224, multires=7, multires_views=4, framecode_ch=128):
+        super().__init__()
+        if (W, D, view_W, multires, multires_views, framecode_ch) != (448, 8, 224, 7, 4, 128):
+            raise NotImplementedError("the sm_100a A-NeRF kernels are specialised for netwidth=448, netdepth=8, "
+                                      "multires=7, multires_views=4, framecode_size=128 (configs/*/anerf_base.txt)")
+        self.W, self.D, self.view_W = W, D, view_W
+        x_ch = J * (1 + 2 * multires) + J * 3
+        v_ch = J * 3 * (1 + 2 * multires_views)
+        layers = [nn.Linear(x_ch, W)]
+        for i in range(D - 1):
+            layers.append(nn.Linear(W + x_ch, W) if i == 4 else nn.Linear(W, W))
+        self.pe_fn = _CutoffPE()
+        self.dirs_pe_fn = _CutoffPE()
+        self.pts_linears = nn.ModuleList(layers)
+        self.alpha_linear = nn.Linear(W, 1)
+        self.views_linears = nn.ModuleList([nn.Linear(v_ch + framecode_ch + 2 * view_W, view_W)])
+        self.feature_linear = nn.Linear(W, 2 * view_W)
+        self.rgb_linear = nn.Linear(view_W, 3)
+        self.framecodes = Optcodes(n_framecodes, framecode_ch)
+
+    def update_embed_fns(self, global_step, args):
+        """trainer.py:294-300: the cutoff temperature schedule."""
+        step, rate = getattr(args, "tau_step", None), getattr(args, "tau_rate", None)
+        if step and rate:
+            self.pe_fn.update_tau(global_step, step, rate)
+            self.dirs_pe_fn.update_tau(global_step, step, rate)
+
+
+class AnerfCaster(RayCaster):
+    """The reference's base RayCaster (raycasters.py:205-546) over the A-NeRF field, on B200 kernels."""
+
+    def __init__(self, network, network_fine=None, single_net=True, rest_poses=None, align_bones="align", skel_type=None,
+                 **kwargs):
+        super().__init__(network, network_fine=network_fine, single_net=single_net, rest_poses=rest_poses,
+                         align_bones=align_bones, skel_type=skel_type, use_volume_near_far=False)
+        self._unit_scale = None
+
+    # ---- helpers --------------------------------------------------------------------------------------------
+    def _align(self):
+        dev = self._device()
+        if self._align_dev is None or self._align_dev.device != dev:
+            self._align_dev = self.transforms[0].to(dev).float().contiguous()
+            self._unit_scale = torch.ones(J, 3, device=dev)
+        return self._align_dev
+
+    def _tau(self):
+        """Cutoff temperature as a host float; read back from the buffer only when the buffer changed."""
+        t = self.network.pe_fn.tau
+        key = (t.data_ptr(), t._version)
+        if getattr(self, "_tau_key", None) != key:
+            self._tau_key, self._tau_val = key, float(t.item())
+        return self._tau_val
+
+    def _packed_mlp(self):
+        net = self.network
+        names = [f"pts_linears.{i}.{w}" for i in range(8) for w in ("weight", "bias")] + [
+            "alpha_linear.weight", "alpha_linear.bias", "feature_linear.weight", "feature_linear.bias",
+            "views_linears.0.weight", "views_linears.0.bias", "rgb_linear.weight", "rgb_linear.bias"]
+        P = dict(net.named_parameters())
+        key = tuple((P[n].data_ptr(), P[n]._version) for n in names)
+        if self._packed is None or self._packed.wstream.device != self._device():
+            self._packed = K.AnerfPacked(self._device())
+            self._packed_key = None
+        if key != self._packed_key:
+            self._packed.pack({n: P[n] for n in names})
+            self._packed_key = key
+        return self._packed
+
+    # ---- render ---------------------------------------------------------------------------------------------
+    def _render_prepared(self, rays, pose_skts, pose_bones, pose_cyls, cam_idx, skip=1, N_samples=96, N_importance=48,
+                         B=1.0, raw_noise_std=0., perturb=0., nanmean_chunk=None, _rand=None, _stages=None):
+        if self.training:
+            raise NotImplementedError("A-NeRF (nerf_type='nerf') is render-only here: the backward kernels exist for the "
+                                      "DANBO field only (BASELINE config #4 is a render benchmark)")
+        N = rays.shape[0]
+        align = self._align()
+        packed = self._packed_mlp()
+        codes = self._codes_with_mean()
+        tau = self._tau()
+        G = pose_skts.shape[0]
+        # every sample is evaluated: bound the rows of one launch sequence (operand images are 2.3 KB per row)
+        max_rays = max(MAX_RAYS_PER_LAUNCH * 24 // (N_samples + N_importance) // 4096, 1) * 4096
+        block = max_rays if G == 1 else max((max_rays // skip) * skip, skip)
+        if nanmean_chunk and G == 1:
+            block = max((block // int(nanmean_chunk)) * int(nanmean_chunk), int(nanmean_chunk))
+        outs = []
+        for s0 in range(0, N, block):
+            s1 = min(N, s0 + block)
+            outs.append(self._render_block_anerf(rays[s0:s1], s0, skip, pose_skts, pose_cyls, cam_idx[s0:s1], codes, align,
+                                                 packed, tau, N_samples, N_importance, B, nanmean_chunk, _stages))
+        if len(outs) == 1:
+            return outs[0]
+        return {k: torch.cat([o[k] for o in outs], 0) for k in outs[0]}
+
+    def _render_block_anerf(self, rays, ray0, skip, pose_skts, pose_cyls, cam_idx, codes, align, packed, tau, S_c, S_f, B,
+                            nanmean_chunk, stages):
+        n = rays.shape[0]
+        dev = rays.device
+        if pose_skts.shape[0] == 1:
+            p0 = 0
+        else:
+            assert ray0 % skip == 0
+            p0 = ray0 // skip
+        p_skts, p_cyls = pose_skts[p0:], pose_cyls[p0:]
+        seg = 0 if not nanmean_chunk else int(nanmean_chunk)
+        near, far = K.nearfar(rays, p_cyls, p_skts, skip, align, self._unit_scale, seg_len=seg, use_box=False)   # NF1
+        enc, code_bias = K.anerf_ray_encode(rays, p_skts, skip, cam_idx, codes, packed)
+        # SM1 (ray_utils.py:206-253, eval): z = near (1 - t) + far t, the reference's own two-product form
+        t = torch.linspace(0., 1., steps=S_c, device=dev)
+        z0 = (near[:, None] * (1. - t) + far[:, None] * t).contiguous()
+        xd, xv = K.anerf_embed(rays, S_c, z0, p_skts, skip, align, enc, tau)
+        raw0 = torch.empty(n * S_c + n, 4, device=dev, dtype=torch.float32)
+        K.anerf_mlp(xd, xv, packed, code_bias, n * S_c, S_c, raw0)
+        ones0 = torch.ones(n, S_c, device=dev, dtype=torch.int32)          # every sample carries its own field value
+        c0 = K.composite_resample(rays, S_c, S_f, raw0, ones0, z0, inv_B=1.0 / B, want_inds=stages is not None)
+        z1 = c0["z_samples"]
+        xd1, xv1 = K.anerf_embed(rays, S_f, z1, p_skts, skip, align, enc, tau, xd=xd, xv=xv)
+        raw1 = torch.empty(n * S_f, 4, device=dev, dtype=torch.float32)
+        K.anerf_mlp(xd1, xv1, packed, code_bias, n * S_f, S_f, raw1)
+        ones1 = torch.ones(n, S_f, device=dev, dtype=torch.int32)
+        c1 = K.merge_composite(rays, S_c, S_f, raw0, ones0, raw1, ones1, c0["z_all"], c0["order"], inv_B=1.0 / B,
+                               want_raw=stages is not None)
+        ret = {"rgb_map": c1["rgb_map"], "disp_map": c1["disp_map"], "acc_map": c1["acc_map"], "alpha": c1["alpha"],
+               "T_i": c1["weights"], "rgb0": c0["rgb_map"], "disp0": c0["disp_map"], "acc0": c0["acc_map"],
+               "alpha0": c0["alpha"]}
+        if stages is not None:
+            stages.update({"near": near, "far": far, "z_coarse": z0, "raw0": raw0, "weights0": c0["weights"],
+                           "z_samples": z1, "z_all": c0["z_all"], "sorted_idxs": c0["order"], "raw1": raw1,
+                           "raw": c1.get("raw"), "ray_enc": enc, "code_bias": code_bias})
+        return ret
+
+    # ---- not part of config #4 --------------------------------------------------------------------------------
+    def render_pts_density(self, *a, **k):
+        raise NotImplementedError("density queries (fwd_type='density'/'mesh') are implemented for the DANBO field only")
+
+    def render_mesh_density(self, *a, **k):
+        raise NotImplementedError("density queries (fwd_type='density'/'mesh') are implemented for the DANBO field only")
+
+
+_ANERF_REQUIRED = {"netdepth": 8, "netwidth": 448, "multires": 7, "multires_views": 4, "multires_bones": 0,
+                   "framecode_size": 128, "single_net": True, "opt_framecode": True, "use_viewdirs": True,
+                   "use_cutoff": True, "cutoff_viewdir": True, "cutoff_inputs": True, "cutoff_shift": True,
+                   "cut_to_dist": True, "cutoff_bones": False, "normalize_cutoff": False, "opt_cutoff": False,
+                   "freq_schedule": False, "cutoff_mm": 500.0, "ext_scale": 0.001, "i_embed": 0, "lindisp": False}
+_ANERF_SUPPORTED = {"align_bones": ("align",), "density_type": ("relu",), "kp_dist_type": ("reldist",),
+                    "view_type": ("relray",), "ray_tr_type": ("local",), "pts_tr_type": ("local",), "bone_type": ("reldir",)}
+
+
+def check_anerf_args(args):
+    """The flag subset of configs/*/anerf_base.txt that selects this path; anything else raises."""
+    for k, allowed in _ANERF_SUPPORTED.items():
+        v = getattr(args, k, allowed[0])
+        if v not in allowed:
+            raise NotImplementedError(f"{k}={v!r} is not implemented for nerf_type='nerf' (supported: {allowed})")
+    for k, want in _ANERF_REQUIRED.items():
+        v = getattr(args, k, want)
+        if v != want:
+            raise NotImplementedError(f"{k}={v!r} is not implemented for nerf_type='nerf' (kernels are built for {k}={want!r})")
+    if getattr(args, "netwidth_view", None) not in (None, 224):
+        raise NotImplementedError("netwidth_view must be None/224")

@@ -508,3 +508,87 @@ def field_agg_bwd(rays, S, z, mask, active, pose_skts, pose_vol, rays_per_pose, 
                                        _p(g_logit_ext), _p(d_hbar), _p(d_logit), _p(fo.work), fo.pair_cap, ga,
                                        num_sms(idx), _stream()), "danbo_field_agg_bwd")
     _count(2)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# AN1: A-NeRF field (nerf_type = nerf, BASELINE config #4)
+ANERF_XD_TILE_BYTES = 7 * 16384
+ANERF_XV_TILE_BYTES = 11 * 16384
+
+
+class AnerfPacked:
+    """Packed weights + per-CTA activation scratch of the A-NeRF MLP (W = 448)."""
+
+    def __init__(self, device):
+        lib = _lib.load()
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        sizes = [ctypes.c_longlong() for _ in range(4)]
+        lib.danbo_anerf_workspace_bytes(num_sms(idx), *[ctypes.byref(x) for x in sizes])
+        self.wstream = torch.empty(sizes[0].value, device=device, dtype=torch.uint8)
+        self.heads = torch.empty(sizes[1].value // 4, device=device, dtype=torch.float32)
+        self.w_code = torch.empty(sizes[2].value // 4, device=device, dtype=torch.float32)
+        self.scratch = torch.empty(sizes[3].value, device=device, dtype=torch.uint8)
+
+    def pack(self, P):
+        lib = _lib.load()
+        ws = [f32c(P[f"pts_linears.{i}.weight"]) for i in range(8)]
+        bs = [f32c(P[f"pts_linears.{i}.bias"]) for i in range(8)]
+        others = [f32c(P[k]) for k in ("alpha_linear.weight", "alpha_linear.bias", "feature_linear.weight",
+                                       "feature_linear.bias", "views_linears.0.weight", "views_linears.0.bias",
+                                       "rgb_linear.weight", "rgb_linear.bias")]
+        _need_cuda(*ws, *bs, *others)
+        wa = (ctypes.c_void_p * 8)(*[t.data_ptr() for t in ws])
+        ba = (ctypes.c_void_p * 8)(*[t.data_ptr() for t in bs])
+        _lib.check(lib.danbo_anerf_pack_weights(wa, ba, *[_p(t) for t in others], _p(self.wstream), _p(self.heads),
+                                                _p(self.w_code), _stream()), "danbo_anerf_pack_weights")
+        self._keep = (ws, bs, others)
+        _count(1)
+        return self
+
+
+def anerf_ray_encode(rays, pose_skts, rays_per_pose, cam_idx, codes_with_mean, packed):
+    """-> ray_enc (n,648), code_bias (n,224)."""
+    _need_cuda(rays, pose_skts, cam_idx, codes_with_mean)
+    lib = _lib.load()
+    n = rays.shape[0]
+    enc = torch.empty(n, 648, device=rays.device, dtype=torch.float32)
+    cb = torch.empty(n, 224, device=rays.device, dtype=torch.float32)
+    with _Timed("anerf_ray_encode"):
+        _lib.check(lib.danbo_anerf_ray_encode(_p(rays), rays.stride(0), n, _p(pose_skts), int(rays_per_pose),
+                                              pose_skts.shape[0], _p(cam_idx), _p(codes_with_mean),
+                                              codes_with_mean.shape[0] - 1, _p(packed.w_code), _p(enc), _p(cb), _stream()),
+                   "danbo_anerf_ray_encode")
+    _count(1)
+    return enc, cb
+
+
+def anerf_embed(rays, S, z, pose_skts, rays_per_pose, align, ray_enc, tau, xd=None, xv=None):
+    """z (n,S) -> operand tile images xd, xv (uint8) of the n*S dense rows."""
+    _need_cuda(rays, z, pose_skts, align, ray_enc)
+    lib = _lib.load()
+    rows = rays.shape[0] * S
+    tiles = (rows + 127) // 128
+    if xd is None:
+        xd = torch.empty(tiles * ANERF_XD_TILE_BYTES, device=rays.device, dtype=torch.uint8)
+    if xv is None:
+        xv = torch.empty(tiles * ANERF_XV_TILE_BYTES, device=rays.device, dtype=torch.uint8)
+    assert xd.numel() >= tiles * ANERF_XD_TILE_BYTES and xv.numel() >= tiles * ANERF_XV_TILE_BYTES
+    with _Timed("anerf_embed"):
+        _lib.check(lib.danbo_anerf_embed(_p(rays), rays.stride(0), int(S), _p(z), rows, _p(pose_skts), int(rays_per_pose),
+                                         pose_skts.shape[0], _p(align), _p(ray_enc), float(tau), _p(xd), _p(xv), _stream()),
+                   "danbo_anerf_embed")
+    _count(1)
+    return xd, xv
+
+
+def anerf_mlp(xd, xv, packed, code_bias, rows, S, out):
+    """out (>= rows, 4) <- [rgb, sigma] of the dense rows."""
+    _need_cuda(xd, xv, code_bias, out)
+    lib = _lib.load()
+    idx = out.device.index if out.device.index is not None else torch.cuda.current_device()
+    with _Timed("anerf_mlp"):
+        _lib.check(lib.danbo_anerf_mlp(_p(xd), _p(xv), _p(packed.wstream), _p(packed.heads), _p(code_bias),
+                                       _p(packed.scratch), int(rows), int(S), _p(out), out.shape[0], num_sms(idx), _stream()),
+                   "danbo_anerf_mlp")
+    _count(1)
+    return out

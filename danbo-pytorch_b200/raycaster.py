@@ -344,17 +344,27 @@ def check_args(args):
 def create_raycaster(args, data_attrs, device=None):
     """Mirror of core/raycasters.py:17-143: returns (render_kwargs_train, render_kwargs_test, start, grad_vars,
     optimizer, loaded_ckpt).  `render_kwargs_train['ray_caster']` exposes `.module` like nn.DataParallel does."""
-    check_args(args)
+    is_anerf = getattr(args, "nerf_type", "danbo") == "nerf"
+    if is_anerf:
+        from . import anerf as _anerf                 # A-NeRF field behind the reference's plain RayCaster (config #4)
+        _anerf.check_anerf_args(args)
+    else:
+        check_args(args)
     device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
     skel_type = data_attrs.get("skel_type", sk.SMPLSkeleton)
     rest_pose = np.asarray(data_attrs["rest_pose"], dtype=np.float32)
     n_framecodes = data_attrs["n_views"] if getattr(args, "n_framecodes", None) is None else args.n_framecodes
     profile = sk.skeleton_profile(rest_pose)
     data_attrs["skel_profile"] = profile
-    net = DanboField(n_framecodes=n_framecodes, skel_profile=profile, opt_scale=bool(getattr(args, "opt_vol_scale", True)),
-                     agg_type=args.agg_type, mask_vol_prob=bool(getattr(args, "mask_vol_prob", True)))
-    caster = RayCaster(net, network_fine=net, single_net=True, rest_poses=rest_pose, align_bones=args.align_bones,
-                       skel_type=skel_type, use_volume_near_far=bool(getattr(args, "use_volume_near_far", False)))
+    if is_anerf:
+        net = _anerf.AnerfField(n_framecodes=n_framecodes)
+        caster = _anerf.AnerfCaster(net, network_fine=net, single_net=True, rest_poses=rest_pose,
+                                    align_bones=args.align_bones, skel_type=skel_type)
+    else:
+        net = DanboField(n_framecodes=n_framecodes, skel_profile=profile, opt_scale=bool(getattr(args, "opt_vol_scale", True)),
+                         agg_type=args.agg_type, mask_vol_prob=bool(getattr(args, "mask_vol_prob", True)))
+        caster = RayCaster(net, network_fine=net, single_net=True, rest_poses=rest_pose, align_bones=args.align_bones,
+                           skel_type=skel_type, use_volume_near_far=bool(getattr(args, "use_volume_near_far", False)))
     caster.to(device)
     grad_vars = [p for p in net.parameters() if p.requires_grad]
     wd = getattr(args, "weight_decay", None)

@@ -183,6 +183,39 @@ int danbo_field_agg_bwd(const float* rays, int ray_stride, int n_rays, int S, co
                         float* d_logit, const int* work, int pair_capacity, float* const* grads, int num_sms,
                         void* stream);
 
+/* ---- AN1: A-NeRF field (nerf_type = nerf, BASELINE config #4) -------------------------------------------------
+ * Replaces core/networks/nerf.py:164-279 (encode_pts / encode_views / inference with W = 448, view_W = 224),
+ * core/cutoff_embedder.py:151-214 and core/encoders.py:305-317,639-651,774-795.  Every sample goes through the field
+ * (the cutoff never makes an encoding exactly zero), rows are dense: row = ray * S + sample. */
+
+/* Buffer sizes: packed weight stream, fp32 head vector, frame-code slice of the view layer, per-CTA activation scratch. */
+int danbo_anerf_workspace_bytes(int num_sms, long long* wstream_bytes, long long* heads_bytes, long long* code_bytes,
+                                long long* scratch_bytes);
+
+/* fp32 nn.Linear weights (pts_linears.0-7 (448,432|448|880), alpha, feature (448,448), views_linears.0 (224,1224), rgb
+ * (3,224)) -> bf16 stage stream in consumption order per CTA of a pair, head vector, transposed code slice + b_view. */
+int danbo_anerf_pack_weights(const float* const* w_pts, const float* const* b_pts, const float* w_alpha,
+                             const float* b_alpha, const float* w_feat, const float* b_feat, const float* w_view,
+                             const float* b_view, const float* w_rgb, const float* b_rgb, void* wstream, float* heads,
+                             float* w_code, void* stream);
+
+/* Per ray: unit ray direction in each of the 24 bone frames with its 4-octave encoding (n,648) fp32 [row 9][72], and
+ * the frame-code contribution of the view layer (n,224) = W_v[:,1096:1224] . code + b_v.  codes as danbo_ray_bias. */
+int danbo_anerf_ray_encode(const float* rays, int ray_stride, int n_rays, const float* pose_skts, int rays_per_pose,
+                           int n_poses, const int* cam_idx, const float* codes, int n_codes, const float* w_code,
+                           float* ray_enc, float* code_bias, void* stream);
+
+/* Per sample (row = ray * S + s, z (n_rays,S)): density input [cutoff PE of the 24 bone distances (360) ; unit vectors
+ * (72)] -> xd, view input [direction encoding x cutoff weight (648)] -> xv; bf16 operand tile images of
+ * ceil(n_rows/128) tiles x 7 (xd) / 11 (xv) chunks of 16 KB.  align = (24,4,4) bone-align transforms, tau = 20 at init. */
+int danbo_anerf_embed(const float* rays, int ray_stride, int S, const float* z, int n_rows, const float* pose_skts,
+                      int rays_per_pose, int n_poses, const float* align, const float* ray_enc, float tau, void* xd,
+                      void* xv, void* stream);
+
+/* The 8 x 448 MLP + heads on n_rows rows: out (rows,4) = [rgb, sigma].  One persistent launch over CTA pairs. */
+int danbo_anerf_mlp(const void* xd, const void* xv, const void* wstream, const float* heads, const float* code_bias,
+                    void* scratch, int n_rows, int S, float* out, int out_capacity, int num_sms, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,129 @@
+"""AN1 (BASELINE config #4, A-NeRF) on the GPU through the C ABI, against the oracle and the reference's golden."""
+import numpy as np
+import pytest
+import torch
+
+import danbo_oracle as orc
+from util import load_fixture, align_A, pose_tensors, decode_tile_image, anerf_mlp_bf16_reference
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def K():
+    import danbo_b200
+    return danbo_b200.kernels
+
+
+def anerf_params(fx):
+    from danbo_b200 import params, synthetic as syn
+    return syn.synth_state_dict(params.anerf_param_shapes(), int(fx["weight_seed"]))
+
+
+def make_anerf_caster(fx):
+    import danbo_b200 as db
+    from danbo_b200 import synthetic as syn, skeleton as sk
+    args = db.make_args("anerf_base", no_reload=True, N_samples=int(fx["N_samples"]), N_importance=int(fx["N_importance"]))
+    attrs = {"skel_type": sk.SMPLSkeleton, "near": syn.NEAR, "far": syn.FAR, "n_views": 8, "rest_pose": syn.rest_pose()}
+    _, kw_test, *_ = db.create_raycaster(args, attrs, device=DEV)
+    caster = kw_test["ray_caster"]
+    P = anerf_params(fx)
+    missing = caster.network.load_state_dict(P, strict=False)
+    assert not missing.unexpected_keys and all("pe_fn" in k for k in missing.missing_keys), missing
+    caster.eval()
+    return caster, args, P
+
+
+def close(a, b, tol, what):
+    scale = max(float(b.abs().max()), 1e-6)
+    err = float((a - b).abs().max())
+    assert err <= tol * scale + 1e-7, f"{what}: err {err:.3e} scale {scale:.3e}"
+
+
+def test_anerf_encodings():
+    """ray_kernel + embed_kernel: the operand tile images hold the oracle's density / view inputs rounded to bf16."""
+    fx = load_fixture("render_anerf")
+    caster, args, P = make_anerf_caster(fx)
+    skts, bones, cyl = pose_tensors(fx)
+    rb = fx["ray_batch"].to(DEV)
+    N, S = rb.shape[0], int(fx["N_samples"])
+    packed = caster._packed_mlp()
+    align = caster._align()
+    cams = fx["cams"].reshape(-1).to(DEV).to(torch.int32)
+    enc, cb = K().anerf_ray_encode(rb, skts.to(DEV).contiguous(), N, cams, caster._codes_with_mean(), packed)
+    z = fx["st.z.0"].to(DEV).contiguous()
+    xd, xv = K().anerf_embed(rb, S, z, skts.to(DEV).contiguous(), N, align, enc, float(fx["tau"]))
+    got_d = decode_tile_image(xd, N * S, 7, 432).cpu()
+    got_v = decode_tile_image(xv, N * S, 11, 648).cpu()
+    pts = orc.ray_points(fx["ray_batch"][:, :3], fx["ray_batch"][:, 3:6], fx["st.z.0"])
+    sk_all = skts.expand(N, -1, -1, -1)
+    want_d, want_v, _ = orc.anerf_inputs(pts, fx["ray_batch"][:, 3:6], fx["cams"], sk_all, align_A(), P, False, float(fx["tau"]))
+    # bf16 rounding (2^-9 relative) on top of the fp32 sensitivity of the top octave (see test_oracle_golden)
+    assert float((got_d - want_d).abs().max()) <= 4.5e-3, float((got_d - want_d).abs().max())
+    assert float((got_v - want_v[:, :648]).abs().max()) <= 4.5e-3
+    assert float((got_d - want_d).abs().mean()) <= 6e-4
+    # and against the reference's own tensors for the rays it kept
+    n_st = fx["st.v.0"].shape[0]
+    assert float((got_d[:n_st * S] - fx["st.density_inputs.0"]).abs().max()) <= 4.5e-3
+    assert float((got_v[:n_st * S] - fx["st.view_inputs.0"][:, :648]).abs().max()) <= 4.5e-3
+    # frame-code part of the view layer, fp32
+    Wv = P["views_linears.0.weight"]
+    want_cb = want_v[::S, 648:] @ Wv[:, 448 + 648:].t() + P["views_linears.0.bias"]
+    close(cb.cpu(), want_cb, 2e-5, "code bias")
+
+
+def test_anerf_mlp():
+    """mlp_kernel (CTA pairs, W = 448) on the embed kernel's rows: against a bf16-emulating restatement (tight) and
+    the fp32 oracle / reference raw (bf16 tolerance)."""
+    fx = load_fixture("render_anerf")
+    caster, args, P = make_anerf_caster(fx)
+    skts, bones, cyl = pose_tensors(fx)
+    rb = fx["ray_batch"].to(DEV)
+    N, S = rb.shape[0], int(fx["N_samples"])
+    packed = caster._packed_mlp()
+    align = caster._align()
+    cams = fx["cams"].reshape(-1).to(DEV).to(torch.int32)
+    enc, cb = K().anerf_ray_encode(rb, skts.to(DEV).contiguous(), N, cams, caster._codes_with_mean(), packed)
+    z = fx["st.z.0"].to(DEV).contiguous()
+    xd, xv = K().anerf_embed(rb, S, z, skts.to(DEV).contiguous(), N, align, enc, float(fx["tau"]))
+    raw = torch.full((N * S + N, 4), float("nan"), device=DEV)
+    K().anerf_mlp(xd, xv, packed, cb, N * S, S, raw)
+    torch.cuda.synchronize()
+    got = raw[:N * S].cpu()
+    assert torch.isfinite(got).all()
+    xd_f = decode_tile_image(xd, N * S, 7, 432).cpu()
+    xv_f = decode_tile_image(xv, N * S, 11, 648).cpu()
+    emu = anerf_mlp_bf16_reference(xd_f, xv_f, cb.cpu().repeat_interleave(S, 0), P)
+    scale = float(emu.abs().max())
+    err = (got - emu).abs()
+    print(f"[anerf mlp] vs bf16 emulation: max {float(err.max()):.3e} mean {float(err.mean()):.3e} scale {scale:.3e}")
+    assert float(err.mean()) <= 2e-4 * scale and float(err.max()) <= 2e-2 * scale
+    want = fx["st.raw.0"].reshape(N * S, 4)
+    err32 = (got - want).abs()
+    print(f"[anerf mlp] vs reference fp32: max {float(err32.max()):.3e} mean {float(err32.mean()):.3e}")
+    assert float(err32.max()) <= 5e-2 * scale and float(err32.mean()) <= 6e-3 * scale
+
+
+def test_anerf_render_end_to_end():
+    """create_raycaster(nerf_type='nerf') -> ray_caster(...) against the reference's rendered pixels."""
+    fx = load_fixture("render_anerf")
+    caster, args, P = make_anerf_caster(fx)
+    skts, bones, cyl = pose_tensors(fx)
+    rb = fx["ray_batch"].to(DEV)
+    N = rb.shape[0]
+    e = lambda t: t.to(DEV).expand(N, *t.shape[1:])
+    st = {}
+    ret = caster(rb, N_samples=args.N_samples, kp_batch=e(fx["pose_kps"][None]), skts=e(skts), cyls=e(cyl), bones=e(bones),
+                 cams=fx["cams"].to(DEV), N_uniques=1, perturb=False, N_importance=args.N_importance, raw_noise_std=0.,
+                 nerf_type="nerf", _stages=st)
+    close(st["near"].cpu(), fx["st.near.0"].reshape(-1), 1e-6, "near")
+    assert torch.equal(st["z_coarse"].cpu(), fx["st.z.0"])
+    for k, tol_mean, tol_max in (("rgb0", 3e-3, 3e-2), ("acc0", 3e-3, 3e-2), ("rgb_map", 4e-3, 5e-2), ("acc_map", 4e-3, 5e-2)):
+        d = (ret[k].cpu() - fx["out." + k]).abs()
+        print(f"[anerf e2e] {k}: mean {float(d.mean()):.3e} max {float(d.max()):.3e}")
+        assert float(d.mean()) <= tol_mean and float(d.max()) <= tol_max, (k, float(d.mean()), float(d.max()))
+    # train mode is not part of this path
+    caster.train()
+    with pytest.raises(NotImplementedError):
+        caster(rb, N_samples=args.N_samples, kp_batch=e(fx["pose_kps"][None]), skts=e(skts), cyls=e(cyl), bones=e(bones),
+               cams=fx["cams"].to(DEV), N_uniques=1, perturb=False, N_importance=args.N_importance, nerf_type="nerf")

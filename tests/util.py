@@ -103,3 +103,33 @@ def mlp_bf16_reference(x, view_bias, P):
     g = torch.relu(feat @ bf(P["views_linears.0.weight"][:, :256]).t() + view_bias)
     rgb = g @ P["rgb_linear.weight"].t() + P["rgb_linear.bias"]
     return torch.cat([rgb, sigma], -1)
+
+
+def decode_tile_image(buf, n_rows, n_chunks, n_cols):
+    """uint8 operand tile images ([tile][chunk][128 rows x 64 k] bf16, 128B-swizzled) -> float32 (n_rows, n_cols)."""
+    off = torch.from_numpy(sw128_offsets(n_chunks * 64).astype(np.int64)).to(buf.device)
+    n_tiles = (n_rows + 127) // 128
+    tile_bytes = n_chunks * 16384
+    words = buf[: n_tiles * tile_bytes].view(torch.int16).view(n_tiles, tile_bytes // 2)
+    idx = (off // 2).reshape(1, -1).expand(n_tiles, -1)
+    vals = torch.gather(words, 1, idx).reshape(n_tiles * 128, n_chunks * 64)
+    return vals.view(torch.bfloat16).float()[:n_rows, :n_cols]
+
+
+def anerf_mlp_bf16_reference(xd, xv, code_bias, P):
+    """The A-NeRF kernel's arithmetic restated in torch: bf16 operands and stored activations, fp32 accumulation,
+    sigma / rgb heads in fp32 from the unrounded last activations."""
+    bf = lambda t: t.to(torch.bfloat16).float()
+    xb = bf(xd)
+    h, a = xb, None
+    for i in range(8):
+        a = torch.relu(h @ bf(P[f"pts_linears.{i}.weight"]).t() + P[f"pts_linears.{i}.bias"])
+        h = bf(a)
+        if i == 4:
+            h = torch.cat([xb, h], -1)
+    sigma = a @ P["alpha_linear.weight"].t() + P["alpha_linear.bias"]
+    feat = bf(h @ bf(P["feature_linear.weight"]).t() + P["feature_linear.bias"])
+    Wv = P["views_linears.0.weight"]
+    g = torch.relu(feat @ bf(Wv[:, :448]).t() + bf(xv) @ bf(Wv[:, 448:448 + 648]).t() + code_bias)
+    rgb = g @ P["rgb_linear.weight"].t() + P["rgb_linear.bias"]
+    return torch.cat([rgb, sigma], -1)
