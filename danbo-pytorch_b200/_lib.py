@@ -22,7 +22,7 @@ _SIGNATURES = {
     "danbo_anerf_pack_weights": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "danbo_anerf_ray_encode": [c_p, c_i, c_i, c_p, c_i, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p],
     "danbo_anerf_embed": [c_p, c_i, c_i, c_p, c_i, c_p, c_i, c_i, c_p, c_p, c_f, c_p, c_p, c_p],
-    "danbo_anerf_mlp": [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_i, c_i, c_p],
+    "danbo_anerf_mlp": [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_i, c_i, c_p, c_p],
     "danbo_pack_mlp_weights": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "danbo_mlp_forward": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_i, c_i, c_i, c_p],
     "danbo_mlp_forward_trace": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_i, c_i, c_i, c_p, c_p],

@@ -35,9 +35,10 @@ constexpr int kXD = 432, kChunksD = 7;   // density input, K padded to 448
 constexpr int kXV = 648, kChunksV = 11;  // view input (without the frame code), K padded to 704
 constexpr int kChunkBytes = 16384;       // [128 rows x 64 k] bf16
 constexpr int kBBytes = kQuartN * 128;   // [112 rows x 64 k] bf16 = 14 336
-constexpr int kSlotBytes = kChunkBytes + kBBytes;     // 30 720 (multiple of 1024)
-constexpr int kSlots = 7;
-constexpr int kStages = 158;             // per tile: 14 + 4*14 + 28 + 14 + 14 + 14 + 18
+constexpr int kSlotBytes = 2 * (kChunkBytes + kBBytes);   // a ring slot holds up to TWO k-chunks: A (32 KB) then B (28 KB)
+constexpr int kSlots = 3;
+constexpr int kStages = 158;             // k-chunks per tile: 14 + 4*14 + 28 + 14 + 14 + 14 + 18
+constexpr int kGroups = 90;              // ring stages per tile (groups of one or two k-chunks), 30 per slot
 constexpr int kThreads = 352;            // warp 0 A producer, 1 MMA issuer / relay, 2-9 epilogue, 10 B producer
 constexpr int kActBytes = kChunksD * kChunkBytes;     // one activation tile image (114 688)
 constexpr float kCutoff = 0.5f;          // cutoff_mm * ext_scale (run_nerf.py:498, encoders.py:62)
@@ -53,8 +54,26 @@ __host__ __device__ constexpr int n_pass(int L) { return L == 9 ? 1 : 2; }
 __host__ __device__ constexpr int stage_base(int L) {
     return L <= 5 ? 14 * L : (L == 6 ? 98 : (L == 7 ? 112 : (L == 8 ? 126 : 140)));
 }
-// uses of ring slot `slot` per tile (158 = 22 * 7 + 4)
-__host__ __device__ constexpr int slot_uses(int slot) { return slot < 4 ? 23 : 22; }
+// A bulk copy costs its issuing warp ~330 clk whatever its size (scripts/micro/bulk_rate.cu), and one k-chunk is only
+// 448 clk of MMAs: ring stages are therefore GROUPS of up to two k-chunks (one copy of A and one of B per group).
+// The 7 chunks of an input run split (0,1)(2,3)(4,5)(6); the 7 chunks of an activation run split (0,1)(2)(3,4)(5,6) so
+// that chunk 3 -- the first one holding columns of the previous layer's second pass -- starts a group; the 11 view
+// chunks split (0,1)...(8,9)(10).
+__host__ __device__ constexpr int groups_per_pass(int L) { return L == 5 ? 8 : (L == 9 ? 10 : 4); }
+__host__ __device__ constexpr int group_base(int L) {
+    return L <= 5 ? 8 * L : (L == 6 ? 56 : (L == 7 ? 64 : (L == 8 ? 72 : 80)));
+}
+__host__ __device__ constexpr bool first_run_is_input(int L) { return L == 0 || L == 5; }
+__host__ __device__ constexpr int act_group_kc(int g) { return g == 0 ? 0 : (g == 1 ? 2 : (g == 2 ? 3 : 5)); }
+// first k-chunk (layer-local) and number of chunks of group gi of a pass of layer L
+__host__ __device__ constexpr int group_kc0(int L, int gi) {
+    return gi < 4 ? (first_run_is_input(L) ? 2 * gi : act_group_kc(gi))
+                  : 7 + (L == 5 ? act_group_kc(gi - 4) : 2 * (gi - 4));
+}
+__host__ __device__ constexpr int group_nch(int L, int gi) {
+    return gi < 4 ? (first_run_is_input(L) ? (gi == 3 ? 1 : 2) : (gi == 1 ? 1 : 2))
+                  : (L == 5 ? (gi - 4 == 1 ? 1 : 2) : (gi - 4 == 5 ? 1 : 2));
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // per-ray quantities
@@ -262,6 +281,8 @@ __global__ void pack_kernel(PackArgs a, __nv_bfloat16* __restrict__ wstream, flo
 // the MLP
 struct __align__(1024) Smem {
     uint8_t ring[kSlots][kSlotBytes];    // per slot: A chunk (16 KB) then this CTA's B rows (14 KB)
+    uint8_t stage[8][4096];              // per epilogue warp: 32 rows x 8 units of 16 B, to turn row-per-lane stores into line-wide ones
+    float head_w[kW + 3 * kViewW];       // w_alpha, W_rgb
     float4 part[DANBO_TILE_M];
     uint64_t w_full[kSlots];
     uint64_t w_empty[kSlots];
@@ -301,6 +322,8 @@ struct EpiCtx {
     uint32_t free_addr;        // leader's acc_free[h], shared::cluster address
     uint64_t* written_bar;     // local act_written[h] (null: this layer writes no activation)
     uint8_t* act_out;          // this CTA's activation tile image of the layer being produced
+    uint32_t stage;            // shared::cta address of this warp's 4 KB staging block
+    long long* dslot;          // profiling aid: 4 clock64 stamps of this call (null when not tracing)
 };
 
 // One thread's 112 columns (two rounds of 56) of one accumulator half.
@@ -316,12 +339,13 @@ __device__ __forceinline__ void epi_half(const EpiCtx& E, int h, const float* __
         float4 b[14];
 #pragma unroll
         for (int i = 0; i < 14; ++i) b[i] = __ldg(reinterpret_cast<const float4*>(bias + rd * 56) + i);
-        if (rd == 0) { mbar_wait(E.acc_bar, E.acc_phase); tc_fence_after(); }
+        if (rd == 0) { mbar_wait(E.acc_bar, E.acc_phase); tc_fence_after(); if (E.dslot) E.dslot[0] = clock64(); }
         uint32_t v[56];
         tmem_ld32p(acc + rd * 56, v);
         tmem_ld16(acc + rd * 56 + 32, v + 32);
         tmem_ld8(acc + rd * 56 + 48, v + 48);
         tmem_wait_ld();
+        if (E.dslot) E.dslot[1 + rd] = clock64();
         if (rd == 1) {                                  // accumulator half drained: the next pass may overwrite it
             tc_fence_before();
             __syncwarp();
@@ -333,7 +357,7 @@ __device__ __forceinline__ void epi_half(const EpiCtx& E, int h, const float* __
             float a0 = __uint_as_float(v[4 * i + 0]) + b[i].x, a1 = __uint_as_float(v[4 * i + 1]) + b[i].y;
             float a2 = __uint_as_float(v[4 * i + 2]) + b[i].z, a3 = __uint_as_float(v[4 * i + 3]) + b[i].w;
             if (kKind == 1) {
-                const float4 wa = __ldg(reinterpret_cast<const float4*>(head_w + rd * 56) + i);
+                const float4 wa = reinterpret_cast<const float4*>(head_w + rd * 56)[i];
                 part[0] = fmaf(fmaxf(a0, 0.f), wa.x, part[0]); part[1] = fmaf(fmaxf(a1, 0.f), wa.y, part[1]);
                 part[2] = fmaf(fmaxf(a2, 0.f), wa.z, part[2]); part[3] = fmaf(fmaxf(a3, 0.f), wa.w, part[3]);
             }
@@ -341,7 +365,7 @@ __device__ __forceinline__ void epi_half(const EpiCtx& E, int h, const float* __
                 a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f);
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    const float4 wr = __ldg(reinterpret_cast<const float4*>(head_w + k * kViewW + rd * 56) + i);
+                    const float4 wr = reinterpret_cast<const float4*>(head_w + k * kViewW + rd * 56)[i];
                     rgb[k] = fmaf(a0, wr.x, rgb[k]); rgb[k] = fmaf(a1, wr.y, rgb[k]);
                     rgb[k] = fmaf(a2, wr.z, rgb[k]); rgb[k] = fmaf(a3, wr.w, rgb[k]);
                 }
@@ -352,29 +376,53 @@ __device__ __forceinline__ void epi_half(const EpiCtx& E, int h, const float* __
             }
         }
         if (kKind != 3) {
+            // A lane owns a row, and a row's 16-byte units land in different 128-byte lines of the operand image: stored
+            // directly, every STG touches 32 lines (the LSU needs a pass per line; 2 500 clk per round, measured).  Stage
+            // the warp's 32 x 7 units in shared memory and copy them out 4 rows per instruction instead.
             const int col0 = h * kHalfN + E.ch * kQuartN + rd * 56;
 #pragma unroll
             for (int pc = 0; pc < 7; ++pc) {
-                const int c = col0 + 8 * pc, chunk = c >> 6, k = c & 63;
-                uint8_t* dst = E.act_out + chunk * kChunkBytes + (E.row >> 3) * 1024 + (E.row & 7) * 128 + (((k >> 3) ^ (E.row & 7)) << 4);
-                *reinterpret_cast<uint4*>(dst) = make_uint4(pk[4 * pc], pk[4 * pc + 1], pk[4 * pc + 2], pk[4 * pc + 3]);
+                const uint32_t a = E.stage + (uint32_t)(E.lane * 128 + ((pc ^ (E.lane & 7)) << 4));
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(pk[4 * pc]), "r"(pk[4 * pc + 1]), "r"(pk[4 * pc + 2]), "r"(pk[4 * pc + 3]) : "memory");
             }
+            __syncwarp();
+            const int u = E.lane & 7;
+            const int c = col0 + 8 * u, chunk = c >> 6, k = c & 63;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rr = 4 * i + (E.lane >> 3);
+                if (u < 7) {
+                    uint4 val;
+                    const uint32_t a = E.stage + (uint32_t)(rr * 128 + ((u ^ (rr & 7)) << 4));
+                    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w) : "r"(a) : "memory");
+                    const int rowg = (E.row & ~31) + rr;
+                    uint8_t* dst = E.act_out + chunk * kChunkBytes + (rowg >> 3) * 1024 + (rowg & 7) * 128 + (((k >> 3) ^ (rowg & 7)) << 4);
+                    *reinterpret_cast<uint4*>(dst) = val;
+                }
+            }
+            __syncwarp();
         }
     }
     if (kKind == 1) alpha += (part[0] + part[1]) + (part[2] + part[3]);
+    if (E.dslot) E.dslot[3] = clock64();
     if (kKind != 3) {
-        // generic-proxy stores -> visible to the bulk (async proxy) loads of this CTA's A producer
-        __threadfence();
-        asm volatile("fence.proxy.async;" ::: "memory");
+        // generic-proxy stores -> visible to the bulk (async proxy) loads of this CTA's A producer.  One lane fences for
+        // the warp (bar.warp.sync orders the other lanes' stores before it); release only: an acq_rel fence also
+        // invalidates the SM's L1 (CCTL.IVALL) and cost ~8 000 clk per pass when every thread issued it (measured).
         __syncwarp();
-        if (E.lane == 0) mbar_arrive(E.written_bar);
+        if (E.lane == 0) {
+            asm volatile("fence.release.gpu;" ::: "memory");
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+            mbar_arrive(E.written_bar);
+        }
     }
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_kernel(const uint8_t* __restrict__ xd, const uint8_t* __restrict__ xv, const uint8_t* __restrict__ wstream,
            const float* __restrict__ heads, const float* __restrict__ code_bias, uint8_t* __restrict__ scratch,
-           float* __restrict__ out /* raw (rows,4) */, int n_rows, int S, int out_capacity) {
+           float* __restrict__ out /* raw (rows,4) */, int n_rows, int S, int out_capacity,
+           long long* __restrict__ trace /* optional clock64 timeline of CTA 0: [2 tiles][2 roles][20][2], or null */) {
     extern __shared__ uint8_t smem_raw[];
     Smem& Sm = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -385,6 +433,7 @@ mlp_kernel(const uint8_t* __restrict__ xd, const uint8_t* __restrict__ xv, const
     const int n_work = (n_tiles + 1) / 2;
     uint8_t* act_buf = scratch + (size_t)blockIdx.x * (2 * kActBytes);
 
+    for (int i = threadIdx.x; i < kW + 3 * kViewW; i += kThreads) Sm.head_w[i] = heads[kHeadWAlpha + i];
     if (threadIdx.x == 0) {
         for (int s = 0; s < kSlots; ++s) { mbar_init(&Sm.w_full[s], lead_cta ? 3 : 2); mbar_init(&Sm.w_empty[s], 1); }
         mbar_init(&Sm.acc_full[0], 1); mbar_init(&Sm.acc_full[1], 1);
@@ -401,6 +450,8 @@ mlp_kernel(const uint8_t* __restrict__ xd, const uint8_t* __restrict__ xv, const
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem = Sm.tmem_base;
+    const bool tr = trace != nullptr && blockIdx.x == 0;
+#define ANERF_TRACE(it, role, L, h, which) do { if (tr && (it) < 2) trace[(((it) * 2 + (role)) * 20 + (L) * 2 + (h)) * 2 + (which)] = clock64(); } while (0)
 
     if (warp == 0 || warp == 10) {
         // ===== producers: warp 0 streams the A operand (input / activation chunks), warp 10 this CTA's B rows =====
@@ -417,10 +468,11 @@ mlp_kernel(const uint8_t* __restrict__ xd, const uint8_t* __restrict__ xv, const
                 const uint8_t* act_in = act_buf + ((L - 1) & 1) * kActBytes;
                 const uint32_t wr_par = (uint32_t)(9 * it + L - 1) & 1u;       // act_written completions: 9 per tile
                 for (int h = 0; h < n_pass(L); ++h) {
-                    for (int kc = 0; kc < n_k(L); ++kc, ++s) {
+                    for (int gi = 0; gi < groups_per_pass(L); ++gi, ++s) {
                         const int slot = s % kSlots;
-                        const uint32_t use = (uint32_t)(it * slot_uses(slot) + s / kSlots);
+                        const uint32_t use = (uint32_t)(s / kSlots);            // 30 uses per slot per tile: parity repeats
                         mbar_wait(&Sm.w_empty[slot], (use & 1u) ^ 1u);
+                        const int kc = group_kc0(L, gi), nch = group_nch(L, gi);
                         if (is_a) {
                             const uint8_t* src;
                             int ka = -1;                                        // activation chunk index, if any
@@ -430,13 +482,15 @@ mlp_kernel(const uint8_t* __restrict__ xd, const uint8_t* __restrict__ xv, const
                             else { ka = kc; src = act_in + ka * kChunkBytes; }
                             if (h == 0 && ka == 0) mbar_wait(&Sm.act_written[0], wr_par);   // columns 0..223 of the previous layer
                             if (h == 0 && ka == 3) mbar_wait(&Sm.act_written[1], wr_par);   // chunk 3 straddles the halves
+                            if (ka >= 0) asm volatile("fence.proxy.async.global;" ::: "memory");
                             if (leader) {
-                                mbar_expect_tx(&Sm.w_full[slot], kChunkBytes);
-                                bulk_g2s(Sm.ring[slot], src, kChunkBytes, &Sm.w_full[slot]);
+                                mbar_expect_tx(&Sm.w_full[slot], nch * kChunkBytes);
+                                bulk_g2s(Sm.ring[slot], src, nch * kChunkBytes, &Sm.w_full[slot]);
                             }
                         } else if (leader) {
-                            mbar_expect_tx(&Sm.w_full[slot], kBBytes);
-                            bulk_g2s(Sm.ring[slot] + kChunkBytes, wsrc + (size_t)s * kBBytes, kBBytes, &Sm.w_full[slot]);
+                            const int chunk_idx = stage_base(L) + h * n_k(L) + kc;          // position in the B stream
+                            mbar_expect_tx(&Sm.w_full[slot], nch * kBBytes);
+                            bulk_g2s(Sm.ring[slot] + 2 * kChunkBytes, wsrc + (size_t)chunk_idx * kBBytes, nch * kBBytes, &Sm.w_full[slot]);
                         }
                         __syncwarp();
                     }
@@ -447,10 +501,9 @@ mlp_kernel(const uint8_t* __restrict__ xd, const uint8_t* __restrict__ xv, const
         // ===== peer CTA: forward "both of my copies of this stage have landed" to the leader =====
         const uint32_t w_full_lead = mapa_cluster(smem_u32(&Sm.w_full[0]), 0);
         for (int w = unit, it = 0; w < n_work; w += n_units, ++it) {
-            for (int s = 0; s < kStages; ++s) {
+            for (int s = 0; s < kGroups; ++s) {
                 const int slot = s % kSlots;
-                const uint32_t use = (uint32_t)(it * slot_uses(slot) + s / kSlots);
-                mbar_wait(&Sm.w_full[slot], use & 1u);
+                mbar_wait(&Sm.w_full[slot], (uint32_t)(s / kSlots) & 1u);
                 if (lane == 0) mbar_arrive_cluster(w_full_lead + 8u * slot);
                 __syncwarp();
             }
@@ -461,7 +514,6 @@ mlp_kernel(const uint8_t* __restrict__ xd, const uint8_t* __restrict__ xv, const
         const uint64_t desc0 = make_desc(0) | (uint64_t)((smem_u32(&Sm.ring[0][0]) >> 4) & 0x3FFF);
         constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t(kHalfN) >> 3) << 17) | ((256u >> 4) << 24);
         for (int w = unit, it = 0; w < n_work; w += n_units, ++it) {
-            const uint32_t flip = (uint32_t)it & 1u;
 #pragma unroll
             for (int L = 0; L < 10; ++L) {
 #pragma unroll
@@ -478,25 +530,31 @@ mlp_kernel(const uint8_t* __restrict__ xd, const uint8_t* __restrict__ xv, const
                     tc_fence_after();
                     const uint32_t d = tmem + 256u * h;
 #pragma unroll
-                    for (int kc = 0; kc < 18; ++kc) {
-                        if (kc >= n_k(L)) continue;
-                        const int s = stage_base(L) + h * n_k(L) + kc;
+                    for (int gi = 0; gi < 10; ++gi) {
+                        if (gi >= groups_per_pass(L)) continue;
+                        const int s = group_base(L) + h * groups_per_pass(L) + gi;
                         const int slot = s % kSlots;
-                        const uint32_t par = ((uint32_t)(s / kSlots) & 1u) ^ ((slot_uses(slot) & 1) ? flip : 0u);
-                        mbar_wait(&Sm.w_full[slot], par);
+                        mbar_wait(&Sm.w_full[slot], (uint32_t)(s / kSlots) & 1u);
                         tc_fence_after();
+                        if (gi == 0) { ANERF_TRACE(it, 0, L, h, 0); }
                         const uint64_t adesc = desc0 + (uint64_t)((slot * kSlotBytes) >> 4);
-                        const uint64_t bdesc = desc0 + (uint64_t)((slot * kSlotBytes + kChunkBytes) >> 4);
+                        const uint64_t bdesc = desc0 + (uint64_t)((slot * kSlotBytes + 2 * kChunkBytes) >> 4);
                         if (leader) {
-                            mma_ss_pair(d, adesc, bdesc, idesc, kc > 0 ? 1u : 0u);
-                            mma_ss_pair(d, adesc + 2, bdesc + 2, idesc, 1u);
-                            mma_ss_pair(d, adesc + 4, bdesc + 4, idesc, 1u);
-                            mma_ss_pair(d, adesc + 6, bdesc + 6, idesc, 1u);
+#pragma unroll
+                            for (int c = 0; c < 2; ++c) {
+                                if (c >= group_nch(L, gi)) continue;
+                                const uint64_t ad = adesc + (uint64_t)((c * kChunkBytes) >> 4), bd = bdesc + (uint64_t)((c * kBBytes) >> 4);
+                                mma_ss_pair(d, ad, bd, idesc, (gi > 0 || c > 0) ? 1u : 0u);
+                                mma_ss_pair(d, ad + 2, bd + 2, idesc, 1u);
+                                mma_ss_pair(d, ad + 4, bd + 4, idesc, 1u);
+                                mma_ss_pair(d, ad + 6, bd + 6, idesc, 1u);
+                            }
                             tc_commit_pair(&Sm.w_empty[slot]);
-                            if (kc == n_k(L) - 1) tc_commit_pair(&Sm.acc_full[h]);
+                            if (gi == groups_per_pass(L) - 1) tc_commit_pair(&Sm.acc_full[h]);
                         }
                         __syncwarp();
                     }
+                    ANERF_TRACE(it, 0, L, h, 1);
                 }
             }
         }
@@ -508,6 +566,7 @@ mlp_kernel(const uint8_t* __restrict__ xd, const uint8_t* __restrict__ xv, const
         E.lane = lane;
         E.row = q * 32 + lane;
         E.tmem_lane = tmem + ((uint32_t)(q * 32) << 16);
+        E.stage = smem_u32(Sm.stage[warp - 2]);
         const uint32_t free_addr[2] = {mapa_cluster(smem_u32(&Sm.acc_free[0]), 0), mapa_cluster(smem_u32(&Sm.acc_free[1]), 0)};
         const float* tail = heads + kHeadTail;
         for (int w = unit, it = 0; w < n_work; w += n_units, ++it) {
@@ -525,10 +584,13 @@ mlp_kernel(const uint8_t* __restrict__ xd, const uint8_t* __restrict__ xv, const
                     E.written_bar = &Sm.act_written[h];
                     E.act_out = act_buf + (L & 1) * kActBytes;
                     const int coff = h * kHalfN + E.ch * kQuartN;
+                    if (warp == 2 && lane == 0) { ANERF_TRACE(it, 1, L, h, 0); }
+                    E.dslot = (tr && it < 2 && warp == 2 && lane == 0) ? trace + 160 + ((it * 20 + L * 2 + h) * 4) : nullptr;
                     if (L < 7) epi_half<0>(E, h, heads + kHeadBias + L * kW + coff, nullptr, alpha, rgb);
-                    else if (L == 7) epi_half<1>(E, h, heads + kHeadBias + L * kW + coff, heads + kHeadWAlpha + coff, alpha, rgb);
+                    else if (L == 7) epi_half<1>(E, h, heads + kHeadBias + L * kW + coff, Sm.head_w + coff, alpha, rgb);
                     else if (L == 8) epi_half<2>(E, h, heads + kHeadBias + L * kW + coff, nullptr, alpha, rgb);
-                    else epi_half<3>(E, 0, code_bias + (size_t)ray * kViewW + E.ch * kQuartN, heads + kHeadWRgb + E.ch * kQuartN, alpha, rgb);
+                    else epi_half<3>(E, 0, code_bias + (size_t)ray * kViewW + E.ch * kQuartN, Sm.head_w + kW + E.ch * kQuartN, alpha, rgb);
+                    if (warp == 2 && lane == 0) { ANERF_TRACE(it, 1, L, h, 1); }
                 }
             }
             if (E.ch == 1) Sm.part[E.row] = make_float4(rgb[0], rgb[1], rgb[2], alpha);
@@ -597,7 +659,7 @@ extern "C" int danbo_anerf_embed(const float* rays, int ray_stride, int S, const
 
 extern "C" int danbo_anerf_mlp(const void* xd, const void* xv, const void* wstream, const float* heads,
                                const float* code_bias, void* scratch, int n_rows, int S, float* out, int out_capacity,
-                               int num_sms, void* stream) {
+                               int num_sms, long long* trace, void* stream) {
     if (n_rows <= 0) return 0;
     if (num_sms < 2) return -1;
     const int smem = (int)sizeof(anerf::Smem) + 1024;
@@ -619,7 +681,7 @@ extern "C" int danbo_anerf_mlp(const void* xd, const void* xv, const void* wstre
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, anerf::mlp_kernel, (const uint8_t*)xd, (const uint8_t*)xv, (const uint8_t*)wstream,
-                                       heads, code_bias, (uint8_t*)scratch, out, n_rows, S, out_capacity);
+                                       heads, code_bias, (uint8_t*)scratch, out, n_rows, S, out_capacity, trace);
     if (e != cudaSuccess) return (int)e;
     DANBO_CHECK_LAUNCH();
     return 0;

@@ -581,14 +581,15 @@ def anerf_embed(rays, S, z, pose_skts, rays_per_pose, align, ray_enc, tau, xd=No
     return xd, xv
 
 
-def anerf_mlp(xd, xv, packed, code_bias, rows, S, out):
-    """out (>= rows, 4) <- [rgb, sigma] of the dense rows."""
+def anerf_mlp(xd, xv, packed, code_bias, rows, S, out, trace=None):
+    """out (>= rows, 4) <- [rgb, sigma] of the dense rows.  trace: optional int64 CUDA tensor (320) for a clock64 timeline."""
     _need_cuda(xd, xv, code_bias, out)
     lib = _lib.load()
     idx = out.device.index if out.device.index is not None else torch.cuda.current_device()
     with _Timed("anerf_mlp"):
         _lib.check(lib.danbo_anerf_mlp(_p(xd), _p(xv), _p(packed.wstream), _p(packed.heads), _p(code_bias),
-                                       _p(packed.scratch), int(rows), int(S), _p(out), out.shape[0], num_sms(idx), _stream()),
+                                       _p(packed.scratch), int(rows), int(S), _p(out), out.shape[0], num_sms(idx),
+                                       _p(trace), _stream()),
                    "danbo_anerf_mlp")
     _count(1)
     return out

@@ -212,9 +212,12 @@ int danbo_anerf_embed(const float* rays, int ray_stride, int S, const float* z, 
                       int rays_per_pose, int n_poses, const float* align, const float* ray_enc, float tau, void* xd,
                       void* xv, void* stream);
 
-/* The 8 x 448 MLP + heads on n_rows rows: out (rows,4) = [rgb, sigma].  One persistent launch over CTA pairs. */
+/* The 8 x 448 MLP + heads on n_rows rows: out (rows,4) = [rgb, sigma].  One persistent launch over CTA pairs.
+ * trace: NULL, or 320 long long receiving a clock64 timeline of CTA 0 ([2 tiles][issuer, epilogue][layer, pass][begin,
+ * end], then [2 tiles][layer, pass][4 stamps inside one epilogue warp]; profiling aid). */
 int danbo_anerf_mlp(const void* xd, const void* xv, const void* wstream, const float* heads, const float* code_bias,
-                    void* scratch, int n_rows, int S, float* out, int out_capacity, int num_sms, void* stream);
+                    void* scratch, int n_rows, int S, float* out, int out_capacity, int num_sms, long long* trace,
+                    void* stream);
 
 #ifdef __cplusplus
 }
