@@ -120,96 +120,135 @@ ray_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, const flo
 
 // ------------------------------------------------------------------------------------------------------------
 // per-sample encodings -> operand tile images
+// One block = one 128-row tile.  A lane owns a row, and a row's 16-byte units lie in different 128-byte lines of the
+// image, so direct global stores cost one LSU pass per lane (the kernel was store-issue bound at 150 ms per 1024^2
+// image).  The image is therefore assembled in shared memory (same swizzled layout: conflict-free 16-byte stores) and
+// leaves as bulk copies: xd (112 KB), then the view image in two parts (112 KB + 64 KB).
+constexpr int kEmbedStage = kChunksD * kChunkBytes;          // 112 KB of dynamic shared memory
+
 __device__ __forceinline__ void emit_piece(uint8_t* __restrict__ tile, int rr, int col0, const float (&v)[8]) {
     const int chunk = col0 >> 6, k = col0 & 63;
-    uint8_t* dst = tile + chunk * kChunkBytes + (rr >> 3) * 1024 + (rr & 7) * 128 + (((k >> 3) ^ (rr & 7)) << 4);
-    *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
-                                                pack_bf16(v[6], v[7]));
+    const uint32_t dst = smem_u32(tile) + chunk * kChunkBytes + (rr >> 3) * 1024 + (rr & 7) * 128 + (((k >> 3) ^ (rr & 7)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pack_bf16(v[0], v[1])), "r"(pack_bf16(v[2], v[3])),
+                 "r"(pack_bf16(v[4], v[5])), "r"(pack_bf16(v[6], v[7])) : "memory");
+}
+
+// all threads: make the staged image visible to the async proxy, then one thread sends it to global memory
+__device__ __forceinline__ void flush_stage(uint8_t* stage, uint8_t* gdst, uint32_t bytes) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(stage)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the stage may be overwritten
+    }
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(128)
 embed_kernel(const float* __restrict__ rays, int ray_stride, int S, const float* __restrict__ z, int n_rows,
              const float* __restrict__ pose_skts, int rays_per_pose, int n_poses, const float* __restrict__ align,
              const float* __restrict__ ray_enc, float tau, uint8_t* __restrict__ xd, uint8_t* __restrict__ xv) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;          // grid covers whole tiles
-    const int tile = e >> 7, rr = e & 127;
-    uint8_t* td = xd + (size_t)tile * (kChunksD * kChunkBytes);
-    uint8_t* tv = xv + (size_t)tile * (kChunksV * kChunkBytes);
+    extern __shared__ uint8_t embed_raw[];
+    uint8_t* stage = embed_raw + ((1024u - (smem_u32(embed_raw) & 1023u)) & 1023u);
+    const int tile = blockIdx.x, rr = threadIdx.x;
+    const int e = tile * DANBO_TILE_M + rr;
+    uint8_t* gd = xd + (size_t)tile * (kChunksD * kChunkBytes);
+    uint8_t* gv = xv + (size_t)tile * (kChunksV * kChunkBytes);
     const float zero8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (e >= n_rows) {                                              // rows of the last tile beyond the data: zeros
-        for (int c = 0; c < kChunksD * 64; c += 8) emit_piece(td, rr, c, zero8);
-        for (int c = 0; c < kChunksV * 64; c += 8) emit_piece(tv, rr, c, zero8);
-        return;
-    }
-    const int n = e / S;
-    const float* r = rays + (size_t)n * ray_stride;
-    const float zz = z[e];
-    const float px = __fadd_rn(r[0], __fmul_rn(r[3], zz));
-    const float py = __fadd_rn(r[1], __fmul_rn(r[4], zz));
-    const float pz = __fadd_rn(r[2], __fmul_rn(r[5], zz));
-    int pose = n / rays_per_pose; if (pose >= n_poses) pose = n_poses - 1;
-    const float* skt = pose_skts + (size_t)pose * DANBO_J * 16;
+    const bool live = e < n_rows;                                 // rows of the last tile beyond the data: zeros
+    const int n = live ? e / S : 0;
     float w[DANBO_J], sn[DANBO_J], cs[DANBO_J];
-#pragma unroll
-    for (int g = 0; g < 3; ++g) {
-        float r8[3][8], iw[8];
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-            const int j = 8 * g + jj;
-            float q0, q1, q2;
-            bone_aligned(skt + j * 16, align + j * 16, px, py, pz, q0, q1, q2);      // T1 + T2
-            const float v = sqrtf(q0 * q0 + q1 * q1 + q2 * q2);                       // RelDistEncoder
-            const float den = fmaxf(v, 1e-12f);
-            r8[(3 * jj + 0) / 8][(3 * jj + 0) % 8] = __fdiv_rn(q0, den);            // VecNormEncoder (F.normalize)
-            r8[(3 * jj + 1) / 8][(3 * jj + 1) % 8] = __fdiv_rn(q1, den);
-            r8[(3 * jj + 2) / 8][(3 * jj + 2) % 8] = __fdiv_rn(q2, den);
-            w[j] = 1.f - 1.f / (1.f + expf(-tau * (v - kCutoff)));                   // cutoff_embedder.py:177-184
-            const float inp = kCutoff - v;                                            // cut_to_cutoff
-            iw[jj] = inp * w[j];
-            sincosf(inp * (2.f / kCutoff) - 1.f, &sn[j], &cs[j]);                     // shift_inputs, octave 0
-        }
-        emit_piece(td, rr, 8 * g, iw);                                                // PE row 0: (c - v) w
-        emit_piece(td, rr, 360 + 24 * g, r8[0]);                                      // unit vectors (bone_type reldir)
-        emit_piece(td, rr, 360 + 24 * g + 8, r8[1]);
-        emit_piece(td, rr, 360 + 24 * g + 16, r8[2]);
-    }
-#pragma unroll
-    for (int f = 0; f < 7; ++f) {                   // rows 1+2f (sin) and 2+2f (cos); next octave by the double-angle step
+    if (live) {
+        const float* r = rays + (size_t)n * ray_stride;
+        const float zz = z[e];
+        const float px = __fadd_rn(r[0], __fmul_rn(r[3], zz));
+        const float py = __fadd_rn(r[1], __fmul_rn(r[4], zz));
+        const float pz = __fadd_rn(r[2], __fmul_rn(r[5], zz));
+        int pose = n / rays_per_pose; if (pose >= n_poses) pose = n_poses - 1;
+        const float* skt = pose_skts + (size_t)pose * DANBO_J * 16;
 #pragma unroll
         for (int g = 0; g < 3; ++g) {
-            float a[8], b[8];
+            float r8[3][8], iw[8];
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) { a[jj] = sn[8 * g + jj] * w[8 * g + jj]; b[jj] = cs[8 * g + jj] * w[8 * g + jj]; }
-            emit_piece(td, rr, (1 + 2 * f) * 24 + 8 * g, a);
-            emit_piece(td, rr, (2 + 2 * f) * 24 + 8 * g, b);
+            for (int jj = 0; jj < 8; ++jj) {
+                const int j = 8 * g + jj;
+                float q0, q1, q2;
+                bone_aligned(skt + j * 16, align + j * 16, px, py, pz, q0, q1, q2);      // T1 + T2
+                const float v = sqrtf(q0 * q0 + q1 * q1 + q2 * q2);                       // RelDistEncoder
+                const float den = fmaxf(v, 1e-12f);
+                r8[(3 * jj + 0) / 8][(3 * jj + 0) % 8] = __fdiv_rn(q0, den);            // VecNormEncoder (F.normalize)
+                r8[(3 * jj + 1) / 8][(3 * jj + 1) % 8] = __fdiv_rn(q1, den);
+                r8[(3 * jj + 2) / 8][(3 * jj + 2) % 8] = __fdiv_rn(q2, den);
+                w[j] = 1.f - 1.f / (1.f + expf(-tau * (v - kCutoff)));                   // cutoff_embedder.py:177-184
+                const float inp = kCutoff - v;                                            // cut_to_cutoff
+                iw[jj] = inp * w[j];
+                sincosf(inp * (2.f / kCutoff) - 1.f, &sn[j], &cs[j]);                     // shift_inputs, octave 0
+            }
+            emit_piece(stage, rr, 8 * g, iw);                                             // PE row 0: (c - v) w
+            emit_piece(stage, rr, 360 + 24 * g, r8[0]);                                   // unit vectors (bone_type reldir)
+            emit_piece(stage, rr, 360 + 24 * g + 8, r8[1]);
+            emit_piece(stage, rr, 360 + 24 * g + 16, r8[2]);
         }
-        if (f < 6) {
 #pragma unroll
-            for (int j = 0; j < DANBO_J; ++j) {
-                const float s2 = 2.f * sn[j] * cs[j];
-                cs[j] = 1.f - 2.f * sn[j] * sn[j];
-                sn[j] = s2;
+        for (int f = 0; f < 7; ++f) {               // rows 1+2f (sin) and 2+2f (cos); next octave by the double-angle step
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+                float a[8], b[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) { a[jj] = sn[8 * g + jj] * w[8 * g + jj]; b[jj] = cs[8 * g + jj] * w[8 * g + jj]; }
+                emit_piece(stage, rr, (1 + 2 * f) * 24 + 8 * g, a);
+                emit_piece(stage, rr, (2 + 2 * f) * 24 + 8 * g, b);
+            }
+            if (f < 6) {
+#pragma unroll
+                for (int j = 0; j < DANBO_J; ++j) {
+                    const float s2 = 2.f * sn[j] * cs[j];
+                    cs[j] = 1.f - 2.f * sn[j] * sn[j];
+                    sn[j] = s2;
+                }
             }
         }
+        emit_piece(stage, rr, 432, zero8);
+        emit_piece(stage, rr, 440, zero8);
+    } else {
+#pragma unroll
+        for (int j = 0; j < DANBO_J; ++j) w[j] = 0.f;
+        for (int c = 0; c < kChunksD * 64; c += 8) emit_piece(stage, rr, c, zero8);
     }
-    emit_piece(td, rr, 432, zero8);
-    emit_piece(td, rr, 440, zero8);
-    // view input: the ray's direction encoding (9 rows x 72) times the sample's cutoff weight of each joint
+    flush_stage(stage, gd, kChunksD * kChunkBytes);
+    // view input: the ray's direction encoding (9 rows x 72) times the sample's cutoff weight of each joint.
+    // Columns 0..447 (7 chunks) first, then 448..703 (4 chunks, zero padded from 648).
     const float4* e4 = reinterpret_cast<const float4*>(ray_enc + (size_t)n * kXV);
 #pragma unroll
-    for (int p = 0; p < 9; ++p) {
+    for (int part = 0; part < 2; ++part) {
 #pragma unroll
-        for (int i8 = 0; i8 < 9; ++i8) {
-            const float4 lo = __ldg(e4 + (p * 72 + 8 * i8) / 4), hi = __ldg(e4 + (p * 72 + 8 * i8) / 4 + 1);
-            const float ev[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-            float o[8];
+        for (int p = 0; p < 9; ++p) {
 #pragma unroll
-            for (int t = 0; t < 8; ++t) o[t] = ev[t] * w[(8 * i8 + t) / 3];
-            emit_piece(tv, rr, p * 72 + 8 * i8, o);
+            for (int i8 = 0; i8 < 9; ++i8) {
+                const int col = p * 72 + 8 * i8;
+                if ((col < 448) != (part == 0)) continue;
+                float o[8];
+                if (live) {
+                    const float4 lo = __ldg(e4 + col / 4), hi = __ldg(e4 + col / 4 + 1);
+                    const float ev[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) o[t] = ev[t] * w[(8 * i8 + t) / 3];
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) o[t] = 0.f;
+                }
+                emit_piece(stage, rr, col - part * 448, o);
+            }
         }
-    }
+        if (part == 1) {
 #pragma unroll
-    for (int c = kXV; c < kChunksV * 64; c += 8) emit_piece(tv, rr, c, zero8);
+            for (int c = kXV; c < kChunksV * 64; c += 8) emit_piece(stage, rr, c - 448, zero8);
+        }
+        flush_stage(stage, gv + part * (7 * kChunkBytes), part == 0 ? 7 * kChunkBytes : 4 * kChunkBytes);
+    }
+    // bulk stores still in flight are completed before the grid ends; nothing reads them earlier (stream order)
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -651,7 +690,14 @@ extern "C" int danbo_anerf_embed(const float* rays, int ray_stride, int S, const
                                  const float* ray_enc, float tau, void* xd, void* xv, void* stream) {
     if (n_rows <= 0) return 0;
     const int tiles = (n_rows + DANBO_TILE_M - 1) / DANBO_TILE_M;
-    anerf::embed_kernel<<<tiles, 128, 0, (cudaStream_t)stream>>>(rays, ray_stride, S, z, n_rows, pose_skts, rays_per_pose,
+    const int esmem = anerf::kEmbedStage + 1024;
+    static bool embed_attr = false;
+    if (!embed_attr) {
+        cudaError_t e = cudaFuncSetAttribute(anerf::embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, esmem);
+        if (e != cudaSuccess) return (int)e;
+        embed_attr = true;
+    }
+    anerf::embed_kernel<<<tiles, 128, esmem, (cudaStream_t)stream>>>(rays, ray_stride, S, z, n_rows, pose_skts, rays_per_pose,
                                                                   n_poses, align, ray_enc, tau, (uint8_t*)xd, (uint8_t*)xv);
     DANBO_CHECK_LAUNCH();
     return 0;
