@@ -1,7 +1,7 @@
 """Runs the BASELINE.json configs this round covers on the B200 and writes profiles/r1_configs.json.
   #1 danbo_base 64x64 render (the reference's CPU-runnable case)      #2 danbo_fast 512x512 render (bench.py headline)
   #3 danbo_base 64+16 training step, 3072 rays                        #5 bullet-time 512x512 views + density lattice
-(#4, A-NeRF, is not implemented in round 1.)   Usage: python scripts/bench_configs.py [n_views] [grid_res]"""
+(#4, A-NeRF: scripts/bench_anerf.py.)   Usage: python scripts/bench_configs.py [n_views] [grid_res]"""
 import sys, os, json, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, ROOT + "/oracle", ROOT + "/tests"): sys.path.insert(0, p)
