@@ -494,38 +494,47 @@ field_rows_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, in
 
 // ---------------------------------------------------------------------------------------------------------
 // V1 folded into the view layer: b_ray[n] = W_v[:, 256:411] . [PE(rays_d) (27) ; frame code (128)] + b_v.
-// nerf.py:252-279, embedding.py:86-108.  8 rays per block of 128 threads; thread = output unit.
+// nerf.py:252-279, embedding.py:86-108.  The frame-code part depends only on the camera index: it is computed once per
+// code (code_table_kernel: n_codes + 1 rows, the last one for the mean code) and added to the per-ray 27-input part.
 __global__ void __launch_bounds__(128)
-ray_bias_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, const int* __restrict__ cam_idx,
-                const float* __restrict__ codes, int n_codes,
+code_table_kernel(const float* __restrict__ codes, const float* __restrict__ wv_ray, float* __restrict__ table) {
+    const int ci = blockIdx.x, o = threadIdx.x;
+    float acc = wv_ray[155 * 128 + o];
+    for (int c = 0; c < 128; ++c) acc = fmaf(codes[(size_t)ci * 128 + c], wv_ray[(27 + c) * 128 + o], acc);
+    table[ci * 128 + o] = acc;
+}
+
+// 32 rays per block of 128 threads; thread = output unit.
+__global__ void __launch_bounds__(128)
+ray_bias_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, const int* __restrict__ cam_idx, int n_codes,
                 const float* __restrict__ wv_ray /* (155,128) transposed view/code slice of W_v, then b_v (128) */,
-                float* __restrict__ out /* (n_rays,128) */) {
-    constexpr int RB = 16, VIN = 155;
-    __shared__ __align__(16) float v[VIN][RB];          // inputs of 16 rays, ray-minor so one LDS.128 feeds 4 FMAs
+                const float* __restrict__ table /* (n_codes+1,128) */, float* __restrict__ out /* (n_rays,128) */) {
+    constexpr int RB = 32, VIN = 27;
+    __shared__ __align__(16) float v[VIN][RB];          // inputs of 32 rays, ray-minor so one LDS.128 feeds 4 FMAs
+    __shared__ int cam_s[RB];
     const int base = blockIdx.x * RB;
     for (int i = threadIdx.x; i < RB * VIN; i += blockDim.x) {
         const int rb = i % RB, c = i / RB;
         const int n = base + rb;
         float val = 0.f;
         if (n < n_rays) {
-            if (c < 27) {
-                const float* r = rays + (size_t)n * ray_stride + 3;
-                if (c < 3) val = r[c];
-                else { const int q = c - 3, f = q / 6, rem = q - 6 * f; const float x = r[rem % 3] * (float)(1 << f); val = rem < 3 ? sinf(x) : cosf(x); }
-            } else {
-                int ci = cam_idx ? cam_idx[n] : 0;
-                ci = ci < 0 ? n_codes : (ci > n_codes - 1 ? n_codes - 1 : ci);      // row n_codes holds the mean code
-                val = codes[(size_t)ci * 128 + (c - 27)];
-            }
+            const float* r = rays + (size_t)n * ray_stride + 3;
+            if (c < 3) val = r[c];
+            else { const int q = c - 3, f = q / 6, rem = q - 6 * f; const float x = r[rem % 3] * (float)(1 << f); val = rem < 3 ? sinf(x) : cosf(x); }
         }
         v[c][rb] = val;
+    }
+    if (threadIdx.x < RB) {
+        const int n = base + threadIdx.x;
+        int ci = (cam_idx && n < n_rays) ? cam_idx[n] : 0;
+        cam_s[threadIdx.x] = ci < 0 ? n_codes : (ci > n_codes - 1 ? n_codes - 1 : ci);      // row n_codes holds the mean code
     }
     __syncthreads();
     const int o = threadIdx.x;
     float acc[RB];
 #pragma unroll
     for (int rb = 0; rb < RB; ++rb) acc[rb] = 0.f;
-#pragma unroll 5
+#pragma unroll 3
     for (int c = 0; c < VIN; ++c) {
         const float wc = __ldg(wv_ray + c * 128 + o);
         const float4* vr = reinterpret_cast<const float4*>(v[c]);
@@ -536,9 +545,9 @@ ray_bias_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, cons
             acc[4 * q + 2] = fmaf(wc, x.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(wc, x.w, acc[4 * q + 3]);
         }
     }
-    const float b = wv_ray[VIN * 128 + o];
 #pragma unroll
-    for (int rb = 0; rb < RB; ++rb) if (base + rb < n_rays) out[(size_t)(base + rb) * 128 + o] = acc[rb] + b;
+    for (int rb = 0; rb < RB; ++rb)
+        if (base + rb < n_rays) out[(size_t)(base + rb) * 128 + o] = acc[rb] + __ldg(table + cam_s[rb] * 128 + o);
 }
 
 }  // namespace danbo
@@ -631,10 +640,13 @@ extern "C" int danbo_field_agg(const float* rays, int ray_stride, int n_rays, in
 }
 
 extern "C" int danbo_ray_bias(const float* rays, int ray_stride, int n_rays, const int* cam_idx, const float* codes,
-                              int n_codes, const float* wv_ray, float* out, void* stream) {
+                              int n_codes, const float* wv_ray, float* table, float* out, void* stream) {
     if (n_rays <= 0) return 0;
-    ray_bias_kernel<<<(n_rays + 15) / 16, 128, 0, (cudaStream_t)stream>>>(rays, ray_stride, n_rays, cam_idx, codes, n_codes,
-                                                                       wv_ray, out);
+    if (!table) return -1;
+    code_table_kernel<<<n_codes + 1, 128, 0, (cudaStream_t)stream>>>(codes, wv_ray, table);
+    DANBO_CHECK_LAUNCH();
+    ray_bias_kernel<<<(n_rays + 31) / 32, 128, 0, (cudaStream_t)stream>>>(rays, ray_stride, n_rays, cam_idx, n_codes, wv_ray,
+                                                                       table, out);
     DANBO_CHECK_LAUNCH();
     return 0;
 }

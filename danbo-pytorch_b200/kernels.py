@@ -219,10 +219,12 @@ def ray_bias(rays, cam_idx, codes_with_mean, packed):
     lib = _lib.load()
     n = rays.shape[0]
     out = torch.empty(n, 128, device=rays.device, dtype=torch.float32)
+    table = torch.empty(codes_with_mean.shape[0], 128, device=rays.device, dtype=torch.float32)
     with _Timed("ray_bias"):
         _lib.check(lib.danbo_ray_bias(_p(rays), rays.stride(0), n, _p(cam_idx), _p(codes_with_mean),
-                                      codes_with_mean.shape[0] - 1, _p(packed.wv_ray), _p(out), _stream()), "danbo_ray_bias")
-    _count(1)
+                                      codes_with_mean.shape[0] - 1, _p(packed.wv_ray), _p(table), _p(out), _stream()),
+                   "danbo_ray_bias")
+    _count(2)
     return out
 
 

@@ -65,9 +65,10 @@ int danbo_field_agg(const float* rays, int ray_stride, int n_rays, int S, const 
 
 /* V1 folded into the view layer: out (n_rays,128) = W_v[:,256:411] . [PE(rays_d) ; frame code] + b_v
  * (core/networks/nerf.py:252-279, core/networks/embedding.py:86-108).  codes is (n_codes+1,128) with the mean code in
- * the last row (used for cam_idx < 0); wv_ray comes from danbo_pack_mlp_weights. */
+ * the last row (used for cam_idx < 0); wv_ray comes from danbo_pack_mlp_weights; table = (n_codes+1,128) floats of
+ * workspace (receives the per-code part, which is shared by all rays of a camera). */
 int danbo_ray_bias(const float* rays, int ray_stride, int n_rays, const int* cam_idx, const float* codes, int n_codes,
-                   const float* wv_ray, float* out, void* stream);
+                   const float* wv_ray, float* table, float* out, void* stream);
 
 /* Sizes of the packed-weight buffers below. */
 int danbo_mlp_workspace_bytes(long long* wstream_bytes, long long* heads_bytes, long long* raybias_bytes);
