@@ -331,3 +331,57 @@ extern "C" int danbo_ray_bias_bwd(const float* rays, int ray_stride, int n_rays,
     DANBO_CHECK_LAUNCH();
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Adam over ONE flat fp32 arena (all 43 parameter tensors are views of it): the update is a single elementwise
+// launch instead of a multi-tensor pass (276 us -> ~10 us for 2.46 M parameters).  torch.optim.Adam's formulas
+// (run_nerf.py / raycasters.py:71-78: Adam(lr, betas=(0.9, 0.999)), no weight decay, no amsgrad):
+//   m = m + (g - m)(1 - b1);  v = b2 v + (1 - b2) g^2;  p -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+// step and lr live on the device so a captured CUDA graph sees their current values.
+namespace danbo {
+namespace bwd {
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            long long n, const float* __restrict__ lr_dev, float beta1, float beta2, float eps,
+                            const float* __restrict__ step_dev) {
+    const float t = *step_dev;                               // already incremented for this update
+    const float bc1 = 1.f - powf(beta1, t), bc2_sqrt = sqrtf(1.f - powf(beta2, t));
+    const float step_size = *lr_dev / bc1;
+    const long long n4 = n >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 pp = reinterpret_cast<float4*>(p)[i], mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+        const float4 gg = reinterpret_cast<const float4*>(g)[i];
+        float* P = &pp.x; float* M = &mm.x; float* V = &vv.x; const float* G = &gg.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            M[k] = M[k] + (G[k] - M[k]) * (1.f - beta1);
+            V[k] = V[k] * beta2 + (1.f - beta2) * G[k] * G[k];
+            P[k] -= step_size * (M[k] / (sqrtf(V[k]) / bc2_sqrt + eps));
+        }
+        reinterpret_cast<float4*>(p)[i] = pp; reinterpret_cast<float4*>(m)[i] = mm; reinterpret_cast<float4*>(v)[i] = vv;
+    }
+    for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float gi = g[i];
+        const float mi = m[i] + (gi - m[i]) * (1.f - beta1);
+        const float vi = v[i] * beta2 + (1.f - beta2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        p[i] -= step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+    }
+}
+}  // namespace bwd
+}  // namespace danbo
+
+extern "C" int danbo_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                               const float* lr_dev, float beta1, float beta2, float eps, const float* step_dev,
+                               int num_sms, void* stream) {
+    if (n <= 0) return 0;
+    if ((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) | reinterpret_cast<uintptr_t>(exp_avg) |
+         reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) return -1;
+    long long blocks = (n / 4 + 255) / 256;
+    if (blocks > (long long)num_sms * 8) blocks = (long long)num_sms * 8;
+    if (blocks < 1) blocks = 1;
+    danbo::bwd::adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr_dev, beta1,
+                                                                          beta2, eps, step_dev);
+    DANBO_CHECK_LAUNCH();
+    return 0;
+}

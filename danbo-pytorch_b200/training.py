@@ -43,6 +43,49 @@ def compute_loss(args, preds, batch, network):
     return sum(terms.values()), terms
 
 
+class FlatAdam(torch.optim.Optimizer):
+    """torch.optim.Adam (lr, betas, eps; no weight decay / amsgrad) as ONE kernel launch: parameters, gradients and both
+    moments live in flat fp32 arenas and every nn.Parameter is a view of the parameter arena.  `step` and `lr` are device
+    scalars, so the update can sit inside a captured CUDA graph (set the rate with `set_lr`)."""
+
+    def __init__(self, params, bucket, lr=5e-4, betas=(0.9, 0.999), eps=1e-8):
+        params = [p for p in params if p.requires_grad]
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        assert [id(p) for p in params] == [id(p) for p in bucket.params], "FlatAdam needs the GradBucket's parameter order"
+        dev = params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("FlatAdam runs on CUDA tensors only (there is no CPU path)")
+        self.bucket = bucket
+        n = bucket.flat.numel()
+        self.flat = torch.empty(n, device=dev, dtype=torch.float32)
+        off = 0
+        with torch.no_grad():
+            for p in params:
+                self.flat[off:off + p.numel()].copy_(p.data.reshape(-1))
+                p.data = self.flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.lr_dev = torch.full((1,), float(lr), device=dev, dtype=torch.float32)
+
+    def set_lr(self, lr):
+        self.param_groups[0]["lr"] = float(lr)
+        self.lr_dev.fill_(float(lr))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        from . import kernels as K, _lib
+        g = self.param_groups[0]
+        self.step_dev += 1
+        idx = self.flat.device.index if self.flat.device.index is not None else torch.cuda.current_device()
+        _lib.check(_lib.load().danbo_adam_step(K._p(self.flat), K._p(self.bucket.flat), K._p(self.exp_avg),
+                                               K._p(self.exp_avg_sq), self.flat.numel(), K._p(self.lr_dev),
+                                               float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
+                                               K._p(self.step_dev), K.num_sms(idx), K._stream()), "danbo_adam_step")
+        K._count(1)
+
+
 class TrainStep:
     """forward -> losses -> backward -> (all-reduce of one flat fp32 gradient bucket) -> Adam."""
 
@@ -51,8 +94,11 @@ class TrainStep:
         params = [p for p in caster.network.parameters() if p.requires_grad]
         self.bucket = parallel.GradBucket(params)
         cuda = params[0].is_cuda
-        self.optimizer = optimizer or torch.optim.Adam(params, lr=args.lrate, betas=(0.9, 0.999), fused=cuda,
-                                                       capturable=bool(graph and cuda))
+        if optimizer is None:
+            # default: the single-launch Adam over flat arenas; pass a torch optimizer to keep the reference's
+            optimizer = FlatAdam(params, self.bucket, lr=args.lrate, betas=(0.9, 0.999)) if cuda else \
+                torch.optim.Adam(params, lr=args.lrate, betas=(0.9, 0.999))
+        self.optimizer = optimizer
         self._graphed = None
         if graph:
             from .graphs import GraphedFn
@@ -73,15 +119,19 @@ class TrainStep:
             out = self._graphed(**batch)
             if self.world > 1:
                 self.bucket.allreduce(average=True)
-                self.optimizer.step()
+                self._optimizer_step()
             return out["loss"], out
         return self._step(batch)
 
     def _step(self, batch):
         loss, preds = self._fwd_bwd(batch)
         self.bucket.allreduce(average=True)
-        self.optimizer.step()
+        self._optimizer_step()
         return loss, preds
+
+    def _optimizer_step(self):
+        self.optimizer.step()
+        self.caster._packed_key = None          # weights changed (a raw-pointer update does not bump tensor versions)
 
     def _fwd_bwd(self, batch):
         a = self.args

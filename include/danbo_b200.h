@@ -184,6 +184,13 @@ int danbo_field_agg_bwd(const float* rays, int ray_stride, int n_rays, int S, co
                         float* d_logit, const int* work, int pair_capacity, float* const* grads, int num_sms,
                         void* stream);
 
+/* Adam (torch.optim.Adam formulas, raycasters.py:71-78: betas (0.9, 0.999), no weight decay) over one flat fp32 arena
+ * holding every parameter; grads / exp_avg / exp_avg_sq are arenas of the same layout; all 16-byte aligned.  lr_dev
+ * and step_dev are device floats (step already incremented) so that a captured graph reads their current values. */
+int danbo_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                    const float* lr_dev, float beta1, float beta2, float eps, const float* step_dev, int num_sms,
+                    void* stream);
+
 /* ---- AN1: A-NeRF field (nerf_type = nerf, BASELINE config #4) -------------------------------------------------
  * Replaces core/networks/nerf.py:164-279 (encode_pts / encode_views / inference with W = 448, view_W = 224),
  * core/cutoff_embedder.py:151-214 and core/encoders.py:305-317,639-651,774-795.  Every sample goes through the field

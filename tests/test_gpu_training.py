@@ -310,3 +310,30 @@ def test_cuda_graph_paths():
     losses = [float(step(batch)[0]) for _ in range(12)]
     print("[train] graphed step losses", ["%.4f" % l for l in losses])
     assert all(l == l for l in losses) and losses[-1] < losses[0]
+
+
+def test_flat_adam_matches_torch_adam():
+    """training.FlatAdam (one launch over flat arenas) against torch.optim.Adam on the same gradients, 4 steps."""
+    import danbo_b200
+    from danbo_b200 import training, parallel
+    torch.manual_seed(0)
+    shapes = [(256, 195), (256,), (24, 15, 32), (3, 128), (1,), (7,)]
+    ref = [torch.nn.Parameter(torch.randn(*s, device=DEV)) for s in shapes]
+    mine = [torch.nn.Parameter(p.detach().clone()) for p in ref]
+    opt_ref = torch.optim.Adam(ref, lr=5e-4, betas=(0.9, 0.999))
+    bucket = parallel.GradBucket(mine)
+    opt = training.FlatAdam(mine, bucket, lr=5e-4, betas=(0.9, 0.999))
+    for it in range(4):
+        grads = [torch.randn(*s, device=DEV) * (10.0 ** (it - 2)) for s in shapes]
+        for p, q, g in zip(ref, mine, grads):
+            p.grad = g.clone()
+            q.grad.copy_(g)
+        opt_ref.step()
+        opt.step()
+        if it == 1:
+            opt.set_lr(2.5e-4)
+            opt_ref.param_groups[0]["lr"] = 2.5e-4
+    for p, q in zip(ref, mine):
+        assert q.data_ptr() >= opt.flat.data_ptr() and q.data_ptr() < opt.flat.data_ptr() + opt.flat.numel() * 4
+        err = float((p - q).abs().max())
+        assert err <= 2e-6 * max(float(p.abs().max()), 1.0), err
