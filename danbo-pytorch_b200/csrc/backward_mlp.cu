@@ -201,66 +201,110 @@ head_bwd_kernel(const float* __restrict__ d_raw, const int* __restrict__ row_sam
 }
 
 // V1 backward: d_ray_bias (n,128) -> grads of views_linears.0.weight[:, 256:411] (128,411 layout), its bias, and the
-// frame codes.  16 rays per block, inputs v recomputed like the forward.
-__global__ void __launch_bounds__(128)
+// frame codes.  Groups of 16 rays (inputs v recomputed like the forward); a block walks several groups and keeps its
+// weight-gradient partial sums in registers (thread = output unit x half of the 155 inputs), so the atomics on the
+// shared (128,155) slice happen once per block, not once per group.
+__global__ void __launch_bounds__(256)
 ray_bias_bwd_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, const int* __restrict__ cam_idx,
                     const float* __restrict__ codes, int n_codes, const float* __restrict__ w_view /* (128,411) */,
                     const float* __restrict__ d_ray_bias, float* __restrict__ d_w_view /* (128,411) */,
                     float* __restrict__ d_b_view, float* __restrict__ d_codes /* (n_codes,128) */) {
-    constexpr int RB = 16, VIN = 155;
+    constexpr int RB = 16, VIN = 155, HALF = 78;
     __shared__ float v[VIN][RB];
     __shared__ float db[RB][128];
     __shared__ int s_cam[RB];
-    const int base = blockIdx.x * RB;
-    for (int i = threadIdx.x; i < RB * VIN; i += blockDim.x) {
-        const int rb = i % RB, c = i / RB;
-        const int n = base + rb;
-        float val = 0.f;
-        if (n < n_rays) {
-            if (c < 27) {
-                const float* r = rays + (size_t)n * ray_stride + 3;
-                if (c < 3) val = r[c];
-                else { const int q = c - 3, f = q / 6, rem = q - 6 * f; const float x = r[rem % 3] * (float)(1 << f); val = rem < 3 ? sinf(x) : cosf(x); }
-            } else {
-                int ci = cam_idx ? cam_idx[n] : 0;
-                ci = ci < 0 ? n_codes : (ci > n_codes - 1 ? n_codes - 1 : ci);
-                val = codes[(size_t)ci * 128 + (c - 27)];
+    __shared__ float dsum[128];
+    __shared__ int one_cam;
+    const int o = threadIdx.x & 127, half = threadIdx.x >> 7;
+    const int c0 = half * HALF, nc = half == 0 ? HALF : VIN - HALF;
+    float acc[HALF];
+#pragma unroll
+    for (int i = 0; i < HALF; ++i) acc[i] = 0.f;
+    float bsum = 0.f;
+    const int n_groups = (n_rays + RB - 1) / RB;
+    for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const int base = g * RB;
+        __syncthreads();                                  // previous group's tiles fully consumed
+        for (int i = threadIdx.x; i < RB * VIN; i += blockDim.x) {
+            const int rb = i % RB, c = i / RB;
+            const int n = base + rb;
+            float val = 0.f;
+            if (n < n_rays) {
+                if (c < 27) {
+                    const float* r = rays + (size_t)n * ray_stride + 3;
+                    if (c < 3) val = r[c];
+                    else { const int q = c - 3, f = q / 6, rem = q - 6 * f; const float x = r[rem % 3] * (float)(1 << f); val = rem < 3 ? sinf(x) : cosf(x); }
+                } else {
+                    int ci = cam_idx ? cam_idx[n] : 0;
+                    ci = ci < 0 ? n_codes : (ci > n_codes - 1 ? n_codes - 1 : ci);
+                    val = codes[(size_t)ci * 128 + (c - 27)];
+                }
+            }
+            v[c][rb] = val;
+        }
+        for (int i = threadIdx.x; i < RB * 128; i += blockDim.x) {
+            const int rb = i / 128, oo = i % 128;
+            db[rb][oo] = (base + rb < n_rays) ? d_ray_bias[(size_t)(base + rb) * 128 + oo] : 0.f;
+        }
+        if (threadIdx.x < RB) {
+            const int n = base + threadIdx.x;
+            int ci = (n < n_rays && cam_idx) ? cam_idx[n] : 0;
+            s_cam[threadIdx.x] = (n < n_rays) ? ci : -2;
+        }
+        __syncthreads();
+        float d[RB];
+#pragma unroll
+        for (int rb = 0; rb < RB; ++rb) { d[rb] = db[rb][o]; bsum += d[rb]; }
+#pragma unroll
+        for (int i = 0; i < HALF; ++i) {
+            if (i < nc) {
+                const float4* vr = reinterpret_cast<const float4*>(v[c0 + i]);
+#pragma unroll
+                for (int q = 0; q < RB / 4; ++q) {
+                    const float4 x = vr[q];
+                    acc[i] = fmaf(d[4 * q + 0], x.x, acc[i]); acc[i] = fmaf(d[4 * q + 1], x.y, acc[i]);
+                    acc[i] = fmaf(d[4 * q + 2], x.z, acc[i]); acc[i] = fmaf(d[4 * q + 3], x.w, acc[i]);
+                }
             }
         }
-        v[c][rb] = val;
-    }
-    for (int i = threadIdx.x; i < RB * 128; i += blockDim.x) {
-        const int rb = i / 128, o = i % 128;
-        db[rb][o] = (base + rb < n_rays) ? d_ray_bias[(size_t)(base + rb) * 128 + o] : 0.f;
-    }
-    if (threadIdx.x < RB) {
-        const int n = base + threadIdx.x;
-        int ci = (n < n_rays && cam_idx) ? cam_idx[n] : 0;
-        s_cam[threadIdx.x] = (n < n_rays) ? ci : -2;
-    }
-    __syncthreads();
-    const int o = threadIdx.x;
-    // weight slice + bias
-    float bsum = 0.f;
+        // frame codes: d code[cam][c'] += sum_o W_v[o][283 + c'] * d_bias[o]   (training: cam >= 0; eval mean code has no grad).
+        // Rays arrive image-major, so a group normally has ONE camera: sum its d_bias rows first and do a single
+        // 128 x 128 product (the per-ray form is a 2 048-step dependent load/FMA chain per thread: 43 us per group).
+        float gsum = 0.f;
 #pragma unroll
-    for (int rb = 0; rb < RB; ++rb) bsum += db[rb][o];
-    atomicAdd(d_b_view + o, bsum);
-    for (int c = 0; c < VIN; ++c) {
-        float s = 0.f;
+        for (int rb = 0; rb < RB; ++rb) gsum += (s_cam[rb] >= 0) ? d[rb] : 0.f;
+        if (half == 0) dsum[o] = gsum;
+        if (threadIdx.x == 0) {
+            int c0 = -3; bool same = true;
+            for (int rb = 0; rb < RB; ++rb) { const int c = s_cam[rb]; if (c < 0) continue; if (c0 == -3) c0 = c; else if (c != c0) same = false; }
+            one_cam = same ? c0 : -4;                   // -3: no ray with a trainable code, -4: mixed
+        }
+        __syncthreads();
+        if (half == 0) {
+            const int cp = o;
+            if (one_cam >= 0) {
+                const int ci = one_cam > n_codes - 1 ? n_codes - 1 : one_cam;
+                float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+                for (int oo = 0; oo < 128; ++oo) s4[oo & 3] = fmaf(__ldg(w_view + (size_t)oo * 411 + 283 + cp), dsum[oo], s4[oo & 3]);
+                atomicAdd(d_codes + (size_t)ci * 128 + cp, (s4[0] + s4[1]) + (s4[2] + s4[3]));
+            } else if (one_cam == -4) {
+                for (int rb = 0; rb < RB; ++rb) {
+                    const int cam = s_cam[rb];
+                    if (cam < 0) continue;
+                    const int ci = cam > n_codes - 1 ? n_codes - 1 : cam;
+                    float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+                    for (int oo = 0; oo < 128; ++oo) s4[oo & 3] = fmaf(__ldg(w_view + (size_t)oo * 411 + 283 + cp), db[rb][oo], s4[oo & 3]);
+                    atomicAdd(d_codes + (size_t)ci * 128 + cp, (s4[0] + s4[1]) + (s4[2] + s4[3]));
+                }
+            }
+        }
+    }
+    if (half == 0) atomicAdd(d_b_view + o, bsum);
 #pragma unroll
-        for (int rb = 0; rb < RB; ++rb) s = fmaf(db[rb][o], v[c][rb], s);
-        atomicAdd(d_w_view + (size_t)o * 411 + 256 + c, s);
-    }
-    // frame codes: d code[cam][c'] += sum_o W_v[o][283 + c'] * d_bias[o]   (training: cam >= 0; eval mean code has no grad)
-    const int cp = threadIdx.x;
-    for (int rb = 0; rb < RB; ++rb) {
-        const int cam = s_cam[rb];
-        if (cam < 0) continue;
-        const int ci = cam > n_codes - 1 ? n_codes - 1 : cam;
-        float s = 0.f;
-        for (int oo = 0; oo < 128; ++oo) s = fmaf(w_view[(size_t)oo * 411 + 283 + cp], db[rb][oo], s);
-        atomicAdd(d_codes + (size_t)ci * 128 + cp, s);
-    }
+    for (int i = 0; i < HALF; ++i)
+        if (i < nc) atomicAdd(d_w_view + (size_t)o * 411 + 256 + c0 + i, acc[i]);
 }
 
 }  // namespace bwd
@@ -326,7 +370,10 @@ extern "C" int danbo_ray_bias_bwd(const float* rays, int ray_stride, int n_rays,
                                   int n_codes, const float* w_view, const float* d_ray_bias, float* d_w_view,
                                   float* d_b_view, float* d_codes, void* stream) {
     if (n_rays <= 0) return 0;
-    bwd::ray_bias_bwd_kernel<<<(n_rays + 15) / 16, 128, 0, (cudaStream_t)stream>>>(
+    int rb_blocks = (n_rays + 15) / 16;
+    if (rb_blocks > 64) rb_blocks = 64 + (rb_blocks - 64) / 8;          // several 16-ray groups per block
+    if (rb_blocks > 1184) rb_blocks = 1184;
+    bwd::ray_bias_bwd_kernel<<<rb_blocks, 256, 0, (cudaStream_t)stream>>>(
         rays, ray_stride, n_rays, cam_idx, codes, n_codes, w_view, d_ray_bias, d_w_view, d_b_view, d_codes);
     DANBO_CHECK_LAUNCH();
     return 0;

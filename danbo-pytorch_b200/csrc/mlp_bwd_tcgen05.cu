@@ -16,7 +16,8 @@ namespace danbo {
 namespace mlpb {
 using namespace danbo::tc;
 
-constexpr int kStages = 9;
+constexpr int kStages = 7;                           // ring slots: 84 tiles per row tile = 12 x 7, so the slot and the barrier
+                                                     // parity of every tile are compile-time constants of the unrolled schedule
 constexpr int kStageBytes = 128 * 64 * 2;
 constexpr int kThreads = 320;
 constexpr int kNumStagesPerTile = 84;                // weight tiles consumed per 128-row tile
@@ -35,13 +36,97 @@ struct __align__(1024) Smem {
 };
 
 // stage -> number of 64-wide K chunks, input activation buffer, kind
-__device__ __forceinline__ int st_kchunks(int s) { return s == 0 ? 2 : 4; }
-__device__ __forceinline__ int st_inbuf(int s) { const int t[kDgradStages] = {0, 1, 0, 1, 0, 0, 1, 0, 1, 0, 1}; return t[s]; }
+__host__ __device__ constexpr int st_kchunks(int s) { return s == 0 ? 2 : 4; }
+// {0, 1, 0, 1, 0, 0, 1, 0, 1, 0, 1}
+__host__ __device__ constexpr int st_inbuf(int s) { return s < 5 ? (s & 1) : ((s - 1) & 1); }
 __device__ __forceinline__ bool st_is_x(int s) { return s == 4 || s == 10; }
 // row-major activation plane whose relu masks the output of stage s (-1: none)
 __device__ __forceinline__ int st_mask_plane(int s) { const int t[kDgradStages] = {-1, 7, 6, 5, -1, 4, 3, 2, 1, 0, -1}; return t[s]; }
 // delta plane written by stage s (-1: none); plane 0 = delta9 comes from the prologue
 __device__ __forceinline__ int st_delta_plane(int s) { const int t[kDgradStages] = {1, 2, 3, 4, -1, 5, 6, 7, 8, 9, -1}; return t[s]; }
+
+// ---- epilogue bodies of the dgrad chain: the stage kind is a template parameter and whatever does not depend on the
+// accumulator (relu masks = saved forward activations) is fetched before the wait on the MMA (see mlp_tcgen05.cu).
+struct EpiArgs {
+    uint64_t* acc_bar; uint32_t phase;
+    uint32_t acc, act_out;
+    int col0;
+    bool valid;
+    float g_sigma;
+    const float* w_alpha;      // shared memory, at col0
+    const uint4* mask;         // forward activation of the layer whose relu gates this delta (row-major bf16), or null
+    uint4* delta_out;          // this stage's delta plane (row-major bf16), or null
+    float* dx;                 // dX row (208 floats)
+};
+
+// dX stages: accumulator -> fp32 row (stage 10 adds to what stage 4 stored)
+template <bool kAccumulate>
+__device__ __forceinline__ void epi_dx(const EpiArgs& E) {
+    mbar_wait(E.acc_bar, E.phase);
+    tc_fence_after();
+    uint32_t v[2][32];
+    tmem_ld32(E.acc, v[0]);
+    tmem_ld32(E.acc + 32, v[1]);
+    tmem_wait_ld();
+    if (!E.valid) return;
+#pragma unroll
+    for (int gq = 0; gq < 2; ++gq)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = E.col0 + 32 * gq + 4 * i;
+            if (c < 208) {
+                float4 o = make_float4(__uint_as_float(v[gq][4 * i]), __uint_as_float(v[gq][4 * i + 1]),
+                                       __uint_as_float(v[gq][4 * i + 2]), __uint_as_float(v[gq][4 * i + 3]));
+                float4* p = reinterpret_cast<float4*>(E.dx + c);
+                if (kAccumulate) { const float4 old = *p; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+                *p = o;
+            }
+        }
+}
+
+// delta stages: accumulator (+ sigma-head term) gated by the saved activation -> bf16 delta in TMEM (next A operand) + HBM
+template <bool kAlpha, bool kMask>
+__device__ __forceinline__ void epi_delta(const EpiArgs& E) {
+    uint4 m[8];
+    if (kMask) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m[i] = E.mask[i];
+    }
+    mbar_wait(E.acc_bar, E.phase);
+    tc_fence_after();
+    uint32_t v[2][32];
+    tmem_ld32(E.acc, v[0]);
+    tmem_ld32(E.acc + 32, v[1]);
+    tmem_wait_ld();
+#pragma unroll
+    for (int gq = 0; gq < 2; ++gq) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+            const uint32_t mw[4] = {m[gq * 4 + c8].x, m[gq * 4 + c8].y, m[gq * 4 + c8].z, m[gq * 4 + c8].w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int e = c8 * 8 + 2 * i;
+                float a0 = __uint_as_float(v[gq][e]), a1 = __uint_as_float(v[gq][e + 1]);
+                if (kAlpha) {                              // sigma head: d a7 += d sigma * w_alpha
+                    a0 = fmaf(E.g_sigma, E.w_alpha[32 * gq + e], a0);
+                    a1 = fmaf(E.g_sigma, E.w_alpha[32 * gq + e + 1], a1);
+                }
+                if (kMask) {
+                    if (!(__uint_as_float(mw[i] << 16) > 0.f)) a0 = 0.f;
+                    if (!(__uint_as_float(mw[i] & 0xffff0000u) > 0.f)) a1 = 0.f;
+                }
+                if (!E.valid) { a0 = 0.f; a1 = 0.f; }
+                pk[c8 * 4 + i] = pack_bf16(a0, a1);
+            }
+        }
+        tmem_st16(E.act_out + 16 * gq, pk);
+        if (E.delta_out != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) E.delta_out[gq * 4 + i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        }
+    }
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
 dgrad_kernel(const uint8_t* __restrict__ wstream,            // [84][16 KB] transposed-weight tiles (pack_dgrad)
@@ -89,36 +174,41 @@ dgrad_kernel(const uint8_t* __restrict__ wstream,            // [84][16 KB] tran
             }
         }
     } else if (warp == 1) {
+        // fully unrolled per-tile schedule (see mlp_tcgen05.cu): runtime ring-slot arithmetic keeps descriptors in vector
+        // registers and costs more issue time than the MMAs themselves
         const bool leader = elect_one();
-        uint32_t ws = 0, wphase = 0, r0 = 0, r1 = 0;
-        const uint64_t desc_hi = make_desc(0);
+        uint32_t r0 = 0, r1 = 0;
+        const uint64_t w_desc0 = make_desc(0) | (uint64_t)((smem_u32(&S.w[0][0]) >> 4) & 0x3FFF);
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+#pragma unroll
             for (int s = 0; s < kDgradStages; ++s) {
                 mbar_wait(&S.act_ready[0], r0 & 1); ++r0;
                 tc_fence_after();
-                bool got_r1 = false;
                 const uint32_t a_in = tmem + kActCol + 128u * st_inbuf(s);
                 const int nkc = st_kchunks(s);
+#pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const uint32_t d = tmem + kAccCol + 128u * h;
-                    for (int kc = 0; kc < nkc; ++kc) {
-                        if (!got_r1 && (kc == 2 || h == 1)) { mbar_wait(&S.act_ready[1], r1 & 1); ++r1; got_r1 = true; }
-                        mbar_wait(&S.w_full[ws], wphase);
+#pragma unroll
+                    for (int kc = 0; kc < 4; ++kc) {
+                        if (kc >= nkc) continue;
+                        if ((h == 0 && kc == 2) || (h == 1 && kc == 0 && nkc <= 2)) { mbar_wait(&S.act_ready[1], r1 & 1); ++r1; }
+                        const int tile = s == 0 ? h * 2 + kc : 4 + (s - 1) * 8 + h * 4 + kc;
+                        const int slot = tile % kStages;
+                        mbar_wait(&S.w_full[slot], (uint32_t)((tile / kStages) & 1));
                         tc_fence_after();
-                        const uint64_t bdesc = desc_hi | (uint64_t)((smem_u32(S.w[ws]) >> 4) & 0x3FFF);
+                        const uint64_t bdesc = w_desc0 + (uint64_t)((slot * kStageBytes) >> 4);
                         const uint32_t a_t = a_in + kc * 32;
                         if (leader) {
                             mma_ts(d, a_t, bdesc, kIdesc, kc > 0 ? 1u : 0u);
                             mma_ts(d, a_t + 8, bdesc + 2, kIdesc, 1u);
                             mma_ts(d, a_t + 16, bdesc + 4, kIdesc, 1u);
                             mma_ts(d, a_t + 24, bdesc + 6, kIdesc, 1u);
-                            tc_commit(&S.w_empty[ws]);
+                            tc_commit(&S.w_empty[slot]);
+                            if (kc == nkc - 1) tc_commit(&S.acc_full[h]);
                         }
                         __syncwarp();
-                        if (++ws == kStages) { ws = 0; wphase ^= 1; }
                     }
-                    if (leader) tc_commit(&S.acc_full[h]);
-                    __syncwarp();
                 }
             }
         }
@@ -166,66 +256,24 @@ dgrad_kernel(const uint8_t* __restrict__ wstream,            // [84][16 KB] tran
             }
             for (int s = 0; s < kDgradStages; ++s) {
                 const int mp = st_mask_plane(s), dp = st_delta_plane(s);
-                const bool is_x = st_is_x(s);
                 for (int h = 0; h < 2; ++h) {
-                    if (h == 0) { mbar_wait(&S.acc_full[0], f0 & 1); ++f0; }
-                    else        { mbar_wait(&S.acc_full[1], f1 & 1); ++f1; }
-                    tc_fence_after();
-                    const uint32_t acc = tmem + lane_addr + kAccCol + 128u * h + 64u * ch;
-                    uint32_t v[2][32];
-                    tmem_ld32(acc, v[0]);
-                    tmem_ld32(acc + 32, v[1]);
-                    tmem_wait_ld();
-                    const int col0 = h * 128 + ch * 64;
-                    if (is_x) {
-                        if (valid) {
-                            float* dx = dX + (size_t)grow * 208;
-#pragma unroll
-                            for (int gq = 0; gq < 2; ++gq)
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const int c = col0 + 32 * gq + 4 * i;
-                                    if (c < 208) {
-                                        float4 o = make_float4(__uint_as_float(v[gq][4 * i]), __uint_as_float(v[gq][4 * i + 1]),
-                                                               __uint_as_float(v[gq][4 * i + 2]), __uint_as_float(v[gq][4 * i + 3]));
-                                        float4* p = reinterpret_cast<float4*>(dx + c);
-                                        if (s == 10) { const float4 old = *p; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
-                                        *p = o;
-                                    }
-                                }
-                        }
-                    } else {
-                        const uint32_t act_out = tmem + lane_addr + kActCol + 128u * (1 - st_inbuf(s)) + 64u * h + 32u * ch;
-                        const uint4* mk = mp >= 0 ? reinterpret_cast<const uint4*>(act_save + ((size_t)mp * cap + (valid ? grow : 0)) * 256 + col0) : nullptr;
-#pragma unroll
-                        for (int gq = 0; gq < 2; ++gq) {
-                            uint32_t pk[16];
-#pragma unroll
-                            for (int c8 = 0; c8 < 4; ++c8) {
-                                uint4 m4 = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);      // bf16 ones: no mask
-                                if (mk) m4 = mk[gq * 4 + c8];
-                                const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    const int e = c8 * 8 + 2 * i;
-                                    float a0 = __uint_as_float(v[gq][e]), a1 = __uint_as_float(v[gq][e + 1]);
-                                    if (s == 1) {                              // sigma head: d a7 += d sigma * w_alpha
-                                        a0 = fmaf(g.w, S.w_alpha[col0 + 32 * gq + e], a0);
-                                        a1 = fmaf(g.w, S.w_alpha[col0 + 32 * gq + e + 1], a1);
-                                    }
-                                    if (!(__uint_as_float(mw[i] << 16) > 0.f) || !valid) a0 = 0.f;
-                                    if (!(__uint_as_float(mw[i] & 0xffff0000u) > 0.f) || !valid) a1 = 0.f;
-                                    pk[c8 * 4 + i] = pack_bf16(a0, a1);
-                                }
-                            }
-                            tmem_st16(act_out + 16 * gq, pk);
-                            if (grow < cap) {
-                                uint4* dst = reinterpret_cast<uint4*>(delta_save + ((size_t)dp * cap + grow) * 256 + col0 + 32 * gq);
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-                            }
-                        }
-                    }
+                    EpiArgs E;
+                    E.acc_bar = &S.acc_full[h];
+                    if (h == 0) { E.phase = f0 & 1; ++f0; } else { E.phase = f1 & 1; ++f1; }
+                    E.acc = tmem + lane_addr + kAccCol + 128u * h + 64u * ch;
+                    E.act_out = tmem + lane_addr + kActCol + 128u * (1 - st_inbuf(s)) + 64u * h + 32u * ch;
+                    E.col0 = h * 128 + ch * 64;
+                    E.valid = valid;
+                    E.g_sigma = g.w;
+                    E.w_alpha = S.w_alpha + E.col0;
+                    E.mask = mp >= 0 ? reinterpret_cast<const uint4*>(act_save + ((size_t)mp * cap + (valid ? grow : 0)) * 256 + E.col0) : nullptr;
+                    E.delta_out = (dp >= 0 && grow < cap) ? reinterpret_cast<uint4*>(delta_save + ((size_t)dp * cap + grow) * 256 + E.col0) : nullptr;
+                    E.dx = dX + (size_t)(valid ? grow : 0) * 208;
+                    if (s == 4) epi_dx<false>(E);
+                    else if (s == 10) epi_dx<true>(E);
+                    else if (s == 0) epi_delta<false, false>(E);
+                    else if (s == 1) epi_delta<true, true>(E);
+                    else epi_delta<false, true>(E);
                     tmem_wait_st();
                     tc_fence_before();
                     __syncwarp();
