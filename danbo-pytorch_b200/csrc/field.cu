@@ -338,78 +338,127 @@ pair_bucket_kernel(const uint32_t* __restrict__ mask, const int* __restrict__ ac
     }
 }
 
+// Two pairs per lane (a warp = 64 pairs of the SAME bone): every aggregation-net weight is a warp-uniform load feeding
+// 64 MACs.  With one pair per lane the kernel was bound by the load/store unit (one LSU pass per weight vector and per
+// feature gather against four FMA pipes), not by FP32 throughput.
 __global__ void __launch_bounds__(128)
 pair_logits_kernel(const float* __restrict__ rays, int ray_stride, int S, const float* __restrict__ z,
                    const int* __restrict__ active_ids, const float* __restrict__ pose_skts,
                    const float* __restrict__ pose_vol, int rays_per_pose, int n_poses, FieldConsts fc, PairWork pw,
                    int pair_capacity, float* __restrict__ logits /* (n_rays*S, 24), visible entries only */) {
+    constexpr int PP = 2;                                // pairs per lane
     const int lane = threadIdx.x & 31;
     const int* cnt = pw.count();
+    // segments are padded to 32 pairs; a warp takes two consecutive 32-pair pieces of one bone's segment
     int n_chunks = 0;
-    for (int j = 0; j < DANBO_J; ++j) n_chunks += (cnt[j] + 31) >> 5;
+    for (int j = 0; j < DANBO_J; ++j) n_chunks += (((cnt[j] + 31) >> 5) + PP - 1) / PP;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     for (int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < n_chunks; c += warps) {
-        // bone of this chunk (warp-uniform)
-        int j = 0, first = 0;
-        for (;; ++j) { const int nc = (cnt[j] + 31) >> 5; if (c < first + nc) break; first += nc; }
-        const int in_seg = (c - first) * 32 + lane;
-        const int at = c * 32 + lane;
-        const bool live = in_seg < cnt[j] && at < pair_capacity;
-        float px = 0.f, py = 0.f, pz = 0.f;
-        int id = 0, pose = 0;
-        if (live) {
-            id = active_ids[pw.pairs()[at]];
-            const int n = id / S;
-            const float* r = rays + (size_t)n * ray_stride;
-            const float zz = z[id];
-            px = __fadd_rn(r[0], __fmul_rn(r[3], zz));
-            py = __fadd_rn(r[1], __fmul_rn(r[4], zz));
-            pz = __fadd_rn(r[2], __fmul_rn(r[5], zz));
-            pose = n / rays_per_pose; if (pose >= n_poses) pose = n_poses - 1;
+        // bone of this chunk (warp-uniform) and the start of its segment in 32-pair units
+        int j = 0, first = 0, seg32 = 0;
+        for (;; ++j) {
+            const int n32 = (cnt[j] + 31) >> 5, nc = (n32 + PP - 1) / PP;
+            if (c < first + nc) break;
+            first += nc; seg32 += n32;
         }
-        const float* skt = pose_skts + (size_t)pose * DANBO_J * 16;
-        const float* vol = pose_vol + (size_t)pose * DANBO_J * DANBO_VOL;
-        float mix[DANBO_AGG_W];
+        const int n32_j = (cnt[j] + 31) >> 5;
+        float px[PP], py[PP], pz[PP];
+        int id[PP], pose[PP];
+        bool live[PP];
 #pragma unroll
-        for (int o = 0; o < DANBO_AGG_W; ++o) mix[o] = 0.f;
+        for (int u = 0; u < PP; ++u) {
+            const int piece = (c - first) * PP + u;                  // 32-pair piece inside the bone's segment
+            const int in_seg = piece * 32 + lane;
+            const int at = (seg32 + piece) * 32 + lane;
+            live[u] = piece < n32_j && in_seg < cnt[j] && at < pair_capacity;
+            px[u] = py[u] = pz[u] = 0.f; id[u] = 0; pose[u] = 0;
+            if (live[u]) {
+                id[u] = active_ids[pw.pairs()[at]];
+                const int n = id[u] / S;
+                const float* r = rays + (size_t)n * ray_stride;
+                const float zz = z[id[u]];
+                px[u] = __fadd_rn(r[0], __fmul_rn(r[3], zz));
+                py[u] = __fadd_rn(r[1], __fmul_rn(r[4], zz));
+                pz[u] = __fadd_rn(r[2], __fmul_rn(r[5], zz));
+                pose[u] = n / rays_per_pose; if (pose[u] >= n_poses) pose[u] = n_poses - 1;
+            }
+        }
+        float mix[PP][DANBO_AGG_W];
+#pragma unroll
+        for (int u = 0; u < PP; ++u)
+#pragma unroll
+            for (int o = 0; o < DANBO_AGG_W; ++o) mix[u][o] = 0.f;
         uint32_t nb = kNbrMask[j];
         while (nb) {                                    // layer 0 of the bone's tree neighbours, mixed by adjacency
             const int k = __ffs(nb) - 1; nb &= nb - 1;
-            float x0, x1, x2, h[DANBO_FEAT];
-            bone_coords(skt + k * 16, fc.align + k * 16, fc.axis_scale + k * 3, px, py, pz, x0, x1, x2);
-            bone_features(vol + k * DANBO_VOL, x0, x1, x2, h);
             const float adj = __ldg(fc.agg_adjw + j * DANBO_J + k) * __ldg(fc.agg_adj + j * DANBO_J + k);
+            float h[PP][DANBO_FEAT];
+#pragma unroll
+            for (int u = 0; u < PP; ++u) {
+                float x0, x1, x2;
+                bone_coords(pose_skts + ((size_t)pose[u] * DANBO_J + k) * 16, fc.align + k * 16, fc.axis_scale + k * 3,
+                            px[u], py[u], pz[u], x0, x1, x2);
+                bone_features(pose_vol + ((size_t)pose[u] * DANBO_J + k) * DANBO_VOL, x0, x1, x2, h[u]);
+            }
             const float4* w = reinterpret_cast<const float4*>(fc.agg_w0 + (size_t)k * DANBO_FEAT * DANBO_AGG_W);
 #pragma unroll
             for (int i = 0; i < DANBO_FEAT; ++i) {
-                const float hi = h[i] * adj;
+                float hi[PP];
+#pragma unroll
+                for (int u = 0; u < PP; ++u) hi[u] = h[u][i] * adj;
 #pragma unroll
                 for (int o4 = 0; o4 < DANBO_AGG_W / 4; ++o4) {
                     const float4 wv = __ldg(w + i * (DANBO_AGG_W / 4) + o4);
-                    mix[4 * o4 + 0] = fmaf(hi, wv.x, mix[4 * o4 + 0]); mix[4 * o4 + 1] = fmaf(hi, wv.y, mix[4 * o4 + 1]);
-                    mix[4 * o4 + 2] = fmaf(hi, wv.z, mix[4 * o4 + 2]); mix[4 * o4 + 3] = fmaf(hi, wv.w, mix[4 * o4 + 3]);
+#pragma unroll
+                    for (int u = 0; u < PP; ++u) {
+                        mix[u][4 * o4 + 0] = fmaf(hi[u], wv.x, mix[u][4 * o4 + 0]); mix[u][4 * o4 + 1] = fmaf(hi[u], wv.y, mix[u][4 * o4 + 1]);
+                        mix[u][4 * o4 + 2] = fmaf(hi[u], wv.z, mix[u][4 * o4 + 2]); mix[u][4 * o4 + 3] = fmaf(hi[u], wv.w, mix[u][4 * o4 + 3]);
+                    }
                 }
             }
         }
 #pragma unroll
-        for (int o = 0; o < DANBO_AGG_W; ++o) mix[o] = fmaxf(mix[o] + __ldg(fc.agg_b0 + o), 0.f);
-        float l1[DANBO_AGG_W];
+        for (int o = 0; o < DANBO_AGG_W; ++o) {
+            const float b0 = __ldg(fc.agg_b0 + o);
 #pragma unroll
-        for (int o = 0; o < DANBO_AGG_W; ++o) l1[o] = __ldg(fc.agg_b1 + j * DANBO_AGG_W + o);
+            for (int u = 0; u < PP; ++u) mix[u][o] = fmaxf(mix[u][o] + b0, 0.f);
+        }
+        // layer 1 (32 -> 32) in two halves of 16 outputs to bound the live registers, then layer 2 (32 -> 1)
+        float a[PP];
+#pragma unroll
+        for (int u = 0; u < PP; ++u) a[u] = __ldg(fc.agg_b2 + j);
         const float4* w1 = reinterpret_cast<const float4*>(fc.agg_w1 + (size_t)j * DANBO_AGG_W * DANBO_AGG_W);
 #pragma unroll
-        for (int i = 0; i < DANBO_AGG_W; ++i) {
+        for (int oh = 0; oh < 2; ++oh) {
+            float l1[PP][16];
 #pragma unroll
-            for (int o4 = 0; o4 < DANBO_AGG_W / 4; ++o4) {
-                const float4 wv = __ldg(w1 + i * (DANBO_AGG_W / 4) + o4);
-                l1[4 * o4 + 0] = fmaf(mix[i], wv.x, l1[4 * o4 + 0]); l1[4 * o4 + 1] = fmaf(mix[i], wv.y, l1[4 * o4 + 1]);
-                l1[4 * o4 + 2] = fmaf(mix[i], wv.z, l1[4 * o4 + 2]); l1[4 * o4 + 3] = fmaf(mix[i], wv.w, l1[4 * o4 + 3]);
+            for (int o = 0; o < 16; ++o) {
+                const float b1 = __ldg(fc.agg_b1 + j * DANBO_AGG_W + oh * 16 + o);
+#pragma unroll
+                for (int u = 0; u < PP; ++u) l1[u][o] = b1;
+            }
+#pragma unroll
+            for (int i = 0; i < DANBO_AGG_W; ++i) {
+#pragma unroll
+                for (int o4 = 0; o4 < 4; ++o4) {
+                    const float4 wv = __ldg(w1 + i * (DANBO_AGG_W / 4) + oh * 4 + o4);
+#pragma unroll
+                    for (int u = 0; u < PP; ++u) {
+                        l1[u][4 * o4 + 0] = fmaf(mix[u][i], wv.x, l1[u][4 * o4 + 0]); l1[u][4 * o4 + 1] = fmaf(mix[u][i], wv.y, l1[u][4 * o4 + 1]);
+                        l1[u][4 * o4 + 2] = fmaf(mix[u][i], wv.z, l1[u][4 * o4 + 2]); l1[u][4 * o4 + 3] = fmaf(mix[u][i], wv.w, l1[u][4 * o4 + 3]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 0; o < 16; ++o) {
+                const float w2 = __ldg(fc.agg_w2 + j * DANBO_AGG_W + oh * 16 + o);
+#pragma unroll
+                for (int u = 0; u < PP; ++u) a[u] = fmaf(fmaxf(l1[u][o], 0.f), w2, a[u]);
             }
         }
-        float a = __ldg(fc.agg_b2 + j);
 #pragma unroll
-        for (int o = 0; o < DANBO_AGG_W; ++o) a = fmaf(fmaxf(l1[o], 0.f), __ldg(fc.agg_w2 + j * DANBO_AGG_W + o), a);
-        if (live) logits[(size_t)id * DANBO_J + j] = a;
+        for (int u = 0; u < PP; ++u)
+            if (live[u]) logits[(size_t)id[u] * DANBO_J + j] = a[u];
     }
 }
 
@@ -625,7 +674,7 @@ extern "C" int danbo_field_agg(const float* rays, int ray_stride, int n_rays, in
     DANBO_CHECK_LAUNCH();
     pair_bucket_kernel<true><<<blocks, 256, 0, st>>>(mask, active_ids, active_count, capacity, total, pw, pair_capacity);
     DANBO_CHECK_LAUNCH();
-    int pblocks = (pair_capacity / 32 + 3) / 4;
+    int pblocks = (pair_capacity / 64 + 24 + 3) / 4;                  // two 32-pair pieces per warp (+ one odd piece per bone)
     if (pblocks > num_sms * 8) pblocks = num_sms * 8;
     pair_logits_kernel<<<pblocks, 128, 0, st>>>(rays, ray_stride, S, z, active_ids, pose_skts, pose_vol, rays_per_pose,
                                                  n_poses, fc, pw, pair_capacity, logits);
