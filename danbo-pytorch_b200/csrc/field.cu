@@ -187,20 +187,25 @@ sample_mask_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, i
             const int rn = ray_first + slot;
             const float* r = rays + (size_t)rn * ray_stride;
             int pose = rn / rays_per_pose; if (pose >= n_poses) pose = n_poses - 1;
-            const float* sk = pose_skts + ((size_t)pose * DANBO_J + j) * 16;
-            const float* A = fc.align + j * 16;
+            // 16-byte loads: lanes walk over bones (64 B apart), so every load instruction costs one LSU pass per touched
+            // line whatever its width -- scalar loads made this table build the kernel's bottleneck (LSU 89 % busy)
+            const float4* sk4 = reinterpret_cast<const float4*>(pose_skts + ((size_t)pose * DANBO_J + j) * 16);
+            const float4* A4 = reinterpret_cast<const float4*>(fc.align + j * 16);
+            const float o0 = r[0], o1 = r[1], o2 = r[2], d0 = r[3], d1 = r[4], d2 = r[5];
             float c[3], d[3];
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                c[i] = sk[4 * i] * r[0] + sk[4 * i + 1] * r[1] + sk[4 * i + 2] * r[2] + sk[4 * i + 3];
-                d[i] = sk[4 * i] * r[3] + sk[4 * i + 1] * r[4] + sk[4 * i + 2] * r[5];
+                const float4 row = __ldg(sk4 + i);
+                c[i] = row.x * o0 + row.y * o1 + row.z * o2 + row.w;
+                d[i] = row.x * d0 + row.y * d1 + row.z * d2;
             }
             float cc[3], ee[3];
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 const float inv = 1.f / fabsf(__ldg(fc.axis_scale + j * 3 + i));
-                cc[i] = (A[4 * i] * c[0] + A[4 * i + 1] * c[1] + A[4 * i + 2] * c[2] + A[4 * i + 3]) * inv;
-                ee[i] = (A[4 * i] * d[0] + A[4 * i + 1] * d[1] + A[4 * i + 2] * d[2]) * inv;
+                const float4 a = __ldg(A4 + i);
+                cc[i] = (a.x * c[0] + a.y * c[1] + a.z * c[2] + a.w) * inv;
+                ee[i] = (a.x * d[0] + a.y * d[1] + a.z * d[2]) * inv;
             }
             tab[2 * e] = make_float4(cc[0], cc[1], cc[2], 0.f);
             tab[2 * e + 1] = make_float4(ee[0], ee[1], ee[2], 0.f);
@@ -341,7 +346,7 @@ pair_bucket_kernel(const uint32_t* __restrict__ mask, const int* __restrict__ ac
 // Two pairs per lane (a warp = 64 pairs of the SAME bone): every aggregation-net weight is a warp-uniform load feeding
 // 64 MACs.  With one pair per lane the kernel was bound by the load/store unit (one LSU pass per weight vector and per
 // feature gather against four FMA pipes), not by FP32 throughput.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 pair_logits_kernel(const float* __restrict__ rays, int ray_stride, int S, const float* __restrict__ z,
                    const int* __restrict__ active_ids, const float* __restrict__ pose_skts,
                    const float* __restrict__ pose_vol, int rays_per_pose, int n_poses, FieldConsts fc, PairWork pw,
@@ -472,8 +477,17 @@ field_rows_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, in
                   __nv_bfloat16* __restrict__ x_rows /* (rows,208) row-major copy for the backward pass, or null */) {
     int count = *active_count; if (count > capacity) count = capacity;
     const int total = n_rays * S;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
-        const int id = active_ids[e];
+    // A lane owns a row, and a row's 16-byte pieces lie in different 128-byte lines of the tile image (one LSU pass per
+    // lane per store, partial-line writes in L2).  Each warp therefore assembles its 32 rows of one 64-column chunk
+    // (4 KB, contiguous in the image) in shared memory and sends it with a bulk copy; two buffers per warp.
+    __shared__ __align__(128) uint8_t stage[4][2][4096];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int n_flush = 0;
+    for (int base = blockIdx.x * blockDim.x; base < count; base += gridDim.x * blockDim.x) {
+        if (base + warp * 32 >= count) break;           // this warp's rows (and those of its later tiles) do not exist
+        const int e = base + threadIdx.x;
+        const bool live = e < count;
+        const int id = live ? active_ids[e] : total;
         float hbar[DANBO_FEAT];
 #pragma unroll
         for (int i = 0; i < DANBO_FEAT; ++i) hbar[i] = 0.f;
@@ -502,8 +516,8 @@ field_rows_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, in
                 for (int i = 0; i < DANBO_FEAT; ++i) hbar[i] = fmaf(p, h[i], hbar[i]);
             }
         }
-        row_ray[e] = n;
-        if (hbar_out) {
+        if (live) row_ray[e] = n;
+        if (hbar_out && live) {
             float4* ho = reinterpret_cast<float4*>(hbar_out + (size_t)e * 16);
             ho[0] = make_float4(hbar[0], hbar[1], hbar[2], hbar[3]);   ho[1] = make_float4(hbar[4], hbar[5], hbar[6], hbar[7]);
             ho[2] = make_float4(hbar[8], hbar[9], hbar[10], hbar[11]); ho[3] = make_float4(hbar[12], hbar[13], hbar[14], 0.f);
@@ -529,8 +543,27 @@ field_rows_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, in
             const uint32_t b = __bfloat16_as_ushort(__float2bfloat16_rn(v));
             if (col & 1) pk[(col & 7) >> 1] |= b << 16; else pk[(col & 7) >> 1] = b;
             if ((col & 7) == 7) {
-                *reinterpret_cast<uint4*>(xt + sw128_offset((uint32_t)rr, (uint32_t)(col - 7))) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                if (x_rows) *reinterpret_cast<uint4*>(x_rows + (size_t)e * 208 + (col - 7)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                const int chunk = (col - 7) >> 6, unit = ((col - 7) & 63) >> 3;
+                if (unit == 0) {                         // first piece of a chunk: its buffer must have been read out
+                    if (n_flush >= 2) {
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        __syncwarp();
+                    }
+                }
+                const uint32_t dst = smem_u32(stage[warp][n_flush & 1]) + (uint32_t)(lane * 128 + ((unit ^ (lane & 7)) << 4));
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+                if (x_rows && live) *reinterpret_cast<uint4*>(x_rows + (size_t)e * 208 + (col - 7)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                if (unit == 7 || col == 207) {           // chunk complete (the last one holds 16 of its 64 columns)
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        uint8_t* gdst = xt + chunk * 16384 + warp * 4096;
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                     ::"l"(gdst), "r"(smem_u32(stage[warp][n_flush & 1])), "r"(4096u) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    ++n_flush;
+                }
             }
             // after the last column of an octave (col == 14 + 30 (f+1)) advance every feature to the next octave
             if (col >= 44 && (col - 44) % 30 == 0 && col < 194) {
@@ -539,6 +572,7 @@ field_rows_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, in
             }
         }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // shared memory is read out before the block ends
 }
 
 // ---------------------------------------------------------------------------------------------------------
