@@ -143,11 +143,14 @@ def run_ours(opt):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # every rank renders a fixed number of rays per step: exchange the shard sizes once, not per step
+    shard_sizes = parallel.gather_sizes(n_rays, device) if world > 1 else None
+
     def step_device(graphed=True):
         ret = caster.render_graphed(rays_dev, **kw_dev) if graphed else caster(rays_dev, **kw_dev)
         pix = parallel.pack_pixels(ret)
         if world > 1:
-            pix = parallel.allgather_rows(pix)
+            pix = parallel.allgather_rows(pix, shard_sizes)
         return pix
 
     # pinned host inputs for the end-to-end path
@@ -159,7 +162,7 @@ def run_ours(opt):
         ret = caster.render_graphed(rays_host, **kw_host)   # H2D of the (n,11) ray batch happens inside
         pix = parallel.pack_pixels(ret)
         if world > 1:
-            pix_all = parallel.allgather_rows(pix)
+            pix_all = parallel.allgather_rows(pix, shard_sizes)
         pix_host.copy_(pix, non_blocking=True)              # D2H of the 20 B / ray result
         torch.cuda.current_stream().synchronize()
         return pix_host
@@ -227,7 +230,7 @@ def run_ours(opt):
             dist.destroy_process_group()
         return
     peaks = measured_peaks()
-    total_rays = n_rays * world * opt.steps
+    total_rays = (sum(shard_sizes) if world > 1 else n_rays) * opt.steps       # every rank renders its own view
     value = total_rays / (dev_ms / 1e3)
     flops = MLP_FLOP_PER_SAMPLE * float(sum(mlp_rows))
     mlp_s = sum(mlp_ms) / 1e3

@@ -43,23 +43,34 @@ def shard_range(n, rank, world_size, align=REF_CHUNK):
     return min(b0 * align, n), min(b1 * align, n)
 
 
+def gather_sizes(n_local, device):
+    """First-dimension sizes of every rank's shard (one tiny all-gather + host read): call once, outside hot loops."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return [int(n_local)]
+    ws = dist.get_world_size()
+    sz = torch.tensor([int(n_local)], device=device, dtype=torch.int64)
+    all_sz = torch.zeros(ws, device=device, dtype=torch.int64)
+    dist.all_gather_into_tensor(all_sz, sz)
+    return [int(v) for v in all_sz.tolist()]
+
+
 def allgather_rows(local, sizes=None):
-    """All-gather tensors that differ in their first dimension -> the concatenation, on every rank."""
+    """All-gather tensors that differ in their first dimension -> the concatenation, on every rank.  With `sizes` given
+    (see gather_sizes) the call is one collective and involves no host synchronisation."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return local
     ws = dist.get_world_size()
     if sizes is None:
-        sz = torch.tensor([local.shape[0]], device=local.device, dtype=torch.int64)
-        all_sz = [torch.zeros_like(sz) for _ in range(ws)]
-        dist.all_gather(all_sz, sz)
-        sizes = [int(s.item()) for s in all_sz]
+        sizes = gather_sizes(local.shape[0], local.device)
     m = max(sizes)
-    pad = local
+    pad = local.contiguous()
     if local.shape[0] < m:
         pad = torch.cat([local, local.new_zeros((m - local.shape[0],) + tuple(local.shape[1:]))], 0)
-    out = [torch.empty_like(pad) for _ in range(ws)]
-    dist.all_gather(out, pad.contiguous())
-    return torch.cat([o[:s] for o, s in zip(out, sizes)], 0)
+    out = torch.empty((ws * m,) + tuple(local.shape[1:]), device=local.device, dtype=local.dtype)
+    dist.all_gather_into_tensor(out, pad)
+    if all(s == m for s in sizes):
+        return out
+    return torch.cat([out[r * m:r * m + s] for r, s in enumerate(sizes)], 0)
 
 
 def pack_pixels(ret):
