@@ -127,3 +127,31 @@ def test_anerf_render_end_to_end():
     with pytest.raises(NotImplementedError):
         caster(rb, N_samples=args.N_samples, kp_batch=e(fx["pose_kps"][None]), skts=e(skts), cyls=e(cyl), bones=e(bones),
                cams=fx["cams"].to(DEV), N_uniques=1, perturb=False, N_importance=args.N_importance, nerf_type="nerf")
+
+
+def test_anerf_full_size_properties():
+    """Config #4 at a full-size image block (512x512 crop of the workload, 96+48 samples): finite outputs, ranges,
+    and chunk invariance (a reference 4096-ray chunk rendered alone gives the same bits)."""
+    import danbo_b200 as db
+    from danbo_b200 import synthetic as syn, skeleton as sk, params
+    args = db.make_args("anerf_base", no_reload=True)
+    attrs = {"skel_type": sk.SMPLSkeleton, "near": syn.NEAR, "far": syn.FAR, "n_views": 8, "rest_pose": syn.rest_pose()}
+    _, kw_test, *_ = db.create_raycaster(args, attrs, device=DEV)
+    caster = kw_test["ray_caster"]
+    caster.network.load_state_dict(syn.synth_state_dict(params.anerf_param_shapes(), 0), strict=False)
+    caster.eval()
+    b = syn.render_batch(syn.make_pose(3), 512, 512)
+    b = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in b.items()}
+    N = b["ray_batch"].shape[0]
+    kw = dict(N_samples=args.N_samples, kp_batch=b["kp_batch"], skts=b["skts"], cyls=b["cyls"], bones=b["bones"],
+              cams=b["cams"], N_uniques=1, perturb=False, N_importance=args.N_importance, raw_noise_std=0., nerf_type="nerf")
+    out = caster(b["ray_batch"], nanmean_chunk=4096, **kw)
+    torch.cuda.synchronize()
+    assert out["rgb_map"].shape == (N, 3)
+    for k, v in out.items():
+        assert torch.isfinite(v).all(), k
+    assert float(out["acc_map"].min()) >= 0 and float(out["acc_map"].max()) <= 1.0
+    assert float(out["T_i"].sum(-1).max()) <= 1.0 + 1e-4
+    sl = slice(8192, 8192 + 4096)
+    sub = caster(b["ray_batch"][sl], **{k: (v[sl] if torch.is_tensor(v) and v.shape[0] == N else v) for k, v in kw.items()})
+    assert torch.equal(sub["rgb_map"], out["rgb_map"][sl]) and torch.equal(sub["acc_map"], out["acc_map"][sl])

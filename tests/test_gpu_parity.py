@@ -358,3 +358,33 @@ def test_render_images_and_density_grid_callers():
     full = caster(kps=t(pose["kps"]), skts=t(pose["skts"]), bones=t(pose["bones"]), radius=0.9, res=15, fwd_type="mesh")
     slabs = render.density_grid(caster, t(pose["kps"]), t(pose["skts"]), t(pose["bones"]), radius=0.9, res=15, slab_points=1024)
     assert torch.equal(full, slabs)
+
+
+def test_mlp_kernel_variants_bit_identical():
+    """The CTA-pair (cta_group::2) and the one-CTA-per-tile MLP kernels accumulate in the same order: same bits, on a
+    full 512x512 image (every tile pair, the odd tail tile included), and so do a shuffled and an ordered ray batch."""
+    from danbo_b200 import synthetic as syn
+    import danbo_b200
+    caster, args, P = make_caster("danbo_fast")
+    pose = syn.make_pose(5)
+    b = syn.render_batch(pose, 512, 512)
+    N = b["ray_batch"].shape[0]
+    kw = dict(N_samples=args.N_samples, kp_batch=b["kp_batch"], skts=b["skts"], cyls=b["cyls"], bones=b["bones"],
+              cams=b["cams"], N_uniques=1, perturb=False, N_importance=args.N_importance, raw_noise_std=0.)
+    prev = danbo_b200.kernels.set_mlp_cta_pair(True)
+    try:
+        out_pair = caster(b["ray_batch"], nanmean_chunk=4096, **kw)
+        danbo_b200.kernels.set_mlp_cta_pair(False)
+        out_single = caster(b["ray_batch"], nanmean_chunk=4096, **kw)
+    finally:
+        danbo_b200.kernels.set_mlp_cta_pair(prev)
+    for k in ("rgb_map", "acc_map", "disp_map", "rgb0", "alpha"):
+        assert torch.equal(out_pair[k], out_single[k]), k
+    # rays are independent: a permutation of the rays of one reference chunk permutes the pixels, bit for bit
+    sl = slice(4096 * 5, 4096 * 6)
+    sub = {k: (v[sl] if torch.is_tensor(v) and v.shape[0] == N else v) for k, v in kw.items()}
+    perm = torch.randperm(4096, generator=torch.Generator().manual_seed(0)).to(b["ray_batch"].device)
+    a = caster(b["ray_batch"][sl], **sub)
+    p = caster(b["ray_batch"][sl][perm], **sub)
+    # (near/far of rays that miss the cylinder take the chunk mean, which does not depend on the order)
+    assert torch.equal(a["rgb_map"][perm], p["rgb_map"]) and torch.equal(a["acc_map"][perm], p["acc_map"])
