@@ -19,7 +19,7 @@ from . import kernels as K
 from . import skeleton as sk
 from .networks import DanboField
 
-MAX_RAYS_PER_LAUNCH = 131072          # multiple of every sane `chunk`; bounds the size of the X tile buffer
+MAX_RAYS_PER_LAUNCH = 262144          # multiple of every sane `chunk`; bounds the size of the X tile buffer (1.5 GB at danbo_fast density)
 
 
 class RayCaster(nn.Module):

@@ -388,3 +388,22 @@ def test_mlp_kernel_variants_bit_identical():
     p = caster(b["ray_batch"][sl][perm], **sub)
     # (near/far of rays that miss the cylinder take the chunk mean, which does not depend on the order)
     assert torch.equal(a["rgb_map"][perm], p["rgb_map"]) and torch.equal(a["acc_map"][perm], p["acc_map"])
+
+
+def test_launch_block_split_invariance():
+    """An image rendered as one launch block or split into several 65 536-ray blocks gives the same bits."""
+    from danbo_b200 import synthetic as syn, raycaster
+    caster, args, P = make_caster("danbo_fast")
+    b = syn.render_batch(syn.make_pose(7), 384, 384)
+    kw = dict(N_samples=args.N_samples, kp_batch=b["kp_batch"], skts=b["skts"], cyls=b["cyls"], bones=b["bones"],
+              cams=b["cams"], N_uniques=1, perturb=False, N_importance=args.N_importance, raw_noise_std=0.)
+    one = caster(b["ray_batch"], nanmean_chunk=4096, **kw)
+    old = raycaster.MAX_RAYS_PER_LAUNCH
+    raycaster.MAX_RAYS_PER_LAUNCH = 65536
+    try:
+        assert b["ray_batch"].shape[0] > 65536
+        split = caster(b["ray_batch"], nanmean_chunk=4096, **kw)
+    finally:
+        raycaster.MAX_RAYS_PER_LAUNCH = old
+    for k in ("rgb_map", "acc_map", "disp_map", "rgb0", "alpha", "T_i"):
+        assert torch.equal(one[k], split[k]), k
