@@ -155,8 +155,11 @@ composite_resample_kernel(const float* __restrict__ rays, int ray_stride, int n_
     const int n_cdf = S - 1;
     for (int j = lane; j < S_f; j += 32) {
         const float u = u_rand ? u_rand[(size_t)n * S_f + j] : u_vals[j];
-        int ind = 0;                                                // searchsorted(cdf, u, right=True)
-        for (int k = 0; k < n_cdf; ++k) ind += (sm.cdf[k] <= u) ? 1 : 0;
+        // searchsorted(cdf, u, right=True) = #{k : cdf[k] <= u}; the cdf is non-decreasing (a running sum of
+        // non-negative terms), so the count is the first index with cdf > u: binary search
+        int lo = 0, hi = n_cdf;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (sm.cdf[mid] <= u) lo = mid + 1; else hi = mid; }
+        const int ind = lo;
         const int below = ind - 1 > 0 ? ind - 1 : 0;
         const int above = ind < n_cdf - 1 ? ind : n_cdf - 1;
         const float cb = sm.cdf[below], ca = sm.cdf[above];
@@ -175,11 +178,36 @@ composite_resample_kernel(const float* __restrict__ rays, int ray_stride, int n_
     const int St = S + S_f;
     for (int i = lane; i < St; i += 32) sm.cat[i] = i < S ? sm.z[i] : sm.zs[i - S];
     __syncwarp();
-    for (int i = lane; i < St; i += 32) {
-        const float v = sm.cat[i];
-        int rank = 0;
-        for (int k = 0; k < St; ++k) { const float c = sm.cat[k]; rank += (c < v || (c == v && k < i)) ? 1 : 0; }
-        sm.order[rank] = i;
+    // rank of element i in the stable sort = #{k : cat[k] < cat[i] or (cat[k] == cat[i] and k < i)}.  When both halves are
+    // already non-decreasing (always for z; for z_samples whenever u is sorted, i.e. eval) this is
+    //   coarse i: i + #{z_samples < z_i}        fine j: S + j' ... = #{z <= zs_j} + j
+    // by two binary searches; otherwise (train mode, random u) the general count.  Checked per ray, so exact either way.
+    bool sorted = true;
+    for (int i = lane; i < St; i += 32)
+        if (i + 1 < St && i + 1 != S) sorted = sorted && !(sm.cat[i + 1] < sm.cat[i]);
+    sorted = __all_sync(0xffffffffu, sorted);
+    if (sorted) {
+        for (int i = lane; i < St; i += 32) {
+            const float v = sm.cat[i];
+            int rank;
+            if (i < S) {
+                int lo = 0, hi = S_f;                               // first fine index with zs >= v
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (sm.zs[mid] < v) lo = mid + 1; else hi = mid; }
+                rank = i + lo;
+            } else {
+                int lo = 0, hi = S;                                 // first coarse index with z > v
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (sm.z[mid] <= v) lo = mid + 1; else hi = mid; }
+                rank = lo + (i - S);
+            }
+            sm.order[rank] = i;
+        }
+    } else {
+        for (int i = lane; i < St; i += 32) {
+            const float v = sm.cat[i];
+            int rank = 0;
+            for (int k = 0; k < St; ++k) { const float c = sm.cat[k]; rank += (c < v || (c == v && k < i)) ? 1 : 0; }
+            sm.order[rank] = i;
+        }
     }
     __syncwarp();
     for (int i = lane; i < St; i += 32) {
