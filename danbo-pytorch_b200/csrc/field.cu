@@ -346,6 +346,7 @@ pair_bucket_kernel(const uint32_t* __restrict__ mask, const int* __restrict__ ac
 // Two pairs per lane (a warp = 64 pairs of the SAME bone): every aggregation-net weight is a warp-uniform load feeding
 // 64 MACs.  With one pair per lane the kernel was bound by the load/store unit (one LSU pass per weight vector and per
 // feature gather against four FMA pipes), not by FP32 throughput.
+template <bool kOnePose>
 __global__ void __launch_bounds__(128, 4)
 pair_logits_kernel(const float* __restrict__ rays, int ray_stride, int S, const float* __restrict__ z,
                    const int* __restrict__ active_ids, const float* __restrict__ pose_skts,
@@ -353,6 +354,14 @@ pair_logits_kernel(const float* __restrict__ rays, int ray_stride, int S, const 
                    int pair_capacity, float* __restrict__ logits /* (n_rays*S, 24), visible entries only */) {
     constexpr int PP = 2;                                // pairs per lane
     const int lane = threadIdx.x & 31;
+    // One pose (every render call): its 24 x 240 feature lines (23 KB) are staged in shared memory, where the 30
+    // data-dependent taps per (pair, neighbour) cost ~1 pass each instead of one per touched 128-byte line of L1.
+    __shared__ __align__(16) float vol_s[kOnePose ? DANBO_J * DANBO_VOL : 4];
+    if (kOnePose) {
+        const float4* src = reinterpret_cast<const float4*>(pose_vol);
+        for (int i = threadIdx.x; i < DANBO_J * DANBO_VOL / 4; i += blockDim.x) reinterpret_cast<float4*>(vol_s)[i] = __ldg(src + i);
+        __syncthreads();
+    }
     const int* cnt = pw.count();
     // segments are padded to 32 pairs; a warp takes two consecutive 32-pair pieces of one bone's segment
     int n_chunks = 0;
@@ -403,7 +412,8 @@ pair_logits_kernel(const float* __restrict__ rays, int ray_stride, int S, const 
                 float x0, x1, x2;
                 bone_coords(pose_skts + ((size_t)pose[u] * DANBO_J + k) * 16, fc.align + k * 16, fc.axis_scale + k * 3,
                             px[u], py[u], pz[u], x0, x1, x2);
-                bone_features(pose_vol + ((size_t)pose[u] * DANBO_J + k) * DANBO_VOL, x0, x1, x2, h[u]);
+                if (kOnePose) bone_features<true>(vol_s + k * DANBO_VOL, x0, x1, x2, h[u]);
+                else bone_features<false>(pose_vol + ((size_t)pose[u] * DANBO_J + k) * DANBO_VOL, x0, x1, x2, h[u]);
             }
             const float4* w = reinterpret_cast<const float4*>(fc.agg_w0 + (size_t)k * DANBO_FEAT * DANBO_AGG_W);
 #pragma unroll
@@ -710,8 +720,12 @@ extern "C" int danbo_field_agg(const float* rays, int ray_stride, int n_rays, in
     DANBO_CHECK_LAUNCH();
     int pblocks = (pair_capacity / 64 + 24 + 3) / 4;                  // two 32-pair pieces per warp (+ one odd piece per bone)
     if (pblocks > num_sms * 8) pblocks = num_sms * 8;
-    pair_logits_kernel<<<pblocks, 128, 0, st>>>(rays, ray_stride, S, z, active_ids, pose_skts, pose_vol, rays_per_pose,
-                                                 n_poses, fc, pw, pair_capacity, logits);
+    if (n_poses == 1)
+        pair_logits_kernel<true><<<pblocks, 128, 0, st>>>(rays, ray_stride, S, z, active_ids, pose_skts, pose_vol, rays_per_pose,
+                                                           n_poses, fc, pw, pair_capacity, logits);
+    else
+        pair_logits_kernel<false><<<pblocks, 128, 0, st>>>(rays, ray_stride, S, z, active_ids, pose_skts, pose_vol, rays_per_pose,
+                                                            n_poses, fc, pw, pair_capacity, logits);
     DANBO_CHECK_LAUNCH();
     int rblocks = (capacity + 127) / 128;
     if (rblocks > num_sms * 16) rblocks = num_sms * 16;

@@ -76,7 +76,9 @@ __device__ __forceinline__ int seg_start(const int* __restrict__ count, int j) {
     return off;
 }
 
-// features of bone k at local coordinates x (closed form of misc.py:331-351 + window, gnn_backbone.py:802-826)
+// features of bone k at local coordinates x (closed form of misc.py:331-351 + window, gnn_backbone.py:802-826).
+// kShared: vol_k points into shared memory (plain loads) instead of global memory (read-only cache loads).
+template <bool kShared = false>
 __device__ __forceinline__ void bone_features(const float* __restrict__ vol_k, float x0, float x1, float x2, float (&h)[DANBO_FEAT]) {
     const float a2 = x0 * x0, b2 = x1 * x1, c2 = x2 * x2;
     const float win = expf(-2.f * (a2 * a2 * a2 + b2 * b2 * b2 + c2 * c2 * c2));
@@ -91,8 +93,8 @@ __device__ __forceinline__ void bone_features(const float* __restrict__ vol_k, f
 #pragma unroll
         for (int f = 0; f < 5; ++f) {
             const float* line = vol_k + f * (DANBO_RES * 3) + a;
-            const float v0 = ok0 ? __ldg(line + i0 * 3) : 0.f;
-            const float v1 = ok1 ? __ldg(line + i1 * 3) : 0.f;
+            const float v0 = ok0 ? (kShared ? line[i0 * 3] : __ldg(line + i0 * 3)) : 0.f;
+            const float v1 = ok1 ? (kShared ? line[i1 * 3] : __ldg(line + i1 * 3)) : 0.f;
             h[f * 3 + a] = (v0 * w0 + v1 * w1) * win;
         }
     }
