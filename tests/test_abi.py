@@ -39,3 +39,28 @@ def test_unsupported_flags_raise():
     for kw in ({"agg_type": "softmax"}, {"gnn_backbone": "PNBGNN"}, {"netwidth": 128}, {"nerf_type": "nerf"}):
         with pytest.raises(NotImplementedError):
             danbo_b200.raycaster.check_args(danbo_b200.make_args("danbo_base", **kw))
+
+
+def test_anerf_flag_subset():
+    """nerf_type='nerf' (A-NeRF, BASELINE config #4): the preset passes the flag check, anything outside the shipped
+    anerf_base.txt subset raises (no silent fallback)."""
+    import pytest
+    import danbo_b200 as db
+    from danbo_b200 import anerf
+    args = db.make_args("anerf_base", no_reload=True)
+    anerf.check_anerf_args(args)
+    for k, v in (("netwidth", 256), ("multires", 10), ("cutoff_viewdir", False), ("view_type", "world"),
+                 ("bone_type", "axisang"), ("cutoff_mm", 400.0)):
+        bad = db.make_args("anerf_base", no_reload=True, **{k: v})
+        with pytest.raises(NotImplementedError):
+            anerf.check_anerf_args(bad)
+    # parameter inventory = the reference's state_dict (probe in oracle/gen_golden.py), minus the embedder constants
+    from danbo_b200 import params
+    shapes = params.anerf_param_shapes()
+    assert shapes["pts_linears.0.weight"] == (448, 432) and shapes["pts_linears.5.weight"] == (448, 880)
+    assert shapes["views_linears.0.weight"] == (224, 1224) and shapes["rgb_linear.weight"] == (3, 224)
+    net = anerf.AnerfField()
+    sd = net.state_dict()
+    assert set(shapes) <= set(sd) and {"pe_fn.cutoff_dist", "pe_fn.tau", "dirs_pe_fn.cutoff_dist", "dirs_pe_fn.tau"} <= set(sd)
+    for k, shp in shapes.items():
+        assert tuple(sd[k].shape) == tuple(shp), k
