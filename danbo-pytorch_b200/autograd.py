@@ -53,7 +53,17 @@ class _RenderBlock(torch.autograd.Function):
         g_rgb0, g_acc0 = cg(g["rgb0"], n, 3), cg(g["acc0"], n)
         g_confd = None if g["confd"] is None else g["confd"].contiguous().float()
         P = dict(zip(PARAM_NAMES, ctx.params))
-        G = {name: torch.zeros_like(p, dtype=torch.float32) for name, p in P.items()}
+        # Every backward kernel ACCUMULATES into its gradient buffers.  When the trainer keeps all gradients in one flat,
+        # pre-zeroed bucket (parallel.GradBucket, opted in through caster.grads_in_place) the kernels add straight into
+        # the parameters' .grad views and this node returns no parameter gradients: that removes one zero-fill and one
+        # AccumulateGrad add per parameter tensor (86 launches per iteration).
+        in_place = bool(getattr(ctx.caster, "grads_in_place", False)) and all(
+            p.grad is not None and p.grad.dtype == torch.float32 and p.grad.is_contiguous() and p.grad.shape == p.shape
+            for p in ctx.params)
+        if in_place:
+            G = {name: p.grad for name, p in P.items()}
+        else:
+            G = {name: torch.zeros_like(p, dtype=torch.float32) for name, p in P.items()}
         d_raw0, d_raw1 = zeros(n * S_c + n, 4), zeros(n * S_f, 4)
         gl0 = gl1 = None
         if g_confd is not None:
@@ -83,6 +93,8 @@ class _RenderBlock(torch.autograd.Function):
         K.ray_bias_bwd(rays, k["cam_idx"], k["codes"], P["views_linears.0.weight"], d_ray_bias,
                        G["views_linears.0.weight"], G["views_linears.0.bias"], G["framecodes.codes.weight"])
         ctx.keep = None
+        if in_place:
+            return (None, None, d_vol) + (None,) * len(PARAM_NAMES)
         return (None, None, d_vol) + tuple(G[name] for name in PARAM_NAMES)
 
 

@@ -93,6 +93,7 @@ class TrainStep:
         self.caster, self.args, self.world = caster, args, world_size
         params = [p for p in caster.network.parameters() if p.requires_grad]
         self.bucket = parallel.GradBucket(params)
+        caster.grads_in_place = True            # backward kernels add into the bucket's views (see autograd._RenderBlock)
         cuda = params[0].is_cuda
         if optimizer is None:
             # default: the single-launch Adam over flat arenas; pass a torch optimizer to keep the reference's

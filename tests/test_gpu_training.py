@@ -337,3 +337,34 @@ def test_flat_adam_matches_torch_adam():
         assert q.data_ptr() >= opt.flat.data_ptr() and q.data_ptr() < opt.flat.data_ptr() + opt.flat.numel() * 4
         err = float((p - q).abs().max())
         assert err <= 2e-6 * max(float(p.abs().max()), 1.0), err
+
+
+def test_grads_in_place_equals_returned_grads():
+    """With a GradBucket the backward kernels add straight into the parameters' .grad views (caster.grads_in_place);
+    the gradients must equal those of the ordinary path (fresh buffers returned to autograd) on the same random draws."""
+    from danbo_b200 import synthetic as syn, training, parallel
+    batch = syn.training_batch(2, 64, seed=5)
+    batch = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in batch.items()}
+
+    def run(in_place):
+        caster, args, _ = make_caster("danbo_cfg3", train=True)
+        params = [p for p in caster.network.parameters() if p.requires_grad]
+        if in_place:
+            bucket = parallel.GradBucket(params)
+            caster.grads_in_place = True
+        torch.manual_seed(11)
+        preds = caster(batch["ray_batch"], N_samples=args.N_samples, kp_batch=batch["kp_batch"], skts=batch["skts"],
+                       cyls=batch["cyls"], bones=batch["bones"], cams=batch["cams"], N_uniques=batch["N_uniques"],
+                       perturb=args.perturb, N_importance=args.N_importance, raw_noise_std=args.raw_noise_std)
+        loss, _ = training.compute_loss(args, preds, batch, caster.network)
+        loss.backward()
+        return {n: p.grad.detach().clone() for n, p in caster.network.named_parameters() if p.grad is not None}, float(loss)
+
+    ga, la = run(False)
+    gb, lb = run(True)
+    assert la == lb
+    assert set(ga) == set(gb)
+    for n in ga:
+        scale = max(float(ga[n].abs().max()), 1e-12)
+        err = float((ga[n] - gb[n]).abs().max())
+        assert err <= 2e-4 * scale + 1e-9, (n, err, scale)       # atomics reorder fp32 sums between runs
