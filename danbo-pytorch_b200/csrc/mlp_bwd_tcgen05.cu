@@ -26,6 +26,7 @@ constexpr uint32_t kAccCol = 0, kActCol = 256;
 
 struct __align__(1024) Smem {
     uint8_t w[kStages][kStageBytes];
+    uint8_t stage[8][4096];              // per epilogue warp: [64 features][32 rows] bf16, to write deltas row-transposed
     float w_rgb[3 * 128];
     float w_alpha[256];
     uint64_t w_full[kStages];
@@ -45,6 +46,31 @@ __device__ __forceinline__ int st_mask_plane(int s) { const int t[kDgradStages] 
 // delta plane written by stage s (-1: none); plane 0 = delta9 comes from the prologue
 __device__ __forceinline__ int st_delta_plane(int s) { const int t[kDgradStages] = {1, 2, 3, 4, -1, 5, 6, 7, 8, 9, -1}; return t[s]; }
 
+// A warp's 32 rows x 64 features (thread = row, pk = its 64 bf16 values packed in pairs) -> the row-TRANSPOSED image of a
+// plane (tr_offset layout, F = 256: blocks of 64 rows, 16-byte units of 8 consecutive rows per feature), which is what
+// the weight-gradient MMAs (K = rows) bulk-copy as operands.  Goes through a 4 KB shared-memory block: every thread
+// drops its values feature-major, then the warp copies out 16-byte units.  Replaces a separate transpose pass over HBM.
+__device__ __forceinline__ void store_transposed(uint32_t stage, int lane, const uint32_t (&pk)[32], uint8_t* __restrict__ plane_t,
+                                                 int block64, int rowgroup0, int col0) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const uint32_t a = stage + (uint32_t)((2 * j) * 64 + lane * 2);
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)(pk[j] & 0xffffu)) : "memory");
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(a + 64u), "h"((unsigned short)(pk[j] >> 16)) : "memory");
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int u = lane + 32 * i, f = u >> 2, g = u & 3;
+        uint4 v;
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "r"(stage + (uint32_t)(f * 64 + g * 16)) : "memory");
+        const int gf = col0 + f, rg = rowgroup0 + g;
+        *reinterpret_cast<uint4*>(plane_t + (size_t)block64 * (256 * 128) + (gf >> 3) * 1024 + (gf & 7) * 128 + ((rg ^ (gf & 7)) << 4)) = v;
+    }
+    __syncwarp();
+}
+
 // ---- epilogue bodies of the dgrad chain: the stage kind is a template parameter and whatever does not depend on the
 // accumulator (relu masks = saved forward activations) is fetched before the wait on the MMA (see mlp_tcgen05.cu).
 struct EpiArgs {
@@ -56,6 +82,8 @@ struct EpiArgs {
     const float* w_alpha;      // shared memory, at col0
     const uint4* mask;         // forward activation of the layer whose relu gates this delta (row-major bf16), or null
     uint4* delta_out;          // this stage's delta plane (row-major bf16), or null
+    uint8_t* delta_t;          // the same plane's row-transposed image, or null
+    uint32_t stage; int lane, block64, rowgroup0;
     float* dx;                 // dX row (208 floats)
 };
 
@@ -98,9 +126,9 @@ __device__ __forceinline__ void epi_delta(const EpiArgs& E) {
     tmem_ld32(E.acc, v[0]);
     tmem_ld32(E.acc + 32, v[1]);
     tmem_wait_ld();
+    uint32_t pk[32];
 #pragma unroll
     for (int gq = 0; gq < 2; ++gq) {
-        uint32_t pk[16];
 #pragma unroll
         for (int c8 = 0; c8 < 4; ++c8) {
             const uint32_t mw[4] = {m[gq * 4 + c8].x, m[gq * 4 + c8].y, m[gq * 4 + c8].z, m[gq * 4 + c8].w};
@@ -117,15 +145,17 @@ __device__ __forceinline__ void epi_delta(const EpiArgs& E) {
                     if (!(__uint_as_float(mw[i] & 0xffff0000u) > 0.f)) a1 = 0.f;
                 }
                 if (!E.valid) { a0 = 0.f; a1 = 0.f; }
-                pk[c8 * 4 + i] = pack_bf16(a0, a1);
+                pk[gq * 16 + c8 * 4 + i] = pack_bf16(a0, a1);
             }
         }
-        tmem_st16(E.act_out + 16 * gq, pk);
+        tmem_st16(E.act_out + 16 * gq, *reinterpret_cast<const uint32_t(*)[16]>(&pk[gq * 16]));
         if (E.delta_out != nullptr) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) E.delta_out[gq * 4 + i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+            for (int i = 0; i < 4; ++i)
+                E.delta_out[gq * 4 + i] = make_uint4(pk[gq * 16 + 4 * i], pk[gq * 16 + 4 * i + 1], pk[gq * 16 + 4 * i + 2], pk[gq * 16 + 4 * i + 3]);
         }
     }
+    if (E.delta_t != nullptr) store_transposed(E.stage, E.lane, pk, E.delta_t, E.block64, E.rowgroup0, E.col0);
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -137,6 +167,7 @@ dgrad_kernel(const uint8_t* __restrict__ wstream,            // [84][16 KB] tran
              const __nv_bfloat16* __restrict__ g_save,       // [cap][128]
              int cap,
              __nv_bfloat16* __restrict__ delta_save,         // [10][cap][256] deltas (row-major, bf16)
+             uint8_t* __restrict__ delta_t,                  // [10][blocks of 64 rows][32 KB] the same, row-transposed
              float* __restrict__ dX) {                       // [cap][208]
     extern __shared__ uint8_t smem_raw[];
     Smem& S = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
@@ -216,10 +247,14 @@ dgrad_kernel(const uint8_t* __restrict__ wstream,            // [84][16 KB] tran
         const int q = warp & 3, ch = (warp - 2) >> 2;
         const int row = q * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const uint32_t stage_addr = smem_u32(S.stage[warp - 2]);
+        const int n_blk64 = (cap + 63) / 64;
+        const size_t plane_t_bytes = (size_t)n_blk64 * (256 * 128);
         uint32_t f0 = 0, f1 = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             const int grow = t * DANBO_TILE_M + row;
             const bool valid = grow < n_rows;
+            const int blk64 = t * 2 + (q >> 1);                  // 64-row block of this warp's rows in the transposed images
             float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
             if (valid) g = reinterpret_cast<const float4*>(d_raw)[row_sample[grow]];
             // ---- prologue: delta9 = (d rgb . W_rgb) * [g > 0] for this thread's 64 of the 128 view-layer units
@@ -249,6 +284,8 @@ dgrad_kernel(const uint8_t* __restrict__ wstream,            // [84][16 KB] tran
 #pragma unroll
                     for (int i = 0; i < 8; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
                 }
+                if (delta_t != nullptr && blk64 < n_blk64)
+                    store_transposed(stage_addr, lane, pk, delta_t, blk64, (q & 1) * 4, ch * 64);
                 tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
@@ -268,6 +305,8 @@ dgrad_kernel(const uint8_t* __restrict__ wstream,            // [84][16 KB] tran
                     E.w_alpha = S.w_alpha + E.col0;
                     E.mask = mp >= 0 ? reinterpret_cast<const uint4*>(act_save + ((size_t)mp * cap + (valid ? grow : 0)) * 256 + E.col0) : nullptr;
                     E.delta_out = (dp >= 0 && grow < cap) ? reinterpret_cast<uint4*>(delta_save + ((size_t)dp * cap + grow) * 256 + E.col0) : nullptr;
+                    E.delta_t = (dp >= 0 && delta_t != nullptr && blk64 < n_blk64) ? delta_t + (size_t)dp * plane_t_bytes : nullptr;
+                    E.stage = stage_addr; E.lane = lane; E.block64 = blk64; E.rowgroup0 = (q & 1) * 4;
                     E.dx = dX + (size_t)(valid ? grow : 0) * 208;
                     if (s == 4) epi_dx<false>(E);
                     else if (s == 10) epi_dx<true>(E);
@@ -522,7 +561,8 @@ extern "C" int danbo_pack_mlp_dgrad(const float* const* w_pts, const float* w_fe
 // of pts_linears.7..0.  dX (cap,208) fp32 is fully written for valid rows.
 extern "C" int danbo_mlp_dgrad(const void* wstream_t, const float* w_rgb, const float* w_alpha, const float* d_raw,
                                const int* row_sample, const int* rows_dev, int max_rows, const void* act_save,
-                               const void* g_save, int cap, void* delta_save, float* dX, int num_sms, void* stream) {
+                               const void* g_save, int cap, void* delta_save, void* delta_t, float* dX, int num_sms,
+                               void* stream) {
     if (max_rows <= 0) return 0;
     const int smem = (int)sizeof(mlpb::Smem) + 1024;
     static bool attr = false;
@@ -535,7 +575,7 @@ extern "C" int danbo_mlp_dgrad(const void* wstream_t, const float* w_rgb, const 
     int grid = num_sms < tiles ? num_sms : tiles;
     mlpb::dgrad_kernel<<<grid, mlpb::kThreads, smem, (cudaStream_t)stream>>>(
         (const uint8_t*)wstream_t, w_rgb, w_alpha, d_raw, row_sample, rows_dev, (const __nv_bfloat16*)act_save,
-        (const __nv_bfloat16*)g_save, cap, (__nv_bfloat16*)delta_save, dX);
+        (const __nv_bfloat16*)g_save, cap, (__nv_bfloat16*)delta_save, (uint8_t*)delta_t, dX);
     DANBO_CHECK_LAUNCH();
     return 0;
 }
@@ -546,17 +586,19 @@ extern "C" int danbo_mlp_dgrad(const void* wstream_t, const float* w_rgb, const 
 //   dw[11] = { views_linears.0.weight (128,411), feature_linear.weight, pts_linears.7, .6, .5 (256,451), .4, .3, .2, .1,
 //              .0 (256,195) } -- wait order below; db[9] = { feature_linear.bias, pts_linears.7..0 bias }.  Accumulated.
 extern "C" int danbo_mlp_wgrad(const void* act_save, const void* x_rows, const void* delta_save, int cap,
-                               const int* rows_dev, int max_rows, void* deltaT, void* actT, float* partial,
-                               float* const* dw, float* const* db, void* stream) {
+                               const int* rows_dev, int max_rows, void* deltaT, int delta_t_ready, void* actT,
+                               float* partial, float* const* dw, float* const* db, void* stream) {
     if (max_rows <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     const int blocks = (cap + 63) / 64;
     const size_t plane_bytes = (size_t)blocks * 256 * 128;
     const int used_blocks = (max_rows + 63) / 64;
-    // 1. transposes: deltas (10 planes), activations (9 planes), X
-    mlpb::transpose_kernel<<<dim3(used_blocks, 4, 10), 256, 0, st>>>((const __nv_bfloat16*)delta_save, cap, 256, 256, rows_dev,
-                                                                      (uint8_t*)deltaT, plane_bytes);
-    DANBO_CHECK_LAUNCH();
+    // 1. transposes: deltas (10 planes; skipped when danbo_mlp_dgrad wrote deltaT itself), activations (9 planes), X
+    if (!delta_t_ready) {
+        mlpb::transpose_kernel<<<dim3(used_blocks, 4, 10), 256, 0, st>>>((const __nv_bfloat16*)delta_save, cap, 256, 256, rows_dev,
+                                                                          (uint8_t*)deltaT, plane_bytes);
+        DANBO_CHECK_LAUNCH();
+    }
     mlpb::transpose_kernel<<<dim3(used_blocks, 4, 9), 256, 0, st>>>((const __nv_bfloat16*)act_save, cap, 256, 256, rows_dev,
                                                                      (uint8_t*)actT, plane_bytes);
     DANBO_CHECK_LAUNCH();

@@ -476,14 +476,14 @@ def mlp_backward_tc(P, G, d_raw, active, fo, save, d_ray_bias, ws, repack=True):
     dX = torch.empty(cap, 208, device=dev, dtype=torch.float32)
     _lib.check(lib.danbo_mlp_dgrad(_p(ws.wstream), _p(P["rgb_linear.weight"]), _p(P["alpha_linear.weight"]), _p(d_raw),
                                    _p(active.ids), _p(active.count), cap, _p(save.act), _p(save.g), cap, _p(ws.delta),
-                                   _p(dX), num_sms(idx), _stream()), "danbo_mlp_dgrad")
+                                   _p(ws.deltaT), _p(dX), num_sms(idx), _stream()), "danbo_mlp_dgrad")
     dw_names = ["views_linears.0.weight", "feature_linear.weight"] + [f"pts_linears.{i}.weight" for i in range(7, -1, -1)]
     db_names = ["feature_linear.bias"] + [f"pts_linears.{i}.bias" for i in range(7, -1, -1)]
     dw = (ctypes.c_void_p * 10)(*[G[n].data_ptr() for n in dw_names])
     db = (ctypes.c_void_p * 9)(*[G[n].data_ptr() for n in db_names])
-    _lib.check(lib.danbo_mlp_wgrad(_p(save.act), _p(fo.x_rows), _p(ws.delta), cap, _p(active.count), cap, _p(ws.deltaT),
+    _lib.check(lib.danbo_mlp_wgrad(_p(save.act), _p(fo.x_rows), _p(ws.delta), cap, _p(active.count), cap, _p(ws.deltaT), 1,
                                    _p(ws.actT), _p(ws.partial), dw, db, _stream()), "danbo_mlp_wgrad")
-    _count(9)
+    _count(8)
     return dX
 
 

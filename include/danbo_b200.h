@@ -155,7 +155,9 @@ int danbo_colsum(const float* A, int lda, float* db, const int* rows_dev, int ma
 
 /* Tensor-core (tcgen05) M1 backward.  danbo_mlp_bwd_workspace: sizes for a row capacity; danbo_pack_mlp_dgrad: transposed
  * bf16 weight tiles (once per iteration); danbo_mlp_dgrad: fused data-gradient chain (deltas of every layer saved as
- * bf16 planes [10][cap][256]: 0 = views_linears.0, 1 = d feature, 2..9 = pts_linears.7..0; dX (cap,208) fp32);
+ * bf16 planes [10][cap][256]: 0 = views_linears.0, 1 = d feature, 2..9 = pts_linears.7..0; dX (cap,208) fp32; with
+ * delta_t != NULL the planes are also written row-transposed (the deltaT workspace: operand images of the K = rows GEMMs),
+ * and danbo_mlp_wgrad is told so with delta_t_ready = 1 and skips that transpose pass);
  * danbo_mlp_wgrad: dW = delta^T . act (K = rows) for dw[10] = { views_linears.0.weight, feature_linear.weight,
  * pts_linears.7, .6, .5, .4, .3, .2, .1, .0 } and db[9] = { feature_linear.bias, pts_linears.7..0 bias }, accumulated. */
 int danbo_mlp_bwd_workspace(int cap, long long* wstream_bytes, long long* delta_bytes, long long* deltaT_bytes,
@@ -163,10 +165,10 @@ int danbo_mlp_bwd_workspace(int cap, long long* wstream_bytes, long long* delta_
 int danbo_pack_mlp_dgrad(const float* const* w_pts, const float* w_feat, const float* w_view, void* wstream, void* stream);
 int danbo_mlp_dgrad(const void* wstream_t, const float* w_rgb, const float* w_alpha, const float* d_raw,
                     const int* row_sample, const int* rows_dev, int max_rows, const void* act_save, const void* g_save,
-                    int cap, void* delta_save, float* dX, int num_sms, void* stream);
+                    int cap, void* delta_save, void* delta_t, float* dX, int num_sms, void* stream);
 int danbo_mlp_wgrad(const void* act_save, const void* x_rows, const void* delta_save, int cap, const int* rows_dev,
-                    int max_rows, void* deltaT, void* actT, float* partial, float* const* dw, float* const* db,
-                    void* stream);
+                    int max_rows, void* deltaT, int delta_t_ready, void* actT, float* partial, float* const* dw,
+                    float* const* db, void* stream);
 
 /* V1 backward: d ray_bias (n,128) -> grads of views_linears.0.weight[:,256:411] (written into the (128,411) layout),
  * its bias and the frame codes (core/networks/nerf.py:252-279, embedding.py:86-108). */

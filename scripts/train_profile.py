@@ -22,3 +22,10 @@ print("cpu issue ms/iter", (t1 - t0) * 100, "total ms/iter", (t2 - t0) * 100)
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     step(batch); torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=22, max_name_column_width=60))
+# kernels only, by launch count
+rows = [(e.key, e.count, e.device_time_total) for e in prof.key_averages() if e.device_type == torch.autograd.DeviceType.CUDA]
+rows.sort(key=lambda r: -r[1])
+tot_n, tot_t = sum(r[1] for r in rows), sum(r[2] for r in rows)
+print(f"--- {tot_n} kernel launches, {tot_t:.0f} us of kernel time; by count:")
+for k, n, t in rows[:40]:
+    print(f"{n:4d} x {t / max(n, 1):7.1f} us = {t:8.1f} us  {k[:100]}")
