@@ -32,9 +32,9 @@ import torch  # noqa: E402
 
 MLP_FLOP_PER_SAMPLE = 1354752          # SURVEY §8(a) row M1 (FlopCounter-verified): 677 376 MAC / sample
 # dram__bytes_read.sum + dram__bytes_write.sum of one mlp_kernel launch from the ncu --set full capture under profiles/
-# (profiles/r1b_ncu_mlp_summary.txt, launch 0: the 1.31 M-row coarse launch of a 131 072-ray block; 528 B/row read once
-# = the X tiles with K padded 208 -> 256, + 16 B/row of output)
-MLP_DRAM_BYTES_PER_LAUNCH = 692983808 + 25177856
+# (profiles/r1c_ncu_mlp_summary.txt, launch 0: the 2.13 M-row coarse launch of the whole 261 121-ray image; 528 B/row read
+# once = the X tiles with K padded 208 -> 256, + 16 B/row of output)
+MLP_DRAM_BYTES_PER_LAUNCH = 1126916000 + 34257152
 H = W = 512
 PRESET = "danbo_fast"
 
