@@ -179,36 +179,70 @@ sample_mask_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, i
     int n = 0, s = 0;
     __shared__ float4 tab[kTable ? kMaxRaysPerBlock * DANBO_J * 2 : 1];     // (c.xyz, e.xyz) per (ray slot, bone)
     const int ray_first = (blockIdx.x * kMaskBlock) / S;
+    __shared__ float4 pm[kTable ? DANBO_J * 3 : 1];                          // per bone: rows of [diag(1/|s|) A R | offset]
     if (kTable) {
         const int ray_last = min(n_rays - 1, (blockIdx.x * kMaskBlock + kMaskBlock - 1) / S);
         const int n_ent = (ray_last - ray_first + 1) * DANBO_J;
-        for (int e = threadIdx.x; e < n_ent; e += kMaskBlock) {
-            const int slot = e / DANBO_J, j = e - slot * DANBO_J;
-            const int rn = ray_first + slot;
-            const float* r = rays + (size_t)rn * ray_stride;
-            int pose = rn / rays_per_pose; if (pose >= n_poses) pose = n_poses - 1;
-            // 16-byte loads: lanes walk over bones (64 B apart), so every load instruction costs one LSU pass per touched
-            // line whatever its width -- scalar loads made this table build the kernel's bottleneck (LSU 89 % busy)
-            const float4* sk4 = reinterpret_cast<const float4*>(pose_skts + ((size_t)pose * DANBO_J + j) * 16);
-            const float4* A4 = reinterpret_cast<const float4*>(fc.align + j * 16);
-            const float o0 = r[0], o1 = r[1], o2 = r[2], d0 = r[3], d1 = r[4], d2 = r[5];
-            float c[3], d[3];
+        int pose_a = ray_first / rays_per_pose; if (pose_a >= n_poses) pose_a = n_poses - 1;
+        int pose_b = ray_last / rays_per_pose; if (pose_b >= n_poses) pose_b = n_poses - 1;
+        if (pose_a == pose_b) {
+            // one pose in this block (always in a render call): fold the two affine steps and the scale into one 3x4
+            // map per bone first (24 threads), then an entry costs two 3x3 products against shared memory.  The table
+            // is approximate by construction (faces within 2e-4 are re-evaluated exactly below), so folding is free.
+            if (threadIdx.x < DANBO_J) {
+                const int j = threadIdx.x;
+                const float4* sk4 = reinterpret_cast<const float4*>(pose_skts + ((size_t)pose_a * DANBO_J + j) * 16);
+                const float4* A4 = reinterpret_cast<const float4*>(fc.align + j * 16);
+                const float4 r0 = __ldg(sk4), r1 = __ldg(sk4 + 1), r2 = __ldg(sk4 + 2);
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const float4 row = __ldg(sk4 + i);
-                c[i] = row.x * o0 + row.y * o1 + row.z * o2 + row.w;
-                d[i] = row.x * d0 + row.y * d1 + row.z * d2;
+                for (int i = 0; i < 3; ++i) {
+                    const float inv = 1.f / fabsf(__ldg(fc.axis_scale + j * 3 + i));
+                    const float4 a = __ldg(A4 + i);
+                    pm[j * 3 + i] = make_float4((a.x * r0.x + a.y * r1.x + a.z * r2.x) * inv, (a.x * r0.y + a.y * r1.y + a.z * r2.y) * inv,
+                                                (a.x * r0.z + a.y * r1.z + a.z * r2.z) * inv,
+                                                (a.x * r0.w + a.y * r1.w + a.z * r2.w + a.w) * inv);
+                }
             }
-            float cc[3], ee[3];
+            __syncthreads();
+            for (int e = threadIdx.x; e < n_ent; e += kMaskBlock) {
+                const int slot = e / DANBO_J, j = e - slot * DANBO_J;
+                const float* r = rays + (size_t)(ray_first + slot) * ray_stride;
+                const float o0 = r[0], o1 = r[1], o2 = r[2], d0 = r[3], d1 = r[4], d2 = r[5];
+                const float4 m0 = pm[j * 3], m1 = pm[j * 3 + 1], m2 = pm[j * 3 + 2];
+                tab[2 * e] = make_float4(m0.x * o0 + m0.y * o1 + m0.z * o2 + m0.w, m1.x * o0 + m1.y * o1 + m1.z * o2 + m1.w,
+                                         m2.x * o0 + m2.y * o1 + m2.z * o2 + m2.w, 0.f);
+                tab[2 * e + 1] = make_float4(m0.x * d0 + m0.y * d1 + m0.z * d2, m1.x * d0 + m1.y * d1 + m1.z * d2,
+                                             m2.x * d0 + m2.y * d1 + m2.z * d2, 0.f);
+            }
+        } else {
+            for (int e = threadIdx.x; e < n_ent; e += kMaskBlock) {
+                const int slot = e / DANBO_J, j = e - slot * DANBO_J;
+                const int rn = ray_first + slot;
+                const float* r = rays + (size_t)rn * ray_stride;
+                int pose = rn / rays_per_pose; if (pose >= n_poses) pose = n_poses - 1;
+                // 16-byte loads: lanes walk over bones (64 B apart), so every load instruction costs one LSU pass per
+                // touched line whatever its width -- scalar loads made this table build the kernel's bottleneck
+                const float4* sk4 = reinterpret_cast<const float4*>(pose_skts + ((size_t)pose * DANBO_J + j) * 16);
+                const float4* A4 = reinterpret_cast<const float4*>(fc.align + j * 16);
+                const float o0 = r[0], o1 = r[1], o2 = r[2], d0 = r[3], d1 = r[4], d2 = r[5];
+                float c[3], d[3];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const float inv = 1.f / fabsf(__ldg(fc.axis_scale + j * 3 + i));
-                const float4 a = __ldg(A4 + i);
-                cc[i] = (a.x * c[0] + a.y * c[1] + a.z * c[2] + a.w) * inv;
-                ee[i] = (a.x * d[0] + a.y * d[1] + a.z * d[2]) * inv;
+                for (int i = 0; i < 3; ++i) {
+                    const float4 row = __ldg(sk4 + i);
+                    c[i] = row.x * o0 + row.y * o1 + row.z * o2 + row.w;
+                    d[i] = row.x * d0 + row.y * d1 + row.z * d2;
+                }
+                float cc[3], ee[3];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const float inv = 1.f / fabsf(__ldg(fc.axis_scale + j * 3 + i));
+                    const float4 a = __ldg(A4 + i);
+                    cc[i] = (a.x * c[0] + a.y * c[1] + a.z * c[2] + a.w) * inv;
+                    ee[i] = (a.x * d[0] + a.y * d[1] + a.z * d[2]) * inv;
+                }
+                tab[2 * e] = make_float4(cc[0], cc[1], cc[2], 0.f);
+                tab[2 * e + 1] = make_float4(ee[0], ee[1], ee[2], 0.f);
             }
-            tab[2 * e] = make_float4(cc[0], cc[1], cc[2], 0.f);
-            tab[2 * e + 1] = make_float4(ee[0], ee[1], ee[2], 0.f);
         }
         __syncthreads();
     }
