@@ -104,7 +104,10 @@ class AnerfCaster(RayCaster):
 
     # ---- render ---------------------------------------------------------------------------------------------
     def _render_prepared(self, rays, pose_skts, pose_bones, pose_cyls, cam_idx, skip=1, N_samples=96, N_importance=48,
-                         B=1.0, raw_noise_std=0., perturb=0., nanmean_chunk=None, _rand=None, _stages=None):
+                         B=1.0, raw_noise_std=0., perturb=0., nanmean_chunk=None, lindisp=False, _rand=None,
+                         _stages=None):
+        if lindisp:
+            raise NotImplementedError("lindisp is implemented for the DANBO field only (anerf_base.txt ships lindisp=False)")
         if self.training:
             raise NotImplementedError("A-NeRF (nerf_type='nerf') is render-only here: the backward kernels exist for the "
                                       "DANBO field only (BASELINE config #4 is a render benchmark)")

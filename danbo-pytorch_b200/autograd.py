@@ -32,7 +32,7 @@ class _RenderBlock(torch.autograd.Function):
             ret = caster._render_block(cfg["rays"], 0, cfg["skip"], cfg["pose_skts"], cfg["pose_cyls"], vol, cfg["cam_idx"],
                                        cfg["codes"], cfg["consts"], cfg["packed"], cfg["S_c"], cfg["S_f"], cfg["B"],
                                        cfg["raw_noise_std"], cfg["perturb"], True, cfg["nanmean_chunk"], cfg["rand"],
-                                       cfg["stages"], keep=keep)
+                                       cfg["stages"], keep=keep, lindisp=cfg["lindisp"])
         ctx.keep = keep
         ctx.caster = caster
         ctx.params = params
@@ -99,11 +99,11 @@ class _RenderBlock(torch.autograd.Function):
 
 
 def render_block_with_grad(caster, rays, skip, pose_skts, pose_cyls, vol, cam_idx, codes, consts, packed, S_c, S_f, B,
-                           raw_noise_std, perturb, nanmean_chunk, rand, stages):
+                           raw_noise_std, perturb, nanmean_chunk, rand, stages, lindisp=False):
     named = dict(caster.network.named_parameters())
     params = [named[n] for n in PARAM_NAMES]
     cfg = dict(rays=rays, skip=skip, pose_skts=pose_skts, pose_cyls=pose_cyls, cam_idx=cam_idx, codes=codes, consts=consts,
                packed=packed, S_c=S_c, S_f=S_f, B=B, raw_noise_std=raw_noise_std, perturb=perturb,
-               nanmean_chunk=nanmean_chunk, rand=rand, stages=stages)
+               nanmean_chunk=nanmean_chunk, rand=rand, stages=stages, lindisp=lindisp)
     outs = _RenderBlock.apply(caster, cfg, vol, *params)
     return dict(zip(OUT_KEYS, outs))

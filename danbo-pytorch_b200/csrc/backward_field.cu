@@ -18,7 +18,8 @@ field_rows_bwd_kernel(const float* __restrict__ rays, int ray_stride, int n_rays
                       const float* __restrict__ pose_vol, int rays_per_pose, int n_poses, FieldConsts fc,
                       const float* __restrict__ logits, const float* __restrict__ hbar /* (rows,16) */,
                       const float* __restrict__ dX /* (rows,208) */, const float* __restrict__ g_logit_ext /* (n*S,24) or null */,
-                      float* __restrict__ d_hbar /* (rows,16) */, float* __restrict__ d_logit /* (n*S,24) */) {
+                      float* __restrict__ d_hbar /* (rows,16) */, float* __restrict__ d_logit /* (n*S,24) */,
+                      int agg_mode /* 0 sigmoid, 1 masked softmax */) {
     int count = *active_count; if (count > capacity) count = capacity;
     const int total = n_rays * S;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
@@ -50,8 +51,13 @@ field_rows_bwd_kernel(const float* __restrict__ rays, int ray_stride, int n_rays
         int pose = n / rays_per_pose; if (pose >= n_poses) pose = n_poses - 1;
         const float* skt = pose_skts + (size_t)pose * DANBO_J * 16;
         const float* vol = pose_vol + (size_t)pose * DANBO_J * DANBO_VOL;
-        uint32_t m = mask[id];
-        while (m) {
+        const uint32_t vis = mask[id];
+        const float* a_row = logits + (size_t)id * DANBO_J;
+        float* da_row = d_logit + (size_t)id * DANBO_J;
+        float amax = 0.f, inv_den = 0.f, dot = 0.f;      // softmax: dot = sum_j dL/dp_j p_j
+        int amax_at = 0;
+        if (agg_mode == 1) softmax_terms(a_row, vis, amax, inv_den, &amax_at);
+        for (uint32_t m = vis; m;) {
             const int j = __ffs(m) - 1; m &= m - 1;
             float x0, x1, x2, h[DANBO_FEAT];
             bone_coords(skt + j * 16, fc.align + j * 16, fc.axis_scale + j * 3, px, py, pz, x0, x1, x2);
@@ -59,10 +65,31 @@ field_rows_bwd_kernel(const float* __restrict__ rays, int ray_stride, int n_rays
             float dp = 0.f;
 #pragma unroll
             for (int i = 0; i < DANBO_FEAT; ++i) dp = fmaf(dh[i], h[i], dp);
-            const float sg = 1.f / (1.f + expf(-logits[(size_t)id * DANBO_J + j]));
+            if (agg_mode == 1) {
+                dot = fmaf(dp, expf(a_row[j] - amax) * inv_den, dot);
+                da_row[j] = dp;                          // parked; turned into d a_j below
+                continue;
+            }
+            const float sg = 1.f / (1.f + expf(-a_row[j]));
             float da = dp * 1.002f * sg * (1.f - sg);
             if (g_logit_ext) da += g_logit_ext[(size_t)id * DANBO_J + j];
-            d_logit[(size_t)id * DANBO_J + j] = da;
+            da_row[j] = da;
+        }
+        if (agg_mode == 1) {
+            // p_j = e_j / D, e_j = v_j exp(a_j - M), D = sum_k e_k + 24 eps:  d a_k = p_k (dp_k - dot) for visible k, and
+            // through M = max_k a_k (autograd routes it to the arg max): dM = -(24 eps / D) dot.  Every bone's entry is
+            // written: the pair list of a softmax pass is dense.
+            const float d_max = -(float)DANBO_J * kSoftmaxEps * inv_den * dot;
+#pragma unroll 4
+            for (int k = 0; k < DANBO_J; ++k) {
+                float da = 0.f;
+                if ((vis >> k) & 1u) {
+                    da = expf(a_row[k] - amax) * inv_den * (da_row[k] - dot);
+                    if (g_logit_ext) da += g_logit_ext[(size_t)id * DANBO_J + k];
+                }
+                if (k == amax_at) da += d_max;
+                da_row[k] = da;
+            }
         }
     }
 }
@@ -83,12 +110,15 @@ __device__ __forceinline__ float tile_colsum(const float* T, int lane) {
     return s;
 }
 
+// kSoftmax: agg_mode 1 (dense pair lists, blend weight of the pair from the row's masked softmax); the sigmoid
+// instantiation carries none of that code.
+template <bool kSoftmax>
 __global__ void __launch_bounds__(128)
 pair_logits_bwd_kernel(const float* __restrict__ rays, int ray_stride, int S, const float* __restrict__ z,
                        const int* __restrict__ active_ids, const float* __restrict__ pose_skts,
                        const float* __restrict__ pose_vol, int rays_per_pose, int n_poses, FieldConsts fc, PairWork pw,
                        int pair_capacity, const float* __restrict__ logits, const float* __restrict__ d_logit,
-                       const float* __restrict__ d_hbar, AggGrads G) {
+                       const float* __restrict__ d_hbar, AggGrads G, const uint32_t* __restrict__ mask) {
     __shared__ float tiles[4][2][32 * kTileLd];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     float* T1 = tiles[wib][0];
@@ -116,8 +146,19 @@ pair_logits_bwd_kernel(const float* __restrict__ rays, int ray_stride, int S, co
             pz = __fadd_rn(r[2], __fmul_rn(r[5], zz));
             pose = n / rays_per_pose; if (pose >= n_poses) pose = n_poses - 1;
             da = d_logit[(size_t)id * DANBO_J + j];
-            pj = (1.f / (1.f + expf(-logits[(size_t)id * DANBO_J + j]))) * 1.002f - 0.001f;
+            if (kSoftmax) {
+                const uint32_t vis = mask[id];
+                if ((vis >> j) & 1u) {
+                    float amax, inv_den;
+                    softmax_terms(logits + (size_t)id * DANBO_J, vis, amax, inv_den);
+                    pj = expf(logits[(size_t)id * DANBO_J + j] - amax) * inv_den;
+                }
+            } else {
+                pj = (1.f / (1.f + expf(-logits[(size_t)id * DANBO_J + j]))) * 1.002f - 0.001f;
+            }
         }
+        // dense (softmax) pair lists: a pair of an invisible bone that is not the row's arg max carries no gradient
+        if (kSoftmax && !__any_sync(0xffffffffu, live && (da != 0.f || pj != 0.f))) continue;
         const float* skt = pose_skts + (size_t)pose * DANBO_J * 16;
         const float* vol = pose_vol + (size_t)pose * DANBO_J * DANBO_VOL;
         // ---- forward recompute: mix -> o1 -> l1 -> o2
@@ -284,23 +325,30 @@ extern "C" int danbo_field_agg_bwd(const float* rays, int ray_stride, int n_rays
                                    int capacity, const float* pose_skts, const float* pose_vol, int rays_per_pose,
                                    int n_poses, const float* const* consts, const float* logits, const float* hbar,
                                    const float* dX, const float* g_logit_ext, float* d_hbar, float* d_logit,
-                                   const int* work, int pair_capacity, float* const* grads, int num_sms, void* stream) {
+                                   const int* work, int pair_capacity, float* const* grads, int num_sms, int agg_mode,
+                                   void* stream) {
     if (capacity <= 0) return 0;
+    if (agg_mode < 0 || agg_mode > 1) return -1;
     cudaStream_t st = (cudaStream_t)stream;
     const FieldConsts fc = make_consts_b(consts);
     int rblocks = (capacity + 127) / 128;
     if (rblocks > num_sms * 16) rblocks = num_sms * 16;
     field_rows_bwd_kernel<<<rblocks, 128, 0, st>>>(rays, ray_stride, n_rays, S, z, mask, active_ids, active_count,
                                                     capacity, pose_skts, pose_vol, rays_per_pose, n_poses, fc, logits,
-                                                    hbar, dX, g_logit_ext, d_hbar, d_logit);
+                                                    hbar, dX, g_logit_ext, d_hbar, d_logit, agg_mode);
     DANBO_CHECK_LAUNCH();
     AggGrads G{grads[0], grads[1], grads[2], grads[3], grads[4], grads[5], grads[6], grads[7], grads[8]};
     PairWork pw{const_cast<int*>(work)};
     int pblocks = (pair_capacity / 32 + 3) / 4;
     if (pblocks > num_sms * 4) pblocks = num_sms * 4;
-    pair_logits_bwd_kernel<<<pblocks, 128, 0, st>>>(rays, ray_stride, S, z, active_ids, pose_skts, pose_vol,
-                                                     rays_per_pose, n_poses, fc, pw, pair_capacity, logits, d_logit,
-                                                     d_hbar, G);
+    if (agg_mode == 1)
+        pair_logits_bwd_kernel<true><<<pblocks, 128, 0, st>>>(rays, ray_stride, S, z, active_ids, pose_skts, pose_vol,
+                                                               rays_per_pose, n_poses, fc, pw, pair_capacity, logits,
+                                                               d_logit, d_hbar, G, mask);
+    else
+        pair_logits_bwd_kernel<false><<<pblocks, 128, 0, st>>>(rays, ray_stride, S, z, active_ids, pose_skts, pose_vol,
+                                                                rays_per_pose, n_poses, fc, pw, pair_capacity, logits,
+                                                                d_logit, d_hbar, G, mask);
     DANBO_CHECK_LAUNCH();
     return 0;
 }

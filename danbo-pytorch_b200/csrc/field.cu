@@ -172,7 +172,7 @@ sample_mask_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, i
                                    const float* __restrict__ z_in, float* __restrict__ z_out,
                                    const float* __restrict__ pose_skts, int rays_per_pose, int n_poses,
                                    FieldConsts fc, uint32_t* __restrict__ mask_out, int* __restrict__ active_ids,
-                                   int* __restrict__ active_count, int capacity, int append_empty) {
+                                   int* __restrict__ active_count, int capacity, int append_empty, int lindisp) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int total = n_rays * S;
     uint32_t mask = 0;
@@ -253,8 +253,14 @@ sample_mask_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, i
         if (z_in) {
             z = z_in[idx];
         } else {
-            const float nr = near[n], fr = far[n];
-            auto zv = [&](int i) { const float t = t_vals[i]; return __fadd_rn(__fmul_rn(nr, __fsub_rn(1.f, t)), __fmul_rn(fr, t)); };
+            // lindisp (ray_utils.py:226-227): linear in inverse depth, 1/(1/near (1-t) + 1/far t); torch's `1./x` is a
+            // correctly rounded reciprocal, so __frcp_rn reproduces it bit for bit
+            const float nr = lindisp ? __frcp_rn(near[n]) : near[n], fr = lindisp ? __frcp_rn(far[n]) : far[n];
+            auto zv = [&](int i) {
+                const float t = t_vals[i];
+                const float v = __fadd_rn(__fmul_rn(nr, __fsub_rn(1.f, t)), __fmul_rn(fr, t));
+                return lindisp ? __frcp_rn(v) : v;
+            };
             z = zv(s);
             if (t_rand) {                                // ray_utils.py:233-248
                 const float lower = (s == 0) ? z : __fmul_rn(.5f, __fadd_rn(z, zv(s - 1)));
@@ -332,7 +338,8 @@ sample_mask_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, i
 template <bool kScatter>
 __global__ void __launch_bounds__(256)
 pair_bucket_kernel(const uint32_t* __restrict__ mask, const int* __restrict__ active_ids,
-                   const int* __restrict__ active_count, int capacity, int total, PairWork pw, int pair_capacity) {
+                   const int* __restrict__ active_count, int capacity, int total, PairWork pw, int pair_capacity,
+                   int dense) {
     int count = *active_count; if (count > capacity) count = capacity;
     const int lane = threadIdx.x & 31;
     __shared__ int hist[DANBO_J];        // pairs of this block's current batch, per bone
@@ -343,6 +350,9 @@ pair_bucket_kernel(const uint32_t* __restrict__ mask, const int* __restrict__ ac
         const int e = b0 + threadIdx.x;
         uint32_t m = 0;
         if (e < count) { const int id = active_ids[e]; if (id < total) m = mask[id]; }
+        // dense (softmax aggregation): the max over the logits runs over all 24 bones (danbo.py:399), so a row seen
+        // by any bone needs the logit of every bone
+        if (dense && m) m = (1u << DANBO_J) - 1u;
         uint32_t any = m;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) any |= __shfl_xor_sync(0xffffffffu, any, o);
@@ -518,7 +528,8 @@ field_rows_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, in
                   const float* __restrict__ pose_vol, int rays_per_pose, int n_poses, FieldConsts fc,
                   const float* __restrict__ logits, uint8_t* __restrict__ xtiles, int* __restrict__ row_ray,
                   float* __restrict__ hbar_out /* (rows,16) or null */,
-                  __nv_bfloat16* __restrict__ x_rows /* (rows,208) row-major copy for the backward pass, or null */) {
+                  __nv_bfloat16* __restrict__ x_rows /* (rows,208) row-major copy for the backward pass, or null */,
+                  int agg_mode /* 0 sigmoid, 1 masked softmax */) {
     int count = *active_count; if (count > capacity) count = capacity;
     const int total = n_rays * S;
     // A lane owns a row, and a row's 16-byte pieces lie in different 128-byte lines of the tile image (one LSU pass per
@@ -549,13 +560,16 @@ field_rows_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, in
             const float* skt = pose_skts + (size_t)pose * DANBO_J * 16;
             const float* vol = pose_vol + (size_t)pose * DANBO_J * DANBO_VOL;
             uint32_t m = mask[id];
+            float amax = 0.f, inv_den = 0.f;
+            if (agg_mode == 1) softmax_terms(logits + (size_t)id * DANBO_J, m, amax, inv_den);
             while (m) {
                 const int j = __ffs(m) - 1; m &= m - 1;
                 float x0, x1, x2, h[DANBO_FEAT];
                 bone_coords(skt + j * 16, fc.align + j * 16, fc.axis_scale + j * 3, px, py, pz, x0, x1, x2);
                 bone_features(vol + j * DANBO_VOL, x0, x1, x2, h);
                 const float a = logits[(size_t)id * DANBO_J + j];
-                const float p = (1.f / (1.f + expf(-a))) * 1.002f - 0.001f;      // danbo.py:410, visible bone
+                const float p = agg_mode == 1 ? expf(a - amax) * inv_den                       // danbo.py:388-404
+                                              : (1.f / (1.f + expf(-a))) * 1.002f - 0.001f;   // danbo.py:410, visible bone
 #pragma unroll
                 for (int i = 0; i < DANBO_FEAT; ++i) hbar[i] = fmaf(p, h[i], hbar[i]);
             }
@@ -713,7 +727,7 @@ extern "C" int danbo_sample_mask(const float* rays, int ray_stride, int n_rays, 
                                  const float* far, const float* t_vals, const float* t_rand, const float* z_in,
                                  float* z_out, const float* pose_skts, int rays_per_pose, int n_poses,
                                  const float* const* consts, unsigned int* mask_out, int* active_ids,
-                                 int* active_count, int capacity, int append_empty, void* stream) {
+                                 int* active_count, int capacity, int append_empty, int lindisp, void* stream) {
     if (n_rays <= 0 || S <= 0) return 0;
     if (!z_in && (!near || !far || !t_vals || !z_out)) return -1;
     const long long total = (long long)n_rays * S;
@@ -723,12 +737,12 @@ extern "C" int danbo_sample_mask(const float* rays, int ray_stride, int n_rays, 
         sample_mask_kernel<true><<<G, B, 0, (cudaStream_t)stream>>>(rays, ray_stride, n_rays, S, near, far, t_vals, t_rand,
                                                                     z_in, z_out, pose_skts, rays_per_pose, n_poses,
                                                                     make_consts(consts), mask_out, active_ids,
-                                                                    active_count, capacity, append_empty);
+                                                                    active_count, capacity, append_empty, lindisp);
     else
         sample_mask_kernel<false><<<G, B, 0, (cudaStream_t)stream>>>(rays, ray_stride, n_rays, S, near, far, t_vals, t_rand,
                                                                      z_in, z_out, pose_skts, rays_per_pose, n_poses,
                                                                      make_consts(consts), mask_out, active_ids,
-                                                                     active_count, capacity, append_empty);
+                                                                     active_count, capacity, append_empty, lindisp);
     DANBO_CHECK_LAUNCH();
     return 0;
 }
@@ -737,9 +751,10 @@ extern "C" int danbo_field_agg(const float* rays, int ray_stride, int n_rays, in
                                const unsigned int* mask, const int* active_ids, const int* active_count,
                                int capacity, const float* pose_skts, const float* pose_vol, int rays_per_pose,
                                int n_poses, const float* const* consts, void* xtiles, int* row_ray, float* logits,
-                               float* hbar_out, void* x_rows, int* work, int pair_capacity, int num_sms, void* stream) {
+                               float* hbar_out, void* x_rows, int* work, int pair_capacity, int num_sms, int agg_mode,
+                               void* stream) {
     if (capacity <= 0) return 0;
-    if (!logits || !work || pair_capacity < 32) return -1;
+    if (!logits || !work || pair_capacity < 32 || agg_mode < 0 || agg_mode > 1) return -1;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(work, 0, 64 * sizeof(int), st);
     if (e != cudaSuccess) return (int)e;
@@ -748,9 +763,9 @@ extern "C" int danbo_field_agg(const float* rays, int ray_stride, int n_rays, in
     const int total = n_rays * S;
     int blocks = (capacity + 255) / 256;
     if (blocks > num_sms * 8) blocks = num_sms * 8;
-    pair_bucket_kernel<false><<<blocks, 256, 0, st>>>(mask, active_ids, active_count, capacity, total, pw, pair_capacity);
+    pair_bucket_kernel<false><<<blocks, 256, 0, st>>>(mask, active_ids, active_count, capacity, total, pw, pair_capacity, agg_mode);
     DANBO_CHECK_LAUNCH();
-    pair_bucket_kernel<true><<<blocks, 256, 0, st>>>(mask, active_ids, active_count, capacity, total, pw, pair_capacity);
+    pair_bucket_kernel<true><<<blocks, 256, 0, st>>>(mask, active_ids, active_count, capacity, total, pw, pair_capacity, agg_mode);
     DANBO_CHECK_LAUNCH();
     int pblocks = (pair_capacity / 64 + 24 + 3) / 4;                  // two 32-pair pieces per warp (+ one odd piece per bone)
     if (pblocks > num_sms * 8) pblocks = num_sms * 8;
@@ -765,7 +780,7 @@ extern "C" int danbo_field_agg(const float* rays, int ray_stride, int n_rays, in
     if (rblocks > num_sms * 16) rblocks = num_sms * 16;
     field_rows_kernel<<<rblocks, 128, 0, st>>>(rays, ray_stride, n_rays, S, z, mask, active_ids, active_count, capacity,
                                                 pose_skts, pose_vol, rays_per_pose, n_poses, fc, logits,
-                                                (uint8_t*)xtiles, row_ray, hbar_out, (__nv_bfloat16*)x_rows);
+                                                (uint8_t*)xtiles, row_ray, hbar_out, (__nv_bfloat16*)x_rows, agg_mode);
     DANBO_CHECK_LAUNCH();
     return 0;
 }

@@ -100,4 +100,21 @@ __device__ __forceinline__ void bone_features(const float* __restrict__ vol_k, f
     }
 }
 
+// A2, agg_type = softmax with mask_vol_prob (danbo.py:388-404): p_j = v_j exp(a_j - M) / max(sum_k (v_k exp(a_k - M) + eps), eps)
+// with M the max over ALL 24 logits (invisible bones included) and eps = 1e-7.  Returns M and 1 / denominator.
+constexpr float kSoftmaxEps = 1e-7f;
+__device__ __forceinline__ void softmax_terms(const float* __restrict__ a, uint32_t visible, float& amax, float& inv_den,
+                                              int* argmax = nullptr) {
+    float m = a[0];
+    int am = 0;
+#pragma unroll
+    for (int k = 1; k < DANBO_J; ++k) { const float v = a[k]; if (v > m) { m = v; am = k; } }     // first maximum, like torch.max
+    float den = 0.f;
+#pragma unroll
+    for (int k = 0; k < DANBO_J; ++k) den += (((visible >> k) & 1u) ? expf(a[k] - m) : 0.f) + kSoftmaxEps;
+    amax = m;
+    inv_den = 1.f / fmaxf(den, kSoftmaxEps);
+    if (argmax) *argmax = am;
+}
+
 }  // namespace danbo

@@ -124,7 +124,7 @@ class ActiveList:
 
 
 def sample_mask(rays, S, pose_skts, rays_per_pose, consts, near=None, far=None, t_rand=None, z_in=None,
-                append_empty=False, capacity=None):
+                append_empty=False, capacity=None, lindisp=False):
     """-> z (n,S), mask (n,S) uint32-as-int32, ActiveList."""
     _need_cuda(rays, pose_skts, near, far, t_rand, z_in)
     lib = _lib.load()
@@ -144,21 +144,25 @@ def sample_mask(rays, S, pose_skts, rays_per_pose, consts, near=None, far=None, 
         _lib.check(lib.danbo_sample_mask(_p(rays), rays.stride(0), n, S, _p(near), _p(far), _p(t_vals), _p(t_rand),
                                          _p(z if z_in is not None else None), _p(z_out), _p(pose_skts),
                                          int(rays_per_pose), pose_skts.shape[0], consts.array, _p(mask), _p(active.ids),
-                                         _p(active.count), active.capacity, int(append_empty), _stream()),
-                   "danbo_sample_mask")
+                                         _p(active.count), active.capacity, int(append_empty), int(bool(lindisp)),
+                                         _stream()), "danbo_sample_mask")
     _count(1)
     return z, mask, active
 
 
 class FieldOut:
     """What danbo_field_agg produced for one pass (kept whole in train mode: the backward reuses the pair lists)."""
-    __slots__ = ("xtiles", "row_ray", "logits", "hbar", "x_rows", "work", "pair_cap")
+    __slots__ = ("xtiles", "row_ray", "logits", "hbar", "x_rows", "work", "pair_cap", "agg_mode")
+
+
+AGG_MODES = {"sigmoid": 0, "softmax": 1}
 
 
 def field_agg(rays, S, z, mask, active, pose_skts, pose_vol, rays_per_pose, consts, want_hbar=False,
-              want_xrows=False, pairs_per_row=6):
-    """-> FieldOut: xtiles (uint8 tiles), row_ray (cap) int32, logits (n*S,24) [visible entries only],
-    hbar (cap,16) / x_rows (cap,208 bf16) when asked."""
+              want_xrows=False, pairs_per_row=6, agg_mode=0):
+    """-> FieldOut: xtiles (uint8 tiles), row_ray (cap) int32, logits (n*S,24) [visible entries only; all 24 entries
+    of every active row with agg_mode 1], hbar (cap,16) / x_rows (cap,208 bf16) when asked.
+    agg_mode: AGG_MODES[agg_type] (0 sigmoid, 1 masked softmax, which evaluates every bone of an active row)."""
     _need_cuda(rays, z, mask, pose_skts, pose_vol)
     lib = _lib.load()
     n = rays.shape[0]
@@ -170,15 +174,18 @@ def field_agg(rays, S, z, mask, active, pose_skts, pose_vol, rays_per_pose, cons
     o.logits = torch.empty(n * S, J, device=dev, dtype=torch.float32)
     o.hbar = torch.empty(active.capacity, 16, device=dev, dtype=torch.float32) if want_hbar else None
     o.x_rows = torch.empty(active.capacity, 208, device=dev, dtype=torch.bfloat16) if want_xrows else None
+    if agg_mode == 1:
+        pairs_per_row = J
     o.pair_cap = int(pairs_per_row) * active.capacity + 24 * 32
+    o.agg_mode = int(agg_mode)
     o.work = torch.empty(64 + o.pair_cap, device=dev, dtype=torch.int32)
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
     with _Timed("field_agg"):
         _lib.check(lib.danbo_field_agg(_p(rays), rays.stride(0), n, S, _p(z), _p(mask), _p(active.ids), _p(active.count),
                                        active.capacity, _p(pose_skts), _p(pose_vol), int(rays_per_pose),
                                        pose_skts.shape[0], consts.array, _p(o.xtiles), _p(o.row_ray), _p(o.logits),
-                                       _p(o.hbar), _p(o.x_rows), _p(o.work), o.pair_cap, num_sms(idx), _stream()),
-                   "danbo_field_agg")
+                                       _p(o.hbar), _p(o.x_rows), _p(o.work), o.pair_cap, num_sms(idx), o.agg_mode,
+                                       _stream()), "danbo_field_agg")
     _count(4)
     return o
 
@@ -508,7 +515,7 @@ def field_agg_bwd(rays, S, z, mask, active, pose_skts, pose_vol, rays_per_pose, 
                                        active.capacity, _p(pose_skts), _p(pose_vol), int(rays_per_pose),
                                        pose_skts.shape[0], consts.array, _p(fo.logits), _p(fo.hbar), _p(dX),
                                        _p(g_logit_ext), _p(d_hbar), _p(d_logit), _p(fo.work), fo.pair_cap, ga,
-                                       num_sms(idx), _stream()), "danbo_field_agg_bwd")
+                                       num_sms(idx), fo.agg_mode, _stream()), "danbo_field_agg_bwd")
     _count(2)
 
 

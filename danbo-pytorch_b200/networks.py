@@ -167,8 +167,12 @@ class DanboField(nn.Module):
                 or multires_voxel != 6 or framecode_ch != 128 or multires_views != 4:
             raise NotImplementedError("the sm_100a kernels are specialised for netdepth=8, netwidth=256, agg_W=32, "
                                       "voxel_feat=5, voxel_res=16, multires_voxel=6, multires_views=4, framecode_size=128")
-        if agg_type != "sigmoid":
-            raise NotImplementedError(f"agg_type={agg_type}: only the shipped 'sigmoid' aggregation is implemented")
+        if agg_type not in ("sigmoid", "softmax"):
+            raise NotImplementedError(f"agg_type={agg_type!r} is not implemented (supported: 'sigmoid', 'softmax')")
+        if agg_type == "softmax" and not mask_vol_prob:
+            # plain F.softmax (danbo.py:389-390) gives bones that do not see the sample a non-zero weight, so a sample no
+            # bone sees no longer has h = 0 and the sparse evaluation is not result-identical
+            raise NotImplementedError("agg_type='softmax' needs mask_vol_prob=True (as in every shipped config)")
         self.W, self.D, self.view_W = W, D, view_W
         self.multires_voxel, self.multires_graph, self.multires_views = multires_voxel, multires_graph, multires_views
         self.agg_type, self.mask_vol_prob = agg_type, mask_vol_prob
@@ -194,6 +198,23 @@ class DanboField(nn.Module):
         if mask_invalid:
             p = p * (1 - invalid.flatten(end_dim=-2))
         return p
+
+    def softmax(self, logit, invalid, eps=1e-7, temp=1.0):
+        """danbo.py:388-404 (torch ops; the kernels compute the same inside field_rows)."""
+        if not self.mask_vol_prob:
+            return torch.softmax(logit / temp, dim=-1)
+        logit = logit / temp
+        valid = 1 - invalid.flatten(end_dim=-2)
+        nominator = torch.exp(logit - logit.max(dim=-1, keepdim=True)[0]) * valid
+        return nominator / torch.sum(nominator + eps, dim=-1, keepdim=True).clamp(min=eps)
+
+    def get_agg(self, logit, invalid, eps=1e-7):
+        return self.softmax(logit, invalid, eps=eps) if self.agg_type == "softmax" else self.sigmoid(logit, invalid, eps=eps)
+
+    @property
+    def agg_mode(self):
+        """`agg_mode` argument of danbo_field_agg / danbo_field_agg_bwd."""
+        return 1 if self.agg_type == "softmax" else 0
 
     def get_adjw(self):
         return self.graph_net.get_adjw() + self.prob_linears.get_adjw()

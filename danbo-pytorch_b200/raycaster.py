@@ -66,12 +66,14 @@ class RayCaster(nn.Module):
         return self.network, self.network_fine
 
     def render_graphed(self, ray_batch, N_samples, kp_batch=None, skts=None, cyls=None, bones=None, cams=None,
-                       N_uniques=1, N_importance=0, nanmean_chunk=None, preproc_kwargs=None, **ignored):
+                       N_uniques=1, N_importance=0, nanmean_chunk=None, preproc_kwargs=None, lindisp=False, **ignored):
         """Eval-mode render replayed from a CUDA graph (one graph per ray count).  Same inputs and returned dict as the
         plain call; the returned tensors are static buffers that the next graphed call overwrites."""
         from .graphs import GraphedFn
         if self.training:
             raise RuntimeError("render_graphed is for eval mode")
+        if ignored.get("ray_noise_std", 0.) > 0 or ignored.get("render_confd") or ignored.get("render_entropy"):
+            raise NotImplementedError("ray_noise_std / render_confd / render_entropy are not implemented")
         B = float((preproc_kwargs or {}).get("density_scale", 1.0))
         rays, pose_skts, pose_bones, pose_cyls, cam_idx, skip = self._prepare(ray_batch, skts, cyls, bones, cams, N_uniques)
         if self._graphed is None:
@@ -80,7 +82,8 @@ class RayCaster(nn.Module):
                     return self._render_prepared(rays, pose_skts, pose_bones, pose_cyls, cam_idx, **kw)
             self._graphed = GraphedFn(run, self._device())
         return self._graphed(rays=rays, pose_skts=pose_skts, pose_bones=pose_bones, pose_cyls=pose_cyls, cam_idx=cam_idx,
-                             skip=skip, N_samples=N_samples, N_importance=N_importance, B=B, nanmean_chunk=nanmean_chunk)
+                             skip=skip, N_samples=N_samples, N_importance=N_importance, B=B, nanmean_chunk=nanmean_chunk,
+                             lindisp=bool(lindisp))
 
     def update_embed_fns(self, global_step, args):
         self.network.update_embed_fns(global_step, args)
@@ -145,8 +148,8 @@ class RayCaster(nn.Module):
         Extra (optional) keywords: `nanmean_chunk` keeps the reference's per-chunk near/far fill (F8) when more than
         one reference chunk is passed in a single call; `_rand`/`_stages` are test hooks (inject the four random
         tensors / collect stage tensors)."""
-        if lindisp or ray_noise_std > 0 or render_confd or render_entropy or pytest:
-            raise NotImplementedError("lindisp / ray_noise_std / render_confd / render_entropy / pytest are not implemented")
+        if ray_noise_std > 0 or render_confd or render_entropy or pytest:
+            raise NotImplementedError("ray_noise_std / render_confd / render_entropy / pytest are not implemented")
         if N_importance <= 0:
             raise NotImplementedError("N_importance must be > 0 (the reference itself requires it, SURVEY F10)")
         if skts is None or bones is None or cyls is None or cams is None:
@@ -158,7 +161,7 @@ class RayCaster(nn.Module):
         rays, pose_skts, pose_bones, pose_cyls, cam_idx, skip = self._prepare(ray_batch, skts, cyls, bones, cams, N_uniques)
         return self._render_prepared(rays, pose_skts, pose_bones, pose_cyls, cam_idx, skip=skip, N_samples=N_samples,
                                      N_importance=N_importance, B=B, raw_noise_std=raw_noise_std, perturb=perturb,
-                                     nanmean_chunk=nanmean_chunk, _rand=_rand, _stages=_stages)
+                                     nanmean_chunk=nanmean_chunk, lindisp=bool(lindisp), _rand=_rand, _stages=_stages)
 
     def _prepare(self, ray_batch, skts, cyls, bones, cams, N_uniques):
         """Host-side reduction of the reference's per-ray stride-0 expands to per-pose tables (encoders.py:465-471)."""
@@ -173,7 +176,7 @@ class RayCaster(nn.Module):
         return rays, pose_skts, pose_bones, pose_cyls, cam_idx, skip
 
     def _render_prepared(self, rays, pose_skts, pose_bones, pose_cyls, cam_idx, skip=1, N_samples=64, N_importance=16,
-                         B=1.0, raw_noise_std=0., perturb=0., nanmean_chunk=None, _rand=None, _stages=None):
+                         B=1.0, raw_noise_std=0., perturb=0., nanmean_chunk=None, lindisp=False, _rand=None, _stages=None):
         dev = self._device()
         N = rays.shape[0]
         net = self.network
@@ -195,7 +198,7 @@ class RayCaster(nn.Module):
                 raise NotImplementedError(f"training batches above {MAX_RAYS_PER_LAUNCH} rays are not implemented")
             return render_block_with_grad(self, rays, skip, pose_skts, pose_cyls, vol, cam_idx, codes, consts, packed,
                                           N_samples, N_importance, B, raw_noise_std, perturb, nanmean_chunk,
-                                          {k: v.to(dev).contiguous() for k, v in rand.items()}, _stages)
+                                          {k: v.to(dev).contiguous() for k, v in rand.items()}, _stages, lindisp=lindisp)
         outs = []
         # internal launches: any split works for a single pose; with several poses a block holds whole poses
         G = pose_skts.shape[0]
@@ -207,13 +210,13 @@ class RayCaster(nn.Module):
             sub_rand = {k: v[s0:s1].to(dev).contiguous() for k, v in rand.items()}
             outs.append(self._render_block(rays[s0:s1], s0, skip, pose_skts, pose_cyls, vol, cam_idx[s0:s1], codes,
                                            consts, packed, N_samples, N_importance, B, raw_noise_std, perturb,
-                                           training, nanmean_chunk, sub_rand, _stages))
+                                           training, nanmean_chunk, sub_rand, _stages, lindisp=lindisp))
         if len(outs) == 1:
             return outs[0]
         return {k: torch.cat([o[k] for o in outs], 0) for k in outs[0]}
 
     def _render_block(self, rays, ray0, skip, pose_skts, pose_cyls, vol, cam_idx, codes, consts, packed, S_c, S_f, B,
-                      raw_noise_std, perturb, training, nanmean_chunk, rand, stages, keep=None):
+                      raw_noise_std, perturb, training, nanmean_chunk, rand, stages, keep=None, lindisp=False):
         """One launch sequence over <= MAX_RAYS_PER_LAUNCH rays.  `keep` (dict) receives every intermediate the
         backward pass needs (train mode with gradients)."""
         n = rays.shape[0]
@@ -233,8 +236,10 @@ class RayCaster(nn.Module):
         # ---- coarse pass
         t_rand = rand.get("t_rand") if (training and perturb > 0) or "t_rand" in rand else None
         z0, mask0, act0 = K.sample_mask(rays, S_c, p_skts, skip, consts, near=near, far=far, t_rand=t_rand,
-                                        append_empty=True)
-        f0 = K.field_agg(rays, S_c, z0, mask0, act0, p_skts, p_vol, skip, consts, want_hbar=save, want_xrows=save)
+                                        append_empty=True, lindisp=lindisp)
+        agg_mode = self.network.agg_mode
+        f0 = K.field_agg(rays, S_c, z0, mask0, act0, p_skts, p_vol, skip, consts, want_hbar=save, want_xrows=save,
+                         agg_mode=agg_mode)
         raw0 = torch.empty(n * S_c + n, 4, device=rays.device, dtype=torch.float32)
         sv0 = sv1 = None
         if save:
@@ -247,7 +252,8 @@ class RayCaster(nn.Module):
                                   want_inds=stages is not None)
         # ---- fine pass: only the S_f new samples go through the field (single_net)
         z1, mask1, act1 = K.sample_mask(rays, S_f, p_skts, skip, consts, z_in=c0["z_samples"], append_empty=False)
-        f1 = K.field_agg(rays, S_f, z1, mask1, act1, p_skts, p_vol, skip, consts, want_hbar=save, want_xrows=save)
+        f1 = K.field_agg(rays, S_f, z1, mask1, act1, p_skts, p_vol, skip, consts, want_hbar=save, want_xrows=save,
+                         agg_mode=agg_mode)
         raw1 = torch.empty(n * S_f, 4, device=rays.device, dtype=torch.float32)
         if save:
             sv1 = K.ActSave(act1.capacity, rays.device)
@@ -293,7 +299,7 @@ class RayCaster(nn.Module):
         z = torch.zeros(P, 1, device=dev)
         # append_empty=2: one extra entry (id 2P-1) carries sigma of a point that no bone sees (h = 0)
         _, mask, act = K.sample_mask(rays, 1, p_skts, P, consts, z_in=z, append_empty=2, capacity=P + 1)
-        fo = K.field_agg(rays, 1, z, mask, act, p_skts, vol, P, consts)
+        fo = K.field_agg(rays, 1, z, mask, act, p_skts, vol, P, consts, agg_mode=self.network.agg_mode)
         sigma = torch.empty(2 * P, device=dev)
         K.mlp_forward(fo.xtiles, packed, None, act, fo.row_ray, sigma, density_only=True)
         out = torch.where(mask.reshape(-1) != 0, sigma[:P], sigma[2 * P - 1])
@@ -316,14 +322,14 @@ GraphCaster = RayCaster
 
 # ------------------------------------------------------------------------------------------------------ factory
 _SUPPORTED = {"nerf_type": ("danbo", "graph"), "gnn_backbone": ("FGNNcat",), "agg_backbone": ("vox_MIXGNN",),
-              "agg_type": ("sigmoid",), "align_bones": ("align",), "density_type": ("relu",),
+              "agg_type": ("sigmoid", "softmax"), "align_bones": ("align",), "density_type": ("relu",),
               "kp_dist_type": ("reldist",), "view_type": ("identity",), "ray_tr_type": ("world",),
               "pts_tr_type": ("local",), "bone_type": ("Nope",), "graph_input_type": ("rot6d",)}
 _REQUIRED = {"netdepth": 8, "netwidth": 256, "agg_W": 32, "agg_D": 3, "node_W": 128, "gcn_D": 4, "gcn_fc_D": 1,
              "voxel_res": 16, "voxel_feat": 5, "multires_voxel": 6, "multires_graph": 5, "multires_views": 4,
              "framecode_size": 128, "single_net": True, "opt_framecode": True, "use_viewdirs": True,
              "mask_root": True, "attenuate_feat": True, "attenuate_invalid": False, "use_cutoff": False,
-             "lindisp": False, "opt_posecode": False, "gnn_concat": False, "no_adj": False, "adj_self_one": False,
+             "opt_posecode": False, "gnn_concat": False, "no_adj": False, "adj_self_one": False,
              "align_corners": False, "vol_cal_scale": True}
 
 
@@ -393,7 +399,7 @@ def create_raycaster(args, data_attrs, device=None):
                 "N_samples": args.N_samples, "use_viewdirs": args.use_viewdirs, "raw_noise_std": args.raw_noise_std,
                 "ray_noise_std": getattr(args, "ray_noise_std", 0.), "ext_scale": getattr(args, "ext_scale", 0.001),
                 "preproc_kwargs": {"density_scale": getattr(args, "density_scale", 1.0), "density_fn": F.relu},
-                "lindisp": False, "nerf_type": args.nerf_type}
+                "lindisp": bool(getattr(args, "lindisp", False)), "nerf_type": args.nerf_type}
     kw_test = dict(kw_train)
     kw_test.update({"ray_caster": caster, "perturb": False, "raw_noise_std": 0., "ray_noise_std": 0.})
     optimizer.zero_grad()

@@ -38,14 +38,15 @@ int danbo_nearfar(const float* rays, int ray_stride, int n_rays, const float* po
 /* SM1 + T1/T2 + bone-visibility mask + compaction.
  * sample_from_lineseg (ray_utils.py:206-253), transform_batch_pts (core/encoders.py:288-303), bone align
  * (encoders.py:442-444), x/|axis_scale| and invalid = any(|x|>1) (core/networks/gnn_backbone.py:802-808).
- * Coarse mode (z_in NULL): z = near(1-t)+far t with t_vals = linspace(0,1,S) (+ jitter t_rand (n,S) or NULL) -> z_out.
+ * Coarse mode (z_in NULL): z = near(1-t)+far t with t_vals = linspace(0,1,S) (+ jitter t_rand (n,S) or NULL) -> z_out;
+ * lindisp != 0 samples linearly in inverse depth instead, z = 1/(1/near (1-t) + 1/far t) (ray_utils.py:226-227).
  * Fine mode: z_in (n,S) given.  mask_out (n,S) gets bit j set when bone j sees the sample; ids of samples with a
  * non-zero mask (and, with append_empty, one extra id per ray) are appended to active_ids at *active_count. */
 int danbo_sample_mask(const float* rays, int ray_stride, int n_rays, int S, const float* near, const float* far,
                       const float* t_vals, const float* t_rand, const float* z_in, float* z_out,
                       const float* pose_skts, int rays_per_pose, int n_poses, const float* const* consts,
                       unsigned int* mask_out, int* active_ids, int* active_count, int capacity, int append_empty,
-                      void* stream);
+                      int lindisp, void* stream);
 
 /* G1/G2 + A1-A3 + positional encoding for the active entries.
  * FactorizeGNN.sample_from_volume / factorize_grid_sample (gnn_backbone.py:787-828, core/networks/misc.py:331-351),
@@ -56,12 +57,15 @@ int danbo_sample_mask(const float* rays, int ray_stride, int n_rays, int S, cons
  * ((capacity+127)/128 tiles of 64 KB, swizzled MMA operand image), row_ray[row], the blend logits ("confd") of every
  * visible (sample, bone) into logits (n_rays*S,24) and optionally hbar (rows,16) and x_rows (rows,208 bf16, a
  * row-major copy of the encoded rows for the backward pass).
- * work: int workspace of 64 + pair_capacity entries; pair_capacity >= number of visible pairs + 24*32. */
+ * work: int workspace of 64 + pair_capacity entries; pair_capacity >= number of visible pairs + 24*32.
+ * agg_mode 0: sigmoid blend weights (danbo.py:406-415, every shipped config).  agg_mode 1: agg_type = softmax with
+ * mask_vol_prob (danbo.py:388-404); its max runs over all 24 logits, so every bone of an active row is evaluated
+ * (pair_capacity >= 24 * rows + 24*32) and logits holds all 24 entries of those rows. */
 int danbo_field_agg(const float* rays, int ray_stride, int n_rays, int S, const float* z, const unsigned int* mask,
                     const int* active_ids, const int* active_count, int capacity, const float* pose_skts,
                     const float* pose_vol, int rays_per_pose, int n_poses, const float* const* consts, void* xtiles,
                     int* row_ray, float* logits, float* hbar_out, void* x_rows, int* work, int pair_capacity,
-                    int num_sms, void* stream);
+                    int num_sms, int agg_mode, void* stream);
 
 /* V1 folded into the view layer: out (n_rays,128) = W_v[:,256:411] . [PE(rays_d) ; frame code] + b_v
  * (core/networks/nerf.py:252-279, core/networks/embedding.py:86-108).  codes is (n_codes+1,128) with the mean code in
@@ -178,13 +182,14 @@ int danbo_ray_bias_bwd(const float* rays, int ray_stride, int n_rays, const int*
 
 /* G1/G2 + A1-A3 + PE backward (danbo.py:261-302, gnn_backbone.py:787-828, misc.py:331-351): d X (rows,208) and the
  * extra logit gradient -> grads[9] = { w0, adj_w, b0, w1, b1, w2, b2 of prob_linears, d vol (n_poses,24,240),
- * d axis_scale (24,3) } (fp32, accumulated).  work = the workspace the forward danbo_field_agg filled. */
+ * d axis_scale (24,3) } (fp32, accumulated).  work = the workspace the forward danbo_field_agg filled; agg_mode as
+ * in that call. */
 int danbo_field_agg_bwd(const float* rays, int ray_stride, int n_rays, int S, const float* z, const unsigned int* mask,
                         const int* active_ids, const int* active_count, int capacity, const float* pose_skts,
                         const float* pose_vol, int rays_per_pose, int n_poses, const float* const* consts,
                         const float* logits, const float* hbar, const float* dX, const float* g_logit_ext, float* d_hbar,
                         float* d_logit, const int* work, int pair_capacity, float* const* grads, int num_sms,
-                        void* stream);
+                        int agg_mode, void* stream);
 
 /* Adam (torch.optim.Adam formulas, raycasters.py:71-78: betas (0.9, 0.999), no weight decay) over one flat fp32 arena
  * holding every parameter; grads / exp_avg / exp_avg_sq are arenas of the same layout; all 16-byte aligned.  lr_dev

@@ -93,10 +93,14 @@ def box_near_far(rays_o, rays_d, skts, A, axis_scale, near, far, bound=1.3, eps=
 # ----------------------------------------------------------------------------------------------------------
 # SM1  core/utils/ray_utils.py:206-253 sample_from_lineseg ; core/raycasters.py:455-468
 # ----------------------------------------------------------------------------------------------------------
-def coarse_z(near, far, S, t_rand=None):
-    """z = near(1-t)+far*t on t=linspace(0,1,S); stratified jitter when t_rand (N,S) is given."""
+def coarse_z(near, far, S, t_rand=None, lindisp=False):
+    """z = near(1-t)+far*t on t=linspace(0,1,S) (lindisp: linear in inverse depth, ray_utils.py:226-227);
+    stratified jitter when t_rand (N,S) is given."""
     t = torch.linspace(0., 1., steps=S).expand([near.size(0), S])
-    z = near * (1. - t) + far * t
+    if not lindisp:
+        z = near * (1. - t) + far * t
+    else:
+        z = 1. / (1. / near * (1. - t) + 1. / far * t)
     if t_rand is not None:
         mids = .5 * (z[..., 1:] + z[..., :-1])
         upper = torch.cat([mids, z[..., -1:]], -1)
@@ -362,7 +366,7 @@ def field_eval(pts, rays_d, cams, skts, A, vol, P, rays_per_pose, training, agg_
 
 def render_rays(ray_batch, pose_skts, pose_bones, pose_cyls, cams, A, P, S_c, S_f, rays_per_pose,
                 use_volume_near_far=False, training=False, rand=None, raw_noise_std=0., agg_type="sigmoid",
-                return_stages=False, z_samples=None):
+                return_stages=False, z_samples=None, lindisp=False):
     """ray_batch (N,>=8); pose_* are per unique pose (G,...); ray n belongs to pose n // rays_per_pose.
     rand (training) = dict(t_rand (N,S_c), noise0 (N,S_c), u (N,S_f), noise1 (N,S_t)) drawn by the caller in
     the reference's order (SURVEY §7 hard part 4)."""
@@ -379,7 +383,7 @@ def render_rays(ray_batch, pose_skts, pose_bones, pose_cyls, cams, A, P, S_c, S_
             near, far, _, _ = box_near_far(rays_o, rays_d, skts, A, P["graph_net.axis_scale"], near, far)
     vol = graph_net(graph_inputs(pose_bones), P)
     rand = rand or {}
-    z = coarse_z(near, far, S_c, rand.get("t_rand"))
+    z = coarse_z(near, far, S_c, rand.get("t_rand"), lindisp)
     pts = ray_points(rays_o, rays_d, z)
     raw0, confd0, inv0, st0 = field_eval(pts, rays_d, cams, skts, A, vol, P, rays_per_pose, training, agg_type)
     n0 = rand["noise0"] * raw_noise_std if "noise0" in rand else None
@@ -540,14 +544,15 @@ def density_grid(kps, skts, bones, A, P, radius, res, agg_type="sigmoid"):
 # ----------------------------------------------------------------------------------------------------------
 # L*  core/trainer.py:396-422,507-553 (losses stay in PyTorch in the product too; here for the training parity test)
 # ----------------------------------------------------------------------------------------------------------
-def training_loss(ret, target, bgs, P, init_scale, soft_coef=0.001, vol_coef=0.001, coarse_weight=1.0):
+def training_loss(ret, target, bgs, P, init_scale, soft_coef=0.001, vol_coef=0.001, coarse_weight=1.0, agg_type="sigmoid"):
     def l1(rgb, acc):
         return torch.mean(torch.abs(rgb + (1. - acc)[..., None] * bgs - target))
     loss = l1(ret["rgb_map"], ret["acc_map"]) + coarse_weight * l1(ret["rgb0"], ret["acc0"])
-    labels = ((ret["T_i"] * ret["alpha"]) > 0).float()
-    valid = 1 - ret["part_invalid"]
-    p = torch.sigmoid(ret["confd"]) * 1.002 - 0.001
-    loss = loss + soft_coef * (labels - (p * valid).sum(-1)).pow(2.).mean()
+    if agg_type == "sigmoid":                                       # trainer.py:372: only with sigmoid blend weights
+        labels = ((ret["T_i"] * ret["alpha"]) > 0).float()
+        valid = 1 - ret["part_invalid"]
+        p = torch.sigmoid(ret["confd"]) * 1.002 - 0.001
+        loss = loss + soft_coef * (labels - (p * valid).sum(-1)).pow(2.).mean()
     scale = P["graph_net.axis_scale"].abs().clamp(min=init_scale * 0.05)
     loss = loss + vol_coef * torch.prod(scale, dim=-1).sum()
     return loss

@@ -376,6 +376,9 @@ def main():
     if only == "anerf":
         run_anerf_case("render_anerf", ["--N_samples", "24", "--N_importance", "12"], pose_seed=4, H=64, n_rays=64)
         return
+    if only == "variants":
+        variants()
+        return
     run_render_case("render_fast", "h36m_zju/danbo_fast.txt", [], pose_seed=3, H=64, n_rays=256)
     run_render_case("render_base", "h36m_zju/danbo_base.txt", [], pose_seed=5, H=64, n_rays=96)
     run_render_case("render_fast_miss", "h36m_zju/danbo_fast.txt", [], pose_seed=7, H=48, n_rays=192, full_image=True)
@@ -384,6 +387,15 @@ def main():
                    n_poses=2, rays_per_pose=32)
     run_grid_case("grid_base", "h36m_zju/danbo_base.txt", pose_seed=3, res=11)
     run_anerf_case("render_anerf", ["--N_samples", "24", "--N_importance", "12"], pose_seed=4, H=64, n_rays=64)
+    variants()
+
+
+def variants():
+    """Flag values outside the shipped configs that the path supports: agg_type=softmax (the CLI default,
+    run_nerf.py:364; danbo.py:388-404) in eval and train mode, and lindisp (ray_utils.py:226-227)."""
+    run_render_case("render_fast_softmax", "h36m_zju/danbo_fast.txt", ["--agg_type", "softmax"], pose_seed=3, H=64, n_rays=128)
+    run_train_case("train_fast_softmax", "h36m_zju/danbo_fast.txt", ["--agg_type", "softmax"], n_poses=4, rays_per_pose=48)
+    run_render_case("render_fast_lindisp", "h36m_zju/danbo_fast.txt", ["--lindisp"], pose_seed=3, H=64, n_rays=256)
 
 
 if __name__ == "__main__":

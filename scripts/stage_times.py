@@ -1,4 +1,4 @@
-"""Per-stage CUDA-event timing of one danbo_fast 512x512 render (profiling aid)."""
+"""Per-stage CUDA-event timing of one danbo_fast 512x512 render (profiling aid).  `--softmax`: agg_type=softmax."""
 import sys, os, collections
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, ROOT + "/oracle", ROOT + "/tests"): sys.path.insert(0, p)
@@ -8,6 +8,8 @@ import danbo_b200
 from danbo_b200 import kernels
 dev = torch.device("cuda", 0)
 caster, args, batch = bench.build_scene(0, dev)
+if "--softmax" in sys.argv:
+    caster.network.agg_type = "softmax"          # dense pair lists: every bone of an active row is evaluated
 rays = batch["ray_batch"].to(dev)
 kw = bench.caster_kwargs(args, batch, dev)
 for _ in range(3): caster(rays, **kw)

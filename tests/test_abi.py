@@ -36,9 +36,16 @@ def test_kernels_refuse_cpu_tensors():
 
 def test_unsupported_flags_raise():
     import pytest
-    for kw in ({"agg_type": "softmax"}, {"gnn_backbone": "PNBGNN"}, {"netwidth": 128}, {"nerf_type": "nerf"}):
+    for kw in ({"agg_type": "relu"}, {"agg_type": "sum"}, {"gnn_backbone": "PNBGNN"}, {"netwidth": 128},
+               {"nerf_type": "nerf"}, {"single_net": False}):
         with pytest.raises(NotImplementedError):
             danbo_b200.raycaster.check_args(danbo_b200.make_args("danbo_base", **kw))
+    # both aggregation types of danbo.py:431-435 that a config can reach pass the check; softmax needs mask_vol_prob
+    for agg in ("sigmoid", "softmax"):
+        danbo_b200.raycaster.check_args(danbo_b200.make_args("danbo_base", agg_type=agg, lindisp=True))
+    from danbo_b200.networks import DanboField
+    with pytest.raises(NotImplementedError):
+        DanboField(agg_type="softmax", mask_vol_prob=False)
 
 
 def test_anerf_flag_subset():

@@ -11,11 +11,17 @@ import torch
 
 import danbo_oracle as orc
 from util import (load_fixture, params_for, align_A, pose_tensors, mask_mismatch_report, decode_xtiles, make_caster,
-                  preset_of, mlp_bf16_reference)
+                  preset_of, mlp_bf16_reference, agg_type_of, lindisp_of)
 
 pytestmark = pytest.mark.gpu
 RENDER = ["render_fast", "render_base", "render_fast_miss"]
+# flag values outside the shipped configs: agg_type=softmax (danbo.py:388-404) and lindisp (ray_utils.py:226-227)
+VARIANTS = ["render_fast_softmax", "render_fast_lindisp"]
 DEV = "cuda"
+
+
+def caster_for(fx, **kw):
+    return make_caster(preset_of(fx), agg_type=agg_type_of(fx), lindisp=lindisp_of(fx), **kw)
 
 
 def K():
@@ -60,16 +66,16 @@ def test_nearfar(name):
         assert torch.equal(vv.cpu().bool(), fx["st.v_valid.0"].bool())
 
 
-@pytest.mark.parametrize("name", RENDER)
+@pytest.mark.parametrize("name", RENDER + VARIANTS[1:])
 def test_sample_mask_and_compaction(name):
     fx = load_fixture(name)
-    caster, args, P = make_caster(preset_of(fx))
+    caster, args, P = caster_for(fx)
     skts, _, _ = pose_tensors(fx)
     rb = fx["ray_batch"].to(DEV)
     N, S = rb.shape[0], int(fx["N_samples"])
     consts = caster._consts()
     z, mask, act = K().sample_mask(rb, S, skts.to(DEV).contiguous(), N, consts, near=fx["st.near.0"].reshape(-1).to(DEV),
-                                   far=fx["st.far.0"].reshape(-1).to(DEV), append_empty=True)
+                                   far=fx["st.far.0"].reshape(-1).to(DEV), append_empty=True, lindisp=lindisp_of(fx))
     assert torch.equal(z.cpu(), fx["st.z.0"]), "coarse z must be bit-identical to the reference"
     got_inv = bits_to_invalid(mask)
     want_inv = fx["st.invalid.0"]
@@ -89,12 +95,13 @@ def test_sample_mask_and_compaction(name):
     assert bool(flat[ids[ids < N * S]].all()) and int((ids >= N * S).sum()) == N
 
 
-@pytest.mark.parametrize("name", RENDER)
+@pytest.mark.parametrize("name", RENDER + VARIANTS[:1])
 @pytest.mark.parametrize("which", [0, 1])
 def test_field_agg(name, which):
     """G1/G2/A1-A3 + PE on the golden sample positions against the oracle (fp32 hbar/confd, bf16 encoded rows)."""
     fx = load_fixture(name)
-    caster, args, P = make_caster(preset_of(fx))
+    caster, args, P = caster_for(fx)
+    agg = agg_type_of(fx)
     Pc = params_for(fx)
     skts, bones, _ = pose_tensors(fx)
     rb = fx["ray_batch"]
@@ -105,7 +112,7 @@ def test_field_agg(name, which):
     vol = fx["st.vol.0"].to(DEV).contiguous()
     zg, mask, act = K().sample_mask(rb.to(DEV), S, skts.to(DEV).contiguous(), N, consts, z_in=z.to(DEV), append_empty=False)
     fo = K().field_agg(rb.to(DEV), S, zg, mask, act, skts.to(DEV).contiguous(), vol, N, consts, want_hbar=True,
-                       want_xrows=True)
+                       want_xrows=True, agg_mode=K().AGG_MODES[agg])
     xt, row_ray, confd, hbar = fo.xtiles, fo.row_ray, fo.logits, fo.hbar
     n_act = int(act.count.item())
     ids = act.ids[:n_act].cpu().long()
@@ -116,7 +123,7 @@ def test_field_agg(name, which):
     h, invalid, x = orc.bone_features(pts_t, fx["st.vol.0"], Pc["graph_net.axis_scale"], rays_per_pose=N)
     hf = h.reshape(N * S, 24, 15)
     a = orc.agg_net(hf, Pc)
-    p = orc.agg_prob(a, invalid.reshape(N * S, 24))
+    p = orc.agg_prob(a, invalid.reshape(N * S, 24), agg)
     hb = (hf * p[..., None]).sum(-2)
     got_inv = bits_to_invalid(mask).reshape(N * S, 24)
     same = (got_inv == invalid.reshape(N * S, 24)).all(-1)          # skip the (rare) samples whose mask flipped
@@ -125,6 +132,8 @@ def test_field_agg(name, which):
     valid = 1 - invalid.reshape(N * S, 24)
     confd_v = torch.where(valid.bool(), confd.cpu(), torch.zeros(()))        # only visible entries are defined
     close(confd_v[ids][sel], (a * valid)[ids][sel], 1e-4, "confd (visible bones)")
+    if agg == "softmax":                                             # dense pair list: all 24 logits of an active row
+        close(confd.cpu()[ids][sel], a[ids][sel], 1e-4, "confd (every bone of the active rows)")
     assert torch.equal(row_ray[:n_act].cpu().long(), ids // S)
     X = decode_xtiles(xt, n_act).cpu()
     want = orc.pe_embed(hbar[:n_act, :15].cpu(), 6)
@@ -243,19 +252,20 @@ def _report(tag, got, want):
     return err
 
 
-@pytest.mark.parametrize("name", RENDER)
+@pytest.mark.parametrize("name", RENDER + VARIANTS)
 def test_render_rays_end_to_end(name):
     """The drop-in call: ray_caster(ray_batch, N_samples=..., kp_batch=..., skts=..., ...) in eval mode."""
     fx = load_fixture(name)
-    caster, args, P = make_caster(preset_of(fx))
+    caster, args, P = caster_for(fx)
     skts, bones, cyl = pose_tensors(fx)
     N = fx["ray_batch"].shape[0]
     ex = lambda t: t.expand(N, *t.shape[1:])
     stages = {}
     out = caster(fx["ray_batch"], N_samples=args.N_samples, kp_batch=ex(fx["pose_kps"][None]), skts=ex(skts),
                  cyls=ex(cyl), bones=ex(bones), cams=fx["cams"], N_uniques=1, perturb=False,
-                 N_importance=args.N_importance, raw_noise_std=0., _stages=stages)
+                 N_importance=args.N_importance, raw_noise_std=0., lindisp=args.lindisp, _stages=stages)
     torch.cuda.synchronize()
+    close(stages["z_coarse"], fx["st.z.0"], 2e-6, "coarse z (near/far from this path's own NF1/NF2 kernels)")
     assert set(out) == {"rgb_map", "disp_map", "acc_map", "alpha", "T_i", "rgb0", "disp0", "acc0", "alpha0"}
     # coarse pass: identical sample positions, so this isolates the bf16 MLP error
     act = (stages["mask0"] != 0).cpu()
@@ -285,12 +295,12 @@ def test_density_grid():
     assert float(e.max()) <= 3e-2 * float(fx["sigma"].abs().max())
 
 
-@pytest.mark.parametrize("name", ["train_fast", "train_cfg3"])
+@pytest.mark.parametrize("name", ["train_fast", "train_cfg3", "train_fast_softmax"])
 def test_train_mode_forward(name):
     """Train-mode forward with the reference's own random draws (perturbed samples, density noise, random u)."""
     from danbo_b200 import synthetic as syn
     fx = load_fixture(name)
-    caster, args, P = make_caster(preset_of(fx), train=True)
+    caster, args, P = caster_for(fx, train=True)
     b = syn.training_batch(int(fx["n_poses"]), int(fx["rays_per_pose"]), seed=int(fx["batch_seed"]))
     rand = {k: fx["rand." + k].to(DEV) for k in ("t_rand", "noise0", "u", "noise1")}
     stages = {}

@@ -14,30 +14,32 @@ import pytest
 import torch
 
 import danbo_oracle as orc
-from util import load_fixture, params_for, align_A, make_caster, preset_of
+from util import load_fixture, params_for, align_A, make_caster, preset_of, agg_type_of
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-def torch_loss(ret, target, bgs, axis_scale, init_scale):
+def torch_loss(ret, target, bgs, axis_scale, init_scale, agg_type="sigmoid"):
     """The trainer's losses restated on whatever device the tensors live on (trainer.py:396-422,507-553)."""
     def l1(rgb, acc):
         return torch.mean(torch.abs(rgb + (1. - acc)[..., None] * bgs - target))
     loss = l1(ret["rgb_map"], ret["acc_map"]) + l1(ret["rgb0"], ret["acc0"])
-    labels = ((ret["T_i"] * ret["alpha"]) > 0).float()
-    valid = 1 - ret["part_invalid"]
-    p = torch.sigmoid(ret["confd"]) * 1.002 - 0.001
-    loss = loss + 0.001 * (labels - (p * valid).sum(-1)).pow(2.).mean()
+    if agg_type == "sigmoid":                                       # trainer.py:372
+        labels = ((ret["T_i"] * ret["alpha"]) > 0).float()
+        valid = 1 - ret["part_invalid"]
+        p = torch.sigmoid(ret["confd"]) * 1.002 - 0.001
+        loss = loss + 0.001 * (labels - (p * valid).sum(-1)).pow(2.).mean()
     scale = axis_scale.abs().clamp(min=init_scale * 0.05)
     return loss + 0.001 * torch.prod(scale, dim=-1).sum()
 
 
-@pytest.mark.parametrize("name", ["train_fast", "train_cfg3"])
+@pytest.mark.parametrize("name", ["train_fast", "train_cfg3", "train_fast_softmax"])
 def test_training_step_gradients(name):
     from danbo_b200 import synthetic as syn, skeleton as sk
     fx = load_fixture(name)
-    caster, args, _ = make_caster(preset_of(fx), train=True)
+    agg = agg_type_of(fx)
+    caster, args, _ = make_caster(preset_of(fx), train=True, agg_type=agg)
     b = syn.training_batch(int(fx["n_poses"]), int(fx["rays_per_pose"]), seed=int(fx["batch_seed"]))
     rpp = int(fx["rays_per_pose"])
     rand = {k: fx["rand." + k] for k in ("t_rand", "noise0", "u", "noise1")}
@@ -48,7 +50,8 @@ def test_training_step_gradients(name):
                              cyls=b["cyls"], bones=b["bones"], cams=b["cams"], N_uniques=int(fx["n_poses"]), perturb=1.0,
                              N_importance=args.N_importance, raw_noise_std=float(fx["raw_noise_std"]),
                              _rand={k: v.to(DEV) for k, v in rand.items()}, _stages=stages)
-    loss = torch_loss(out, b["target_s"].to(DEV), b["bgs"].to(DEV), caster.network.graph_net.axis_scale, init_scale.to(DEV))
+    loss = torch_loss(out, b["target_s"].to(DEV), b["bgs"].to(DEV), caster.network.graph_net.axis_scale,
+                      init_scale.to(DEV), agg)
     loss.backward()
     torch.cuda.synchronize()
     got = {n: p.grad.detach().cpu() for n, p in caster.network.named_parameters() if p.grad is not None}
@@ -58,8 +61,8 @@ def test_training_step_gradients(name):
     ref = orc.render_rays(b["ray_batch"], b["skts"][::rpp], b["bones"][::rpp], b["cyls"][::rpp], b["cams"], align_A(), P,
                           int(fx["N_samples"]), int(fx["N_importance"]), rays_per_pose=rpp,
                           use_volume_near_far=bool(fx["use_volume_near_far"]), training=True, rand=rand,
-                          raw_noise_std=float(fx["raw_noise_std"]), z_samples=stages["z_samples"].cpu())
-    ref_loss = orc.training_loss(ref, b["target_s"], b["bgs"], P, init_scale)
+                          raw_noise_std=float(fx["raw_noise_std"]), z_samples=stages["z_samples"].cpu(), agg_type=agg)
+    ref_loss = orc.training_loss(ref, b["target_s"], b["bgs"], P, init_scale, agg_type=agg)
     ref_loss.backward()
     print(f"[train] {name}: loss cuda {float(loss):.6f} oracle {float(ref_loss):.6f} reference {float(fx['loss.total']):.6f}")
     assert abs(float(loss) - float(ref_loss)) <= 5e-3
@@ -81,7 +84,9 @@ def test_training_step_gradients(name):
             want = fx["grad_val." + k].double()
             ref_err = float((a[idx] - want).norm() / max(float(want.norm()), 1e-3 * big))
         print(f"[train] {name} {k:40s} |g| {rn:.3e} cos {cos:.5f} rel {rel:.3e} | vs reference samples {ref_err:.3e}")
-        cos_min, rel_max = (0.985, 0.2) if name == "train_fast" else (0.85, 0.8)
+        # softmax blend weights sum to ~1 over the visible bones (sigmoid ones sit near 0.5 each at random init), so the
+        # same bf16 / noise-gate flips move the bone-volume gradients about twice as far: measured cos >= 0.974
+        cos_min, rel_max = {"train_fast": (0.985, 0.2), "train_fast_softmax": (0.965, 0.3)}.get(name, (0.85, 0.8))
         if (rn > 1e-3 * big and cos < cos_min) or rel > rel_max:
             bad.append((k, cos, rel))
     assert not bad, bad
@@ -232,12 +237,14 @@ def test_mlp_backward(impl):
         assert rel <= (3e-2 if impl == "tc" else 2e-2), (nm, rel)
 
 
-@pytest.mark.parametrize("name", ["render_fast", "render_base"])
-def test_field_backward(name):
-    """G1/G2 + A1-A3 + PE backward against torch autograd of the oracle on the same sample positions (fp32 both)."""
+@pytest.mark.parametrize("name,agg", [("render_fast", "sigmoid"), ("render_base", "sigmoid"), ("render_fast", "softmax"),
+                                      ("render_base", "softmax")])
+def test_field_backward(name, agg):
+    """G1/G2 + A1-A3 + PE backward against torch autograd of the oracle on the same sample positions (fp32 both),
+    for both aggregation types (softmax: dense pair lists, gradient through the row maximum to its arg max)."""
     from util import pose_tensors
     fx = load_fixture(name)
-    caster, args, Pdev = make_caster(preset_of(fx), train=True)
+    caster, args, Pdev = make_caster(preset_of(fx), train=True, agg_type=agg)
     K = _K()
     Pc = params_for(fx)
     skts, bones, _ = pose_tensors(fx)
@@ -248,7 +255,8 @@ def test_field_backward(name):
     vol = fx["st.vol.0"]
     d = lambda t: t.to(DEV).contiguous()
     zg, mask, act = K.sample_mask(d(rb), S, d(skts), N, consts, z_in=d(z), append_empty=1)
-    fo = K.field_agg(d(rb), S, zg, mask, act, d(skts), d(vol), N, consts, want_hbar=True, want_xrows=True)
+    fo = K.field_agg(d(rb), S, zg, mask, act, d(skts), d(vol), N, consts, want_hbar=True, want_xrows=True,
+                     agg_mode=K.AGG_MODES[agg])
     n_act = int(act.count.item())
     ids = act.ids[:n_act].cpu().long()
     torch.manual_seed(5)
@@ -270,7 +278,7 @@ def test_field_backward(name):
     hf = h.reshape(N * S, 24, 15)
     a = orc.agg_net(hf, P)
     valid = 1 - invalid.reshape(N * S, 24)
-    p = orc.agg_prob(a, invalid.reshape(N * S, 24))
+    p = orc.agg_prob(a, invalid.reshape(N * S, 24), agg)
     X = orc.pe_embed((hf * p[..., None]).sum(-2), 6)
     real = ids < N * S
     rows_real = torch.nonzero(real).reshape(-1)
@@ -282,7 +290,7 @@ def test_field_backward(name):
     checks += [("d vol", grads[7].cpu(), vol_r.grad), ("d axis_scale", grads[8].cpu(), P["graph_net.axis_scale"].grad)]
     for nm, got, want in checks:
         rel = float((got.reshape(-1) - want.reshape(-1)).norm() / (want.norm() + 1e-12))
-        print(f"[train] field bwd {name} {nm:36s} |g| {float(want.norm()):.3e} rel {rel:.3e}")
+        print(f"[train] field bwd {name}/{agg} {nm:36s} |g| {float(want.norm()):.3e} rel {rel:.3e}")
         assert rel <= 2e-4, (nm, rel)
 
 

@@ -65,9 +65,9 @@ def decode_xtiles(xtiles, n_rows, n_cols=195):
     return vals.view(torch.bfloat16).float()[:n_rows, :n_cols]
 
 
-def make_caster(preset, weight_seed=0, device="cuda", train=False):
+def make_caster(preset, weight_seed=0, device="cuda", train=False, **flags):
     import danbo_b200 as db
-    args = db.make_args(preset, no_reload=True)
+    args = db.make_args(preset, no_reload=True, **flags)
     data_attrs = {"skel_type": sk.SMPLSkeleton, "near": syn.NEAR, "far": syn.FAR, "n_views": 8,
                   "rest_pose": syn.rest_pose()}
     kw_train, kw_test, *_ = db.create_raycaster(args, data_attrs, device=device)
@@ -76,6 +76,15 @@ def make_caster(preset, weight_seed=0, device="cuda", train=False):
     caster.network.load_state_dict(P)
     caster.train(train)
     return caster, args, {k: v.to(device) for k, v in P.items()}
+
+
+def agg_type_of(fx):
+    """Aggregation type of a fixture (`--agg_type softmax` in its extra flags; the configs ship sigmoid)."""
+    return "softmax" if "agg_type softmax" in str(fx.get("extra", "")) else "sigmoid"
+
+
+def lindisp_of(fx):
+    return "--lindisp" in str(fx.get("extra", ""))
 
 
 def preset_of(fx):
