@@ -519,6 +519,43 @@ def field_agg_bwd(rays, S, z, mask, active, pose_skts, pose_vol, rays_per_pose, 
     _count(2)
 
 
+LOSS_KINDS = {"L1": 0, "MSE": 1}
+
+
+def train_loss(preds, target, bgs, loss_kind, rgb_coef, coarse_weight, soft_coef=None, axis_scale=None, init_scale=None,
+               vol_coef=0., g_axis_scale=None, use_background=True):
+    """L*: the trainer's losses and their gradients in one launch (danbo_train_loss).
+    preds: the caster's train-mode dict.  bgs: (n,3) tensor or a float.  soft_coef None -> no soft-softmax term;
+    axis_scale None -> no volume-scale term (otherwise its gradient is ADDED to g_axis_scale (24,3)).
+    -> terms (4,) float64 [rgb, rgb coarse, soft-softmax, volume-scale], grads dict keyed like preds."""
+    lib = _lib.load()
+    rgb, acc = preds["rgb_map"], preds["acc_map"]
+    _need_cuda(rgb, acc, target, axis_scale)
+    n, dev = rgb.shape[0], rgb.device
+    c = lambda t: None if t is None else t.detach().float().contiguous()
+    rgb0, acc0 = c(preds.get("rgb0")), c(preds.get("acc0"))
+    confd = pinv = Ti = al = None
+    S_t = 0
+    if soft_coef is not None:
+        confd, pinv, Ti, al = c(preds["confd"]), c(preds["part_invalid"]), c(preds["T_i"]), c(preds["alpha"])
+        S_t = confd.shape[1]
+    bg_t = c(bgs).expand(n, 3).contiguous() if torch.is_tensor(bgs) else None
+    terms = torch.empty(4, device=dev, dtype=torch.float64)
+    g = {"rgb_map": torch.empty(n, 3, device=dev), "acc_map": torch.empty(n, device=dev)}
+    if rgb0 is not None:
+        g["rgb0"], g["acc0"] = torch.empty(n, 3, device=dev), torch.empty(n, device=dev)
+    if confd is not None:
+        g["confd"] = torch.empty_like(confd)
+    _lib.check(lib.danbo_train_loss(_p(c(rgb)), _p(c(acc)), _p(rgb0), _p(acc0), _p(c(target)), _p(bg_t),
+                                    0.0 if bg_t is not None else float(bgs), int(bool(use_background)), n,
+                                    LOSS_KINDS[loss_kind], float(rgb_coef), float(coarse_weight), _p(confd), _p(pinv), _p(Ti),
+                                    _p(al), int(S_t), float(soft_coef or 0.), _p(c(axis_scale)), _p(c(init_scale)),
+                                    float(vol_coef), _p(terms), _p(g["rgb_map"]), _p(g["acc_map"]), _p(g.get("rgb0")),
+                                    _p(g.get("acc0")), _p(g.get("confd")), _p(g_axis_scale), _stream()), "danbo_train_loss")
+    _count(1)
+    return terms, g
+
+
 # ------------------------------------------------------------------------------------------------------------
 # AN1: A-NeRF field (nerf_type = nerf, BASELINE config #4)
 ANERF_XD_TILE_BYTES = 7 * 16384

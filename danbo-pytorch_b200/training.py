@@ -43,6 +43,32 @@ def compute_loss(args, preds, batch, network):
     return sum(terms.values()), terms
 
 
+def fused_loss_supported(args, preds):
+    return args.loss_fn in ("L1", "MSE") and preds["rgb_map"].is_cuda
+
+
+def fused_loss_backward(args, preds, batch, network):
+    """compute_loss + backward as ONE kernel launch (danbo_train_loss) followed by the path's own backward: the loss terms
+    and d loss / d (rgb_map, acc_map, rgb0, acc0, confd) come out of the same pass, the volume-scale gradient is added to
+    axis_scale.grad directly, and autograd is entered at the render block's outputs.  -> (total loss, dict of terms)."""
+    from . import kernels as K
+    soft = args.soft_softmax_loss_coef if ("confd" in preds and args.agg_type == "sigmoid") else None
+    gn = network.graph_net
+    vol = bool(getattr(args, "opt_vol_scale", False)) and gn.axis_scale.requires_grad
+    if vol and gn.axis_scale.grad is None:
+        gn.axis_scale.grad = torch.zeros_like(gn.axis_scale)
+    terms, g = K.train_loss(preds, batch["target_s"], batch.get("bgs", 1.0), args.loss_fn, getattr(args, "rgb_loss_coef", 1.0),
+                            getattr(args, "coarse_weight", 1.0), soft_coef=soft,
+                            axis_scale=gn.axis_scale if vol else None, init_scale=gn.init_scale if vol else None,
+                            vol_coef=getattr(args, "vol_scale_penalty", 0.) if vol else 0.,
+                            g_axis_scale=gn.axis_scale.grad if vol else None,
+                            use_background=getattr(args, "use_background", True))
+    keys = [k for k in ("rgb_map", "acc_map", "rgb0", "acc0", "confd") if k in g and preds[k].requires_grad]
+    torch.autograd.backward([preds[k] for k in keys], [g[k] for k in keys])
+    names = ("rgb_loss", "rgb_loss0", "soft_softmax_loss", "vol_scale_loss")
+    return terms.sum().float(), {n: terms[i] for i, n in enumerate(names)}
+
+
 class FlatAdam(torch.optim.Optimizer):
     """torch.optim.Adam (lr, betas, eps; no weight decay / amsgrad) as ONE kernel launch: parameters, gradients and both
     moments live in flat fp32 arenas and every nn.Parameter is a view of the parameter arena.  `step` and `lr` are device
@@ -89,8 +115,9 @@ class FlatAdam(torch.optim.Optimizer):
 class TrainStep:
     """forward -> losses -> backward -> (all-reduce of one flat fp32 gradient bucket) -> Adam."""
 
-    def __init__(self, caster, args, optimizer=None, world_size=1, graph=False):
+    def __init__(self, caster, args, optimizer=None, world_size=1, graph=False, fused_loss=True):
         self.caster, self.args, self.world = caster, args, world_size
+        self.fused_loss = fused_loss           # False: the trainer's losses as PyTorch ops + autograd (compute_loss)
         params = [p for p in caster.network.parameters() if p.requires_grad]
         self.bucket = parallel.GradBucket(params)
         caster.grads_in_place = True            # backward kernels add into the bucket's views (see autograd._RenderBlock)
@@ -141,10 +168,11 @@ class TrainStep:
         preds = self.caster(batch["ray_batch"], N_samples=a.N_samples, kp_batch=batch["kp_batch"], skts=batch["skts"],
                             cyls=batch["cyls"], bones=batch["bones"], cams=batch["cams"], N_uniques=batch["N_uniques"],
                             perturb=a.perturb, N_importance=a.N_importance, raw_noise_std=a.raw_noise_std)
+        # every rank holds 1/world of the batch: mean-reduced data terms are averaged by the all-reduce; the parameter-only
+        # volume penalty is identical on every rank, so averaging leaves it unchanged
+        if self.fused_loss and fused_loss_supported(a, preds):
+            loss, terms = fused_loss_backward(a, preds, batch, self.caster.network)
+            return loss, preds
         loss, terms = compute_loss(a, preds, batch, self.caster.network)
-        if self.world > 1:
-            # every rank holds 1/world of the batch: mean-reduced data terms are averaged by the all-reduce; the
-            # parameter-only volume penalty is identical on every rank, so averaging leaves it unchanged
-            pass
         loss.backward()
         return loss.detach(), preds

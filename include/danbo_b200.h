@@ -191,6 +191,20 @@ int danbo_field_agg_bwd(const float* rays, int ray_stride, int n_rays, int S, co
                         float* d_logit, const int* work, int pair_capacity, float* const* grads, int num_sms,
                         int agg_mode, void* stream);
 
+/* L*: the trainer's losses on the outputs of the path, value and gradients in one launch (core/trainer.py:396-422
+ * _compute_nerf_loss with loss_fn L1 (loss_kind 0) or MSE (1) on rgb + (1 - acc) bg for the fine and, if rgb0 != NULL,
+ * the coarse maps; :507-536 _compute_soft_softmax_loss when confd != NULL; :538-553 _compute_volume_scale_loss when
+ * axis_scale != NULL).  target (n,3); bgs (n,3) or NULL (then bg_scalar); confd / part_invalid (n,S_t,24); T_i / alpha
+ * (n,S_t).  terms[4] (device doubles, overwritten) = { rgb, rgb coarse, soft-softmax, volume-scale } with their
+ * coefficients applied; their sum is the trainer's total loss.  g_* receive d total / d input (written), except
+ * g_axis_scale (24,3), which is added to. */
+int danbo_train_loss(const float* rgb_map, const float* acc_map, const float* rgb0, const float* acc0,
+                     const float* target, const float* bgs, float bg_scalar, int use_background, int n_rays,
+                     int loss_kind, float rgb_coef, float coarse_weight, const float* confd, const float* part_invalid,
+                     const float* T_i, const float* alpha, int S_t, float soft_coef, const float* axis_scale,
+                     const float* init_scale, float vol_coef, double* terms, float* g_rgb_map, float* g_acc_map,
+                     float* g_rgb0, float* g_acc0, float* g_confd, float* g_axis_scale, void* stream);
+
 /* Adam (torch.optim.Adam formulas, raycasters.py:71-78: betas (0.9, 0.999), no weight decay) over one flat fp32 arena
  * holding every parameter; grads / exp_avg / exp_avg_sq are arenas of the same layout; all 16-byte aligned.  lr_dev
  * and step_dev are device floats (step already incremented) so that a captured graph reads their current values. */

@@ -376,3 +376,82 @@ def test_grads_in_place_equals_returned_grads():
         scale = max(float(ga[n].abs().max()), 1e-12)
         err = float((ga[n] - gb[n]).abs().max())
         assert err <= 2e-4 * scale + 1e-9, (n, err, scale)       # atomics reorder fp32 sums between runs
+
+
+@pytest.mark.parametrize("kind", ["L1", "MSE"])
+def test_fused_loss_matches_torch_losses(kind):
+    """danbo_train_loss (values + closed-form gradients, one launch) against the trainer's losses as PyTorch ops +
+    autograd (training.compute_loss, which restates core/trainer.py:396-422,507-553) on random render outputs,
+    including axis scales below the clamp and with negative sign."""
+    import danbo_b200 as db
+    from danbo_b200 import training, kernels
+    caster, _, _ = make_caster("danbo_cfg3", train=True)
+    args = db.make_args("danbo_cfg3", no_reload=True, loss_fn=kind, rgb_loss_coef=0.7, coarse_weight=0.5)
+    net = caster.network
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    R = lambda *s: torch.rand(*s, device=DEV, generator=gen)
+    n, S_t = 333, 80
+    with torch.no_grad():
+        sc = net.graph_net.axis_scale
+        sc[3, 1] = -sc[3, 1]
+        sc[5, 0] = 1e-4
+        sc[7, 2] = -1e-4
+    alpha = R(n, S_t) * (R(n, S_t) > 0.4)
+    preds = {"rgb_map": R(n, 3), "acc_map": R(n), "rgb0": R(n, 3), "acc0": R(n), "confd": (R(n, S_t, 24) - 0.5) * 6,
+             "part_invalid": (R(n, S_t, 24) > 0.3).float(), "T_i": R(n, S_t), "alpha": alpha}
+    diff = ("rgb_map", "acc_map", "rgb0", "acc0", "confd")
+    for k in diff:
+        preds[k].requires_grad_(True)
+    batch = {"target_s": R(n, 3), "bgs": R(n, 3)}
+    loss_ref, terms_ref = training.compute_loss(args, preds, batch, net)
+    net.graph_net.axis_scale.grad = None
+    loss_ref.backward()
+    g_scale_ref = net.graph_net.axis_scale.grad.clone()
+    g_scale = torch.zeros_like(g_scale_ref)
+    terms, g = kernels.train_loss({k: v.detach() for k, v in preds.items()}, batch["target_s"], batch["bgs"], kind,
+                                  args.rgb_loss_coef, args.coarse_weight, soft_coef=args.soft_softmax_loss_coef,
+                                  axis_scale=net.graph_net.axis_scale, init_scale=net.graph_net.init_scale,
+                                  vol_coef=args.vol_scale_penalty, g_axis_scale=g_scale)
+    torch.cuda.synchronize()
+    names = ("rgb_loss", "rgb_loss0", "soft_softmax_loss", "vol_scale_loss")
+    for i, nm in enumerate(names):
+        a, b = float(terms[i]), float(terms_ref[nm])
+        print(f"[loss] {kind} {nm}: fused {a:.8f} torch {b:.8f}")
+        assert abs(a - b) <= 2e-6 * max(abs(b), 1e-3), (nm, a, b)
+    assert abs(float(terms.sum()) - float(loss_ref)) <= 2e-6 * abs(float(loss_ref))
+    for k in diff:
+        want = preds[k].grad
+        err = float((g[k] - want).abs().max())
+        assert err <= 2e-5 * float(want.abs().max()) + 1e-12, (k, err, float(want.abs().max()))
+    assert float((g_scale - g_scale_ref).abs().max()) <= 1e-6 * float(g_scale_ref.abs().max())
+    # scalar background / no soft-softmax term / no coarse maps
+    p2 = {k: v.detach().clone().requires_grad_(k in diff) for k, v in preds.items() if k not in ("rgb0", "acc0", "confd")}
+    l2, _ = training.compute_loss(args, p2, {"target_s": batch["target_s"]}, net)
+    l2.backward()
+    t2, g2 = kernels.train_loss({k: v.detach() for k, v in p2.items()}, batch["target_s"], 1.0, kind, args.rgb_loss_coef,
+                                args.coarse_weight)
+    assert abs(float(t2.sum()) - float(l2 - terms_ref["vol_scale_loss"])) <= 2e-6 * abs(float(l2))
+    assert float((g2["acc_map"] - p2["acc_map"].grad).abs().max()) <= 2e-5 * float(p2["acc_map"].grad.abs().max())
+
+
+def test_train_step_fused_loss_equals_torch_loss_path():
+    """A whole iteration with the fused loss kernel gives the loss and gradients of the PyTorch-op loss path."""
+    from danbo_b200 import synthetic as syn, training
+    batch = syn.training_batch(2, 64, seed=9)
+    batch = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in batch.items()}
+
+    def run(fused):
+        caster, args, _ = make_caster("danbo_cfg3", train=True)
+        step = training.TrainStep(caster, args, fused_loss=fused)
+        torch.manual_seed(21)
+        loss, _ = step._fwd_bwd(batch)
+        return float(loss), {n: p.grad.detach().clone() for n, p in caster.network.named_parameters() if p.grad is not None}
+
+    la, ga = run(False)
+    lb, gb = run(True)
+    assert abs(la - lb) <= 2e-6 * abs(la), (la, lb)
+    assert set(ga) == set(gb)
+    for n in ga:
+        scale = max(float(ga[n].abs().max()), 1e-12)
+        err = float((ga[n] - gb[n]).abs().max())
+        assert err <= 3e-4 * scale + 1e-9, (n, err, scale)       # atomics reorder fp32 sums between runs
