@@ -107,3 +107,40 @@ def render_block_with_grad(caster, rays, skip, pose_skts, pose_cyls, vol, cam_id
                nanmean_chunk=nanmean_chunk, rand=rand, stages=stages, lindisp=lindisp)
     outs = _RenderBlock.apply(caster, cfg, vol, *params)
     return dict(zip(OUT_KEYS, outs))
+
+
+class _GraphNet(torch.autograd.Function):
+    """GN1 + GN2 (pose -> bone feature lines) as three launches each way; gradients go to the ten graph-net parameters
+    (the pose itself is not optimised on this path: opt_pose is off in every shipped config)."""
+
+    @staticmethod
+    def forward(ctx, net, pose_bones, *params):
+        named = {n: p for n, p in zip(K.GN_GRADS, params)}
+        gn = net.graph_net
+        named["layers.0.adj"], named["layers.1.adj"] = gn.layers[0].adj, gn.layers[1].adj
+        vol, saved = K.graph_net_fwd(pose_bones, [named[n].detach() for n in K.GN_PARAMS])
+        ctx.saved_bufs, ctx.net, ctx.params = saved, net, params
+        return vol
+
+    @staticmethod
+    def backward(ctx, d_vol):
+        params = ctx.params
+        # same contract as _RenderBlock: with a pre-zeroed flat gradient bucket the kernels add straight into .grad
+        in_place = bool(getattr(ctx.net, "grads_in_place", False)) and all(
+            p.grad is not None and p.grad.dtype == torch.float32 and p.grad.is_contiguous() and p.grad.shape == p.shape
+            for p in params)
+        grads = [p.grad if in_place else torch.zeros_like(p, dtype=torch.float32) for p in params]
+        K.graph_net_bwd(ctx.saved_bufs, d_vol, grads)
+        ctx.saved_bufs = None
+        if in_place:
+            return (None, None) + (None,) * len(params)
+        return (None, None) + tuple(grads)
+
+
+def graph_net_volumes(net, pose_bones):
+    named = dict(net.graph_net.named_parameters())
+    params = [named[n] for n in K.GN_GRADS]
+    if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+        return _GraphNet.apply(net, pose_bones, *params)
+    named["layers.0.adj"], named["layers.1.adj"] = net.graph_net.layers[0].adj, net.graph_net.layers[1].adj
+    return K.graph_net_fwd(pose_bones, [named[n].detach() for n in K.GN_PARAMS])[0]

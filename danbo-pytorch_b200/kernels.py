@@ -519,6 +519,43 @@ def field_agg_bwd(rays, S, z, mask, active, pose_skts, pose_vol, rays_per_pose, 
     _count(2)
 
 
+GN_PARAMS = ["layers.0.lin.weight", "layers.0.adj_w", "layers.0.adj", "layers.0.bias", "layers.1.lin.weight",
+             "layers.1.adj_w", "layers.1.adj", "layers.1.bias", "layers.2.weight", "layers.2.bias", "layers.3.weight",
+             "layers.3.bias"]                                    # order of danbo_graph_net_fwd's params[12]
+GN_GRADS = [n for n in GN_PARAMS if not n.endswith(".adj")]     # order of danbo_graph_net_bwd's grads[10]
+
+
+def graph_net_fwd(pose_bones, tensors):
+    """GN1 + GN2 in three launches.  pose_bones (G,24,3); tensors: the 12 GN_PARAMS tensors (fp32, CUDA).
+    -> vol (G,24,240), saved (what graph_net_bwd needs)."""
+    lib = _lib.load()
+    pb = f32c(pose_bones)
+    tensors = [f32c(t) for t in tensors]
+    _need_cuda(pb, *tensors)
+    G, dev = pb.shape[0], pb.device
+    bufs = [torch.empty(G, J, 66, device=dev)] + [torch.empty(G, J, 128, device=dev) for _ in range(5)]
+    vol = torch.empty(G, J, 240, device=dev)
+    pa = (ctypes.c_void_p * 12)(*[t.data_ptr() for t in tensors])
+    sa = (ctypes.c_void_p * 6)(*[t.data_ptr() for t in bufs])
+    _lib.check(lib.danbo_graph_net_fwd(_p(pb), G, pa, sa, _p(vol), _stream()), "danbo_graph_net_fwd")
+    _count(3)
+    return vol, (tensors, bufs)
+
+
+def graph_net_bwd(saved, d_vol, grads):
+    """grads: the 10 fp32 accumulators in GN_GRADS order (added to)."""
+    lib = _lib.load()
+    tensors, bufs = saved
+    d_vol = f32c(d_vol)
+    G, dev = d_vol.shape[0], d_vol.device
+    work = torch.empty(2 * G * J * 128, device=dev)
+    pa = (ctypes.c_void_p * 12)(*[t.data_ptr() for t in tensors])
+    sa = (ctypes.c_void_p * 6)(*[t.data_ptr() for t in bufs])
+    ga = (ctypes.c_void_p * 10)(*[g.data_ptr() for g in grads])
+    _lib.check(lib.danbo_graph_net_bwd(G, pa, sa, _p(d_vol), ga, _p(work), _stream()), "danbo_graph_net_bwd")
+    _count(3)
+
+
 LOSS_KINDS = {"L1": 0, "MSE": 1}
 
 

@@ -223,8 +223,13 @@ class DanboField(nn.Module):
         pass                                                     # no cutoff / frequency schedule in DANBO configs
 
     # ---- GN1 + GN2 (PyTorch, per unique pose) ---------------------------------------------------------------
+    fused_graph_net = True        # GN1 + GN2 as danbo_graph_net_fwd/_bwd (CUDA tensors); False: the PyTorch ops below
+
     def bone_volumes(self, pose_bones):
         """pose_bones (G,24,3) axis-angle -> (G,24,240) feature lines (encoders.py:460-473,859-877; danbo.py:190-194)."""
+        if self.fused_graph_net and pose_bones.is_cuda:
+            from .autograd import graph_net_volumes
+            return graph_net_volumes(self, pose_bones)
         R = axis_angle_to_matrix(pose_bones)
         w = pe_embed(R[..., :3, :2].flatten(start_dim=-2), self.multires_graph)
         return self.graph_net(w)

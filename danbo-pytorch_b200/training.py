@@ -121,6 +121,7 @@ class TrainStep:
         params = [p for p in caster.network.parameters() if p.requires_grad]
         self.bucket = parallel.GradBucket(params)
         caster.grads_in_place = True            # backward kernels add into the bucket's views (see autograd._RenderBlock)
+        caster.network.grads_in_place = True    # ... and so does the graph net's backward (autograd._GraphNet)
         cuda = params[0].is_cuda
         if optimizer is None:
             # default: the single-launch Adam over flat arenas; pass a torch optimizer to keep the reference's

@@ -191,6 +191,21 @@ int danbo_field_agg_bwd(const float* rays, int ray_stride, int n_rays, int S, co
                         float* d_logit, const int* work, int pair_capacity, float* const* grads, int num_sms,
                         int agg_mode, void* stream);
 
+/* GN1 + GN2: the per-pose skeleton graph net, pose_bones (n_poses,24,3) axis-angle -> vol_out (n_poses,24,240) bone
+ * feature lines (encode_graph_inputs core/encoders.py:460-473,859-877; BodyGNN.forward on FactorizeGNN
+ * core/networks/gnn_backbone.py:683-704,225-274; ParallelLinear core/networks/misc.py:174-183; incl. the doubled layer-0
+ * output).  params[12] = graph_net.layers.{0.lin.weight (24,66,128), 0.adj_w (24,24), 0.adj (24,24), 0.bias
+ * (128), 1.lin.weight (24,128,128), 1.adj_w, 1.adj, 1.bias, 2.weight (24,128,128), 2.bias (24,128), 3.weight (24,128,240),
+ * 3.bias (24,240)}.  saved[6] = { graph inputs (n_poses,24,66), lin0, n1, lin1, n2, n3 (each n_poses,24,128) }: written by
+ * the forward call, read by the backward call.  3 launches each way. */
+int danbo_graph_net_fwd(const float* pose_bones, int n_poses, const float* const* params, float* const* saved,
+                        float* vol_out, void* stream);
+
+/* grads[10] = d { 0.lin.weight, 0.adj_w, 0.bias, 1.lin.weight, 1.adj_w, 1.bias, 2.weight, 2.bias, 3.weight, 3.bias } (fp32,
+ * added to); d_vol (n_poses,24,240); work = 2 * n_poses*24*128 floats. */
+int danbo_graph_net_bwd(int n_poses, const float* const* params, float* const* saved, const float* d_vol,
+                        float* const* grads, float* work, void* stream);
+
 /* L*: the trainer's losses on the outputs of the path, value and gradients in one launch (core/trainer.py:396-422
  * _compute_nerf_loss with loss_fn L1 (loss_kind 0) or MSE (1) on rgb + (1 - acc) bg for the fine and, if rgb0 != NULL,
  * the coarse maps; :507-536 _compute_soft_softmax_loss when confd != NULL; :538-553 _compute_volume_scale_loss when

@@ -455,3 +455,49 @@ def test_train_step_fused_loss_equals_torch_loss_path():
         scale = max(float(ga[n].abs().max()), 1e-12)
         err = float((ga[n] - gb[n]).abs().max())
         assert err <= 3e-4 * scale + 1e-9, (n, err, scale)       # atomics reorder fp32 sums between runs
+
+
+@pytest.mark.parametrize("G", [1, 16, 21])
+def test_graph_net_kernels(G):
+    """GN1 + GN2 as CUDA kernels (danbo_graph_net_fwd / _bwd) against the same module as PyTorch fp32 ops + autograd
+    (networks.GraphNet, which mirrors gnn_backbone.py:683-704), and against the reference's own vol tensor.
+    G = 21 spans two 16-pose groups (the gradient accumulation then uses atomics)."""
+    caster, args, _ = make_caster("danbo_fast", train=True)
+    net = caster.network
+    gen = torch.Generator(device=DEV).manual_seed(G)
+    with torch.no_grad():                                   # biases are zero-initialised: give every term a gradient path
+        for n, p in net.graph_net.named_parameters():
+            if n.endswith("bias"):
+                p.copy_(torch.randn(p.shape, device=DEV, generator=gen) * 0.1)
+    bones = torch.randn(G, 24, 3, device=DEV, generator=gen) * 0.3
+    bones[0, 3] = 0.                                        # small-angle branch of the axis-angle conversion
+    d_vol = torch.randn(G, 24, 240, device=DEV, generator=gen)
+    params = dict(net.graph_net.named_parameters())
+
+    def run(fused):
+        net.fused_graph_net = fused
+        for p in params.values():
+            p.grad = None
+        vol = net.bone_volumes(bones)
+        (vol * d_vol).sum().backward()
+        return vol.detach().clone(), {n: p.grad.detach().clone() for n, p in params.items() if p.grad is not None}
+
+    try:
+        v_ref, g_ref = run(False)
+        v_got, g_got = run(True)
+    finally:
+        net.fused_graph_net = True
+    err = float((v_got - v_ref).abs().max())
+    assert err <= 2e-5 * float(v_ref.abs().max()), err
+    assert set(g_ref) == set(g_got), (set(g_ref) ^ set(g_got))
+    for n in g_ref:
+        scale = float(g_ref[n].abs().max())
+        e = float((g_got[n] - g_ref[n]).abs().max())
+        print(f"[gn] G={G} {n:24s} |g| {scale:.3e} err {e:.3e}")
+        assert e <= 1e-4 * scale + 1e-9, (n, e, scale)
+    if G == 1:                                              # the reference's own output for a fixture pose
+        fx = load_fixture("render_fast")
+        caster2, _, _ = make_caster("danbo_fast")
+        vol = caster2.network.bone_volumes(fx["pose_bones"][None].to(DEV))
+        want = fx["st.vol.0"]
+        assert float((vol.cpu() - want).abs().max()) <= 2e-5 * float(want.abs().max())
