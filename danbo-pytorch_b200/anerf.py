@@ -106,8 +106,6 @@ class AnerfCaster(RayCaster):
     def _render_prepared(self, rays, pose_skts, pose_bones, pose_cyls, cam_idx, skip=1, N_samples=96, N_importance=48,
                          B=1.0, raw_noise_std=0., perturb=0., nanmean_chunk=None, lindisp=False, _rand=None,
                          _stages=None):
-        if lindisp:
-            raise NotImplementedError("lindisp is implemented for the DANBO field only (anerf_base.txt ships lindisp=False)")
         if self.training:
             raise NotImplementedError("A-NeRF (nerf_type='nerf') is render-only here: the backward kernels exist for the "
                                       "DANBO field only (BASELINE config #4 is a render benchmark)")
@@ -126,13 +124,14 @@ class AnerfCaster(RayCaster):
         for s0 in range(0, N, block):
             s1 = min(N, s0 + block)
             outs.append(self._render_block_anerf(rays[s0:s1], s0, skip, pose_skts, pose_cyls, cam_idx[s0:s1], codes, align,
-                                                 packed, tau, N_samples, N_importance, B, nanmean_chunk, _stages))
+                                                 packed, tau, N_samples, N_importance, B, nanmean_chunk, _stages,
+                                                 lindisp=lindisp))
         if len(outs) == 1:
             return outs[0]
         return {k: torch.cat([o[k] for o in outs], 0) for k in outs[0]}
 
     def _render_block_anerf(self, rays, ray0, skip, pose_skts, pose_cyls, cam_idx, codes, align, packed, tau, S_c, S_f, B,
-                            nanmean_chunk, stages):
+                            nanmean_chunk, stages, lindisp=False):
         n = rays.shape[0]
         dev = rays.device
         if pose_skts.shape[0] == 1:
@@ -146,7 +145,10 @@ class AnerfCaster(RayCaster):
         enc, code_bias = K.anerf_ray_encode(rays, p_skts, skip, cam_idx, codes, packed)
         # SM1 (ray_utils.py:206-253, eval): z = near (1 - t) + far t, the reference's own two-product form
         t = torch.linspace(0., 1., steps=S_c, device=dev)
-        z0 = (near[:, None] * (1. - t) + far[:, None] * t).contiguous()
+        if not lindisp:
+            z0 = (near[:, None] * (1. - t) + far[:, None] * t).contiguous()
+        else:                                                # ray_utils.py:226-227, the reference's own expression
+            z0 = (1. / (1. / near[:, None] * (1. - t) + 1. / far[:, None] * t)).contiguous()
         xd, xv = K.anerf_embed(rays, S_c, z0, p_skts, skip, align, enc, tau)
         raw0 = torch.empty(n * S_c + n, 4, device=dev, dtype=torch.float32)
         K.anerf_mlp(xd, xv, packed, code_bias, n * S_c, S_c, raw0)
@@ -168,19 +170,43 @@ class AnerfCaster(RayCaster):
                            "raw": c1.get("raw"), "ray_enc": enc, "code_bias": code_bias})
         return ret
 
-    # ---- not part of config #4 --------------------------------------------------------------------------------
-    def render_pts_density(self, *a, **k):
-        raise NotImplementedError("density queries (fwd_type='density'/'mesh') are implemented for the DANBO field only")
+    # ---- density queries (D1 for this field; not part of config #4) ------------------------------------------
+    @torch.no_grad()
+    def render_pts_density(self, pts, kps, skts, bones=None, netchunk=1024 * 64, network=None):
+        """Raw sigma at points (P,1,3) or (P,3) for ONE pose (raycasters.py:439-453, nerf.py:136-154 forward_pts).
+        Each point is a one-sample ray (o = point, z = 0) through the render path's own kernels; sigma is the head of the
+        density trunk and does not depend on the view branch, which runs on an arbitrary unit direction."""
+        assert kps.shape[0] == 1, f"Assuming only one poses are provided, got {kps.shape[0]} instead"
+        dev = self._device()
+        P = pts.shape[0]
+        p = pts.reshape(P, 3).to(dev).float()
+        align, packed, codes, tau = self._align(), self._packed_mlp(), self._codes_with_mean(), self._tau()
+        p_skts = skts.to(dev).float().contiguous()
+        out = torch.empty(P, device=dev)
+        block = MAX_RAYS_PER_LAUNCH * 8                     # rows per launch sequence (operand images: 2.3 KB per row)
+        for s0 in range(0, P, block):
+            s1 = min(P, s0 + block)
+            n = s1 - s0
+            rays = torch.zeros(n, 8, device=dev)
+            rays[:, :3] = p[s0:s1]
+            rays[:, 5] = 1.0
+            cam = torch.zeros(n, device=dev, dtype=torch.int32)
+            enc, code_bias = K.anerf_ray_encode(rays, p_skts, n, cam, codes, packed)
+            z = torch.zeros(n, 1, device=dev)
+            xd, xv = K.anerf_embed(rays, 1, z, p_skts, n, align, enc, tau)
+            raw = torch.empty(n, 4, device=dev, dtype=torch.float32)
+            K.anerf_mlp(xd, xv, packed, code_bias, n, 1, raw)
+            out[s0:s1] = raw[:, 3]
+        return out.reshape(P, 1, 1) if pts.dim() == 3 else out.reshape(P, 1)
 
-    def render_mesh_density(self, *a, **k):
-        raise NotImplementedError("density queries (fwd_type='density'/'mesh') are implemented for the DANBO field only")
+    # render_mesh_density: inherited (lattice around the root joint -> render_pts_density)
 
 
 _ANERF_REQUIRED = {"netdepth": 8, "netwidth": 448, "multires": 7, "multires_views": 4, "multires_bones": 0,
                    "framecode_size": 128, "single_net": True, "opt_framecode": True, "use_viewdirs": True,
                    "use_cutoff": True, "cutoff_viewdir": True, "cutoff_inputs": True, "cutoff_shift": True,
                    "cut_to_dist": True, "cutoff_bones": False, "normalize_cutoff": False, "opt_cutoff": False,
-                   "freq_schedule": False, "cutoff_mm": 500.0, "ext_scale": 0.001, "i_embed": 0, "lindisp": False}
+                   "freq_schedule": False, "cutoff_mm": 500.0, "ext_scale": 0.001, "i_embed": 0}
 _ANERF_SUPPORTED = {"align_bones": ("align",), "density_type": ("relu",), "kp_dist_type": ("reldist",),
                     "view_type": ("relray",), "ray_tr_type": ("local",), "pts_tr_type": ("local",), "bone_type": ("reldir",)}
 

@@ -72,8 +72,8 @@ class RayCaster(nn.Module):
         from .graphs import GraphedFn
         if self.training:
             raise RuntimeError("render_graphed is for eval mode")
-        if ignored.get("ray_noise_std", 0.) > 0 or ignored.get("render_confd") or ignored.get("render_entropy"):
-            raise NotImplementedError("ray_noise_std / render_confd / render_entropy are not implemented")
+        if ignored.get("ray_noise_std", 0.) > 0 or ignored.get("pytest"):
+            raise NotImplementedError("ray_noise_std > 0 and pytest are not implemented")
         B = float((preproc_kwargs or {}).get("density_scale", 1.0))
         rays, pose_skts, pose_bones, pose_cyls, cam_idx, skip = self._prepare(ray_batch, skts, cyls, bones, cams, N_uniques)
         if self._graphed is None:
@@ -148,8 +148,11 @@ class RayCaster(nn.Module):
         Extra (optional) keywords: `nanmean_chunk` keeps the reference's per-chunk near/far fill (F8) when more than
         one reference chunk is passed in a single call; `_rand`/`_stages` are test hooks (inject the four random
         tensors / collect stage tensors)."""
-        if ray_noise_std > 0 or render_confd or render_entropy or pytest:
-            raise NotImplementedError("ray_noise_std / render_confd / render_entropy / pytest are not implemented")
+        # render_confd / render_entropy / verbose / retraw are accepted and ignored, as in the reference's render_rays
+        # (raycasters.py:245-377 never reads them)
+        if ray_noise_std > 0 or pytest:
+            raise NotImplementedError("ray_noise_std > 0 (samples moved off their ray) and pytest (numpy's fixed random "
+                                      "numbers) are not implemented")
         if N_importance <= 0:
             raise NotImplementedError("N_importance must be > 0 (the reference itself requires it, SURVEY F10)")
         if skts is None or bones is None or cyls is None or cams is None:

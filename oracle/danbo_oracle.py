@@ -488,7 +488,7 @@ def anerf_mlp(x, view, P):
 
 
 def anerf_render_rays(ray_batch, pose_skts, pose_cyls, cams, A, P, S_c, S_f, rays_per_pose, training=False, rand=None,
-                      raw_noise_std=0., tau=20., return_stages=False, z_samples=None):
+                      raw_noise_std=0., tau=20., return_stages=False, z_samples=None, lindisp=False):
     """RayCaster.render_rays (raycasters.py:245-377) for nerf_type=nerf: cylinder near/far only (:419-420), the field
     evaluated on every sample, single_net fine pass on the S_f new samples (F9)."""
     N = ray_batch.shape[0]
@@ -498,7 +498,7 @@ def anerf_render_rays(ray_batch, pose_skts, pose_cyls, cams, A, P, S_c, S_f, ray
     rays_o, rays_d = ray_batch[:, 0:3], ray_batch[:, 3:6]
     near, far = cylinder_near_far(rays_o, rays_d, cyls, ray_batch[:, 6:7], ray_batch[:, 7:8])
     rand = rand or {}
-    z = coarse_z(near, far, S_c, rand.get("t_rand"))
+    z = coarse_z(near, far, S_c, rand.get("t_rand"), lindisp)
     x0, v0, st0 = anerf_inputs(ray_points(rays_o, rays_d, z), rays_d, cams, skts, A, P, training, tau)
     raw0 = anerf_mlp(x0, v0, P).reshape(N, S_c, 4)
     n0 = rand["noise0"] * raw_noise_std if "noise0" in rand else None
@@ -538,6 +538,27 @@ def density_grid(kps, skts, bones, A, P, radius, res, agg_type="sigmoid"):
     p = agg_prob(agg_net(hf, P), invalid.reshape(-1, J), agg_type)
     x = pe_embed((hf * p[..., None]).sum(-2), 6)
     sigma = F.linear(density_trunk(x, P), P["alpha_linear.weight"], P["alpha_linear.bias"])
+    return sigma.reshape(*sh[:-1]).transpose(1, 0)
+
+
+def anerf_density_grid(kps, skts, A, P, radius, res, tau=20.):
+    """The same lattice query for the A-NeRF field (nerf.py:136-154 forward_pts -> encode_pts :222-250): raw sigma =
+    alpha_linear of the W=448 trunk on [cutoff PE(v) ; r]; the view branch is not evaluated."""
+    t = np.linspace(-radius, radius, res + 1)
+    grid = np.stack(np.meshgrid(t, t, t), axis=-1).astype(np.float32)
+    sh = grid.shape
+    pts = (torch.tensor(grid.reshape(-1, 3)) + kps[0, 0]).reshape(-1, 1, 3)
+    n = pts.shape[0]
+    pts_t = world_to_bone(pts, skts.expand(n, -1, -1, -1), A)
+    v = torch.norm(pts_t, dim=-1, p=2)
+    r = F.normalize(pts_t, dim=-1, p=2).flatten(start_dim=2)
+    x = torch.cat([anerf_dist_pe(v, tau), r], -1).reshape(n, -1)
+    h = x
+    for i in range(8):
+        h = F.relu(F.linear(h, P[f"pts_linears.{i}.weight"], P[f"pts_linears.{i}.bias"]))
+        if i == 4:
+            h = torch.cat([x, h], -1)
+    sigma = F.linear(h, P["alpha_linear.weight"], P["alpha_linear.bias"])
     return sigma.reshape(*sh[:-1]).transpose(1, 0)
 
 

@@ -355,7 +355,8 @@ def run_grid_case(name, config, pose_seed, res, radius=0.9, weight_seed=0):
     rest = syn.rest_pose()
     caster, kw = rh.build(args, rest)
     caster.eval()
-    rh.load_weights(caster, syn.synth_state_dict(params.danbo_param_shapes(), weight_seed))
+    shapes = params.anerf_param_shapes() if args.nerf_type == "nerf" else params.danbo_param_shapes()
+    rh.load_weights(caster, syn.synth_state_dict(shapes, weight_seed))
     pose = syn.make_pose(pose_seed)
     t = lambda a: torch.as_tensor(a)[None]
     with torch.no_grad():
@@ -379,6 +380,9 @@ def main():
     if only == "variants":
         variants()
         return
+    if only == "grid_anerf":
+        run_grid_case("grid_anerf", "h36m_zju/anerf_base.txt", pose_seed=4, res=9)
+        return
     run_render_case("render_fast", "h36m_zju/danbo_fast.txt", [], pose_seed=3, H=64, n_rays=256)
     run_render_case("render_base", "h36m_zju/danbo_base.txt", [], pose_seed=5, H=64, n_rays=96)
     run_render_case("render_fast_miss", "h36m_zju/danbo_fast.txt", [], pose_seed=7, H=48, n_rays=192, full_image=True)
@@ -388,6 +392,7 @@ def main():
     run_grid_case("grid_base", "h36m_zju/danbo_base.txt", pose_seed=3, res=11)
     run_anerf_case("render_anerf", ["--N_samples", "24", "--N_importance", "12"], pose_seed=4, H=64, n_rays=64)
     variants()
+    run_grid_case("grid_anerf", "h36m_zju/anerf_base.txt", pose_seed=4, res=9)
 
 
 def variants():

@@ -23,7 +23,8 @@ def anerf_params(fx):
 def make_anerf_caster(fx):
     import danbo_b200 as db
     from danbo_b200 import synthetic as syn, skeleton as sk
-    args = db.make_args("anerf_base", no_reload=True, N_samples=int(fx["N_samples"]), N_importance=int(fx["N_importance"]))
+    args = db.make_args("anerf_base", no_reload=True, N_samples=int(fx.get("N_samples", 96)),
+                        N_importance=int(fx.get("N_importance", 48)))
     attrs = {"skel_type": sk.SMPLSkeleton, "near": syn.NEAR, "far": syn.FAR, "n_views": 8, "rest_pose": syn.rest_pose()}
     _, kw_test, *_ = db.create_raycaster(args, attrs, device=DEV)
     caster = kw_test["ray_caster"]
@@ -155,3 +156,54 @@ def test_anerf_full_size_properties():
     sl = slice(8192, 8192 + 4096)
     sub = caster(b["ray_batch"][sl], **{k: (v[sl] if torch.is_tensor(v) and v.shape[0] == N else v) for k, v in kw.items()})
     assert torch.equal(sub["rgb_map"], out["rgb_map"][sl]) and torch.equal(sub["acc_map"], out["acc_map"][sl])
+
+
+def test_anerf_density_grid_and_points():
+    """fwd_type='mesh' / 'density' for the A-NeRF field (D1): the reference's render_mesh_density on a 10^3 lattice."""
+    fx = load_fixture("grid_anerf")
+    caster, args, P = make_anerf_caster(fx)
+    t = lambda a: a[None].to(DEV)
+    sig = caster(kps=t(fx["pose_kps"]), skts=t(fx["pose_skts"]), bones=t(fx["pose_bones"]), radius=float(fx["radius"]),
+                 res=int(fx["res"]), fwd_type="mesh")
+    want = fx["sigma"]
+    assert sig.shape == want.shape
+    err = (sig.cpu() - want).abs()
+    print(f"[anerf grid] sigma: mean {float(err.mean()):.3e} max {float(err.max()):.3e} scale {float(want.abs().max()):.3e}")
+    assert float(err.max()) <= 3e-2 * float(want.abs().max()) and float(err.mean()) <= 4e-3 * float(want.abs().max())
+    # point queries ('density') return the same numbers as the lattice they were taken from
+    import numpy as np
+    r, res = float(fx["radius"]), int(fx["res"])
+    tt = np.linspace(-r, r, res + 1)
+    grid = np.stack(np.meshgrid(tt, tt, tt), axis=-1).astype(np.float32).reshape(-1, 3)
+    pts = torch.tensor(grid).to(DEV) + fx["pose_kps"][0].to(DEV)
+    pd = caster(pts.reshape(-1, 1, 3), t(fx["pose_kps"]), t(fx["pose_skts"]), t(fx["pose_bones"]), fwd_type="density")
+    assert pd.shape == (pts.shape[0], 1, 1)
+    assert torch.equal(pd.reshape(res + 1, res + 1, res + 1).transpose(1, 0), sig)
+
+
+def test_anerf_lindisp():
+    """--lindisp on the A-NeRF path: coarse depths bit-identical to the oracle's (whose lindisp z is pinned by the
+    reference-generated render_fast_lindisp fixture), pixels within the bf16 tolerance of the oracle's."""
+    import danbo_oracle as orc
+    from util import align_A
+    fx = load_fixture("render_anerf")
+    caster, args, P = make_anerf_caster(fx)
+    skts, bones, cyl = pose_tensors(fx)
+    rb = fx["ray_batch"]
+    N = rb.shape[0]
+    e = lambda t: t.to(DEV).expand(N, *t.shape[1:])
+    st = {}
+    ret = caster(rb.to(DEV), N_samples=args.N_samples, kp_batch=e(fx["pose_kps"][None]), skts=e(skts), cyls=e(cyl),
+                 bones=e(bones), cams=fx["cams"].to(DEV), N_uniques=1, perturb=False, N_importance=args.N_importance,
+                 raw_noise_std=0., nerf_type="nerf", lindisp=True, _stages=st)
+    with torch.no_grad():
+        want = orc.anerf_render_rays(rb, skts, cyl, fx["cams"], align_A(), {k: v.cpu() for k, v in P.items()},
+                                     int(fx["N_samples"]), int(fx["N_importance"]), rays_per_pose=N, tau=float(fx["tau"]),
+                                     lindisp=True, return_stages=True, z_samples=st["z_samples"].cpu())
+    z_ref = want["_stages"]["z_coarse"]
+    assert float((st["z_coarse"].cpu() - z_ref).abs().max()) <= 2e-6 * float(z_ref.abs().max())
+    assert not torch.equal(z_ref, fx["st.z.0"])                      # really sampled in inverse depth
+    for k, tol_mean, tol_max in (("rgb0", 3e-3, 3e-2), ("acc0", 3e-3, 3e-2), ("rgb_map", 4e-3, 5e-2), ("acc_map", 4e-3, 5e-2)):
+        d = (ret[k].cpu() - want[k]).abs()
+        print(f"[anerf lindisp] {k}: mean {float(d.mean()):.3e} max {float(d.max()):.3e}")
+        assert float(d.mean()) <= tol_mean and float(d.max()) <= tol_max, (k, float(d.mean()), float(d.max()))
