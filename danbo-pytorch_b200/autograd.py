@@ -110,7 +110,7 @@ def render_block_with_grad(caster, rays, skip, pose_skts, pose_cyls, vol, cam_id
 
 
 class _GraphNet(torch.autograd.Function):
-    """GN1 + GN2 (pose -> bone feature lines) as three launches each way; gradients go to the ten graph-net parameters
+    """GN1 + GN2 (pose -> bone feature lines) as four launches each way; gradients go to the ten graph-net parameters
     (the pose itself is not optimised on this path: opt_pose is off in every shipped config)."""
 
     @staticmethod

@@ -526,7 +526,7 @@ GN_GRADS = [n for n in GN_PARAMS if not n.endswith(".adj")]     # order of danbo
 
 
 def graph_net_fwd(pose_bones, tensors):
-    """GN1 + GN2 in three launches.  pose_bones (G,24,3); tensors: the 12 GN_PARAMS tensors (fp32, CUDA).
+    """GN1 + GN2 in four launches.  pose_bones (G,24,3); tensors: the 12 GN_PARAMS tensors (fp32, CUDA).
     -> vol (G,24,240), saved (what graph_net_bwd needs)."""
     lib = _lib.load()
     pb = f32c(pose_bones)
@@ -538,7 +538,7 @@ def graph_net_fwd(pose_bones, tensors):
     pa = (ctypes.c_void_p * 12)(*[t.data_ptr() for t in tensors])
     sa = (ctypes.c_void_p * 6)(*[t.data_ptr() for t in bufs])
     _lib.check(lib.danbo_graph_net_fwd(_p(pb), G, pa, sa, _p(vol), _stream()), "danbo_graph_net_fwd")
-    _count(3)
+    _count(4)
     return vol, (tensors, bufs)
 
 
@@ -553,7 +553,7 @@ def graph_net_bwd(saved, d_vol, grads):
     sa = (ctypes.c_void_p * 6)(*[t.data_ptr() for t in bufs])
     ga = (ctypes.c_void_p * 10)(*[g.data_ptr() for g in grads])
     _lib.check(lib.danbo_graph_net_bwd(G, pa, sa, _p(d_vol), ga, _p(work), _stream()), "danbo_graph_net_bwd")
-    _count(3)
+    _count(4)
 
 
 LOSS_KINDS = {"L1": 0, "MSE": 1}

@@ -197,7 +197,7 @@ int danbo_field_agg_bwd(const float* rays, int ray_stride, int n_rays, int S, co
  * output).  params[12] = graph_net.layers.{0.lin.weight (24,66,128), 0.adj_w (24,24), 0.adj (24,24), 0.bias
  * (128), 1.lin.weight (24,128,128), 1.adj_w, 1.adj, 1.bias, 2.weight (24,128,128), 2.bias (24,128), 3.weight (24,128,240),
  * 3.bias (24,240)}.  saved[6] = { graph inputs (n_poses,24,66), lin0, n1, lin1, n2, n3 (each n_poses,24,128) }: written by
- * the forward call, read by the backward call.  3 launches each way. */
+ * the forward call, read by the backward call.  4 launches each way. */
 int danbo_graph_net_fwd(const float* pose_bones, int n_poses, const float* const* params, float* const* saved,
                         float* vol_out, void* stream);
 
