@@ -44,25 +44,31 @@ struct Grads {                     // accumulated into (+=)
 
 // Graph inputs of (pose g, joint j): rot6d of the axis-angle (quaternion route, skeleton_utils.py:411-418) and its
 // 5-octave encoding [x, sin 2^0 x, cos 2^0 x, sin 2^1 x, ...] in blocks of 6, zeroed for the root (mask_root).
-__device__ __forceinline__ void graph_inputs(const float* __restrict__ aa, int j, float* row) {
+// One thread per (pose, rot6d component i): it writes the 11 entries that derive from component i.
+__device__ __forceinline__ void graph_inputs(const float* __restrict__ aa, int j, int i, float* row, float* keep) {
     const float ax = aa[0], ay = aa[1], az = aa[2];
     const float ang = sqrtf(ax * ax + ay * ay + az * az), half = 0.5f * ang;
     const float k = fabsf(ang) < 1e-6f ? 0.5f - ang * ang / 48.f : sinf(half) / ang;
     const float qr = cosf(half), qi = ax * k, qj = ay * k, qk = az * k;
     const float two_s = 2.f / (qr * qr + qi * qi + qj * qj + qk * qk);
-    const float r6[6] = {1.f - two_s * (qj * qj + qk * qk), two_s * (qi * qj - qk * qr),       // R00 R01
-                         two_s * (qi * qj + qk * qr), 1.f - two_s * (qi * qi + qk * qk),       // R10 R11
-                         two_s * (qi * qk - qj * qr), two_s * (qj * qk + qi * qr)};            // R20 R21
+    float r;
+    switch (i) {                                                                   // R00 R01 R10 R11 R20 R21
+        case 0: r = 1.f - two_s * (qj * qj + qk * qk); break;
+        case 1: r = two_s * (qi * qj - qk * qr); break;
+        case 2: r = two_s * (qi * qj + qk * qr); break;
+        case 3: r = 1.f - two_s * (qi * qi + qk * qk); break;
+        case 4: r = two_s * (qi * qk - qj * qr); break;
+        default: r = two_s * (qj * qk + qi * qr); break;
+    }
     const float root = j == 0 ? 0.f : 1.f;
+    float v = r * root;
+    row[i] = v;
+    if (keep) keep[i] = v;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        row[i] = r6[i] * root;
-#pragma unroll
-        for (int f = 0; f < 5; ++f) {
-            const float x = r6[i] * (float)(1 << f);
-            row[6 + 12 * f + i] = sinf(x) * root;
-            row[12 + 12 * f + i] = cosf(x) * root;
-        }
+    for (int f = 0; f < 5; ++f) {
+        const float x = r * (float)(1 << f);
+        v = sinf(x) * root; row[6 + 12 * f + i] = v; if (keep) keep[6 + 12 * f + i] = v;
+        v = cosf(x) * root; row[12 + 12 * f + i] = v; if (keep) keep[12 + 12 * f + i] = v;
     }
 }
 
@@ -103,13 +109,10 @@ fwd_kernel(const float* __restrict__ bones, int G, Params P, Saved S, float* __r
     if (MODE == 0) {
         for (int e = tid; e < kG * kP; e += kThreads) in_s[e] = 0.f;
         __syncthreads();
-        if (tid < ng) {
-            float* row = in_s + tid * kP;
-            graph_inputs(bones + ((size_t)(g0 + tid) * DANBO_J + j) * 3, j, row);
-            if (blockIdx.y == 0) {
-                float* keep = S.w_in + ((size_t)(g0 + tid) * DANBO_J + j) * kIn;
-                for (int i = 0; i < kIn; ++i) keep[i] = row[i];
-            }
+        if (tid < ng * 6) {
+            const int g = tid / 6, i = tid - g * 6;
+            graph_inputs(bones + ((size_t)(g0 + g) * DANBO_J + j) * 3, j, i, in_s + g * kP,
+                         blockIdx.y == 0 ? S.w_in + ((size_t)(g0 + g) * DANBO_J + j) * kIn : nullptr);
         }
     } else if (MODE == 3) {
         for (int e = tid; e < kG * kW; e += kThreads) {
