@@ -412,7 +412,11 @@ def run_reference(opt):
             "n_gpus": opt.gpus, "steps": opt.steps, "warmup": opt.warmup, "ms_per_step": n / v * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"danbo_fast {H}x{W} render, 1 synthetic 24-joint pose, {args.N_samples}+{args.N_importance} "
-                                   f"samples/ray; each step = {n}-ray sample of the image on the host CPU"},
+                                   f"samples/ray, box-restricted rays, random-init weights",
+                       "samples_per_ray": args.N_samples + args.N_importance, "chunk": args.chunk,
+                       "parallelism": f"host CPU, {base['cores']} threads (rank 0 only)",
+                       "sample": f"each step = {n} consecutive rays from the middle of the image (bounded sample of the "
+                                 "same workload)"},
             "cpu_baseline": dict(base, value=v),
             "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}

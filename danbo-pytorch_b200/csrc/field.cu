@@ -159,8 +159,8 @@ __global__ void nearfar_finish_kernel(const float* __restrict__ rays, int ray_st
 // list; with append_empty, one extra entry per ray (id = n_rays*S + ray) stands for "a sample no bone sees".
 // kTable: the block first builds, per ray it covers and per bone, the affine map z -> x = c + z e of the two-step
 // transform (x is affine in the sample depth), then every sample needs 3 FMAs per bone instead of ~45 instructions.
-// Rounding differs from the reference's op order by ~1e-5 at most, so a coordinate within 2e-4 of a box face is
-// re-evaluated in the exact order: the emitted mask is identical to the direct evaluation.
+// Rounding differs from the reference's op order by ~1e-5 at most, so a sample whose largest |coordinate| lies within
+// 2e-4 of a box face is re-evaluated in the exact order: the emitted mask is identical to the direct evaluation.
 constexpr int kMaskBlock = 256;
 constexpr int kMaxRaysPerBlock = 18;       // 256 / 16 + 2
 
@@ -279,11 +279,12 @@ sample_mask_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, i
         for (int j = 0; j < DANBO_J; ++j) {
             bool decided = false, invalid = false;
             if (kTable) {
+                // the largest |coordinate| decides: clearly above 1 -> outside (whatever the other two are), clearly below
+                // -> inside; only a maximum within 2e-4 of the face needs the exact evaluation
                 const float4 c = tr[2 * j], e = tr[2 * j + 1];
-                const float a0 = fabsf(fmaf(z, e.x, c.x)), a1 = fabsf(fmaf(z, e.y, c.y)), a2 = fabsf(fmaf(z, e.z, c.z));
-                const float m = fminf(fminf(fabsf(a0 - 1.f), fabsf(a1 - 1.f)), fabsf(a2 - 1.f));
-                invalid = (a0 > 1.f) || (a1 > 1.f) || (a2 > 1.f);
-                decided = m > 2e-4f;
+                const float am = fmaxf(fmaxf(fabsf(fmaf(z, e.x, c.x)), fabsf(fmaf(z, e.y, c.y))), fabsf(fmaf(z, e.z, c.z)));
+                invalid = am > 1.f;
+                decided = fabsf(am - 1.f) > 2e-4f;
             }
             if (!decided) {
                 // |fl(t/s)| > 1  <=>  |t| > |s| for correctly rounded division (t > s implies t/s > 1 + 2^-24, which
