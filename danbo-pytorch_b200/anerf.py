@@ -63,7 +63,10 @@ class AnerfField(nn.Module):
 
 
 class AnerfCaster(RayCaster):
-    """The reference's base RayCaster (raycasters.py:205-546) over the A-NeRF field, on B200 kernels."""
+    """The reference's base RayCaster (raycasters.py:205-546) over the A-NeRF field, on B200 kernels.  With a separate
+    fine network (single_net=False, configs/*/anerf_h.txt) the importance weights are the unsmoothed coarse weights and the
+    fine network is evaluated on all S_c + S_f merged samples (raycasters.py:345-371)."""
+    _supports_fine_network = True
 
     def __init__(self, network, network_fine=None, single_net=True, rest_poses=None, align_bones="align", skel_type=None,
                  **kwargs):
@@ -79,28 +82,38 @@ class AnerfCaster(RayCaster):
             self._unit_scale = torch.ones(J, 3, device=dev)
         return self._align_dev
 
-    def _tau(self):
+    def _tau(self, net=None):
         """Cutoff temperature as a host float; read back from the buffer only when the buffer changed."""
-        t = self.network.pe_fn.tau
+        net = self.network if net is None else net
+        t = net.pe_fn.tau
         key = (t.data_ptr(), t._version)
-        if getattr(self, "_tau_key", None) != key:
-            self._tau_key, self._tau_val = key, float(t.item())
-        return self._tau_val
+        cache = self.__dict__.setdefault("_tau_cache", {})
+        if cache.get(id(net), (None, None))[0] != key:
+            cache[id(net)] = (key, float(t.item()))
+        return cache[id(net)][1]
 
-    def _packed_mlp(self):
-        net = self.network
+    def _packed_mlp(self, net=None):
+        net = self.network if net is None else net
         names = [f"pts_linears.{i}.{w}" for i in range(8) for w in ("weight", "bias")] + [
             "alpha_linear.weight", "alpha_linear.bias", "feature_linear.weight", "feature_linear.bias",
             "views_linears.0.weight", "views_linears.0.bias", "rgb_linear.weight", "rgb_linear.bias"]
         P = dict(net.named_parameters())
         key = tuple((P[n].data_ptr(), P[n]._version) for n in names)
-        if self._packed is None or self._packed.wstream.device != self._device():
-            self._packed = K.AnerfPacked(self._device())
-            self._packed_key = None
-        if key != self._packed_key:
-            self._packed.pack({n: P[n] for n in names})
-            self._packed_key = key
-        return self._packed
+        cache = self.__dict__.setdefault("_packed_cache", {})
+        if self._packed_key is None:                         # set by load_state_dict / an optimizer step: repack everything
+            cache.clear()
+            self._packed_key = "valid"
+        ent = cache.get(id(net))
+        if ent is None or ent[1].wstream.device != self._device():
+            ent = cache[id(net)] = [None, K.AnerfPacked(self._device())]
+        if ent[0] != key:
+            ent[1].pack({n: P[n] for n in names})
+            ent[0] = key
+        return ent[1]
+
+    def _codes_of(self, net):
+        w = net.framecodes.codes.weight.detach()
+        return torch.cat([w, w.mean(0, keepdim=True)], 0).contiguous()
 
     # ---- render ---------------------------------------------------------------------------------------------
     def _render_prepared(self, rays, pose_skts, pose_bones, pose_cyls, cam_idx, skip=1, N_samples=96, N_importance=48,
@@ -153,8 +166,11 @@ class AnerfCaster(RayCaster):
         raw0 = torch.empty(n * S_c + n, 4, device=dev, dtype=torch.float32)
         K.anerf_mlp(xd, xv, packed, code_bias, n * S_c, S_c, raw0)
         ones0 = torch.ones(n, S_c, device=dev, dtype=torch.int32)          # every sample carries its own field value
-        c0 = K.composite_resample(rays, S_c, S_f, raw0, ones0, z0, inv_B=1.0 / B, want_inds=stages is not None)
+        c0 = K.composite_resample(rays, S_c, S_f, raw0, ones0, z0, inv_B=1.0 / B, want_inds=stages is not None,
+                                  smooth=self.single_net)
         z1 = c0["z_samples"]
+        if not self.single_net:
+            return self._fine_network_pass(rays, p_skts, skip, cam_idx, align, S_c, S_f, B, c0, near, far, z0, raw0, stages)
         xd1, xv1 = K.anerf_embed(rays, S_f, z1, p_skts, skip, align, enc, tau, xd=xd, xv=xv)
         raw1 = torch.empty(n * S_f, 4, device=dev, dtype=torch.float32)
         K.anerf_mlp(xd1, xv1, packed, code_bias, n * S_f, S_f, raw1)
@@ -168,6 +184,28 @@ class AnerfCaster(RayCaster):
             stages.update({"near": near, "far": far, "z_coarse": z0, "raw0": raw0, "weights0": c0["weights"],
                            "z_samples": z1, "z_all": c0["z_all"], "sorted_idxs": c0["order"], "raw1": raw1,
                            "raw": c1.get("raw"), "ray_enc": enc, "code_bias": code_bias})
+        return ret
+
+    def _fine_network_pass(self, rays, p_skts, skip, cam_idx, align, S_c, S_f, B, c0, near, far, z0, raw0, stages):
+        """single_net=False (raycasters.py:350-376): the fine network on all S_c + S_f merged samples, then raw2outputs."""
+        n, dev = rays.shape[0], rays.device
+        fine = self.network_fine
+        S_t = S_c + S_f
+        packed_f = self._packed_mlp(fine)
+        enc_f, code_bias_f = K.anerf_ray_encode(rays, p_skts, skip, cam_idx, self._codes_of(fine), packed_f)
+        z_all = c0["z_all"]
+        xd, xv = K.anerf_embed(rays, S_t, z_all, p_skts, skip, align, enc_f, self._tau(fine))
+        raw = torch.empty(n * S_t + n, 4, device=dev, dtype=torch.float32)       # tail rows: unused empty entries
+        K.anerf_mlp(xd, xv, packed_f, code_bias_f, n * S_t, S_t, raw)
+        ones = torch.ones(n, S_t, device=dev, dtype=torch.int32)
+        c1 = K.composite_resample(rays, S_t, 0, raw, ones, z_all, inv_B=1.0 / B)
+        ret = {"rgb_map": c1["rgb_map"], "disp_map": c1["disp_map"], "acc_map": c1["acc_map"], "alpha": c1["alpha"],
+               "T_i": c1["weights"], "rgb0": c0["rgb_map"], "disp0": c0["disp_map"], "acc0": c0["acc_map"],
+               "alpha0": c0["alpha"]}
+        if stages is not None:
+            stages.update({"near": near, "far": far, "z_coarse": z0, "raw0": raw0, "weights0": c0["weights"],
+                           "z_samples": c0["z_samples"], "z_all": z_all, "sorted_idxs": c0["order"],
+                           "raw": raw[: n * S_t].reshape(n, S_t, 4)})
         return ret
 
     # ---- density queries (D1 for this field; not part of config #4) ------------------------------------------
@@ -203,7 +241,7 @@ class AnerfCaster(RayCaster):
 
 
 _ANERF_REQUIRED = {"netdepth": 8, "netwidth": 448, "multires": 7, "multires_views": 4, "multires_bones": 0,
-                   "framecode_size": 128, "single_net": True, "opt_framecode": True, "use_viewdirs": True,
+                   "framecode_size": 128, "opt_framecode": True, "use_viewdirs": True,
                    "use_cutoff": True, "cutoff_viewdir": True, "cutoff_inputs": True, "cutoff_shift": True,
                    "cut_to_dist": True, "cutoff_bones": False, "normalize_cutoff": False, "opt_cutoff": False,
                    "freq_schedule": False, "cutoff_mm": 500.0, "ext_scale": 0.001, "i_embed": 0}

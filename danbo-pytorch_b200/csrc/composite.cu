@@ -103,7 +103,8 @@ composite_resample_kernel(const float* __restrict__ rays, int ray_stride, int n_
                           const float* __restrict__ u_rand /* (n_rays,S_f) or null */,
                           float* __restrict__ weights, float* __restrict__ alpha, float* __restrict__ rgb0,
                           float* __restrict__ disp0, float* __restrict__ acc0, float* __restrict__ z_samples,
-                          float* __restrict__ z_all, int* __restrict__ order_out, int* __restrict__ inds_out) {
+                          float* __restrict__ z_all, int* __restrict__ order_out, int* __restrict__ inds_out,
+                          int smooth /* 1: single_net weights (is_only, ray_utils.py:272-279); 0: the interior weights */) {
     __shared__ RaySmem smem[kWarpsPerBlock];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int n = blockIdx.x * kWarpsPerBlock + wib;
@@ -129,8 +130,12 @@ composite_resample_kernel(const float* __restrict__ rays, int ray_stride, int n_
         const int k = lane * epl + e;
         dw[e] = 0.f;
         if (e < epl && k < nb) {
-            const float a = fmaxf(sm.w[k], sm.w[k + 1]), b = fmaxf(sm.w[k + 1], sm.w[k + 2]);
-            dw[e] = __fadd_rn(__fadd_rn(__fmul_rn(0.5f, __fadd_rn(a, b)), 0.01f), 1e-5f);
+            if (smooth) {
+                const float a = fmaxf(sm.w[k], sm.w[k + 1]), b = fmaxf(sm.w[k + 1], sm.w[k + 2]);
+                dw[e] = __fadd_rn(__fadd_rn(__fmul_rn(0.5f, __fadd_rn(a, b)), 0.01f), 1e-5f);
+            } else {
+                dw[e] = __fadd_rn(sm.w[k + 1], 1e-5f);                     // weights[..., 1:-1] + 1e-5 (sample_pdf)
+            }
             lsum += (double)dw[e];
         }
     }
@@ -272,14 +277,14 @@ extern "C" int danbo_composite_resample(const float* rays, int ray_stride, int n
                                         const unsigned int* mask, const float* z, const float* noise, float inv_B,
                                         const float* u_vals, const float* u_rand, float* weights, float* alpha,
                                         float* rgb0, float* disp0, float* acc0, float* z_samples, float* z_all,
-                                        int* order, int* inds, void* stream) {
+                                        int* order, int* inds, int smooth_weights, void* stream) {
     if (n_rays <= 0) return 0;
     if (S < 3 || S > kMaxS || S + S_f > kMaxS) return -1;
     if (S_f > 0 && !u_vals && !u_rand) return -2;
     const int G = (n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock;
     composite_resample_kernel<<<G, 32 * kWarpsPerBlock, 0, (cudaStream_t)stream>>>(
         rays, ray_stride, n_rays, S, S_f, raw, mask, z, noise, inv_B, u_vals, u_rand, weights, alpha, rgb0, disp0, acc0,
-        z_samples, z_all, order, inds);
+        z_samples, z_all, order, inds, smooth_weights);
     DANBO_CHECK_LAUNCH();
     return 0;
 }

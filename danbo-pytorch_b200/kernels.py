@@ -270,8 +270,9 @@ def mlp_forward(xtiles, packed, rbias, active, row_ray, out, density_only=False,
     return out
 
 
-def composite_resample(rays, S, S_f, raw, mask, z, noise=None, inv_B=1.0, u_rand=None, want_inds=False):
-    """C1 + R1 on the coarse samples.  raw (n*S+n,4).  -> dict."""
+def composite_resample(rays, S, S_f, raw, mask, z, noise=None, inv_B=1.0, u_rand=None, want_inds=False, smooth=True):
+    """C1 + R1 on the coarse samples.  raw (n*S+n,4).  -> dict.  smooth: single_net importance weights (is_only);
+    S_f = 0: compositing only."""
     _need_cuda(rays, raw, mask, z, noise, u_rand)
     lib = _lib.load()
     n = rays.shape[0]
@@ -291,7 +292,7 @@ def composite_resample(rays, S, S_f, raw, mask, z, noise=None, inv_B=1.0, u_rand
                                                 float(inv_B), _p(u_vals), _p(u_rand), _p(out["weights"]), _p(out["alpha"]),
                                                 _p(out["rgb_map"]), _p(out["disp_map"]), _p(out["acc_map"]),
                                                 _p(out.get("z_samples")), _p(out.get("z_all")), _p(out.get("order")),
-                                                _p(out.get("inds")), _stream()), "danbo_composite_resample")
+                                                _p(out.get("inds")), int(bool(smooth)), _stream()), "danbo_composite_resample")
     _count(1)
     return out
 

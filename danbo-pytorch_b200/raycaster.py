@@ -25,17 +25,21 @@ MAX_RAYS_PER_LAUNCH = 262144          # multiple of every sane `chunk`; bounds t
 class RayCaster(nn.Module):
     """GraphCaster of the reference (raycasters.py:642-716) on B200 kernels."""
 
+    _supports_fine_network = False        # a separate fine network (single_net=False): the A-NeRF caster only
+
     def __init__(self, network, network_fine=None, single_net=True, rest_poses=None, align_bones="align",
                  skel_type=None, use_volume_near_far=False, **kwargs):
         super().__init__()
-        if not single_net or (network_fine is not None and network_fine is not network):
-            raise NotImplementedError("single_net=False (separate fine network) is not implemented; every DANBO "
-                                      "config ships single_net=True")
+        separate = (not single_net) and network_fine is not None and network_fine is not network
+        if (not single_net or (network_fine is not None and network_fine is not network)) and not (
+                separate and self._supports_fine_network):
+            raise NotImplementedError("single_net=False (separate fine network) is implemented for nerf_type='nerf' only "
+                                      "(configs/*/anerf_h.txt); every DANBO config ships single_net=True")
         if align_bones != "align":
             raise NotImplementedError(f"align_bones={align_bones!r}: only 'align' is implemented")
         self.network = network
-        self.network_fine = network
-        self.single_net = True
+        self.network_fine = network_fine if separate else network
+        self.single_net = not separate
         self.rest_poses = rest_poses
         self.skel_type = skel_type if skel_type is not None else sk.SMPLSkeleton
         self.align_bones = align_bones
@@ -87,20 +91,29 @@ class RayCaster(nn.Module):
 
     def update_embed_fns(self, global_step, args):
         self.network.update_embed_fns(global_step, args)
+        if self.network_fine is not self.network:                      # raycasters.py:596-597
+            self.network_fine.update_embed_fns(global_step, args)
 
     # custom key scheme of raycasters.py:601-637
     def state_dict(self, *args, **kwargs):
         sd = self.network.state_dict()
-        return {"network_fn_state_dict": sd, "network_fine_state_dict": sd}
+        fine = sd if self.network_fine is self.network else self.network_fine.state_dict()
+        return {"network_fn_state_dict": sd, "network_fine_state_dict": fine}
+
+    @staticmethod
+    def _load_into(net, sd, strict):
+        own = net.state_dict()
+        try:
+            net.load_state_dict(sd, strict=strict)
+        except (KeyError, RuntimeError):
+            filt = {k: v for k, v in sd.items() if k in own and tuple(own[k].shape) == tuple(v.shape)}
+            net.load_state_dict(filt, strict=False)
 
     def load_state_dict(self, ckpt, strict=True):
         sd = ckpt["network_fn_state_dict"] if "network_fn_state_dict" in ckpt else ckpt
-        own = self.network.state_dict()
-        try:
-            self.network.load_state_dict(sd, strict=strict)
-        except (KeyError, RuntimeError):
-            filt = {k: v for k, v in sd.items() if k in own and tuple(own[k].shape) == tuple(v.shape)}
-            self.network.load_state_dict(filt, strict=False)
+        self._load_into(self.network, sd, strict)
+        if self.network_fine is not self.network and "network_fine_state_dict" in ckpt:
+            self._load_into(self.network_fine, ckpt["network_fine_state_dict"], strict)
         self._packed_key = None
 
     # ------------------------------------------------------------------------------------------------ helpers
@@ -367,7 +380,9 @@ def create_raycaster(args, data_attrs, device=None):
     data_attrs["skel_profile"] = profile
     if is_anerf:
         net = _anerf.AnerfField(n_framecodes=n_framecodes)
-        caster = _anerf.AnerfCaster(net, network_fine=net, single_net=True, rest_poses=rest_pose,
+        single = bool(getattr(args, "single_net", True))
+        net_fine = net if single else _anerf.AnerfField(n_framecodes=n_framecodes)        # networks/__init__.py:64-67
+        caster = _anerf.AnerfCaster(net, network_fine=net_fine, single_net=single, rest_poses=rest_pose,
                                     align_bones=args.align_bones, skel_type=skel_type)
     else:
         net = DanboField(n_framecodes=n_framecodes, skel_profile=profile, opt_scale=bool(getattr(args, "opt_vol_scale", True)),
@@ -376,6 +391,8 @@ def create_raycaster(args, data_attrs, device=None):
                            skel_type=skel_type, use_volume_near_far=bool(getattr(args, "use_volume_near_far", False)))
     caster.to(device)
     grad_vars = [p for p in net.parameters() if p.requires_grad]
+    if caster.network_fine is not net:                                 # raycasters.py:188
+        grad_vars += [p for p in caster.network_fine.parameters() if p.requires_grad]
     wd = getattr(args, "weight_decay", None)
     if wd is None:
         optimizer = torch.optim.Adam(params=grad_vars, lr=args.lrate, betas=(0.9, 0.999))

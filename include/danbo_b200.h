@@ -107,12 +107,14 @@ int danbo_mlp_set_cta_pair(int enable);
 /* C1 + R1: raw2outputs (nerf.py:281-347) on the coarse samples, then isample_from_lineseg / sample_pdf
  * (ray_utils.py:159-203,257-291) and the sorted merge order.  raw is (n_rays*S + n_rays,4); samples whose mask is 0
  * read the ray's empty entry.  noise (n,S) already scaled, or NULL.  u_vals = linspace(0,1,S_f) (eval) or u_rand
- * (n,S_f) (train).  order (n,S+S_f) int32 = sorted_idxs. */
+ * (n,S_f) (train).  order (n,S+S_f) int32 = sorted_idxs.  smooth_weights 1: the single_net importance weights
+ * (is_only: 0.5 (max(w_k-1, w_k) + max(w_k, w_k+1)) + 0.01); 0: the interior weights themselves (separate fine network,
+ * raycasters.py:348).  S_f = 0 composites only. */
 int danbo_composite_resample(const float* rays, int ray_stride, int n_rays, int S, int S_f, const float* raw,
                              const unsigned int* mask, const float* z, const float* noise, float inv_B,
                              const float* u_vals, const float* u_rand, float* weights, float* alpha, float* rgb0,
                              float* disp0, float* acc0, float* z_samples, float* z_all, int* order, int* inds,
-                             void* stream);
+                             int smooth_weights, void* stream);
 
 /* R2 + C1: merge coarse and fine raw by `order` (core/raycasters.py:484-514,745-761) and composite the merged ray.
  * Optional training outputs: merged raw, confd and part_invalid (raycasters.py:710-716). */

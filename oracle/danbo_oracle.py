@@ -310,12 +310,14 @@ def composite(raw, z, rays_d, noise=None, B=1.0):
 # ----------------------------------------------------------------------------------------------------------
 # R1  core/utils/ray_utils.py:159-203 sample_pdf, :257-291 isample_from_lineseg (is_only=True)
 # ----------------------------------------------------------------------------------------------------------
-def importance_sample(z, weights, S_f, u=None, alpha_base=0.01):
+def importance_sample(z, weights, S_f, u=None, alpha_base=0.01, is_only=True):
     """Returns z_all (N,S_t) sorted, z_samples (N,S_f), sorted_idxs (N,S_t) int64, inds (N,S_f) int64.
-    u=None -> deterministic linspace(0,1,S_f) (eval); else the caller's uniform draws (train)."""
+    u=None -> deterministic linspace(0,1,S_f) (eval); else the caller's uniform draws (train).
+    is_only = single_net (raycasters.py:348): smoothed weights + alpha_base; False: the interior weights themselves
+    (ray_utils.py:272-281)."""
     mid = .5 * (z[..., 1:] + z[..., :-1])
     wl, wk, wu = weights[..., 0:-2], weights[..., 1:-1], weights[..., 2:]
-    dw = 0.5 * (torch.maximum(wl, wk) + torch.maximum(wk, wu)) + alpha_base
+    dw = 0.5 * (torch.maximum(wl, wk) + torch.maximum(wk, wu)) + alpha_base if is_only else wk
     dw = dw + 1e-5
     pdf = dw / torch.sum(dw, -1, keepdim=True)
     cdf = torch.cumsum(pdf, -1)
@@ -488,9 +490,11 @@ def anerf_mlp(x, view, P):
 
 
 def anerf_render_rays(ray_batch, pose_skts, pose_cyls, cams, A, P, S_c, S_f, rays_per_pose, training=False, rand=None,
-                      raw_noise_std=0., tau=20., return_stages=False, z_samples=None, lindisp=False):
+                      raw_noise_std=0., tau=20., return_stages=False, z_samples=None, lindisp=False, P_fine=None):
     """RayCaster.render_rays (raycasters.py:245-377) for nerf_type=nerf: cylinder near/far only (:419-420), the field
-    evaluated on every sample, single_net fine pass on the S_f new samples (F9)."""
+    evaluated on every sample, single_net fine pass on the S_f new samples (F9).  P_fine: parameters of a separate
+    fine network (single_net = False, configs/h36m_zju/anerf_h.txt): importance weights are the raw interior coarse
+    weights and the fine network is evaluated on all S_c + S_f merged samples (raycasters.py:350-371)."""
     N = ray_batch.shape[0]
     G = pose_skts.shape[0]
     pose = torch.clamp(torch.arange(N) // rays_per_pose, max=G - 1)
@@ -503,13 +507,18 @@ def anerf_render_rays(ray_batch, pose_skts, pose_cyls, cams, A, P, S_c, S_f, ray
     raw0 = anerf_mlp(x0, v0, P).reshape(N, S_c, 4)
     n0 = rand["noise0"] * raw_noise_std if "noise0" in rand else None
     out0 = composite(raw0, z, rays_d, n0)
-    z_all, zs, order, inds = importance_sample(z, out0["weights"], S_f, rand.get("u"))
+    z_all, zs, order, inds = importance_sample(z, out0["weights"], S_f, rand.get("u"), is_only=P_fine is None)
     if z_samples is not None:                                               # test hook, see render_rays
         zs = z_samples
         z_all, order = torch.sort(torch.cat([z, zs], -1), -1)
-    x1, v1, st1 = anerf_inputs(ray_points(rays_o, rays_d, zs), rays_d, cams, skts, A, P, training, tau)
-    raw1 = anerf_mlp(x1, v1, P).reshape(N, S_f, 4)
-    raw = merge_sorted(raw0, raw1, order)
+    if P_fine is None:
+        x1, v1, st1 = anerf_inputs(ray_points(rays_o, rays_d, zs), rays_d, cams, skts, A, P, training, tau)
+        raw1 = anerf_mlp(x1, v1, P).reshape(N, S_f, 4)
+        raw = merge_sorted(raw0, raw1, order)
+    else:
+        pts_all = merge_sorted(ray_points(rays_o, rays_d, z), ray_points(rays_o, rays_d, zs), order)
+        x1, v1, st1 = anerf_inputs(pts_all, rays_d, cams, skts, A, P_fine, training, tau)
+        raw1 = raw = anerf_mlp(x1, v1, P_fine).reshape(N, S_c + S_f, 4)
     n1 = rand["noise1"] * raw_noise_std if "noise1" in rand else None
     out = composite(raw, z_all, rays_d, n1)
     ret = {"rgb_map": out["rgb_map"], "disp_map": out["disp_map"], "acc_map": out["acc_map"],

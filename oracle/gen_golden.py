@@ -213,16 +213,23 @@ def run_render_case(name, config, extra, pose_seed, H, n_rays, weight_seed=0, fu
     print(name, "->", path, f"{os.path.getsize(path) / 1e6:.2f} MB", {k: len(v) for k, v in tap.rec.items()})
 
 
-def run_anerf_case(name, extra, pose_seed, H, n_rays, weight_seed=0):
-    """A-NeRF (BASELINE config #4): eval-mode render_rays of the reference's plain RayCaster + NeRF(W=448)."""
+def run_anerf_case(name, extra, pose_seed, H, n_rays, weight_seed=0, config="h36m_zju/anerf_base.txt"):
+    """A-NeRF (BASELINE config #4): eval-mode render_rays of the reference's plain RayCaster + NeRF(W=448).
+    With configs/h36m_zju/anerf_h.txt (single_net = False) the separate fine network gets the weights of seed + 1."""
     rc, _ = rh._imports()
-    config = "h36m_zju/anerf_base.txt"
     args = rh.parse_args(config, extra)
     rest = syn.rest_pose()
     caster, kw = rh.build(args, rest)
     caster.eval()
     sd = syn.synth_state_dict(params.anerf_param_shapes(), weight_seed)
     rh.load_weights(caster, sd)
+    if caster.network_fine is not caster.network:
+        fine = caster.network_fine
+        own = fine.state_dict()
+        for k, v in syn.synth_state_dict(params.anerf_param_shapes(), weight_seed + 1).items():
+            assert k in own and tuple(own[k].shape) == tuple(v.shape), k
+            own[k] = v.clone()
+        fine.load_state_dict(own)
     pose = syn.make_pose(pose_seed)
     b = subsample_rays(syn.render_batch(pose, H, H), n_rays, seed=pose_seed)
     net = caster.network
@@ -265,6 +272,8 @@ def run_anerf_case(name, extra, pose_seed, H, n_rays, weight_seed=0):
         tap.add("raw", raw), tap.add("weights", out["weights"]), tap.add("alpha", out["alpha"])
         return out
     tap.wrap(net, "raw2outputs", r2o)
+    if caster.network_fine is not net:
+        tap.wrap(caster.network_fine, "raw2outputs", r2o)
 
     kwargs = {k: v for k, v in kw.items() if k not in ("ray_caster", "N_samples", "use_viewdirs")}
     with torch.no_grad():
@@ -272,6 +281,7 @@ def run_anerf_case(name, extra, pose_seed, H, n_rays, weight_seed=0):
                      cyls=b["cyls"], bones=b["bones"], cams=b["cams"], N_uniques=1, **kwargs)
     tap.undo()
     fx = {"config": config, "extra": " ".join(extra), "pose_seed": pose_seed, "weight_seed": weight_seed, "H": H,
+          "single_net": int(bool(args.single_net)),
           "N_samples": args.N_samples, "N_importance": args.N_importance, "tau": float(net.pe_fn.get_tau()),
           "ray_batch": b["ray_batch"], "cams": b["cams"], "pose_bones": pose["bones"], "pose_kps": pose["kps"],
           "pose_skts": pose["skts"], "pose_cyl": pose["cyl"]}
@@ -380,6 +390,10 @@ def main():
     if only == "variants":
         variants()
         return
+    if only == "anerf_h":
+        run_anerf_case("render_anerf_h", ["--N_samples", "24", "--N_importance", "12"], pose_seed=4, H=64, n_rays=48,
+                       config="h36m_zju/anerf_h.txt")
+        return
     if only == "grid_anerf":
         run_grid_case("grid_anerf", "h36m_zju/anerf_base.txt", pose_seed=4, res=9)
         return
@@ -393,6 +407,8 @@ def main():
     run_anerf_case("render_anerf", ["--N_samples", "24", "--N_importance", "12"], pose_seed=4, H=64, n_rays=64)
     variants()
     run_grid_case("grid_anerf", "h36m_zju/anerf_base.txt", pose_seed=4, res=9)
+    run_anerf_case("render_anerf_h", ["--N_samples", "24", "--N_importance", "12"], pose_seed=4, H=64, n_rays=48,
+                   config="h36m_zju/anerf_h.txt")
 
 
 def variants():

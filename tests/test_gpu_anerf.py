@@ -207,3 +207,55 @@ def test_anerf_lindisp():
         d = (ret[k].cpu() - want[k]).abs()
         print(f"[anerf lindisp] {k}: mean {float(d.mean()):.3e} max {float(d.max()):.3e}")
         assert float(d.mean()) <= tol_mean and float(d.max()) <= tol_max, (k, float(d.mean()), float(d.max()))
+
+
+def test_anerf_separate_fine_network():
+    """single_net = False (configs/h36m_zju/anerf_h.txt): unsmoothed importance weights, a second network evaluated on
+    all S_c + S_f merged samples, against the reference's pixels."""
+    import danbo_b200 as db
+    from danbo_b200 import params, synthetic as syn, skeleton as sk
+    fx = load_fixture("render_anerf_h")
+    args = db.make_args("anerf_base", no_reload=True, single_net=False, N_samples=int(fx["N_samples"]),
+                        N_importance=int(fx["N_importance"]))
+    attrs = {"skel_type": sk.SMPLSkeleton, "near": syn.NEAR, "far": syn.FAR, "n_views": 8, "rest_pose": syn.rest_pose()}
+    _, kw_test, _, grad_vars, *_ = db.create_raycaster(args, attrs, device=DEV)
+    caster = kw_test["ray_caster"]
+    assert caster.network_fine is not caster.network and not caster.single_net
+    assert len(grad_vars) == 2 * len([p for p in caster.network.parameters() if p.requires_grad])
+    seed = int(fx["weight_seed"])
+    caster.network.load_state_dict(syn.synth_state_dict(params.anerf_param_shapes(), seed), strict=False)
+    caster.network_fine.load_state_dict(syn.synth_state_dict(params.anerf_param_shapes(), seed + 1), strict=False)
+    caster.eval()
+    sd = caster.state_dict()
+    assert not torch.equal(sd["network_fn_state_dict"]["alpha_linear.weight"], sd["network_fine_state_dict"]["alpha_linear.weight"])
+    skts, bones, cyl = pose_tensors(fx)
+    rb = fx["ray_batch"].to(DEV)
+    N = rb.shape[0]
+    e = lambda t: t.to(DEV).expand(N, *t.shape[1:])
+    st = {}
+    ret = caster(rb, N_samples=args.N_samples, kp_batch=e(fx["pose_kps"][None]), skts=e(skts), cyls=e(cyl), bones=e(bones),
+                 cams=fx["cams"].to(DEV), N_uniques=1, perturb=False, N_importance=args.N_importance, raw_noise_std=0.,
+                 nerf_type="nerf", _stages=st)
+    assert torch.equal(st["z_coarse"].cpu(), fx["st.z.0"])
+    for k, tol_mean, tol_max in (("rgb0", 3e-3, 3e-2), ("acc0", 3e-3, 3e-2), ("rgb_map", 4e-3, 5e-2), ("acc_map", 4e-3, 5e-2)):
+        d = (ret[k].cpu() - fx["out." + k]).abs()
+        print(f"[anerf_h e2e] {k}: mean {float(d.mean()):.3e} max {float(d.max()):.3e}")
+        assert float(d.mean()) <= tol_mean and float(d.max()) <= tol_max, (k, float(d.mean()), float(d.max()))
+    assert ret["alpha"].shape == fx["out.alpha"].shape and ret["T_i"].shape == fx["out.T_i"].shape
+    # R1 with the unsmoothed weights (smooth=False), given identical weights: the oracle on the weights the kernel itself
+    # composited from the reference's raw.  Without the +0.01 floor the pdf is ~1e-5 / sum in empty space, where the
+    # `denom < 1e-5 -> 1` branch of sample_pdf (ray_utils.py:196-197) sits within an ulp of flipping, so a few samples may
+    # land elsewhere in their bin: at least 90 % within 2e-6 of scale (an indexing error would leave ~0 %), all inside the
+    # ray's depth range.
+    S, S_f = args.N_samples, args.N_importance
+    raw_g = torch.cat([fx["st.raw.0"].reshape(N * S, 4), torch.zeros(N, 4)], 0).to(DEV).contiguous()
+    ones = torch.ones(N, S, dtype=torch.int32, device=DEV)
+    c = K().composite_resample(rb, S, S_f, raw_g, ones, fx["st.z.0"].to(DEV), smooth=False)
+    close(c["weights"].cpu(), fx["st.weights.0"], 2e-6, "coarse weights")
+    _, zs, _, _ = orc.importance_sample(fx["st.z.0"], c["weights"].cpu(), S_f, is_only=False)
+    dz = (c["z_samples"].cpu() - zs).abs() / float(zs.abs().max())
+    print(f"[anerf_h] z_samples vs oracle on the same weights: within 2e-6: {float((dz <= 2e-6).float().mean()):.4f} max {float(dz.max()):.3e}")
+    assert float((dz <= 2e-6).float().mean()) >= 0.9
+    za = c["z_all"].cpu()
+    assert bool((za[:, 1:] >= za[:, :-1]).all()) and float(za.min()) >= float(fx["st.z.0"].min()) - 1e-6 \
+        and float(za.max()) <= float(fx["st.z.0"].max()) + 1e-6
