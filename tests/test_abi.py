@@ -71,3 +71,52 @@ def test_anerf_flag_subset():
     assert set(shapes) <= set(sd) and {"pe_fn.cutoff_dist", "pe_fn.tau", "dirs_pe_fn.cutoff_dist", "dirs_pe_fn.tau"} <= set(sd)
     for k, shp in shapes.items():
         assert tuple(sd[k].shape) == tuple(shp), k
+
+
+def header_declarations():
+    """name -> list of parameter strings, parsed from include/danbo_b200.h."""
+    text = open(os.path.join(ROOT, "include", "danbo_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\bint\s+(danbo_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+        params = [p.strip() for p in m.group(2).replace("\n", " ").split(",")]
+        out[m.group(1)] = [] if params in ([""], ["void"]) else params
+    return out
+
+
+def test_ctypes_signatures_match_header_parameters():
+    """Every ctypes signature has the header's parameter count, and pointer / int / float kinds line up (an argument
+    added on one side only would shift every later argument of a call)."""
+    decls = header_declarations()
+    assert set(decls) == set(_lib.EXPORTS)
+    kinds = {ctypes.c_void_p: "ptr", ctypes.c_int: "int", ctypes.c_float: "float", ctypes.c_longlong: "longlong"}
+    for name, params in decls.items():
+        sig = _lib._SIGNATURES[name]
+        assert len(sig) == len(params), (name, len(sig), len(params))
+        for i, (p, t) in enumerate(zip(params, sig)):
+            if "*" in p:
+                want = "ptr"
+            elif re.match(r"(const\s+)?long long\b", p):
+                want = "longlong"
+            elif re.match(r"(const\s+)?float\b", p):
+                want = "float"
+            else:
+                want = "int"
+            assert kinds[t] == want, (name, i, p, kinds[t])
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the oracle port on the host cores) prints one JSON line with the keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["unit"] == "rays/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in line["config"]
