@@ -302,11 +302,13 @@ def run_train_case(name, config, extra, n_poses, rays_per_pose, weight_seed=0, b
     rest = syn.rest_pose()
     caster, kw = rh.build(args, rest)
     caster.train()
-    sd = syn.synth_state_dict(params.danbo_param_shapes(), weight_seed)
+    anerf = args.nerf_type == "nerf"
+    sd = syn.synth_state_dict(params.anerf_param_shapes() if anerf else params.danbo_param_shapes(), weight_seed)
     rh.load_weights(caster, sd)
     b = syn.training_batch(n_poses, rays_per_pose, seed=batch_seed)
     tap = Tap()
-    tap_reference(caster, tap, rc)
+    if not anerf:
+        tap_reference(caster, tap, rc)
     torch.manual_seed(1234)
     with RandTape() as tape:
         ret = caster(b["ray_batch"], N_samples=args.N_samples, kp_batch=b["kp_batch"], skts=b["skts"],
@@ -390,6 +392,10 @@ def main():
     if only == "variants":
         variants()
         return
+    if only == "train_anerf":
+        run_train_case("train_anerf", "h36m_zju/anerf_base.txt", ["--N_samples", "24", "--N_importance", "12"],
+                       n_poses=2, rays_per_pose=24)
+        return
     if only == "anerf_h":
         run_anerf_case("render_anerf_h", ["--N_samples", "24", "--N_importance", "12"], pose_seed=4, H=64, n_rays=48,
                        config="h36m_zju/anerf_h.txt")
@@ -409,6 +415,9 @@ def main():
     run_grid_case("grid_anerf", "h36m_zju/anerf_base.txt", pose_seed=4, res=9)
     run_anerf_case("render_anerf_h", ["--N_samples", "24", "--N_importance", "12"], pose_seed=4, H=64, n_rays=48,
                    config="h36m_zju/anerf_h.txt")
+    # train-mode A-NeRF step (loss + gradients): pins the oracle ahead of the A-NeRF backward kernels
+    run_train_case("train_anerf", "h36m_zju/anerf_base.txt", ["--N_samples", "24", "--N_importance", "12"],
+                   n_poses=2, rays_per_pose=24)
 
 
 def variants():
