@@ -5,6 +5,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PATH = os.path.join(_HERE, "libdanbo_b200.so")
 _lib = None
+ABI_VERSION = 2          # danbo_version() of the header this binding was written against
 
 c_p = ctypes.c_void_p
 c_i = ctypes.c_int
@@ -67,6 +68,10 @@ def load():
             fn = getattr(lib, name)
             fn.argtypes = argtypes
             fn.restype = ctypes.c_int
+        got = lib.danbo_version()
+        if got != ABI_VERSION:
+            raise RuntimeError(f"{_PATH} has ABI version {got}, this binding expects {ABI_VERSION}: rebuild it with "
+                               "`python __graft_entry__.py build`")
         if os.environ.get("DANBO_MLP_CTA_PAIR", "") == "0":      # debugging aid: single-CTA MLP kernel variant
             lib.danbo_mlp_set_cta_pair(0)
         _lib = lib

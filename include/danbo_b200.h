@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-/* ABI version of this header (bumped on any signature change). */
+/* ABI version of this header (bumped on any signature change): 2. */
 int danbo_version(void);
 
 /* NF1 + NF2.  get_near_far_in_cylinder (core/utils/ray_utils.py:294-346) followed, when use_box != 0, by

@@ -23,7 +23,7 @@ def test_header_and_library_agree():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/danbo_b200.h but not exported"
     assert sorted(_lib.EXPORTS) == syms, "ctypes signatures must cover exactly the header's entry points"
-    assert lib.danbo_version() == 1
+    assert lib.danbo_version() == _lib.ABI_VERSION
 
 
 def test_kernels_refuse_cpu_tensors():
@@ -120,3 +120,29 @@ def test_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["unit"] == "rays/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in line["config"]
+
+
+def test_header_compiles_as_c_and_links():
+    """include/danbo_b200.h is plain C: a gcc-compiled program that includes it, takes the address of every declared
+    entry point and calls danbo_version() links against the library and runs (no GPU needed)."""
+    import subprocess
+    import tempfile
+    build.build()
+    syms = header_symbols()
+    src = ['#include <stdio.h>', '#include "danbo_b200.h"', "int main(void) {", "    const void* fns[] = {"]
+    src += [f"        (const void*)&{s}," for s in syms]
+    src += ["    };", "    unsigned n = 0;", "    for (unsigned i = 0; i < sizeof(fns) / sizeof(fns[0]); ++i) n += fns[i] != 0;",
+            '    printf("%u %d\\n", n, danbo_version());', "    return 0;", "}"]
+    with tempfile.TemporaryDirectory() as d:
+        c, exe = os.path.join(d, "abi.c"), os.path.join(d, "abi")
+        open(c, "w").write("\n".join(src) + "\n")
+        libdir = os.path.dirname(_lib.path())
+        cmd = ["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), c, "-o", exe,
+               "-L", libdir, "-l:libdanbo_b200.so", f"-Wl,-rpath,{libdir}", "-Wl,-rpath,/usr/local/cuda/lib64",
+               "-L", "/usr/local/cuda/lib64"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-3000:]
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+        assert out.returncode == 0, out.stderr[-2000:]
+        n, ver = out.stdout.split()
+        assert int(n) == len(syms) and int(ver) == _lib.ABI_VERSION
