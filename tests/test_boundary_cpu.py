@@ -1,0 +1,98 @@
+"""The drop-in boundary of SURVEY §8(b) that does not need a GPU: what `create_raycaster` returns, the attribute surface
+the reference's trainer / run scripts touch on the caster, the checkpoint key scheme and the parameter inventory
+(SURVEY appendix A).  Kernels are never launched here."""
+import os
+import tempfile
+
+import pytest
+import torch
+
+import danbo_b200 as db
+from danbo_b200 import params, skeleton as sk, synthetic as syn
+
+
+def _attrs():
+    return {"skel_type": sk.SMPLSkeleton, "near": syn.NEAR, "far": syn.FAR, "n_views": 8, "rest_pose": syn.rest_pose()}
+
+
+def test_create_raycaster_return_contract():
+    """core/raycasters.py:17-143: (render_kwargs_train, render_kwargs_test, start, grad_vars, optimizer, loaded_ckpt) and the
+    keys of the two kwargs dicts (:115-137)."""
+    args = db.make_args("danbo_base", no_reload=True)
+    attrs = _attrs()
+    kw_train, kw_test, start, grad_vars, optimizer, loaded = db.create_raycaster(args, attrs, device="cpu")
+    keys = {"ray_caster", "perturb", "N_importance", "N_samples", "use_viewdirs", "raw_noise_std", "ray_noise_std",
+            "ext_scale", "preproc_kwargs", "lindisp", "nerf_type"}
+    assert set(kw_train) == keys and set(kw_test) == keys
+    assert set(kw_train["preproc_kwargs"]) == {"density_scale", "density_fn"}
+    assert kw_test["perturb"] is False and kw_test["raw_noise_std"] == 0. and kw_test["ray_noise_std"] == 0.
+    assert start == 0 and loaded is None and "skel_profile" in attrs                      # added in place, :31-32
+    caster = kw_test["ray_caster"]
+    assert kw_train["ray_caster"].module is caster                                       # where the reference has DataParallel
+    assert isinstance(optimizer, torch.optim.Adam) and optimizer.param_groups[0]["lr"] == args.lrate
+    n_train = sum(p.numel() for p in grad_vars)
+    assert n_train == 2455876, n_train
+
+
+def test_attribute_surface_the_trainer_touches():
+    """trainer.py:208-220,294-300,509-546,616; run_render.py:125-132; run_nerf.py:156,162."""
+    args = db.make_args("danbo_fast", no_reload=True)
+    _, kw_test, *_ = db.create_raycaster(args, _attrs(), device="cpu")
+    c = kw_test["ray_caster"]
+    net, fine = c.get_networks()
+    assert net is c.network and fine is c.network_fine and fine is net
+    assert tuple(c.transforms.shape) == (1, 24, 4, 4) and c.rest_poses.shape == (24, 3)
+    assert isinstance(net.pe_fn.get_tau(), float)
+    c.update_embed_fns(1000, args)
+    gn = net.graph_net
+    assert tuple(gn.axis_scale.shape) == (24, 3) and tuple(gn.init_scale.shape) == (24, 3)
+    assert gn.get_axis_scale() is gn.axis_scale and gn.axis_scale.requires_grad
+    confd, invalid = torch.randn(5, 7, 24), (torch.rand(5, 7, 24) > 0.5).float()
+    p = net.sigmoid(confd, invalid, mask_invalid=False, clamp=False)                     # trainer.py:521
+    assert torch.allclose(p, torch.sigmoid(confd) * 1.002 - 0.001)
+    pm = net.sigmoid(confd.reshape(-1, 24), invalid)
+    assert torch.equal(pm == 0, (invalid.reshape(-1, 24) == 1) | (pm == 0))
+    assert len(net.get_adjw()) == 3
+    c.train(); assert c.training and net.training
+    c.eval(); assert not c.training
+    assert all(p.grad is None for p in c.parameters())
+    with pytest.raises(NotImplementedError):
+        c(fwd_type="density_color")                                                      # broken in the reference itself
+
+
+def test_checkpoint_key_scheme_and_parameter_inventory():
+    """raycasters.py:601-637 (custom state_dict keys), trainer.py:610-617 (checkpoint dict), SURVEY appendix A (names and
+    shapes): a checkpoint written in the reference's format reloads through create_raycaster."""
+    args = db.make_args("danbo_base", no_reload=True)
+    _, kw_test, _, _, optimizer, _ = db.create_raycaster(args, _attrs(), device="cpu")
+    c = kw_test["ray_caster"]
+    sd = c.state_dict()
+    assert set(sd) == {"network_fn_state_dict", "network_fine_state_dict"}
+    shapes = params.danbo_param_shapes()
+    net_sd = sd["network_fn_state_dict"]
+    for k, shp in shapes.items():
+        assert k in net_sd and tuple(net_sd[k].shape) == tuple(shp), k
+    c.network.load_state_dict(syn.synthetic_params(3))
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(os.path.join(d, "exp"))
+        ckpt = {"global_step": 1234, "network_fn_state_dict": c.state_dict()["network_fn_state_dict"],
+                "network_fine_state_dict": c.state_dict()["network_fine_state_dict"],
+                "optimizer_state_dict": optimizer.state_dict()}
+        torch.save(ckpt, os.path.join(d, "exp", "001234.tar"))
+        args2 = db.make_args("danbo_base", basedir=d, expname="exp")
+        _, kw2, start, _, _, loaded = db.create_raycaster(args2, _attrs(), device="cpu")
+        assert start == 1234 and loaded is not None
+        got = kw2["ray_caster"].network.state_dict()
+        for k in shapes:
+            assert torch.equal(got[k], c.network.state_dict()[k]), k
+
+
+def test_kernels_fail_loudly_without_a_gpu():
+    """No CPU fallback: the ray caster raises on CPU tensors instead of computing anything."""
+    args = db.make_args("danbo_fast", no_reload=True)
+    _, kw_test, *_ = db.create_raycaster(args, _attrs(), device="cpu")
+    c = kw_test["ray_caster"]
+    b = syn.render_batch(syn.make_pose(0), 16, 16)
+    with pytest.raises(RuntimeError):
+        c(b["ray_batch"], N_samples=args.N_samples, kp_batch=b["kp_batch"], skts=b["skts"], cyls=b["cyls"], bones=b["bones"],
+          cams=b["cams"], N_uniques=1, perturb=False, N_importance=args.N_importance, raw_noise_std=0.)
