@@ -1,0 +1,55 @@
+"""Live comparison of the CPU oracle with the UNMODIFIED reference on inputs that are NOT among the committed fixtures
+(other poses, ray subsets and weight seeds).  Needs /root/reference, so it runs in the authoring container only and is
+skipped on the GPU box (nothing under tests/ reads the reference there)."""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import ref_harness as rh  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not rh.available(), reason="/root/reference is not present (GPU box)")
+
+
+def _render_both(config, extra, pose_seed, weight_seed, n_rays, agg_type="sigmoid", lindisp=False):
+    import danbo_oracle as orc
+    from danbo_b200 import params, synthetic as syn
+    from util import align_A
+    args = rh.parse_args(config, list(extra))
+    caster, kw = rh.build(args, syn.rest_pose())
+    caster.eval()
+    rh.load_weights(caster, syn.synth_state_dict(params.danbo_param_shapes(), weight_seed))
+    pose = syn.make_pose(pose_seed)
+    full = syn.render_batch(pose, 48, 48)
+    g = torch.Generator().manual_seed(pose_seed)
+    pick = torch.sort(torch.randperm(full["ray_batch"].shape[0], generator=g)[:n_rays]).values
+    b = {k: (v[pick].contiguous() if torch.is_tensor(v) and v.shape[0] == full["ray_batch"].shape[0] else v)
+         for k, v in full.items()}
+    kwargs = {k: v for k, v in kw.items() if k not in ("ray_caster", "N_samples", "use_viewdirs")}
+    with torch.no_grad():
+        want = caster(b["ray_batch"], N_samples=args.N_samples, kp_batch=b["kp_batch"], skts=b["skts"], cyls=b["cyls"],
+                      bones=b["bones"], cams=b["cams"], N_uniques=1, **kwargs)
+        t = lambda a: torch.as_tensor(a)[None]
+        got = orc.render_rays(b["ray_batch"], t(pose["skts"]), t(pose["bones"]), t(pose["cyl"]), b["cams"], align_A(),
+                              syn.synthetic_params(weight_seed), args.N_samples, args.N_importance, rays_per_pose=n_rays,
+                              use_volume_near_far=bool(args.use_volume_near_far), agg_type=agg_type, lindisp=lindisp)
+    return got, want, n_rays
+
+
+@pytest.mark.parametrize("config,extra,kw", [
+    ("h36m_zju/danbo_fast.txt", (), {}),
+    ("h36m_zju/danbo_base.txt", ("--N_samples", "40", "--N_importance", "24"), {}),
+    ("h36m_zju/danbo_fast.txt", ("--agg_type", "softmax"), {"agg_type": "softmax"}),
+    ("h36m_zju/danbo_fast.txt", ("--lindisp",), {"lindisp": True}),
+])
+def test_oracle_matches_live_reference(config, extra, kw):
+    got, want, N = _render_both(config, extra, pose_seed=11, weight_seed=2, n_rays=96, **kw)
+    for k in ("rgb_map", "acc_map", "disp_map", "rgb0", "acc0"):
+        err = (got[k] - want[k]).abs().reshape(N, -1).max(-1).values
+        scale = max(float(want[k].abs().max()), 1.0)
+        # a sample within rounding of a bone-box face flips its mask and moves that ray discontinuously (see
+        # test_oracle_golden.test_render_rays_end_to_end): 98 % of rays within 2e-5 of scale
+        assert float((err <= 2e-5 * scale).float().mean()) >= 0.98, (k, float(err.max()))
