@@ -146,3 +146,29 @@ def test_header_compiles_as_c_and_links():
         assert out.returncode == 0, out.stderr[-2000:]
         n, ver = out.stdout.split()
         assert int(n) == len(syms) and int(ver) == _lib.ABI_VERSION
+
+
+def test_entry_points_validate_arguments_without_touching_the_gpu():
+    """Error behaviour of the C ABI (include/danbo_b200.h: 0 = ok, < 0 = invalid argument): empty inputs are a no-op and
+    invalid arguments are refused before anything is launched, so these calls need no GPU."""
+    build.build()
+    lib = _lib.load()
+    N = None                                         # NULL pointer
+    # empty inputs -> 0
+    assert lib.danbo_nearfar(N, 8, 0, N, 3, N, 1, 1, N, N, 0, 0, 1.3, 1.3001, N, N, N, 1, N, N, N) == 0
+    assert lib.danbo_sample_mask(N, 8, 0, 32, N, N, N, N, N, N, N, 1, 1, N, N, N, N, 0, 0, 0, N) == 0
+    assert lib.danbo_field_agg(N, 8, 0, 32, N, N, N, N, 0, N, N, 1, 1, N, N, N, N, N, N, N, 0, 148, 0, N) == 0
+    assert lib.danbo_composite_resample(N, 8, 0, 32, 16, N, N, N, N, 1.0, N, N, N, N, N, N, N, N, N, N, N, 1, N) == 0
+    assert lib.danbo_graph_net_fwd(N, 0, N, N, N, N) == 0
+    assert lib.danbo_train_loss(N, N, N, N, N, N, 1.0, 1, 0, 0, 1.0, 1.0, N, N, N, N, 0, 0.0, N, N, 0.0, N, N, N, N, N, N, N, N) == 0
+    # invalid arguments -> negative, nothing launched
+    assert lib.danbo_nearfar(N, 4, 16, N, 3, N, 1, 1, N, N, 0, 0, 1.3, 1.3001, N, N, N, 1, N, N, N) < 0        # ray_stride < 8
+    assert lib.danbo_sample_mask(N, 8, 16, 32, N, N, N, N, N, N, N, 1, 1, N, N, N, N, 16, 0, 0, N) < 0       # no near/far/z_in
+    assert lib.danbo_sample_mask(N, 8, 1 << 20, 1 << 12, N, N, N, N, N, N, N, 1, 1, N, N, N, N, 16, 0, 0, N) < 0   # ids overflow int32
+    assert lib.danbo_field_agg(N, 8, 16, 32, N, N, N, N, 64, N, N, 1, 1, N, N, N, N, N, N, N, 0, 148, 0, N) < 0   # no logits / workspace
+    assert lib.danbo_composite_resample(N, 8, 16, 2, 16, N, N, N, N, 1.0, N, N, N, N, N, N, N, N, N, N, N, 1, N) < 0     # S < 3
+    assert lib.danbo_composite_resample(N, 8, 16, 128, 64, N, N, N, N, 1.0, N, N, N, N, N, N, N, N, N, N, N, 1, N) < 0  # S + S_f > 160
+    assert lib.danbo_composite_resample(N, 8, 16, 32, 16, N, N, N, N, 1.0, N, N, N, N, N, N, N, N, N, N, N, 1, N) < 0   # no u_vals / u_rand
+    assert lib.danbo_merge_composite(N, 8, 16, 128, 64, N, N, N, N, N, N, N, 1.0, N, N, N, N, N, N, N, N, N, N, N) < 0
+    assert lib.danbo_graph_net_fwd(N, 4, N, N, N, N) < 0
+    assert lib.danbo_train_loss(N, N, N, N, N, N, 1.0, 1, 16, 0, 1.0, 1.0, N, N, N, N, 0, 0.0, N, N, 0.0, N, N, N, N, N, N, N, N) < 0
