@@ -21,7 +21,7 @@ import torch
 class RayFeed:
     def __init__(self, imgs, masks, sampling_masks, kp3d, bones, skts, cyls, c2ws, focals, img_shape, near, far,
                  centers=None, bkgds=None, bkgd_idxs=None, cam_idxs=None, N_rand=3072, N_sample_images=16,
-                 mask_img=True, perturb_bg=True, patch_size=1, N_nms=0, device=None):
+                 mask_img=True, perturb_bg=True, patch_size=1, N_nms=0, device=None, rank=0, world_size=1, seed=0):
         if patch_size != 1 or N_nms != 0:
             raise NotImplementedError("patch_size > 1 / N_nms > 0 are not implemented (no shipped config sets them)")
         dev = torch.device(device) if device is not None else torch.as_tensor(imgs).device
@@ -43,6 +43,13 @@ class RayFeed:
         self.near, self.far = float(near), float(far)
         self.N_sample_images = int(N_sample_images)
         self.rays_per_image = int(N_rand) // int(N_sample_images)
+        # data parallel: every rank draws the SAME images (a host generator seeded alike everywhere) and
+        # keeps a contiguous run of the sorted batch, so the ranks' batches concatenated are the global image-major batch
+        self.rank, self.world_size = int(rank), int(world_size)
+        if self.N_sample_images % self.world_size:
+            raise ValueError(f"N_sample_images={N_sample_images} is not a multiple of world_size={world_size}")
+        self._image_gen = torch.Generator().manual_seed(int(seed))
+        self._perm, self._cursor = None, 0
         self.mask_img, self.perturb_bg = bool(mask_img), bool(perturb_bg)
         # dataset.py:163-183: pixel directions before the division by the focal length (x right, y up, looking down -z)
         j, i = torch.meshgrid(torch.arange(self.H, dtype=torch.float32, device=dev),
@@ -53,18 +60,68 @@ class RayFeed:
         else:
             off_y = off_x = 0.
         self._dirs = torch.stack([i - off_x, -(j - off_y), -torch.ones_like(i)], -1)
+        self.rebuild_sampling_index()
 
     # ---- dataset.py:307-356 -------------------------------------------------------------------------------------
+    def rebuild_sampling_index(self):
+        """Compressed list of every image's candidate pixels (CSR: `_valid_flat[_valid_off[i] : _valid_off[i+1]]`,
+        increasing): the sampling mask, or the whole image when the mask holds fewer pixels than one draw needs
+        (dataset.py:317-319).  Call again after editing `sampling_masks`."""
+        m = self.sampling_masks > 0
+        m = m | (m.sum(-1, keepdim=True) < self.rays_per_image)
+        self._n_valid = m.sum(-1)                                            # (n_images,)
+        off = torch.zeros(self.n_images + 1, dtype=torch.int64, device=self.device)
+        off[1:] = torch.cumsum(self._n_valid, 0)
+        self._valid_off = off
+        self._valid_flat = torch.nonzero(m)[:, 1].to(torch.int32)           # row-major: per image, increasing
+        # rejection-free fast path needs collisions among the candidates to be rare (see sample_pixels)
+        self._sparse_draw = bool((self._n_valid >= 64 * self.rays_per_image).all()) if self.n_images else False
+
     def sample_pixels(self, image_idxs, generator=None):
-        """(B,) image indices -> (B, rays_per_image) sorted flat pixel indices, uniform without replacement over each
-        image's sampling mask (over the whole image when the mask holds fewer pixels than requested)."""
+        """(B,) image indices -> (B, rays_per_image) increasing flat pixel indices, uniform without replacement over each
+        image's candidate pixels.  Two exact samplers, chosen once per data set (no per-step host decision):
+
+        * masks of >= 64 R pixels (real data: ~1e5 foreground pixels, R = 192): draw 2R candidates WITH replacement and
+          keep the first R distinct ones in draw order - sequentially skipping repeats is a uniform draw without
+          replacement; fewer than R distinct among 2R has probability < (2R choose R)·(R/n)^R, below 1e-100 here.
+          Cost O(B·R), independent of the image size;
+        * otherwise random keys over the image's pixels and the R largest (cost O(B·H·W))."""
+        R = self.rays_per_image
+        B = image_idxs.shape[0]
+        if self._sparse_draw:
+            n = self._n_valid[image_idxs][:, None]
+            u = torch.rand(B, 2 * R, device=self.device, generator=generator, dtype=torch.float64)
+            cand = torch.minimum((u * n).long(), n - 1)
+            val, perm = torch.sort(cand, dim=-1, stable=True)
+            rep_sorted = torch.zeros_like(cand)
+            rep_sorted[:, 1:] = (val[:, 1:] == val[:, :-1]).long()           # stable sort: the later draw is the repeat
+            rep = torch.zeros_like(cand).scatter_(1, perm, rep_sorted)
+            order = torch.arange(2 * R, device=self.device)[None] + rep * (2 * R)
+            first = torch.topk(order, R, dim=-1, largest=False).indices      # the first R distinct draws
+            k = torch.sort(torch.gather(cand, 1, first), -1).values
+            return self._valid_flat[self._valid_off[image_idxs][:, None] + k].long()
         m = self.sampling_masks[image_idxs] > 0
-        few = m.sum(-1, keepdim=True) < self.rays_per_image
-        m = m | few
+        m = m | (m.sum(-1, keepdim=True) < R)
         keys = torch.rand(m.shape, device=self.device, generator=generator)
         keys = torch.where(m, keys, torch.full_like(keys, -1.))
-        pix = torch.topk(keys, self.rays_per_image, dim=-1).indices          # random keys: a uniform draw without replacement
+        pix = torch.topk(keys, R, dim=-1).indices                            # random keys: a uniform draw without replacement
         return torch.sort(pix, -1).values
+
+    # ---- dataset.py:915-976 -------------------------------------------------------------------------------------
+    def draw_images(self):
+        """The next N_sample_images image indices as `RayImageSampler` yields them: consecutive entries of a random
+        permutation of the data set (every image once per pass; a batch that straddles two passes continues into a
+        fresh permutation), sorted.  Host-side and seeded alike on every rank; this rank's share is returned."""
+        batch = []
+        while len(batch) < self.N_sample_images:
+            if self._perm is None or self._cursor >= self.n_images:
+                self._perm, self._cursor = torch.randperm(self.n_images, generator=self._image_gen), 0
+            take = min(self.N_sample_images - len(batch), self.n_images - self._cursor)
+            batch += self._perm[self._cursor:self._cursor + take].tolist()
+            self._cursor += take
+        full = torch.sort(torch.tensor(batch, dtype=torch.int64)).values
+        per = self.N_sample_images // self.world_size
+        return full[self.rank * per:(self.rank + 1) * per]
 
     # ---- dataset.py:383-401 -------------------------------------------------------------------------------------
     def get_rays(self, image_idxs, pix):
@@ -99,10 +156,10 @@ class RayFeed:
     def next_batch(self, generator=None, image_idxs=None, pixel_idxs=None):
         """One training batch.  `image_idxs` / `pixel_idxs` ((B,) and (B, R), both increasing) replace the random draws
         (that is how the parity test replays the reference's draws); the indices used are kept in `self.last_idxs`."""
-        B, R = self.N_sample_images, self.rays_per_image
+        R = self.rays_per_image
         if image_idxs is None:
-            image_idxs = torch.randperm(self.n_images, device=self.device, generator=generator)[:B]
-        image_idxs = torch.sort(torch.as_tensor(image_idxs, device=self.device).long()).values
+            image_idxs = self.draw_images()
+        image_idxs = torch.sort(torch.as_tensor(image_idxs).long()).values.to(self.device, non_blocking=True)
         B = image_idxs.shape[0]
         if pixel_idxs is None:
             pix = self.sample_pixels(image_idxs, generator)
@@ -166,4 +223,4 @@ def synthetic_feed(n_images=32, H=128, W=128, device="cpu", seed=0, centers=Fals
     import numpy as np
     from . import synthetic as syn
     return RayFeed.from_arrays(synthetic_arrays(n_images, H, W, seed, centers), syn.NEAR, syn.FAR,
-                               cam_idxs=np.arange(n_images) % 8, device=device, **kw)
+                               cam_idxs=np.arange(n_images) % 8, device=device, seed=seed, **kw)

@@ -65,34 +65,88 @@ def test_cam_idxs_default_is_the_queried_index():
     np.testing.assert_array_equal(b["cams"][:, 0].numpy(), fx["cam_idxs"])
 
 
-def test_sample_pixels_properties():
+@pytest.mark.parametrize("sparse", [False, True])
+def test_sample_pixels_properties(sparse):
     """dataset.py:307-356: N_rand pixels per image, without replacement, inside the sampling mask, increasing; the whole
-    image when the mask holds fewer pixels than requested; every mask pixel equally likely."""
-    feed = fd.synthetic_feed(n_images=8, H=16, W=16, N_rand=8 * 20, N_sample_images=8)
+    image when the mask holds fewer pixels than requested; every mask pixel equally likely.  Both samplers: random keys
+    over the image (small masks) and first-R-distinct-of-2R candidates (masks of >= 64 R pixels)."""
+    if sparse:
+        feed = fd.synthetic_feed(n_images=4, H=48, W=48, N_rand=4 * 8, N_sample_images=4)      # disc: ~886 px >= 64 * 8
+        B, R, reps = 4, 8, 3000
+    else:
+        feed = fd.synthetic_feed(n_images=8, H=16, W=16, N_rand=8 * 20, N_sample_images=8)
+        B, R, reps = 8, 20, 400
+    assert feed._sparse_draw == sparse
+    HW = feed.H * feed.W
     g = torch.Generator().manual_seed(0)
-    idx = torch.arange(8)
+    idx = torch.arange(B)
     mask = feed.sampling_masks > 0
-    counts = torch.zeros(16 * 16)
-    reps = 400
+    counts = torch.zeros(HW)
     for _ in range(reps):
         pix = feed.sample_pixels(idx, g)
-        assert pix.shape == (8, 20)
+        assert pix.shape == (B, R) and pix.dtype == torch.int64
         assert (pix[:, 1:] > pix[:, :-1]).all()                       # increasing => distinct
         assert torch.gather(mask, 1, pix).all()
-        counts += torch.bincount(pix.reshape(-1), minlength=256)
+        counts += torch.bincount(pix.reshape(-1), minlength=HW)
     m = mask[0]
     assert counts[~m].sum() == 0
-    expect = reps * 8 * 20 / int(m.sum())
+    expect = reps * B * R / int(m.sum())
     assert (counts[m] - expect).abs().max() < 6 * expect ** 0.5       # ~binomial spread
+    assert abs(float(counts[m].mean()) - expect) < 1e-3
     # mask smaller than the request -> whole image (dataset.py:318-319)
     feed.sampling_masks[3] = 0
     feed.sampling_masks[3, :5] = 1
+    feed.rebuild_sampling_index()
+    assert int(feed._n_valid[3]) == HW and not (sparse and HW < 64 * R and feed._sparse_draw)
     seen_outside = False
     for _ in range(20):
         pix = feed.sample_pixels(torch.tensor([3]), g)
         assert (pix[:, 1:] > pix[:, :-1]).all()
         seen_outside |= bool((pix >= 5).any())
     assert seen_outside
+
+
+def test_sparse_draw_repeats_are_skipped_in_draw_order():
+    """The 2R-candidate sampler on a mask barely above its threshold, where repeated candidates are common: the result
+    must still be R distinct candidate pixels, and pairs of pixels equally likely (no bias from the dedupe)."""
+    feed = fd.synthetic_feed(n_images=1, H=24, W=24, N_rand=3, N_sample_images=1)
+    feed.sampling_masks[:] = 0
+    feed.sampling_masks[0, 100:292] = 1                               # 192 = 64 * 3 candidates
+    feed.rebuild_sampling_index()
+    assert feed._sparse_draw and int(feed._n_valid[0]) == 192
+    g = torch.Generator().manual_seed(3)
+    counts = torch.zeros(576)
+    reps = 20000
+    for _ in range(reps // 50):
+        pix = feed.sample_pixels(torch.zeros(50, dtype=torch.long), g)        # 50 independent draws of the same image
+        assert (pix[:, 1:] > pix[:, :-1]).all() and int(pix.min()) >= 100 and int(pix.max()) < 292
+        counts += torch.bincount(pix.reshape(-1), minlength=576)
+    expect = reps * 3 / 192
+    assert (counts[100:292] - expect).abs().max() < 6 * expect ** 0.5
+
+
+def test_image_sampler_passes_and_rank_shares():
+    """RayImageSampler (dataset.py:941-976): consecutive entries of a permutation, so every image appears once per pass;
+    batches sorted.  With world_size 2 the ranks' shares concatenated are the single-process batch."""
+    mk = lambda **kw: fd.synthetic_feed(n_images=12, H=8, W=8, N_rand=4 * 2, N_sample_images=4, seed=5, **kw)
+    one, r0, r1 = mk(), mk(rank=0, world_size=2), mk(rank=1, world_size=2)
+    seen = []
+    for step in range(9):                                              # 3 passes over 12 images
+        full = one.draw_images()
+        assert full.shape == (4,) and (full[1:] >= full[:-1]).all()
+        assert torch.equal(torch.cat([r0.draw_images(), r1.draw_images()]), full)
+        seen += full.tolist()
+        if step % 3 == 2:
+            assert sorted(seen) == list(range(12))                     # one pass = every image exactly once
+            seen = []
+    b0 = r0.next_batch(torch.Generator().manual_seed(0))
+    assert b0["N_uniques"] == 2 and b0["ray_batch"].shape == (4, 11)
+    with pytest.raises(ValueError):
+        mk(world_size=3)
+    # a batch that straddles two passes continues into a fresh permutation (dataset.py:964-970)
+    odd = fd.synthetic_feed(n_images=5, H=8, W=8, N_rand=4 * 2, N_sample_images=4, seed=1)
+    flat = [i for _ in range(5) for i in odd.draw_images().tolist()]
+    assert len(flat) == 20 and sorted(flat) == sorted(list(range(5)) * 4)          # 4 whole passes in 5 batches
 
 
 def test_next_batch_draws_distinct_sorted_images_and_perturbs_background_only():
@@ -102,7 +156,7 @@ def test_next_batch_draws_distinct_sorted_images_and_perturbs_background_only():
     for _ in range(30):
         b = feed.next_batch(g)
         img, pix = feed.last_idxs
-        assert img.shape == (6,) and (img[1:] > img[:-1]).all()       # RayImageSampler: distinct, np.sort (dataset.py:959-975)
+        assert img.shape == (6,) and (img[1:] > img[:-1]).all()       # 12 images, 6 per batch: distinct; np.sort (dataset.py:959-975)
         seen.update(img.tolist())
         fg = b["fgs"]
         plain = torch.gather(feed.bkgds[feed.bkgd_idxs[img]], 1, pix[..., None].expand(-1, -1, 3)).float().reshape(-1, 3) / 255.
