@@ -295,7 +295,7 @@ def run_anerf_case(name, extra, pose_seed, H, n_rays, weight_seed=0, config="h36
     print(name, "->", path, f"{os.path.getsize(path) / 1e6:.2f} MB", {k: len(v) for k, v in tap.rec.items()})
 
 
-def run_train_case(name, config, extra, n_poses, rays_per_pose, weight_seed=0, batch_seed=0):
+def run_train_case(name, config, extra, n_poses, rays_per_pose, weight_seed=0, batch_seed=0, pose_grads=False):
     rc, _ = rh._imports()
     import core.trainer as trainer_mod
     args = rh.parse_args(config, extra)
@@ -306,6 +306,11 @@ def run_train_case(name, config, extra, n_poses, rays_per_pose, weight_seed=0, b
     sd = syn.synth_state_dict(params.anerf_param_shapes() if anerf else params.danbo_param_shapes(), weight_seed)
     rh.load_weights(caster, sd)
     b = syn.training_batch(n_poses, rays_per_pose, seed=batch_seed)
+    if pose_grads:
+        # the pose tensors as leaves: what the pose layer's outputs are to the ray caster under --opt_pose
+        # (core/trainer.py:314-341); their gradients pin the oracle for the backward-to-poses kernels
+        for k in ("skts", "bones", "kp_batch"):
+            b[k] = b[k].clone().requires_grad_(True)
     tap = Tap()
     if not anerf:
         tap_reference(caster, tap, rc)
@@ -345,6 +350,12 @@ def run_train_case(name, config, extra, n_poses, rays_per_pose, weight_seed=0, b
             continue
         for i, v in enumerate(lst):
             fx[f"st.{k}.{i}"] = v
+    if pose_grads:
+        for k in ("skts", "bones", "kp_batch"):
+            g = b[k].grad
+            fx["pose_grad." + k] = torch.zeros(n_poses, *b[k].shape[1:]) if g is None else \
+                g.reshape(n_poses, rays_per_pose, *g.shape[1:]).sum(1)
+            fx["pose_grad_none." + k] = int(g is None)
     rng = np.random.RandomState(7)
     for n, p in caster.network.named_parameters():
         g = p.grad
@@ -396,6 +407,10 @@ def main():
         run_train_case("train_anerf", "h36m_zju/anerf_base.txt", ["--N_samples", "24", "--N_importance", "12"],
                        n_poses=2, rays_per_pose=24)
         return
+    if only == "train_popt":
+        run_train_case("train_fast_popt", "h36m_zju/danbo_fast.txt", [], n_poses=4, rays_per_pose=48, batch_seed=1,
+                       pose_grads=True)
+        return
     if only == "anerf_h":
         run_anerf_case("render_anerf_h", ["--N_samples", "24", "--N_importance", "12"], pose_seed=4, H=64, n_rays=48,
                        config="h36m_zju/anerf_h.txt")
@@ -418,6 +433,9 @@ def main():
     # train-mode A-NeRF step (loss + gradients): pins the oracle ahead of the A-NeRF backward kernels
     run_train_case("train_anerf", "h36m_zju/anerf_base.txt", ["--N_samples", "24", "--N_importance", "12"],
                    n_poses=2, rays_per_pose=24)
+    # gradients with respect to the pose tensors (skts, bones): pins the oracle ahead of the backward-to-poses kernels
+    run_train_case("train_fast_popt", "h36m_zju/danbo_fast.txt", [], n_poses=4, rays_per_pose=48, batch_seed=1,
+                   pose_grads=True)
 
 
 def variants():
