@@ -5,7 +5,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PATH = os.path.join(_HERE, "libdanbo_b200.so")
 _lib = None
-ABI_VERSION = 2          # danbo_version() of the header this binding was written against
+ABI_VERSION = 3          # danbo_version() of the header this binding was written against
 
 c_p = ctypes.c_void_p
 c_i = ctypes.c_int

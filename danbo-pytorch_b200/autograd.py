@@ -4,8 +4,10 @@ Forward = the same kernel sequence as inference (train mode keeps the bf16 MLP a
 pair lists); backward = hand-written kernels for compositing, MLP, aggregation net, feature gather and ray bias
 (csrc/backward_*.cu, composite.cu).  Gradient sources are rgb_map, acc_map, rgb0, acc0 and confd, exactly the tensors the
 trainer's losses read (core/trainer.py:396-422,507-536); disp / alpha / T_i / part_invalid are non-differentiable, as in
-the reference where they are used only under comparisons.  The per-pose graph net stays in PyTorch: its output `vol` is
-an input of this Function and receives d vol.
+the reference where they are used only under comparisons.  The per-pose graph net is its own node (`_GraphNet`, or the
+PyTorch ops when the pose itself needs a gradient): its output `vol` is an input of this Function and receives d vol.
+The per-pose world-to-bone matrices are an input too: when they require a gradient (the pose layer under --opt_pose,
+core/trainer.py:314-341) `danbo_field_agg_bwd` also accumulates d loss / d skts.
 """
 import torch
 
@@ -26,10 +28,10 @@ DIFF_KEYS = ("rgb_map", "acc_map", "rgb0", "acc0", "confd")
 class _RenderBlock(torch.autograd.Function):
 
     @staticmethod
-    def forward(ctx, caster, cfg, vol, *params):
+    def forward(ctx, caster, cfg, vol, pose_skts, *params):
         keep = {}
         with torch.no_grad():
-            ret = caster._render_block(cfg["rays"], 0, cfg["skip"], cfg["pose_skts"], cfg["pose_cyls"], vol, cfg["cam_idx"],
+            ret = caster._render_block(cfg["rays"], 0, cfg["skip"], pose_skts, cfg["pose_cyls"], vol, cfg["cam_idx"],
                                        cfg["codes"], cfg["consts"], cfg["packed"], cfg["S_c"], cfg["S_f"], cfg["B"],
                                        cfg["raw_noise_std"], cfg["perturb"], True, cfg["nanmean_chunk"], cfg["rand"],
                                        cfg["stages"], keep=keep, lindisp=cfg["lindisp"])
@@ -78,6 +80,7 @@ class _RenderBlock(torch.autograd.Function):
         d_vol = zeros(*ctx.vol_shape)
         d_vol_blk = d_vol[k["p0"]:]
         agg_grads = [G[nm] for nm in AGG_NAMES] + [d_vol_blk, G["graph_net.axis_scale"]]
+        d_skts = zeros(*k["p_skts"].shape) if ctx.needs_input_grad[3] else None      # p0 == 0: a block holds every pose
         ws = None
         if K.BACKWARD_IMPL == "tc":
             ws = K.BwdWorkspace(max(k["act0"].capacity, k["act1"].capacity), dev)
@@ -89,23 +92,24 @@ class _RenderBlock(torch.autograd.Function):
                 first = False
             else:
                 dX = K.mlp_backward(P, G, d_raw, act, fo, sv, d_ray_bias)
-            K.field_agg_bwd(rays, S, z, mask, act, k["p_skts"], k["p_vol"], k["skip"], k["consts"], fo, dX, gl, agg_grads)
+            K.field_agg_bwd(rays, S, z, mask, act, k["p_skts"], k["p_vol"], k["skip"], k["consts"], fo, dX, gl, agg_grads,
+                            d_skts=d_skts)
         K.ray_bias_bwd(rays, k["cam_idx"], k["codes"], P["views_linears.0.weight"], d_ray_bias,
                        G["views_linears.0.weight"], G["views_linears.0.bias"], G["framecodes.codes.weight"])
         ctx.keep = None
         if in_place:
-            return (None, None, d_vol) + (None,) * len(PARAM_NAMES)
-        return (None, None, d_vol) + tuple(G[name] for name in PARAM_NAMES)
+            return (None, None, d_vol, d_skts) + (None,) * len(PARAM_NAMES)
+        return (None, None, d_vol, d_skts) + tuple(G[name] for name in PARAM_NAMES)
 
 
 def render_block_with_grad(caster, rays, skip, pose_skts, pose_cyls, vol, cam_idx, codes, consts, packed, S_c, S_f, B,
                            raw_noise_std, perturb, nanmean_chunk, rand, stages, lindisp=False):
     named = dict(caster.network.named_parameters())
     params = [named[n] for n in PARAM_NAMES]
-    cfg = dict(rays=rays, skip=skip, pose_skts=pose_skts, pose_cyls=pose_cyls, cam_idx=cam_idx, codes=codes, consts=consts,
+    cfg = dict(rays=rays, skip=skip, pose_cyls=pose_cyls, cam_idx=cam_idx, codes=codes, consts=consts,
                packed=packed, S_c=S_c, S_f=S_f, B=B, raw_noise_std=raw_noise_std, perturb=perturb,
                nanmean_chunk=nanmean_chunk, rand=rand, stages=stages, lindisp=lindisp)
-    outs = _RenderBlock.apply(caster, cfg, vol, *params)
+    outs = _RenderBlock.apply(caster, cfg, vol, pose_skts, *params)
     return dict(zip(OUT_KEYS, outs))
 
 

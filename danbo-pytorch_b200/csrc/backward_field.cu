@@ -98,6 +98,7 @@ struct AggGrads {             // fp32 accumulators (atomicAdd), shapes of the pa
     float* w0; float* adjw; float* b0; float* w1; float* b1; float* w2; float* b2;
     float* vol;               // (G,24,240)
     float* axis_scale;        // (24,3)
+    float* skts;              // (G,24,4,4) or nullptr: d loss / d world-to-bone matrices (pose optimisation, pose_opt.py:264-339)
 };
 
 constexpr int kTileLd = 33;
@@ -278,6 +279,7 @@ pair_logits_bwd_kernel(const float* __restrict__ rays, int ray_stride, int S, co
             const float win = expf(-2.f * (a2 * a2 * a2 + b2 * b2 * b2 + c2 * c2 * c2));
             float* dvol = G.vol + ((size_t)pose * DANBO_J + k) * DANBO_VOL;
             const float* volk = vol + k * DANBO_VOL;
+            float dt[3];                                             // d loss / d t, t = A_k (R_k p + t_k) + a_k = x |s|
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
                 const float iy = ((x[a] + 1.f) * (float)DANBO_RES - 1.f) * 0.5f;
@@ -301,6 +303,38 @@ pair_logits_bwd_kernel(const float* __restrict__ rays, int ray_stride, int S, co
                 // x = t / |s|  ->  d x / d s = -x / |s| * sign(s) = -x / s
                 const float ds = warp_sum(live ? -dxa * x[a] / sc : 0.f);
                 if (lane == 0) atomicAdd(G.axis_scale + k * 3 + a, ds);
+                dt[a] = live ? dxa / fabsf(sc) : 0.f;
+            }
+            if (G.skts != nullptr) {
+                // ---- d x -> d skts[pose][k] (encoders.py:288-303, :442-444): t = A l + a, l = R p + t_k, so
+                // d l = A^T d t and d [R | t_k] = d l (x) [p, 1].  A warp's pairs usually share their pose (rays are
+                // image-major): one warp reduction and 12 atomics; mixed warps fall back to per-lane atomics.
+                const float* A = fc.align + k * 16;
+                float dl[3];
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                    dl[i] = fmaf(__ldg(A + 8 + i), dt[2], fmaf(__ldg(A + 4 + i), dt[1], __ldg(A + i) * dt[0]));
+                const uint32_t lm = __ballot_sync(0xffffffffu, live);
+                if (lm != 0u) {
+                    const int pose_ref = __shfl_sync(0xffffffffu, pose, __ffs(lm) - 1);
+                    const float pw4[4] = {px, py, pz, 1.f};
+                    if (__all_sync(0xffffffffu, !live || pose == pose_ref)) {
+                        float* dst = G.skts + ((size_t)pose_ref * DANBO_J + k) * 16;
+#pragma unroll
+                        for (int i = 0; i < 3; ++i)
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                const float v = warp_sum(dl[i] * pw4[c]);          // dl = 0 on dead lanes
+                                if (lane == 0) atomicAdd(dst + i * 4 + c, v);
+                            }
+                    } else if (live) {
+                        float* dst = G.skts + ((size_t)pose * DANBO_J + k) * 16;
+#pragma unroll
+                        for (int i = 0; i < 3; ++i)
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) atomicAdd(dst + i * 4 + c, dl[i] * pw4[c]);
+                    }
+                }
             }
         }
     }
@@ -317,8 +351,9 @@ static FieldConsts make_consts_b(const float* const* p) {
     return fc;
 }
 
-// grads[9] = { d_w0 (24,15,32), d_adj_w (24,24), d_b0 (32), d_w1 (24,32,32), d_b1 (24,32), d_w2 (24,32), d_b2 (24),
-//              d_vol (n_poses,24,240), d_axis_scale (24,3) }: fp32 accumulators, added to (zero them first).
+// grads[10] = { d_w0 (24,15,32), d_adj_w (24,24), d_b0 (32), d_w1 (24,32,32), d_b1 (24,32), d_w2 (24,32), d_b2 (24),
+//               d_vol (n_poses,24,240), d_axis_scale (24,3), d_skts (n_poses,24,4,4) or NULL }: fp32 accumulators, added
+//               to (zero them first).  d_skts = NULL (poses are constants) skips that gradient.
 // work / pair_capacity: the SAME workspace the forward danbo_field_agg call filled (pair lists are reused).
 extern "C" int danbo_field_agg_bwd(const float* rays, int ray_stride, int n_rays, int S, const float* z,
                                    const unsigned int* mask, const int* active_ids, const int* active_count,
@@ -337,7 +372,7 @@ extern "C" int danbo_field_agg_bwd(const float* rays, int ray_stride, int n_rays
                                                     capacity, pose_skts, pose_vol, rays_per_pose, n_poses, fc, logits,
                                                     hbar, dX, g_logit_ext, d_hbar, d_logit, agg_mode);
     DANBO_CHECK_LAUNCH();
-    AggGrads G{grads[0], grads[1], grads[2], grads[3], grads[4], grads[5], grads[6], grads[7], grads[8]};
+    AggGrads G{grads[0], grads[1], grads[2], grads[3], grads[4], grads[5], grads[6], grads[7], grads[8], grads[9]};
     PairWork pw{const_cast<int*>(work)};
     int pblocks = (pair_capacity / 32 + 3) / 4;
     if (pblocks > num_sms * 4) pblocks = num_sms * 4;

@@ -503,14 +503,22 @@ def ray_bias_bwd(rays, cam_idx, codes_with_mean, w_view, d_ray_bias, d_w_view, d
     _count(1)
 
 
-def field_agg_bwd(rays, S, z, mask, active, pose_skts, pose_vol, rays_per_pose, consts, fo, dX, g_logit_ext, grads):
-    """grads: list of the 9 fp32 accumulators in the order of danbo_field_agg_bwd (see danbo_b200.h)."""
+def field_agg_bwd(rays, S, z, mask, active, pose_skts, pose_vol, rays_per_pose, consts, fo, dX, g_logit_ext, grads,
+                  d_skts=None):
+    """grads: list of the 9 fp32 parameter / volume accumulators in the order of danbo_field_agg_bwd (see danbo_b200.h);
+    d_skts: (n_poses,24,4,4) fp32 accumulator of the gradient w.r.t. the world-to-bone matrices, or None."""
     lib = _lib.load()
     dev = rays.device
     n = rays.shape[0]
     d_hbar = torch.empty(active.capacity, 16, device=dev, dtype=torch.float32)
     d_logit = torch.empty(n * S, J, device=dev, dtype=torch.float32)
-    ga = (ctypes.c_void_p * 9)(*[g.data_ptr() for g in grads])
+    if len(grads) != 9:
+        raise ValueError("field_agg_bwd takes 9 accumulators (+ d_skts)")
+    if d_skts is not None:
+        _need_cuda(d_skts)
+        if d_skts.dtype != torch.float32 or not d_skts.is_contiguous() or tuple(d_skts.shape) != (pose_skts.shape[0], J, 4, 4):
+            raise ValueError("d_skts must be a contiguous fp32 (n_poses,24,4,4) tensor")
+    ga = (ctypes.c_void_p * 10)(*([g.data_ptr() for g in grads] + [None if d_skts is None else d_skts.data_ptr()]))
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
     _lib.check(lib.danbo_field_agg_bwd(_p(rays), rays.stride(0), n, S, _p(z), _p(mask), _p(active.ids), _p(active.count),
                                        active.capacity, _p(pose_skts), _p(pose_vol), int(rays_per_pose),

@@ -227,12 +227,15 @@ class DanboField(nn.Module):
 
     def bone_volumes(self, pose_bones):
         """pose_bones (G,24,3) axis-angle -> (G,24,240) feature lines (encoders.py:460-473,859-877; danbo.py:190-194)."""
-        if self.fused_graph_net and pose_bones.is_cuda:
+        # a pose that itself needs a gradient (pose layer under --opt_pose) takes the PyTorch ops below: the graph-net
+        # kernels' backward stops at the parameters
+        pose_grad = torch.is_grad_enabled() and pose_bones.requires_grad
+        six = pose_bones.shape[-1] == 6          # a rot6d pose layer hands its parameters over as they are (encoders.py:873-877)
+        if self.fused_graph_net and pose_bones.is_cuda and not pose_grad and not six:
             from .autograd import graph_net_volumes
             return graph_net_volumes(self, pose_bones)
-        R = axis_angle_to_matrix(pose_bones)
-        w = pe_embed(R[..., :3, :2].flatten(start_dim=-2), self.multires_graph)
-        return self.graph_net(w)
+        rot6d = pose_bones if six else axis_angle_to_matrix(pose_bones)[..., :3, :2].flatten(start_dim=-2)
+        return self.graph_net(pe_embed(rot6d, self.multires_graph))
 
     def agg_tensors(self):
         l = self.prob_linears.layers

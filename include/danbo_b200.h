@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-/* ABI version of this header (bumped on any signature change): 2. */
+/* ABI version of this header (bumped on any change of a signature or of a pointer-array contract): 3. */
 int danbo_version(void);
 
 /* NF1 + NF2.  get_near_far_in_cylinder (core/utils/ray_utils.py:294-346) followed, when use_box != 0, by
@@ -183,9 +183,11 @@ int danbo_ray_bias_bwd(const float* rays, int ray_stride, int n_rays, const int*
                        void* stream);
 
 /* G1/G2 + A1-A3 + PE backward (danbo.py:261-302, gnn_backbone.py:787-828, misc.py:331-351): d X (rows,208) and the
- * extra logit gradient -> grads[9] = { w0, adj_w, b0, w1, b1, w2, b2 of prob_linears, d vol (n_poses,24,240),
- * d axis_scale (24,3) } (fp32, accumulated).  work = the workspace the forward danbo_field_agg filled; agg_mode as
- * in that call. */
+ * extra logit gradient -> grads[10] = { w0, adj_w, b0, w1, b1, w2, b2 of prob_linears, d vol (n_poses,24,240),
+ * d axis_scale (24,3), d skts (n_poses,24,4,4) or NULL } (fp32, accumulated).  d skts is the gradient with respect to
+ * the world-to-bone matrices (what the pose layer, core/pose_opt.py:264-339, receives under --opt_pose; rows 0-2 only,
+ * the homogeneous row gets none); NULL when the poses are constants.  work = the workspace the forward danbo_field_agg
+ * filled; agg_mode as in that call. */
 int danbo_field_agg_bwd(const float* rays, int ray_stride, int n_rays, int S, const float* z, const unsigned int* mask,
                         const int* active_ids, const int* active_count, int capacity, const float* pose_skts,
                         const float* pose_vol, int rays_per_pose, int n_poses, const float* const* consts,
