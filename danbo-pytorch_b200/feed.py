@@ -177,7 +177,7 @@ class RayFeed:
         batch = {"ray_batch": torch.cat([rays_o, rays_d, self.near * ones, self.far * ones, view], -1).contiguous(),
                  "kp_batch": per_ray(self.kp3d), "skts": per_ray(self.skts), "bones": per_ray(self.bones),
                  "cyls": per_ray(self.cyls), "cams": per_ray(self.cam_idxs[:, None]), "target_s": flat(img),
-                 "fgs": flat(fg), "N_uniques": B}
+                 "fgs": flat(fg), "kp_idx": image_idxs[:, None].expand(B, R).reshape(n), "N_uniques": B}
         if bg is not None:
             batch["bgs"] = flat(bg)
         self.last_idxs = (image_idxs, pix)

@@ -331,11 +331,12 @@ def kp_loss(args, anchors, kp_idx, kp_opts, popt_layer=None, temp_val=None):
     """-> ({'kp_loss'[, 'temp_loss']}, {'MPJPC'}).  `kp_opts`: {'kp_batch', 'bones', 'rots'} from the layer's forward."""
     kp_idx = torch.as_tensor(kp_idx).long()
     dev = kp_opts["bones"].device
+    pick = lambda t: t[kp_idx.to(t.device)].to(dev)       # anchors kept on the layer's device are indexed there (no sync)
     if getattr(args, "opt_rot6d", False):
-        reg = rot_to_rot6d(anchors["rots"][kp_idx.cpu()]).to(dev)
+        reg = rot_to_rot6d(pick(anchors["rots"]))
         bones = rot_to_rot6d(kp_opts["rots"])
     else:
-        reg = anchors["bones"][kp_idx.cpu()].to(dev)
+        reg = pick(anchors["bones"])
         bones = kp_opts["bones"]
     assert len(reg) == len(bones)
     tol = float(getattr(args, "opt_pose_tol", 0.))
@@ -353,5 +354,5 @@ def kp_loss(args, anchors, kp_idx, kp_opts, popt_layer=None, temp_val=None):
         ang = ((bones - prev_b) - (next_b - bones)).pow(2.).sum(-1)
         vel = ((kps - prev_k) - (next_k - kps)).pow(2.).sum(-1)
         losses["temp_loss"] = ((ang + vel) * temp_val[..., None].to(dev)).mean() * float(args.temp_coef)
-    pjpc = (anchors["kps"][kp_idx.cpu()].to(dev) - kp_opts["kp_batch"].detach()).pow(2.).sum(-1).pow(0.5)
+    pjpc = (pick(anchors["kps"]) - kp_opts["kp_batch"].detach()).pow(2.).sum(-1).pow(0.5)
     return losses, {"MPJPC": pjpc.mean() / float(getattr(args, "ext_scale", 0.001))}

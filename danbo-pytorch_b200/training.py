@@ -47,10 +47,11 @@ def fused_loss_supported(args, preds):
     return args.loss_fn in ("L1", "MSE") and preds["rgb_map"].is_cuda
 
 
-def fused_loss_backward(args, preds, batch, network):
+def fused_loss_backward(args, preds, batch, network, extra_loss=None):
     """compute_loss + backward as ONE kernel launch (danbo_train_loss) followed by the path's own backward: the loss terms
     and d loss / d (rgb_map, acc_map, rgb0, acc0, confd) come out of the same pass, the volume-scale gradient is added to
-    axis_scale.grad directly, and autograd is entered at the render block's outputs.  -> (total loss, dict of terms)."""
+    axis_scale.grad directly, and autograd is entered at the render block's outputs.  `extra_loss` (a scalar with its own
+    autograd graph, e.g. the pose regulariser) is back-propagated in the same sweep.  -> (total loss, dict of terms)."""
     from . import kernels as K
     soft = args.soft_softmax_loss_coef if ("confd" in preds and args.agg_type == "sigmoid") else None
     gn = network.graph_net
@@ -64,9 +65,15 @@ def fused_loss_backward(args, preds, batch, network):
                             g_axis_scale=gn.axis_scale.grad if vol else None,
                             use_background=getattr(args, "use_background", True))
     keys = [k for k in ("rgb_map", "acc_map", "rgb0", "acc0", "confd") if k in g and preds[k].requires_grad]
-    torch.autograd.backward([preds[k] for k in keys], [g[k] for k in keys])
+    roots, seeds = [preds[k] for k in keys], [g[k] for k in keys]
+    if extra_loss is not None:
+        roots, seeds = roots + [extra_loss], seeds + [torch.ones_like(extra_loss)]
+    torch.autograd.backward(roots, seeds)
     names = ("rgb_loss", "rgb_loss0", "soft_softmax_loss", "vol_scale_loss")
-    return terms.sum().float(), {n: terms[i] for i, n in enumerate(names)}
+    total = terms.sum().float()
+    if extra_loss is not None:
+        total = total + extra_loss.detach().float()
+    return total, {n: terms[i] for i, n in enumerate(names)}
 
 
 class FlatAdam(torch.optim.Optimizer):
@@ -115,8 +122,23 @@ class FlatAdam(torch.optim.Optimizer):
 class TrainStep:
     """forward -> losses -> backward -> (all-reduce of one flat fp32 gradient bucket) -> Adam."""
 
-    def __init__(self, caster, args, optimizer=None, world_size=1, graph=False, fused_loss=True):
+    def __init__(self, caster, args, optimizer=None, world_size=1, graph=False, fused_loss=True, popt_kwargs=None,
+                 pose_optimizer=None):
+        """`popt_kwargs` / `pose_optimizer`: what `pose_opt.create_popt` returns (--opt_pose, core/trainer.py:314-341):
+        the batch's poses then come from the pose layer (indexed by `batch['kp_idx']`), the pose regulariser
+        (`pose_opt.kp_loss`) joins the loss and the pose optimiser steps with the network's."""
         self.caster, self.args, self.world = caster, args, world_size
+        self.popt = popt_kwargs if (popt_kwargs and popt_kwargs.get("popt_layer") is not None) else None
+        self.pose_optimizer = pose_optimizer
+        self.last_stats = {}
+        if self.popt is not None:
+            if graph:
+                raise NotImplementedError("graph capture of a training step with a pose layer is not implemented")
+            dev = next(caster.network.parameters()).device
+            self.popt["popt_layer"].to(dev)
+            # anchors on the layer's device once: indexing them by the batch's kp_idx then needs no host round trip
+            self.popt["popt_anchors"] = {k: (v.to(dev) if torch.is_tensor(v) else v)
+                                         for k, v in self.popt["popt_anchors"].items()}
         self.fused_loss = fused_loss           # False: the trainer's losses as PyTorch ops + autograd (compute_loss)
         params = [p for p in caster.network.parameters() if p.requires_grad]
         self.bucket = parallel.GradBucket(params)
@@ -160,20 +182,42 @@ class TrainStep:
 
     def _optimizer_step(self):
         self.optimizer.step()
+        if self.popt is not None and self.pose_optimizer is not None:
+            if self.world > 1:                  # every rank saw other frames: average like the network's gradients
+                import torch.distributed as dist
+                for p in self.popt["popt_layer"].parameters():
+                    if p.grad is not None:
+                        dist.all_reduce(p.grad)
+                        p.grad /= self.world
+            self.pose_optimizer.step()
         self.caster._packed_key = None          # weights changed (a raw-pointer update does not bump tensor versions)
 
     def _fwd_bwd(self, batch):
         a = self.args
         self.caster.train()
         self.bucket.zero()
+        extra = None
+        if self.popt is not None:
+            from . import pose_opt
+            layer = self.popt["popt_layer"]
+            if self.pose_optimizer is not None:
+                self.pose_optimizer.zero_grad(set_to_none=True)
+            kps, bones, skts, _, rots = layer(batch["kp_idx"], N_uniques=batch["N_uniques"])
+            batch = dict(batch, kp_batch=kps, skts=skts, bones=bones)
+            losses, self.last_stats = pose_opt.kp_loss(a, self.popt["popt_anchors"], batch["kp_idx"],
+                                                       {"kp_batch": kps, "bones": bones, "rots": rots}, popt_layer=layer,
+                                                       temp_val=batch.get("temp_val"))
+            extra = sum(losses.values())
         preds = self.caster(batch["ray_batch"], N_samples=a.N_samples, kp_batch=batch["kp_batch"], skts=batch["skts"],
                             cyls=batch["cyls"], bones=batch["bones"], cams=batch["cams"], N_uniques=batch["N_uniques"],
                             perturb=a.perturb, N_importance=a.N_importance, raw_noise_std=a.raw_noise_std)
         # every rank holds 1/world of the batch: mean-reduced data terms are averaged by the all-reduce; the parameter-only
         # volume penalty is identical on every rank, so averaging leaves it unchanged
         if self.fused_loss and fused_loss_supported(a, preds):
-            loss, terms = fused_loss_backward(a, preds, batch, self.caster.network)
+            loss, terms = fused_loss_backward(a, preds, batch, self.caster.network, extra_loss=extra)
             return loss, preds
         loss, terms = compute_loss(a, preds, batch, self.caster.network)
+        if extra is not None:
+            loss = loss + extra
         loss.backward()
         return loss.detach(), preds

@@ -51,6 +51,7 @@ def test_feed_reproduces_reference_batch(name):
     np.testing.assert_array_equal(b["skts"].numpy(), fx["skts"])
     np.testing.assert_array_equal(b["cyls"].numpy(), fx["cyls"])
     assert b["N_uniques"] == 4
+    np.testing.assert_array_equal(b["kp_idx"].numpy(), fx["kp_idx"])                # the queried index (dataset.py:424-430)
     img, pix = feed.last_idxs
     np.testing.assert_array_equal(img.numpy(), fx["image_idxs"])
     np.testing.assert_array_equal(pix.numpy(), fx["pixel_idxs"])

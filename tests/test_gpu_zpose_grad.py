@@ -127,3 +127,34 @@ def test_training_step_pose_gradients():
         # same bounds as the parameter gradients of train_fast (bf16 forward MLP, noise-gate flips)
         assert cos >= 0.985 and rel <= 0.2, (nm, cos, rel)
         assert cos_ref >= 0.95, (nm, cos_ref)
+
+
+def test_train_step_with_pose_layer_and_feed():
+    """--opt_pose iteration end to end: device-resident feed -> pose layer -> render block -> losses (+ pose regulariser)
+    -> both optimisers.  The poses of the frames in the batch must move, stay finite, and the loss must not blow up."""
+    from danbo_b200 import feed as fd, pose_opt as po, training, synthetic as syn
+    caster, args, _ = make_caster("danbo_fast", train=True)
+    arrays = fd.synthetic_arrays(n_images=6, H=64, W=64, seed=2)
+    feed = fd.RayFeed.from_arrays(arrays, syn.NEAR, syn.FAR, N_rand=4 * 48, N_sample_images=4, device=DEV, seed=1)
+    args.opt_pose_coef, args.opt_pose_tol, args.opt_pose_lrate = 1.0, 0.0, 1e-3
+    attrs = {"rest_pose": syn.rest_pose()[None], "betas": torch.zeros(1, 10).numpy(), "kp3d": arrays["kp3d"],
+             "bones": arrays["bones"]}
+    pose_optimizer, kw = po.create_popt(args, attrs, device=DEV)
+    layer = kw["popt_layer"]
+    before = layer.bones.detach().clone()
+    step = training.TrainStep(caster, args, popt_kwargs=kw, pose_optimizer=pose_optimizer)
+    g = torch.Generator(device=DEV).manual_seed(0)
+    losses, touched = [], set()
+    for _ in range(6):
+        batch = feed.next_batch(g)
+        touched.update(feed.last_idxs[0].tolist())
+        loss, preds = step(batch)
+        losses.append(float(loss))
+        assert preds["rgb_map"].shape == (4 * 48, 3)
+    torch.cuda.synchronize()
+    print("[popt] losses", [f"{v:.4f}" for v in losses], "MPJPC", float(step.last_stats["MPJPC"]))
+    assert all(l == l and l < 10 for l in losses)
+    moved = (layer.bones.detach() - before).abs().amax(dim=(1, 2)).cpu()
+    assert bool(torch.isfinite(layer.bones).all()) and bool(torch.isfinite(layer.pelvis).all())
+    for i in range(6):
+        assert (float(moved[i]) > 0) == (i in touched), (i, float(moved[i]), sorted(touched))

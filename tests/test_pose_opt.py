@@ -131,3 +131,66 @@ def test_create_popt_and_checkpoint_round_trip(tmp_path):
     assert float((kw2["popt_anchors"]["kps"] - full[0].detach()).abs().max()) < 1e-6
     with pytest.raises(NotImplementedError):
         po.pose_ckpt_to_pose_data(path, legacy=True)
+
+
+def test_train_step_with_pose_layer_on_a_stand_in_caster():
+    """`training.TrainStep(popt_kwargs=..., pose_optimizer=...)` plumbing on the CPU with a stand-in ray caster (the real
+    one needs a GPU): poses come from the layer by `kp_idx`, the regulariser joins the loss, both optimisers step."""
+    from danbo_b200 import training
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.full((3,), 0.5))
+
+    class Caster(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.network = Net()
+            self.seen = None
+
+        def forward(self, ray_batch, kp_batch=None, skts=None, bones=None, N_uniques=1, **kw):
+            self.seen = dict(kp_batch=kp_batch, skts=skts, bones=bones, N_uniques=N_uniques)
+            rgb = torch.sigmoid(skts[:, 3, :3, 3] * self.network.w + bones[:, 5, :3].sum(-1, keepdim=True))
+            acc = torch.sigmoid(kp_batch[:, 7, 0])
+            return {"rgb_map": rgb, "acc_map": acc}
+
+    n_frames, B, R = 7, 3, 4
+    args = types.SimpleNamespace(opt_rot6d=False, opt_pose_lrate=1e-2, init_poseopt=None, no_poseopt_reload=False,
+                                 use_ckpt_anchor=False, opt_pose_cache=False, opt_pose_tol=0.0, opt_pose_coef=2.0,
+                                 use_temp_loss=False, ext_scale=0.001, lrate=1e-2, loss_fn="L1", agg_type="sigmoid",
+                                 N_samples=8, N_importance=4, perturb=1.0, raw_noise_std=0., use_background=False,
+                                 opt_vol_scale=False)
+    attrs = {"rest_pose": FX["rest_pose"], "betas": np.zeros((1, 10), np.float32), "kp3d": FX["init_kps"],
+             "bones": FX["init_bones"]}
+    pose_opt_, kw = po.create_popt(args, attrs)
+    layer = kw["popt_layer"]
+    caster = Caster()
+    step = training.TrainStep(caster, args, popt_kwargs=kw, pose_optimizer=pose_opt_)
+    kp_idx = torch.tensor([1, 4, 6]).repeat_interleave(R)
+    batch = {"ray_batch": torch.zeros(B * R, 11), "kp_idx": kp_idx, "N_uniques": B, "cams": torch.zeros(B * R, 1),
+             "cyls": torch.zeros(B * R, 5), "target_s": torch.full((B * R, 3), 0.25),
+             # what the data feed put there; the layer's outputs must replace them
+             "kp_batch": torch.full((B * R, 24, 3), 9.), "skts": torch.full((B * R, 24, 4, 4), 9.),
+             "bones": torch.full((B * R, 24, 3), 9.)}
+    before = {k: v.detach().clone() for k, v in layer.state_dict().items()}
+    w0 = caster.network.w.detach().clone()
+    with torch.no_grad():
+        layer.bones[4, 9] += 0.3                                     # off the anchor -> the regulariser is active
+    loss1, _ = step(batch)
+    want = layer.calculate_kinematic(kp_idx.numpy())
+    assert caster.seen["N_uniques"] == B and caster.seen["skts"].shape == (B * R, 24, 4, 4)
+    assert float(caster.seen["kp_batch"].abs().max()) < 9.           # the layer's poses, not the feed's
+    assert "MPJPC" in step.last_stats and float(step.last_stats["MPJPC"]) > 0
+    after = layer.state_dict()
+    touched = [1, 4, 6]
+    rest = [i for i in range(n_frames) if i not in touched]
+    assert float((after["bones"][touched] - before["bones"][touched]).abs().max()) > 0          # pose optimiser stepped
+    assert float((after["pelvis"][touched] - before["pelvis"][touched]).abs().max()) > 0
+    assert torch.equal(after["bones"][rest], before["bones"][rest])                             # frames not in the batch untouched
+    assert not torch.equal(caster.network.w.detach(), w0)                                       # network optimiser stepped
+    assert float((after["bones"][4, 9] - FX["init_bones"][4, 9]).abs().max()) < 0.3 + 1e-6      # pulled back towards the anchor
+    losses = [float(loss1)] + [float(step(batch)[0]) for _ in range(20)]
+    assert losses[-1] < losses[0]
+    with pytest.raises(NotImplementedError):
+        training.TrainStep(caster, args, popt_kwargs=kw, pose_optimizer=pose_opt_, graph=True)
