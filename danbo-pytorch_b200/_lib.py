@@ -16,6 +16,8 @@ _SIGNATURES = {
     "danbo_nearfar": [c_p, c_i, c_i, c_p, c_i, c_p, c_i, c_i, c_p, c_p, c_i, c_i, c_f, c_f, c_p, c_p, c_p, c_i, c_p, c_p, c_p],
     "danbo_sample_mask": [c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p],
     "danbo_field_agg": [c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p],
+    "danbo_agg_frag_bytes": [],
+    "danbo_pack_agg_frags": [c_p, c_p, c_p],
     "danbo_ray_bias": [c_p, c_i, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p],
     "danbo_mlp_workspace_bytes": [c_p, c_p, c_p],
     "danbo_mlp_set_cta_pair": [c_i],

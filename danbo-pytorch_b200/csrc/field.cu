@@ -717,6 +717,14 @@ extern "C" int danbo_nearfar(const float* rays, int ray_stride, int n_rays, cons
     return 0;
 }
 
+namespace danbo {
+// field_mma.cu: the aggregation net as split-bf16 mma.sync products (opt-in through consts[10])
+int launch_pair_logits_mma(const float* rays, int ray_stride, int S, const float* z, const int* active_ids,
+                           const float* pose_skts, const float* pose_vol, int rays_per_pose, int n_poses,
+                           const FieldConsts& fc, PairWork pw, int pair_capacity, const void* frags, float* logits,
+                           int num_sms, cudaStream_t st);
+}
+
 static FieldConsts make_consts(const float* const* p) {
     FieldConsts fc;
     fc.align = p[0]; fc.axis_scale = p[1]; fc.agg_w0 = p[2]; fc.agg_adjw = p[3]; fc.agg_adj = p[4];
@@ -770,7 +778,12 @@ extern "C" int danbo_field_agg(const float* rays, int ray_stride, int n_rays, in
     DANBO_CHECK_LAUNCH();
     int pblocks = (pair_capacity / 64 + 24 + 3) / 4;                  // two 32-pair pieces per warp (+ one odd piece per bone)
     if (pblocks > num_sms * 8) pblocks = num_sms * 8;
-    if (n_poses == 1)
+    const void* agg_frags = consts[10];                               // danbo_pack_agg_frags table, or NULL (FFMA kernel)
+    if (agg_frags != nullptr) {
+        const int rc = launch_pair_logits_mma(rays, ray_stride, S, z, active_ids, pose_skts, pose_vol, rays_per_pose,
+                                              n_poses, fc, pw, pair_capacity, agg_frags, logits, num_sms, st);
+        if (rc != 0) return rc;
+    } else if (n_poses == 1)
         pair_logits_kernel<true><<<pblocks, 128, 0, st>>>(rays, ray_stride, S, z, active_ids, pose_skts, pose_vol, rays_per_pose,
                                                            n_poses, fc, pw, pair_capacity, logits);
     else

@@ -69,14 +69,33 @@ def f32c(t):
     return t.detach().to(torch.float32).contiguous()
 
 
-class FieldConsts:
-    """Device pointers to the ten constant tensors the field kernels read (see danbo_b200.h)."""
+# "ffma": the fp32 aggregation-net kernel every published number was measured with.  "mma": split-bf16 mma.sync
+# (csrc/field_mma.cu), opt-in until it has run on hardware - `DANBO_PAIR_LOGITS=mma` or set this before building a caster.
+import os as _os
+PAIR_LOGITS_IMPL = _os.environ.get("DANBO_PAIR_LOGITS", "ffma")
 
-    def __init__(self, align, axis_scale, agg):
+
+class FieldConsts:
+    """Device pointers to the ten constant tensors the field kernels read, plus the optional MMA fragment table of the
+    aggregation net (see danbo_b200.h)."""
+
+    def __init__(self, align, axis_scale, agg, pair_logits_impl=None):
         self.tensors = [f32c(align), f32c(axis_scale), f32c(agg["w0"]), f32c(agg["adj_w"]), f32c(agg["adj"]),
                         f32c(agg["b0"]), f32c(agg["w1"]), f32c(agg["b1"]), f32c(agg["w2"]), f32c(agg["b2"])]
         _need_cuda(*self.tensors)
-        self.array = (ctypes.c_void_p * 10)(*[t.data_ptr() for t in self.tensors])
+        impl = PAIR_LOGITS_IMPL if pair_logits_impl is None else pair_logits_impl
+        if impl not in ("ffma", "mma"):
+            raise ValueError(f"pair-logits implementation {impl!r}: 'ffma' or 'mma'")
+        self.frags = None
+        ptrs = [t.data_ptr() for t in self.tensors] + [None]
+        if impl == "mma":
+            lib = _lib.load()
+            self.frags = torch.empty(int(lib.danbo_agg_frag_bytes()), device=self.tensors[0].device, dtype=torch.uint8)
+            ptrs[10] = self.frags.data_ptr()
+        self.array = (ctypes.c_void_p * 11)(*ptrs)
+        if impl == "mma":
+            _lib.check(lib.danbo_pack_agg_frags(self.array, _p(self.frags), _stream()), "danbo_pack_agg_frags")
+            _count(1)
 
     @property
     def align(self):

@@ -31,9 +31,19 @@ int danbo_nearfar(const float* rays, int ray_stride, int n_rays, const float* po
                   int seg_len, int use_box, float bound, float bound_hi, float* near_out, float* far_out,
                   double* seg_acc, int n_seg, unsigned char* p_valid, unsigned char* v_valid, void* stream);
 
-/* consts[10] = { align (24,4,4), axis_scale (24,3), prob_linears.layers.0.lin.weight (24,15,32),
+/* consts[11] = { align (24,4,4), axis_scale (24,3), prob_linears.layers.0.lin.weight (24,15,32),
  *               .layers.0.adj_w (24,24), .layers.0.adj (24,24), .layers.0.bias (32), .layers.1.weight (24,32,32),
- *               .layers.1.bias (24,32), .layers.2.weight (24,32), .layers.2.bias (24) }  (device pointers) */
+ *               .layers.1.bias (24,32), .layers.2.weight (24,32), .layers.2.bias (24),
+ *               agg_frags or NULL }  (device pointers).
+ * consts[10] is read by danbo_field_agg only: NULL selects the fp32 FFMA aggregation-net kernel (the one every
+ * published number was measured with); a table filled by danbo_pack_agg_frags selects the split-bf16 mma.sync kernel
+ * (csrc/field_mma.cu; logits within 3e-6 of scale; NOT yet run on hardware). */
+
+/* Bytes of the fragment table, and the packing of prob_linears' layer-0 / layer-1 weights (consts[2], consts[6]) into
+ * split-bf16 m16n8k16 B fragments for the tensor-core aggregation net (MixGNN, gnn_backbone.py:225-274,567-629).
+ * Re-run after every update of those weights. */
+int danbo_agg_frag_bytes(void);
+int danbo_pack_agg_frags(const float* const* consts, void* frags, void* stream);
 
 /* SM1 + T1/T2 + bone-visibility mask + compaction.
  * sample_from_lineseg (ray_utils.py:206-253), transform_batch_pts (core/encoders.py:288-303), bone align

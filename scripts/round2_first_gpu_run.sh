@@ -1,0 +1,20 @@
+#!/bin/bash
+# First gpurun call of round 2: everything that was written at the end of round 1 without GPU access, in one go.
+#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash scripts/round2_first_gpu_run.sh'
+# Outputs land in gpurun_out/ (r2a_*).  Nothing here is a bench value.
+set -u
+mkdir -p gpurun_out
+# 1. the verified suite must still be green with the rebuilt library (ABI 3, consts[11], grads[10])
+python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_zpose_grad.py --deselect tests/test_gpu_zz_pair_logits_mma.py \
+    > gpurun_out/r2a_gpu_verified.log 2>&1
+# 2. the unverified paths, with their xfail markers ignored so that failures show as failures
+python -m pytest tests/test_gpu_zpose_grad.py tests/test_gpu_zz_pair_logits_mma.py -m gpu -q -s --runxfail \
+    > gpurun_out/r2a_gpu_unverified.log 2>&1
+# 3. legacy-MMA issue rate (decides how far the split-bf16 aggregation net can go)
+mkdir -p scripts/micro/bin
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o scripts/micro/bin/mma_sync_rate scripts/micro/mma_sync_rate.cu \
+    && scripts/micro/bin/mma_sync_rate > gpurun_out/r2a_mma_sync_rate.log 2>&1
+# 4. headline step with either aggregation-net kernel
+python bench.py --steps 10 --warmup 3 > gpurun_out/r2a_bench_ffma.json 2> gpurun_out/r2a_bench_ffma.err
+DANBO_PAIR_LOGITS=mma python bench.py --steps 10 --warmup 3 > gpurun_out/r2a_bench_mma.json 2> gpurun_out/r2a_bench_mma.err
+tail -3 gpurun_out/r2a_gpu_verified.log gpurun_out/r2a_gpu_unverified.log
