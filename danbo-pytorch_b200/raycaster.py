@@ -20,6 +20,10 @@ from . import skeleton as sk
 from .networks import DanboField
 
 MAX_RAYS_PER_LAUNCH = 262144          # multiple of every sane `chunk`; bounds the size of the X tile buffer (1.5 GB at danbo_fast density)
+# Opt-in (not yet measured on hardware): an eval call of one pose is cut into this many ray blocks whose launch
+# sequences are issued on separate streams, so that the issue-/LSU-bound kernels of one block can fill the SM time the
+# tensor-bound MLP kernel of the other leaves (and the gaps between dependent launches).  1 = one stream, as measured.
+BLOCK_STREAMS = int(os.environ.get("DANBO_BLOCK_STREAMS", "1"))
 
 
 class RayCaster(nn.Module):
@@ -51,6 +55,8 @@ class RayCaster(nn.Module):
         self._packed_key = None
         self._align_dev = None
         self._graphed = None
+        self.block_streams = BLOCK_STREAMS
+        self._side_streams = []
 
     # ------------------------------------------------------------------------------------------------ dispatch
     def forward(self, *args, fwd_type="", **kwargs):
@@ -219,14 +225,37 @@ class RayCaster(nn.Module):
         # internal launches: any split works for a single pose; with several poses a block holds whole poses
         G = pose_skts.shape[0]
         block = MAX_RAYS_PER_LAUNCH if G == 1 else max((MAX_RAYS_PER_LAUNCH // skip) * skip, skip)
+        # (only with nanmean_chunk: blocks are then whole near/far fill chunks, so the split cannot change any pixel)
+        n_streams = self.block_streams if (G == 1 and not training and _stages is None and nanmean_chunk
+                                           and N >= 32768) else 1
+        if n_streams > 1:
+            unit = int(nanmean_chunk)
+            block = min(block, -(-(-(-N // n_streams)) // unit) * unit)     # ceil(N / n_streams) rounded up to the unit
         if nanmean_chunk:
             block = max((block // int(nanmean_chunk)) * int(nanmean_chunk), int(nanmean_chunk)) if G == 1 else block
-        for s0 in range(0, N, block):
+        cur = torch.cuda.current_stream(dev) if n_streams > 1 else None
+        while len(self._side_streams) < (n_streams if n_streams > 1 else 0):
+            self._side_streams.append(torch.cuda.Stream(device=dev))
+        used = []
+        for i, s0 in enumerate(range(0, N, block)):
             s1 = min(N, s0 + block)
             sub_rand = {k: v[s0:s1].to(dev).contiguous() for k, v in rand.items()}
-            outs.append(self._render_block(rays[s0:s1], s0, skip, pose_skts, pose_cyls, vol, cam_idx[s0:s1], codes,
-                                           consts, packed, N_samples, N_importance, B, raw_noise_std, perturb,
-                                           training, nanmean_chunk, sub_rand, _stages, lindisp=lindisp))
+            args = (rays[s0:s1], s0, skip, pose_skts, pose_cyls, vol, cam_idx[s0:s1], codes, consts, packed, N_samples,
+                    N_importance, B, raw_noise_std, perturb, training, nanmean_chunk, sub_rand, _stages)
+            if n_streams > 1:
+                side = self._side_streams[i % n_streams]
+                if side not in used:
+                    side.wait_stream(cur)                                   # inputs, packed weights, bone volumes
+                    used.append(side)
+                with torch.cuda.stream(side):
+                    out = self._render_block(*args, lindisp=lindisp)
+                for t in out.values():
+                    t.record_stream(cur)                                    # consumed (cat) on the caller's stream
+                outs.append(out)
+            else:
+                outs.append(self._render_block(*args, lindisp=lindisp))
+        for side in used:
+            cur.wait_stream(side)
         if len(outs) == 1:
             return outs[0]
         return {k: torch.cat([o[k] for o in outs], 0) for k in outs[0]}

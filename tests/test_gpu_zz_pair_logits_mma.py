@@ -108,3 +108,32 @@ def test_pair_logits_mma_multi_pose_and_speed():
         e1.record()
         torch.cuda.synchronize()
         print(f"[mma] field_agg, 512x512 coarse pass, {impl}: {e0.elapsed_time(e1) / 10:.3f} ms")
+
+
+def test_block_streams_same_pixels_and_speed():
+    """Opt-in stream pipelining of ray blocks (raycaster.BLOCK_STREAMS): identical pixels, timing printed."""
+    from danbo_b200 import synthetic as syn
+    caster, args, _ = make_caster("danbo_fast")
+    pose = syn.make_pose(3)
+    rb = syn.render_batch(pose, 512, 512)
+    kw = dict(N_samples=args.N_samples, kp_batch=rb["kp_batch"], skts=rb["skts"], cyls=rb["cyls"], bones=rb["bones"],
+              cams=rb["cams"], N_uniques=1, perturb=False, N_importance=args.N_importance, raw_noise_std=0.,
+              nanmean_chunk=4096)
+    rays = rb["ray_batch"].to(DEV)
+    res = {}
+    for n in (1, 2, 3):
+        caster.block_streams = n
+        for _ in range(2):
+            out = caster(rays, **kw)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            out = caster(rays, **kw)
+        e1.record()
+        torch.cuda.synchronize()
+        res[n] = {k: v.clone() for k, v in out.items()}
+        print(f"[streams] 512x512 danbo_fast eager, {n} stream(s): {e0.elapsed_time(e1) / 5:.3f} ms")
+    for n in (2, 3):
+        for k in ("rgb_map", "acc_map", "disp_map", "rgb0"):
+            assert torch.equal(res[1][k], res[n][k]), (n, k)
