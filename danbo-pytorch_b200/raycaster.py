@@ -249,8 +249,9 @@ class RayCaster(nn.Module):
                     used.append(side)
                 with torch.cuda.stream(side):
                     out = self._render_block(*args, lindisp=lindisp)
-                for t in out.values():
-                    t.record_stream(cur)                                    # consumed (cat) on the caller's stream
+                if not torch.cuda.is_current_stream_capturing():           # a captured graph's memory is static anyway
+                    for t in out.values():
+                        t.record_stream(cur)                                # consumed (cat) on the caller's stream
                 outs.append(out)
             else:
                 outs.append(self._render_block(*args, lindisp=lindisp))
