@@ -9,7 +9,7 @@ csrc/, reached only through the C ABI declared in include/danbo_b200.h (ctypes, 
 There is no CPU fallback: calling any kernel entry without the built library raises.
 """
 from . import skeleton, synthetic, params, config  # noqa: F401
-from . import _lib, build, kernels, networks, raycaster, anerf, parallel, training, render, feed, pose_opt  # noqa: F401
+from . import _lib, build, kernels, networks, raycaster, anerf, parallel, training, render, feed, pose_opt, mesh  # noqa: F401
 from .raycaster import RayCaster, GraphCaster, create_raycaster  # noqa: F401
 from .config import make_args  # noqa: F401
 
