@@ -139,12 +139,14 @@ class RayFeed:
 
     # ---- dataset.py:281-305 -------------------------------------------------------------------------------------
     def get_img_data(self, image_idxs, pix, generator=None):
-        gather = lambda a, ch: torch.gather(a[image_idxs], 1, pix[..., None].expand(-1, -1, ch))
-        fg = gather(self.masks, 1).float()
-        img = gather(self.imgs, 3).float() / 255.
+        # only the sampled pixels are touched: (image, pixel) -> row of the flattened (N*H*W, C) array
+        HW = self.H * self.W
+        gather = lambda a, rows: a.reshape(-1, a.shape[-1])[rows[:, None] * HW + pix]
+        fg = gather(self.masks, image_idxs).float()
+        img = gather(self.imgs, image_idxs).float() / 255.
         bg = None
         if self.bkgds is not None:
-            bg = torch.gather(self.bkgds[self.bkgd_idxs[image_idxs]], 1, pix[..., None].expand(-1, -1, 3)).float() / 255.
+            bg = gather(self.bkgds, self.bkgd_idxs[image_idxs]).float() / 255.
             if self.perturb_bg:
                 noise = torch.rand(bg.shape, device=self.device, generator=generator)
                 bg = (1 - fg) * noise + fg * bg
