@@ -14,10 +14,13 @@ the closed-form rigid inverse [R^T | -R^T t] instead of `torch.inverse` (24 LU f
 (`N_uniques` image-major batches skip even the unique()) and returned as stride-0 expands, which is what the ray caster
 reduces back to per-pose tables (raycaster._prepare).
 
-What is NOT here yet: the gradient of the rendered colours with respect to `skts` through the CUDA path
-(`sample_mask` / `field_agg` backward to sample coordinates) - so `--opt_pose` training of the poses themselves is
-round-2 work; with it absent, `RayCaster` treats the layer's outputs as constants (they carry no gradient into the
-kernels), while the regulariser below and refined-pose rendering work as in the reference.
+The gradient of the rendered colours with respect to the layer's outputs comes from the CUDA path: d loss / d skts from
+`danbo_field_agg_bwd` (`grads[9]`, csrc/backward_field.cu; the render block's autograd node takes the per-pose matrices
+as an input) and d loss / d bones through the graph net's PyTorch ops (`networks.DanboField.bone_volumes`); `kp_batch`
+receives none in the DANBO field, as in the reference.  `training.TrainStep(popt_kwargs=..., pose_optimizer=...)` runs
+the whole --opt_pose iteration.  That gradient path was written after round 1's GPU minutes were spent: it is pinned on
+the CPU (oracle vs the reference's own pose gradients, tests/golden/train_fast_popt.npz) and its GPU tests
+(tests/test_gpu_zpose_grad.py) have not run on hardware yet.
 """
 import numpy as np
 import torch
