@@ -53,3 +53,35 @@ def test_oracle_matches_live_reference(config, extra, kw):
         # a sample within rounding of a bone-box face flips its mask and moves that ray discontinuously (see
         # test_oracle_golden.test_render_rays_end_to_end): 98 % of rays within 2e-5 of scale
         assert float((err <= 2e-5 * scale).float().mean()) >= 0.98, (k, float(err.max()))
+
+
+def test_anerf_oracle_matches_live_reference():
+    """AN1 live: another pose, other weights and sample counts than the committed `render_anerf` fixture."""
+    import danbo_oracle as orc
+    from danbo_b200 import params, synthetic as syn
+    from util import align_A
+    args = rh.parse_args("h36m_zju/anerf_base.txt", ["--N_samples", "20", "--N_importance", "10"])
+    caster, kw = rh.build(args, syn.rest_pose())
+    caster.eval()
+    sd = syn.synth_state_dict(params.anerf_param_shapes(), 5)
+    rh.load_weights(caster, sd)
+    pose = syn.make_pose(13)
+    full = syn.render_batch(pose, 40, 40)
+    g = torch.Generator().manual_seed(13)
+    N = 48
+    pick = torch.sort(torch.randperm(full["ray_batch"].shape[0], generator=g)[:N]).values
+    b = {k: (v[pick].contiguous() if torch.is_tensor(v) and v.shape[0] == full["ray_batch"].shape[0] else v)
+         for k, v in full.items()}
+    kwargs = {k: v for k, v in kw.items() if k not in ("ray_caster", "N_samples", "use_viewdirs")}
+    with torch.no_grad():
+        want = caster(b["ray_batch"], N_samples=args.N_samples, kp_batch=b["kp_batch"], skts=b["skts"], cyls=b["cyls"],
+                      bones=b["bones"], cams=b["cams"], N_uniques=1, **kwargs)
+        P = {k: torch.as_tensor(v) for k, v in sd.items()}
+        t = lambda a: torch.as_tensor(a)[None]
+        got = orc.anerf_render_rays(b["ray_batch"], t(pose["skts"]), t(pose["cyl"]), b["cams"], align_A(), P,
+                                    args.N_samples, args.N_importance, rays_per_pose=N,
+                                    tau=float(caster.network.pe_fn.get_tau()))
+    for k in ("rgb_map", "acc_map", "rgb0", "acc0"):
+        err = (got[k] - want[k]).abs().reshape(N, -1).max(-1).values
+        # the 64x-amplified top octave of the cutoff PE moves raw by ~1e-4; a ray whose importance samples flip a bin moves more
+        assert float((err <= 2e-4).float().mean()) >= 0.95, (k, float(err.max()))
