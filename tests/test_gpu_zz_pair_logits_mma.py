@@ -137,3 +137,27 @@ def test_block_streams_same_pixels_and_speed():
     for n in (2, 3):
         for k in ("rgb_map", "acc_map", "disp_map", "rgb0"):
             assert torch.equal(res[1][k], res[n][k]), (n, k)
+
+
+def test_render_mesh_on_the_device():
+    """`mesh.render_mesh` (run_render.py:1266-1281) on the real caster: the lattice of `fwd_type='mesh'` is extracted on
+    the GPU; the surface must be closed and consistently oriented, and equal to the extraction of the same lattice on
+    the CPU."""
+    from danbo_b200 import mesh, synthetic as syn
+    from test_mesh import check_closed_oriented
+    caster, args, _ = make_caster("danbo_fast")
+    pose = syn.make_pose(3)
+    t = lambda a: torch.as_tensor(a)[None].to(DEV)
+    res = 63
+    raw = caster(kps=t(pose["kps"]), skts=t(pose["skts"]), bones=t(pose["bones"]), radius=1.0, res=res, fwd_type="mesh")
+    sig = torch.relu(raw.reshape(res + 1, res + 1, res + 1))
+    thr = float(sig.max()) * 0.25
+    sig[0], sig[-1], sig[:, 0], sig[:, -1], sig[:, :, 0], sig[:, :, -1] = 0., 0., 0., 0., 0., 0.     # closed inside the lattice
+    v, tri = mesh.marching_cubes(sig, thr)
+    assert v.is_cuda and tri.shape[0] > 0
+    check_closed_oriented(tri.cpu())
+    v2, tri2 = mesh.marching_cubes(sig.cpu(), thr)
+    assert torch.equal(tri.cpu(), tri2) and float((v.cpu() - v2).abs().max()) < 1e-5
+    out = mesh.render_mesh(caster, t(pose["kps"]), t(pose["skts"]), t(pose["bones"]), radius=1.0, res=res, threshold=thr)
+    assert len(out) == 1 and out[0][0].shape[1] == 3
+    print(f"[mesh] {v.shape[0]} vertices, {tri.shape[0]} triangles at threshold {thr:.3f}")
