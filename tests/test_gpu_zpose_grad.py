@@ -13,7 +13,7 @@ import torch
 import danbo_oracle as orc
 from util import load_fixture, params_for, align_A, make_caster, preset_of, agg_type_of
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),          # a hung kernel must not hang the box
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300, method="thread"),   # a hung kernel must not hang the box
               pytest.mark.xfail(strict=False, reason="pose-gradient path not yet run on hardware (written without GPU access)")]
 DEV = "cuda"
 

@@ -12,7 +12,7 @@ import torch
 import danbo_oracle as orc
 from util import load_fixture, params_for, align_A, make_caster, preset_of, agg_type_of, pose_tensors
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),          # a hung kernel must not hang the box
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300, method="thread"),   # a hung kernel must not hang the box
               pytest.mark.xfail(strict=False, reason="mma pair-logits kernel not yet run on hardware (written without GPU access)")]
 DEV = "cuda"
 
