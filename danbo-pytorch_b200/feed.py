@@ -67,13 +67,17 @@ class RayFeed:
         """Compressed list of every image's candidate pixels (CSR: `_valid_flat[_valid_off[i] : _valid_off[i+1]]`,
         increasing): the sampling mask, or the whole image when the mask holds fewer pixels than one draw needs
         (dataset.py:317-319).  Call again after editing `sampling_masks`."""
-        m = self.sampling_masks > 0
-        m = m | (m.sum(-1, keepdim=True) < self.rays_per_image)
-        self._n_valid = m.sum(-1)                                            # (n_images,)
+        counts, flat = [], []
+        for s in range(0, self.n_images, 64):                               # 64 images at a time bounds the temporaries
+            m = self.sampling_masks[s:s + 64] > 0
+            m = m | (m.sum(-1, keepdim=True) < self.rays_per_image)
+            counts.append(m.sum(-1))
+            flat.append(torch.nonzero(m)[:, 1].to(torch.int32))             # row-major: per image, increasing
+        self._n_valid = torch.cat(counts) if counts else torch.zeros(0, dtype=torch.int64, device=self.device)
         off = torch.zeros(self.n_images + 1, dtype=torch.int64, device=self.device)
         off[1:] = torch.cumsum(self._n_valid, 0)
         self._valid_off = off
-        self._valid_flat = torch.nonzero(m)[:, 1].to(torch.int32)           # row-major: per image, increasing
+        self._valid_flat = torch.cat(flat) if flat else torch.zeros(0, dtype=torch.int32, device=self.device)
         # rejection-free fast path needs collisions among the candidates to be rare (see sample_pixels)
         self._sparse_draw = bool((self._n_valid >= 64 * self.rays_per_image).all()) if self.n_images else False
 
