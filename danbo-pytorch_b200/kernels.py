@@ -3,6 +3,7 @@
 Every function requires CUDA tensors and enqueues on torch's current stream.  There is no CPU path."""
 import ctypes
 import functools
+import os
 
 import torch
 
@@ -22,14 +23,22 @@ def _count(n):
         PROFILE["launches"] += n
 
 
+# True (or DANBO_NVTX=1): every stage wrapper opens an NVTX range (`ncu --nvtx --nvtx-include "field_agg/"`)
+NVTX = os.environ.get("DANBO_NVTX", "") == "1"
+
+
 class _Timed:
-    """with _Timed("name"): ... -> CUDA-event pair appended to PROFILE["stages"] when stage timing is on."""
+    """with _Timed("name"): ... -> CUDA-event pair appended to PROFILE["stages"] when stage timing is on; an NVTX range
+    of the same name when NVTX is on."""
 
     def __init__(self, name):
         self.name = name
 
     def __enter__(self):
         self.on = PROFILE is not None and "stages" in PROFILE
+        self.nvtx = NVTX
+        if self.nvtx:
+            torch.cuda.nvtx.range_push(self.name)
         if self.on:
             self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             self.e0.record()
@@ -38,6 +47,8 @@ class _Timed:
         if self.on:
             self.e1.record()
             PROFILE["stages"].append((self.name, self.e0, self.e1))
+        if self.nvtx:
+            torch.cuda.nvtx.range_pop()
 
 
 def _p(t):
@@ -71,8 +82,7 @@ def f32c(t):
 
 # "ffma": the fp32 aggregation-net kernel every published number was measured with.  "mma": split-bf16 mma.sync
 # (csrc/field_mma.cu), opt-in until it has run on hardware - `DANBO_PAIR_LOGITS=mma` or set this before building a caster.
-import os as _os
-PAIR_LOGITS_IMPL = _os.environ.get("DANBO_PAIR_LOGITS", "ffma")
+PAIR_LOGITS_IMPL = os.environ.get("DANBO_PAIR_LOGITS", "ffma")
 
 
 class FieldConsts:

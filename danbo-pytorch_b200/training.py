@@ -76,6 +76,57 @@ def fused_loss_backward(args, preds, batch, network, extra_loss=None):
     return total, {n: terms[i] for i, n in enumerate(names)}
 
 
+def adam_state_to_dict(params, exp_avg, exp_avg_sq, step, group):
+    """Flat moment arenas -> a state dict in torch.optim.Adam's own format (so checkpoints written here resume under the
+    reference's `torch.optim.Adam`, core/raycasters.py:71-78,99-101, and the other way round)."""
+    state, off = {}, 0
+    for i, p in enumerate(params):
+        n = p.numel()
+        state[i] = {"step": torch.tensor(float(step)), "exp_avg": exp_avg[off:off + n].view_as(p).clone(),
+                    "exp_avg_sq": exp_avg_sq[off:off + n].view_as(p).clone()}
+        off += n
+    pg = {"lr": group["lr"], "betas": tuple(group["betas"]), "eps": group["eps"], "weight_decay": 0, "amsgrad": False,
+          "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+          "params": list(range(len(params)))}
+    return {"state": state, "param_groups": [pg]}
+
+
+def adam_state_from_dict(sd, params, exp_avg, exp_avg_sq):
+    """Inverse of adam_state_to_dict for a torch.optim.Adam state dict over the same parameters (one group, any
+    steps).  Fills the flat arenas in place -> (step, lr).  Parameters without state (never stepped) get zeros."""
+    ids = [i for g in sd["param_groups"] for i in g["params"]]
+    if len(ids) != len(params):
+        raise ValueError(f"optimizer state holds {len(ids)} parameters, the model has {len(params)}")
+    off, step = 0, 0.0
+    for i, p in zip(ids, params):
+        n = p.numel()
+        st = sd["state"].get(i)
+        if st is None:
+            exp_avg[off:off + n].zero_()
+            exp_avg_sq[off:off + n].zero_()
+        else:
+            if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                raise ValueError(f"optimizer state {i}: shape {tuple(st['exp_avg'].shape)} vs parameter {tuple(p.shape)}")
+            exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
+            exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+            step = max(step, float(st["step"]))
+        off += n
+    return step, float(sd["param_groups"][0]["lr"])
+
+
+def save_checkpoint(path, global_step, caster, optimizer, popt_kwargs=None, pose_optimizer=None):
+    """Trainer.save_nerf (core/trainer.py:597-618): the same keys, so `create_raycaster` here or in the reference resumes
+    from the file."""
+    popt_sd = poptim_sd = anchors = None
+    if popt_kwargs is not None and popt_kwargs.get("popt_layer") is not None:
+        popt_sd = popt_kwargs["popt_layer"].state_dict()
+        poptim_sd = pose_optimizer.state_dict() if pose_optimizer is not None else None
+        anchors = popt_kwargs.get("popt_anchors")
+    torch.save({"global_step": global_step, "optimizer_state_dict": optimizer.state_dict(),
+                "poseopt_layer_state_dict": popt_sd, "pose_optimizer_state_dict": poptim_sd, "poseopt_anchors": anchors,
+                **caster.state_dict()}, path)
+
+
 class FlatAdam(torch.optim.Optimizer):
     """torch.optim.Adam (lr, betas, eps; no weight decay / amsgrad) as ONE kernel launch: parameters, gradients and both
     moments live in flat fp32 arenas and every nn.Parameter is a view of the parameter arena.  `step` and `lr` are device
@@ -105,6 +156,16 @@ class FlatAdam(torch.optim.Optimizer):
     def set_lr(self, lr):
         self.param_groups[0]["lr"] = float(lr)
         self.lr_dev.fill_(float(lr))
+
+    def state_dict(self):
+        """torch.optim.Adam's format (one host read of the step counter)."""
+        return adam_state_to_dict(self.bucket.params, self.exp_avg, self.exp_avg_sq, float(self.step_dev.item()),
+                                  self.param_groups[0])
+
+    def load_state_dict(self, sd):
+        step, lr = adam_state_from_dict(sd, self.bucket.params, self.exp_avg, self.exp_avg_sq)
+        self.step_dev.fill_(step)
+        self.set_lr(lr)
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -179,6 +240,22 @@ class TrainStep:
         self.bucket.allreduce(average=True)
         self._optimizer_step()
         return loss, preds
+
+    def save(self, path, global_step):
+        """Checkpoint in the reference's format (Trainer.save_nerf, core/trainer.py:597-618)."""
+        save_checkpoint(path, global_step, self.caster, self.optimizer, self.popt, self.pose_optimizer)
+
+    def resume(self, ckpt):
+        """Optimizer (and pose layer) state of a loaded checkpoint dict; the network weights are loaded by
+        `create_raycaster` / `caster.load_state_dict`.  -> global_step."""
+        if ckpt.get("optimizer_state_dict") is not None:
+            self.optimizer.load_state_dict(ckpt["optimizer_state_dict"])
+        if self.popt is not None and ckpt.get("poseopt_layer_state_dict") is not None:
+            self.popt["popt_layer"].load_state_dict(ckpt["poseopt_layer_state_dict"])
+            if self.pose_optimizer is not None and ckpt.get("pose_optimizer_state_dict") is not None:
+                self.pose_optimizer.load_state_dict(ckpt["pose_optimizer_state_dict"])
+        self.caster._packed_key = None
+        return int(ckpt.get("global_step", 0))
 
     def _optimizer_step(self):
         self.optimizer.step()

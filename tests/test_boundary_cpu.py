@@ -96,3 +96,56 @@ def test_kernels_fail_loudly_without_a_gpu():
     with pytest.raises(RuntimeError):
         c(b["ray_batch"], N_samples=args.N_samples, kp_batch=b["kp_batch"], skts=b["skts"], cyls=b["cyls"], bones=b["bones"],
           cams=b["cams"], N_uniques=1, perturb=False, N_importance=args.N_importance, raw_noise_std=0.)
+
+
+def test_flat_adam_state_is_interchangeable_with_torch_adam(tmp_path):
+    """Checkpoints keep the reference's format (core/trainer.py:597-618): the flat moment arenas of the single-launch Adam
+    serialise to torch.optim.Adam's own state dict and back, so either side resumes from the other's file."""
+    import torch
+    from danbo_b200 import training
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 4), torch.nn.Linear(4, 2))
+    params = list(net.parameters())
+    opt = torch.optim.Adam(params, lr=3e-4, betas=(0.9, 0.999))
+    for _ in range(3):
+        opt.zero_grad()
+        net(torch.randn(7, 5)).pow(2).sum().backward()
+        opt.step()
+    sd = opt.state_dict()
+    n = sum(p.numel() for p in params)
+    m, v = torch.full((n,), 9.), torch.full((n,), 9.)
+    step, lr = training.adam_state_from_dict(sd, params, m, v)
+    assert step == 3.0 and lr == 3e-4
+    off = 0
+    for i, p in enumerate(params):
+        assert torch.equal(m[off:off + p.numel()].view_as(p), sd["state"][i]["exp_avg"])
+        assert torch.equal(v[off:off + p.numel()].view_as(p), sd["state"][i]["exp_avg_sq"])
+        off += p.numel()
+    back = training.adam_state_to_dict(params, m, v, step, {"lr": lr, "betas": (0.9, 0.999), "eps": 1e-8})
+    # a fresh torch Adam resumed from the flat state continues exactly like the original
+    import copy
+    net2 = copy.deepcopy(net)
+    opt2 = torch.optim.Adam(list(net2.parameters()), lr=1.0)
+    opt2.load_state_dict(back)
+    x = torch.randn(7, 5)
+    for o, nn_ in ((opt, net), (opt2, net2)):
+        o.zero_grad()
+        nn_(x).pow(2).sum().backward()
+        o.step()
+    for a, b in zip(net.parameters(), net2.parameters()):
+        assert torch.equal(a, b)
+    # parameters that never stepped have no state: zeros
+    opt3 = torch.optim.Adam(params, lr=1e-3)
+    m.fill_(5.)
+    assert training.adam_state_from_dict(opt3.state_dict(), params, m, v)[0] == 0.0 and float(m.abs().max()) == 0.0
+    # the checkpoint file carries the reference's keys
+
+    class Caster:
+        def state_dict(self):
+            return {"network_fn_state_dict": net.state_dict(), "network_fine_state_dict": net.state_dict()}
+    path = os.path.join(tmp_path, "000010.tar")
+    training.save_checkpoint(path, 10, Caster(), opt)
+    ck = torch.load(path, weights_only=False)
+    assert set(ck) == {"global_step", "optimizer_state_dict", "poseopt_layer_state_dict", "pose_optimizer_state_dict",
+                       "poseopt_anchors", "network_fn_state_dict", "network_fine_state_dict"}
+    assert ck["global_step"] == 10 and ck["poseopt_layer_state_dict"] is None
