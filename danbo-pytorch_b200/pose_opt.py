@@ -208,13 +208,20 @@ class PoseOptLayer(nn.Module):
             return self.rest_pose
         if rest_pose_idxs is not None:
             return self.rest_pose[rest_pose_idxs]
-        return self.rest_pose[torch.as_tensor(self.rest_pose_idxs)[kp_idxs]]
+        table = torch.as_tensor(self.rest_pose_idxs, device=self.rest_pose.device).long()
+        return self.rest_pose[table[torch.as_tensor(kp_idxs, device=table.device).long()]]
 
     @torch.no_grad()
     def update_cache(self):
         self._cache = None
         self._cache = tuple(t.detach() for t in self.calculate_kinematic(np.arange(self.N_kps)))
         self.cache_kps, self.cache_bones, self.cache_skts, self.cache_l2ws, self.cache_rots = self._cache
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)             # .to(device) / .float(): the cache follows the parameters
+        if getattr(self, "_cache", None) is not None:
+            self.update_cache()
+        return out
 
     def forward(self, idxs, rest_pose_idxs=None, N_uniques=None):
         if self.use_cache and self._cache is not None:

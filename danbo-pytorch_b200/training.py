@@ -267,6 +267,8 @@ class TrainStep:
                         dist.all_reduce(p.grad)
                         p.grad /= self.world
             self.pose_optimizer.step()
+            if self.popt["popt_layer"].use_cache:                # pose_opt.py:577-578
+                self.popt["popt_layer"].update_cache()
         self.caster._packed_key = None          # weights changed (a raw-pointer update does not bump tensor versions)
 
     def _fwd_bwd(self, batch):
@@ -279,7 +281,8 @@ class TrainStep:
             layer = self.popt["popt_layer"]
             if self.pose_optimizer is not None:
                 self.pose_optimizer.zero_grad(set_to_none=True)
-            kps, bones, skts, _, rots = layer(batch["kp_idx"], N_uniques=batch["N_uniques"])
+            # not the layer's cache: the poses must carry their graph (the cache is refreshed after the pose step)
+            kps, bones, skts, _, rots = layer.calculate_kinematic(batch["kp_idx"], N_uniques=batch["N_uniques"])
             batch = dict(batch, kp_batch=kps, skts=skts, bones=bones)
             losses, self.last_stats = pose_opt.kp_loss(a, self.popt["popt_anchors"], batch["kp_idx"],
                                                        {"kp_batch": kps, "bones": bones, "rots": rots}, popt_layer=layer,

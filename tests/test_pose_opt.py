@@ -194,3 +194,23 @@ def test_train_step_with_pose_layer_on_a_stand_in_caster():
     assert losses[-1] < losses[0]
     with pytest.raises(NotImplementedError):
         training.TrainStep(caster, args, popt_kwargs=kw, pose_optimizer=pose_opt_, graph=True)
+
+
+def test_cache_follows_the_parameters_and_rest_pose_tables():
+    kps, bones = T("init_kps"), T("init_bones")
+    layer = po.PoseOptLayer(kps, bones, T("rest_pose"), use_cache=True)
+    a = layer(FX["idxs"])
+    with torch.no_grad():
+        layer.pelvis += 1.0
+    assert torch.equal(layer(FX["idxs"])[0], a[0])                               # served from the (stale) cache
+    layer.update_cache()
+    assert float((layer(FX["idxs"])[0] - a[0] - 1.0).abs().max()) < 1e-6
+    layer.double()                                                                # _apply refreshes the cache
+    assert layer(FX["idxs"])[0].dtype == torch.float64
+    # several rest poses, chosen per frame (pose_opt.py:256-262)
+    rest2 = torch.cat([T("rest_pose"), T("rest_pose") * 1.1], 0)
+    multi = po.PoseOptLayer(kps, bones, rest2, rest_pose_idxs=np.array([0, 1, 0, 1, 0, 1, 0]))
+    k = multi(np.array([1, 2]))[0]
+    one = po.PoseOptLayer(kps, bones, T("rest_pose") * 1.1)(np.array([1]))[0]
+    assert float((k[0] - one[0]).abs().max()) < 1e-6
+    assert float((k[1] - po.PoseOptLayer(kps, bones, T("rest_pose"))(np.array([2]))[0][0]).abs().max()) < 1e-6
