@@ -171,4 +171,6 @@ def test_entry_points_validate_arguments_without_touching_the_gpu():
     assert lib.danbo_composite_resample(N, 8, 16, 32, 16, N, N, N, N, 1.0, N, N, N, N, N, N, N, N, N, N, N, 1, N) < 0   # no u_vals / u_rand
     assert lib.danbo_merge_composite(N, 8, 16, 128, 64, N, N, N, N, N, N, N, 1.0, N, N, N, N, N, N, N, N, N, N, N) < 0
     assert lib.danbo_graph_net_fwd(N, 4, N, N, N, N) < 0
+    assert lib.danbo_pack_agg_frags(N, N, N) < 0                                                             # no table
+    assert lib.danbo_agg_frag_bytes() == 4 * 24 * (2 * 4 * 32 * 2 + 2 * 2 * 4 * 32 * 2)                     # W0 + W1 fragments
     assert lib.danbo_train_loss(N, N, N, N, N, N, 1.0, 1, 16, 0, 1.0, 1.0, N, N, N, N, 0, 0.0, N, N, 0.0, N, N, N, N, N, N, N, N) < 0
