@@ -192,6 +192,8 @@ class TrainStep:
         self.popt = popt_kwargs if (popt_kwargs and popt_kwargs.get("popt_layer") is not None) else None
         self.pose_optimizer = pose_optimizer
         self.last_stats = {}
+        self.n_steps = 0                        # optimizer steps taken (the `step` of Adam's state; restored by resume())
+        self.lrate = float(args.lrate)
         if self.popt is not None:
             if graph:
                 raise NotImplementedError("graph capture of a training step with a pose layer is not implemented")
@@ -232,8 +234,11 @@ class TrainStep:
             if self.world > 1:
                 self.bucket.allreduce(average=True)
                 self._optimizer_step()
+            self._after_step()
             return out["loss"], out
-        return self._step(batch)
+        out = self._step(batch)
+        self._after_step()
+        return out
 
     def _step(self, batch):
         loss, preds = self._fwd_bwd(batch)
@@ -255,7 +260,34 @@ class TrainStep:
             if self.pose_optimizer is not None and ckpt.get("pose_optimizer_state_dict") is not None:
                 self.pose_optimizer.load_state_dict(ckpt["pose_optimizer_state_dict"])
         self.caster._packed_key = None
+        sd = ckpt.get("optimizer_state_dict")
+        if sd is not None and sd.get("state"):
+            self.n_steps = int(max(float(st["step"]) for st in sd["state"].values()))
+            self.lrate = None                   # force the rate of the resumed step count at the next iteration
         return int(ckpt.get("global_step", 0))
+
+    def decayed_lrate(self):
+        """decay_optimizer_lrate (core/trainer.py:189-200): lrate * rate ** ((steps // decay_unit) / lrate_decay)."""
+        a = self.args
+        decay, unit = getattr(a, "lrate_decay", None), int(getattr(a, "decay_unit", 1000))
+        if not decay:
+            return float(a.lrate)
+        return float(a.lrate) * float(getattr(a, "lrate_decay_rate", 0.1)) ** ((self.n_steps // unit) / decay)
+
+    def _after_step(self):
+        """Steps 4-5 of train_batch (core/trainer.py:286-294): learning-rate decay and the encoders' schedules."""
+        self.n_steps += 1
+        new = self.decayed_lrate()
+        if new != self.lrate:                   # a staircase in units of decay_unit steps: rarely changes
+            self.lrate = new
+            if hasattr(self.optimizer, "set_lr"):
+                self.optimizer.set_lr(new)      # device scalar: also seen by a captured graph
+            else:
+                for g in self.optimizer.param_groups:
+                    g["lr"] = new
+        update = getattr(self.caster, "update_embed_fns", None)
+        if update is not None and not getattr(self.args, "finetune", False):
+            update(self.n_steps, self.args)
 
     def _optimizer_step(self):
         self.optimizer.step()

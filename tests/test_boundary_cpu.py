@@ -149,3 +149,57 @@ def test_flat_adam_state_is_interchangeable_with_torch_adam(tmp_path):
     assert set(ck) == {"global_step", "optimizer_state_dict", "poseopt_layer_state_dict", "pose_optimizer_state_dict",
                        "poseopt_anchors", "network_fn_state_dict", "network_fine_state_dict"}
     assert ck["global_step"] == 10 and ck["poseopt_layer_state_dict"] is None
+
+
+def test_train_step_learning_rate_schedule_and_resume(tmp_path):
+    """Steps 4-5 of train_batch (core/trainer.py:286-294) on a stand-in caster: the rate follows decay_optimizer_lrate
+    (:189-200) in units of decay_unit optimizer steps, the encoders' schedule hook is called, and a checkpoint written by
+    `TrainStep.save` resumes at the same step count and rate."""
+    import types
+    import torch
+    from danbo_b200 import training
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.full((3,), 0.5))
+
+    class Caster(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.network = Net()
+            self.calls = []
+
+        def update_embed_fns(self, step, args):
+            self.calls.append(step)
+
+        def state_dict(self, *a, **k):
+            return {"network_fn_state_dict": self.network.state_dict(), "network_fine_state_dict": self.network.state_dict()}
+
+        def forward(self, ray_batch, **kw):
+            rgb = torch.sigmoid(ray_batch[:, :3] * self.network.w)
+            return {"rgb_map": rgb, "acc_map": torch.sigmoid(ray_batch[:, 3])}
+
+    args = types.SimpleNamespace(lrate=1e-2, lrate_decay=4, lrate_decay_rate=0.1, decay_unit=3, loss_fn="L1",
+                                 agg_type="sigmoid", N_samples=8, N_importance=4, perturb=1.0, raw_noise_std=0.,
+                                 use_background=False, opt_vol_scale=False)
+    batch = {"ray_batch": torch.randn(6, 11), "kp_batch": None, "skts": None, "cyls": None, "bones": None, "cams": None,
+             "N_uniques": 1, "target_s": torch.full((6, 3), 0.3)}
+    caster = Caster()
+    step = training.TrainStep(caster, args)
+    rates = []
+    for _ in range(7):
+        step(batch)
+        rates.append(step.optimizer.param_groups[0]["lr"])
+    want = [1e-2 * 0.1 ** (((i + 1) // 3) / 4) for i in range(7)]          # rate in force after optimizer step i + 1
+    assert all(abs(a - b) < 1e-12 for a, b in zip(rates, want)), (rates, want)
+    assert caster.calls == list(range(1, 8))
+    path = os.path.join(tmp_path, "ck.tar")
+    step.save(path, 7)
+    caster2 = Caster()
+    caster2.network.load_state_dict(torch.load(path, weights_only=False)["network_fn_state_dict"])
+    step2 = training.TrainStep(caster2, args)
+    assert step2.resume(torch.load(path, weights_only=False)) == 7 and step2.n_steps == 7
+    step(batch), step2(batch)
+    assert torch.equal(caster.network.w, caster2.network.w)                 # same moments, same rate, same update
+    assert step2.optimizer.param_groups[0]["lr"] == step.optimizer.param_groups[0]["lr"]
