@@ -285,6 +285,15 @@ class TrainStep:
             else:
                 for g in self.optimizer.param_groups:
                     g["lr"] = new
+        if self.popt is not None and self.pose_optimizer is not None:
+            # update_pose_opt_params (core/pose_opt.py:454-463): continuous decay in units of decay * unit steps
+            a = self.args
+            rate = float(getattr(a, "opt_pose_decay_rate", 1.0))
+            if rate != 1.0:
+                steps = float(getattr(a, "opt_pose_lrate_decay", 250)) * float(getattr(a, "opt_pose_decay_unit", 400))
+                lr = float(getattr(a, "opt_pose_lrate", 5e-4)) * rate ** (self.n_steps / steps)
+                for g in self.pose_optimizer.param_groups:
+                    g["lr"] = lr
         update = getattr(self.caster, "update_embed_fns", None)
         if update is not None and not getattr(self.args, "finetune", False):
             update(self.n_steps, self.args)
