@@ -189,6 +189,35 @@ class RayFeed:
         self.last_idxs = (image_idxs, pix)
         return batch
 
+    def prefetch(self, generator=None):
+        """`next_batch` one iteration ahead on a side stream (CUDA arrays only; plain `next_batch` otherwise): the ~25
+        small launches of a draw overlap the previous training iteration instead of preceding the next one - the role
+        the reference gives its DataLoader workers (run_nerf.py:596-600).  The returned batch is safe to use on the
+        caller's current stream."""
+        if self.device.type != "cuda":
+            return self.next_batch(generator)
+        cur = torch.cuda.current_stream(self.device)
+        if getattr(self, "_side", None) is None:
+            self._side, self._pending = torch.cuda.Stream(device=self.device), None
+
+        def produce():
+            self._side.wait_stream(cur)                       # the arrays (and a generator's state) as the caller left them
+            with torch.cuda.stream(self._side):
+                b = self.next_batch(generator)
+                ev = torch.cuda.Event()
+                ev.record(self._side)
+            return b, ev, self.last_idxs
+        if self._pending is None:
+            self._pending = produce()
+        batch, ev, idxs = self._pending
+        cur.wait_event(ev)
+        for v in batch.values():
+            if torch.is_tensor(v):
+                v.record_stream(cur)                          # allocated on the side stream, consumed on the caller's
+        self._pending = produce()
+        self.last_idxs = idxs
+        return batch
+
     # ---- the reference's HDF5 keys (dataset.py:155-205, process_spin.py:234-297) ---------------------------------
     @classmethod
     def from_arrays(cls, d, near, far, **kw):

@@ -20,5 +20,6 @@ DANBO_PAIR_LOGITS=mma python bench.py --steps 10 --warmup 3 > gpurun_out/r2a_ben
 DANBO_BLOCK_STREAMS=2 python bench.py --steps 10 --warmup 3 > gpurun_out/r2a_bench_streams2.json 2> gpurun_out/r2a_bench_streams2.err
 # 5. training with the data feed in the loop, then with the pose layer
 python scripts/train_feed.py --iters 100 --graph > gpurun_out/r2a_train_feed.log 2>&1
+python scripts/train_feed.py --iters 100 --graph --prefetch >> gpurun_out/r2a_train_feed.log 2>&1
 python scripts/train_feed.py --iters 100 --opt_pose >> gpurun_out/r2a_train_feed.log 2>&1
 tail -3 gpurun_out/r2a_gpu_verified.log gpurun_out/r2a_gpu_unverified.log

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--opt_pose", action="store_true")
     ap.add_argument("--graph", action="store_true", help="replay the iteration from a CUDA graph (not with --opt_pose)")
+    ap.add_argument("--prefetch", action="store_true", help="draw the next batch on a side stream during the iteration")
     a = ap.parse_args()
     rank, world, local = parallel.init_distributed() if "RANK" in os.environ else (0, 1, 0)
     dev = torch.device("cuda", local)
@@ -45,20 +46,21 @@ def main():
     step = training.TrainStep(caster, args, world_size=world, graph=a.graph and not a.opt_pose, popt_kwargs=popt_kw,
                               pose_optimizer=pose_optimizer)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    draw = feed.prefetch if a.prefetch else feed.next_batch
     for _ in range(5):
-        loss, _ = step(feed.next_batch(gen))
+        loss, _ = step(draw(gen))
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.iters):
-        loss, _ = step(feed.next_batch(gen))
+        loss, _ = step(draw(gen))
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.iters
     if rank == 0:
         print(f"{1e3 / ms:.1f} it/s  {ms:.3f} ms/iter (device)  {(time.perf_counter() - t0) * 1e3 / a.iters:.3f} ms/iter (wall)  "
-              f"loss {float(loss):.4f}  world {world}  opt_pose {a.opt_pose}  graph {a.graph and not a.opt_pose}")
+              f"loss {float(loss):.4f}  world {world}  opt_pose {a.opt_pose}  graph {a.graph and not a.opt_pose}  prefetch {a.prefetch}")
 
 
 if __name__ == "__main__":

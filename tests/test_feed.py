@@ -205,3 +205,12 @@ def test_live_reference_other_draws():
         assert ("bgs" in b) == (not drop_bg)
         if not drop_bg:
             np.testing.assert_array_equal(b["bgs"].numpy(), ref["bgs"])
+
+
+def test_prefetch_on_the_cpu_is_next_batch():
+    a = fd.synthetic_feed(n_images=6, H=12, W=12, N_rand=3 * 5, N_sample_images=3, seed=2, perturb_bg=False)
+    b = fd.synthetic_feed(n_images=6, H=12, W=12, N_rand=3 * 5, N_sample_images=3, seed=2, perturb_bg=False)
+    ga, gb = torch.Generator().manual_seed(4), torch.Generator().manual_seed(4)
+    for _ in range(3):
+        x, y = a.prefetch(ga), b.next_batch(gb)
+        assert all(torch.equal(x[k], y[k]) for k in x if torch.is_tensor(x[k]))
