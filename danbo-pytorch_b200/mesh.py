@@ -198,6 +198,37 @@ def write_png(path, img):
                  + chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))
 
 
+def write_video(path, frames, fps=14):
+    """(N,H,W,3) uint8 RGB frames -> mp4 (imageio.mimwrite of run_render.py:1348), through OpenCV's writer."""
+    try:
+        import cv2
+    except ImportError as e:                               # no silent skip: the caller asked for a file
+        raise RuntimeError("write_video needs OpenCV (cv2), the only video encoder in this image") from e
+    a = torch.as_tensor(frames).detach().cpu().numpy() if torch.is_tensor(frames) else np.asarray(frames)
+    if a.dtype != np.uint8 or a.ndim != 4 or a.shape[-1] != 3:
+        raise ValueError("write_video takes (N,H,W,3) uint8 frames")
+    w = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"mp4v"), float(fps), (a.shape[2], a.shape[1]))
+    if not w.isOpened():
+        raise RuntimeError(f"cannot open {path} for writing")
+    for f in a:
+        w.write(np.ascontiguousarray(f[..., ::-1]))        # OpenCV takes BGR
+    w.release()
+
+
+def save_renders(basedir, rgbs, accs, fps=14):
+    """run_render.py:1332-1348 without the skeleton overlay: float images in [0,1] -> image/{i:05d}.png,
+    acc/{i:05d}.png and render_rgb.mp4."""
+    import os
+    to8 = lambda x: (torch.as_tensor(x).detach().float().cpu().clamp(0, 1) * 255).to(torch.uint8).numpy()
+    rgbs, accs = to8(rgbs), to8(accs)
+    for d in ("image", "acc"):
+        os.makedirs(os.path.join(basedir, d), exist_ok=True)
+    for i, (rgb, acc) in enumerate(zip(rgbs, accs)):
+        write_png(os.path.join(basedir, "image", f"{i:05d}.png"), rgb)
+        write_png(os.path.join(basedir, "acc", f"{i:05d}.png"), acc.reshape(acc.shape[0], acc.shape[1]))
+    write_video(os.path.join(basedir, "render_rgb.mp4"), rgbs, fps=fps)
+
+
 @torch.no_grad()
 def render_mesh(ray_caster, kps, skts, bones, radius=1.80, res=255, threshold=10., out_dir=None, preproc_kwargs=None):
     """run_render.py:1266-1281: per pose, the (res+1)^3 raw-density lattice (`fwd_type='mesh'`), relu, marching cubes at

@@ -153,3 +153,23 @@ def test_render_mesh_on_a_stand_in_caster(tmp_path):
     # sigma = 10  <=>  r = 1 - 15/40 = 0.625 world units = 0.625 / 3.6 of the unit cube
     r = ((v * 1.0).norm(dim=-1))
     assert float((r - 0.625 / 3.6).abs().max()) < 0.01
+
+
+def test_save_renders_writes_pngs_and_video(tmp_path):
+    cv2 = pytest.importorskip("cv2")
+    from PIL import Image
+    rng = np.random.RandomState(1)
+    rgbs = torch.tensor(rng.rand(5, 32, 48, 3).astype(np.float32))
+    accs = torch.tensor(rng.rand(5, 32, 48).astype(np.float32))
+    mesh.save_renders(str(tmp_path), rgbs, accs, fps=10)
+    img = np.asarray(Image.open(os.path.join(tmp_path, "image", "00003.png")))
+    np.testing.assert_array_equal(img, (rgbs[3].clamp(0, 1) * 255).to(torch.uint8).numpy())
+    acc = np.asarray(Image.open(os.path.join(tmp_path, "acc", "00000.png")))
+    assert acc.shape == (32, 48)
+    cap = cv2.VideoCapture(os.path.join(tmp_path, "render_rgb.mp4"))
+    n = 0
+    while cap.read()[0]:
+        n += 1
+    assert n == 5 and abs(cap.get(cv2.CAP_PROP_FPS) - 10) < 0.5
+    with pytest.raises(ValueError):
+        mesh.write_video(os.path.join(tmp_path, "x.mp4"), np.zeros((2, 4, 4, 3), np.float32))
