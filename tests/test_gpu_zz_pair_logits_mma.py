@@ -1,5 +1,6 @@
-"""The tensor-core aggregation net (csrc/field_mma.cu, `FieldConsts(pair_logits_impl="mma")`) against the fp32 FFMA
-kernel and the oracle (run with -m gpu).
+"""GPU checks of everything else that was written without GPU access at the end of round 1 (run with -m gpu):
+the tensor-core aggregation net (csrc/field_mma.cu, `FieldConsts(pair_logits_impl="mma")`) against the fp32 FFMA kernel
+and the oracle, the stream-pipelined ray blocks (`raycaster.BLOCK_STREAMS`), and mesh extraction on the device.
 
 STATUS: written at the end of round 1 after the round's GPU minutes were spent; the kernel compiles for sm_100a (137
 registers, no spills, 72 HMMA.16816 per instantiation) and its index arithmetic is checked on the CPU by
