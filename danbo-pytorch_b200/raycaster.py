@@ -224,15 +224,8 @@ class RayCaster(nn.Module):
         outs = []
         # internal launches: any split works for a single pose; with several poses a block holds whole poses
         G = pose_skts.shape[0]
-        block = MAX_RAYS_PER_LAUNCH if G == 1 else max((MAX_RAYS_PER_LAUNCH // skip) * skip, skip)
-        # (only with nanmean_chunk: blocks are then whole near/far fill chunks, so the split cannot change any pixel)
-        n_streams = self.block_streams if (G == 1 and not training and _stages is None and nanmean_chunk
-                                           and N >= 32768) else 1
-        if n_streams > 1:
-            unit = int(nanmean_chunk)
-            block = min(block, -(-(-(-N // n_streams)) // unit) * unit)     # ceil(N / n_streams) rounded up to the unit
-        if nanmean_chunk:
-            block = max((block // int(nanmean_chunk)) * int(nanmean_chunk), int(nanmean_chunk)) if G == 1 else block
+        block, n_streams = self._plan_blocks(N, G, skip, nanmean_chunk,
+                                             self.block_streams if (not training and _stages is None) else 1)
         cur = torch.cuda.current_stream(dev) if n_streams > 1 else None
         while len(self._side_streams) < (n_streams if n_streams > 1 else 0):
             self._side_streams.append(torch.cuda.Stream(device=dev))
@@ -260,6 +253,21 @@ class RayCaster(nn.Module):
         if len(outs) == 1:
             return outs[0]
         return {k: torch.cat([o[k] for o in outs], 0) for k in outs[0]}
+
+    @staticmethod
+    def _plan_blocks(N, G, skip, nanmean_chunk, want_streams):
+        """-> (rays per internal launch block, streams to issue the blocks on).  One pose: any split gives the same
+        pixels as long as blocks are whole near/far fill chunks (F8); several poses: a block holds whole poses.  More than
+        one stream only for a single pose, with `nanmean_chunk` given (so the split cannot change a pixel) and a call
+        large enough to be worth it."""
+        block = MAX_RAYS_PER_LAUNCH if G == 1 else max((MAX_RAYS_PER_LAUNCH // skip) * skip, skip)
+        n_streams = int(want_streams) if (G == 1 and nanmean_chunk and N >= 32768 and want_streams > 1) else 1
+        if n_streams > 1:
+            unit = int(nanmean_chunk)
+            block = min(block, -(-(-(-N // n_streams)) // unit) * unit)     # ceil(N / n_streams) rounded up to the unit
+        if nanmean_chunk and G == 1:
+            block = max((block // int(nanmean_chunk)) * int(nanmean_chunk), int(nanmean_chunk))
+        return block, n_streams
 
     def _render_block(self, rays, ray0, skip, pose_skts, pose_cyls, vol, cam_idx, codes, consts, packed, S_c, S_f, B,
                       raw_noise_std, perturb, training, nanmean_chunk, rand, stages, keep=None, lindisp=False):

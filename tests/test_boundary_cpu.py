@@ -203,3 +203,25 @@ def test_train_step_learning_rate_schedule_and_resume(tmp_path):
     step(batch), step2(batch)
     assert torch.equal(caster.network.w, caster2.network.w)                 # same moments, same rate, same update
     assert step2.optimizer.param_groups[0]["lr"] == step.optimizer.param_groups[0]["lr"]
+
+
+def test_internal_block_plan():
+    """`RayCaster._plan_blocks`: how a call is cut into launch blocks (and, opt-in, streams)."""
+    from danbo_b200.raycaster import RayCaster, MAX_RAYS_PER_LAUNCH
+    plan = RayCaster._plan_blocks
+    # one stream: the measured behaviour - one block per 262 144 rays, whole chunks when a fill chunk is given
+    assert plan(261121, 1, 261121, 4096, 1) == (MAX_RAYS_PER_LAUNCH, 1)
+    assert plan(261121, 1, 261121, None, 1) == (MAX_RAYS_PER_LAUNCH, 1)
+    assert plan(1 << 20, 1, 1 << 20, 3000, 1) == ((MAX_RAYS_PER_LAUNCH // 3000) * 3000, 1)
+    # several poses: whole poses per block, never more than one stream
+    assert plan(16 * 192, 16, 192, None, 2) == ((MAX_RAYS_PER_LAUNCH // 192) * 192, 1)
+    assert plan(400000, 4, 100000, 4096, 3) == (200000, 1)
+    # streams: only with a fill chunk and a big single-pose call; blocks are whole chunks and cover the call
+    assert plan(261121, 1, 261121, None, 2)[1] == 1 and plan(20000, 1, 20000, 4096, 2)[1] == 1
+    for N in (32768, 40000, 261121, 1000000):
+        for ns in (2, 3):
+            for chunk in (1024, 4096):
+                block, s = plan(N, 1, N, chunk, ns)
+                assert s == ns and block % chunk == 0 and 0 < block <= MAX_RAYS_PER_LAUNCH
+                n_blocks = -(-N // block)
+                assert n_blocks >= min(ns, -(-N // chunk)) and (n_blocks - 1) * block < N
