@@ -74,3 +74,57 @@ def test_live_reference_other_cameras():
         ro, rd, idx = render.rays_in_box(64, 72, 50.0, c2ws[i], cyls[0], "cpu")
         np.testing.assert_array_equal(idx.numpy(), valid[i].numpy())
         np.testing.assert_allclose(rd.numpy(), rays[i][1].numpy(), rtol=0, atol=3e-7)
+
+
+class _Recorder:
+    """Stand-in ray caster: records what it is called with and returns per-ray tensors derived from the rays."""
+
+    def __init__(self):
+        self.calls = []
+
+    def __call__(self, ray_batch, **kw):
+        self.calls.append((ray_batch.clone(), {k: (v.clone() if torch.is_tensor(v) else v) for k, v in kw.items()}))
+        return {"rgb_map": ray_batch[:, 3:6] * 2, "acc_map": ray_batch[:, 6], "T_i": ray_batch[:, None, :4].expand(-1, 5, -1)}
+
+
+def _render_inputs(n=10):
+    g = torch.Generator().manual_seed(0)
+    rays = (torch.randn(n, 3, generator=g), torch.randn(n, 3, generator=g))
+    kw = dict(kp_batch=torch.randn(n, 24, 3, generator=g), skts=torch.randn(n, 24, 4, 4, generator=g),
+              cams=torch.arange(n)[:, None], N_uniques=1, perturb=0.)
+    return rays, kw
+
+
+def test_render_chunks_like_batchify_rays():
+    """`render(single_call=False)` = the reference's loop: every tensor kwarg sliced per chunk, results concatenated;
+    `single_call=True` hands the whole batch over once with nanmean_chunk = chunk."""
+    rays, kw = _render_inputs()
+    a, b = _Recorder(), _Recorder()
+    ra = render.render(8, 8, 10., chunk=4, rays=rays, near=1., far=5., use_viewdirs=True, single_call=False, ray_caster=a, **kw)
+    rb = render.render(8, 8, 10., chunk=4, rays=rays, near=1., far=5., use_viewdirs=True, single_call=True, ray_caster=b, **kw)
+    assert [c[0].shape[0] for c in a.calls] == [4, 4, 2] and len(b.calls) == 1 and b.calls[0][1]["nanmean_chunk"] == 4
+    full = torch.cat([c[0] for c in a.calls], 0)
+    assert torch.equal(full, b.calls[0][0]) and full.shape == (10, 11)
+    assert torch.equal(full[:, 6], torch.ones(10)) and torch.equal(full[:, 7], torch.full((10,), 5.))
+    assert float((full[:, 8:].norm(dim=-1) - 1).abs().max()) < 1e-6
+    assert torch.equal(a.calls[1][1]["skts"], kw["skts"][4:8]) and a.calls[1][1]["N_uniques"] == 1
+    for k in ra:
+        assert torch.equal(ra[k], rb[k])
+    assert ra["rgb_map"].shape == (10, 3) and ra["T_i"].shape == (10, 5, 4)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/core"), reason="authoring container only")
+def test_render_hands_the_caster_what_the_reference_does():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_harness
+    ref_harness._imports()
+    import core.trainer as tr
+    rays, kw = _render_inputs()
+    a, b = _Recorder(), _Recorder()
+    want = tr.render(8, 8, 10., chunk=4, rays=rays, near=1., far=5., use_viewdirs=True, ray_caster=a, **kw)
+    got = render.render(8, 8, 10., chunk=4, rays=rays, near=1., far=5., use_viewdirs=True, single_call=False, ray_caster=b, **kw)
+    assert len(a.calls) == len(b.calls) == 3
+    for (ra, ka), (rb, kb) in zip(a.calls, b.calls):
+        assert torch.equal(ra, rb) and set(ka) == set(kb)
+        assert all(torch.equal(ka[k], kb[k]) if torch.is_tensor(ka[k]) else ka[k] == kb[k] for k in ka)
+    assert set(want) == set(got) and all(torch.equal(want[k], got[k]) for k in want)
