@@ -249,3 +249,27 @@ def test_compute_loss_on_the_references_outputs(name):
         assert abs(float(v) - float(fx["loss." + k])) <= 2e-6 * max(1e-3, abs(float(fx["loss." + k]))), (k, float(v))
     ref_terms = {k[5:] for k in fx if k.startswith("loss.")} - {"total", "total_loss"}
     assert ref_terms == set(terms), (ref_terms, set(terms))
+
+
+@pytest.mark.parametrize("name", ["render_fast", "render_base"])
+def test_graph_net_module_matches_reference_volumes(name):
+    """`DanboField.bone_volumes` as PyTorch ops (the parameter owner, the twin the graph-net kernels are tested against
+    on the GPU, and the route a pose with a gradient takes) against the reference's own bone volumes; a rot6d pose
+    (6 numbers per joint, as a rot6d pose layer hands it over, encoders.py:873-877) gives the same volumes."""
+    from danbo_b200 import networks, pose_opt as po
+    from util import load_fixture
+    fx = load_fixture(name)
+    net = networks.DanboField(n_framecodes=8, skel_profile=sk.skeleton_profile(syn.rest_pose()), opt_scale=True)
+    net.load_state_dict(syn.synthetic_params(int(fx.get("weight_seed", 0))))
+    bones = fx["pose_bones"].reshape(1, 24, 3)
+    with torch.no_grad():
+        vol = net.bone_volumes(bones)
+        rot6d = po.rot_to_rot6d(po.axisang_to_rot(bones))
+        vol6 = net.bone_volumes(rot6d)
+    want = fx["st.vol.0"].reshape(1, 24, 240)
+    assert float((vol - want).abs().max()) <= 2e-5 * float(want.abs().max())
+    assert float((vol6 - vol).abs().max()) <= 1e-5 * float(want.abs().max())
+    # and it is differentiable with respect to the pose
+    b = bones.clone().requires_grad_(True)
+    net.bone_volumes(b).square().sum().backward()
+    assert b.grad is not None and float(b.grad.abs().max()) > 0
