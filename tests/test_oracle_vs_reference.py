@@ -85,3 +85,25 @@ def test_anerf_oracle_matches_live_reference():
         err = (got[k] - want[k]).abs().reshape(N, -1).max(-1).values
         # the 64x-amplified top octave of the cutoff PE moves raw by ~1e-4; a ray whose importance samples flip a bin moves more
         assert float((err <= 2e-4).float().mean()) >= 0.95, (k, float(err.max()))
+
+
+@pytest.mark.parametrize("config", ["h36m_zju/danbo_base.txt", "h36m_zju/danbo_fast.txt", "h36m_zju/anerf_base.txt",
+                                    "h36m_zju/anerf_h.txt"])
+def test_flag_defaults_and_config_reader_match_the_reference_parser(config):
+    """`config.DEFAULTS` + `read_config_file` against the reference's own argparse (run_nerf.py:186-572) on the shipped
+    configs: every flag this path looks at must come out with the reference's value; the presets are those configs."""
+    import danbo_b200 as db
+    from danbo_b200 import config as cfg, raycaster, anerf
+    want = vars(rh.parse_args(config, []))
+    got = vars(db.make_args(config_file=os.path.join(rh.REF, "configs", config)))
+    skip = {"expname", "basedir", "no_reload"}                      # set by the harness itself
+    bad = {k: (got[k], want[k]) for k in cfg.DEFAULTS if k in want and k not in skip and got[k] != want[k]}
+    assert not bad, bad
+    args = db.make_args(config_file=os.path.join(rh.REF, "configs", config), no_reload=True)
+    (anerf.check_anerf_args if args.nerf_type == "nerf" else raycaster.check_args)(args)       # the path accepts them
+    preset = {"h36m_zju/danbo_base.txt": "danbo_base", "h36m_zju/danbo_fast.txt": "danbo_fast",
+              "h36m_zju/anerf_base.txt": "anerf_base"}.get(config)
+    if preset:
+        p = vars(db.make_args(preset))
+        bad = {k: (p[k], want[k]) for k in cfg.DEFAULTS if k in want and k not in skip and p[k] != want[k]}
+        assert not bad, bad
