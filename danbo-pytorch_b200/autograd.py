@@ -94,7 +94,7 @@ class _RenderBlock(torch.autograd.Function):
                 dX = K.mlp_backward(P, G, d_raw, act, fo, sv, d_ray_bias)
             K.field_agg_bwd(rays, S, z, mask, act, k["p_skts"], k["p_vol"], k["skip"], k["consts"], fo, dX, gl, agg_grads,
                             d_skts=d_skts)
-        K.ray_bias_bwd(rays, k["cam_idx"], k["codes"], P["views_linears.0.weight"], d_ray_bias,
+        K.ray_bias_bwd(k["rays_v"], k["cam_idx"], k["codes"], P["views_linears.0.weight"], d_ray_bias,
                        G["views_linears.0.weight"], G["views_linears.0.bias"], G["framecodes.codes.weight"])
         ctx.keep = None
         if in_place:
@@ -104,8 +104,14 @@ class _RenderBlock(torch.autograd.Function):
 
 def render_block_with_grad(caster, rays, skip, pose_skts, pose_cyls, vol, cam_idx, codes, consts, packed, S_c, S_f, B,
                            raw_noise_std, perturb, nanmean_chunk, rand, stages, lindisp=False):
+    if not getattr(caster.network, "opt_framecode", True):
+        raise NotImplementedError("training without frame codes (opt_framecode=False, configs/surreal) is not implemented: "
+                                  "the backward kernels write the view layer's gradient in its 411-input layout")
     named = dict(caster.network.named_parameters())
     params = [named[n] for n in PARAM_NAMES]
+    if pose_skts.requires_grad and getattr(caster, "view_mode", "world") != "world":
+        raise NotImplementedError("pose gradients with root-local view directions (perfcap configs): the view branch's "
+                                  "dependence on the root rotation is not differentiated")
     cfg = dict(rays=rays, skip=skip, pose_cyls=pose_cyls, cam_idx=cam_idx, codes=codes, consts=consts,
                packed=packed, S_c=S_c, S_f=S_f, B=B, raw_noise_std=raw_noise_std, perturb=perturb,
                nanmean_chunk=nanmean_chunk, rand=rand, stages=stages, lindisp=lindisp)

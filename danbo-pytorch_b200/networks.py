@@ -161,7 +161,7 @@ class DanboField(nn.Module):
 
     def __init__(self, n_framecodes=8, W=256, D=8, view_W=128, node_W=128, agg_W=32, voxel_feat=5, voxel_res=16,
                  multires_voxel=6, multires_graph=5, multires_views=4, framecode_ch=128, skel_profile=None,
-                 opt_scale=True, agg_type="sigmoid", mask_vol_prob=True):
+                 opt_scale=True, agg_type="sigmoid", mask_vol_prob=True, opt_framecode=True):
         super().__init__()
         if D != 8 or W != 256 or view_W != 128 or agg_W != 32 or voxel_feat != 5 or voxel_res != 16 \
                 or multires_voxel != 6 or framecode_ch != 128 or multires_views != 4:
@@ -183,10 +183,11 @@ class DanboField(nn.Module):
             layers.append(nn.Linear(W + x_ch, W) if i == 4 else nn.Linear(W, W))
         self.pts_linears = nn.ModuleList(layers)
         self.alpha_linear = nn.Linear(W, 1)
-        self.views_linears = nn.ModuleList([nn.Linear(v_ch + framecode_ch + 2 * view_W, view_W)])
+        self.opt_framecode = bool(opt_framecode)        # False (configs/surreal): no per-frame code in the view layer
+        self.views_linears = nn.ModuleList([nn.Linear(v_ch + (framecode_ch if opt_framecode else 0) + 2 * view_W, view_W)])
         self.feature_linear = nn.Linear(W, 2 * view_W)
         self.rgb_linear = nn.Linear(view_W, 3)
-        self.framecodes = Optcodes(n_framecodes, framecode_ch)
+        self.framecodes = Optcodes(n_framecodes, framecode_ch) if opt_framecode else None
         self.graph_net = GraphNet(6 * (1 + 2 * multires_graph), node_W, voxel_res, voxel_feat, skel_profile,
                                   opt_scale=opt_scale)
         self.prob_linears = AggNet(voxel_feat * 3, agg_W)

@@ -10,7 +10,11 @@ J = 24
 
 
 def danbo_param_shapes(n_framecodes=8, W=256, view_W=128, node_W=128, agg_W=32, voxel_feat=5, voxel_res=16,
-                       multires_voxel=6, multires_graph=5, multires_views=4, framecode_ch=128):
+                       multires_voxel=6, multires_graph=5, multires_views=4, framecode_ch=128, opt_framecode=True):
+    """opt_framecode=False (configs/surreal/danbo_*.txt): no per-frame code - the view layer takes 256 + 27 inputs and
+    `framecodes.codes.weight` does not exist."""
+    if not opt_framecode:
+        framecode_ch = 0
     feat = voxel_feat * 3                       # FGNNcat: three axis lines concatenated
     x_ch = feat * (1 + 2 * multires_voxel)      # 195
     g_ch = 6 * (1 + 2 * multires_graph)         # 66
@@ -29,7 +33,8 @@ def danbo_param_shapes(n_framecodes=8, W=256, view_W=128, node_W=128, agg_W=32, 
     s["feature_linear.bias"] = (2 * view_W,)
     s["rgb_linear.weight"] = (3, view_W)
     s["rgb_linear.bias"] = (3,)
-    s["framecodes.codes.weight"] = (n_framecodes, framecode_ch)
+    if opt_framecode:
+        s["framecodes.codes.weight"] = (n_framecodes, framecode_ch)
     s["graph_net.axis_scale"] = (J, 3)
     for i, cin in ((0, g_ch), (1, node_W)):
         s[f"graph_net.layers.{i}.bias"] = (node_W,)

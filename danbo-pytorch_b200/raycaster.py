@@ -32,7 +32,7 @@ class RayCaster(nn.Module):
     _supports_fine_network = False        # a separate fine network (single_net=False): the A-NeRF caster only
 
     def __init__(self, network, network_fine=None, single_net=True, rest_poses=None, align_bones="align",
-                 skel_type=None, use_volume_near_far=False, **kwargs):
+                 skel_type=None, use_volume_near_far=False, view_mode="world", **kwargs):
         super().__init__()
         separate = (not single_net) and network_fine is not None and network_fine is not network
         if (not single_net or (network_fine is not None and network_fine is not network)) and not (
@@ -48,6 +48,9 @@ class RayCaster(nn.Module):
         self.skel_type = skel_type if skel_type is not None else sk.SMPLSkeleton
         self.align_bones = align_bones
         self.use_volume_near_far = bool(use_volume_near_far)
+        if view_mode not in ("world", "root_local"):
+            raise NotImplementedError(f"view_mode={view_mode!r}")
+        self.view_mode = view_mode                # what V1 encodes: rays_d as they are, or in the root joint's frame
         A, child = sk.bone_align_transforms(rest_poses)          # S0
         self.transforms = torch.from_numpy(A)[None]               # (1,24,4,4) like the reference attribute
         self.child_idxs = child
@@ -144,17 +147,42 @@ class RayCaster(nn.Module):
             self._packed = K.PackedMLP(self._device())
             self._packed_key = None
         if key != self._packed_key:
-            self._packed.pack({n: P[n] for n in names})
+            tensors = {n: P[n] for n in names}
+            if not getattr(net, "opt_framecode", True):
+                # no frame code: the kernels' view layer keeps its 411-input layout with zero weights (and zero codes,
+                # `_codes_with_mean`) in the code columns, which adds exact zeros
+                tensors["views_linears.0.weight"] = F.pad(P["views_linears.0.weight"].detach(), (0, 128))
+            self._packed.pack(tensors)
             self._packed_key = key
         return self._packed
 
     def _codes_with_mean(self):
+        if not getattr(self.network, "opt_framecode", True):
+            return torch.zeros(2, 128, device=self._device())
         w = self.network.framecodes.codes.weight.detach()
         return torch.cat([w, w.mean(0, keepdim=True)], 0).contiguous()
 
     @staticmethod
     def _unique(t, skip):
         return t[::skip].contiguous().float()
+
+    def _view_rays(self, rays, p_skts, skip):
+        """The rays whose direction columns V1 encodes.  "world" (ray_tr_type=world + view_type=identity, the h36m_zju
+        and surreal configs): the rays themselves.  "root_local" (ray_tr_type=root_local + view_type=relray, the perfcap
+        configs; RootLocalEncoder encoders.py:570-578, VecNormEncoder :774-795): a copy whose direction is rotated into
+        the root joint's frame of the ray's pose and normalised - a per-ray quantity, so the folded view layer
+        (`ray_bias`) takes it unchanged."""
+        if self.view_mode == "world":
+            return rays
+        n, G = rays.shape[0], p_skts.shape[0]
+        if G == 1:
+            d = rays[:, 3:6] @ p_skts[0, 0, :3, :3].t()
+        else:
+            pose = torch.clamp(torch.arange(n, device=rays.device) // skip, max=G - 1)
+            d = (p_skts[pose, 0, :3, :3] @ rays[:, 3:6, None])[..., 0]
+        out = rays[:, :8].clone()
+        out[:, 3:6] = F.normalize(d, dim=-1, p=2)
+        return out
 
     # ------------------------------------------------------------------------------------------------ render
     def render_rays(self, ray_batch, N_samples, kp_batch, skts=None, cyls=None, bones=None, cams=None,
@@ -174,8 +202,10 @@ class RayCaster(nn.Module):
                                       "numbers) are not implemented")
         if N_importance <= 0:
             raise NotImplementedError("N_importance must be > 0 (the reference itself requires it, SURVEY F10)")
-        if skts is None or bones is None or cyls is None or cams is None:
-            raise ValueError("skts, bones, cyls and cams are required")
+        if skts is None or bones is None or cyls is None:
+            raise ValueError("skts, bones and cyls are required")
+        if cams is None and getattr(self.network, "opt_framecode", True):
+            raise ValueError("cams are required (the field has per-frame codes)")
         pk = preproc_kwargs or {}
         if pk.get("density_fn", F.relu) is not F.relu:
             raise NotImplementedError("density_type other than 'relu' is not implemented")
@@ -194,7 +224,10 @@ class RayCaster(nn.Module):
         pose_skts = self._unique(skts, skip).to(dev, non_blocking=True)
         pose_bones = self._unique(bones, skip).to(dev, non_blocking=True)
         pose_cyls = self._unique(cyls, skip).to(dev, non_blocking=True)
-        cam_idx = cams.reshape(N, -1)[:, 0].to(dev, non_blocking=True).to(torch.int32).contiguous()
+        if cams is None or not getattr(self.network, "opt_framecode", True):
+            cam_idx = torch.zeros(N, device=dev, dtype=torch.int32)       # no frame codes: row 0 of the zero table
+        else:
+            cam_idx = cams.reshape(N, -1)[:, 0].to(dev, non_blocking=True).to(torch.int32).contiguous()
         return rays, pose_skts, pose_bones, pose_cyls, cam_idx, skip
 
     def _render_prepared(self, rays, pose_skts, pose_bones, pose_cyls, cam_idx, skip=1, N_samples=64, N_importance=16,
@@ -284,7 +317,8 @@ class RayCaster(nn.Module):
         seg = 0 if not nanmean_chunk else int(nanmean_chunk)
         near, far = K.nearfar(rays, p_cyls, p_skts, skip, consts.align, consts.axis_scale, seg_len=seg,
                               use_box=self.use_volume_near_far, bound=1.3)
-        rbias = K.ray_bias(rays, cam_idx, codes, packed)
+        rays_v = self._view_rays(rays, p_skts, skip)
+        rbias = K.ray_bias(rays_v, cam_idx, codes, packed)
         inv_B = 1.0 / B
         save = keep is not None
         # ---- coarse pass
@@ -325,7 +359,7 @@ class RayCaster(nn.Module):
             ret["confd"] = c1["confd"]
             ret["part_invalid"] = c1["part_invalid"]
         if save:
-            keep.update(dict(rays=rays, cam_idx=cam_idx, codes=codes, p_skts=p_skts, p_vol=p_vol, p0=p0, skip=skip,
+            keep.update(dict(rays=rays, rays_v=rays_v, cam_idx=cam_idx, codes=codes, p_skts=p_skts, p_vol=p_vol, p0=p0, skip=skip,
                              consts=consts, S_c=S_c, S_f=S_f, inv_B=inv_B, z0=z0, mask0=mask0, act0=act0, f0=f0, raw0=raw0,
                              sv0=sv0, noise0=noise0, z1=z1, mask1=mask1, act1=act1, f1=f1, raw1=raw1, sv1=sv1,
                              noise1=noise1, z_all=c0["z_all"], order=c0["order"]))
@@ -377,11 +411,11 @@ GraphCaster = RayCaster
 # ------------------------------------------------------------------------------------------------------ factory
 _SUPPORTED = {"nerf_type": ("danbo", "graph"), "gnn_backbone": ("FGNNcat",), "agg_backbone": ("vox_MIXGNN",),
               "agg_type": ("sigmoid", "softmax"), "align_bones": ("align",), "density_type": ("relu",),
-              "kp_dist_type": ("reldist",), "view_type": ("identity",), "ray_tr_type": ("world",),
+              "kp_dist_type": ("reldist",), "view_type": ("identity", "relray"), "ray_tr_type": ("world", "root_local"),
               "pts_tr_type": ("local",), "bone_type": ("Nope",), "graph_input_type": ("rot6d",)}
 _REQUIRED = {"netdepth": 8, "netwidth": 256, "agg_W": 32, "agg_D": 3, "node_W": 128, "gcn_D": 4, "gcn_fc_D": 1,
              "voxel_res": 16, "voxel_feat": 5, "multires_voxel": 6, "multires_graph": 5, "multires_views": 4,
-             "framecode_size": 128, "single_net": True, "opt_framecode": True, "use_viewdirs": True,
+             "framecode_size": 128, "single_net": True, "use_viewdirs": True,
              "mask_root": True, "attenuate_feat": True, "attenuate_invalid": False, "use_cutoff": False,
              "opt_posecode": False, "gnn_concat": False, "no_adj": False, "adj_self_one": False,
              "align_corners": False, "vol_cal_scale": True}
@@ -399,6 +433,10 @@ def check_args(args):
             raise NotImplementedError(f"{k}={v!r} is not implemented by danbo_b200 (kernels are built for {k}={want!r})")
     if getattr(args, "netwidth_view", None) not in (None, 128):
         raise NotImplementedError("netwidth_view must be None/128")
+    view = (getattr(args, "view_type", "identity"), getattr(args, "ray_tr_type", "world"))
+    if view not in (("identity", "world"), ("relray", "root_local")):
+        raise NotImplementedError(f"view_type / ray_tr_type = {view}: the shipped pairs are identity + world "
+                                  "(h36m_zju, surreal) and relray + root_local (perfcap)")
 
 
 def create_raycaster(args, data_attrs, device=None):
@@ -424,9 +462,11 @@ def create_raycaster(args, data_attrs, device=None):
                                     align_bones=args.align_bones, skel_type=skel_type)
     else:
         net = DanboField(n_framecodes=n_framecodes, skel_profile=profile, opt_scale=bool(getattr(args, "opt_vol_scale", True)),
-                         agg_type=args.agg_type, mask_vol_prob=bool(getattr(args, "mask_vol_prob", True)))
+                         agg_type=args.agg_type, mask_vol_prob=bool(getattr(args, "mask_vol_prob", True)),
+                         opt_framecode=bool(getattr(args, "opt_framecode", True)))
         caster = RayCaster(net, network_fine=net, single_net=True, rest_poses=rest_pose, align_bones=args.align_bones,
-                           skel_type=skel_type, use_volume_near_far=bool(getattr(args, "use_volume_near_far", False)))
+                           skel_type=skel_type, use_volume_near_far=bool(getattr(args, "use_volume_near_far", False)),
+                           view_mode="root_local" if getattr(args, "ray_tr_type", "world") == "root_local" else "world")
     caster.to(device)
     grad_vars = [p for p in net.parameters() if p.requires_grad]
     if caster.network_fine is not net:                                 # raycasters.py:188

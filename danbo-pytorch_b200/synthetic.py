@@ -175,7 +175,7 @@ def synth_state_dict(shapes, seed=0):
     return out
 
 
-def synthetic_params(seed=0, n_framecodes=8, rest=None):
+def synthetic_params(seed=0, n_framecodes=8, rest=None, opt_framecode=True):
     """Full parameter dict (reference state_dict names) for the DANBO field: synthetic weights plus the
     geometry-defined entries (tree adjacency buffers, initial per-bone half extents)."""
     from . import params as _params
@@ -186,4 +186,10 @@ def synthetic_params(seed=0, n_framecodes=8, rest=None):
     for name in _params.BUFFER_NAMES:
         P[name] = adj.clone()
     P["graph_net.axis_scale"] = sk.initial_axis_scale(sk.skeleton_profile(rest), base_scale=0.4)
-    return {k: P[k] for k in shapes}
+    P = {k: P[k] for k in shapes}
+    if not opt_framecode:
+        # the same weights without the frame-code part: the code columns are the last 128 inputs of the view layer
+        # ([feature ; view PE ; code], nerf.py:200-209), so existing fixtures' random streams are untouched
+        P.pop("framecodes.codes.weight")
+        P["views_linears.0.weight"] = P["views_linears.0.weight"][:, :-128].contiguous()
+    return P

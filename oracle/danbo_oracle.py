@@ -255,6 +255,8 @@ def agg_prob(a, invalid, agg_type="sigmoid", mask_vol_prob=True, eps=1e-7):
 # ----------------------------------------------------------------------------------------------------------
 def view_inputs(rays_d, cams, P, training, n_freq=4):
     """Per-ray (N,155): PE(un-normalised rays_d) (27) ++ frame code (128); mean code when eval and idx<0."""
+    if "framecodes.codes.weight" not in P:                   # opt_framecode=False (configs/surreal): no code (nerf.py:262-279)
+        return pe_embed(rays_d, n_freq)
     codes = P["framecodes.codes.weight"]
     if (not training) and cams.max() < 0:
         c = codes.mean(0, keepdim=True).expand(len(cams), -1)
@@ -349,7 +351,18 @@ def merge_sorted(coarse, fine, order):
 # ----------------------------------------------------------------------------------------------------------
 # whole path: core/raycasters.py:245-377 render_rays (single_net=True, N_importance>0)
 # ----------------------------------------------------------------------------------------------------------
-def field_eval(pts, rays_d, cams, skts, A, vol, P, rays_per_pose, training, agg_type="sigmoid"):
+def view_directions(rays_d, skts, view_mode="world"):
+    """What V1 encodes.  "world" (ray_tr_type=world, view_type=identity; h36m_zju and surreal configs): the un-normalised
+    rays_d.  "root_local" (ray_tr_type=root_local, view_type=relray; perfcap configs): the direction rotated into the
+    root joint's frame and normalised (RootLocalEncoder encoders.py:570-578, VecNormEncoder :774-795)."""
+    if view_mode == "world":
+        return rays_d
+    if view_mode == "root_local":
+        return F.normalize((skts[:, 0, :3, :3] @ rays_d[..., None])[..., 0], dim=-1, p=2)
+    raise NotImplementedError(view_mode)
+
+
+def field_eval(pts, rays_d, cams, skts, A, vol, P, rays_per_pose, training, agg_type="sigmoid", view_mode="world"):
     """T1..A3 + V1 + M1 for points (N,S,3) -> raw (N,S,4), confd (N,S,24), invalid (N,S,24), stage dict."""
     N, S = pts.shape[:2]
     pts_t = world_to_bone(pts, skts, A)
@@ -359,16 +372,16 @@ def field_eval(pts, rays_d, cams, skts, A, vol, P, rays_per_pose, training, agg_
     p = agg_prob(a, invalid.reshape(N * S, J), agg_type)
     hbar = (hf * p[..., None]).sum(-2)
     dens_in = pe_embed(hbar, 6)
-    v = view_inputs(rays_d, cams, P, training)
-    v = v[:, None].expand(N, S, -1).reshape(N * S, -1)
+    v_ray = view_inputs(view_directions(rays_d, skts, view_mode), cams, P, training)
+    v = v_ray[:, None].expand(N, S, -1).reshape(N * S, -1)
     raw = field_mlp(dens_in, v, P).reshape(N, S, 4)
-    stages = {"pts_t": pts_t, "x": x, "h": h, "p": p.reshape(N, S, J), "hbar": hbar.reshape(N, S, -1)}
+    stages = {"pts_t": pts_t, "x": x, "h": h, "p": p.reshape(N, S, J), "hbar": hbar.reshape(N, S, -1), "view_inputs": v_ray}
     return raw, a.reshape(N, S, J), invalid, stages
 
 
 def render_rays(ray_batch, pose_skts, pose_bones, pose_cyls, cams, A, P, S_c, S_f, rays_per_pose,
                 use_volume_near_far=False, training=False, rand=None, raw_noise_std=0., agg_type="sigmoid",
-                return_stages=False, z_samples=None, lindisp=False):
+                return_stages=False, z_samples=None, lindisp=False, view_mode="world"):
     """ray_batch (N,>=8); pose_* are per unique pose (G,...); ray n belongs to pose n // rays_per_pose.
     rand (training) = dict(t_rand (N,S_c), noise0 (N,S_c), u (N,S_f), noise1 (N,S_t)) drawn by the caller in
     the reference's order (SURVEY §7 hard part 4)."""
@@ -387,7 +400,7 @@ def render_rays(ray_batch, pose_skts, pose_bones, pose_cyls, cams, A, P, S_c, S_
     rand = rand or {}
     z = coarse_z(near, far, S_c, rand.get("t_rand"), lindisp)
     pts = ray_points(rays_o, rays_d, z)
-    raw0, confd0, inv0, st0 = field_eval(pts, rays_d, cams, skts, A, vol, P, rays_per_pose, training, agg_type)
+    raw0, confd0, inv0, st0 = field_eval(pts, rays_d, cams, skts, A, vol, P, rays_per_pose, training, agg_type, view_mode)
     n0 = rand["noise0"] * raw_noise_std if "noise0" in rand else None
     out0 = composite(raw0, z, rays_d, n0)
     z_all, zs, order, inds = importance_sample(z, out0["weights"], S_f, rand.get("u"))
@@ -397,7 +410,7 @@ def render_rays(ray_batch, pose_skts, pose_bones, pose_cyls, cams, A, P, S_c, S_
         zs = z_samples
         z_all, order = torch.sort(torch.cat([z, zs], -1), -1)
     pts_f = ray_points(rays_o, rays_d, zs)
-    raw1, confd1, inv1, st1 = field_eval(pts_f, rays_d, cams, skts, A, vol, P, rays_per_pose, training, agg_type)
+    raw1, confd1, inv1, st1 = field_eval(pts_f, rays_d, cams, skts, A, vol, P, rays_per_pose, training, agg_type, view_mode)
     raw = merge_sorted(raw0, raw1, order)
     confd = merge_sorted(confd0, confd1, order)
     inv = merge_sorted(inv0, inv1, order)

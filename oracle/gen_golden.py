@@ -187,20 +187,23 @@ def run_render_case(name, config, extra, pose_seed, H, n_rays, weight_seed=0, fu
     rest = syn.rest_pose()
     caster, kw = rh.build(args, rest)
     caster.eval()
-    sd = syn.synth_state_dict(params.danbo_param_shapes(), weight_seed)
+    # (opt_framecode=False, configs/surreal: the standard synthetic weights without the frame-code part)
+    sd = {k: v for k, v in syn.synthetic_params(weight_seed, opt_framecode=bool(args.opt_framecode)).items()
+          if k not in params.BUFFER_NAMES and k != "graph_net.axis_scale"}
     rh.load_weights(caster, sd)
     pose = syn.make_pose(pose_seed)
     b = subsample_rays(syn.render_batch(pose, H, H, full_image=full_image), n_rays, seed=pose_seed)
+    cams = b["cams"] if args.opt_framecode else None           # trainer.py:310: no cams without frame codes
     tap = Tap()
     tap_reference(caster, tap, rc)
     kwargs = {k: v for k, v in kw.items() if k not in ("ray_caster", "N_samples", "use_viewdirs")}
     with torch.no_grad():
         ret = caster(b["ray_batch"], N_samples=args.N_samples, kp_batch=b["kp_batch"], skts=b["skts"],
-                     cyls=b["cyls"], bones=b["bones"], cams=b["cams"], N_uniques=1, **kwargs)
+                     cyls=b["cyls"], bones=b["bones"], cams=cams, N_uniques=1, **kwargs)
     tap.undo()
     fx = {"config": config, "extra": " ".join(extra), "pose_seed": pose_seed, "weight_seed": weight_seed, "H": H,
           "N_samples": args.N_samples, "N_importance": args.N_importance,
-          "use_volume_near_far": int(bool(args.use_volume_near_far)),
+          "use_volume_near_far": int(bool(args.use_volume_near_far)), "opt_framecode": int(bool(args.opt_framecode)),
           "ray_batch": b["ray_batch"], "cams": b["cams"], "pose_bones": pose["bones"], "pose_kps": pose["kps"],
           "pose_skts": pose["skts"], "pose_cyl": pose["cyl"]}
     for k, v in ret.items():
@@ -411,6 +414,12 @@ def main():
         run_train_case("train_fast_popt", "h36m_zju/danbo_fast.txt", [], n_poses=4, rays_per_pose=48, batch_seed=1,
                        pose_grads=True)
         return
+    if only == "surreal":
+        run_render_case("render_surreal", "surreal/danbo_fast.txt", [], pose_seed=5, H=64, n_rays=200)
+        return
+    if only == "perfcap":
+        run_render_case("render_perfcap", "perfcap/danbo_fast.txt", [], pose_seed=6, H=64, n_rays=160)
+        return
     if only == "anerf_h":
         run_anerf_case("render_anerf_h", ["--N_samples", "24", "--N_importance", "12"], pose_seed=4, H=64, n_rays=48,
                        config="h36m_zju/anerf_h.txt")
@@ -433,6 +442,10 @@ def main():
     # train-mode A-NeRF step (loss + gradients): pins the oracle ahead of the A-NeRF backward kernels
     run_train_case("train_anerf", "h36m_zju/anerf_base.txt", ["--N_samples", "24", "--N_importance", "12"],
                    n_poses=2, rays_per_pose=24)
+    # configs/perfcap/danbo_*.txt: view directions in the root joint's frame (ray_tr_type=root_local, view_type=relray)
+    run_render_case("render_perfcap", "perfcap/danbo_fast.txt", [], pose_seed=6, H=64, n_rays=160)
+    # configs/surreal/danbo_*.txt: no per-frame code (opt_framecode=False)
+    run_render_case("render_surreal", "surreal/danbo_fast.txt", [], pose_seed=5, H=64, n_rays=200)
     # gradients with respect to the pose tensors (skts, bones): pins the oracle ahead of the backward-to-poses kernels
     run_train_case("train_fast_popt", "h36m_zju/danbo_fast.txt", [], n_poses=4, rays_per_pose=48, batch_seed=1,
                    pose_grads=True)

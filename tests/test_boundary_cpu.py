@@ -273,3 +273,23 @@ def test_graph_net_module_matches_reference_volumes(name):
     b = bones.clone().requires_grad_(True)
     net.bone_volumes(b).square().sum().backward()
     assert b.grad is not None and float(b.grad.abs().max()) > 0
+
+
+def test_field_without_frame_codes_and_view_modes():
+    """configs/surreal (opt_framecode=False): no `framecodes.codes.weight`, a 283-input view layer - the reference's
+    own parameter inventory for that config; configs/perfcap (relray + root_local) are accepted, mixed pairs are not."""
+    from danbo_b200 import networks, raycaster
+    net = networks.DanboField(n_framecodes=8, skel_profile=sk.skeleton_profile(syn.rest_pose()), opt_framecode=False)
+    P = syn.synthetic_params(0, opt_framecode=False)
+    net.load_state_dict(P, strict=True)
+    assert net.framecodes is None and net.views_linears[0].weight.shape == (128, 283)
+    full = syn.synthetic_params(0)
+    assert torch.equal(P["views_linears.0.weight"], full["views_linears.0.weight"][:, :283])
+    n = sum(p.numel() for p in net.parameters() if p.requires_grad)
+    assert n == 2455876 - 8 * 128 - 128 * 128
+    assert set(params.danbo_param_shapes(opt_framecode=False)) == set(params.danbo_param_shapes()) - {"framecodes.codes.weight"}
+    raycaster.check_args(db.make_args("danbo_fast", opt_framecode=False, loss_fn="MSE"))
+    raycaster.check_args(db.make_args("danbo_fast", view_type="relray", ray_tr_type="root_local", nerf_type="graph"))
+    for bad in (dict(view_type="relray"), dict(ray_tr_type="root_local"), dict(view_type="world"), dict(ray_tr_type="local")):
+        with pytest.raises(NotImplementedError):
+            raycaster.check_args(db.make_args("danbo_fast", **bad))

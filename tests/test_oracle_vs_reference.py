@@ -88,7 +88,8 @@ def test_anerf_oracle_matches_live_reference():
 
 
 @pytest.mark.parametrize("config", ["h36m_zju/danbo_base.txt", "h36m_zju/danbo_fast.txt", "h36m_zju/anerf_base.txt",
-                                    "h36m_zju/anerf_h.txt"])
+                                    "h36m_zju/anerf_h.txt", "perfcap/danbo_base.txt", "perfcap/danbo_fast.txt",
+                                    "perfcap/anerf_base.txt", "surreal/danbo_base.txt", "surreal/danbo_fast.txt"])
 def test_flag_defaults_and_config_reader_match_the_reference_parser(config):
     """`config.DEFAULTS` + `read_config_file` against the reference's own argparse (run_nerf.py:186-572) on the shipped
     configs: every flag this path looks at must come out with the reference's value; the presets are those configs."""

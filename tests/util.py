@@ -20,7 +20,19 @@ def load_fixture(name):
 
 
 def params_for(fx):
-    return syn.synthetic_params(int(fx["weight_seed"]))
+    return syn.synthetic_params(int(fx["weight_seed"]), opt_framecode=bool(int(fx.get("opt_framecode", 1))))
+
+
+def config_flags_of(fx):
+    """Flags (beyond the preset) of the shipped config a fixture was rendered with: perfcap's root-local view
+    directions, surreal's missing frame codes."""
+    cfg = str(fx.get("config", ""))
+    flags = {}
+    if "perfcap" in cfg:
+        flags.update(view_type="relray", ray_tr_type="root_local", nerf_type="graph")
+    if not int(fx.get("opt_framecode", 1)):
+        flags.update(opt_framecode=False, loss_fn="MSE")
+    return flags
 
 
 def align_A():
@@ -72,7 +84,7 @@ def make_caster(preset, weight_seed=0, device="cuda", train=False, **flags):
                   "rest_pose": syn.rest_pose()}
     kw_train, kw_test, *_ = db.create_raycaster(args, data_attrs, device=device)
     caster = kw_test["ray_caster"]
-    P = syn.synthetic_params(weight_seed)
+    P = syn.synthetic_params(weight_seed, opt_framecode=bool(getattr(args, "opt_framecode", True)))
     caster.network.load_state_dict(P)
     caster.train(train)
     return caster, args, {k: v.to(device) for k, v in P.items()}
@@ -81,6 +93,11 @@ def make_caster(preset, weight_seed=0, device="cuda", train=False, **flags):
 def agg_type_of(fx):
     """Aggregation type of a fixture (`--agg_type softmax` in its extra flags; the configs ship sigmoid)."""
     return "softmax" if "agg_type softmax" in str(fx.get("extra", "")) else "sigmoid"
+
+
+def view_mode_of(fx):
+    """"root_local" for fixtures of the perfcap configs (ray_tr_type=root_local, view_type=relray), else "world"."""
+    return "root_local" if "perfcap" in str(fx.get("config", "")) else "world"
 
 
 def lindisp_of(fx):
