@@ -293,3 +293,25 @@ def test_field_without_frame_codes_and_view_modes():
     for bad in (dict(view_type="relray"), dict(ray_tr_type="root_local"), dict(view_type="world"), dict(ray_tr_type="local")):
         with pytest.raises(NotImplementedError):
             raycaster.check_args(db.make_args("danbo_fast", **bad))
+
+
+def test_view_rays_root_local_matches_oracle():
+    """`RayCaster._view_rays` (perfcap configs) against the oracle's `view_directions`, one pose and several."""
+    import types
+    sys_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle")
+    import sys
+    sys.path.insert(0, sys_path)
+    import danbo_oracle as orc
+    from danbo_b200.raycaster import RayCaster
+    g = torch.Generator().manual_seed(0)
+    for G, skip in ((1, 12), (3, 4)):
+        rays = torch.randn(12, 11, generator=g)
+        skts = torch.stack([torch.as_tensor(syn.make_pose(30 + i)["skts"]) for i in range(G)])
+        me = types.SimpleNamespace(view_mode="root_local")
+        out = RayCaster._view_rays(me, rays, skts, skip)
+        pose = torch.clamp(torch.arange(12) // skip, max=G - 1)
+        want = orc.view_directions(rays[:, 3:6], skts[pose], "root_local")
+        assert out.shape == (12, 8) and float((out[:, 3:6] - want).abs().max()) < 1e-6
+        assert torch.equal(out[:, :3], rays[:, :3]) and torch.equal(out[:, 6:8], rays[:, 6:8])
+        assert float((out[:, 3:6].norm(dim=-1) - 1).abs().max()) < 1e-6
+        assert RayCaster._view_rays(types.SimpleNamespace(view_mode="world"), rays, skts, skip) is rays
