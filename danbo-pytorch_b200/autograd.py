@@ -104,10 +104,14 @@ class _RenderBlock(torch.autograd.Function):
 
 def render_block_with_grad(caster, rays, skip, pose_skts, pose_cyls, vol, cam_idx, codes, consts, packed, S_c, S_f, B,
                            raw_noise_std, perturb, nanmean_chunk, rand, stages, lindisp=False):
-    if not getattr(caster.network, "opt_framecode", True):
-        raise NotImplementedError("training without frame codes (opt_framecode=False, configs/surreal) is not implemented: "
-                                  "the backward kernels write the view layer's gradient in its 411-input layout")
     named = dict(caster.network.named_parameters())
+    if not getattr(caster.network, "opt_framecode", True):
+        # no frame codes (configs/surreal): the kernels keep the view layer's 411-input layout, so the node gets a
+        # zero-padded view weight (F.pad is differentiable: the gradient of the 283 real columns flows back to the
+        # parameter, the rest is dropped) and a zero code table that takes no gradient.  These temporaries have no
+        # .grad, so the backward pass returns its gradients through autograd instead of adding them in place.
+        named["views_linears.0.weight"] = torch.nn.functional.pad(named["views_linears.0.weight"], (0, 128))
+        named["framecodes.codes.weight"] = torch.zeros(1, 128, device=rays.device)
     params = [named[n] for n in PARAM_NAMES]
     if pose_skts.requires_grad and getattr(caster, "view_mode", "world") != "world":
         raise NotImplementedError("pose gradients with root-local view directions (perfcap configs): the view branch's "

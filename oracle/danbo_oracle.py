@@ -587,9 +587,11 @@ def anerf_density_grid(kps, skts, A, P, radius, res, tau=20.):
 # ----------------------------------------------------------------------------------------------------------
 # L*  core/trainer.py:396-422,507-553 (losses stay in PyTorch in the product too; here for the training parity test)
 # ----------------------------------------------------------------------------------------------------------
-def training_loss(ret, target, bgs, P, init_scale, soft_coef=0.001, vol_coef=0.001, coarse_weight=1.0, agg_type="sigmoid"):
-    def l1(rgb, acc):
-        return torch.mean(torch.abs(rgb + (1. - acc)[..., None] * bgs - target))
+def training_loss(ret, target, bgs, P, init_scale, soft_coef=0.001, vol_coef=0.001, coarse_weight=1.0, agg_type="sigmoid",
+                  loss_fn="L1"):
+    def l1(rgb, acc):                                               # img2l1 / img2mse, core/trainer.py:164-187
+        d = rgb + (1. - acc)[..., None] * bgs - target
+        return torch.mean(torch.abs(d)) if loss_fn == "L1" else torch.mean(d ** 2)
     loss = l1(ret["rgb_map"], ret["acc_map"]) + coarse_weight * l1(ret["rgb0"], ret["acc0"])
     if agg_type == "sigmoid":                                       # trainer.py:372: only with sigmoid blend weights
         labels = ((ret["T_i"] * ret["alpha"]) > 0).float()

@@ -306,9 +306,14 @@ def run_train_case(name, config, extra, n_poses, rays_per_pose, weight_seed=0, b
     caster, kw = rh.build(args, rest)
     caster.train()
     anerf = args.nerf_type == "nerf"
-    sd = syn.synth_state_dict(params.anerf_param_shapes() if anerf else params.danbo_param_shapes(), weight_seed)
+    if anerf:
+        sd = syn.synth_state_dict(params.anerf_param_shapes(), weight_seed)
+    else:
+        sd = {k: v for k, v in syn.synthetic_params(weight_seed, opt_framecode=bool(args.opt_framecode)).items()
+              if k not in params.BUFFER_NAMES and k != "graph_net.axis_scale"}
     rh.load_weights(caster, sd)
     b = syn.training_batch(n_poses, rays_per_pose, seed=batch_seed)
+    cams = b["cams"] if args.opt_framecode else None               # trainer.py:310
     if pose_grads:
         # the pose tensors as leaves: what the pose layer's outputs are to the ray caster under --opt_pose
         # (core/trainer.py:314-341); their gradients pin the oracle for the backward-to-poses kernels
@@ -320,7 +325,7 @@ def run_train_case(name, config, extra, n_poses, rays_per_pose, weight_seed=0, b
     torch.manual_seed(1234)
     with RandTape() as tape:
         ret = caster(b["ray_batch"], N_samples=args.N_samples, kp_batch=b["kp_batch"], skts=b["skts"],
-                     cyls=b["cyls"], bones=b["bones"], cams=b["cams"], N_uniques=n_poses,
+                     cyls=b["cyls"], bones=b["bones"], cams=cams, N_uniques=n_poses,
                      perturb=args.perturb, N_importance=args.N_importance, raw_noise_std=args.raw_noise_std,
                      ray_noise_std=0., ext_scale=args.ext_scale, lindisp=False, nerf_type=args.nerf_type,
                      preproc_kwargs={"density_scale": args.density_scale, "density_fn": torch.nn.functional.relu})
@@ -338,7 +343,7 @@ def run_train_case(name, config, extra, n_poses, rays_per_pose, weight_seed=0, b
           "n_poses": n_poses, "rays_per_pose": rays_per_pose,
           "N_samples": args.N_samples, "N_importance": args.N_importance,
           "use_volume_near_far": int(bool(args.use_volume_near_far)),
-          "raw_noise_std": args.raw_noise_std,
+          "raw_noise_std": args.raw_noise_std, "opt_framecode": int(bool(args.opt_framecode)), "loss_fn": args.loss_fn,
           "loss.total": loss_dict["total_loss"].detach()}
     for k, v in loss_dict.items():
         fx["loss." + k] = v.detach()
@@ -414,6 +419,9 @@ def main():
         run_train_case("train_fast_popt", "h36m_zju/danbo_fast.txt", [], n_poses=4, rays_per_pose=48, batch_seed=1,
                        pose_grads=True)
         return
+    if only == "train_surreal":
+        run_train_case("train_surreal", "surreal/danbo_fast.txt", [], n_poses=4, rays_per_pose=48, batch_seed=2)
+        return
     if only == "surreal":
         run_render_case("render_surreal", "surreal/danbo_fast.txt", [], pose_seed=5, H=64, n_rays=200)
         return
@@ -446,6 +454,7 @@ def main():
     run_render_case("render_perfcap", "perfcap/danbo_fast.txt", [], pose_seed=6, H=64, n_rays=160)
     # configs/surreal/danbo_*.txt: no per-frame code (opt_framecode=False)
     run_render_case("render_surreal", "surreal/danbo_fast.txt", [], pose_seed=5, H=64, n_rays=200)
+    run_train_case("train_surreal", "surreal/danbo_fast.txt", [], n_poses=4, rays_per_pose=48, batch_seed=2)
     # gradients with respect to the pose tensors (skts, bones): pins the oracle ahead of the backward-to-poses kernels
     run_train_case("train_fast_popt", "h36m_zju/danbo_fast.txt", [], n_poses=4, rays_per_pose=48, batch_seed=1,
                    pose_grads=True)

@@ -227,19 +227,19 @@ def test_internal_block_plan():
                 assert n_blocks >= min(ns, -(-N // chunk)) and (n_blocks - 1) * block < N
 
 
-@pytest.mark.parametrize("name", ["train_fast", "train_cfg3", "train_fast_softmax"])
+@pytest.mark.parametrize("name", ["train_fast", "train_cfg3", "train_fast_softmax", "train_surreal"])
 def test_compute_loss_on_the_references_outputs(name):
     """`training.compute_loss` (the PyTorch-op restatement of core/trainer.py:396-422,507-553 the loss kernel is tested
     against on the GPU) on the reference's OWN render outputs must give the reference's own loss terms."""
     import numpy as np
     from danbo_b200 import networks, training
-    from util import load_fixture, agg_type_of, preset_of
+    from util import load_fixture, agg_type_of, preset_of, config_flags_of, params_for
     fx = load_fixture(name)
     agg = agg_type_of(fx)
-    args = db.make_args(preset_of(fx), no_reload=True, agg_type=agg)
+    args = db.make_args(preset_of(fx), no_reload=True, agg_type=agg, **config_flags_of(fx))
     net = networks.DanboField(n_framecodes=8, skel_profile=sk.skeleton_profile(syn.rest_pose()), opt_scale=True,
-                              agg_type=agg, mask_vol_prob=True)
-    net.load_state_dict(syn.synthetic_params(int(fx["weight_seed"])))
+                              agg_type=agg, mask_vol_prob=True, opt_framecode=bool(args.opt_framecode))
+    net.load_state_dict(params_for(fx))
     b = syn.training_batch(int(fx["n_poses"]), int(fx["rays_per_pose"]), seed=int(fx["batch_seed"]))
     preds = {k[4:]: v for k, v in fx.items() if k.startswith("out.")}
     total, terms = training.compute_loss(args, preds, {"target_s": b["target_s"], "bgs": b["bgs"]}, net)
