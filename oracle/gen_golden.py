@@ -419,6 +419,9 @@ def main():
         run_train_case("train_fast_popt", "h36m_zju/danbo_fast.txt", [], n_poses=4, rays_per_pose=48, batch_seed=1,
                        pose_grads=True)
         return
+    if only == "train_perfcap":
+        run_train_case("train_perfcap", "perfcap/danbo_fast.txt", [], n_poses=4, rays_per_pose=48, batch_seed=3)
+        return
     if only == "train_surreal":
         run_train_case("train_surreal", "surreal/danbo_fast.txt", [], n_poses=4, rays_per_pose=48, batch_seed=2)
         return
@@ -455,6 +458,7 @@ def main():
     # configs/surreal/danbo_*.txt: no per-frame code (opt_framecode=False)
     run_render_case("render_surreal", "surreal/danbo_fast.txt", [], pose_seed=5, H=64, n_rays=200)
     run_train_case("train_surreal", "surreal/danbo_fast.txt", [], n_poses=4, rays_per_pose=48, batch_seed=2)
+    run_train_case("train_perfcap", "perfcap/danbo_fast.txt", [], n_poses=4, rays_per_pose=48, batch_seed=3)
     # gradients with respect to the pose tensors (skts, bones): pins the oracle ahead of the backward-to-poses kernels
     run_train_case("train_fast_popt", "h36m_zju/danbo_fast.txt", [], n_poses=4, rays_per_pose=48, batch_seed=1,
                    pose_grads=True)

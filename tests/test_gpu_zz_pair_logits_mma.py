@@ -201,13 +201,16 @@ def test_render_other_shipped_configs(name):
         assert float(e.mean()) <= 4e-3 and float(e.flatten().quantile(0.99)) <= 5e-2 and float(e.max()) <= 0.2, k
 
 
-def test_training_step_without_frame_codes():
-    """configs/surreal training (MSE loss, no frame codes): the autograd node runs on a zero-padded view weight; the
-    283-column gradient that comes back must match the oracle's, like the other parameters (bounds of
-    test_gpu_training.py::test_training_step_gradients[train_fast])."""
+@pytest.mark.parametrize("name", ["train_surreal", "train_perfcap"])
+def test_training_step_other_shipped_configs(name):
+    """configs/surreal training (MSE loss, no frame codes: the autograd node runs on a zero-padded view weight and the
+    283-column gradient must come back) and configs/perfcap training (root-local view directions of four poses): loss and
+    parameter gradients against the oracle's (bounds of test_gpu_training.py::test_training_step_gradients[train_fast])."""
     from danbo_b200 import synthetic as syn, skeleton as sk
-    from util import config_flags_of
-    fx = load_fixture("train_surreal")
+    from util import config_flags_of, view_mode_of
+    fx = load_fixture(name)
+    loss_fn = str(fx.get("loss_fn", "L1"))
+    has_codes = bool(int(fx.get("opt_framecode", 1)))
     caster, args, _ = make_caster(preset_of(fx), train=True, **config_flags_of(fx))
     n_poses, rpp = int(fx["n_poses"]), int(fx["rays_per_pose"])
     b = syn.training_batch(n_poses, rpp, seed=int(fx["batch_seed"]))
@@ -215,24 +218,26 @@ def test_training_step_without_frame_codes():
     init_scale = sk.initial_axis_scale(sk.skeleton_profile(syn.rest_pose()), 0.4)
     stages = {}
     out = caster.render_rays(b["ray_batch"], N_samples=args.N_samples, kp_batch=b["kp_batch"], skts=b["skts"],
-                             cyls=b["cyls"], bones=b["bones"], cams=None, N_uniques=n_poses, perturb=1.0,
+                             cyls=b["cyls"], bones=b["bones"], cams=b["cams"] if has_codes else None, N_uniques=n_poses,
+                             perturb=1.0,
                              N_importance=args.N_importance, raw_noise_std=float(fx["raw_noise_std"]),
                              _rand={k: v.to(DEV) for k, v in rand.items()}, _stages=stages)
     P = {k: v.clone().requires_grad_(v.dtype.is_floating_point and not k.endswith(".adj")) for k, v in params_for(fx).items()}
     dev_out = {k: v for k, v in out.items()}
     loss = orc.training_loss(dev_out, b["target_s"].to(DEV), b["bgs"].to(DEV),
-                             {"graph_net.axis_scale": caster.network.graph_net.axis_scale}, init_scale.to(DEV), loss_fn="MSE")
+                             {"graph_net.axis_scale": caster.network.graph_net.axis_scale}, init_scale.to(DEV), loss_fn=loss_fn)
     loss.backward()
     torch.cuda.synchronize()
     ref = orc.render_rays(b["ray_batch"], b["skts"][::rpp], b["bones"][::rpp], b["cyls"][::rpp], b["cams"], align_A(), P,
                           int(fx["N_samples"]), int(fx["N_importance"]), rays_per_pose=rpp,
                           use_volume_near_far=bool(fx["use_volume_near_far"]), training=True, rand=rand,
-                          raw_noise_std=float(fx["raw_noise_std"]), z_samples=stages["z_samples"].cpu())
-    ref_loss = orc.training_loss(ref, b["target_s"], b["bgs"], P, init_scale, loss_fn="MSE")
+                          raw_noise_std=float(fx["raw_noise_std"]), z_samples=stages["z_samples"].cpu(),
+                          view_mode=view_mode_of(fx))
+    ref_loss = orc.training_loss(ref, b["target_s"], b["bgs"], P, init_scale, loss_fn=loss_fn)
     ref_loss.backward()
     assert abs(float(loss) - float(ref_loss)) <= 5e-3
     g = caster.network.views_linears[0].weight.grad
-    assert g is not None and g.shape == (128, 283)
+    assert g is not None and g.shape == (128, 411 if has_codes else 283)
     big = max(float(v.grad.norm()) for v in P.values() if v.grad is not None)
     for k, v in P.items():
         if v.grad is None:
@@ -241,5 +246,5 @@ def test_training_step_without_frame_codes():
         r = v.grad.reshape(-1).double()
         cos = float(torch.dot(a, r) / (a.norm() * r.norm() + 1e-30))
         rel = float((a - r).norm() / max(float(r.norm()), 1e-3 * big))
-        print(f"[surreal] {k:40s} cos {cos:.5f} rel {rel:.3e}")
+        print(f"[{name}] {k:40s} cos {cos:.5f} rel {rel:.3e}")
         assert (float(r.norm()) <= 1e-3 * big or cos >= 0.985) and rel <= 0.2, (k, cos, rel)
