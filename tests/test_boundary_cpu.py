@@ -315,3 +315,30 @@ def test_view_rays_root_local_matches_oracle():
         assert torch.equal(out[:, :3], rays[:, :3]) and torch.equal(out[:, 6:8], rays[:, 6:8])
         assert float((out[:, 3:6].norm(dim=-1) - 1).abs().max()) < 1e-6
         assert RayCaster._view_rays(types.SimpleNamespace(view_mode="world"), rays, skts, skip) is rays
+
+
+def test_create_raycaster_for_the_other_shipped_configs(tmp_path):
+    """configs/surreal (no frame codes) and configs/perfcap (root-local view directions) through the factory: module
+    shapes, checkpoint keys, and a checkpoint round trip through the reference's file layout."""
+    args = db.make_args("danbo_fast", no_reload=True, opt_framecode=False, loss_fn="MSE")
+    _, kw, _, grad_vars, _, _ = db.create_raycaster(args, _attrs(), device="cpu")
+    caster = kw["ray_caster"]
+    sd = caster.state_dict()
+    assert "framecodes.codes.weight" not in sd["network_fn_state_dict"]
+    assert sd["network_fn_state_dict"]["views_linears.0.weight"].shape == (128, 283)
+    assert sum(p.numel() for p in grad_vars) == 2455876 - 8 * 128 - 128 * 128
+    assert caster.view_mode == "world" and not caster.network.opt_framecode
+    caster.network.load_state_dict(syn.synthetic_params(1, opt_framecode=False))
+    path = os.path.join(tmp_path, "000001.tar")
+    torch.save({"global_step": 1, **caster.state_dict()}, path)
+    args2 = db.make_args("danbo_fast", opt_framecode=False, ft_path=path)
+    _, kw2, start, *_ = db.create_raycaster(args2, _attrs(), device="cpu")
+    assert start == 1
+    for k, v in kw2["ray_caster"].state_dict()["network_fn_state_dict"].items():
+        assert torch.equal(v, caster.state_dict()["network_fn_state_dict"][k]), k
+    with pytest.raises(ValueError):                                   # a field WITH frame codes needs cams
+        c3 = db.create_raycaster(db.make_args("danbo_fast", no_reload=True), _attrs(), device="cpu")[1]["ray_caster"]
+        c3.render_rays(torch.zeros(4, 11), 8, None, skts=torch.zeros(4, 24, 4, 4), cyls=torch.zeros(4, 5),
+                       bones=torch.zeros(4, 24, 3), cams=None, N_importance=4)
+    perf = db.make_args("danbo_fast", no_reload=True, view_type="relray", ray_tr_type="root_local", nerf_type="graph")
+    assert db.create_raycaster(perf, _attrs(), device="cpu")[1]["ray_caster"].view_mode == "root_local"
