@@ -108,3 +108,21 @@ def test_flag_defaults_and_config_reader_match_the_reference_parser(config):
         p = vars(db.make_args(preset))
         bad = {k: (p[k], want[k]) for k in cfg.DEFAULTS if k in want and k not in skip and p[k] != want[k]}
         assert not bad, bad
+
+
+def test_setup_constants_match_live_reference():
+    """S0 / S1: the bone-align transforms (raycasters.py:548-591) and the initial per-bone half extents
+    (misc.py:675-724, gnn_backbone.py:777-785) of the reference's freshly constructed caster, for two rest poses."""
+    import numpy as np
+    from danbo_b200 import skeleton as sk, synthetic as syn
+    for scale in (0.5, 0.43):
+        rest = (sk.SMPL_REST_POSE * scale).astype(np.float32)
+        args = rh.parse_args("h36m_zju/danbo_fast.txt", [])
+        caster, _ = rh.build(args, rest)
+        A, child = sk.bone_align_transforms(rest)
+        want_A = caster.transforms.detach().numpy().reshape(24, 4, 4)
+        assert np.abs(A - want_A).max() <= 1e-6, np.abs(A - want_A).max()
+        assert list(np.asarray(child)) == list(np.asarray(caster.child_idxs))
+        got = sk.initial_axis_scale(sk.skeleton_profile(rest), 0.4)
+        want = caster.network.graph_net.axis_scale.detach()
+        assert float((got - want).abs().max()) <= 1e-6 * float(want.abs().max()), float((got - want).abs().max())
