@@ -12,7 +12,7 @@ accumulator fragments as layer-1 A fragments, the quad reduction of layer 2 - ar
 and compares the logits with the fp32 oracle (`danbo_oracle.agg_net`) on random features: the 3-term split-bf16
 products must stay within 1e-5 of the logits' scale.  It also checks that the kernel's tree-neighbour masks are the
 skeleton's.  What this cannot catch is a wrong memory of the PTX layouts themselves; the GPU test
-(tests/test_gpu_zz_pair_logits_mma.py) is the final word."""
+(tests/test_gpu_zzz_pair_logits_mma.py) is the final word."""
 import os
 import re
 import sys
