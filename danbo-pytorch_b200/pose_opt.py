@@ -20,7 +20,7 @@ as an input) and d loss / d bones through the graph net's PyTorch ops (`networks
 receives none in the DANBO field, as in the reference.  `training.TrainStep(popt_kwargs=..., pose_optimizer=...)` runs
 the whole --opt_pose iteration.  That gradient path was written after round 1's GPU minutes were spent: it is pinned on
 the CPU (oracle vs the reference's own pose gradients, tests/golden/train_fast_popt.npz) and its GPU tests
-(tests/test_gpu_zpose_grad.py) have not run on hardware yet.
+(tests/test_gpu_zzy_pose_grad.py) have not run on hardware yet.
 """
 import numpy as np
 import torch

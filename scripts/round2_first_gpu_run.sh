@@ -5,11 +5,11 @@
 set -u
 mkdir -p gpurun_out
 # 1. the verified suite must still be green with the rebuilt library (ABI 3, consts[11], grads[10])
-python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_zpose_grad.py --deselect tests/test_gpu_zz_unverified_host_paths.py \
+python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_zzy_pose_grad.py --deselect tests/test_gpu_zz_unverified_host_paths.py \
     --deselect tests/test_gpu_zzz_pair_logits_mma.py \
     > gpurun_out/r2a_gpu_verified.log 2>&1
 # 2. the unverified paths, with their xfail markers ignored so that failures show as failures
-python -m pytest tests/test_gpu_zpose_grad.py tests/test_gpu_zz_unverified_host_paths.py tests/test_gpu_zzz_pair_logits_mma.py \
+python -m pytest tests/test_gpu_zzy_pose_grad.py tests/test_gpu_zz_unverified_host_paths.py tests/test_gpu_zzz_pair_logits_mma.py \
     -m gpu -q -s --runxfail \
     > gpurun_out/r2a_gpu_unverified.log 2>&1
 # 3. legacy-MMA issue rate (decides how far the split-bf16 aggregation net can go)
