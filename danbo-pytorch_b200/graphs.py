@@ -23,8 +23,16 @@ class GraphedFn:
     inputs: dict name -> tensor (copied into static device buffers before each replay) or non-tensor (part of the key).
     fn must be free of host synchronisation and data-dependent host control flow."""
 
-    def __init__(self, fn, device, warmup=3):
+    def __init__(self, fn, device, warmup=3, state=None, capture_error_mode="global"):
+        """state: tensors `fn` updates in place (parameters, optimizer moments, step counters).  They are snapshotted
+        before the warm-up calls and restored after capture, so that building a graph has no side effect: the first
+        replay is the first real application of `fn` (a captured optimizer step would otherwise be applied warmup + 1
+        times to the first batch of every new input signature).
+        capture_error_mode: "thread_local" when the captured region holds NCCL collectives (the process group's watchdog
+        thread polls CUDA events, which a "global" capture would turn into an error)."""
         self.fn, self.device, self.warmup = fn, torch.device(device), warmup
+        self.state = list(state) if state is not None else []
+        self.capture_error_mode = capture_error_mode
         self.cache = {}
 
     @staticmethod
@@ -41,6 +49,7 @@ class GraphedFn:
         if ent is None:
             static = {n: (torch.empty(v.shape, dtype=v.dtype, device=self.device).copy_(v, non_blocking=True)
                           if torch.is_tensor(v) else v) for n, v in inputs.items()}
+            snap = [t.detach().clone() for t in self.state]
             s = torch.cuda.Stream(device=self.device)
             s.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(s):
@@ -49,8 +58,11 @@ class GraphedFn:
             torch.cuda.current_stream(self.device).wait_stream(s)
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, capture_error_mode=self.capture_error_mode):
                 out = self.fn(**static)
+            with torch.no_grad():
+                for t, v in zip(self.state, snap):
+                    t.copy_(v)
             ent = self.cache[key] = (g, static, out)
         else:
             g, static, out = ent

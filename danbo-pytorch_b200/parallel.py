@@ -113,6 +113,9 @@ class GradBucket:
 
     def allreduce(self, average=True):
         if dist.is_initialized() and dist.get_world_size() > 1:
+            if average and dist.get_backend() == "nccl":
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)        # one collective, no separate scaling launch
+                return
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
             if average:
                 self.flat.div_(dist.get_world_size())

@@ -90,13 +90,17 @@ class RayCaster(nn.Module):
         B = float((preproc_kwargs or {}).get("density_scale", 1.0))
         rays, pose_skts, pose_bones, pose_cyls, cam_idx, skip = self._prepare(ray_batch, skts, cyls, bones, cams, N_uniques)
         if self._graphed is None:
-            def run(rays, pose_skts, pose_bones, pose_cyls, cam_idx, **kw):
+            def run(rays, pose_skts, pose_bones, pose_cyls, cam_idx, _param_ptrs=None, **kw):
                 with torch.no_grad():
                     return self._render_prepared(rays, pose_skts, pose_bones, pose_cyls, cam_idx, **kw)
             self._graphed = GraphedFn(run, self._device())
+        # A captured graph reads the parameters through the raw pointers they had at capture time (the weight pack, the
+        # graph net and the aggregation net all read them live, so value changes are always seen); the pointers are part
+        # of the graph key, so re-pointed storage (`.to()`, an optimizer's flat arena) gets a fresh capture.
+        ptrs = hash(tuple(p.data_ptr() for p in self.parameters()))
         return self._graphed(rays=rays, pose_skts=pose_skts, pose_bones=pose_bones, pose_cyls=pose_cyls, cam_idx=cam_idx,
                              skip=skip, N_samples=N_samples, N_importance=N_importance, B=B, nanmean_chunk=nanmean_chunk,
-                             lindisp=bool(lindisp))
+                             lindisp=bool(lindisp), _param_ptrs=ptrs)
 
     def update_embed_fns(self, global_step, args):
         self.network.update_embed_fns(global_step, args)
@@ -146,7 +150,12 @@ class RayCaster(nn.Module):
         if self._packed is None or self._packed.wstream.device != self._device():
             self._packed = K.PackedMLP(self._device())
             self._packed_key = None
-        if key != self._packed_key:
+        # The host-side key cannot see an update made by a kernel through raw pointers (the single-launch Adam), and a
+        # replayed CUDA graph never runs this Python at all.  So the pack is unconditional (a) while a graph is being
+        # captured - the pack launch then belongs to the graph and every replay reads the live parameters - and (b) in
+        # every train-mode forward (one 5 us launch per iteration).  Only eager eval calls rely on the key.
+        force = torch.cuda.is_current_stream_capturing() or (self.training and torch.is_grad_enabled())
+        if force or key != self._packed_key:
             tensors = {n: P[n] for n in names}
             if not getattr(net, "opt_framecode", True):
                 # no frame code: the kernels' view layer keeps its 411-input layout with zero weights (and zero codes,
@@ -338,6 +347,11 @@ class RayCaster(nn.Module):
         noise0 = (rand["noise0"] * (raw_noise_std * B)).contiguous() if ("noise0" in rand and raw_noise_std > 0) else None
         c0 = K.composite_resample(rays, S_c, S_f, raw0, mask0, z0, noise=noise0, inv_B=inv_B, u_rand=rand.get("u"),
                                   want_inds=stages is not None)
+        if "z_fine" in rand:
+            # test hook: evaluate the fine pass at given importance samples (z_fine, z_all, order as the reference
+            # produced them) instead of this pass's own - cuts the coarse -> fine coupling for stage-wise parity checks
+            c0 = dict(c0, z_samples=rand["z_fine"].float().contiguous(), z_all=rand["z_all"].float().contiguous(),
+                      order=rand["order"].to(torch.int32).contiguous())
         # ---- fine pass: only the S_f new samples go through the field (single_net)
         z1, mask1, act1 = K.sample_mask(rays, S_f, p_skts, skip, consts, z_in=c0["z_samples"], append_empty=False)
         f1 = K.field_agg(rays, S_f, z1, mask1, act1, p_skts, p_vol, skip, consts, want_hbar=save, want_xrows=save,

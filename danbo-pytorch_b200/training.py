@@ -1,6 +1,8 @@
 """Training step around the hot path: the trainer's losses (they stay PyTorch elementwise ops, SURVEY §8a row L*),
 Adam, and the data-parallel gradient exchange.  Mirrors core/trainer.py:257-300 (train_batch), :348-422,507-553
 (losses), :563-576 (optimize) for the flags the shipped DANBO configs use."""
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -189,6 +191,12 @@ class TrainStep:
         the batch's poses then come from the pose layer (indexed by `batch['kp_idx']`), the pose regulariser
         (`pose_opt.kp_loss`) joins the loss and the pose optimiser steps with the network's."""
         self.caster, self.args, self.world = caster, args, world_size
+        # flags the reference trainer honours and this step does not implement: raise, never ignore (no shipped config
+        # sets any of them)
+        for flag, ok in (("opt_pose_step", (None, 1)), ("opt_pose_stop", (None, False, 0)), ("weight_decay", (None, 0, 0.0)),
+                         ("reg_fn", (None, "", "None")), ("use_lpips_loss", (None, False))):
+            if getattr(args, flag, None) not in ok:
+                raise NotImplementedError(f"{flag}={getattr(args, flag)!r} is not implemented by danbo_b200.TrainStep")
         self.popt = popt_kwargs if (popt_kwargs and popt_kwargs.get("popt_layer") is not None) else None
         self.pose_optimizer = pose_optimizer
         self.last_stats = {}
@@ -214,25 +222,31 @@ class TrainStep:
                 torch.optim.Adam(params, lr=args.lrate, betas=(0.9, 0.999))
         self.optimizer = optimizer
         self._graphed = None
+        self._graph_whole = False
         if graph:
             from .graphs import GraphedFn
-            if world_size > 1:
-                # the graph holds forward + backward; the gradient all-reduce and Adam stay ordinary stream work, so no
-                # NCCL call is ever captured
-                def run(**b):
-                    loss, preds = self._fwd_bwd(b)
-                    return {"loss": loss, "rgb_map": preds["rgb_map"], "acc_map": preds["acc_map"]}
-            else:
-                def run(**b):
-                    loss, preds = self._step(b)
-                    return {"loss": loss, "rgb_map": preds["rgb_map"], "acc_map": preds["acc_map"]}
-            self._graphed = GraphedFn(run, params[0].device, warmup=3)
+            flat = isinstance(optimizer, FlatAdam)
+            # The whole iteration - forward, losses, backward, the NCCL all-reduce of the gradient bucket and the
+            # single-launch Adam - is ONE captured graph (NCCL collectives are capturable; DANBO_GRAPH_ALLREDUCE=0 keeps
+            # the all-reduce and Adam as ordinary stream work after the replay).  A torch optimizer cannot be captured,
+            # so it always steps outside.  The weight pack is part of the captured forward (RayCaster._packed_mlp), so a
+            # replay always evaluates the weights the previous replay's Adam wrote.
+            self._graph_whole = flat and (world_size == 1 or os.environ.get("DANBO_GRAPH_ALLREDUCE", "1") == "1")
+
+            def run(**b):
+                loss, preds = self._step(b) if self._graph_whole else self._fwd_bwd(b)
+                return {"loss": loss, "rgb_map": preds["rgb_map"], "acc_map": preds["acc_map"]}
+            # building the graph must not train: parameters, moments and the step counter are restored after capture
+            state = [optimizer.flat, optimizer.exp_avg, optimizer.exp_avg_sq, optimizer.step_dev] if flat else []
+            self._graphed = GraphedFn(run, params[0].device, warmup=3, state=state if self._graph_whole else [],
+                                      capture_error_mode="thread_local" if world_size > 1 else "global")
 
     def __call__(self, batch):
         if self._graphed is not None:
             out = self._graphed(**batch)
-            if self.world > 1:
-                self.bucket.allreduce(average=True)
+            if not self._graph_whole:
+                if self.world > 1:
+                    self.bucket.allreduce(average=True)
                 self._optimizer_step()
             self._after_step()
             return out["loss"], out
@@ -242,7 +256,8 @@ class TrainStep:
 
     def _step(self, batch):
         loss, preds = self._fwd_bwd(batch)
-        self.bucket.allreduce(average=True)
+        if self.world > 1:
+            self.bucket.allreduce(average=True)
         self._optimizer_step()
         return loss, preds
 
@@ -277,6 +292,8 @@ class TrainStep:
     def _after_step(self):
         """Steps 4-5 of train_batch (core/trainer.py:286-294): learning-rate decay and the encoders' schedules."""
         self.n_steps += 1
+        # a replayed graph runs no Python: invalidate the eager-eval weight pack here, once per iteration, as well
+        self.caster._packed_key = None
         new = self.decayed_lrate()
         if new != self.lrate:                   # a staircase in units of decay_unit steps: rarely changes
             self.lrate = new
@@ -285,15 +302,8 @@ class TrainStep:
             else:
                 for g in self.optimizer.param_groups:
                     g["lr"] = new
-        if self.popt is not None and self.pose_optimizer is not None:
-            # update_pose_opt_params (core/pose_opt.py:454-463): continuous decay in units of decay * unit steps
-            a = self.args
-            rate = float(getattr(a, "opt_pose_decay_rate", 1.0))
-            if rate != 1.0:
-                steps = float(getattr(a, "opt_pose_lrate_decay", 250)) * float(getattr(a, "opt_pose_decay_unit", 400))
-                lr = float(getattr(a, "opt_pose_lrate", 5e-4)) * rate ** (self.n_steps / steps)
-                for g in self.pose_optimizer.param_groups:
-                    g["lr"] = lr
+        # the pose optimiser's rate stays constant: the reference defines update_pose_opt_params (core/pose_opt.py:454-463)
+        # but its trainer never calls it
         update = getattr(self.caster, "update_embed_fns", None)
         if update is not None and not getattr(self.args, "finetune", False):
             update(self.n_steps, self.args)

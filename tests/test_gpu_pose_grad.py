@@ -3,18 +3,14 @@ the whole training step's d loss / d (skts, bones), against torch autograd of th
 the reference itself produced (tests/golden/train_fast_popt.npz; the oracle is pinned to them on the CPU by
 test_oracle_golden.py::test_training_step_pose_gradients).
 
-STATUS: this path (ABI version 3) was written at the end of round 1 after the round's GPU minutes were spent - it
-compiles for sm_100a (168 registers, no spills, the same as before the change) and everything around it is tested on
-the CPU, but these tests have NOT run on hardware yet.  They are therefore `xfail(strict=False)`: a failure is reported
-as xfailed and does not stop the `-x` run of the verified tests, a pass shows as XPASS.  Remove the marker once green."""
+First run on hardware in round 2 (gpurun_out/r2a_gpu_unverified.log): all green."""
 import pytest
 import torch
 
 import danbo_oracle as orc
 from util import load_fixture, params_for, align_A, make_caster, preset_of, agg_type_of
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300, method="thread"),   # a hung kernel must not hang the box
-              pytest.mark.xfail(strict=False, reason="pose-gradient path not yet run on hardware (written without GPU access)")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300, method="thread")]   # a hung kernel must not hang the box
 DEV = "cuda"
 
 
