@@ -2,7 +2,7 @@
 """Benchmark of the DANBO hot path on B200 (contract: see the task statement / DESIGN.md §Measurement).
 
     python bench.py --gpus 1 --steps 10 --warmup 3                 # this repo's CUDA path
-    python bench.py --impl reference --steps 2 --warmup 1           # the reference algorithm (oracle port) on host cores
+    python bench.py --impl reference --steps 2 --warmup 1           # the unmodified reference (baseline/_ref) on host cores
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
 Workload (BASELINE.json configs[1]): DANBO `danbo_fast` (32 coarse + 16 fine samples, per-part volume near/far),
@@ -286,13 +286,12 @@ def run_ours(opt):
         "steps": opt.steps, "warmup": max(opt.warmup, 3), "ms_per_step": dev_ms / opt.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16 (tensor-core MLP, fp32 accumulate); fp32 elsewhere; fp64 box test",
         "data": "synthetic",
-        "config": {"workload": f"danbo_fast {H}x{W} render, 1 synthetic 24-joint pose, {args.N_samples}+{args.N_importance} "
-                               f"samples/ray, box-restricted rays ({n_rays} rays/image), random-init weights",
-                   "rays_per_image": n_rays, "samples_per_ray": samples_per_ray,
-                   "parallelism": f"1 image per GPU x {world} + NCCL all-gather of pixels" if world > 1 else "single GPU",
-                   "l2": "256 MiB buffer written between timed steps (untimed)", "chunk": args.chunk,
-                   "launch": "each step replays one CUDA graph of the call's fixed launch sequence",
-                   "wall_ms_per_step_incl_flush": t_wall * 1e3 / opt.steps},
+        "config": workload_config(args, n_rays),
+        "run": {"parallelism": f"1 image per GPU x {world} + NCCL all-gather of pixels" if world > 1 else "single GPU",
+                "rays_this_view": n_rays,
+                "l2": "256 MiB buffer written between timed steps (untimed)",
+                "launch": "each step replays one CUDA graph of the call's fixed launch sequence",
+                "wall_ms_per_step_incl_flush": t_wall * 1e3 / opt.steps},
         "e2e": {"value": total_rays / (e2e_ms / 1e3), "unit": "rays/s", "h2d_bytes_per_step": int(rays_host.numel() * 4),
                 "d2h_bytes_per_step": int(pix_host.numel() * 4),
                 "pipeline": "ray_caster call per step on rays uploaded from pinned host memory; uploads / downloads of "
@@ -310,7 +309,7 @@ def run_ours(opt):
     }
     line["train"] = train_info
     if world == 1:
-        line["cpu_baseline"] = cpu_baseline(sample_rays=32768, repeats=1)     # ~8 s on the box's 16 host cores
+        line["cpu_baseline"] = cpu_baseline(sample_rays=REF_SAMPLE_RAYS, repeats=1)     # ~8 s on the box's 16 host cores
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -330,42 +329,79 @@ def run_train(rank, world, device, steps, warmup):
     caster.network.load_state_dict(syn.synthetic_params(0))
     n_poses, rpp = 16, 192
     full = syn.training_batch(n_poses, rpp, seed=0)
+    cfg = ("danbo_base --N_samples 64 --N_importance 16, 16 poses x 192 rays, perturb=1, raw_noise_std=1, L1 + "
+           "soft-softmax + volume-scale losses, Adam 5e-4; whole iteration (fwd, losses, bwd, NCCL all-reduce of the flat "
+           "9.8 MB gradient bucket, single-launch Adam) replayed as one CUDA graph")
+
+    def measure(batch, tag):
+        step = training.TrainStep(caster, args, world_size=world, graph=True)
+        torch.manual_seed(1234 + rank)
+        for _ in range(max(warmup, 3)):
+            step(batch)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss, _ = step(batch)
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1), float(loss)], device=device, dtype=torch.float64)
+        if world > 1:
+            ms = t[:1].clone()
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            ls = t[1:].clone()
+            dist.all_reduce(ls)                             # mean over ranks = the loss of the global batch
+            t = torch.cat([ms, ls / world])
+        return float(t[0]) / steps, float(t[1]), bool(step._graph_whole)
+
+    # strong scaling: the 3072-ray batch of config #3 split over the ranks (16 / world poses each)
     per = max(n_poses // world, 1)
     lo = (rank % (n_poses // per)) * per * rpp
-    hi = lo + per * rpp
-    batch = {k: (v[lo:hi].to(device) if torch.is_tensor(v) else v) for k, v in full.items()}
+    batch = {k: (v[lo:lo + per * rpp].to(device) if torch.is_tensor(v) else v) for k, v in full.items()}
     batch["N_uniques"] = per
-    step = training.TrainStep(caster, args, world_size=world, graph=True)
-    torch.manual_seed(1234 + rank)
-    for _ in range(max(warmup, 3)):
-        step(batch)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        loss, _ = step(batch)
-    e1.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms[0]) / steps
-    return {"metric": "training iterations/s (fwd+bwd+Adam)", "value": 1e3 / ms, "unit": "it/s", "ms_per_iter": ms,
+    ms, loss, whole = measure(batch, "strong")
+    info = {"metric": "training iterations/s (fwd+bwd+Adam)", "value": 1e3 / ms, "unit": "it/s", "ms_per_iter": ms,
             "global_rays": per * rpp * world, "rays_per_gpu": per * rpp, "samples_per_ray": args.N_samples + args.N_importance,
-            "scaling": "strong" if world <= n_poses else "weak", "loss": float(loss),
-            "config": "danbo_base --N_samples 64 --N_importance 16, 16 poses x 192 rays, perturb=1, raw_noise_std=1, L1 + "
-                      "soft-softmax + volume-scale losses, Adam 5e-4; grads all-reduced as one flat 9.8 MB bucket"}
+            "scaling": "strong" if world <= n_poses else "weak", "loss": loss, "loss_note": "mean over ranks after the "
+            "timed iterations, all starting from the same weights: equal across N up to the draws", "whole_iteration_graphed": whole,
+            "config": cfg}
+    if world > 1:
+        # weak scaling: every rank keeps a full 3072-ray batch (its own poses), global batch = world x 3072 rays
+        caster.network.load_state_dict(syn.synthetic_params(0))
+        own = syn.training_batch(n_poses, rpp, seed=100 + rank)
+        b2 = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in own.items()}
+        b2["N_uniques"] = n_poses
+        ms2, loss2, _ = measure(b2, "weak")
+        info["weak"] = {"value": 1e3 / ms2, "unit": "it/s", "ms_per_iter": ms2, "rays_per_gpu": n_poses * rpp,
+                        "global_rays": n_poses * rpp * world, "rays_per_s": n_poses * rpp * world * 1e3 / ms2, "loss": loss2}
+    else:
+        info["rays_per_s"] = n_poses * rpp * 1e3 / ms
+    return info
 
 
-def cpu_baseline(sample_rays=1024, repeats=1, threads=None, chunk=4096):
-    """The reference algorithm (oracle port, torch CPU ops like the reference itself) on the host cores, on a bounded
-    sample of the same workload, fed in the reference's own ray chunks (`batchify_rays`, core/trainer.py:75-90)."""
+# the bounded sample of the 261 121-ray image both arms quote the CPU figure on (the env override is for the unit test)
+REF_SAMPLE_RAYS = int(os.environ.get("DANBO_REF_SAMPLE_RAYS", "32768"))
+
+
+def workload_config(args, n_rays=None):
+    """`config` of the JSON line - identical for this repo's arm and the reference arm."""
+    return {"workload": f"danbo_fast {H}x{W} render, 1 synthetic 24-joint pose, {args.N_samples}+{args.N_importance} "
+                        "samples/ray, box-restricted rays (261121 rays/image), random-init weights",
+            "rays_per_image": 261121, "samples_per_ray": args.N_samples + args.N_importance, "chunk": args.chunk}
+
+
+def cpu_baseline(sample_rays=REF_SAMPLE_RAYS, repeats=1, threads=None):
+    """The reference's CPU implementation of the path on the host cores, on a bounded sample of the same workload.
+
+    kind "reference": the UNMODIFIED reference (baseline/_ref, copied by scripts/vendor_ref.sh; /root/reference in the
+    authoring container) through its own `render` (core/trainer.py:96-162: ray assembly + `batchify_rays` in
+    `args.chunk` = 4096-ray chunks, as `render_path` calls it per image, run_nerf.py:92-96) and its own GraphCaster, with
+    this repo's synthetic weights.  kind "port": the oracle restatement, only if the reference copy is absent."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import danbo_oracle as orc
     import danbo_b200 as db
     from danbo_b200 import synthetic as syn, skeleton as sk
     threads = threads or os.cpu_count()
@@ -376,37 +412,49 @@ def cpu_baseline(sample_rays=1024, repeats=1, threads=None, chunk=4096):
     n = min(sample_rays, b["ray_batch"].shape[0])
     lo = (b["ray_batch"].shape[0] - n) // 2
     rays = b["ray_batch"][lo:lo + n].contiguous()
-    P = syn.synthetic_params(0)
-    A = torch.from_numpy(sk.bone_align_transforms(syn.rest_pose())[0])
-    t = lambda a: torch.as_tensor(a)[None]
-    best = None
     cams = b["cams"][lo:lo + n]
+    chunk = args.chunk
+    import ref_harness as rh
+    if rh.available():
+        kind = "reference"
+        render, kw_test, rargs = rh.reference_render_setup("h36m_zju/danbo_fast.txt")
+        assert rargs.chunk == chunk and rargs.N_samples == args.N_samples and rargs.N_importance == args.N_importance
 
-    def run(s0, s1):
-        orc.render_rays(rays[s0:s1], t(pose["skts"]), t(pose["bones"]), t(pose["cyl"]), cams[s0:s1], A, P,
-                        args.N_samples, args.N_importance, rays_per_pose=s1 - s0, use_volume_near_far=True)
+        def run(m):
+            rh.reference_render_rays(render, kw_test, rargs, rays[:m, 0:3], rays[:m, 3:6], pose, cams[:m], H, W, 1.2 * H)
+    else:
+        kind = "port"
+        import danbo_oracle as orc
+        P = syn.synthetic_params(0)
+        A = torch.from_numpy(sk.bone_align_transforms(syn.rest_pose())[0])
+        t = lambda a: torch.as_tensor(a)[None]
+
+        def run(m):
+            for s0 in range(0, m, chunk):
+                s1 = min(m, s0 + chunk)
+                orc.render_rays(rays[s0:s1], t(pose["skts"]), t(pose["bones"]), t(pose["cyl"]), cams[s0:s1], A, P,
+                                args.N_samples, args.N_importance, rays_per_pose=s1 - s0, use_volume_near_far=True)
+    best = None
     with torch.no_grad():
-        run(0, min(n, chunk))                                # warm-up: one chunk
+        run(min(n, chunk))                                   # warm-up: one chunk
         for _ in range(repeats):
             t0 = time.perf_counter()
-            for s0 in range(0, n, chunk):
-                run(s0, min(n, s0 + chunk))
+            run(n)
             dt = time.perf_counter() - t0
             best = dt if best is None else min(best, dt)
-    return {"value": n / best, "unit": "rays/s", "cores": int(torch.get_num_threads()), "kind": "port",
-            "sample": f"{n} consecutive rays from the middle of the same {H}x{W} danbo_fast image in chunks of {chunk} rays, "
-                      f"fp32 torch CPU ops, best of {repeats} after a one-chunk warm-up ({best:.2f} s)"}
+    return {"value": n / best, "unit": "rays/s", "cores": int(torch.get_num_threads()), "kind": kind,
+            "sample": f"{n} consecutive rays from the middle of the same {H}x{W} danbo_fast image, rendered in chunks of "
+                      f"{chunk} rays, fp32 torch CPU ops, best of {repeats} after a one-chunk warm-up ({best:.2f} s)"}
 
 
 def run_reference(opt):
+    """The reference arm: the reference's own CPU implementation on the host cores (rank 0 only), each step one bounded
+    sample (REF_SAMPLE_RAYS rays) of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = 2048
-    # each step = one bounded sample of the workload
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    res = []
-    base = None
+    n = REF_SAMPLE_RAYS
+    res, base = [], None
     for i in range(opt.warmup + opt.steps):
         base = cpu_baseline(sample_rays=n, repeats=1)
         if i >= opt.warmup:
@@ -417,12 +465,10 @@ def run_reference(opt):
     line = {"impl": "reference", "metric": "DANBO render rays/s (fwd+composite)", "value": v, "unit": "rays/s",
             "n_gpus": opt.gpus, "steps": opt.steps, "warmup": opt.warmup, "ms_per_step": n / v * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"danbo_fast {H}x{W} render, 1 synthetic 24-joint pose, {args.N_samples}+{args.N_importance} "
-                                   f"samples/ray, box-restricted rays, random-init weights",
-                       "samples_per_ray": args.N_samples + args.N_importance, "chunk": args.chunk,
-                       "parallelism": f"host CPU, {base['cores']} threads (rank 0 only)",
-                       "sample": f"each step = {n} consecutive rays from the middle of the image (bounded sample of the "
-                                 "same workload)"},
+            "config": workload_config(args),
+            "run": {"parallelism": f"host CPU, {base['cores']} threads (rank 0 only)",
+                    "sample": f"each step = {n} consecutive rays from the middle of the image (bounded sample of the same "
+                              "workload); rays/s does not depend on the sample size beyond one 4096-ray chunk"},
             "cpu_baseline": dict(base, value=v),
             "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}

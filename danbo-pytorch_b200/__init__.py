@@ -9,9 +9,10 @@ csrc/, reached only through the C ABI declared in include/danbo_b200.h (ctypes, 
 There is no CPU fallback: calling any kernel entry without the built library raises.
 """
 from . import skeleton, synthetic, params, config  # noqa: F401
-from . import _lib, build, kernels, networks, raycaster, anerf, parallel, training, render, feed, pose_opt, mesh  # noqa: F401
+from . import _lib, build, kernels, networks, raycaster, anerf, parallel, training, render, feed, pose_opt, mesh, dropin  # noqa: F401
 from .raycaster import RayCaster, GraphCaster, create_raycaster  # noqa: F401
 from .config import make_args  # noqa: F401
+from .dropin import install, uninstall  # noqa: F401
 
 __all__ = ["skeleton", "synthetic", "params", "config", "kernels", "networks", "raycaster", "RayCaster",
            "GraphCaster", "create_raycaster", "make_args", "build"]

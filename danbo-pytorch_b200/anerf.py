@@ -253,12 +253,13 @@ _ANERF_SUPPORTED = {"align_bones": ("align",), "density_type": ("relu",), "kp_di
 
 def check_anerf_args(args):
     """The flag subset of configs/*/anerf_base.txt that selects this path; anything else raises."""
+    from .raycaster import _flag
     for k, allowed in _ANERF_SUPPORTED.items():
-        v = getattr(args, k, allowed[0])
+        v = _flag(args, k)
         if v not in allowed:
             raise NotImplementedError(f"{k}={v!r} is not implemented for nerf_type='nerf' (supported: {allowed})")
     for k, want in _ANERF_REQUIRED.items():
-        v = getattr(args, k, want)
+        v = _flag(args, k)
         if v != want:
             raise NotImplementedError(f"{k}={v!r} is not implemented for nerf_type='nerf' (kernels are built for {k}={want!r})")
     if getattr(args, "netwidth_view", None) not in (None, 224):

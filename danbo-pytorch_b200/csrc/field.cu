@@ -381,6 +381,7 @@ pair_bucket_kernel(const uint32_t* __restrict__ mask, const int* __restrict__ ac
                 if ((m >> j) & 1u) {
                     const int at = base[j] + woff + __popc(b & ((1u << lane) - 1));
                     if (at < pair_capacity) pw.pairs()[at] = e;
+                    else pw.base[DANBO_PAIR_OVERFLOW_WORD] = 1;       // more visible pairs than the caller sized `work` for
                 }
             }
         }
@@ -530,9 +531,12 @@ field_rows_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, in
                   const float* __restrict__ logits, uint8_t* __restrict__ xtiles, int* __restrict__ row_ray,
                   float* __restrict__ hbar_out /* (rows,16) or null */,
                   __nv_bfloat16* __restrict__ x_rows /* (rows,208) row-major copy for the backward pass, or null */,
-                  int agg_mode /* 0 sigmoid, 1 masked softmax */) {
+                  int agg_mode /* 0 sigmoid, 1 masked softmax */, const int* __restrict__ work) {
     int count = *active_count; if (count > capacity) count = capacity;
     const int total = n_rays * S;
+    // pair list overflow (pair_bucket dropped pairs, so some logits were never written): every row of this call is
+    // poisoned with NaN - the caller sees NaN pixels / a NaN loss instead of silently wrong densities
+    const float poison = work[DANBO_PAIR_OVERFLOW_WORD] ? __int_as_float(0x7fc00000) : 0.f;
     // A lane owns a row, and a row's 16-byte pieces lie in different 128-byte lines of the tile image (one LSU pass per
     // lane per store, partial-line writes in L2).  Each warp therefore assembles its 32 rows of one 64-column chunk
     // (4 KB, contiguous in the image) in shared memory and sends it with a bulk copy; two buffers per warp.
@@ -574,6 +578,10 @@ field_rows_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, in
 #pragma unroll
                 for (int i = 0; i < DANBO_FEAT; ++i) hbar[i] = fmaf(p, h[i], hbar[i]);
             }
+        }
+        if (poison != 0.f) {
+#pragma unroll
+            for (int i = 0; i < DANBO_FEAT; ++i) hbar[i] = poison;
         }
         if (live) row_ray[e] = n;
         if (hbar_out && live) {
@@ -794,7 +802,7 @@ extern "C" int danbo_field_agg(const float* rays, int ray_stride, int n_rays, in
     if (rblocks > num_sms * 16) rblocks = num_sms * 16;
     field_rows_kernel<<<rblocks, 128, 0, st>>>(rays, ray_stride, n_rays, S, z, mask, active_ids, active_count, capacity,
                                                 pose_skts, pose_vol, rays_per_pose, n_poses, fc, logits,
-                                                (uint8_t*)xtiles, row_ray, hbar_out, (__nv_bfloat16*)x_rows, agg_mode);
+                                                (uint8_t*)xtiles, row_ray, hbar_out, (__nv_bfloat16*)x_rows, agg_mode, work);
     DANBO_CHECK_LAUNCH();
     return 0;
 }

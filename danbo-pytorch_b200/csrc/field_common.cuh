@@ -63,7 +63,8 @@ __device__ __forceinline__ void bone_coords(const float* __restrict__ skt, const
     x2 = __fdiv_rn(t2, fabsf(__ldg(scale + 2)));
 }
 
-struct PairWork {            // int workspace: [0,24) count per bone, [24,48) scatter cursor, [64, 64+cap) pairs
+#define DANBO_PAIR_OVERFLOW_WORD 48   // work[48] != 0: pair_bucket saw more visible pairs than pair_capacity
+struct PairWork {            // int workspace: [0,24) count per bone, [24,48) scatter cursor, [48] overflow flag, [64, 64+cap) pairs
     int* base;
     __device__ __forceinline__ int* count() const { return base; }
     __device__ __forceinline__ int* cursor() const { return base + 24; }

@@ -183,12 +183,20 @@ class FieldOut:
     """What danbo_field_agg produced for one pass (kept whole in train mode: the backward reuses the pair lists)."""
     __slots__ = ("xtiles", "row_ray", "logits", "hbar", "x_rows", "work", "pair_cap", "agg_mode")
 
+    def overflowed(self):
+        """True if the call saw more visible (row, bone) pairs than its workspace held (host read: synchronises).  The
+        call's rows are NaN in that case."""
+        return bool(self.work[48].item())
+
 
 AGG_MODES = {"sigmoid": 0, "softmax": 1}
 
 
+WORST_CASE_PAIR_ROWS = 65536      # up to this many rows the pair workspace is sized for 24 visible bones per row
+
+
 def field_agg(rays, S, z, mask, active, pose_skts, pose_vol, rays_per_pose, consts, want_hbar=False,
-              want_xrows=False, pairs_per_row=6, agg_mode=0):
+              want_xrows=False, pairs_per_row=None, agg_mode=0):
     """-> FieldOut: xtiles (uint8 tiles), row_ray (cap) int32, logits (n*S,24) [visible entries only; all 24 entries
     of every active row with agg_mode 1], hbar (cap,16) / x_rows (cap,208 bf16) when asked.
     agg_mode: AGG_MODES[agg_type] (0 sigmoid, 1 masked softmax, which evaluates every bone of an active row)."""
@@ -203,6 +211,14 @@ def field_agg(rays, S, z, mask, active, pose_skts, pose_vol, rays_per_pose, cons
     o.logits = torch.empty(n * S, J, device=dev, dtype=torch.float32)
     o.hbar = torch.empty(active.capacity, 16, device=dev, dtype=torch.float32) if want_hbar else None
     o.x_rows = torch.empty(active.capacity, 208, device=dev, dtype=torch.bfloat16) if want_xrows else None
+    if pairs_per_row is None:
+        # a sample can lie in all 24 bone boxes, but `capacity` of the render / training calls counts every sample of
+        # the batch while only the samples inside at least one box (15 % on the 512x512 image, with 1.3 visible bones
+        # each) own pairs: 6 per row of capacity is > 24 per active row as long as <= 25 % of the samples are active.
+        # Small calls (density queries at points that may all sit inside the torso) get the exact worst case.  Beyond
+        # that an overflow is detected on the device: work[48] is set and every row of the call becomes NaN
+        # (`FieldOut.overflowed()` reads the flag; render_pts_density re-runs with the worst-case size).
+        pairs_per_row = J if active.capacity <= WORST_CASE_PAIR_ROWS else 6
     if agg_mode == 1:
         pairs_per_row = J
     o.pair_cap = int(pairs_per_row) * active.capacity + 24 * 32

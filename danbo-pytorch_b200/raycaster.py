@@ -402,6 +402,10 @@ class RayCaster(nn.Module):
         # append_empty=2: one extra entry (id 2P-1) carries sigma of a point that no bone sees (h = 0)
         _, mask, act = K.sample_mask(rays, 1, p_skts, P, consts, z_in=z, append_empty=2, capacity=P + 1)
         fo = K.field_agg(rays, 1, z, mask, act, p_skts, vol, P, consts, agg_mode=self.network.agg_mode)
+        if not torch.cuda.is_current_stream_capturing() and fo.overflowed():
+            # a dense lattice inside the body: more than 6 visible bones per point on average -> worst-case workspace
+            fo = K.field_agg(rays, 1, z, mask, act, p_skts, vol, P, consts, agg_mode=self.network.agg_mode,
+                             pairs_per_row=K.J)
         sigma = torch.empty(2 * P, device=dev)
         K.mlp_forward(fo.xtiles, packed, None, act, fo.row_ray, sigma, density_only=True)
         out = torch.where(mask.reshape(-1) != 0, sigma[:P], sigma[2 * P - 1])
@@ -435,19 +439,30 @@ _REQUIRED = {"netdepth": 8, "netwidth": 256, "agg_W": 32, "agg_D": 3, "node_W": 
              "align_corners": False, "vol_cal_scale": True}
 
 
+def _flag(args, k):
+    """A flag's value; a flag the namespace does not carry has the reference CLI's own default (run_nerf.py:186-572,
+    config.DEFAULTS), exactly what the reference's parser would have filled in - never "whatever is supported"."""
+    from .config import DEFAULTS
+    if hasattr(args, k):
+        return getattr(args, k)
+    if k in DEFAULTS:
+        return DEFAULTS[k]
+    raise NotImplementedError(f"flag {k!r} is missing from args and has no reference default on record")
+
+
 def check_args(args):
     """The flag subset that selects this path (SURVEY §8a 'config' row); anything else raises."""
     for k, allowed in _SUPPORTED.items():
-        v = getattr(args, k, allowed[0])
+        v = _flag(args, k)
         if v not in allowed:
             raise NotImplementedError(f"{k}={v!r} is not implemented by danbo_b200 (supported: {allowed})")
     for k, want in _REQUIRED.items():
-        v = getattr(args, k, want)
+        v = _flag(args, k)
         if v != want:
             raise NotImplementedError(f"{k}={v!r} is not implemented by danbo_b200 (kernels are built for {k}={want!r})")
-    if getattr(args, "netwidth_view", None) not in (None, 128):
+    if _flag(args, "netwidth_view") not in (None, 128):
         raise NotImplementedError("netwidth_view must be None/128")
-    view = (getattr(args, "view_type", "identity"), getattr(args, "ray_tr_type", "world"))
+    view = (_flag(args, "view_type"), _flag(args, "ray_tr_type"))
     if view not in (("identity", "world"), ("relray", "root_local")):
         raise NotImplementedError(f"view_type / ray_tr_type = {view}: the shipped pairs are identity + world "
                                   "(h36m_zju, surreal) and relray + root_local (perfcap)")

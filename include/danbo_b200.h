@@ -67,7 +67,9 @@ int danbo_sample_mask(const float* rays, int ray_stride, int n_rays, int S, cons
  * ((capacity+127)/128 tiles of 64 KB, swizzled MMA operand image), row_ray[row], the blend logits ("confd") of every
  * visible (sample, bone) into logits (n_rays*S,24) and optionally hbar (rows,16) and x_rows (rows,208 bf16, a
  * row-major copy of the encoded rows for the backward pass).
- * work: int workspace of 64 + pair_capacity entries; pair_capacity >= number of visible pairs + 24*32.
+ * work: int workspace of 64 + pair_capacity entries; pair_capacity >= number of visible pairs + 24*32 (worst case
+ * 24 * rows + 24*32).  If there are more visible pairs than that, work[48] is set to 1 and EVERY row of the call is
+ * written as NaN (never a silently wrong value); the caller re-runs with a larger workspace.
  * agg_mode 0: sigmoid blend weights (danbo.py:406-415, every shipped config).  agg_mode 1: agg_type = softmax with
  * mask_vol_prob (danbo.py:388-404); its max runs over all 24 logits, so every bone of an active row is evaluated
  * (pair_capacity >= 24 * rows + 24*32) and logits holds all 24 entries of those rows. */

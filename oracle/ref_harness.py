@@ -1,7 +1,10 @@
-"""Runs the UNMODIFIED reference from /root/reference (authoring container only).  TEST INFRASTRUCTURE.
+"""Runs the UNMODIFIED reference: /root/reference in the authoring container, else the git-ignored copy under
+baseline/_ref/ that scripts/vendor_ref.sh makes (it travels to the GPU box).  TEST / BASELINE INFRASTRUCTURE - nothing
+in the product imports this.
 
-Used by oracle/gen_golden.py to pin the oracle and by tests/test_oracle_vs_reference.py (skipped when
-/root/reference is absent, i.e. on the GPU box).  Needs only import stubs for packages that are not installed
+Used by oracle/gen_golden.py to pin the oracle, by tests/test_oracle_vs_reference.py, by the drop-in tests
+(tests/test_gpu_dropin.py: the reference's own Trainer / render_path driving this repo's ray caster) and by bench.py's
+reference arm / cpu_baseline (the reference's own `render`, core/trainer.py:96-162, on the host cores).  Needs only import stubs for packages that are not installed
 (SURVEY §8c): pytorch3d's three rotation conversions (published formula), empty plotly/matplotlib, an argparse
 shim for configargparse, and empty h5py/imageio/deepdish/smplx/pytorch_msssim.  Two compatibility shims:
 F6 (np.float32 widths into a tensor under numpy 2) and F5 (A-NeRF ctor kwargs).
@@ -13,7 +16,9 @@ import tempfile
 import numpy as np
 import torch
 
-REF = os.environ.get("DANBO_REFERENCE", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CANDIDATES = [os.environ.get("DANBO_REFERENCE"), "/root/reference", os.path.join(os.path.dirname(_HERE), "baseline", "_ref")]
+REF = next((c for c in _CANDIDATES if c and os.path.isdir(os.path.join(c, "core"))), "/root/reference")
 STUBS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_stubs")
 
 
@@ -82,3 +87,31 @@ def load_weights(caster, sd):
         own[k] = v.clone()
     net.load_state_dict(own)
     return {k: v.clone() for k, v in net.state_dict().items()}
+
+
+def reference_render_setup(preset_config="h36m_zju/danbo_fast.txt", device="cpu", weight_seed=0, extra=()):
+    """-> (render_fn, kw_test): the reference ray caster with this repo's synthetic weights on `device`, and the reference's
+    own `render` (core/trainer.py:96-162: ray batch assembly + `batchify_rays` in `chunk`s)."""
+    rc, _ = _imports()
+    from core.trainer import render
+    root = os.path.dirname(_HERE)
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    from danbo_b200 import synthetic as syn
+    args = parse_args(preset_config, extra)
+    caster, kw_test = build(args, syn.rest_pose())
+    load_weights(caster, syn.synthetic_params(weight_seed))
+    caster.to(device)
+    caster.eval()
+    return render, kw_test, args
+
+
+def reference_render_rays(render, kw_test, args, rays_o, rays_d, pose, cams, H, W, focal, device="cpu"):
+    """One call of the reference's `render` on a ray set of one pose (what `render_path` does per image,
+    run_nerf.py:92-96).  pose: dict with kps / skts / bones / cyl arrays.  -> dict of outputs."""
+    n = rays_o.shape[0]
+    t = lambda a: torch.as_tensor(a, dtype=torch.float32, device=device)[None].expand(n, *np.shape(a))
+    with torch.no_grad():
+        return render(H, W, focal, rays=(rays_o.to(device), rays_d.to(device)), chunk=args.chunk,
+                      kp_batch=t(pose["kps"]), skts=t(pose["skts"]), cyls=t(pose["cyl"]), bones=t(pose["bones"]),
+                      cams=cams.to(device), **kw_test)

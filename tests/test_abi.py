@@ -106,19 +106,24 @@ def test_ctypes_signatures_match_header_parameters():
 
 
 def test_reference_arm_prints_the_contract_line():
-    """`bench.py --impl reference` (the oracle port on the host cores) prints one JSON line with the keys the driver reads."""
+    """`bench.py --impl reference` (the unmodified reference from baseline/_ref or /root/reference on the host cores; the
+    oracle port only where neither exists) prints one JSON line with the keys the driver reads."""
     import json
     import subprocess
     import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_harness
+    env = dict(os.environ, DANBO_REF_SAMPLE_RAYS="4096")          # one reference chunk: keeps the CPU suite short
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
-                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+                         capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in line, k
     assert line["impl"] == "reference" and line["unit"] == "rays/s" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["kind"] == ("reference" if ref_harness.available() else "port")
+    assert line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in line["config"]
 
 
