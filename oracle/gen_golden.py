@@ -348,8 +348,13 @@ def run_train_case(name, config, extra, n_poses, rays_per_pose, weight_seed=0, b
     for k, v in loss_dict.items():
         fx["loss." + k] = v.detach()
     kinds = [k for k, _ in tape.tape]
-    assert kinds == ["rand", "randn", "rand", "randn"], kinds
-    for nm, (_, t) in zip(("t_rand", "noise0", "u", "noise1"), tape.tape):
+    if args.raw_noise_std > 0:
+        assert kinds == ["rand", "randn", "rand", "randn"], kinds
+        names = ("t_rand", "noise0", "u", "noise1")
+    else:                                                    # no density noise drawn (nerf.py:314-316)
+        assert kinds == ["rand", "rand"], kinds
+        names = ("t_rand", "u")
+    for nm, (_, t) in zip(names, tape.tape):
         fx["rand." + nm] = t
     for k, v in ret.items():
         fx["out." + k] = v.detach()
@@ -419,6 +424,9 @@ def main():
         run_train_case("train_fast_popt", "h36m_zju/danbo_fast.txt", [], n_poses=4, rays_per_pose=48, batch_seed=1,
                        pose_grads=True)
         return
+    if only == "train_nonoise":
+        nonoise()
+        return
     if only == "train_perfcap":
         run_train_case("train_perfcap", "perfcap/danbo_fast.txt", [], n_poses=4, rays_per_pose=48, batch_seed=3)
         return
@@ -462,6 +470,15 @@ def main():
     # gradients with respect to the pose tensors (skts, bones): pins the oracle ahead of the backward-to-poses kernels
     run_train_case("train_fast_popt", "h36m_zju/danbo_fast.txt", [], n_poses=4, rays_per_pose=48, batch_seed=1,
                    pose_grads=True)
+    nonoise()
+
+
+def nonoise():
+    """The two training cases again with --raw_noise_std 0: without the reference's random density gate
+    (relu(raw + noise)) the end-to-end gradient comparison measures the kernels, not which samples the noise kept."""
+    run_train_case("train_fast_nonoise", "h36m_zju/danbo_fast.txt", ["--raw_noise_std", "0"], n_poses=4, rays_per_pose=48)
+    run_train_case("train_cfg3_nonoise", "h36m_zju/danbo_base.txt",
+                   ["--N_samples", "64", "--N_importance", "16", "--raw_noise_std", "0"], n_poses=2, rays_per_pose=32)
 
 
 def variants():

@@ -1,18 +1,13 @@
-"""GPU checks of host-level paths that were written without GPU access at the end of round 1 (run with -m gpu): the
-stream-pipelined ray blocks (`raycaster.BLOCK_STREAMS`), mesh extraction on the device, the perfcap / surreal config
-variants of the view branch (render and training).  No new kernel runs here - the riskier tensor-core aggregation kernel
-has its own file, which sorts after this one.
-
-STATUS: NOT yet run on hardware.  `xfail(strict=False)` with a timeout and late in the `-m gpu` order, so a failure cannot
-stop the `-x` run of the verified tests; remove the marker once green."""
+"""GPU checks of host-level paths (run with -m gpu): the stream-pipelined ray blocks (`raycaster.BLOCK_STREAMS`), mesh
+extraction on the device, the perfcap / surreal config variants of the view branch (render and training).  First run on
+hardware in round 2 (gpurun_out/r2a_gpu_unverified.log)."""
 import pytest
 import torch
 
 import danbo_oracle as orc
 from util import load_fixture, params_for, align_A, make_caster, preset_of, agg_type_of, pose_tensors
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300, method="thread"),   # a hung kernel must not hang the box
-              pytest.mark.xfail(strict=False, reason="host-level paths not yet run on hardware (written without GPU access)")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300, method="thread")]   # a hung kernel must not hang the box
 DEV = "cuda"
 
 
@@ -103,14 +98,20 @@ def test_render_other_shipped_configs(name):
     for k in ("rgb0", "acc0", "rgb_map", "acc_map"):
         e = (out[k].cpu() - fx["out." + k]).abs()
         print(f"[configs] {name} {k}: mean {float(e.mean()):.3e} max {float(e.max()):.3e}")
-        assert float(e.mean()) <= 4e-3 and float(e.flatten().quantile(0.99)) <= 5e-2 and float(e.max()) <= 0.2, k
+        assert float(e.mean()) <= 4e-3 and float(e.max()) <= 0.2, k
+    from util import pixel_parity
+    kw = dict(N_samples=args.N_samples, kp_batch=ex(fx["pose_kps"][None]), skts=ex(skts), cyls=ex(cyl), bones=ex(bones),
+              cams=cams, N_uniques=1, perturb=False, N_importance=args.N_importance, raw_noise_std=0.)
+    pixel_parity(caster, fx, kw, name)
 
 
 @pytest.mark.parametrize("name", ["train_surreal", "train_perfcap"])
 def test_training_step_other_shipped_configs(name):
     """configs/surreal training (MSE loss, no frame codes: the autograd node runs on a zero-padded view weight and the
     283-column gradient must come back) and configs/perfcap training (root-local view directions of four poses): loss and
-    parameter gradients against the oracle's (bounds of test_gpu_training.py::test_training_step_gradients[train_fast])."""
+    parameter gradients against the oracle's autograd on the same samples.  Both sides run with raw_noise_std = 0 (the
+    fixture's other draws are kept): the reference's random density gate relu(raw + noise) would otherwise turn bf16-sized
+    differences of raw into flipped gates (see test_gpu_training.py::test_training_step_gradients)."""
     from danbo_b200 import synthetic as syn, skeleton as sk
     from util import config_flags_of, view_mode_of
     fx = load_fixture(name)
@@ -125,7 +126,7 @@ def test_training_step_other_shipped_configs(name):
     out = caster.render_rays(b["ray_batch"], N_samples=args.N_samples, kp_batch=b["kp_batch"], skts=b["skts"],
                              cyls=b["cyls"], bones=b["bones"], cams=b["cams"] if has_codes else None, N_uniques=n_poses,
                              perturb=1.0,
-                             N_importance=args.N_importance, raw_noise_std=float(fx["raw_noise_std"]),
+                             N_importance=args.N_importance, raw_noise_std=0.,
                              _rand={k: v.to(DEV) for k, v in rand.items()}, _stages=stages)
     P = {k: v.clone().requires_grad_(v.dtype.is_floating_point and not k.endswith(".adj")) for k, v in params_for(fx).items()}
     dev_out = {k: v for k, v in out.items()}
@@ -136,7 +137,7 @@ def test_training_step_other_shipped_configs(name):
     ref = orc.render_rays(b["ray_batch"], b["skts"][::rpp], b["bones"][::rpp], b["cyls"][::rpp], b["cams"], align_A(), P,
                           int(fx["N_samples"]), int(fx["N_importance"]), rays_per_pose=rpp,
                           use_volume_near_far=bool(fx["use_volume_near_far"]), training=True, rand=rand,
-                          raw_noise_std=float(fx["raw_noise_std"]), z_samples=stages["z_samples"].cpu(),
+                          raw_noise_std=0., z_samples=stages["z_samples"].cpu(),
                           view_mode=view_mode_of(fx))
     ref_loss = orc.training_loss(ref, b["target_s"], b["bgs"], P, init_scale, loss_fn=loss_fn)
     ref_loss.backward()
@@ -152,4 +153,4 @@ def test_training_step_other_shipped_configs(name):
         cos = float(torch.dot(a, r) / (a.norm() * r.norm() + 1e-30))
         rel = float((a - r).norm() / max(float(r.norm()), 1e-3 * big))
         print(f"[{name}] {k:40s} cos {cos:.5f} rel {rel:.3e}")
-        assert (float(r.norm()) <= 1e-3 * big or cos >= 0.985) and rel <= 0.2, (k, cos, rel)
+        assert (float(r.norm()) <= 1e-3 * big or cos >= 0.999) and rel <= 2e-2, (k, cos, rel)

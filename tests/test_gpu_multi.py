@@ -73,17 +73,17 @@ def _single_gpu_reference(path):
                path)
 
 
-def _worker(rank, world, port, ref_path, out_path):
+def _say(rank, msg):
+    print(f"[multi rank {rank}] {msg}", flush=True)
+
+
+def worker_main(ref_path, out_path):
+    """Body of one rank (launched by torch.distributed.run, like bench.py at N > 1)."""
     import torch.distributed as dist
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
-                      LOCAL_RANK=str(rank))
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for p in (root, os.path.join(root, "tests")):
-        if p not in sys.path:
-            sys.path.insert(0, p)
-    torch.cuda.set_device(rank)
-    dev = torch.device("cuda", rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from danbo_b200 import parallel
+    rank, world, local = parallel.init_distributed()
+    dev = torch.device("cuda", local)
+    _say(rank, f"init done, world {world}")
     ref = torch.load(ref_path)
     res = {}
     rel = lambda a, b: float((a - b).norm() / b.norm().clamp_min(1e-30))
@@ -98,10 +98,12 @@ def _worker(rank, world, port, ref_path, out_path):
     res["grad_rel"] = rel(step.bucket.flat.cpu(), ref["grad"])
     res["loss0"] = float(lt) / world
     res["loss0_ref"] = ref["loss0"]
-    # (2) graphed iterations: forward + backward + all-reduce + Adam in one captured graph
+    _say(rank, f"gradient check done: rel {res['grad_rel']:.3e}")
+    # (2) graphed iterations: forward + backward + all-reduce + Adam in one captured graph; (3) the same, eager
     for tag, graph in (("graph", True), ("eager", False)):
         _, _, st = _setup(dev, world=world, graph=graph)
         losses = _train(st, b, ITERS).to(dev)
+        _say(rank, f"{tag}: {ITERS} iterations done")
         dist.all_reduce(losses)
         losses = (losses / world).cpu()
         res[tag + "_whole_graph"] = bool(st._graph_whole)
@@ -115,15 +117,28 @@ def _worker(rank, world, port, ref_path, out_path):
             json.dump(res, f)
     dist.barrier()
     dist.destroy_process_group()
+    _say(rank, "done")
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
 def test_two_rank_training_equals_single_gpu():
-    import torch.multiprocessing as mp
+    import signal
+    import subprocess
     with tempfile.TemporaryDirectory() as d:
         ref_path, out_path = os.path.join(d, "ref.pt"), os.path.join(d, "out.json")
         _single_gpu_reference(ref_path)
-        mp.spawn(_worker, args=(2, _free_port(), ref_path, out_path), nprocs=2, join=True)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+               "127.0.0.1", "--master-port", str(_free_port()), os.path.abspath(__file__), ref_path, out_path]
+        # own process group + a hard limit: a hung collective must not outlive the test
+        proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, start_new_session=True)
+        try:
+            log, _ = proc.communicate(timeout=300)
+        except subprocess.TimeoutExpired:
+            os.killpg(proc.pid, signal.SIGKILL)
+            log, _ = proc.communicate()
+            pytest.fail("2-rank worker hung:\n" + log[-4000:])
+        print(log[-3000:])
+        assert proc.returncode == 0, log[-4000:]
         res = json.load(open(out_path))
     print("[multi]", json.dumps(res))
     assert res["grad_rel"] <= 2e-3, res                      # fp32 atomics order + per-shard near/far fill only
@@ -171,3 +186,11 @@ def test_graph_build_has_no_side_effect_and_sees_new_weights():
     assert not torch.equal(g0["rgb_map"], g1["rgb_map"])
     for k in ("rgb_map", "acc_map", "rgb0"):
         assert torch.equal(g1[k], e1[k]), k
+
+
+if __name__ == "__main__":                                  # one rank of test_two_rank_training_equals_single_gpu
+    _root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for _p in (_root, os.path.join(_root, "tests")):
+        if _p not in sys.path:
+            sys.path.insert(0, _p)
+    worker_main(sys.argv[1], sys.argv[2])

@@ -277,11 +277,15 @@ def test_render_rays_end_to_end(name):
     if want_empty.numel():
         e = _report(name + " raw0 (empty samples)", empty[:, None].expand(-1, args.N_samples, -1)[~act], want_empty)
         assert float(e.max()) <= 3e-2 * float(fx["st.raw.0"].abs().max())
-    for k, tol_mean in (("rgb0", 4e-3), ("acc0", 4e-3), ("rgb_map", 4e-3), ("acc_map", 4e-3)):
+    for k in ("rgb0", "acc0"):                # coarse pass: identical sample positions -> the bf16 MLP error alone
         e = _report(f"{name} {k}", out[k], fx["out." + k])
-        # mean / p99 bound the bf16 error; single rays can move further when a fine sample crosses a bone-box face
-        assert float(e.mean()) <= tol_mean, (k, float(e.mean()))
-        assert float(e.flatten().quantile(0.99)) <= 5e-2 and float(e.max()) <= 0.2, (k, float(e.max()))
+        assert float(e.mean()) <= 1e-3 and float(e.max()) <= 1.5e-2, (k, float(e.mean()), float(e.max()))
+    # fine pass: at the reference's importance samples (tight), and free-running with every outlier accounted for
+    from util import pixel_parity
+    kw = dict(N_samples=args.N_samples, kp_batch=ex(fx["pose_kps"][None]), skts=ex(skts), cyls=ex(cyl), bones=ex(bones),
+              cams=fx["cams"], N_uniques=1, perturb=False, N_importance=args.N_importance, raw_noise_std=0.,
+              lindisp=args.lindisp)
+    pixel_parity(caster, fx, kw, name)
     assert out["alpha"].shape == fx["out.alpha"].shape and out["T_i"].shape == fx["out.T_i"].shape
     assert torch.isfinite(out["rgb_map"]).all()
 

@@ -34,15 +34,19 @@ def torch_loss(ret, target, bgs, axis_scale, init_scale, agg_type="sigmoid"):
     return loss + 0.001 * torch.prod(scale, dim=-1).sum()
 
 
-@pytest.mark.parametrize("name", ["train_fast", "train_cfg3", "train_fast_softmax"])
+@pytest.mark.parametrize("name", ["train_fast", "train_cfg3", "train_fast_softmax", "train_fast_nonoise", "train_cfg3_nonoise"])
 def test_training_step_gradients(name):
+    """End-to-end parameter gradients of one training step against the oracle's autograd on the same samples.  The
+    `*_nonoise` fixtures (--raw_noise_std 0) carry the tight bound: with the shipped raw_noise_std = 1 the reference gates
+    every density with relu(raw + N(0,1)), so a bf16-sized change of raw flips gates and the comparison measures the
+    noise, not the kernels."""
     from danbo_b200 import synthetic as syn, skeleton as sk
     fx = load_fixture(name)
     agg = agg_type_of(fx)
     caster, args, _ = make_caster(preset_of(fx), train=True, agg_type=agg)
     b = syn.training_batch(int(fx["n_poses"]), int(fx["rays_per_pose"]), seed=int(fx["batch_seed"]))
     rpp = int(fx["rays_per_pose"])
-    rand = {k: fx["rand." + k] for k in ("t_rand", "noise0", "u", "noise1")}
+    rand = {k: fx["rand." + k] for k in ("t_rand", "noise0", "u", "noise1") if ("rand." + k) in fx}
     init_scale = sk.initial_axis_scale(sk.skeleton_profile(syn.rest_pose()), 0.4)
     # ---- CUDA path
     stages = {}
@@ -86,7 +90,8 @@ def test_training_step_gradients(name):
         print(f"[train] {name} {k:40s} |g| {rn:.3e} cos {cos:.5f} rel {rel:.3e} | vs reference samples {ref_err:.3e}")
         # softmax blend weights sum to ~1 over the visible bones (sigmoid ones sit near 0.5 each at random init), so the
         # same bf16 / noise-gate flips move the bone-volume gradients about twice as far: measured cos >= 0.974
-        cos_min, rel_max = {"train_fast": (0.985, 0.2), "train_fast_softmax": (0.965, 0.3)}.get(name, (0.85, 0.8))
+        cos_min, rel_max = {"train_fast": (0.985, 0.2), "train_fast_softmax": (0.965, 0.3),
+                            "train_fast_nonoise": (0.999, 2e-2), "train_cfg3_nonoise": (0.999, 2e-2)}.get(name, (0.85, 0.8))
         if (rn > 1e-3 * big and cos < cos_min) or rel > rel_max:
             bad.append((k, cos, rel))
     assert not bad, bad
