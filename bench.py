@@ -146,12 +146,29 @@ def run_ours(opt):
     # every rank renders a fixed number of rays per step: exchange the shard sizes once, not per step
     shard_sizes = parallel.gather_sizes(n_rays, device) if world > 1 else None
 
-    def step_device(graphed=True):
+    # N > 1: the pixel all-gather of step i runs on a communication stream while step i+1 renders (the exchange is
+    # 5 MB per rank; issued on the render stream it is a per-step rendezvous of all ranks).  The timed region ends only
+    # after the last gather has completed.
+    main_stream = torch.cuda.current_stream()
+    comm = torch.cuda.Stream() if world > 1 else None
+    rendered = [torch.cuda.Event() for _ in range(2)]
+    gathered = [None, None]
+
+    def step_device(graphed=True, i=0):
         ret = caster.render_graphed(rays_dev, **kw_dev) if graphed else caster(rays_dev, **kw_dev)
-        pix = parallel.pack_pixels(ret)
+        pix = parallel.pack_pixels(ret)                      # a fresh (n,5) tensor: the graph's static outputs are free again
         if world > 1:
-            pix = parallel.allgather_rows(pix, shard_sizes)
+            b = i & 1
+            rendered[b].record(main_stream)
+            with torch.cuda.stream(comm):
+                comm.wait_event(rendered[b])
+                gathered[b] = parallel.allgather_rows(pix, shard_sizes)
+            pix.record_stream(comm)
         return pix
+
+    def drain():
+        if world > 1:
+            main_stream.wait_stream(comm)
 
     # pinned host inputs for the end-to-end path
     rays_host = batch["ray_batch"].pin_memory()
@@ -167,9 +184,10 @@ def run_ours(opt):
         torch.cuda.current_stream().synchronize()
         return pix_host
 
-    for _ in range(max(opt.warmup, 3)):
-        step_device()
+    for i in range(max(opt.warmup, 3)):
+        step_device(i=i)
         flush.fill_(1)
+    drain()
     _mark("warmup issued")
     barrier()
     _mark("warmup done")
@@ -179,20 +197,25 @@ def run_ours(opt):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(opt.steps)]
     barrier()
     t_wall0 = time.perf_counter()
+    tail0, tail1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for i in range(opt.steps):
         ev[i][0].record()
-        step_device()
+        step_device(i=i)
         ev[i][1].record()
         flush.fill_(i)                                       # L2 flush between timed iterations (not timed)
+    tail0.record()
+    drain()                                                  # the last all-gather must have landed inside the timed region
+    tail1.record()
     barrier()
     _mark("timed steps done")
     t_wall = time.perf_counter() - t_wall0
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev) + (tail0.elapsed_time(tail1) if world > 1 else 0.0)
     # the timed steps replay one CUDA graph; the same steps are run once more launch by launch with CUDA events around
     # the dominant kernel (and the launch counter on) for the roofline line
     for i in range(opt.steps):
-        step_device(graphed=False)
+        step_device(graphed=False, i=i)
         flush.fill_(i)
+    drain()
     barrier()
     prof = kernels.PROFILE
     kernels.PROFILE = None
@@ -267,6 +290,15 @@ def run_ours(opt):
         _mark("train done")
     except Exception as exc:                                  # the headline render number must survive a training failure
         train_info = {"error": repr(exc)}
+    configs = {}
+    if os.environ.get("DANBO_BENCH_SKIP_CONFIGS", "") != "1":
+        for key, fn in (("config4_anerf_1024", run_config4), ("config5_bullet_time_lattice", run_config5)):
+            torch.cuda.empty_cache()
+            try:
+                _mark(key + " start")
+                configs[key] = fn(rank, world, device)
+            except Exception as exc:
+                configs[key] = {"error": repr(exc)}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -308,11 +340,15 @@ def run_ours(opt):
                              "samples seen by at least one bone (+1 per ray); the rest reuse the ray's empty-sample output"},
     }
     line["train"] = train_info
+    line["configs"] = configs
     if world == 1:
         line["cpu_baseline"] = cpu_baseline(sample_rays=REF_SAMPLE_RAYS, repeats=1)     # ~8 s on the box's 16 host cores
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+_KEEP_ALIVE = []
 
 
 def run_train(rank, world, device, steps, warmup):
@@ -335,6 +371,7 @@ def run_train(rank, world, device, steps, warmup):
 
     def measure(batch, tag):
         step = training.TrainStep(caster, args, world_size=world, graph=True)
+        _KEEP_ALIVE.append(step)      # its captured graph holds NCCL nodes: never destroyed while collectives are in flight
         torch.manual_seed(1234 + rank)
         for _ in range(max(warmup, 3)):
             step(batch)
@@ -381,6 +418,117 @@ def run_train(rank, world, device, steps, warmup):
     else:
         info["rays_per_s"] = n_poses * rpp * 1e3 / ms
     return info
+
+
+def _max_over_ranks(ms, device, world):
+    import torch.distributed as dist
+    t = torch.tensor([ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
+
+def run_config4(rank, world, device, reps=2, H4=1024):
+    """BASELINE configs[3]: A-NeRF anerf_base (relative-encoding MLP, no GNN) 1024x1024 render of ONE image, 96+48
+    samples, its rays sharded across the ranks in chunk-aligned ranges (`parallel.render_sharded`, the reference's
+    4096-ray chunks of core/trainer.py:75-90 dealt to GPUs) + one all-gather of the pixels: strong scaling."""
+    import torch.distributed as dist
+    import danbo_b200 as db
+    from danbo_b200 import synthetic as syn, skeleton as sk, params, parallel
+    args = db.make_args("anerf_base", no_reload=True)
+    attrs = {"skel_type": sk.SMPLSkeleton, "near": syn.NEAR, "far": syn.FAR, "n_views": 8, "rest_pose": syn.rest_pose()}
+    _, kw_test, *_ = db.create_raycaster(args, attrs, device=device)
+    caster = kw_test["ray_caster"]
+    caster.network.load_state_dict(syn.synth_state_dict(params.anerf_param_shapes(), 0), strict=False)
+    caster.eval()
+    b = syn.render_batch(syn.make_pose(3), H4, H4)
+    rays = b["ray_batch"].to(device)
+    n = rays.shape[0]
+    tkw = {k: b[k].to(device) for k in ("kp_batch", "skts", "cyls", "bones", "cams")}
+    okw = dict(N_samples=args.N_samples, N_uniques=1, perturb=False, N_importance=args.N_importance, raw_noise_std=0.,
+               nerf_type="nerf")
+    lo, hi = parallel.shard_range(n, rank, world, align=args.chunk)
+    sizes = [b_ - a_ for a_, b_ in (parallel.shard_range(n, r, world, align=args.chunk) for r in range(world))]
+
+    def image():
+        ret = caster(rays[lo:hi], nanmean_chunk=args.chunk, **{k: v[lo:hi] for k, v in tkw.items()}, **okw)
+        pix = parallel.pack_pixels(ret)
+        e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e_a.record()
+        full = parallel.allgather_rows(pix, sizes) if world > 1 else pix
+        e_b.record()
+        return full, (e_a, e_b)
+    image()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    gathers = []
+    for _ in range(reps):
+        full, ev = image()
+        gathers.append(ev)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = _max_over_ranks(e0.elapsed_time(e1) / reps, device, world)
+    coll = _max_over_ranks(sum(a_.elapsed_time(b_) for a_, b_ in gathers) / reps, device, world)
+    S_t = args.N_samples + args.N_importance
+    return {"workload": f"anerf_base {H4}x{H4} render, one synthetic pose, {args.N_samples}+{args.N_importance} samples/ray, "
+                        f"box-restricted rays ({n} rays), rays sharded across {world} GPU(s) in {args.chunk}-ray chunks",
+            "n_gpus": world, "scaling": "strong", "rays": n, "rays_this_rank": hi - lo, "ms_per_image": ms,
+            "value": n / (ms / 1e3), "unit": "rays/s", "allgather_ms_per_image": coll,
+            "tensor_tflops_whole_job": 4536000.0 * n * S_t / (ms / 1e3) / 1e12,
+            "pixels_finite": bool(torch.isfinite(full).all()), "reps": reps}
+
+
+def run_config5(rank, world, device, n_poses=100, res=255):
+    """BASELINE configs[4]: bullet-time render of 100 synthetic poses at 512x512 (danbo_fast; images dealt round robin to
+    the ranks, one all-gather of the finished images) plus a 256^3 density lattice for mesh extraction (danbo_fast field;
+    z-slabs of the lattice split across the ranks, one all-gather)."""
+    import torch.distributed as dist
+    import danbo_b200 as db
+    from danbo_b200 import synthetic as syn, skeleton as sk, render
+    args = db.make_args(PRESET, no_reload=True)
+    attrs = {"skel_type": sk.SMPLSkeleton, "near": syn.NEAR, "far": syn.FAR, "n_views": 8, "rest_pose": syn.rest_pose()}
+    _, kw_test, *_ = db.create_raycaster(args, attrs, device=device)
+    caster = kw_test["ray_caster"]
+    caster.network.load_state_dict(syn.synthetic_params(0))
+    caster.eval()
+    poses = [syn.make_pose(100 + k) for k in range(n_poses)]
+    c2ws = list(syn.bullet_time_cameras(syn.camera(), n_poses))
+    dist_on = world > 1
+
+    def timed(fn):
+        if dist_on:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn()
+        e1.record()
+        if dist_on:
+            dist.barrier()
+        torch.cuda.synchronize()
+        return _max_over_ranks(e0.elapsed_time(e1), device, world), r
+    render.render_images(caster, args, c2ws[:2 * world], poses[:2 * world], H, W, distributed=dist_on)        # warm-up
+    ms_img, imgs = timed(lambda: render.render_images(caster, args, c2ws, poses, H, W, distributed=dist_on))
+    n_rays = sum(int(np.prod(np.subtract(*syn.cylinder_image_box(p["cyl"], H, W, 1.2 * H, np.asarray(c))[::-1])))
+                 for p, c in zip(poses, c2ws))
+    t = lambda a: torch.as_tensor(a)[None].to(device)
+    pose = poses[0]
+    grid_fn = lambda r: render.density_grid(caster, t(pose["kps"]), t(pose["skts"]), t(pose["bones"]), radius=1.8, res=r,
+                                            distributed=dist_on)
+    grid_fn(63)                                                                                              # warm-up
+    ms_grid, grid = timed(lambda: grid_fn(res))
+    return {"workload": f"{n_poses} synthetic poses x {H}x{W} bullet-time views (danbo_fast, {args.N_samples}+"
+                        f"{args.N_importance} samples/ray, box-restricted rays) + {(res + 1)}^3 density lattice, on {world} GPU(s)",
+            "n_gpus": world, "scaling": "strong", "images": n_poses, "rays": n_rays, "ms_images": ms_img,
+            "images_per_s": n_poses / (ms_img / 1e3), "rays_per_s": n_rays / (ms_img / 1e3),
+            "ms_per_image_per_gpu": ms_img * world / n_poses,
+            "lattice_points": (res + 1) ** 3, "ms_lattice": ms_grid, "points_per_s": (res + 1) ** 3 / (ms_grid / 1e3),
+            "mean_pixel": float(imgs.mean()), "lattice_occupied_frac": float((grid > 10).float().mean())}
 
 
 # the bounded sample of the 261 121-ray image both arms quote the CPU figure on (the env override is for the unit test)

@@ -5,7 +5,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PATH = os.path.join(_HERE, "libdanbo_b200.so")
 _lib = None
-ABI_VERSION = 3          # danbo_version() of the header this binding was written against
+ABI_VERSION = 4          # danbo_version() of the header this binding was written against
 
 c_p = ctypes.c_void_p
 c_i = ctypes.c_int
@@ -31,6 +31,9 @@ _SIGNATURES = {
     "danbo_anerf_ray_encode": [c_p, c_i, c_i, c_p, c_i, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p],
     "danbo_anerf_embed": [c_p, c_i, c_i, c_p, c_i, c_p, c_i, c_i, c_p, c_p, c_f, c_p, c_p, c_p],
     "danbo_anerf_mlp": [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_i, c_i, c_p, c_p],
+    "danbo_anerf_save_bytes": [c_i, c_p],
+    "danbo_anerf_mlp_save": [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_i, c_i, c_p, c_p],
+    "danbo_anerf_untile": [c_p, ctypes.c_longlong, c_i, c_i, c_p, c_p],
     "danbo_pack_mlp_weights": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "danbo_mlp_forward": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_i, c_i, c_i, c_p],
     "danbo_mlp_forward_trace": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_i, c_i, c_i, c_p, c_p],

@@ -3,8 +3,9 @@
 `AnerfField` owns the parameters under the reference's names (core/networks/nerf.py:73-105 with W = 448, view_W = 224,
 plus the cutoff embedders' `cutoff_dist` / `tau` entries, cutoff_embedder.py:128-133) so reference checkpoints load.
 `AnerfCaster` mirrors raycasters.py:205-546 for this network type: cylinder near/far only (:419-420), every sample
-goes through the field, single_net fine pass on the S_f new samples (F9).  Rendering only: config #4 is a render
-benchmark, and the backward kernels of this path exist only for the DANBO field, so train mode raises.
+goes through the field, single_net fine pass on the S_f new samples (F9).  Train mode (single_net configs): the forward
+keeps every layer's activation tile image (`danbo_anerf_mlp_save`) and `_AnerfBlock.backward` turns d (rgb, acc) into the
+MLP / frame-code gradients with the compositing backward kernels and `kernels.anerf_mlp_backward`.
 """
 import torch
 import torch.nn as nn
@@ -121,15 +122,29 @@ class AnerfCaster(RayCaster):
     def _render_prepared(self, rays, pose_skts, pose_bones, pose_cyls, cam_idx, skip=1, N_samples=96, N_importance=48,
                          B=1.0, raw_noise_std=0., perturb=0., nanmean_chunk=None, lindisp=False, _rand=None,
                          _stages=None):
-        if self.training:
-            raise NotImplementedError("A-NeRF (nerf_type='nerf') is render-only here: the backward kernels exist for the "
-                                      "DANBO field only (BASELINE config #4 is a render benchmark)")
         N = rays.shape[0]
         align = self._align()
         packed = self._packed_mlp()
         codes = self._codes_with_mean()
         tau = self._tau()
         G = pose_skts.shape[0]
+        dev = rays.device
+        rand = dict(_rand or {})
+        if self.training and perturb > 0 and "t_rand" not in rand:
+            # the reference's draw order (SURVEY §7 hard part 4): rand, randn, rand, randn
+            S_t = N_samples + N_importance
+            rand = {"t_rand": torch.rand(N, N_samples, device=dev), "noise0": torch.randn(N, N_samples, device=dev),
+                    "u": torch.rand(N, N_importance, device=dev), "noise1": torch.randn(N, S_t, device=dev)}
+        rand = {k: v.to(dev).contiguous() for k, v in rand.items()}
+        if self.training and torch.is_grad_enabled():
+            if not self.single_net:
+                raise NotImplementedError("training with a separate fine network (single_net=False, anerf_h.txt) is not "
+                                          "implemented: the backward pass covers the single_net configs")
+            max_train = max(MAX_RAYS_PER_LAUNCH * 24 // (N_samples + N_importance) // 4096, 1) * 4096
+            if N > max_train:
+                raise NotImplementedError(f"A-NeRF training batches above {max_train} rays are not implemented")
+            return _anerf_block_with_grad(self, rays, skip, pose_skts, pose_cyls, cam_idx, codes, align, packed, tau,
+                                          N_samples, N_importance, B, nanmean_chunk, lindisp, rand, raw_noise_std, _stages)
         # every sample is evaluated: bound the rows of one launch sequence (operand images are 2.3 KB per row)
         max_rays = max(MAX_RAYS_PER_LAUNCH * 24 // (N_samples + N_importance) // 4096, 1) * 4096
         block = max_rays if G == 1 else max((max_rays // skip) * skip, skip)
@@ -140,13 +155,18 @@ class AnerfCaster(RayCaster):
             s1 = min(N, s0 + block)
             outs.append(self._render_block_anerf(rays[s0:s1], s0, skip, pose_skts, pose_cyls, cam_idx[s0:s1], codes, align,
                                                  packed, tau, N_samples, N_importance, B, nanmean_chunk, _stages,
-                                                 lindisp=lindisp))
+                                                 lindisp=lindisp, rand={k: v[s0:s1] for k, v in rand.items()},
+                                                 raw_noise_std=raw_noise_std if self.training else 0.))
         if len(outs) == 1:
             return outs[0]
         return {k: torch.cat([o[k] for o in outs], 0) for k in outs[0]}
 
     def _render_block_anerf(self, rays, ray0, skip, pose_skts, pose_cyls, cam_idx, codes, align, packed, tau, S_c, S_f, B,
-                            nanmean_chunk, stages, lindisp=False):
+                            nanmean_chunk, stages, lindisp=False, rand=None, raw_noise_std=0., keep=None):
+        """rand: the four random tensors of a train-mode call (stratified jitter, density noise, importance u); keep
+        (dict): receives what the backward pass needs, and makes the MLP keep its activations."""
+        rand = rand or {}
+        save = keep is not None
         n = rays.shape[0]
         dev = rays.device
         if pose_skts.shape[0] == 1:
@@ -164,21 +184,37 @@ class AnerfCaster(RayCaster):
             z0 = (near[:, None] * (1. - t) + far[:, None] * t).contiguous()
         else:                                                # ray_utils.py:226-227, the reference's own expression
             z0 = (1. / (1. / near[:, None] * (1. - t) + 1. / far[:, None] * t)).contiguous()
+        if "t_rand" in rand:                                 # stratified jitter, ray_utils.py:233-248 (the reference's ops)
+            mids = .5 * (z0[..., 1:] + z0[..., :-1])
+            upper, lower = torch.cat([mids, z0[..., -1:]], -1), torch.cat([z0[..., :1], mids], -1)
+            z0 = (lower + (upper - lower) * rand["t_rand"]).contiguous()
         xd, xv = K.anerf_embed(rays, S_c, z0, p_skts, skip, align, enc, tau)
         raw0 = torch.empty(n * S_c + n, 4, device=dev, dtype=torch.float32)
-        K.anerf_mlp(xd, xv, packed, code_bias, n * S_c, S_c, raw0)
+        sv0 = K.anerf_save_buffer(n * S_c, dev) if save else None
+        K.anerf_mlp(xd, xv, packed, code_bias, n * S_c, S_c, raw0, save=sv0)
         ones0 = torch.ones(n, S_c, device=dev, dtype=torch.int32)          # every sample carries its own field value
-        c0 = K.composite_resample(rays, S_c, S_f, raw0, ones0, z0, inv_B=1.0 / B, want_inds=stages is not None,
-                                  smooth=self.single_net)
+        inv_B = 1.0 / B
+        noise0 = (rand["noise0"] * (raw_noise_std * B)).contiguous() if ("noise0" in rand and raw_noise_std > 0) else None
+        c0 = K.composite_resample(rays, S_c, S_f, raw0, ones0, z0, noise=noise0, inv_B=inv_B, u_rand=rand.get("u"),
+                                  want_inds=stages is not None, smooth=self.single_net)
         z1 = c0["z_samples"]
         if not self.single_net:
             return self._fine_network_pass(rays, p_skts, skip, cam_idx, align, S_c, S_f, B, c0, near, far, z0, raw0, stages)
-        xd1, xv1 = K.anerf_embed(rays, S_f, z1, p_skts, skip, align, enc, tau, xd=xd, xv=xv)
+        if save:                                             # the coarse pass's operand images are read again by the backward
+            xd1, xv1 = K.anerf_embed(rays, S_f, z1, p_skts, skip, align, enc, tau)
+        else:
+            xd1, xv1 = K.anerf_embed(rays, S_f, z1, p_skts, skip, align, enc, tau, xd=xd, xv=xv)
         raw1 = torch.empty(n * S_f, 4, device=dev, dtype=torch.float32)
-        K.anerf_mlp(xd1, xv1, packed, code_bias, n * S_f, S_f, raw1)
+        sv1 = K.anerf_save_buffer(n * S_f, dev) if save else None
+        K.anerf_mlp(xd1, xv1, packed, code_bias, n * S_f, S_f, raw1, save=sv1)
         ones1 = torch.ones(n, S_f, device=dev, dtype=torch.int32)
-        c1 = K.merge_composite(rays, S_c, S_f, raw0, ones0, raw1, ones1, c0["z_all"], c0["order"], inv_B=1.0 / B,
-                               want_raw=stages is not None)
+        noise1 = (rand["noise1"] * (raw_noise_std * B)).contiguous() if ("noise1" in rand and raw_noise_std > 0) else None
+        c1 = K.merge_composite(rays, S_c, S_f, raw0, ones0, raw1, ones1, c0["z_all"], c0["order"], noise=noise1,
+                               inv_B=inv_B, want_raw=stages is not None)
+        if save:
+            keep.update(dict(rays=rays, cam_idx=cam_idx, codes=codes, code_bias=code_bias, S_c=S_c, S_f=S_f, inv_B=inv_B,
+                             z0=z0, raw0=raw0, ones0=ones0, noise0=noise0, xd0=xd, xv0=xv, sv0=sv0, raw1=raw1, ones1=ones1,
+                             noise1=noise1, xd1=xd1, xv1=xv1, sv1=sv1, z_all=c0["z_all"], order=c0["order"]))
         ret = {"rgb_map": c1["rgb_map"], "disp_map": c1["disp_map"], "acc_map": c1["acc_map"], "alpha": c1["alpha"],
                "T_i": c1["weights"], "rgb0": c0["rgb_map"], "disp0": c0["disp_map"], "acc0": c0["acc_map"],
                "alpha0": c0["alpha"]}
@@ -240,6 +276,62 @@ class AnerfCaster(RayCaster):
         return out.reshape(P, 1, 1) if pts.dim() == 3 else out.reshape(P, 1)
 
     # render_mesh_density: inherited (lattice around the root joint -> render_pts_density)
+
+
+ANERF_PARAM_NAMES = [f"pts_linears.{i}.{w}" for i in range(8) for w in ("weight", "bias")] + [
+    "alpha_linear.weight", "alpha_linear.bias", "feature_linear.weight", "feature_linear.bias",
+    "views_linears.0.weight", "views_linears.0.bias", "rgb_linear.weight", "rgb_linear.bias", "framecodes.codes.weight"]
+ANERF_OUT_KEYS = ["rgb_map", "disp_map", "acc_map", "alpha", "T_i", "rgb0", "disp0", "acc0", "alpha0"]
+ANERF_DIFF_KEYS = ("rgb_map", "acc_map", "rgb0", "acc0")
+
+
+class _AnerfBlock(torch.autograd.Function):
+    """Autograd root of A-NeRF training: forward = the render kernels with saved activations; backward = compositing
+    backward kernels (composite.cu) + kernels.anerf_mlp_backward.  Differentiable outputs are what the trainer's losses
+    read (core/trainer.py:396-422): rgb_map, acc_map, rgb0, acc0."""
+
+    @staticmethod
+    def forward(ctx, caster, cfg, *params):
+        keep = {}
+        with torch.no_grad():
+            ret = caster._render_block_anerf(cfg["rays"], 0, cfg["skip"], cfg["pose_skts"], cfg["pose_cyls"], cfg["cam_idx"],
+                                             cfg["codes"], cfg["align"], cfg["packed"], cfg["tau"], cfg["S_c"], cfg["S_f"],
+                                             cfg["B"], cfg["nanmean_chunk"], cfg["stages"], lindisp=cfg["lindisp"],
+                                             rand=cfg["rand"], raw_noise_std=cfg["raw_noise_std"], keep=keep)
+        ctx.keep, ctx.params = keep, params
+        ctx.mark_non_differentiable(*[ret[k] for k in ANERF_OUT_KEYS if k not in ANERF_DIFF_KEYS])
+        return tuple(ret[k] for k in ANERF_OUT_KEYS)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        k = ctx.keep
+        g = dict(zip(ANERF_OUT_KEYS, gouts))
+        rays, dev = k["rays"], k["rays"].device
+        n, S_c, S_f = rays.shape[0], k["S_c"], k["S_f"]
+        zeros = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
+        cg = lambda t, *s: zeros(*s) if t is None else t.contiguous().float()
+        P = dict(zip(ANERF_PARAM_NAMES, ctx.params))
+        G = {name: torch.zeros_like(p, dtype=torch.float32) for name, p in P.items()}
+        d_raw0, d_raw1 = zeros(n * S_c + n, 4), zeros(n * S_f, 4)
+        K.merge_composite_bwd(rays, S_c, S_f, k["raw0"], k["ones0"], k["raw1"], k["ones1"], k["z_all"], k["order"],
+                              k["noise1"], k["inv_B"], cg(g["rgb_map"], n, 3), cg(g["acc_map"], n), None, d_raw0, d_raw1,
+                              None, None)
+        K.composite_bwd(rays, S_c, k["raw0"], k["ones0"], k["z0"], k["noise0"], k["inv_B"], cg(g["rgb0"], n, 3),
+                        cg(g["acc0"], n), d_raw0)
+        for d_raw, S, xd, xv, sv in ((d_raw0, S_c, k["xd0"], k["xv0"], k["sv0"]), (d_raw1, S_f, k["xd1"], k["xv1"], k["sv1"])):
+            K.anerf_mlp_backward(P, G, d_raw, n * S, S, xd, xv, sv, k["code_bias"], k["cam_idx"], k["codes"])
+        ctx.keep = None
+        return (None, None) + tuple(G[name] for name in ANERF_PARAM_NAMES)
+
+
+def _anerf_block_with_grad(caster, rays, skip, pose_skts, pose_cyls, cam_idx, codes, align, packed, tau, S_c, S_f, B,
+                           nanmean_chunk, lindisp, rand, raw_noise_std, stages):
+    named = dict(caster.network.named_parameters())
+    cfg = dict(rays=rays, skip=skip, pose_skts=pose_skts, pose_cyls=pose_cyls, cam_idx=cam_idx, codes=codes, align=align,
+               packed=packed, tau=tau, S_c=S_c, S_f=S_f, B=B, nanmean_chunk=nanmean_chunk, lindisp=lindisp, rand=rand,
+               raw_noise_std=raw_noise_std, stages=stages)
+    outs = _AnerfBlock.apply(caster, cfg, *[named[n] for n in ANERF_PARAM_NAMES])
+    return dict(zip(ANERF_OUT_KEYS, outs))
 
 
 _ANERF_REQUIRED = {"netdepth": 8, "netwidth": 448, "multires": 7, "multires_views": 4, "multires_bones": 0,

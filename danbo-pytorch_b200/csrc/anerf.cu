@@ -461,7 +461,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 mlp_kernel(const uint8_t* __restrict__ xd, const uint8_t* __restrict__ xv, const uint8_t* __restrict__ wstream,
            const float* __restrict__ heads, const float* __restrict__ code_bias, uint8_t* __restrict__ scratch,
            float* __restrict__ out /* raw (rows,4) */, int n_rows, int S, int out_capacity,
-           long long* __restrict__ trace /* optional clock64 timeline of CTA 0: [2 tiles][2 roles][20][2], or null */) {
+           long long* __restrict__ trace /* optional clock64 timeline of CTA 0: [2 tiles][2 roles][20][2], or null */,
+           uint8_t* __restrict__ save /* train mode: [tile][9] activation tile images kept for the backward pass, or null */) {
     extern __shared__ uint8_t smem_raw[];
     Smem& Sm = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -503,8 +504,11 @@ mlp_kernel(const uint8_t* __restrict__ xd, const uint8_t* __restrict__ xv, const
             const uint8_t* xd_t = xd + (size_t)t * (kChunksD * kChunkBytes);
             const uint8_t* xv_t = xv + (size_t)t * (kChunksV * kChunkBytes);
             int s = 0;
+            const size_t t_act = (size_t)(2 * w + (int)rank);            // unclamped: where this CTA's epilogue writes
             for (int L = 0; L < 10; ++L) {
-                const uint8_t* act_in = act_buf + ((L - 1) & 1) * kActBytes;
+                // train mode keeps every layer's activation image ([tile][layer]) instead of the two ping-pong buffers
+                const uint8_t* act_in = save ? save + (t_act * 9 + (size_t)(L > 0 ? L - 1 : 0)) * kActBytes
+                                             : act_buf + ((L - 1) & 1) * kActBytes;
                 const uint32_t wr_par = (uint32_t)(9 * it + L - 1) & 1u;       // act_written completions: 9 per tile
                 for (int h = 0; h < n_pass(L); ++h) {
                     for (int gi = 0; gi < groups_per_pass(L); ++gi, ++s) {
@@ -621,7 +625,7 @@ mlp_kernel(const uint8_t* __restrict__ xd, const uint8_t* __restrict__ xv, const
                     E.acc_phase = h == 0 ? ((uint32_t)L & 1u) : ((uint32_t)(9 * it + L) & 1u);   // 10 / 9 completions per tile
                     E.free_addr = free_addr[h];
                     E.written_bar = &Sm.act_written[h];
-                    E.act_out = act_buf + (L & 1) * kActBytes;
+                    E.act_out = save ? save + ((size_t)t * 9 + (size_t)(L < 9 ? L : 8)) * kActBytes : act_buf + (L & 1) * kActBytes;
                     const int coff = h * kHalfN + E.ch * kQuartN;
                     if (warp == 2 && lane == 0) { ANERF_TRACE(it, 1, L, h, 0); }
                     E.dslot = (tr && it < 2 && warp == 2 && lane == 0) ? trace + 160 + ((it * 20 + L * 2 + h) * 4) : nullptr;
@@ -703,9 +707,9 @@ extern "C" int danbo_anerf_embed(const float* rays, int ray_stride, int S, const
     return 0;
 }
 
-extern "C" int danbo_anerf_mlp(const void* xd, const void* xv, const void* wstream, const float* heads,
-                               const float* code_bias, void* scratch, int n_rows, int S, float* out, int out_capacity,
-                               int num_sms, long long* trace, void* stream) {
+static int anerf_mlp_launch(const void* xd, const void* xv, const void* wstream, const float* heads,
+                            const float* code_bias, void* scratch, int n_rows, int S, float* out, int out_capacity,
+                            int num_sms, long long* trace, void* save, void* stream) {
     if (n_rows <= 0) return 0;
     if (num_sms < 2) return -1;
     const int smem = (int)sizeof(anerf::Smem) + 1024;
@@ -727,8 +731,55 @@ extern "C" int danbo_anerf_mlp(const void* xd, const void* xv, const void* wstre
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, anerf::mlp_kernel, (const uint8_t*)xd, (const uint8_t*)xv, (const uint8_t*)wstream,
-                                       heads, code_bias, (uint8_t*)scratch, out, n_rows, S, out_capacity, trace);
+                                       heads, code_bias, (uint8_t*)scratch, out, n_rows, S, out_capacity, trace, (uint8_t*)save);
     if (e != cudaSuccess) return (int)e;
+    DANBO_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int danbo_anerf_mlp(const void* xd, const void* xv, const void* wstream, const float* heads,
+                               const float* code_bias, void* scratch, int n_rows, int S, float* out, int out_capacity,
+                               int num_sms, long long* trace, void* stream) {
+    return anerf_mlp_launch(xd, xv, wstream, heads, code_bias, scratch, n_rows, S, out, out_capacity, num_sms, trace, nullptr, stream);
+}
+
+extern "C" int danbo_anerf_save_bytes(int n_rows, long long* bytes) {
+    if (!bytes || n_rows < 0) return -1;
+    const long long tiles = (n_rows + DANBO_TILE_M - 1) / DANBO_TILE_M;
+    *bytes = ((tiles + 1) / 2 * 2) * 9 * (long long)anerf::kActBytes;    // tiles rounded up to a CTA pair
+    return 0;
+}
+
+extern "C" int danbo_anerf_mlp_save(const void* xd, const void* xv, const void* wstream, const float* heads,
+                                    const float* code_bias, void* scratch, int n_rows, int S, float* out, int out_capacity,
+                                    int num_sms, void* save, void* stream) {
+    if (!save) return -1;
+    return anerf_mlp_launch(xd, xv, wstream, heads, code_bias, scratch, n_rows, S, out, out_capacity, num_sms, nullptr, save, stream);
+}
+
+namespace danbo { namespace anerf {
+// Operand tile images ([tile][chunk][128 rows x 64 k] bf16, 128-byte swizzle) -> row-major bf16 (rows, n_chunks * 64).
+// One thread per 16-byte piece; `tile_stride` bytes between consecutive tiles of the image (so one layer's plane can be
+// read out of the [tile][9] activation save).
+__global__ void __launch_bounds__(256)
+untile_kernel(const uint8_t* __restrict__ img, long long tile_stride, int n_rows, int n_chunks, uint4* __restrict__ out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int per_row = n_chunks * 8;
+    const long long total = (long long)n_rows * per_row;
+    if (idx >= total) return;
+    const int row = (int)(idx / per_row), piece = (int)(idx - (long long)row * per_row);
+    const int c = piece >> 3, p = piece & 7, t = row >> 7, r = row & 127;
+    const uint8_t* src = img + (size_t)t * tile_stride + (size_t)c * kChunkBytes + (r >> 3) * 1024 + (r & 7) * 128 + ((p ^ (r & 7)) << 4);
+    out[idx] = *reinterpret_cast<const uint4*>(src);
+}
+}}
+
+extern "C" int danbo_anerf_untile(const void* img, long long tile_stride, int n_rows, int n_chunks, void* out, void* stream) {
+    if (n_rows <= 0) return 0;
+    if (n_chunks <= 0 || (tile_stride & 15)) return -1;
+    const long long total = (long long)n_rows * n_chunks * 8;
+    anerf::untile_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)img, tile_stride, n_rows,
+                                                                                      n_chunks, (uint4*)out);
     DANBO_CHECK_LAUNCH();
     return 0;
 }

@@ -164,6 +164,21 @@ __global__ void nearfar_finish_kernel(const float* __restrict__ rays, int ray_st
 constexpr int kMaskBlock = 256;
 constexpr int kMaxRaysPerBlock = 18;       // 256 / 16 + 2
 
+// Sets bit j of *cand unless the affine map x(z) = cc + z ee stays outside |x|_inf <= 1 + kCull for every depth z.
+__device__ __forceinline__ void mark_candidate(uint32_t* cand, int j, const float (&cc)[3], const float (&ee)[3]) {
+    constexpr float kCull = 4e-4f;                                           // > the 2e-4 decision margin + interval rounding
+    float lo = -3.0e38f, hi = 3.0e38f;
+    bool empty = false;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        if (fabsf(ee[i]) < 1e-20f) { empty |= fabsf(cc[i]) > 1.f + kCull; continue; }
+        const float inv = 1.f / ee[i];
+        const float a = (-(1.f + kCull) - cc[i]) * inv, b = ((1.f + kCull) - cc[i]) * inv;
+        lo = fmaxf(lo, fminf(a, b)); hi = fminf(hi, fmaxf(a, b));
+    }
+    if (!(empty || lo > hi)) atomicOr(cand, 1u << j);
+}
+
 template <bool kTable>
 __global__ void __launch_bounds__(kMaskBlock)
 sample_mask_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, int S,
@@ -180,7 +195,12 @@ sample_mask_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, i
     __shared__ float4 tab[kTable ? kMaxRaysPerBlock * DANBO_J * 2 : 1];     // (c.xyz, e.xyz) per (ray slot, bone)
     const int ray_first = (blockIdx.x * kMaskBlock) / S;
     __shared__ float4 pm[kTable ? DANBO_J * 3 : 1];                          // per bone: rows of [diag(1/|s|) A R | offset]
+    // cand[slot] bit j: the ray of this slot comes within kCull of bone j's box at SOME depth.  For every other bone the
+    // table value max|x| exceeds 1 + kCull at every z, i.e. "decided, outside" below: those bones are never visited
+    // (a ray of the 512x512 image comes near 3-5 of the 24 boxes, and half of the rays near none).
+    __shared__ uint32_t cand[kTable ? kMaxRaysPerBlock : 1];
     if (kTable) {
+        if (threadIdx.x < kMaxRaysPerBlock) cand[threadIdx.x] = 0u;
         const int ray_last = min(n_rays - 1, (blockIdx.x * kMaskBlock + kMaskBlock - 1) / S);
         const int n_ent = (ray_last - ray_first + 1) * DANBO_J;
         int pose_a = ray_first / rays_per_pose; if (pose_a >= n_poses) pose_a = n_poses - 1;
@@ -209,12 +229,16 @@ sample_mask_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, i
                 const float* r = rays + (size_t)(ray_first + slot) * ray_stride;
                 const float o0 = r[0], o1 = r[1], o2 = r[2], d0 = r[3], d1 = r[4], d2 = r[5];
                 const float4 m0 = pm[j * 3], m1 = pm[j * 3 + 1], m2 = pm[j * 3 + 2];
-                tab[2 * e] = make_float4(m0.x * o0 + m0.y * o1 + m0.z * o2 + m0.w, m1.x * o0 + m1.y * o1 + m1.z * o2 + m1.w,
-                                         m2.x * o0 + m2.y * o1 + m2.z * o2 + m2.w, 0.f);
-                tab[2 * e + 1] = make_float4(m0.x * d0 + m0.y * d1 + m0.z * d2, m1.x * d0 + m1.y * d1 + m1.z * d2,
-                                             m2.x * d0 + m2.y * d1 + m2.z * d2, 0.f);
+                const float cc[3] = {m0.x * o0 + m0.y * o1 + m0.z * o2 + m0.w, m1.x * o0 + m1.y * o1 + m1.z * o2 + m1.w,
+                                     m2.x * o0 + m2.y * o1 + m2.z * o2 + m2.w};
+                const float ee[3] = {m0.x * d0 + m0.y * d1 + m0.z * d2, m1.x * d0 + m1.y * d1 + m1.z * d2,
+                                     m2.x * d0 + m2.y * d1 + m2.z * d2};
+                tab[2 * e] = make_float4(cc[0], cc[1], cc[2], 0.f);
+                tab[2 * e + 1] = make_float4(ee[0], ee[1], ee[2], 0.f);
+                mark_candidate(&cand[slot], j, cc, ee);
             }
         } else {
+            __syncthreads();                                              // cand[] zeroed
             for (int e = threadIdx.x; e < n_ent; e += kMaskBlock) {
                 const int slot = e / DANBO_J, j = e - slot * DANBO_J;
                 const int rn = ray_first + slot;
@@ -242,6 +266,7 @@ sample_mask_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, i
                 }
                 tab[2 * e] = make_float4(cc[0], cc[1], cc[2], 0.f);
                 tab[2 * e + 1] = make_float4(ee[0], ee[1], ee[2], 0.f);
+                mark_candidate(&cand[slot], j, cc, ee);
             }
         }
         __syncthreads();
@@ -275,8 +300,8 @@ sample_mask_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, i
         int pose = n / rays_per_pose; if (pose >= n_poses) pose = n_poses - 1;
         const float* skt = pose_skts + (size_t)pose * DANBO_J * 16;
         const float4* tr = tab + (kTable ? (n - ray_first) * DANBO_J * 2 : 0);
-#pragma unroll 4
-        for (int j = 0; j < DANBO_J; ++j) {
+        for (uint32_t todo = kTable ? cand[n - ray_first] : (1u << DANBO_J) - 1u; todo; todo &= todo - 1) {
+            const int j = __ffs(todo) - 1;
             bool decided = false, invalid = false;
             if (kTable) {
                 // the largest |coordinate| decides: clearly above 1 -> outside (whatever the other two are), clearly below

@@ -33,7 +33,8 @@ def install(reference_root=None, anerf=True):
     create_raycaster.__danbo_b200__ = True
     rc.create_raycaster = create_raycaster
     for mod in list(sys.modules.values()):                  # `from core.raycasters import create_raycaster` copies
-        if mod is not None and mod is not rc and getattr(mod, "create_raycaster", None) is orig:
+        # only real module globals: a getattr would wake lazy namespaces such as torch.classes
+        if mod is not None and mod is not rc and getattr(mod, "__dict__", {}).get("create_raycaster") is orig:
             setattr(mod, "create_raycaster", create_raycaster)
     return orig
 
@@ -45,7 +46,7 @@ def uninstall():
     rc = importlib.import_module("core.raycasters")
     rc.create_raycaster = orig
     for mod in list(sys.modules.values()):
-        f = getattr(mod, "create_raycaster", None) if mod is not None else None
-        if f is not None and getattr(f, "__danbo_b200__", False):
+        f = getattr(mod, "__dict__", {}).get("create_raycaster") if mod is not None else None
+        if f is not None and getattr(f, "__dict__", {}).get("__danbo_b200__", False):
             setattr(mod, "create_raycaster", orig)
     _STATE["orig"] = None

@@ -437,14 +437,14 @@ def _off(t, elems):
 class _Ptr:
     """Minimal tensor-like view (pointer + row stride + dtype) so GEMM wrappers can address column slices."""
 
-    def __init__(self, t, col0=0):
-        self.t, self.col0, self.dtype = t, col0, t.dtype
+    def __init__(self, t, col0=0, ld=None):
+        self.t, self.col0, self.dtype, self.ld = t, col0, t.dtype, ld
 
     def data_ptr(self):
         return self.t.data_ptr() + self.col0 * self.t.element_size()
 
     def stride(self, d):
-        return self.t.stride(d)
+        return self.ld if (self.ld is not None and d == 0) else self.t.stride(d)
 
 
 def mlp_backward(P, G, d_raw, active, fo, save, d_ray_bias):
@@ -718,11 +718,41 @@ def anerf_embed(rays, S, z, pose_skts, rays_per_pose, align, ray_enc, tau, xd=No
     return xd, xv
 
 
-def anerf_mlp(xd, xv, packed, code_bias, rows, S, out, trace=None):
-    """out (>= rows, 4) <- [rgb, sigma] of the dense rows.  trace: optional int64 CUDA tensor (320) for a clock64 timeline."""
+ANERF_ACT_TILE_BYTES = 7 * 16384          # one layer's activation tile image (128 rows x 448 bf16, operand layout)
+
+
+def anerf_save_buffer(rows, device):
+    """Train mode: room for the nine activation tile images ([tile][9]) danbo_anerf_mlp_save keeps per 128-row tile."""
+    n = ctypes.c_longlong()
+    _lib.check(_lib.load().danbo_anerf_save_bytes(int(rows), ctypes.byref(n)), "danbo_anerf_save_bytes")
+    return torch.empty(n.value, device=device, dtype=torch.uint8)
+
+
+def anerf_untile(img, tile_stride, rows, n_chunks, byte_offset=0):
+    """Operand tile images -> row-major bf16 (rows, 64 * n_chunks).  byte_offset / tile_stride select one layer's plane of
+    the [tile][9] activation save."""
+    _need_cuda(img)
+    out = torch.empty(rows, 64 * n_chunks, device=img.device, dtype=torch.bfloat16)
+    src = ctypes.c_void_p(img.data_ptr() + int(byte_offset))
+    _lib.check(_lib.load().danbo_anerf_untile(src, int(tile_stride), int(rows), int(n_chunks), _p(out), _stream()),
+               "danbo_anerf_untile")
+    _count(1)
+    return out
+
+
+def anerf_mlp(xd, xv, packed, code_bias, rows, S, out, trace=None, save=None):
+    """out (>= rows, 4) <- [rgb, sigma] of the dense rows.  trace: optional int64 CUDA tensor (320) for a clock64 timeline.
+    save: train mode, a buffer from anerf_save_buffer(rows) that receives every layer's activation tile image."""
     _need_cuda(xd, xv, code_bias, out)
     lib = _lib.load()
     idx = out.device.index if out.device.index is not None else torch.cuda.current_device()
+    if save is not None:
+        with _Timed("anerf_mlp"):
+            _lib.check(lib.danbo_anerf_mlp_save(_p(xd), _p(xv), _p(packed.wstream), _p(packed.heads), _p(code_bias),
+                                                _p(packed.scratch), int(rows), int(S), _p(out), out.shape[0], num_sms(idx),
+                                                _p(save), _stream()), "danbo_anerf_mlp_save")
+        _count(1)
+        return out
     with _Timed("anerf_mlp"):
         _lib.check(lib.danbo_anerf_mlp(_p(xd), _p(xv), _p(packed.wstream), _p(packed.heads), _p(code_bias),
                                        _p(packed.scratch), int(rows), int(S), _p(out), out.shape[0], num_sms(idx),
@@ -730,3 +760,81 @@ def anerf_mlp(xd, xv, packed, code_bias, rows, S, out, trace=None):
                    "danbo_anerf_mlp")
     _count(1)
     return out
+
+
+class _RowCount:
+    """Device row counter for the generic GEMM kernels (they read the row count from device memory)."""
+
+    def __init__(self, rows, device):
+        self.count = torch.full((1,), int(rows), device=device, dtype=torch.int32)
+        self.capacity = int(rows)
+
+
+def anerf_mlp_backward(P, G, d_raw, rows, S, xd, xv, save, code_bias, cam_idx, codes_with_mean):
+    """Backward of the A-NeRF MLP (core/networks/nerf.py:164-209 under autograd, trainer.py:573) over the `rows` dense
+    rows of one pass: parameter gradients are ADDED to G (reference names).  No input gradient is needed: the encodings
+    have no trainable parameter (opt_cutoff = False) and the poses are not optimised on this path.
+
+    d_raw (>= rows,4) [d rgb, d sigma]; xd / xv: the pass's operand tile images; save: what danbo_anerf_mlp_save kept;
+    code_bias (n_rays,224) from danbo_anerf_ray_encode.  Built from the generic fp32 GEMM kernels of backward_mlp.cu
+    (danbo_gemm_dgrad / _wgrad / danbo_colsum) on row-major copies of the tile images: correct first, not yet on tensor
+    cores (the DANBO field's backward is: mlp_bwd_tcgen05.cu)."""
+    dev = d_raw.device
+    W, VW, XD, XV = 448, 224, 432, 648
+    n_rays = rows // S
+    rc = _RowCount(rows, dev)
+    rcr = _RowCount(n_rays, dev)
+    f32 = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+    act = lambda L: anerf_untile(save, 9 * ANERF_ACT_TILE_BYTES, rows, 7, byte_offset=L * ANERF_ACT_TILE_BYTES)
+    xd_r = anerf_untile(xd, 7 * 16384, rows, 7)
+    xv_r = anerf_untile(xv, 11 * 16384, rows, 11)
+    Wv, Wf = f32c(P["views_linears.0.weight"]), f32c(P["feature_linear.weight"])
+    WvT = Wv.t().contiguous()                                        # (1224, 224): the forward product needs B = W^T
+    feat, a7 = act(8), act(7)
+    # view layer pre-activation, recomputed: z9 = feat . Wv[:, :448]^T + xv . Wv[:, 448:1096]^T + code_bias[ray]
+    z9 = code_bias[:n_rays].repeat_interleave(S, dim=0).contiguous()
+    _dgrad(feat, WvT, VW, z9, VW, rc, VW, W, accumulate=True)
+    _dgrad(xv_r, _Ptr(WvT.view(-1), W * VW), VW, z9, VW, rc, VW, XV, accumulate=True)
+    g = torch.relu(z9)
+    # rgb head
+    d9 = f32(rows, VW)
+    _dgrad(_Ptr(d_raw.view(-1), 0, ld=4), f32c(P["rgb_linear.weight"]), VW, d9, VW, rc, VW, 3, mask=z9.to(torch.bfloat16))
+    _wgrad(_Ptr(d_raw.view(-1), 0, ld=4), g, G["rgb_linear.weight"], VW, rc, 3, VW)
+    _colsum(_Ptr(d_raw.view(-1), 0, ld=4), G["rgb_linear.bias"], rc, 3)
+    # view layer: weights of the feature / direction / frame-code column blocks, bias, frame codes
+    GWv = G["views_linears.0.weight"]
+    _wgrad(d9, feat, GWv, W + XV + 128, rc, VW, W)
+    _wgrad(d9, xv_r, _Ptr(GWv.view(-1), W), W + XV + 128, rc, VW, XV)
+    d_cb = d9.view(n_rays, S, VW).sum(1).contiguous()                # the code / bias part is per ray
+    code_rows = codes_with_mean[cam_idx[:n_rays].long()].contiguous()
+    _wgrad(d_cb, code_rows, _Ptr(GWv.view(-1), W + XV), W + XV + 128, rcr, VW, 128)
+    _colsum(d_cb, G["views_linears.0.bias"], rcr, VW)
+    d_code = f32(n_rays, 128)
+    _dgrad(d_cb, _Ptr(Wv.view(-1), W + XV), W + XV + 128, d_code, 128, rcr, 128, VW)
+    G["framecodes.codes.weight"].index_add_(0, cam_idx[:n_rays].long(), d_code)
+    # feature layer (no activation) and the sigma head into d a7
+    d_feat = f32(rows, W)
+    _dgrad(d9, Wv, W + XV + 128, d_feat, W, rc, W, VW)
+    _colsum(d_feat, G["feature_linear.bias"], rc, W)
+    _wgrad(d_feat, a7, G["feature_linear.weight"], W, rc, W, W)
+    cur, nxt = f32(rows, W), f32(rows, W)
+    _dgrad(_Ptr(d_raw.view(-1), 3, ld=4), f32c(P["alpha_linear.weight"]), W, cur, W, rc, W, 1)
+    _wgrad(_Ptr(d_raw.view(-1), 3, ld=4), a7, G["alpha_linear.weight"], W, rc, 1, W)
+    _colsum(_Ptr(d_raw.view(-1), 3, ld=4), G["alpha_linear.bias"], rc, 1)
+    _dgrad(d_feat, Wf, W, cur, W, rc, W, W, accumulate=True, mask=a7)
+    a_prev = a7
+    for L in range(7, 0, -1):
+        Wl = f32c(P[f"pts_linears.{L}.weight"])
+        a_in = act(L - 1)
+        _colsum(cur, G[f"pts_linears.{L}.bias"], rc, W)
+        if L == 5:                                                   # skip layer: input = [xd (432) ; a4 (448)]
+            dW = G["pts_linears.5.weight"]
+            _wgrad(cur, xd_r, dW, XD + W, rc, W, XD)
+            _wgrad(cur, a_in, _Ptr(dW.view(-1), XD), XD + W, rc, W, W)
+            _dgrad(cur, _Ptr(Wl.view(-1), XD), XD + W, nxt, W, rc, W, W, mask=a_in)
+        else:
+            _wgrad(cur, a_in, G[f"pts_linears.{L}.weight"], W, rc, W, W)
+            _dgrad(cur, Wl, W, nxt, W, rc, W, W, mask=a_in)
+        cur, nxt = nxt, cur
+    _colsum(cur, G["pts_linears.0.bias"], rc, W)
+    _wgrad(cur, xd_r, G["pts_linears.0.weight"], XD, rc, W, XD)

@@ -49,16 +49,18 @@ def render(H, W, focal, chunk=1024 * 64, rays=None, near=0., far=1., use_viewdir
     return all_ret
 
 
-def rays_in_box(H, W, focal, c2w, cyl, device):
+def rays_in_box(H, W, focal, c2w, cyl, device, c2w_dev=None):
     """Pinhole rays of the pixels inside the image box of a bounding cylinder, generated on the device
-    (ray_utils.py:7-29,84-138; skeleton_utils.py:633-720).  -> rays_o, rays_d (n,3), flat pixel index (n)."""
+    (ray_utils.py:7-29,84-138; skeleton_utils.py:633-720).  -> rays_o, rays_d (n,3), flat pixel index (n).
+    c2w / cyl: host arrays (the pixel box is a host-side computation over 100 projected points); c2w_dev: the same
+    camera already on the device (saves the per-image upload)."""
     c2w_np = np.asarray(c2w, dtype=np.float32)
     tl, br = syn.cylinder_image_box(np.asarray(cyl, dtype=np.float32), H, W, float(focal), c2w_np)
     ys = torch.arange(int(tl[1]), int(br[1]), device=device, dtype=torch.float32)
     xs = torch.arange(int(tl[0]), int(br[0]), device=device, dtype=torch.float32)
     j, i = torch.meshgrid(ys, xs, indexing="ij")
     dirs = torch.stack([(i - W * 0.5) / focal, -(j - H * 0.5) / focal, -torch.ones_like(i)], -1).reshape(-1, 3)
-    c2w_t = torch.as_tensor(c2w_np, device=device)
+    c2w_t = torch.as_tensor(c2w_np, device=device) if c2w_dev is None else c2w_dev
     rays_d = torch.sum(dirs[:, None, :] * c2w_t[:3, :3], -1)
     rays_o = c2w_t[:3, -1].expand(rays_d.shape)
     idx = (j * W + i).reshape(-1).long()
@@ -77,16 +79,23 @@ def render_images(caster, args, c2ws, poses, H, W, focal=None, cam_idx=0, white_
     mine = list(range(rank, len(c2ws), world))
     out = torch.ones(len(mine), H * W, 3, device=dev) if white_bkgd else torch.zeros(len(mine), H * W, 3, device=dev)
     call = caster.render_graphed if graphed else caster
+    # every pose table and camera of this rank's images goes to the device ONCE (5 copies), not per image: a pageable
+    # host-to-device copy is synchronous, and one per tensor per image kept the GPU idle for half of each image
+    mine_poses = sorted({k % len(poses) for k in mine})
+    slot_of = {p: i for i, p in enumerate(mine_poses)}
+    tab = {name: torch.as_tensor(np.stack([np.asarray(poses[p][name], dtype=np.float32) for p in mine_poses])).to(dev)
+           for name in ("kps", "skts", "bones", "cyl")} if mine else {}
+    c2w_dev = torch.as_tensor(np.stack([np.asarray(c2ws[k], dtype=np.float32) for k in mine])).to(dev) if mine else None
     for slot, k in enumerate(mine):
         pose = poses[k % len(poses)]
-        ro, rd, idx = rays_in_box(H, W, focal, c2ws[k], pose["cyl"], dev)
+        ps = slot_of[k % len(poses)]
+        ro, rd, idx = rays_in_box(H, W, focal, c2ws[k], pose["cyl"], dev, c2w_dev=c2w_dev[slot])
         n = ro.shape[0]
         ones = torch.ones(n, 1, device=dev)
         ray_batch = torch.cat([ro, rd, near * ones, far * ones, rd / torch.norm(rd, dim=-1, keepdim=True)], -1)
-        t = lambda a: torch.as_tensor(a, device=dev)
-        ret = call(ray_batch, N_samples=args.N_samples, kp_batch=t(pose["kps"])[None].expand(n, -1, -1),
-                   skts=t(pose["skts"])[None].expand(n, -1, -1, -1), cyls=t(pose["cyl"])[None].expand(n, -1),
-                   bones=t(pose["bones"])[None].expand(n, -1, -1),
+        ret = call(ray_batch, N_samples=args.N_samples, kp_batch=tab["kps"][ps:ps + 1].expand(n, -1, -1),
+                   skts=tab["skts"][ps:ps + 1].expand(n, -1, -1, -1), cyls=tab["cyl"][ps:ps + 1].expand(n, -1),
+                   bones=tab["bones"][ps:ps + 1].expand(n, -1, -1),
                    cams=torch.full((n, 1), cam_idx, dtype=torch.long, device=dev), N_uniques=1, perturb=False,
                    N_importance=args.N_importance, raw_noise_std=0., nanmean_chunk=args.chunk)
         bg = 1.0 if white_bkgd else 0.0

@@ -32,12 +32,12 @@ def compute_loss(args, preds, batch, network):
     terms["rgb_loss"] = rgb_term(preds["rgb_map"], preds["acc_map"])
     if "rgb0" in preds:
         terms["rgb_loss0"] = rgb_term(preds["rgb0"], preds["acc0"]) * getattr(args, "coarse_weight", 1.0)
-    if "confd" in preds and args.agg_type == "sigmoid":
+    if "confd" in preds and getattr(args, "agg_type", None) == "sigmoid":
         labels = ((preds["T_i"] * preds["alpha"]) > 0).float()
         valid = 1 - preds["part_invalid"]
         p = network.sigmoid(preds["confd"], preds["part_invalid"], mask_invalid=False, clamp=False)
         terms["soft_softmax_loss"] = args.soft_softmax_loss_coef * (labels - (p * valid).sum(-1)).pow(2.).mean()
-    if getattr(args, "opt_vol_scale", False):
+    if getattr(args, "opt_vol_scale", False) and hasattr(network, "graph_net"):
         gn = network.graph_net
         scale = gn.axis_scale.abs().clamp(min=gn.init_scale.to(gn.axis_scale.device) * 0.05)
         # product written out: torch.prod's backward inspects the input for zeros on the host (a sync, illegal in capture)
@@ -55,9 +55,9 @@ def fused_loss_backward(args, preds, batch, network, extra_loss=None):
     axis_scale.grad directly, and autograd is entered at the render block's outputs.  `extra_loss` (a scalar with its own
     autograd graph, e.g. the pose regulariser) is back-propagated in the same sweep.  -> (total loss, dict of terms)."""
     from . import kernels as K
-    soft = args.soft_softmax_loss_coef if ("confd" in preds and args.agg_type == "sigmoid") else None
-    gn = network.graph_net
-    vol = bool(getattr(args, "opt_vol_scale", False)) and gn.axis_scale.requires_grad
+    soft = args.soft_softmax_loss_coef if ("confd" in preds and getattr(args, "agg_type", None) == "sigmoid") else None
+    gn = getattr(network, "graph_net", None)                # the A-NeRF field has no graph net / bone volumes
+    vol = gn is not None and bool(getattr(args, "opt_vol_scale", False)) and gn.axis_scale.requires_grad
     if vol and gn.axis_scale.grad is None:
         gn.axis_scale.grad = torch.zeros_like(gn.axis_scale)
     terms, g = K.train_loss(preds, batch["target_s"], batch.get("bgs", 1.0), args.loss_fn, getattr(args, "rgb_loss_coef", 1.0),

@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-/* ABI version of this header (bumped on any change of a signature or of a pointer-array contract): 3. */
+/* ABI version of this header (bumped on any change of a signature or of a pointer-array contract): 4. */
 int danbo_version(void);
 
 /* NF1 + NF2.  get_near_far_in_cylinder (core/utils/ray_utils.py:294-346) followed, when use_box != 0, by
@@ -278,6 +278,18 @@ int danbo_anerf_embed(const float* rays, int ray_stride, int S, const float* z, 
 int danbo_anerf_mlp(const void* xd, const void* xv, const void* wstream, const float* heads, const float* code_bias,
                     void* scratch, int n_rows, int S, float* out, int out_capacity, int num_sms, long long* trace,
                     void* stream);
+
+/* Train-mode variant of danbo_anerf_mlp: every layer's bf16 activation tile image is kept in `save`
+ * (danbo_anerf_save_bytes bytes: [tile][9 = pts_linears.0-7 outputs, feature_linear output][7 chunks of 16 KB],
+ * operand layout) for the backward pass (autograd of core/networks/nerf.py:164-209 as reached from trainer.py:573). */
+int danbo_anerf_save_bytes(int n_rows, long long* bytes);
+int danbo_anerf_mlp_save(const void* xd, const void* xv, const void* wstream, const float* heads, const float* code_bias,
+                         void* scratch, int n_rows, int S, float* out, int out_capacity, int num_sms, void* save,
+                         void* stream);
+
+/* Operand tile images ([tile][chunk][128 rows x 64 k] bf16, 128-byte swizzle; tile_stride bytes between tiles) ->
+ * row-major bf16 out (n_rows, n_chunks * 64): how the A-NeRF backward reads xd / xv / saved activations. */
+int danbo_anerf_untile(const void* img, long long tile_stride, int n_rows, int n_chunks, void* out, void* stream);
 
 #ifdef __cplusplus
 }

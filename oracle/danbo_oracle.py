@@ -362,8 +362,11 @@ def view_directions(rays_d, skts, view_mode="world"):
     raise NotImplementedError(view_mode)
 
 
-def field_eval(pts, rays_d, cams, skts, A, vol, P, rays_per_pose, training, agg_type="sigmoid", view_mode="world"):
-    """T1..A3 + V1 + M1 for points (N,S,3) -> raw (N,S,4), confd (N,S,24), invalid (N,S,24), stage dict."""
+def field_eval(pts, rays_d, cams, skts, A, vol, P, rays_per_pose, training, agg_type="sigmoid", view_mode="world",
+               mlp_fn=None):
+    """T1..A3 + V1 + M1 for points (N,S,3) -> raw (N,S,4), confd (N,S,24), invalid (N,S,24), stage dict.
+    mlp_fn (test hook): replaces `field_mlp` (same signature), e.g. by a restatement with the CUDA kernel's bf16 operand
+    rounding, so that a comparison can separate "declared bf16 arithmetic" from everything else."""
     N, S = pts.shape[:2]
     pts_t = world_to_bone(pts, skts, A)
     h, invalid, x = bone_features(pts_t, vol, P["graph_net.axis_scale"], rays_per_pose)
@@ -374,14 +377,14 @@ def field_eval(pts, rays_d, cams, skts, A, vol, P, rays_per_pose, training, agg_
     dens_in = pe_embed(hbar, 6)
     v_ray = view_inputs(view_directions(rays_d, skts, view_mode), cams, P, training)
     v = v_ray[:, None].expand(N, S, -1).reshape(N * S, -1)
-    raw = field_mlp(dens_in, v, P).reshape(N, S, 4)
+    raw = (mlp_fn or field_mlp)(dens_in, v, P).reshape(N, S, 4)
     stages = {"pts_t": pts_t, "x": x, "h": h, "p": p.reshape(N, S, J), "hbar": hbar.reshape(N, S, -1), "view_inputs": v_ray}
     return raw, a.reshape(N, S, J), invalid, stages
 
 
 def render_rays(ray_batch, pose_skts, pose_bones, pose_cyls, cams, A, P, S_c, S_f, rays_per_pose,
                 use_volume_near_far=False, training=False, rand=None, raw_noise_std=0., agg_type="sigmoid",
-                return_stages=False, z_samples=None, lindisp=False, view_mode="world"):
+                return_stages=False, z_samples=None, lindisp=False, view_mode="world", mlp_fn=None):
     """ray_batch (N,>=8); pose_* are per unique pose (G,...); ray n belongs to pose n // rays_per_pose.
     rand (training) = dict(t_rand (N,S_c), noise0 (N,S_c), u (N,S_f), noise1 (N,S_t)) drawn by the caller in
     the reference's order (SURVEY §7 hard part 4)."""
@@ -400,7 +403,8 @@ def render_rays(ray_batch, pose_skts, pose_bones, pose_cyls, cams, A, P, S_c, S_
     rand = rand or {}
     z = coarse_z(near, far, S_c, rand.get("t_rand"), lindisp)
     pts = ray_points(rays_o, rays_d, z)
-    raw0, confd0, inv0, st0 = field_eval(pts, rays_d, cams, skts, A, vol, P, rays_per_pose, training, agg_type, view_mode)
+    raw0, confd0, inv0, st0 = field_eval(pts, rays_d, cams, skts, A, vol, P, rays_per_pose, training, agg_type, view_mode,
+                                         mlp_fn)
     n0 = rand["noise0"] * raw_noise_std if "noise0" in rand else None
     out0 = composite(raw0, z, rays_d, n0)
     z_all, zs, order, inds = importance_sample(z, out0["weights"], S_f, rand.get("u"))
@@ -410,7 +414,8 @@ def render_rays(ray_batch, pose_skts, pose_bones, pose_cyls, cams, A, P, S_c, S_
         zs = z_samples
         z_all, order = torch.sort(torch.cat([z, zs], -1), -1)
     pts_f = ray_points(rays_o, rays_d, zs)
-    raw1, confd1, inv1, st1 = field_eval(pts_f, rays_d, cams, skts, A, vol, P, rays_per_pose, training, agg_type, view_mode)
+    raw1, confd1, inv1, st1 = field_eval(pts_f, rays_d, cams, skts, A, vol, P, rays_per_pose, training, agg_type, view_mode,
+                                         mlp_fn)
     raw = merge_sorted(raw0, raw1, order)
     confd = merge_sorted(confd0, confd1, order)
     inv = merge_sorted(inv0, inv1, order)

@@ -79,8 +79,10 @@ def _say(rank, msg):
 
 def worker_main(ref_path, out_path):
     """Body of one rank (launched by torch.distributed.run, like bench.py at N > 1)."""
+    import faulthandler
     import torch.distributed as dist
     from danbo_b200 import parallel
+    faulthandler.dump_traceback_later(150, exit=True)       # a hang prints every thread's Python stack, then exits
     rank, world, local = parallel.init_distributed()
     dev = torch.device("cuda", local)
     _say(rank, f"init done, world {world}")
@@ -100,8 +102,10 @@ def worker_main(ref_path, out_path):
     res["loss0_ref"] = ref["loss0"]
     _say(rank, f"gradient check done: rel {res['grad_rel']:.3e}")
     # (2) graphed iterations: forward + backward + all-reduce + Adam in one captured graph; (3) the same, eager
+    alive = [step]            # a CUDA graph holding NCCL nodes must not be destroyed while collectives are still being issued
     for tag, graph in (("graph", True), ("eager", False)):
         _, _, st = _setup(dev, world=world, graph=graph)
+        alive.append(st)
         losses = _train(st, b, ITERS).to(dev)
         _say(rank, f"{tag}: {ITERS} iterations done")
         dist.all_reduce(losses)
@@ -116,8 +120,10 @@ def worker_main(ref_path, out_path):
         with open(out_path, "w") as f:
             json.dump(res, f)
     dist.barrier()
-    dist.destroy_process_group()
+    torch.cuda.synchronize()
     _say(rank, "done")
+    sys.stdout.flush()
+    os._exit(0)               # skip interpreter teardown: the captured graphs (NCCL nodes) die with the process
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
@@ -130,15 +136,20 @@ def test_two_rank_training_equals_single_gpu():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
                "127.0.0.1", "--master-port", str(_free_port()), os.path.abspath(__file__), ref_path, out_path]
         # own process group + a hard limit: a hung collective must not outlive the test
-        proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, start_new_session=True)
-        try:
-            log, _ = proc.communicate(timeout=300)
-        except subprocess.TimeoutExpired:
-            os.killpg(proc.pid, signal.SIGKILL)
-            log, _ = proc.communicate()
-            pytest.fail("2-rank worker hung:\n" + log[-4000:])
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+        log_path = os.path.join(root, "gpurun_out", "multi_worker.log")          # survives whatever happens to this process
+        with open(log_path, "w") as lf:
+            proc = subprocess.Popen(cmd, stdout=lf, stderr=subprocess.STDOUT, start_new_session=True)
+            try:
+                proc.wait(timeout=240)
+            except subprocess.TimeoutExpired:
+                os.killpg(proc.pid, signal.SIGKILL)
+                proc.wait(timeout=30)
+                pytest.fail("2-rank worker hung:\n" + open(log_path).read()[-6000:])
+        log = open(log_path).read()
         print(log[-3000:])
-        assert proc.returncode == 0, log[-4000:]
+        assert proc.returncode == 0, log[-6000:]
         res = json.load(open(out_path))
     print("[multi]", json.dumps(res))
     assert res["grad_rel"] <= 2e-3, res                      # fp32 atomics order + per-shard near/far fill only
