@@ -123,11 +123,13 @@ def test_anerf_render_end_to_end():
         d = (ret[k].cpu() - fx["out." + k]).abs()
         print(f"[anerf e2e] {k}: mean {float(d.mean()):.3e} max {float(d.max()):.3e}")
         assert float(d.mean()) <= tol_mean and float(d.max()) <= tol_max, (k, float(d.mean()), float(d.max()))
-    # train mode is not part of this path
+    # train mode without random draws evaluates the same pixels (the autograd node's forward is the same launch sequence)
     caster.train()
-    with pytest.raises(NotImplementedError):
-        caster(rb, N_samples=args.N_samples, kp_batch=e(fx["pose_kps"][None]), skts=e(skts), cyls=e(cyl), bones=e(bones),
-               cams=fx["cams"].to(DEV), N_uniques=1, perturb=False, N_importance=args.N_importance, nerf_type="nerf")
+    tr = caster(rb, N_samples=args.N_samples, kp_batch=e(fx["pose_kps"][None]), skts=e(skts), cyls=e(cyl), bones=e(bones),
+                cams=fx["cams"].to(DEV), N_uniques=1, perturb=False, N_importance=args.N_importance, nerf_type="nerf")
+    assert tr["rgb_map"].requires_grad
+    for k in ("rgb_map", "acc_map", "rgb0"):
+        assert torch.equal(tr[k].detach(), ret[k]), k
 
 
 def test_anerf_full_size_properties():
@@ -259,3 +261,67 @@ def test_anerf_separate_fine_network():
     za = c["z_all"].cpu()
     assert bool((za[:, 1:] >= za[:, :-1]).all()) and float(za.min()) >= float(fx["st.z.0"].min()) - 1e-6 \
         and float(za.max()) <= float(fx["st.z.0"].max()) + 1e-6
+
+
+def test_anerf_training_step_gradients():
+    """Train-mode A-NeRF step (reference draws of tests/golden/train_anerf.npz): outputs, loss and the gradients of all
+    25 parameter tensors against the oracle's autograd on the same samples (the oracle is pinned to the reference's own
+    gradients by test_oracle_golden.py::test_anerf_training_step)."""
+    from danbo_b200 import synthetic as syn
+    fx = load_fixture("train_anerf")
+    caster, args, _ = make_anerf_caster(fx)
+    caster.train()
+    n_poses, rpp = int(fx["n_poses"]), int(fx["rays_per_pose"])
+    b = syn.training_batch(n_poses, rpp, seed=int(fx["batch_seed"]))
+    rand = {k: fx["rand." + k] for k in ("t_rand", "noise0", "u", "noise1")}
+    stages = {}
+    out = caster.render_rays(b["ray_batch"], N_samples=args.N_samples, kp_batch=b["kp_batch"], skts=b["skts"], cyls=b["cyls"],
+                             bones=b["bones"], cams=b["cams"], N_uniques=n_poses, perturb=1.0, N_importance=args.N_importance,
+                             raw_noise_std=float(fx["raw_noise_std"]), nerf_type="nerf",
+                             _rand={k: v.to(DEV) for k, v in rand.items()}, _stages=stages)
+    assert set(out) == {"rgb_map", "disp_map", "acc_map", "alpha", "T_i", "rgb0", "disp0", "acc0", "alpha0"}
+    tgt, bgs = b["target_s"].to(DEV), b["bgs"].to(DEV)
+    l1 = lambda rgb, acc, t, g: torch.mean(torch.abs(rgb + (1. - acc)[..., None] * g - t))
+    loss = l1(out["rgb_map"], out["acc_map"], tgt, bgs) + l1(out["rgb0"], out["acc0"], tgt, bgs)
+    loss.backward()
+    torch.cuda.synchronize()
+    got = {n: p.grad.detach().cpu() for n, p in caster.network.named_parameters() if p.grad is not None}
+    P = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in anerf_params(fx).items()}
+    ref = orc.anerf_render_rays(b["ray_batch"], b["skts"][::rpp], b["cyls"][::rpp], b["cams"], align_A(), P, int(fx["N_samples"]),
+                                int(fx["N_importance"]), rays_per_pose=rpp, training=True, rand=rand,
+                                raw_noise_std=float(fx["raw_noise_std"]), z_samples=stages["z_samples"].cpu())
+    ref_loss = l1(ref["rgb_map"], ref["acc_map"], b["target_s"], b["bgs"]) + l1(ref["rgb0"], ref["acc0"], b["target_s"], b["bgs"])
+    ref_loss.backward()
+    print(f"[anerf train] loss cuda {float(loss):.6f} oracle {float(ref_loss):.6f} reference {float(fx['loss.total']):.6f}")
+    assert abs(float(loss) - float(ref_loss)) <= 5e-3
+    big = max(float(v.grad.norm()) for v in P.values() if v.grad is not None)
+    checked, bad = 0, []
+    for k, v in P.items():
+        if v.grad is None:
+            continue
+        assert k in got, (k, "no gradient")
+        a, r = got[k].reshape(-1).double(), v.grad.reshape(-1).double()
+        cos = float(torch.dot(a, r) / (a.norm() * r.norm() + 1e-30))
+        rel = float((a - r).norm() / max(float(r.norm()), 1e-3 * big))
+        print(f"[anerf train] {k:32s} |g| {float(r.norm()):.3e} cos {cos:.5f} rel {rel:.3e}")
+        checked += 1
+        # bf16 forward + the reference's raw-noise gate (raw_noise_std = 1), as for the DANBO field's noisy fixtures
+        if (float(r.norm()) > 1e-3 * big and cos < 0.97) or rel > 0.3:
+            bad.append((k, cos, rel))
+    assert checked == 25 and not bad, bad
+
+
+def test_anerf_train_step_trains():
+    """training.TrainStep on the A-NeRF caster: loss kernel, backward, single-launch Adam; the loss must go down."""
+    import danbo_b200 as db
+    from danbo_b200 import synthetic as syn, training
+    fx = load_fixture("train_anerf")
+    caster, args, _ = make_anerf_caster(fx)
+    targs = db.make_args("anerf_base", no_reload=True, N_samples=int(fx["N_samples"]), N_importance=int(fx["N_importance"]))
+    b = syn.training_batch(2, 48, seed=4)
+    b = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in b.items()}
+    step = training.TrainStep(caster, targs)
+    torch.manual_seed(3)
+    losses = [float(step(b)[0]) for _ in range(15)]
+    print("[anerf train] losses", ["%.4f" % l for l in losses])
+    assert all(l == l for l in losses) and losses[-1] < losses[0] - 0.01

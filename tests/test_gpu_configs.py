@@ -156,4 +156,5 @@ def test_training_step_other_shipped_configs(name):
         cos = float(torch.dot(a, r) / (a.norm() * r.norm() + 1e-30))
         rel = float((a - r).norm() / max(float(r.norm()), 1e-3 * big))
         print(f"[{name}] {k:40s} cos {cos:.5f} rel {rel:.3e}")
-        assert (float(r.norm()) <= 1e-3 * big or cos >= 0.995) and rel <= 0.1, (k, cos, rel)
+        # measured on B200: cos >= 0.9992, rel <= 0.045
+        assert (float(r.norm()) <= 1e-3 * big or cos >= 0.997) and rel <= 0.08, (k, cos, rel)

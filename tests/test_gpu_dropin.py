@@ -19,6 +19,18 @@ DEV = "cuda"
 N_POSES, RPP = 4, 96
 
 
+class _reference_cuda_defaults:
+    """The reference runs under `torch.set_default_tensor_type('torch.cuda.FloatTensor')` (run_nerf.py:728,
+    run_render.py:1353): its helpers build constants with the legacy `torch.Tensor([...])` constructor and bare factory
+    calls and expect them on the GPU."""
+
+    def __enter__(self):
+        torch.set_default_tensor_type("torch.cuda.FloatTensor")
+
+    def __exit__(self, *exc):
+        torch.set_default_tensor_type("torch.FloatTensor")
+
+
 class _Handle(torch.nn.Module):
     """`.module`, as nn.DataParallel gives the reference's trainer (DataParallel itself would scatter a CPU module)."""
 
@@ -76,7 +88,8 @@ def test_reference_trainer_train_batch_on_this_caster(perturb):
     batch, b = _ref_batch(DEV)
     torch.manual_seed(11)
     caster.train()
-    loss_dict, stats = trainer.train_batch(batch, i=1, global_step=1)
+    with _reference_cuda_defaults():
+        loss_dict, stats = trainer.train_batch(batch, i=1, global_step=1)
     torch.cuda.synchronize()
     got = {k: float(v) for k, v in loss_dict.items()}
     assert set(got) == {"rgb_loss", "rgb_loss0", "soft_softmax_loss", "vol_scale_loss", "total_loss"}
@@ -133,14 +146,9 @@ def test_reference_render_path_on_this_caster():
     t = lambda a: torch.tensor(np.asarray(a))[None]
     kw = dict(kp=t(pose["kps"]), skts=t(pose["skts"]), bones=t(pose["bones"]), cams=torch.zeros(1, 1, dtype=torch.long),
               ret_acc=True, ext_scale=args.ext_scale)
-    # the reference renders under a CUDA default tensor type (run_nerf.py:728, run_render.py:1353)
-    torch.set_default_device(DEV)
-    try:
-        with torch.no_grad():
-            out = run_nerf.render_path(c2w, (H, H, 1.2 * H), args.chunk, kw_test,
-                                       **{k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in kw.items()})
-    finally:
-        torch.set_default_device("cpu")
+    with _reference_cuda_defaults(), torch.no_grad():
+        out = run_nerf.render_path(c2w.to(DEV), (H, H, 1.2 * H), args.chunk, kw_test,
+                                   **{k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in kw.items()})
     rgbs, disps, accs = out[0], out[1], out[2]
     ref_caster, kw_ref = rh.build(args, syn.rest_pose())
     rh.load_weights(ref_caster, syn.synthetic_params(0))
