@@ -81,21 +81,42 @@ class _RenderBlock(torch.autograd.Function):
         d_vol_blk = d_vol[k["p0"]:]
         agg_grads = [G[nm] for nm in AGG_NAMES] + [d_vol_blk, G["graph_net.axis_scale"]]
         d_skts = zeros(*k["p_skts"].shape) if ctx.needs_input_grad[3] else None      # p0 == 0: a block holds every pose
-        ws = None
-        if K.BACKWARD_IMPL == "tc":
-            ws = K.BwdWorkspace(max(k["act0"].capacity, k["act1"].capacity), dev)
+        # Two launch streams (K.BACKWARD_STREAMS): after a pass's dgrad the weight-gradient launches (transposes, wgrad,
+        # reduce, bias sums; then the ray-bias backward) and the field backward (feature gather + aggregation net) are
+        # independent - they read what dgrad wrote and add into disjoint gradient tensors - so the first group goes to a
+        # side stream.  At training sizes (3 072 rays) every one of these kernels is a partial wave, latency bound.
+        tc = K.BACKWARD_IMPL == "tc"
+        cur = torch.cuda.current_stream(dev)
+        side = None
+        if tc and K.BACKWARD_STREAMS > 1:
+            side = getattr(ctx.caster, "_bwd_side_stream", None)
+            if side is None or side.device != dev:
+                side = ctx.caster._bwd_side_stream = torch.cuda.Stream(device=dev)
+        wss = []
         first = True
         for (d_raw, S, z, mask, act, fo, sv, gl) in ((d_raw0, S_c, k["z0"], k["mask0"], k["act0"], k["f0"], k["sv0"], gl0),
                                                     (d_raw1, S_f, k["z1"], k["mask1"], k["act1"], k["f1"], k["sv1"], gl1)):
-            if ws is not None:
-                dX = K.mlp_backward_tc(P, G, d_raw, act, fo, sv, d_ray_bias, ws, repack=first)
+            if tc:
+                if side is not None or not wss:            # a workspace per pass when the passes' launches overlap
+                    wss.append(K.BwdWorkspace(act.capacity if side is not None else max(k["act0"].capacity, k["act1"].capacity), dev))
+                ws = wss[-1]
+                if not first:
+                    ws.wstream = wss[0].wstream            # the packed transposed weights are the same for both passes
+                dX = K.mlp_backward_tc(P, G, d_raw, act, fo, sv, d_ray_bias, ws, repack=first, wgrad_stream=side)
                 first = False
             else:
                 dX = K.mlp_backward(P, G, d_raw, act, fo, sv, d_ray_bias)
             K.field_agg_bwd(rays, S, z, mask, act, k["p_skts"], k["p_vol"], k["skip"], k["consts"], fo, dX, gl, agg_grads,
                             d_skts=d_skts)
-        K.ray_bias_bwd(k["rays_v"], k["cam_idx"], k["codes"], P["views_linears.0.weight"], d_ray_bias,
-                       G["views_linears.0.weight"], G["views_linears.0.bias"], G["framecodes.codes.weight"])
+        if side is not None:
+            # d_ray_bias is complete once the second pass's head backward has run: the side stream already waits for it
+            with torch.cuda.stream(side):
+                K.ray_bias_bwd(k["rays_v"], k["cam_idx"], k["codes"], P["views_linears.0.weight"], d_ray_bias,
+                               G["views_linears.0.weight"], G["views_linears.0.bias"], G["framecodes.codes.weight"])
+            cur.wait_stream(side)
+        else:
+            K.ray_bias_bwd(k["rays_v"], k["cam_idx"], k["codes"], P["views_linears.0.weight"], d_ray_bias,
+                           G["views_linears.0.weight"], G["views_linears.0.bias"], G["framecodes.codes.weight"])
         ctx.keep = None
         if in_place:
             return (None, None, d_vol, d_skts) + (None,) * len(PARAM_NAMES)

@@ -80,9 +80,10 @@ def f32c(t):
     return t.detach().to(torch.float32).contiguous()
 
 
-# "ffma": the fp32 aggregation-net kernel every published number was measured with.  "mma": split-bf16 mma.sync
-# (csrc/field_mma.cu), opt-in until it has run on hardware - `DANBO_PAIR_LOGITS=mma` or set this before building a caster.
-PAIR_LOGITS_IMPL = os.environ.get("DANBO_PAIR_LOGITS", "ffma")
+# "mma" (default since round 2): the aggregation net on tensor cores, split-bf16 mma.sync (csrc/field_mma.cu; logits
+# within 2e-5 of the fp32 kernel's, 0.85 -> 0.57 ms for the coarse field_agg call of a 512x512 image).  "ffma": the fp32
+# FFMA kernel of round 1 (`DANBO_PAIR_LOGITS=ffma`, or set this before building a caster).
+PAIR_LOGITS_IMPL = os.environ.get("DANBO_PAIR_LOGITS", "mma")
 
 
 class FieldConsts:
@@ -492,6 +493,9 @@ def mlp_backward(P, G, d_raw, active, fo, save, d_ray_bias):
 
 
 BACKWARD_IMPL = "tc"          # "tc": tcgen05 dgrad/wgrad kernels; "simt": the fp32 SIMT GEMM chain (kept as a cross-check)
+# 2: the weight-gradient launches of the training backward run on a side stream beside the field backward (autograd.py);
+# 1: one stream.  DANBO_BWD_STREAMS overrides.
+BACKWARD_STREAMS = int(os.environ.get("DANBO_BWD_STREAMS", "2"))
 
 
 class BwdWorkspace:
@@ -508,8 +512,11 @@ class BwdWorkspace:
         self.packed_key = None
 
 
-def mlp_backward_tc(P, G, d_raw, active, fo, save, d_ray_bias, ws, repack=True):
-    """Tensor-core backward of the fused MLP over the rows of one pass -> dX (cap,208) fp32; parameter grads added to G."""
+def mlp_backward_tc(P, G, d_raw, active, fo, save, d_ray_bias, ws, repack=True, wgrad_stream=None):
+    """Tensor-core backward of the fused MLP over the rows of one pass -> dX (cap,208) fp32; parameter grads added to G.
+    wgrad_stream: a side stream for the weight-gradient launches (transposes, wgrad, reduce, bias column sums).  They
+    depend only on what dgrad wrote and touch only the MLP's gradient tensors, so they can run beside the field backward
+    (which consumes dX on the calling stream); the caller joins the side stream before it returns."""
     lib = _lib.load()
     dev = d_raw.device
     cap = active.capacity
@@ -534,8 +541,16 @@ def mlp_backward_tc(P, G, d_raw, active, fo, save, d_ray_bias, ws, repack=True):
     db_names = ["feature_linear.bias"] + [f"pts_linears.{i}.bias" for i in range(7, -1, -1)]
     dw = (ctypes.c_void_p * 10)(*[G[n].data_ptr() for n in dw_names])
     db = (ctypes.c_void_p * 9)(*[G[n].data_ptr() for n in db_names])
-    _lib.check(lib.danbo_mlp_wgrad(_p(save.act), _p(fo.x_rows), _p(ws.delta), cap, _p(active.count), cap, _p(ws.deltaT), 1,
-                                   _p(ws.actT), _p(ws.partial), dw, db, _stream()), "danbo_mlp_wgrad")
+
+    def wgrad():
+        _lib.check(lib.danbo_mlp_wgrad(_p(save.act), _p(fo.x_rows), _p(ws.delta), cap, _p(active.count), cap, _p(ws.deltaT), 1,
+                                       _p(ws.actT), _p(ws.partial), dw, db, _stream()), "danbo_mlp_wgrad")
+    if wgrad_stream is None:
+        wgrad()
+    else:
+        wgrad_stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(wgrad_stream):
+            wgrad()
     _count(8)
     return dX
 

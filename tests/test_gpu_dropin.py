@@ -29,6 +29,23 @@ class _reference_cuda_defaults:
 
     def __exit__(self, *exc):
         torch.set_default_tensor_type("torch.FloatTensor")
+        if torch.empty(0).device.type != "cpu":             # the legacy call does not always take the device back
+            torch.set_default_device("cpu")
+
+
+def _cpu_ray_generation(fn):
+    """Compatibility shim (like F5 / F6 of oracle/ref_harness.py): under a CUDA default tensor type the reference's
+    `kp_to_valid_rays` (ray_utils.py:84-138) indexes CPU ray tensors with `torch.arange` results that current torch puts
+    on the GPU, which torch >= 2 rejects.  The wrapper runs that one function under the CPU default, unmodified."""
+    def wrapped(*a, **k):
+        torch.set_default_tensor_type("torch.FloatTensor")
+        try:
+            a = [x.cpu() if torch.is_tensor(x) else x for x in a]
+            k = {n: (x.cpu() if torch.is_tensor(x) else x) for n, x in k.items()}
+            return fn(*a, **k)
+        finally:
+            torch.set_default_tensor_type("torch.cuda.FloatTensor")
+    return wrapped
 
 
 class _Handle(torch.nn.Module):
@@ -76,6 +93,19 @@ def test_reference_trainer_train_batch_on_this_caster(perturb):
     extra = ["--N_rand", str(N_POSES * RPP), "--N_sample_images", str(N_POSES), "--perturb", str(perturb),
              "--raw_noise_std", str(perturb)]
     args = rh.parse_args("h36m_zju/danbo_fast.txt", extra)
+    ref_losses = None
+    if perturb == 0.0:
+        # (b) the reference's own caster (CPU, fp32) under the same Trainer code, same batch - run first, before anything
+        # touches the default tensor type
+        ref_caster, kw_ref = rh.build(args, syn.rest_pose())
+        rh.load_weights(ref_caster, syn.synthetic_params(0))
+        ref_caster.train()
+        kw_ref_train = dict(kw_ref, ray_caster=_Handle(ref_caster), perturb=args.perturb, raw_noise_std=args.raw_noise_std)
+        opt_ref = torch.optim.Adam(ref_caster.network.parameters(), lr=args.lrate)
+        tr_ref = Trainer(args, _attrs(), opt_ref, None, kw_ref_train, kw_ref, popt_kwargs=None, device=torch.device("cpu"))
+        batch_cpu, _ = _ref_batch("cpu")
+        ld_ref, _ = tr_ref.train_batch(batch_cpu, i=1, global_step=1)
+        ref_losses = {k: float(v) for k, v in ld_ref.items()}
     db.install()
     try:
         kw_train, kw_test, start, grad_vars, optimizer, _ = run_nerf.create_raycaster(args, _attrs(), device=torch.device(DEV))
@@ -110,21 +140,11 @@ def test_reference_trainer_train_batch_on_this_caster(perturb):
           f"params max diff {float((p_after - p2).abs().max()):.3e}")
     assert abs(got["total_loss"] - float(loss2)) <= 2e-5 * max(abs(float(loss2)), 1.0)
     assert float((p_after - p2).abs().max()) <= 2e-4            # one Adam step moves weights by lr = 5e-4
-
-    if perturb == 0.0:
-        # (b) the reference's own caster (CPU, fp32) under the same Trainer code, same batch
-        ref_caster, kw_ref = rh.build(args, syn.rest_pose())
-        rh.load_weights(ref_caster, syn.synthetic_params(0))
-        ref_caster.train()
-        kw_ref_train = dict(kw_ref, ray_caster=_Handle(ref_caster), perturb=args.perturb, raw_noise_std=args.raw_noise_std)
-        opt_ref = torch.optim.Adam(ref_caster.network.parameters(), lr=args.lrate)
-        tr_ref = Trainer(args, _attrs(), opt_ref, None, kw_ref_train, kw_ref, popt_kwargs=None, device=torch.device("cpu"))
-        batch_cpu, _ = _ref_batch("cpu")
-        ld_ref, _ = tr_ref.train_batch(batch_cpu, i=1, global_step=1)
+    if ref_losses is not None:
         for k in got:
-            r = float(ld_ref[k])
-            print(f"[dropin] {k}: this caster {got[k]:.6f}  reference caster {r:.6f}")
-            assert abs(got[k] - r) <= 3e-3 * max(abs(r), 1e-2), k
+            print(f"[dropin] {k}: this caster {got[k]:.6f}  reference caster (CPU) {ref_losses[k]:.6f}")
+            assert abs(got[k] - ref_losses[k]) <= 3e-3 * max(abs(ref_losses[k]), 1e-2), k
+
 
 
 def test_reference_render_path_on_this_caster():
@@ -146,15 +166,21 @@ def test_reference_render_path_on_this_caster():
     t = lambda a: torch.tensor(np.asarray(a))[None]
     kw = dict(kp=t(pose["kps"]), skts=t(pose["skts"]), bones=t(pose["bones"]), cams=torch.zeros(1, 1, dtype=torch.long),
               ret_acc=True, ext_scale=args.ext_scale)
-    with _reference_cuda_defaults(), torch.no_grad():
-        out = run_nerf.render_path(c2w.to(DEV), (H, H, 1.2 * H), args.chunk, kw_test,
-                                   **{k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in kw.items()})
-    rgbs, disps, accs = out[0], out[1], out[2]
+    # the reference's own caster on the CPU first (before the default tensor type is touched)
     ref_caster, kw_ref = rh.build(args, syn.rest_pose())
     rh.load_weights(ref_caster, syn.synthetic_params(0))
     ref_caster.eval()
     with torch.no_grad():
         out_ref = run_nerf.render_path(c2w, (H, H, 1.2 * H), args.chunk, kw_ref, **kw)
+    orig_rays = run_nerf.kp_to_valid_rays
+    run_nerf.kp_to_valid_rays = _cpu_ray_generation(orig_rays)
+    try:
+        with _reference_cuda_defaults(), torch.no_grad():
+            out = run_nerf.render_path(c2w.to(DEV), (H, H, 1.2 * H), args.chunk, kw_test,
+                                       **{k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in kw.items()})
+    finally:
+        run_nerf.kp_to_valid_rays = orig_rays
+    rgbs, disps, accs = out[0], out[1], out[2]
     for name, a, r in (("rgb", rgbs, out_ref[0]), ("disp", disps, out_ref[1]), ("acc", accs, out_ref[2])):
         e = np.abs(np.asarray(a) - np.asarray(r))
         print(f"[dropin] render_path {name}: shape {np.asarray(a).shape} mean err {e.mean():.3e} max {e.max():.3e}")
