@@ -5,7 +5,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PATH = os.path.join(_HERE, "libdanbo_b200.so")
 _lib = None
-ABI_VERSION = 4          # danbo_version() of the header this binding was written against
+ABI_VERSION = 5          # danbo_version() of the header this binding was written against
 
 c_p = ctypes.c_void_p
 c_i = ctypes.c_int
@@ -20,6 +20,7 @@ _SIGNATURES = {
     "danbo_pack_agg_frags": [c_p, c_p, c_p],
     "danbo_ray_bias": [c_p, c_i, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p],
     "danbo_mlp_workspace_bytes": [c_p, c_p, c_p],
+    "danbo_mlp_empty_rows": [c_p, c_i, c_p, c_p, c_i, c_p],
     "danbo_mlp_set_cta_pair": [c_i],
     "danbo_graph_net_fwd": [c_p, c_i, c_p, c_p, c_p, c_p],
     "danbo_graph_net_bwd": [c_i, c_p, c_p, c_p, c_p, c_p, c_p],

@@ -93,9 +93,19 @@ class _RenderBlock(torch.autograd.Function):
             if side is None or side.device != dev:
                 side = ctx.caster._bwd_side_stream = torch.cuda.Stream(device=dev)
         wss = []
+        alive = []          # tensors read by side-stream launches: must not return to the allocator before the streams join
         first = True
-        for (d_raw, S, z, mask, act, fo, sv, gl) in ((d_raw0, S_c, k["z0"], k["mask0"], k["act0"], k["f0"], k["sv0"], gl0),
-                                                    (d_raw1, S_f, k["z1"], k["mask1"], k["act1"], k["f1"], k["sv1"], gl1)):
+        side2 = None
+        if side is not None:
+            # a third stream for the coarse pass's field backward: it only needs that pass's dX, so the fine pass's head /
+            # dgrad launches (main stream) need not wait for it.  Both passes' field backward add into the aggregation
+            # net / bone volume gradients with atomics, so they may overlap.
+            side2 = getattr(ctx.caster, "_bwd_side_stream2", None)
+            if side2 is None or side2.device != dev:
+                side2 = ctx.caster._bwd_side_stream2 = torch.cuda.Stream(device=dev)
+        for ip, (d_raw, S, z, mask, act, fo, sv, gl) in enumerate((
+                (d_raw0, S_c, k["z0"], k["mask0"], k["act0"], k["f0"], k["sv0"], gl0),
+                (d_raw1, S_f, k["z1"], k["mask1"], k["act1"], k["f1"], k["sv1"], gl1))):
             if tc:
                 if side is not None or not wss:            # a workspace per pass when the passes' launches overlap
                     wss.append(K.BwdWorkspace(act.capacity if side is not None else max(k["act0"].capacity, k["act1"].capacity), dev))
@@ -106,8 +116,17 @@ class _RenderBlock(torch.autograd.Function):
                 first = False
             else:
                 dX = K.mlp_backward(P, G, d_raw, act, fo, sv, d_ray_bias)
-            K.field_agg_bwd(rays, S, z, mask, act, k["p_skts"], k["p_vol"], k["skip"], k["consts"], fo, dX, gl, agg_grads,
-                            d_skts=d_skts)
+            alive.append(dX)
+            if side2 is not None and ip == 0:
+                side2.wait_stream(cur)
+                with torch.cuda.stream(side2):
+                    K.field_agg_bwd(rays, S, z, mask, act, k["p_skts"], k["p_vol"], k["skip"], k["consts"], fo, dX, gl,
+                                    agg_grads, d_skts=d_skts)
+            else:
+                K.field_agg_bwd(rays, S, z, mask, act, k["p_skts"], k["p_vol"], k["skip"], k["consts"], fo, dX, gl,
+                                agg_grads, d_skts=d_skts)
+        if side2 is not None:
+            cur.wait_stream(side2)
         if side is not None:
             # d_ray_bias is complete once the second pass's head backward has run: the side stream already waits for it
             with torch.cuda.stream(side):
@@ -118,6 +137,7 @@ class _RenderBlock(torch.autograd.Function):
             K.ray_bias_bwd(k["rays_v"], k["cam_idx"], k["codes"], P["views_linears.0.weight"], d_ray_bias,
                            G["views_linears.0.weight"], G["views_linears.0.bias"], G["framecodes.codes.weight"])
         ctx.keep = None
+        del alive, wss
         if in_place:
             return (None, None, d_vol, d_skts) + (None,) * len(PARAM_NAMES)
         return (None, None, d_vol, d_skts) + tuple(G[name] for name in PARAM_NAMES)

@@ -38,6 +38,8 @@ __host__ __device__ constexpr int stages_per_slot(bool pair) { return pair ? 2 :
 constexpr int kStageBytes = 128 * 64 * 2;          // 16 KB
 constexpr int kXBytes = DANBO_X_TILE_BYTES;        // 64 KB
 constexpr int kNumHeadFloats = 9 * 256 + 256 + 3 * 128 + 4;   // biases L0..L8, w_alpha, W_rgb, b_alpha, b_rgb[3]
+constexpr int kEmptyOff = kNumHeadFloats + 4;                 // heads[kEmptyOff ..): c[128], sigma0 of a sample no bone sees
+constexpr int kEmptyFloats = 132;
 constexpr int kThreads = 320;            // producer warp, MMA warp, 8 epilogue warps
 
 // TMEM column map
@@ -528,14 +530,94 @@ __global__ void pack_weights_kernel(PackArgs a, __nv_bfloat16* __restrict__ wstr
     }
 }
 
+// The field's output for a sample NO bone sees: blended feature h = 0, so the MLP input is PE(0) for every such sample and
+// only the per-ray view bias varies.  The density trunk, sigma and the feature part of the view layer are therefore
+// constants of the weights: c[o] = (W_v[:, :256] . feat(PE(0)))[o] and sigma0, computed here in fp32 once per weight
+// pack (one block; a warp per output row, coalesced row reads).  danbo_ray_bias then finishes each ray's empty-sample
+// output as rgb = W_rgb . relu(c + ray_bias) + b_rgb - 261 121 of the 2.8 M MLP rows of a 512x512 image disappear.
+// (nerf.py:176-209 on an all-zero blended feature; danbo.py:299-302.)
+__global__ void __launch_bounds__(1024)
+empty_trunk_kernel(PackArgs a, float* __restrict__ out /* c[128], sigma0, 3 unused */) {
+    __shared__ float buf0[DANBO_X_COLS + 256], buf1[DANBO_X_COLS + 256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // PE(0) = [0 x 15 | per octave: sin(0) x 15, cos(0) x 15]
+    for (int i = threadIdx.x; i < DANBO_X_COLS; i += blockDim.x) {
+        const float v = (i >= 15 && ((i - 15) % 30) >= 15) ? 1.f : 0.f;
+        buf0[i] = v; buf1[i] = v;                            // both buffers start with x: layer 5 reads [x ; h4]
+    }
+    __syncthreads();
+    auto layer = [&](const float* in, int n_in, const float* W, int ld, const float* bias, float* dst, int n_out, bool relu) {
+        for (int o = warp; o < n_out; o += 32) {
+            const float* row = W + (size_t)o * ld;
+            float s = 0.f;
+            for (int k = lane; k < n_in; k += 32) s = fmaf(__ldg(row + k), in[k], s);
+#pragma unroll
+            for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+            if (lane == 0) { s += bias ? __ldg(bias + o) : 0.f; dst[o] = relu ? fmaxf(s, 0.f) : s; }
+        }
+        __syncthreads();
+    };
+    // activations live behind the x prefix of the two buffers, ping-pong
+    float* h[2] = {buf0 + DANBO_X_COLS, buf1 + DANBO_X_COLS};
+    layer(buf0, DANBO_X_COLS, a.w[0], DANBO_X_COLS, a.b[0], h[0], 256, true);
+    int cur = 0;
+    for (int L = 1; L < 8; ++L) {
+        if (L == 5) layer((cur ? buf1 : buf0), DANBO_X_COLS + 256, a.w[5], DANBO_X_COLS + 256, a.b[5], h[cur ^ 1], 256, true);
+        else layer(h[cur], 256, a.w[L], 256, a.b[L], h[cur ^ 1], 256, true);
+        cur ^= 1;
+    }
+    // sigma0 = w_alpha . h7 + b_alpha ; feat = W_f h7 + b_f ; c = W_v[:, :256] feat
+    layer(h[cur], 256, a.w_alpha, 256, a.b_alpha, out + 128, 1, false);
+    layer(h[cur], 256, a.w_feat, 256, a.b_feat, h[cur ^ 1], 256, false);
+    layer(h[cur ^ 1], 256, a.w_view, 411, nullptr, out, 128, false);
+}
+
+// One warp per ray: raw_tail[ray] = [W_rgb . relu(c + ray_bias[ray]) + b_rgb, sigma0].
+__global__ void __launch_bounds__(256)
+empty_rows_kernel(const float* __restrict__ ray_bias, int n_rays, const float* __restrict__ heads, float4* __restrict__ raw_tail) {
+    const int lane = threadIdx.x & 31;
+    const float* ec = heads + kEmptyOff;
+    const float4 c = *reinterpret_cast<const float4*>(ec + lane * 4);
+    const float* wr = heads + 10 * 256;                     // W_rgb (3,128), then b_alpha, b_rgb[3]
+    float4 w[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) w[ch] = *reinterpret_cast<const float4*>(wr + ch * 128 + lane * 4);
+    const float sigma0 = ec[128], b0 = wr[385], b1 = wr[386], b2 = wr[387];
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ray < n_rays; ray += warps) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(ray_bias + (size_t)ray * 128) + lane);
+        const float g0 = fmaxf(c.x + b.x, 0.f), g1 = fmaxf(c.y + b.y, 0.f), g2 = fmaxf(c.z + b.z, 0.f), g3 = fmaxf(c.w + b.w, 0.f);
+        float r[3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) r[ch] = w[ch].x * g0 + w[ch].y * g1 + w[ch].z * g2 + w[ch].w * g3;
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            r[0] += __shfl_xor_sync(0xffffffffu, r[0], m); r[1] += __shfl_xor_sync(0xffffffffu, r[1], m);
+            r[2] += __shfl_xor_sync(0xffffffffu, r[2], m);
+        }
+        if (lane == 0) raw_tail[ray] = make_float4(r[0] + b0, r[1] + b1, r[2] + b2, sigma0);
+    }
+}
+
 }  // namespace mlp
 }  // namespace danbo
 
 using namespace danbo;
 
+extern "C" int danbo_mlp_empty_rows(const float* ray_bias, int n_rays, const float* heads, float* raw_tail, int num_sms,
+                                    void* stream) {
+    if (n_rays <= 0) return 0;
+    if (!ray_bias || !heads || !raw_tail || (reinterpret_cast<uintptr_t>(raw_tail) & 15)) return -1;
+    int blocks = (n_rays + 7) / 8;
+    if (blocks > num_sms * 8) blocks = num_sms * 8;
+    mlp::empty_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ray_bias, n_rays, heads, (float4*)raw_tail);
+    DANBO_CHECK_LAUNCH();
+    return 0;
+}
+
 extern "C" int danbo_mlp_workspace_bytes(long long* wstream_bytes, long long* heads_bytes, long long* raybias_bytes) {
     *wstream_bytes = 2 * 84LL * mlp::kStageBytes;        // single-CTA order, then the CTA-pair order
-    *heads_bytes = (long long)mlp::kNumHeadFloats * 4;
+    *heads_bytes = (long long)(mlp::kEmptyOff + mlp::kEmptyFloats) * 4;     // + the empty-sample constants (empty_trunk_kernel)
     *raybias_bytes = (long long)mlp::kRayBiasFloats * 4;
     return 0;
 }
@@ -549,6 +631,8 @@ extern "C" int danbo_pack_mlp_weights(const float* const* w_pts, const float* co
     a.w_alpha = w_alpha; a.b_alpha = b_alpha; a.w_feat = w_feat; a.b_feat = b_feat;
     a.w_view = w_view; a.b_view = b_view; a.w_rgb = w_rgb; a.b_rgb = b_rgb;
     mlp::pack_weights_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(a, (__nv_bfloat16*)wstream, heads, wv_ray);
+    DANBO_CHECK_LAUNCH();
+    mlp::empty_trunk_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(a, heads + mlp::kEmptyOff);
     DANBO_CHECK_LAUNCH();
     return 0;
 }

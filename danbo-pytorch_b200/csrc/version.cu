@@ -1,2 +1,2 @@
 // ABI version of include/danbo_b200.h
-extern "C" int danbo_version(void) { return 4; }
+extern "C" int danbo_version(void) { return 5; }

@@ -262,7 +262,7 @@ class PackedMLP:
         _lib.check(lib.danbo_pack_mlp_weights(wa, ba, *[_p(t) for t in others], _p(self.wstream), _p(self.heads),
                                               _p(self.wv_ray), _stream()), "danbo_pack_mlp_weights")
         self._keep = (ws, bs, others)          # keep sources alive until the stream has consumed them
-        _count(1)
+        _count(2)
         return self
 
 
@@ -279,6 +279,20 @@ def ray_bias(rays, cam_idx, codes_with_mean, packed):
                    "danbo_ray_bias")
     _count(2)
     return out
+
+
+def mlp_empty_rows(rbias, packed, raw_tail):
+    """raw_tail (n,4) <- the field's output for "a sample no bone sees" of every ray, from the constants the weight pack
+    left behind the heads and the ray's view bias (danbo_mlp_empty_rows): these rows then need not go through the MLP."""
+    _need_cuda(rbias, raw_tail)
+    n = rbias.shape[0]
+    assert raw_tail.shape[0] == n and raw_tail.is_contiguous() and raw_tail.dtype == torch.float32
+    dev = rbias.device
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    with _Timed("ray_bias"):
+        _lib.check(_lib.load().danbo_mlp_empty_rows(_p(rbias), n, _p(packed.heads), _p(raw_tail), num_sms(idx), _stream()),
+                   "danbo_mlp_empty_rows")
+    _count(1)
 
 
 def set_mlp_cta_pair(enable):

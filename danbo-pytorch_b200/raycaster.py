@@ -330,14 +330,20 @@ class RayCaster(nn.Module):
         rbias = K.ray_bias(rays_v, cam_idx, codes, packed)
         inv_B = 1.0 / B
         save = keep is not None
+        # A sample no bone sees has MLP input PE(0): its output depends on the ray only through the view bias.  Without a
+        # backward pass the n per-ray rows come from the weight pack's constants (K.mlp_empty_rows) instead of the MLP
+        # (9 % of the rows of a 512x512 image); with one they stay MLP rows, so that their gradient takes the same path.
+        const_empty = not save
+        raw0 = torch.empty(n * S_c + n, 4, device=rays.device, dtype=torch.float32)
+        if const_empty:
+            K.mlp_empty_rows(rbias, packed, raw0[n * S_c:])
         # ---- coarse pass
         t_rand = rand.get("t_rand") if (training and perturb > 0) or "t_rand" in rand else None
         z0, mask0, act0 = K.sample_mask(rays, S_c, p_skts, skip, consts, near=near, far=far, t_rand=t_rand,
-                                        append_empty=True, lindisp=lindisp)
+                                        append_empty=not const_empty, lindisp=lindisp)
         agg_mode = self.network.agg_mode
         f0 = K.field_agg(rays, S_c, z0, mask0, act0, p_skts, p_vol, skip, consts, want_hbar=save, want_xrows=save,
                          agg_mode=agg_mode)
-        raw0 = torch.empty(n * S_c + n, 4, device=rays.device, dtype=torch.float32)
         sv0 = sv1 = None
         if save:
             sv0 = K.ActSave(act0.capacity, rays.device)

@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-/* ABI version of this header (bumped on any change of a signature or of a pointer-array contract): 4. */
+/* ABI version of this header (bumped on any change of a signature or of a pointer-array contract): 5. */
 int danbo_version(void);
 
 /* NF1 + NF2.  get_near_far_in_cylinder (core/utils/ray_utils.py:294-346) followed, when use_box != 0, by
@@ -78,6 +78,13 @@ int danbo_field_agg(const float* rays, int ray_stride, int n_rays, int S, const 
                     const float* pose_vol, int rays_per_pose, int n_poses, const float* const* consts, void* xtiles,
                     int* row_ray, float* logits, float* hbar_out, void* x_rows, int* work, int pair_capacity,
                     int num_sms, int agg_mode, void* stream);
+
+/* Output of the field for a sample NO bone sees (blended feature 0 -> MLP input PE(0), danbo.py:299-302 + nerf.py:176-209):
+ * the density trunk and the feature part of the view layer are constants of the weights (danbo_pack_mlp_weights leaves
+ * them behind the heads), so per ray only rgb = W_rgb . relu(c + ray_bias) + b_rgb remains.  raw_tail (n_rays,4) =
+ * [rgb, sigma0]: the compositing kernels read it for every sample whose visibility mask is 0.  heads = the buffer
+ * danbo_pack_mlp_weights filled; ray_bias = danbo_ray_bias's output. */
+int danbo_mlp_empty_rows(const float* ray_bias, int n_rays, const float* heads, float* raw_tail, int num_sms, void* stream);
 
 /* V1 folded into the view layer: out (n_rays,128) = W_v[:,256:411] . [PE(rays_d) ; frame code] + b_v
  * (core/networks/nerf.py:252-279, core/networks/embedding.py:86-108).  codes is (n_codes+1,128) with the mean code in

@@ -45,7 +45,7 @@ def bits_to_invalid(mask):
 def test_library_loads_and_version():
     import danbo_b200
     lib = danbo_b200._lib.load()
-    assert lib.danbo_version() == danbo_b200._lib.ABI_VERSION == 4
+    assert lib.danbo_version() == danbo_b200._lib.ABI_VERSION == 5
 
 
 @pytest.mark.parametrize("name", RENDER)
