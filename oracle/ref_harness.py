@@ -45,8 +45,9 @@ def parse_args(config="h36m_zju/danbo_fast.txt", extra=()):
     return args
 
 
-def build(args, rest_pose, n_views=8, near=1.0, far=5.0, seed=0):
-    """create_raycaster under the shims -> the bare (non-DataParallel) reference ray caster."""
+def build(args, rest_pose, n_views=8, near=1.0, far=5.0, seed=0, device="cpu"):
+    """create_raycaster under the shims -> the bare (non-DataParallel) reference ray caster, on `device` (the reference
+    wraps its caster in nn.DataParallel, which MOVES the module to the GPU when exactly one is visible)."""
     rc, _ = _imports()
     from core.utils.skeleton_utils import SMPLSkeleton
 
@@ -75,6 +76,7 @@ def build(args, rest_pose, n_views=8, near=1.0, far=5.0, seed=0):
     finally:
         rc.get_skel_profile_from_rest_pose = orig_profile
         rc.create_nerf = orig_create
+    kw_test["ray_caster"].to(device)
     return kw_test["ray_caster"], kw_test
 
 
