@@ -32,9 +32,9 @@ import torch  # noqa: E402
 
 MLP_FLOP_PER_SAMPLE = 1354752          # SURVEY §8(a) row M1 (FlopCounter-verified): 677 376 MAC / sample
 # dram__bytes_read.sum + dram__bytes_write.sum of one mlp_kernel launch from the ncu --set full capture under profiles/
-# (profiles/r1c_ncu_mlp_summary.txt, launch 0: the 2.13 M-row coarse launch of the whole 261 121-ray image; 528 B/row read
-# once = the X tiles with K padded 208 -> 256, + 16 B/row of output)
-MLP_DRAM_BYTES_PER_LAUNCH = 1126916000 + 34257152
+# (profiles/r2_ncu_render_summary.txt: the 1.03 M-row fine-pass launch of the whole 261 121-ray image; 512 B/row of X tile
+# read once - K padded 208 -> 256 - + 16 B/row of output).  A constant from that capture, not measured in the run.
+MLP_DRAM_BYTES_PER_LAUNCH = 522275000 + 18544896
 H = W = 512
 PRESET = "danbo_fast"
 
@@ -337,6 +337,8 @@ def run_ours(opt):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "danbo::mlp::mlp_kernel<true, true> (CTA pairs, cta_group::2)", "achieved": achieved,
                      "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": MLP_DRAM_BYTES_PER_LAUNCH,
+                     "traffic_source": "profiles/r2_ncu_render_summary.txt (ncu --set full, dram__bytes read + write of the fine-pass "
+                                       "launch, 1.03 M rows = 525 B/row); not measured in this run",
                      "peak_source": f"MEASURED_PEAKS.json bf16_tflops, burst: each launch timed alone ({peaks['source']})",
                      "frac_of_sustained": achieved / peaks["bf16_tflops_sustained"],
                      "launches_timed": len(mlp_ms), "rows_per_step": float(sum(mlp_rows)) / max(opt.steps, 1),

@@ -26,6 +26,12 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    if force:                                               # from clean: no stale object can end up in the library
+        for f in os.listdir(CSRC):
+            if f.endswith(".o"):
+                os.remove(os.path.join(CSRC, f))
+        if os.path.exists(LIB):
+            os.remove(LIB)
     objs = []
     procs = []
     for src in SOURCES:
