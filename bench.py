@@ -304,8 +304,7 @@ def run_ours(opt):
             except Exception as exc:
                 configs[key] = {"error": repr(exc)}
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world)
         return
     peaks = measured_peaks()
     total_rays = (sum(shard_sizes) if world > 1 else n_rays) * opt.steps       # every rank renders its own view
@@ -351,8 +350,22 @@ def run_ours(opt):
     if world == 1:
         line["cpu_baseline"] = cpu_baseline(sample_rays=REF_SAMPLE_RAYS, repeats=1)     # ~8 s on the box's 16 host cores
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    _finish(world)
+
+
+def _finish(world):
+    """End of a rank.  At N > 1 the captured training graphs hold NCCL nodes; tearing the process group down (or letting the
+    interpreter destroy those graphs) while they are alive deadlocks in NCCL's teardown - measured: the 8-rank job printed
+    its line and then hung until the driver's limit.  So: rendezvous, flush, and leave without running destructors; the
+    communicator and the graphs die with the process."""
+    if world <= 1:
+        return
+    import torch.distributed as dist
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 _KEEP_ALIVE = []

@@ -41,20 +41,22 @@ __device__ __forceinline__ double warp_excl_sum(double v, int lane) {
 
 // Composites one ray whose S samples are described by fetch(i) -> raw (rgb, sigma).  sm.z must hold z[0..S).
 // Writes weights / alpha rows and the per-ray maps; leaves the weights in sm.w.
-template <class Fetch>
+// kE = samples per lane = ceil(S / 32), a template parameter so that the per-lane loops have no dead iterations (the
+// generic 5-element loops spent 4 of 5 iterations on predicated-off work at S = 32).
+template <int kE, class Fetch>
 __device__ __forceinline__ void composite_ray(RaySmem& sm, int S, int lane, float norm_d, float inv_B,
                                               const float* __restrict__ noise_row, Fetch fetch,
                                               float* __restrict__ w_row, float* __restrict__ alpha_row,
                                               float* __restrict__ rgb_out, float* __restrict__ disp_out,
                                               float* __restrict__ acc_out) {
-    const int epl = (S + 31) / 32;
-    float al[kEPL], cr[kEPL], cg[kEPL], cb[kEPL];
+    constexpr int epl = kE;
+    float al[kE], cr[kE], cg[kE], cb[kE];
     double lp = 1.0;
 #pragma unroll
-    for (int e = 0; e < kEPL; ++e) {
+    for (int e = 0; e < kE; ++e) {
         const int i = lane * epl + e;
         al[e] = 0.f; cr[e] = cg[e] = cb[e] = 0.f;
-        if (e < epl && i < S) {
+        if (i < S) {
             const float4 raw = fetch(i);
             float d = (i + 1 < S) ? __fsub_rn(sm.z[i + 1], sm.z[i]) : 1e10f;
             d = __fmul_rn(d, norm_d);
@@ -71,9 +73,9 @@ __device__ __forceinline__ void composite_ray(RaySmem& sm, int S, int lane, floa
     double T = warp_excl_prod(lp, lane);
     float sr = 0.f, sg_ = 0.f, sb = 0.f, sd = 0.f, sw = 0.f;
 #pragma unroll
-    for (int e = 0; e < kEPL; ++e) {
+    for (int e = 0; e < kE; ++e) {
         const int i = lane * epl + e;
-        if (e < epl && i < S) {
+        if (i < S) {
             const float w = __fmul_rn(al[e], (float)T);
             T *= (double)__fadd_rn(__fsub_rn(1.f, al[e]), 1e-10f);
             sm.w[i] = w;
@@ -95,6 +97,7 @@ __device__ __forceinline__ void composite_ray(RaySmem& sm, int S, int lane, floa
 }
 
 // Coarse pass: composite + inverse-CDF importance sampling + merge order.
+template <int kE>
 __global__ void __launch_bounds__(32 * kWarpsPerBlock)
 composite_resample_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, int S, int S_f,
                           const float* __restrict__ raw /* (n_rays*S + n_rays, 4); tail = per-ray empty sample */,
@@ -117,16 +120,16 @@ composite_resample_kernel(const float* __restrict__ rays, int ray_stride, int n_
     const float4* raw4 = reinterpret_cast<const float4*>(raw);
     const float4 empty = raw4[(size_t)n_rays * S + n];
     auto fetch = [&](int i) { return mask[(size_t)n * S + i] ? raw4[(size_t)n * S + i] : empty; };
-    composite_ray(sm, S, lane, norm_d, inv_B, noise ? noise + (size_t)n * S : nullptr, fetch,
-                  weights + (size_t)n * S, alpha + (size_t)n * S, rgb0 + (size_t)n * 3, disp0 + n, acc0 + n);
+    composite_ray<kE>(sm, S, lane, norm_d, inv_B, noise ? noise + (size_t)n * S : nullptr, fetch,
+                      weights + (size_t)n * S, alpha + (size_t)n * S, rgb0 + (size_t)n * 3, disp0 + n, acc0 + n);
     if (S_f <= 0) return;
     // ---- R1: pdf over the S-2 interior bins, cdf with a leading zero (ray_utils.py:161-164,272-279)
     const int nb = S - 2;
-    const int epl = (nb + 31) / 32;
-    float dw[kEPL];
+    const int epl = (nb + 31) / 32;                     // <= kE
+    float dw[kE];
     double lsum = 0.0;
 #pragma unroll
-    for (int e = 0; e < kEPL; ++e) {
+    for (int e = 0; e < kE; ++e) {
         const int k = lane * epl + e;
         dw[e] = 0.f;
         if (e < epl && k < nb) {
@@ -145,14 +148,14 @@ composite_resample_kernel(const float* __restrict__ rays, int ray_stride, int n_
     const float total = (float)tot;
     double lpdf = 0.0;
 #pragma unroll
-    for (int e = 0; e < kEPL; ++e) {
+    for (int e = 0; e < kE; ++e) {
         const int k = lane * epl + e;
         if (e < epl && k < nb) { dw[e] = __fdiv_rn(dw[e], total); lpdf += (double)dw[e]; }
     }
     double run = warp_excl_sum(lpdf, lane);
     if (lane == 0) sm.cdf[0] = 0.f;
 #pragma unroll
-    for (int e = 0; e < kEPL; ++e) {
+    for (int e = 0; e < kE; ++e) {
         const int k = lane * epl + e;
         if (e < epl && k < nb) { run += (double)dw[e]; sm.cdf[k + 1] = (float)run; }
     }
@@ -223,6 +226,7 @@ composite_resample_kernel(const float* __restrict__ rays, int ray_stride, int n_
 }
 
 // Fine pass: gather coarse / fine raw by merge order, composite the S_t samples.
+template <int kE>
 __global__ void __launch_bounds__(32 * kWarpsPerBlock)
 merge_composite_kernel(const float* __restrict__ rays, int ray_stride, int n_rays, int S_c, int S_f,
                        const float* __restrict__ raw0 /* (n_rays*S_c + n_rays, 4) */, const uint32_t* __restrict__ mask0,
@@ -253,8 +257,8 @@ merge_composite_kernel(const float* __restrict__ rays, int ray_stride, int n_ray
         if (raw_merged) reinterpret_cast<float4*>(raw_merged)[(size_t)n * St + i] = v;
         return v;
     };
-    composite_ray(sm, St, lane, norm_d, inv_B, noise ? noise + (size_t)n * St : nullptr, fetch,
-                  weights + (size_t)n * St, alpha + (size_t)n * St, rgb + (size_t)n * 3, disp + n, acc + n);
+    composite_ray<kE>(sm, St, lane, norm_d, inv_B, noise ? noise + (size_t)n * St : nullptr, fetch,
+                      weights + (size_t)n * St, alpha + (size_t)n * St, rgb + (size_t)n * 3, disp + n, acc + n);
     if (confd_merged || invalid_merged) {                          // training outputs (raycasters.py:710-716)
         for (int e = lane; e < St * DANBO_J; e += 32) {
             const int i = e / DANBO_J, j = e - i * DANBO_J;
@@ -282,9 +286,17 @@ extern "C" int danbo_composite_resample(const float* rays, int ray_stride, int n
     if (S < 3 || S > kMaxS || S + S_f > kMaxS) return -1;
     if (S_f > 0 && !u_vals && !u_rand) return -2;
     const int G = (n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    composite_resample_kernel<<<G, 32 * kWarpsPerBlock, 0, (cudaStream_t)stream>>>(
-        rays, ray_stride, n_rays, S, S_f, raw, mask, z, noise, inv_B, u_vals, u_rand, weights, alpha, rgb0, disp0, acc0,
-        z_samples, z_all, order, inds, smooth_weights);
+#define DANBO_CR_LAUNCH(E) composite_resample_kernel<E><<<G, 32 * kWarpsPerBlock, 0, (cudaStream_t)stream>>>( \
+        rays, ray_stride, n_rays, S, S_f, raw, mask, z, noise, inv_B, u_vals, u_rand, weights, alpha, rgb0, disp0, acc0, \
+        z_samples, z_all, order, inds, smooth_weights)
+    switch ((S + 31) / 32) {                                 // samples per lane: the kernel is specialised on it
+        case 1: DANBO_CR_LAUNCH(1); break;
+        case 2: DANBO_CR_LAUNCH(2); break;
+        case 3: DANBO_CR_LAUNCH(3); break;
+        case 4: DANBO_CR_LAUNCH(4); break;
+        default: DANBO_CR_LAUNCH(5); break;
+    }
+#undef DANBO_CR_LAUNCH
     DANBO_CHECK_LAUNCH();
     return 0;
 }
@@ -298,9 +310,17 @@ extern "C" int danbo_merge_composite(const float* rays, int ray_stride, int n_ra
     if (n_rays <= 0) return 0;
     if (S_c + S_f > kMaxS) return -1;
     const int G = (n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    merge_composite_kernel<<<G, 32 * kWarpsPerBlock, 0, (cudaStream_t)stream>>>(
-        rays, ray_stride, n_rays, S_c, S_f, raw0, mask0, raw1, mask1, z_all, order, noise, inv_B, weights, alpha, rgb,
-        disp, acc, raw_merged, confd0, confd1, confd_merged, invalid_merged);
+#define DANBO_MC_LAUNCH(E) merge_composite_kernel<E><<<G, 32 * kWarpsPerBlock, 0, (cudaStream_t)stream>>>( \
+        rays, ray_stride, n_rays, S_c, S_f, raw0, mask0, raw1, mask1, z_all, order, noise, inv_B, weights, alpha, rgb, \
+        disp, acc, raw_merged, confd0, confd1, confd_merged, invalid_merged)
+    switch ((S_c + S_f + 31) / 32) {
+        case 1: DANBO_MC_LAUNCH(1); break;
+        case 2: DANBO_MC_LAUNCH(2); break;
+        case 3: DANBO_MC_LAUNCH(3); break;
+        case 4: DANBO_MC_LAUNCH(4); break;
+        default: DANBO_MC_LAUNCH(5); break;
+    }
+#undef DANBO_MC_LAUNCH
     DANBO_CHECK_LAUNCH();
     return 0;
 }
