@@ -147,10 +147,13 @@ class RayFeed:
         HW = self.H * self.W
         gather = lambda a, rows: a.reshape(-1, a.shape[-1])[rows[:, None] * HW + pix]
         fg = gather(self.masks, image_idxs).float()
-        img = gather(self.imgs, image_idxs).float() / 255.
+        # a TENSOR divisor: torch's CUDA kernels turn division by a Python scalar into a multiplication by its reciprocal,
+        # which is 1 ulp off the reference's true division for about half of the 256 byte values
+        s255 = torch.full((), 255., device=self.device)
+        img = gather(self.imgs, image_idxs).float() / s255
         bg = None
         if self.bkgds is not None:
-            bg = gather(self.bkgds, self.bkgd_idxs[image_idxs]).float() / 255.
+            bg = gather(self.bkgds, self.bkgd_idxs[image_idxs]).float() / s255
             if self.perturb_bg:
                 noise = torch.rand(bg.shape, device=self.device, generator=generator)
                 bg = (1 - fg) * noise + fg * bg

@@ -222,7 +222,7 @@ def field_agg(rays, S, z, mask, active, pose_skts, pose_vol, rays_per_pose, cons
         pairs_per_row = J if active.capacity <= WORST_CASE_PAIR_ROWS else 6
     if agg_mode == 1:
         pairs_per_row = J
-    o.pair_cap = int(pairs_per_row) * active.capacity + 24 * 32
+    o.pair_cap = int(pairs_per_row * active.capacity) + 24 * 32
     o.agg_mode = int(agg_mode)
     o.work = torch.empty(64 + o.pair_cap, device=dev, dtype=torch.int32)
     idx = dev.index if dev.index is not None else torch.cuda.current_device()

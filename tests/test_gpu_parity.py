@@ -421,3 +421,34 @@ def test_launch_block_split_invariance():
         raycaster.MAX_RAYS_PER_LAUNCH = old
     for k in ("rgb_map", "acc_map", "disp_map", "rgb0", "alpha", "T_i"):
         assert torch.equal(one[k], split[k]), k
+
+
+def test_pair_list_overflow_is_detected_not_silent():
+    """A lattice inside the torso, where several bone boxes overlap: with a pair workspace sized for fewer visible
+    (row, bone) pairs than there are, the call must raise its device flag and return NaN rows - never silently wrong
+    densities; the default sizing (worst case for small calls) and `render_pts_density` must be unaffected."""
+    from danbo_b200 import synthetic as syn
+    caster, args, P = make_caster("danbo_base")
+    pose = syn.make_pose(3)
+    t = lambda a: torch.as_tensor(a)[None].to(DEV)
+    kps, skts, bones = t(pose["kps"]), t(pose["skts"]), t(pose["bones"])
+    g = torch.linspace(-0.08, 0.08, 12)
+    pts = (torch.stack(torch.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3) + torch.as_tensor(pose["kps"][0])).to(DEV)
+    Pn = pts.shape[0]
+    rays = torch.zeros(Pn, 8, device=DEV)
+    rays[:, :3] = pts
+    consts = caster._consts()
+    vol = caster.network.bone_volumes(bones.float()).float().contiguous()
+    z = torch.zeros(Pn, 1, device=DEV)
+    _, mask, act = K().sample_mask(rays, 1, skts[0:1].float().contiguous(), Pn, consts, z_in=z, append_empty=2, capacity=Pn + 1)
+    n_pairs = int(sum(bin(int(m) & 0xFFFFFF).count("1") for m in mask.reshape(-1).tolist()))
+    assert n_pairs > Pn + 24 * 32, "the lattice should sit where boxes overlap"
+    ok = K().field_agg(rays, 1, z, mask, act, skts[0:1].float().contiguous(), vol, Pn, consts, want_hbar=True)
+    torch.cuda.synchronize()
+    assert not ok.overflowed() and torch.isfinite(ok.hbar[: int(act.count.item())]).all()
+    small = K().field_agg(rays, 1, z, mask, act, skts[0:1].float().contiguous(), vol, Pn, consts, want_hbar=True,
+                          pairs_per_row=0.5)
+    torch.cuda.synchronize()
+    assert small.overflowed() and torch.isnan(small.hbar[: int(act.count.item())]).all()
+    sig = caster.render_pts_density(pts.reshape(-1, 1, 3), kps, skts, bones)
+    assert torch.isfinite(sig).all()
