@@ -449,6 +449,6 @@ def test_pair_list_overflow_is_detected_not_silent():
     small = K().field_agg(rays, 1, z, mask, act, skts[0:1].float().contiguous(), vol, Pn, consts, want_hbar=True,
                           pairs_per_row=0.5)
     torch.cuda.synchronize()
-    assert small.overflowed() and torch.isnan(small.hbar[: int(act.count.item())]).all()
+    assert small.overflowed() and torch.isnan(small.hbar[: int(act.count.item()), :15]).all()      # column 15 is padding
     sig = caster.render_pts_density(pts.reshape(-1, 1, 3), kps, skts, bones)
     assert torch.isfinite(sig).all()
