@@ -17,6 +17,7 @@ _SIGNATURES = {
     "danbo_sample_mask": [c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p],
     "danbo_field_agg": [c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p],
     "danbo_agg_frag_bytes": [],
+    "danbo_pair_logits_set_blocks": [c_i],
     "danbo_pack_agg_frags": [c_p, c_p, c_p],
     "danbo_ray_bias": [c_p, c_i, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p],
     "danbo_mlp_workspace_bytes": [c_p, c_p, c_p],
@@ -78,6 +79,8 @@ def load():
         if got != ABI_VERSION:
             raise RuntimeError(f"{_PATH} has ABI version {got}, this binding expects {ABI_VERSION}: rebuild it with "
                                "`python __graft_entry__.py build`")
+        if os.environ.get("DANBO_PAIR_LOGITS_BLOCKS", ""):       # tuning aid: resident blocks per SM of the mma agg net
+            lib.danbo_pair_logits_set_blocks(int(os.environ["DANBO_PAIR_LOGITS_BLOCKS"]))
         if os.environ.get("DANBO_MLP_CTA_PAIR", "") == "0":      # debugging aid: single-CTA MLP kernel variant
             lib.danbo_mlp_set_cta_pair(0)
         _lib = lib

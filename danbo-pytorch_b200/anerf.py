@@ -107,8 +107,8 @@ class AnerfCaster(RayCaster):
         ent = cache.get(id(net))
         if ent is None or ent[1].wstream.device != self._device():
             ent = cache[id(net)] = [None, K.AnerfPacked(self._device())]
-        # same rule as RayCaster._packed_mlp: inside a graph capture / a train-mode forward the pack is unconditional
-        force = torch.cuda.is_current_stream_capturing() or (self.training and torch.is_grad_enabled())
+        # same rule as RayCaster._packed_mlp: in a train-mode forward with gradients the pack is unconditional
+        force = self.training and torch.is_grad_enabled()
         if force or ent[0] != key:
             ent[1].pack({n: P[n] for n in names})
             ent[0] = key

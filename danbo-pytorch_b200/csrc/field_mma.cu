@@ -76,8 +76,11 @@ __global__ void pack_frags_kernel(const float* __restrict__ w0 /* (24,15,32) */,
     dst[1] = hl ? pack_bf16(l[2], l[3]) : pack_bf16(h[2], h[3]);
 }
 
-template <bool kOnePose>
-__global__ void __launch_bounds__(128, 3)
+// kBlocks = resident blocks per SM the register allocation is bounded for: the kernel is latency bound (dependent chain
+// feature taps -> MMA -> mix -> MMA per 32-pair chunk; ncu at 12 warps/SM: tensor pipe 24 %, long-scoreboard stalls), so
+// occupancy is what hides it.  3 -> 137 registers, 4 -> 128 (no spill), 5 -> 96 (20 bytes of spill).
+template <bool kOnePose, int kBlocks>
+__global__ void __launch_bounds__(128, kBlocks)
 pair_logits_mma_kernel(const float* __restrict__ rays, int ray_stride, int S, const float* __restrict__ z,
                        const int* __restrict__ active_ids, const float* __restrict__ pose_skts,
                        const float* __restrict__ pose_vol, int rays_per_pose, int n_poses, FieldConsts fc, PairWork pw,
@@ -240,21 +243,28 @@ pair_logits_mma_kernel(const float* __restrict__ rays, int ray_stride, int S, co
 
 }  // namespace aggmma
 
+static int g_pair_logits_blocks = 4;     // resident blocks per SM of pair_logits_mma_kernel (3, 4 or 5)
+
+int set_pair_logits_blocks(int b) {
+    const int old = g_pair_logits_blocks;
+    if (b >= 3 && b <= 5) g_pair_logits_blocks = b;
+    return old;
+}
+
 int launch_pair_logits_mma(const float* rays, int ray_stride, int S, const float* z, const int* active_ids,
                            const float* pose_skts, const float* pose_vol, int rays_per_pose, int n_poses,
                            const FieldConsts& fc, PairWork pw, int pair_capacity, const void* frags, float* logits,
                            int num_sms, cudaStream_t st) {
+    const int occ = g_pair_logits_blocks;
     int pblocks = (pair_capacity / 32 + 3) / 4;
-    if (pblocks > num_sms * 6) pblocks = num_sms * 6;
+    if (pblocks > num_sms * occ) pblocks = num_sms * occ;             // one resident wave, grid-stride over the chunks
     if (pblocks < 1) pblocks = 1;
-    if (n_poses == 1)
-        aggmma::pair_logits_mma_kernel<true><<<pblocks, 128, 0, st>>>(rays, ray_stride, S, z, active_ids, pose_skts, pose_vol,
-                                                                        rays_per_pose, n_poses, fc, pw, pair_capacity,
-                                                                        (const uint32_t*)frags, logits);
-    else
-        aggmma::pair_logits_mma_kernel<false><<<pblocks, 128, 0, st>>>(rays, ray_stride, S, z, active_ids, pose_skts, pose_vol,
-                                                                         rays_per_pose, n_poses, fc, pw, pair_capacity,
-                                                                         (const uint32_t*)frags, logits);
+#define DANBO_PLM_LAUNCH(ONE, OCC) aggmma::pair_logits_mma_kernel<ONE, OCC><<<pblocks, 128, 0, st>>>( \
+        rays, ray_stride, S, z, active_ids, pose_skts, pose_vol, rays_per_pose, n_poses, fc, pw, pair_capacity, \
+        (const uint32_t*)frags, logits)
+    if (n_poses == 1) { if (occ == 3) DANBO_PLM_LAUNCH(true, 3); else if (occ == 4) DANBO_PLM_LAUNCH(true, 4); else DANBO_PLM_LAUNCH(true, 5); }
+    else { if (occ == 3) DANBO_PLM_LAUNCH(false, 3); else if (occ == 4) DANBO_PLM_LAUNCH(false, 4); else DANBO_PLM_LAUNCH(false, 5); }
+#undef DANBO_PLM_LAUNCH
     DANBO_CHECK_LAUNCH();
     return 0;
 }
@@ -263,6 +273,9 @@ int launch_pair_logits_mma(const float* rays, int ray_stride, int S, const float
 
 // Packs prob_linears' layer-0 / layer-1 weights (consts[2] = (24,15,32), consts[6] = (24,32,32), fp32) into split-bf16
 // MMA B fragments: `frags` = danbo_agg_frag_bytes() bytes of device memory.  Re-run after every weight update.
+// Resident blocks per SM (3, 4 or 5) the tensor-core aggregation-net kernel is compiled / launched for -> previous value.
+extern "C" int danbo_pair_logits_set_blocks(int blocks) { return danbo::set_pair_logits_blocks(blocks); }
+
 extern "C" int danbo_agg_frag_bytes(void) {
     return (danbo::aggmma::kW0Words + danbo::aggmma::kW1Words) * 4;
 }

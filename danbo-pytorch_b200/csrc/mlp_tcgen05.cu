@@ -546,14 +546,28 @@ empty_trunk_kernel(PackArgs a, float* __restrict__ out /* c[128], sigma0, 3 unus
         buf0[i] = v; buf1[i] = v;                            // both buffers start with x: layer 5 reads [x ; h4]
     }
     __syncthreads();
+    // a warp owns up to 8 consecutive output rows and walks all of them together: 8 independent row loads per step keep
+    // the single SM's memory pipeline full (one row at a time was a chain of exposed L2 latencies: 140 us for the trunk)
     auto layer = [&](const float* in, int n_in, const float* W, int ld, const float* bias, float* dst, int n_out, bool relu) {
-        for (int o = warp; o < n_out; o += 32) {
-            const float* row = W + (size_t)o * ld;
-            float s = 0.f;
-            for (int k = lane; k < n_in; k += 32) s = fmaf(__ldg(row + k), in[k], s);
+        const int per = (n_out + 31) / 32;                  // rows per warp (<= 8)
+        const int o0 = warp * per;
+        float s[8];
 #pragma unroll
-            for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
-            if (lane == 0) { s += bias ? __ldg(bias + o) : 0.f; dst[o] = relu ? fmaxf(s, 0.f) : s; }
+        for (int r = 0; r < 8; ++r) s[r] = 0.f;
+        for (int k = lane; k < n_in; k += 32) {
+            const float x = in[k];
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                if (r < per && o0 + r < n_out) s[r] = fmaf(__ldg(W + (size_t)(o0 + r) * ld + k), x, s[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int m = 16; m > 0; m >>= 1) s[r] += __shfl_xor_sync(0xffffffffu, s[r], m);
+            if (lane == 0 && r < per && o0 + r < n_out) {
+                const float v = s[r] + (bias ? __ldg(bias + o0 + r) : 0.f);
+                dst[o0 + r] = relu ? fmaxf(v, 0.f) : v;
+            }
         }
         __syncthreads();
     };

@@ -98,6 +98,7 @@ class RayCaster(nn.Module):
         # graph net and the aggregation net all read them live, so value changes are always seen); the pointers are part
         # of the graph key, so re-pointed storage (`.to()`, an optimizer's flat arena) gets a fresh capture.
         ptrs = hash(tuple(p.data_ptr() for p in self.parameters()))
+        self._packed_mlp()                    # eager: repacks (into the buffers the graph reads) iff the weights changed
         return self._graphed(rays=rays, pose_skts=pose_skts, pose_bones=pose_bones, pose_cyls=pose_cyls, cam_idx=cam_idx,
                              skip=skip, N_samples=N_samples, N_importance=N_importance, B=B, nanmean_chunk=nanmean_chunk,
                              lindisp=bool(lindisp), _param_ptrs=ptrs)
@@ -150,11 +151,14 @@ class RayCaster(nn.Module):
         if self._packed is None or self._packed.wstream.device != self._device():
             self._packed = K.PackedMLP(self._device())
             self._packed_key = None
-        # The host-side key cannot see an update made by a kernel through raw pointers (the single-launch Adam), and a
-        # replayed CUDA graph never runs this Python at all.  So the pack is unconditional (a) while a graph is being
-        # captured - the pack launch then belongs to the graph and every replay reads the live parameters - and (b) in
-        # every train-mode forward (one 5 us launch per iteration).  Only eager eval calls rely on the key.
-        force = torch.cuda.is_current_stream_capturing() or (self.training and torch.is_grad_enabled())
+        # The host-side key cannot see an update made by a kernel through raw pointers, and a replayed CUDA graph never
+        # runs this Python at all.  So the pack is unconditional in every train-mode forward with gradients - eager or
+        # being captured: the pack launches then belong to the training graph and every replay packs the weights the
+        # previous replay's Adam wrote.  Eval calls rely on the key: it changes with every torch in-place op
+        # (`_version`), `load_state_dict`, `TrainStep` (which invalidates it after every iteration) and `FlatAdam.step`
+        # (which bumps the parameters' versions); `render_graphed` checks it EAGERLY before each replay and repacks into
+        # the same static buffers, so an eval graph holds no pack launch and still never sees stale weights.
+        force = self.training and torch.is_grad_enabled()
         if force or key != self._packed_key:
             tensors = {n: P[n] for n in names}
             if not getattr(net, "opt_framecode", True):

@@ -180,6 +180,11 @@ class FlatAdam(torch.optim.Optimizer):
                                                float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
                                                K._p(self.step_dev), K.num_sms(idx), K._stream()), "danbo_adam_step")
         K._count(1)
+        if not torch.cuda.is_current_stream_capturing():
+            # the kernel wrote through raw pointers: bump the tensors' versions so that version-keyed caches (the packed
+            # bf16 weights of an eval caster) see the update; a captured replay is covered by TrainStep._after_step
+            for p in self.bucket.params:
+                torch.autograd.graph.increment_version(p)
 
 
 class TrainStep:

@@ -39,6 +39,10 @@ int danbo_nearfar(const float* rays, int ray_stride, int n_rays, const float* po
  * published number was measured with); a table filled by danbo_pack_agg_frags selects the split-bf16 mma.sync kernel
  * (csrc/field_mma.cu; logits within 3e-6 of scale; NOT yet run on hardware). */
 
+/* Tuning knob of the tensor-core aggregation net (pair_logits_mma_kernel): resident blocks per SM its register
+ * allocation is bounded for (3: 137 registers, 4: 128, 5: 96 with 20 bytes of spill).  Returns the previous value. */
+int danbo_pair_logits_set_blocks(int blocks);
+
 /* Bytes of the fragment table, and the packing of prob_linears' layer-0 / layer-1 weights (consts[2], consts[6]) into
  * split-bf16 m16n8k16 B fragments for the tensor-core aggregation net (MixGNN, gnn_backbone.py:225-274,567-629).
  * Re-run after every update of those weights. */
