@@ -109,6 +109,24 @@ __global__ void nearfar_finish_kernel(const float* __restrict__ rays, int ray_st
             int n_in = 0;
             uint32_t bits = 0;
             float seg[2][3];
+            // fp32 slab test of the whole LINE against the box grown by a margin far above fp32 rounding: if even that
+            // misses, none of the six plane points below can lie inside the box (n_in = 0, the bone is not valid), so the
+            // fp64 plane intersections are skipped - a ray of the 512x512 image comes near 3-5 of the 24 boxes.
+            bool may_hit = true;
+            {
+                const float H = hi * 1.002f + 2e-3f;
+                float lo_t = -3.0e38f, hi_t = 3.0e38f;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    if (fabsf(ds[i]) < 1e-12f) { may_hit = may_hit && !(fabsf(os[i]) > H); continue; }
+                    const float inv = 1.f / ds[i];
+                    const float ta = (-H - os[i]) * inv, tb = (H - os[i]) * inv;
+                    lo_t = fmaxf(lo_t, fminf(ta, tb)); hi_t = fminf(hi_t, fmaxf(ta, tb));
+                }
+                // widen the interval test itself: t values are O(1..10), their fp32 error O(1e-6)
+                may_hit = may_hit && !(lo_t > hi_t + 1e-3f * (1.f + fabsf(lo_t) + fabsf(hi_t)));
+            }
+            if (may_hit)
 #pragma unroll
             for (int k = 0; k < 6; ++k) {               // planes: -b on x,y,z then +b on x,y,z
                 const int a = k % 3;
