@@ -342,3 +342,29 @@ def test_create_raycaster_for_the_other_shipped_configs(tmp_path):
                        bones=torch.zeros(4, 24, 3), cams=None, N_importance=4)
     perf = db.make_args("danbo_fast", no_reload=True, view_type="relray", ray_tr_type="root_local", nerf_type="graph")
     assert db.create_raycaster(perf, _attrs(), device="cpu")[1]["ray_caster"].view_mode == "root_local"
+
+
+def test_dropin_hook_rebinds_create_raycaster_only():
+    """`danbo_b200.install()` (dropin.py): the reference's `create_raycaster` name - in core.raycasters and in the modules
+    that copied it (run_nerf) - points at this repo's factory, nothing else changes, and `uninstall()` restores it.  Needs
+    the reference (`/root/reference` or the vendored baseline/_ref)."""
+    import ref_harness as rh                 # tests/conftest.py puts oracle/ on sys.path
+    if not rh.available():
+        pytest.skip("no reference copy")
+    import danbo_b200 as db
+    rc, run_nerf = rh._imports()
+    orig = rc.create_raycaster
+    names_before = {k: id(v) for k, v in vars(rc).items() if not k.startswith("__")}
+    db.install()
+    try:
+        assert getattr(rc.create_raycaster, "__danbo_b200__", False)
+        assert run_nerf.create_raycaster is rc.create_raycaster
+        changed = [k for k, v in vars(rc).items() if not k.startswith("__") and names_before.get(k) != id(v)]
+        assert changed == ["create_raycaster"], changed
+        # flags outside the supported subset raise through the hook as well (no fallback to the reference's caster)
+        args = rh.parse_args("h36m_zju/danbo_fast.txt", ["--agg_type", "relu"])
+        with pytest.raises(NotImplementedError):
+            rc.create_raycaster(args, {"rest_pose": None, "n_views": 8})
+    finally:
+        db.uninstall()
+    assert rc.create_raycaster is orig and run_nerf.create_raycaster is orig
