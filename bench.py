@@ -270,10 +270,13 @@ def run_ours(opt):
                 main.wait_event(down_done[b])                # pix_stage[b] has been read out
             ret = caster.render_graphed(rays_stage[b], **kw_stage[b])
             pix = parallel.pack_pixels(ret)
-            if world > 1:
-                parallel.allgather_rows(pix, shard_sizes)
             pix_stage[b].copy_(pix)
             used[b].record(main)
+            if world > 1:                                    # the exchange of step i overlaps step i+1, as in the device loop
+                with torch.cuda.stream(comm):
+                    comm.wait_event(used[b])
+                    gathered[b] = parallel.allgather_rows(pix, shard_sizes)
+                pix.record_stream(comm)
             if i + 1 < k:
                 upload(i + 1)
             with torch.cuda.stream(copy):
@@ -282,6 +285,7 @@ def run_ours(opt):
                 down_done[b].record(copy)
             flush.fill_(i)
         main.wait_stream(copy)
+        drain()
 
     run_pipelined(3)
     barrier()
