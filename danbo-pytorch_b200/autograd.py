@@ -75,6 +75,8 @@ class _RenderBlock(torch.autograd.Function):
         K.merge_composite_bwd(rays, S_c, S_f, k["raw0"], k["mask0"], k["raw1"], k["mask1"], k["z_all"], k["order"],
                               k["noise1"], k["inv_B"], g_rgb, g_acc, g_confd, d_raw0, d_raw1, gl0, gl1)
         K.composite_bwd(rays, S_c, k["raw0"], k["mask0"], k["z0"], k["noise0"], k["inv_B"], g_rgb0, g_acc0, d_raw0)
+        if getattr(ctx.caster, "_debug_bwd", None) is not None:     # diagnostics (scripts/mlp_bwd_e2e_check.py): what the MLP
+            ctx.caster._debug_bwd.update(d_raw0=d_raw0.clone(), d_raw1=d_raw1.clone(), keep=dict(k))   # backward was fed
         # MLP + field, per pass
         d_ray_bias = zeros(n, 128)
         d_vol = zeros(*ctx.vol_shape)
