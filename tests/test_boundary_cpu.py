@@ -368,3 +368,26 @@ def test_dropin_hook_rebinds_create_raycaster_only():
     finally:
         db.uninstall()
     assert rc.create_raycaster is orig and run_nerf.create_raycaster is orig
+
+
+def test_run_launcher_executes_a_reference_script_with_the_hook_installed(tmp_path):
+    """`python -m danbo_b200.run <script> [args]`: the script runs as __main__ from the reference's root with
+    `create_raycaster` already rebound and its own argv.  A stand-in script is placed beside the reference's `core/`."""
+    import shutil
+    import subprocess
+    import sys
+    import ref_harness as rh
+    if not rh.available():
+        pytest.skip("no reference copy")
+    root = tmp_path / "ref"
+    shutil.copytree(os.path.join(rh.REF, "core"), root / "core")
+    (root / "probe_script.py").write_text(
+        "import sys, os\n"
+        "from core.raycasters import create_raycaster\n"
+        "print('HOOKED', getattr(create_raycaster, '__danbo_b200__', False), sys.argv[1:], os.path.basename(os.getcwd()), __name__)\n")
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([repo, os.path.join(repo, "oracle", "ref_stubs")]))
+    out = subprocess.run([sys.executable, "-m", "danbo_b200.run", str(root / "probe_script.py"), "--config", "x.txt"],
+                         capture_output=True, text=True, timeout=300, env=env, cwd=str(tmp_path))
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "HOOKED True ['--config', 'x.txt'] ref __main__" in out.stdout, out.stdout[-500:]
