@@ -21,6 +21,7 @@ _SIGNATURES = {
     "danbo_pack_agg_frags": [c_p, c_p, c_p],
     "danbo_ray_bias": [c_p, c_i, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p],
     "danbo_mlp_workspace_bytes": [c_p, c_p, c_p],
+    "danbo_mlp_set_pack_empty": [c_i],
     "danbo_mlp_empty_rows": [c_p, c_i, c_p, c_p, c_i, c_p],
     "danbo_mlp_set_cta_pair": [c_i],
     "danbo_graph_net_fwd": [c_p, c_i, c_p, c_p, c_p, c_p],

@@ -636,6 +636,16 @@ extern "C" int danbo_mlp_workspace_bytes(long long* wstream_bytes, long long* he
     return 0;
 }
 
+static int g_pack_empty = 1;      // 1: danbo_pack_mlp_weights also computes the empty-sample constants (one-block trunk, ~80 us)
+
+// Training packs the weights every iteration and never reads the empty-sample constants (its per-ray empty rows go
+// through the MLP so that their gradient does): the caller switches the constants off for those packs.  -> previous.
+extern "C" int danbo_mlp_set_pack_empty(int enable) {
+    const int old = g_pack_empty;
+    g_pack_empty = enable ? 1 : 0;
+    return old;
+}
+
 extern "C" int danbo_pack_mlp_weights(const float* const* w_pts, const float* const* b_pts, const float* w_alpha,
                                       const float* b_alpha, const float* w_feat, const float* b_feat,
                                       const float* w_view, const float* b_view, const float* w_rgb,
@@ -646,8 +656,10 @@ extern "C" int danbo_pack_mlp_weights(const float* const* w_pts, const float* co
     a.w_view = w_view; a.b_view = b_view; a.w_rgb = w_rgb; a.b_rgb = b_rgb;
     mlp::pack_weights_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(a, (__nv_bfloat16*)wstream, heads, wv_ray);
     DANBO_CHECK_LAUNCH();
-    mlp::empty_trunk_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(a, heads + mlp::kEmptyOff);
-    DANBO_CHECK_LAUNCH();
+    if (g_pack_empty) {
+        mlp::empty_trunk_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(a, heads + mlp::kEmptyOff);
+        DANBO_CHECK_LAUNCH();
+    }
     return 0;
 }
 

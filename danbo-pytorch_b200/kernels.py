@@ -247,10 +247,14 @@ class PackedMLP:
         self.heads = torch.empty(b.value // 4, device=device, dtype=torch.float32)
         self.wv_ray = torch.empty(c.value // 4, device=device, dtype=torch.float32)
         self.key = None
+        self.has_empty = False
 
-    def pack(self, P):
-        """P: mapping with the reference's names (pts_linears.i.weight ...) -> fp32 CUDA tensors."""
+    def pack(self, P, want_empty=True):
+        """P: mapping with the reference's names (pts_linears.i.weight ...) -> fp32 CUDA tensors.  want_empty: also compute
+        the empty-sample constants (`mlp_empty_rows` reads them; a training pack does not need them)."""
         lib = _lib.load()
+        lib.danbo_mlp_set_pack_empty(int(bool(want_empty)))
+        self.has_empty = bool(want_empty)
         ws = [f32c(P[f"pts_linears.{i}.weight"]) for i in range(8)]
         bs = [f32c(P[f"pts_linears.{i}.bias"]) for i in range(8)]
         others = [f32c(P[k]) for k in ("alpha_linear.weight", "alpha_linear.bias", "feature_linear.weight",
@@ -262,7 +266,7 @@ class PackedMLP:
         _lib.check(lib.danbo_pack_mlp_weights(wa, ba, *[_p(t) for t in others], _p(self.wstream), _p(self.heads),
                                               _p(self.wv_ray), _stream()), "danbo_pack_mlp_weights")
         self._keep = (ws, bs, others)          # keep sources alive until the stream has consumed them
-        _count(2)
+        _count(2 if want_empty else 1)
         return self
 
 
@@ -287,6 +291,8 @@ def mlp_empty_rows(rbias, packed, raw_tail):
     _need_cuda(rbias, raw_tail)
     n = rbias.shape[0]
     assert raw_tail.shape[0] == n and raw_tail.is_contiguous() and raw_tail.dtype == torch.float32
+    if not packed.has_empty:
+        raise RuntimeError("the packed weights carry no empty-sample constants (packed by a training forward): repack")
     dev = rbias.device
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
     with _Timed("ray_bias"):

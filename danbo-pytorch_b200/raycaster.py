@@ -159,13 +159,14 @@ class RayCaster(nn.Module):
         # (which bumps the parameters' versions); `render_graphed` checks it EAGERLY before each replay and repacks into
         # the same static buffers, so an eval graph holds no pack launch and still never sees stale weights.
         force = self.training and torch.is_grad_enabled()
-        if force or key != self._packed_key:
+        # a forced (training) pack skips the empty-sample constants, which only calls without a backward pass read
+        if force or key != self._packed_key or not self._packed.has_empty:
             tensors = {n: P[n] for n in names}
             if not getattr(net, "opt_framecode", True):
                 # no frame code: the kernels' view layer keeps its 411-input layout with zero weights (and zero codes,
                 # `_codes_with_mean`) in the code columns, which adds exact zeros
                 tensors["views_linears.0.weight"] = F.pad(P["views_linears.0.weight"].detach(), (0, 128))
-            self._packed.pack(tensors)
+            self._packed.pack(tensors, want_empty=not force)
             self._packed_key = key
         return self._packed
 

@@ -83,6 +83,11 @@ int danbo_field_agg(const float* rays, int ray_stride, int n_rays, int S, const 
                     int* row_ray, float* logits, float* hbar_out, void* x_rows, int* work, int pair_capacity,
                     int num_sms, int agg_mode, void* stream);
 
+/* Whether danbo_pack_mlp_weights also computes the empty-sample constants behind the heads (default 1).  A training
+ * iteration repacks every step and never reads them (danbo_mlp_empty_rows is an eval-path call): switch them off for
+ * those packs.  Returns the previous setting. */
+int danbo_mlp_set_pack_empty(int enable);
+
 /* Output of the field for a sample NO bone sees (blended feature 0 -> MLP input PE(0), danbo.py:299-302 + nerf.py:176-209):
  * the density trunk and the feature part of the view layer are constants of the weights (danbo_pack_mlp_weights leaves
  * them behind the heads), so per ray only rgb = W_rgb . relu(c + ray_bias) + b_rgb remains.  raw_tail (n_rays,4) =
