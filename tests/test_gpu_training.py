@@ -93,7 +93,10 @@ def test_training_step_gradients(name):
     # rel <= 0.16 (192 rays) and cos >= 0.978 / rel <= 0.22 (64 rays): heads and late layers agree to 0.5 - 2 %, the error
     # grows towards the input (8 bf16 layers deep) and is largest for the graph net, which sees the MLP only through d X.
     # SURVEY §8(d)'s cos >= 0.999 / rel <= 2e-2 is NOT met end to end with bf16 tensor-core operands; it is met per stage
-    # (test_composite_backward, test_field_backward, test_mlp_backward) - see DESIGN.md §2.
+    # (test_composite_backward, test_field_backward, test_mlp_backward).  The end-to-end size is the problem's conditioning:
+    # a 1e-3 relative perturbation of the MLP input alone moves these gradients by 2 - 19 % (scripts/grad_conditioning.py,
+    # profiles/r2_grad_conditioning.txt), and the kernels are exact to rounding on their own inputs
+    # (profiles/r2_mlp_bwd_e2e_check.txt) - see DESIGN.md §2.
     cos_min, rel_max = {"train_fast": (0.985, 0.2), "train_fast_softmax": (0.965, 0.3), "train_fast_nonoise": (0.985, 0.2),
                         "train_cfg3_nonoise": (0.97, 0.3)}.get(name, (0.85, 0.8))
     bad = [(k, c, r) for k, sig, c, r in results["fp32"] if (sig and c < cos_min) or r > rel_max]
