@@ -276,7 +276,9 @@ def test_render_rays_end_to_end(name):
     want_empty = fx["st.raw.0"][~act]
     if want_empty.numel():
         e = _report(name + " raw0 (empty samples)", empty[:, None].expand(-1, args.N_samples, -1)[~act], want_empty)
-        assert float(e.max()) <= 3e-2 * float(fx["st.raw.0"].abs().max())
+        # eval calls take these rows from the fp32 constants of the weight pack, not from the bf16 MLP: fp32-level
+        # agreement with the reference (measured 1.05e-5 absolute at a raw scale of 40)
+        assert float(e.max()) <= 1e-5 * float(fx["st.raw.0"].abs().max())
     for k in ("rgb0", "acc0"):                # coarse pass: identical sample positions -> the bf16 MLP error alone
         e = _report(f"{name} {k}", out[k], fx["out." + k])
         assert float(e.mean()) <= 1e-3 and float(e.max()) <= 1.5e-2, (k, float(e.mean()), float(e.max()))
