@@ -391,3 +391,42 @@ def test_run_launcher_executes_a_reference_script_with_the_hook_installed(tmp_pa
                          capture_output=True, text=True, timeout=300, env=env, cwd=str(tmp_path))
     assert out.returncode == 0, out.stderr[-2000:]
     assert "HOOKED True ['--config', 'x.txt'] ref __main__" in out.stdout, out.stdout[-500:]
+
+
+def test_check_args_is_fail_closed_on_missing_flags():
+    """A namespace that does not carry a flag is checked against the REFERENCE CLI's default for it (config.DEFAULTS =
+    run_nerf.py:186-572), never against "whatever is supported": an empty namespace therefore selects the reference's
+    default model (nerf_type = 'nerf', PoolPNGCN, ...), which the DANBO path must refuse."""
+    import argparse
+    from danbo_b200 import raycaster
+    with pytest.raises(NotImplementedError):
+        raycaster.check_args(argparse.Namespace())
+    full = db.make_args("danbo_fast")
+    raycaster.check_args(full)
+    partial = argparse.Namespace(**{k: v for k, v in vars(full).items() if k not in ("agg_backbone", "voxel_res")})
+    with pytest.raises(NotImplementedError):                    # reference defaults: agg_backbone='mlp', voxel_res=4
+        raycaster.check_args(partial)
+
+
+def test_train_step_refuses_trainer_flags_it_does_not_implement():
+    """core/trainer.py honours opt_pose_step / opt_pose_stop / weight_decay / reg_fn / use_lpips_loss; TrainStep raises
+    for any of them instead of silently training something else (checked before any device work)."""
+    from danbo_b200 import training
+    for flag, val in (("opt_pose_step", 4), ("opt_pose_stop", 1000), ("weight_decay", 0.01), ("reg_fn", "L1"),
+                      ("use_lpips_loss", True)):
+        args = db.make_args("danbo_fast", **{flag: val})
+        with pytest.raises(NotImplementedError, match=flag):
+            training.TrainStep(object(), args)
+
+
+def test_both_bench_arms_quote_the_same_config():
+    """The driver compares the `config` dict of `bench.py` and `bench.py --impl reference`: one function builds both."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    args = db.make_args(bench.PRESET)
+    a, b = bench.workload_config(args, 261121), bench.workload_config(args)
+    assert a == b and a["rays_per_image"] == 261121 and a["samples_per_ray"] == 48 and a["chunk"] == 4096
+    src = open(bench.__file__).read()
+    assert src.count('"config": workload_config(args') == 2            # both JSON lines
