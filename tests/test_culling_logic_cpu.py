@@ -105,3 +105,37 @@ def test_nearfar_prefilter_never_skips_a_box_with_a_plane_hit():
     assert any_hit.sum() > 100_000 and (~any_hit).sum() > 100_000
     assert not (any_hit & ~may).any(), int((any_hit & ~may).sum())
     assert (may & ~any_hit).sum() < 0.05 * (~any_hit).sum()
+
+
+def test_empty_sample_constants_identity():
+    """The identity behind `empty_trunk_kernel` / `empty_rows_kernel` (csrc/mlp_tcgen05.cu): for a sample no bone sees the
+    blended feature is 0, the MLP input is PE(0), and the field's output is
+        sigma0 = alpha(trunk(PE(0))),   rgb = W_rgb relu(c + ray_bias) + b_rgb,   c = W_v[:, :256] feat(trunk(PE(0))),
+    with ray_bias = W_v[:, 256:] [PE(d) ; code] + b_v the only per-ray quantity.  Checked against the oracle's `field_mlp`
+    (core/networks/nerf.py:176-209) on random view inputs."""
+    import sys, os
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import danbo_oracle as orc
+    from danbo_b200 import synthetic as syn
+    P = syn.synthetic_params(0)
+    torch.manual_seed(0)
+    n = 64
+    view = torch.randn(n, 155) * 0.5
+    x0 = orc.pe_embed(torch.zeros(1, 15), 6)                                  # PE(0): zeros, then (sin 0, cos 0) per octave
+    assert x0.shape == (1, 195) and float(x0.sum()) == 6 * 15
+    ones_at = [30 + 30 * f + i for f in range(6) for i in range(15)]          # the kernel's own index rule
+    assert torch.equal(torch.nonzero(x0[0])[:, 0], torch.tensor(ones_at))
+    want = orc.field_mlp(x0.expand(n, -1), view, P)
+    h = orc.density_trunk(x0, P)
+    sigma0 = h @ P["alpha_linear.weight"].t() + P["alpha_linear.bias"]
+    feat = h @ P["feature_linear.weight"].t() + P["feature_linear.bias"]
+    Wv = P["views_linears.0.weight"]
+    c = feat @ Wv[:, :256].t()
+    ray_bias = view @ Wv[:, 256:].t() + P["views_linears.0.bias"]
+    rgb = torch.relu(c + ray_bias) @ P["rgb_linear.weight"].t() + P["rgb_linear.bias"]
+    got = torch.cat([rgb, sigma0.expand(n, 1)], -1)
+    assert float((got - want).abs().max()) <= 2e-5 * float(want.abs().max())
